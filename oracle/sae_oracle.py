@@ -1,0 +1,317 @@
+"""CPU oracle for the saev SAE training step.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in plain dense fp32 PyTorch-CPU tensor ops with *explicit* gradient
+formulas (no autograd), the arithmetic of one step of the reference training loop
+
+    /root/reference/src/saev/framework/train.py:332-460
+    /root/reference/src/saev/nn/objectives.py:101-156, 224-237
+    /root/reference/src/saev/nn/modeling.py:25-103, 150-179, 343-445
+    /root/reference/src/saev/utils/scheduling.py:43-71
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs may import it; the product package `saev_b200` never does (it has no CPU path at all).
+
+Parity status: PINNED.  `oracle/gen_golden.py` runs the *live* reference (imported from
+/root/reference/src in the build container) on fixed seeds and writes `tests/golden/*.npz`;
+`tests/test_oracle_golden.py` checks every function here against those vectors and against the
+hand-computed known answers the reference's own tests hold (tests/test_auxk.py,
+tests/test_nn_activations.py, tests/test_nn_objectives.py, tests/test_nn_modeling.py).
+
+All tensors are fp32, row-major.  Shapes: x[B,D]  W_enc[D,S]  b_enc[S]  W_dec[S,D]  b_dec[D].
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import torch
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# configuration (mirrors modeling.py:109-146, 259-284; objectives.py:13-25; train.py:50-78)
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class OracleConfig:
+    d_model: int
+    d_sae: int
+    activation: str = "topk"  # "topk" | "relu"            modeling.py:111-126
+    top_k: int = 32  # modeling.py:123
+    l1_coeff: float = 0.0  # L1Sparsity.coeff (0 => NoSparsity)  modeling.py:25-42
+    aux: bool = True  # AuxK vs NoAux                  modeling.py:50-103
+    k_aux: int = 512  # modeling.py:72
+    aux_alpha: float = 1.0 / 32  # modeling.py:73
+    dead_threshold_tokens: int = 10_000_000  # objectives.py:24
+    normalize_w_dec: bool = True  # modeling.py:283
+    remove_parallel_grads: bool = True  # modeling.py:281
+    lr: float = 4e-4  # train.py:73
+    n_lr_warmup: int = 500  # train.py:75
+    n_steps: int = 1000  # len(BatchLimiter)  scheduling.py:94-95
+    grad_clip: float = 1.0  # train.py:77
+    beta1: float = 0.9  # torch.optim.Adam defaults, train.py:294
+    beta2: float = 0.999
+    eps: float = 1e-8
+
+
+@dataclasses.dataclass
+class OracleState:
+    W_enc: Tensor
+    b_enc: Tensor
+    W_dec: Tensor
+    b_dec: Tensor
+    m: dict
+    v: dict
+    t: int = 0  # Adam step count
+    lr: float = 0.0  # param_group lr; 0.0 before the first step (train.py:118)
+    sched_step: int = 0  # WarmupCosine._step
+    toks_since_active: Tensor | None = None  # objectives.py:99,108-111 (lazily created)
+
+    @staticmethod
+    def from_params(W_enc, b_enc, W_dec, b_dec) -> "OracleState":
+        ps = dict(W_enc=W_enc.clone(), b_enc=b_enc.clone(), W_dec=W_dec.clone(), b_dec=b_dec.clone())
+        return OracleState(
+            **ps,
+            m={k: torch.zeros_like(p) for k, p in ps.items()},
+            v={k: torch.zeros_like(p) for k, p in ps.items()},
+        )
+
+    def params(self) -> dict:
+        return dict(W_enc=self.W_enc, b_enc=self.b_enc, W_dec=self.W_dec, b_dec=self.b_dec)
+
+
+def init_params(d_model: int, d_sae: int, generator: torch.Generator | None = None):
+    """modeling.py:306-329: W_dec = kaiming_uniform_([S,D]) row-normalised; W_enc = W_dec.T.clone();
+    biases zero.  kaiming_uniform_ with a=0 on a [S,D] tensor: fan_in = D, bound = sqrt(6/D)."""
+    bound = math.sqrt(6.0 / d_model)
+    W_dec = (torch.rand(d_sae, d_model, generator=generator) * 2 - 1) * bound
+    W_dec = W_dec / torch.norm(W_dec, dim=1, keepdim=True)
+    W_enc = W_dec.T.clone()
+    return W_enc, torch.zeros(d_sae), W_dec, torch.zeros(d_model)
+
+
+# --------------------------------------------------------------------------------------
+# forward pieces
+# --------------------------------------------------------------------------------------
+def normalize_w_dec(W_dec: Tensor) -> Tensor:
+    """modeling.py:411-417: W_dec /= ||W_dec||_2 along dim=1 (rows = dictionary atoms)."""
+    return W_dec / torch.norm(W_dec, dim=1, keepdim=True)
+
+
+def encode_pre(x: Tensor, W_enc: Tensor, b_enc: Tensor) -> Tensor:
+    """modeling.py:344-347: h = x @ W_enc + b_enc."""
+    return x @ W_enc + b_enc
+
+
+def topk_activation(h: Tensor, top_k: int):
+    """modeling.py:174-179: idx = topk(h, min(k,S), sorted=False); f = scatter(zeros, idx, 1) * h.
+    No ReLU: negative pre-activations can be selected.  Returns (f, mask)."""
+    k = min(top_k, h.shape[1])
+    _, idx = torch.topk(h, k, dim=-1, sorted=False)
+    mask = torch.zeros_like(h).scatter(-1, idx, 1.0)
+    return mask * h, mask
+
+
+def relu_activation(h: Tensor):
+    """modeling.py:155-156: relu(h).  Returns (f, mask) with mask = h > 0 (autograd of relu)."""
+    return torch.relu(h), (h > 0).to(h.dtype)
+
+
+def dead_tracker_update(toks: Tensor | None, f: Tensor, dead_threshold_tokens: int):
+    """objectives.py:107-120 (training only): active = any_b(|f|>0); toks += B; toks[active] = 0;
+    dead = toks >= threshold.  Returns (toks_new int64[S], dead bool[S])."""
+    B, S = f.shape
+    if toks is None:
+        toks = torch.zeros(S, dtype=torch.int64)
+    active = (f.abs() > 0).any(dim=0)
+    toks = toks + B
+    toks = torch.where(active, torch.zeros_like(toks), toks)
+    return toks, toks >= dead_threshold_tokens
+
+
+def decode(f: Tensor, W_dec: Tensor, b_dec: Tensor) -> Tensor:
+    """modeling.py:386-406 with the default single prefix [d_sae]: x_hat = f @ W_dec + b_dec."""
+    return f @ W_dec + b_dec
+
+
+def mean_squared_err(x_hat: Tensor, x: Tensor) -> Tensor:
+    """objectives.py:224-237 followed by .mean() (objectives.py:133-138):
+    u = max|x| clamped at 1e-12; ((x_hat/u - x/u)^2) * u^2, mean over all elements."""
+    upper = x.abs().max().clamp(min=1e-12)
+    d = x_hat / upper - x / upper
+    return (d * d * upper * upper).mean()
+
+
+def auxk(h: Tensor, r: Tensor, dead: Tensor, W_dec: Tensor, b_dec: Tensor, k_aux: int, alpha: float):
+    """modeling.py:89-103.  e = (x - x_hat).detach() = -r; masked = h.masked_fill(~dead, -inf);
+    k_use = min(k_aux, n_dead); top_i = masked.topk(k_use); f_aux = scatter(h at top_i);
+    x_aux = decode(f_aux) (b_dec IS added); aux = alpha * mean((x_aux - e)^2).
+    Returns (aux scalar, f_aux[B,S] or None, r_aux[B,D] or None)."""
+    n_dead = int(dead.sum())
+    k_use = min(k_aux, n_dead)
+    if k_use == 0:
+        return torch.zeros(()), None, None
+    e = -r
+    masked = h.masked_fill(~dead, float("-inf"))
+    _, top_i = masked.topk(k_use, dim=-1)
+    f_aux = torch.zeros_like(h)
+    f_aux.scatter_(-1, top_i, h.gather(-1, top_i))
+    x_aux = decode(f_aux, W_dec, b_dec)
+    r_aux = x_aux - e
+    mask_aux = torch.zeros_like(h).scatter_(-1, top_i, 1.0)
+    return alpha * r_aux.pow(2).mean(), (f_aux, mask_aux), r_aux
+
+
+@dataclasses.dataclass
+class ForwardOut:
+    h: Tensor
+    f: Tensor
+    mask: Tensor
+    x_hat: Tensor
+    r: Tensor
+    mse: Tensor
+    sparsity: Tensor
+    l0: Tensor
+    l1: Tensor
+    aux: Tensor
+    n_dead: int
+    f_aux: Tensor | None
+    mask_aux: Tensor | None
+    r_aux: Tensor | None
+
+    @property
+    def loss(self) -> Tensor:
+        """objectives.py:76-78."""
+        return self.mse + self.sparsity + self.aux
+
+
+def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True) -> ForwardOut:
+    """objectives.py:101-156 with Matryoshka(n_prefixes=1)."""
+    h = encode_pre(x, st.W_enc, st.b_enc)
+    if cfg.activation == "topk":
+        f, mask = topk_activation(h, cfg.top_k)
+    elif cfg.activation == "relu":
+        f, mask = relu_activation(h)
+    else:
+        raise ValueError(cfg.activation)
+
+    dead = None
+    if training:
+        st.toks_since_active, dead = dead_tracker_update(st.toks_since_active, f, cfg.dead_threshold_tokens)
+
+    x_hat = decode(f, st.W_dec, st.b_dec)
+    r = x_hat - x
+    mse = mean_squared_err(x_hat, x)
+
+    # modeling.py:30-31, 40-42
+    l1 = f.abs().sum(dim=1).mean(dim=0)
+    sparsity = l1 * cfg.l1_coeff if cfg.l1_coeff != 0.0 else torch.zeros(())
+    # objectives.py:150-151
+    l0 = (f != 0).float().sum(dim=1).mean(dim=0)
+
+    aux, fa, r_aux = torch.zeros(()), None, None
+    n_dead = 0
+    if training and dead is not None:
+        n_dead = int(dead.sum())
+        if cfg.aux:
+            aux, fa, r_aux = auxk(h, r, dead, st.W_dec, st.b_dec, cfg.k_aux, cfg.aux_alpha)
+    f_aux, mask_aux = fa if fa is not None else (None, None)
+    return ForwardOut(h, f, mask, x_hat, r, mse, sparsity, l0, l1, aux, n_dead, f_aux, mask_aux, r_aux)
+
+
+# --------------------------------------------------------------------------------------
+# backward (what autograd computes for train.py:347-348), projection, clip, Adam, schedule
+# --------------------------------------------------------------------------------------
+def backward(cfg: OracleConfig, st: OracleState, x: Tensor, out: ForwardOut) -> dict:
+    """Gradients of loss = mse + sparsity + aux w.r.t. the four parameters.
+    G = 2 r/(B D);  G_a = 2 alpha r_a/(B D)
+    gW_dec = f^T G + f_a^T G_a ; gb_dec = sum_b G + sum_b G_a
+    dh = mask*(G W_dec^T) + mask_a*(G_a W_dec^T) (+ coeff*sign(f)/B on the active set for L1)
+    gW_enc = x^T dh ; gb_enc = sum_b dh."""
+    B, D = x.shape
+    G = out.r * (2.0 / (B * D))
+    gW_dec = out.f.T @ G
+    gb_dec = G.sum(dim=0)
+    df = G @ st.W_dec.T
+    if cfg.l1_coeff != 0.0:
+        df = df + (cfg.l1_coeff / B) * torch.sign(out.f)
+    dh = out.mask * df
+    if out.f_aux is not None:
+        Ga = out.r_aux * (2.0 * cfg.aux_alpha / (B * D))
+        gW_dec = gW_dec + out.f_aux.T @ Ga
+        gb_dec = gb_dec + Ga.sum(dim=0)
+        dh = dh + out.mask_aux * (Ga @ st.W_dec.T)
+    return dict(W_enc=x.T @ dh, b_enc=dh.sum(dim=0), W_dec=gW_dec, b_dec=gb_dec)
+
+
+def remove_parallel_grads(gW_dec: Tensor, W_dec: Tensor) -> Tensor:
+    """modeling.py:419-445: g_j -= (<g_j,w_j>/||w_j||^2) w_j; rows with ||w_j||^2 == 0 untouched."""
+    par = (gW_dec * W_dec).sum(dim=1)
+    nsq = (W_dec * W_dec).sum(dim=1)
+    scales = torch.where(nsq > 0, par / torch.where(nsq > 0, nsq, torch.ones_like(nsq)), torch.zeros_like(par))
+    return gW_dec - scales[:, None] * W_dec
+
+
+PARAM_ORDER = ("W_dec", "b_dec", "W_enc", "b_enc")  # nn.Module registration order, modeling.py:312-327
+
+
+def clip_grad_norm(grads: dict, max_norm: float):
+    """torch.nn.utils.clip_grad_norm_ as called at train.py:358-360:
+    n = ||(all grads)||_2 ; coef = min(1, max_norm/(n+1e-6)) ; g *= coef.  Returns (grads, n)."""
+    norms = torch.stack([torch.linalg.vector_norm(grads[k]) for k in PARAM_ORDER])
+    total = torch.linalg.vector_norm(norms)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return {k: g * coef for k, g in grads.items()}, total
+
+
+def adam_step(cfg: OracleConfig, st: OracleState, grads: dict) -> None:
+    """torch.optim.Adam(fused=True) defaults (train.py:294,444-446): t += 1;
+    m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+    p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  lr is the value assigned at the END of
+    the previous step (0.0 on the first step)."""
+    st.t += 1
+    bc1 = 1.0 - cfg.beta1**st.t
+    bc2 = 1.0 - cfg.beta2**st.t
+    step_size = st.lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    for k, p in st.params().items():
+        g = grads[k]
+        st.m[k] = st.m[k] + (g - st.m[k]) * (1.0 - cfg.beta1)  # lerp form used by torch's fused kernel
+        st.v[k] = st.v[k] * cfg.beta2 + (1.0 - cfg.beta2) * g * g
+        denom = st.v[k].sqrt() / bc2_sqrt + cfg.eps
+        setattr(st, k, p - step_size * (st.m[k] / denom))
+
+
+def warmup_cosine(step: int, n_warmup: int, peak: float, n_steps: int, init: float = 0.0, final: float = 0.0) -> float:
+    """scheduling.py:58-68 evaluated at the already-incremented 1-based `_step`."""
+    if step < n_warmup:
+        return init + (peak - init) * (step / n_warmup)
+    if step < n_steps:
+        progress = (step - n_warmup) / (n_steps - n_warmup)
+        return final + (peak - final) * (1 + math.cos(math.pi * progress)) / 2
+    return final
+
+
+def train_step(cfg: OracleConfig, st: OracleState, x: Tensor) -> dict:
+    """One iteration of train.py:332-460 (log block excluded).  Mutates `st`; returns scalars and,
+    for parity tests, the clipped gradients."""
+    if cfg.normalize_w_dec:
+        st.W_dec = normalize_w_dec(st.W_dec)  # train.py:334-335
+    out = forward(cfg, st, x, training=True)  # train.py:341
+    grads = backward(cfg, st, x, out)  # train.py:348
+    if cfg.remove_parallel_grads:
+        grads["W_dec"] = remove_parallel_grads(grads["W_dec"], st.W_dec)  # train.py:352
+    grads, gnorm = clip_grad_norm(grads, cfg.grad_clip)  # train.py:358-360
+    adam_step(cfg, st, grads)  # train.py:444-446
+    st.sched_step += 1
+    st.lr = warmup_cosine(st.sched_step, cfg.n_lr_warmup, cfg.lr, cfg.n_steps)  # train.py:449-451
+    return dict(
+        loss=float(out.loss), mse=float(out.mse), aux=float(out.aux), sparsity=float(out.sparsity),
+        l0=float(out.l0), l1=float(out.l1), n_dead=out.n_dead, grad_norm=float(gnorm), grads=grads, out=out,
+    )
+
+
+def eval_forward(cfg: OracleConfig, st: OracleState, x: Tensor) -> ForwardOut:
+    """Objective in eval mode (train.py:526-527,559): no dead tracking, aux = 0."""
+    return forward(cfg, st, x, training=False)

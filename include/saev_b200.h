@@ -1,0 +1,151 @@
+/* saev_b200 — C ABI of the B200-native SAE training step (libsaev_b200.so).
+ *
+ * Drop-in boundary for the hot path of OSU-NLP-Group/saev (citations are file:line under the
+ * reference checkout):
+ *   src/saev/nn/modeling.py:343-349    SparseAutoencoder.encode          -> saev_b200_forward (phase A)
+ *   src/saev/nn/modeling.py:169-179    TopKActivation.forward            -> saev_b200_forward (phase A)
+ *   src/saev/nn/modeling.py:351-409    SparseAutoencoder.decode          -> saev_b200_forward (phase A)
+ *   src/saev/nn/objectives.py:101-156  MatryoshkaObjective.forward       -> saev_b200_forward (A + B)
+ *   src/saev/nn/objectives.py:107-122  dead-latent tracker               -> saev_b200_forward (phase B)
+ *   src/saev/nn/modeling.py:75-103     AuxK.loss                         -> saev_b200_forward (phase B)
+ *   src/saev/framework/train.py:348    loss.backward() (autograd)        -> saev_b200_backward
+ *   src/saev/nn/modeling.py:419-445    remove_parallel_grads             -> saev_b200_backward (fused)
+ *   src/saev/framework/train.py:358    clip_grad_norm_                   -> saev_b200_grad_sumsq + saev_b200_adam_step
+ *   src/saev/framework/train.py:294,444-446  torch.optim.Adam(fused=True).step -> saev_b200_adam_step
+ *   src/saev/nn/modeling.py:411-417    normalize_w_dec                   -> saev_b200_normalize_w_dec / adam_step(renorm)
+ *   src/saev/framework/train.py:333    batch["act"].to(device)           -> saev_b200_ring_* (pinned staging ring)
+ *
+ * Conventions
+ *   - Plain C types only.  Every `float*` / `int*` below is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors in practice) unless the name says `host_`.  The library never frees or
+ *     resizes caller memory and allocates no device memory of its own: scratch comes from the
+ *     caller-provided workspace blob (saev_b200_workspace_bytes).
+ *   - All tensors are fp32, row-major, contiguous.  The encoder weight is passed ATOM-MAJOR:
+ *         W_enc_t[d_sae, d_model]  ==  saev's W_enc[d_model, d_sae] transposed
+ *     (the Python module exposes saev's [d_model, d_sae] parameter as a transposed view of it).
+ *   - Gradients and Adam moments use one flat order: [W_enc_t (S*D), b_enc (S), W_dec (S*D), b_dec (D)].
+ *   - Every entry enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising the host.  Return value 0 = ok, otherwise an error code; the message is
+ *     available from saev_b200_last_error().  One handle per (process, device); calls on one handle
+ *     must not race.
+ */
+#ifndef SAEV_B200_H_
+#define SAEV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAEV_B200_ABI_VERSION 1
+
+enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
+enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
+enum { SAEV_B200_PHASE_A = 1, SAEV_B200_PHASE_B = 2, SAEV_B200_PHASE_ALL = 3 };
+
+typedef struct saev_b200_cfg {
+  int32_t d_model;               /* SparseAutoencoderConfig.d_model      modeling.py:265 */
+  int32_t d_sae;                 /* SparseAutoencoderConfig.d_sae        modeling.py:267 */
+  int32_t act_kind;              /* TopK | Relu                          modeling.py:111-126 */
+  int32_t top_k;                 /* TopK.top_k                           modeling.py:123 */
+  int32_t aux_kind;              /* NoAux | AuxK                         modeling.py:50-106 */
+  int32_t k_aux;                 /* AuxK.k_aux                           modeling.py:72 */
+  float aux_alpha;               /* AuxK.alpha                           modeling.py:73 */
+  float l1_coeff;                /* L1Sparsity.coeff, 0 = NoSparsity     modeling.py:25-42 */
+  int64_t dead_threshold_tokens; /* Matryoshka.dead_threshold_tokens     objectives.py:24 */
+  int32_t remove_parallel_grads; /* SparseAutoencoderConfig              modeling.py:281 */
+  int32_t max_batch;             /* largest B any call will pass */
+  int32_t aux_cols_cap;          /* max dead latents AuxK scratch is sized for; 0 = d_sae */
+  int32_t reserved;
+} saev_b200_cfg;
+
+typedef struct saev_b200_handle saev_b200_handle;
+
+int saev_b200_abi_version(void);
+const char* saev_b200_last_error(const saev_b200_handle* h);
+
+int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out);
+int saev_b200_destroy(saev_b200_handle* h);
+
+/* Bytes of scratch the caller must provide (256-byte aligned) for batches up to cfg.max_batch. */
+size_t saev_b200_workspace_bytes(const saev_b200_handle* h);
+
+/* (Re)build the bf16 operand copy of W_enc_t kept in the workspace.  Call after the weights were
+ * written by anything other than saev_b200_adam_step (init, load_state_dict, datapoint init). */
+int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* workspace, void* stream);
+
+/* W_dec[j,:] /= ||W_dec[j,:]||_2    (modeling.py:411-417) */
+int saev_b200_normalize_w_dec(saev_b200_handle* h, float* W_dec, void* stream);
+
+/* Objective forward on one batch x[B, d_model]  (objectives.py:101-156, Matryoshka n_prefixes = 1).
+ *   phase A: encode + TopK + decode + residual + per-row loss partials (+ d loss/d h when training);
+ *            marks the atoms that fired in `active` (workspace).
+ *   phase B: dead tracker update on toks_since_active[S] (int64; pass NULL in eval), AuxK forward,
+ *            loss scalars.  Data-parallel callers all-reduce saev_b200_active_flags() (MAX) between
+ *            A and B and pass the global batch size as `tokens_global`.
+ * Outputs: topk_idx[B,K] (int32, -1 = empty slot), topk_val[B,K], resid[B,D] = x_hat - x,
+ *          losses[8] = {mse, aux, sparsity, l0, l1, n_dead, loss, 0} (device).
+ * `training` != 0 additionally prepares what saev_b200_backward consumes (kept in the workspace). */
+int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B, int64_t tokens_global,
+                      const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
+                      int64_t* toks_since_active, int32_t training, int32_t* topk_idx, float* topk_val,
+                      float* resid, float* losses, void* workspace, void* stream);
+
+/* int32[d_sae] activity flags written by phase A (device pointer inside the workspace). */
+int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace);
+/* uint32 diagnostic counter: rows whose top-k could not be proven from the screen margin. */
+uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace);
+
+/* Gradients of loss = mse + sparsity + aux for the batch of the last training forward
+ * (what loss.backward() + remove_parallel_grads() leave in .grad; train.py:348,352).
+ * Overwrites gW_enc_t[S,D], gb_enc[S], gW_dec[S,D], gb_dec[D]. */
+int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t tokens_global,
+                       const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
+                       const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
+                       float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream);
+
+/* sumsq_out[0] = sum of squares over the flat gradient bucket of `n` floats (after any all-reduce). */
+int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,
+                         void* workspace, void* stream);
+
+/* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + bf16 operand refresh.
+ *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)
+ *   `step` is the 1-based Adam step count AFTER this update (bias corrections use it).
+ *   gnorm_out (optional, device) receives ||g_eff||, the value clip_grad_norm_ returns. */
+int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float* W_dec, float* b_dec,
+                        const float* grads_flat, float* m_flat, float* v_flat, float lr, float beta1,
+                        float beta2, float eps, int64_t step, float max_norm, float grad_scale,
+                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, void* workspace,
+                        void* stream);
+
+/* Lazy dense views for saev's logging block (train.py:365-442). */
+int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,
+                      float* f_x_out /* [B, d_sae] */, void* stream);
+int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B,
+                    float* x_hat_out /* [B, d_model] */, void* stream);
+
+/* Test hook for the tensor-core contraction alone: out[M, N] = A[M, K] . Bt[N, K]^T + bias[N], computed
+ * from bf16 copies of the operands (nterms = 1) or the 3-term split product (nterms = 3).
+ * scratch must hold 2 * (M + N) * K bf16. */
+int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
+                      int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream);
+
+/* ---- pinned staging ring for activation batches (replaces the pageable-memory H2D copy of
+ *      train.py:333 / buffers.py:199) ----
+ * `n_slots` pinned host buffers of `slot_bytes`; saev_b200_ring_submit enqueues cudaMemcpyAsync of a
+ * filled slot to `dst_device` on the ring's own copy stream and records an event;
+ * saev_b200_ring_wait makes `consumer_stream` wait for that event (no host sync). */
+typedef struct saev_b200_ring saev_b200_ring;
+int saev_b200_ring_create(int32_t n_slots, size_t slot_bytes, saev_b200_ring** out);
+int saev_b200_ring_destroy(saev_b200_ring* r);
+void* saev_b200_ring_host_ptr(saev_b200_ring* r, int32_t slot);
+int saev_b200_ring_submit(saev_b200_ring* r, int32_t slot, void* dst_device, size_t bytes);
+int saev_b200_ring_wait(saev_b200_ring* r, int32_t slot, void* consumer_stream);
+int saev_b200_ring_host_sync(saev_b200_ring* r, int32_t slot); /* block host until the slot's copy is done */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAEV_B200_H_ */

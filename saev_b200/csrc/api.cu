@@ -1,0 +1,558 @@
+// extern "C" surface of libsaev_b200.so (see include/saev_b200.h for the contract).
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include <new>
+
+#include "../../include/saev_b200.h"
+#include "kernels.h"
+
+using namespace sb;
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
+
+struct Workspace {
+  size_t shadow_hi, x_hi, cand_val, cand_idx, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+      entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, total;
+};
+
+}  // namespace
+
+struct saev_b200_handle {
+  saev_b200_cfg cfg;
+  int device = 0;
+  int num_sms = 148;
+  int kp = 40;
+  int aux_cap = 0;
+  Workspace ws;
+  bool last_forward_training = false;
+  bool last_forward_tracked = false;
+  mutable char err[512];
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const saev_b200_handle* h, int code, const char* fmt, const char* detail = "") {
+  char* dst = h ? h->err : g_err;
+  snprintf(dst, 512, fmt, detail);
+  return code;
+}
+
+int check_cuda(const saev_b200_handle* h, const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  char buf[400];
+  snprintf(buf, sizeof(buf), "%s: %s", where, cudaGetErrorString(e));
+  return fail(h, 100, "CUDA error at %s", buf);
+}
+
+Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
+  Workspace w;
+  const size_t S = c.d_sae, D = c.d_model, B = c.max_batch, K = c.top_k;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += align_up(bytes);
+    return at;
+  };
+  w.shadow_hi = take(S * D * 2);
+  w.x_hi = take(B * D * 2);
+  w.cand_val = take(B * ENCODE_MAX_NSPLIT * kp * 4);
+  w.cand_idx = take(B * ENCODE_MAX_NSPLIT * kp * 4);
+  w.dh = take(B * K * 4);
+  w.row_sse = take(B * 4);
+  w.row_l1 = take(B * 4);
+  w.row_l0 = take(B * 4);
+  w.row_sse_aux = take(B * 4);
+  w.feat_count = take(S * 4);
+  w.feat_off = take((S + 1) * 4);
+  w.cursor = take(S * 4);
+  w.entries = take(B * K * 4);
+  w.active = take(S * 4);
+  w.dead_list = take(S * 4);
+  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] sumsq scratch
+  w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
+  w.sumsq_partial = take(1024 * 8);
+  if (c.aux_kind == SAEV_B200_AUX_AUXK) {
+    w.h_aux = take(B * static_cast<size_t>(aux_cap) * 4);
+    w.mask_aux = take(B * static_cast<size_t>(aux_cap));
+    w.r_aux = take(B * D * 4);
+  } else {
+    w.h_aux = w.mask_aux = w.r_aux = o;
+  }
+  w.total = o;
+  return w;
+}
+
+template <typename T>
+inline T* at(void* ws, size_t off) {
+  return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
+}
+
+}  // namespace
+
+extern "C" {
+
+int saev_b200_abi_version(void) { return SAEV_B200_ABI_VERSION; }
+
+const char* saev_b200_last_error(const saev_b200_handle* h) { return h ? h->err : g_err; }
+
+int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
+  if (!cfg || !out) return fail(nullptr, 1, "saev_b200_create: null argument%s");
+  *out = nullptr;
+  if (cfg->d_model <= 0 || cfg->d_sae <= 0 || cfg->max_batch <= 0)
+    return fail(nullptr, 2, "saev_b200_create: d_model, d_sae and max_batch must be positive%s");
+  if (cfg->d_model % 8 != 0 || cfg->d_model > 2048)
+    return fail(nullptr, 2, "saev_b200_create: d_model must be a multiple of 8 and <= 2048%s");
+  if (cfg->d_sae % 4 != 0) return fail(nullptr, 2, "saev_b200_create: d_sae must be a multiple of 4%s");
+  if (cfg->act_kind != SAEV_B200_ACT_TOPK)
+    return fail(nullptr, 3, "saev_b200_create: only the TopK activation has a CUDA path in this build%s");
+  if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
+    return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
+  const int kp = encode_gemm_kp(cfg->top_k);
+  if (kp < 0) return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
+  int dev = 0, cc_major = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(nullptr, 4, "saev_b200_create: no CUDA device (this library has no CPU path)%s");
+  }
+  cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cc_major != 10)
+    return fail(nullptr, 4, "saev_b200_create: kernels are built for sm_100a (Blackwell B200) only%s");
+  saev_b200_handle* h = new (std::nothrow) saev_b200_handle();
+  if (!h) return fail(nullptr, 5, "saev_b200_create: out of host memory%s");
+  h->cfg = *cfg;
+  h->device = dev;
+  h->num_sms = sms;
+  h->kp = kp;
+  h->aux_cap = (cfg->aux_cols_cap > 0 && cfg->aux_cols_cap < cfg->d_sae) ? cfg->aux_cols_cap : cfg->d_sae;
+  h->ws = plan_workspace(h->cfg, kp, h->aux_cap);
+  h->err[0] = 0;
+  *out = h;
+  return 0;
+}
+
+int saev_b200_destroy(saev_b200_handle* h) {
+  delete h;
+  return 0;
+}
+
+size_t saev_b200_workspace_bytes(const saev_b200_handle* h) { return h ? h->ws.total : 0; }
+
+int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace) {
+  return at<int32_t>(workspace, h->ws.active);
+}
+uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace) {
+  return at<uint32_t>(workspace, h->ws.scalars) + 1;
+}
+
+int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n = static_cast<long long>(h->cfg.d_sae) * h->cfg.d_model;
+  if (launch_split_bf16(W_enc_t, at<__nv_bfloat16>(workspace, h->ws.shadow_hi), nullptr, n, s))
+    return fail(h, 30, "sync_weights: split_bf16 launch failed%s");
+  return check_cuda(h, "sync_weights");
+}
+
+int saev_b200_normalize_w_dec(saev_b200_handle* h, float* W_dec, void* stream) {
+  if (launch_normalize_rows(W_dec, h->cfg.d_sae, h->cfg.d_model, static_cast<cudaStream_t>(stream)))
+    return fail(h, 31, "normalize_w_dec: launch failed%s");
+  return check_cuda(h, "normalize_w_dec");
+}
+
+int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B, int64_t tokens_global,
+                      const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
+                      int64_t* toks_since_active, int32_t training, int32_t* topk_idx, float* topk_val,
+                      float* resid, float* losses, void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const saev_b200_cfg& c = h->cfg;
+  const Workspace& w = h->ws;
+  if (B <= 0 || B > c.max_batch) return fail(h, 40, "forward: B out of range (0 < B <= cfg.max_batch)%s");
+  if (tokens_global <= 0) tokens_global = B;
+  const int D = c.d_model, S = c.d_sae, K = c.top_k;
+  int* scal_i = at<int>(workspace, w.scalars);
+  float* aux_loss = at<float>(workspace, w.scalars) + 2;
+  const bool tracked = training && toks_since_active != nullptr;
+
+  if (phase & SAEV_B200_PHASE_A) {
+    cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
+    if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
+    __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
+    if (launch_split_bf16(x, x_hi, nullptr, static_cast<long long>(B) * D, s))
+      return fail(h, 41, "forward: split_bf16 launch failed%s");
+
+    EncodeGemmArgs g;
+    g.A_hi = x_hi;
+    g.B_hi = at<__nv_bfloat16>(workspace, w.shadow_hi);
+    g.nterms = 1;
+    g.M = B;
+    g.N = S;
+    g.K = D;
+    g.bias = b_enc;
+    g.epilogue = 0;
+    g.kp = h->kp;
+    g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
+    g.num_sms = h->num_sms;
+    g.cand_val = at<float>(workspace, w.cand_val);
+    g.cand_idx = at<int>(workspace, w.cand_idx);
+    if (int rc = launch_encode_gemm(g, s)) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%d", rc);
+      return fail(h, 42, "forward: encode GEMM launch failed (code %s)", buf);
+    }
+
+    RescoreArgs r;
+    r.cand_val = g.cand_val;
+    r.cand_idx = g.cand_idx;
+    r.nsplit = g.nsplit;
+    r.kp = h->kp;
+    r.x = x;
+    r.W_enc_t = W_enc_t;
+    r.b_enc = b_enc;
+    r.B = B;
+    r.D = D;
+    r.S = S;
+    r.K = K;
+    r.topk_idx = topk_idx;
+    r.topk_val = topk_val;
+    r.feat_count = training ? at<int>(workspace, w.feat_count) : nullptr;
+    r.active = at<int>(workspace, w.active);
+    r.unsafe_rows = reinterpret_cast<unsigned int*>(scal_i + 1);
+    if (launch_rescore_topk(r, s)) return fail(h, 43, "forward: rescore launch failed%s");
+
+    DecodeArgs d;
+    d.x = x;
+    d.topk_idx = topk_idx;
+    d.topk_val = topk_val;
+    d.W_dec = W_dec;
+    d.b_dec = b_dec;
+    d.B = B;
+    d.D = D;
+    d.K = K;
+    d.grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+    d.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
+    d.resid = resid;
+    d.dh = training ? at<float>(workspace, w.dh) : nullptr;
+    d.row_sse = at<float>(workspace, w.row_sse);
+    d.row_l1 = at<float>(workspace, w.row_l1);
+    d.row_l0 = at<float>(workspace, w.row_l0);
+    if (launch_decode(d, s)) return fail(h, 44, "forward: decode launch failed%s");
+    h->last_forward_training = training != 0;
+    h->last_forward_tracked = false;
+  }
+
+  if (phase & SAEV_B200_PHASE_B) {
+    bool aux_live = false;
+    if (tracked) {
+      if (launch_dead_update(reinterpret_cast<long long*>(toks_since_active), at<int>(workspace, w.active), S,
+                             tokens_global, c.dead_threshold_tokens, at<int>(workspace, w.dead_list), scal_i, s))
+        return fail(h, 45, "forward: dead tracker launch failed%s");
+      h->last_forward_tracked = true;
+      if (c.aux_kind == SAEV_B200_AUX_AUXK) {
+        AuxArgs a;
+        a.x = x;
+        a.resid = resid;
+        a.W_enc_t = W_enc_t;
+        a.b_enc = b_enc;
+        a.W_dec = W_dec;
+        a.b_dec = b_dec;
+        a.dead_list = at<int>(workspace, w.dead_list);
+        a.n_dead = scal_i;
+        a.B = B;
+        a.D = D;
+        a.S = h->aux_cap;
+        a.k_aux = c.k_aux;
+        a.alpha = c.aux_alpha;
+        a.inv_bd = static_cast<float>(1.0 / (static_cast<double>(tokens_global) * D));
+        a.remove_parallel = c.remove_parallel_grads;
+        a.h_aux = at<float>(workspace, w.h_aux);
+        a.mask_aux = at<unsigned char>(workspace, w.mask_aux);
+        a.r_aux = at<float>(workspace, w.r_aux);
+        a.row_sse_aux = at<float>(workspace, w.row_sse_aux);
+        a.aux_loss = aux_loss;
+        a.gW_enc_t = a.gb_enc = a.gW_dec = nullptr;
+        a.colsum_partial = at<float>(workspace, w.colsum_partial);
+        a.gb_dec = nullptr;
+        if (launch_aux_forward(a, s)) return fail(h, 46, "forward: AuxK launch failed%s");
+        aux_live = true;
+      }
+    } else {
+      cudaMemsetAsync(scal_i, 0, 4, s);  // n_dead = 0 (eval: dead_mask is None, objectives.py:121-122)
+    }
+    FinalizeArgs f;
+    f.row_sse = at<float>(workspace, w.row_sse);
+    f.row_l1 = at<float>(workspace, w.row_l1);
+    f.row_l0 = at<float>(workspace, w.row_l0);
+    f.B = B;
+    f.D = D;
+    // per-rank partial means compose: each rank divides by the GLOBAL batch
+    f.inv_bd = 1.0 / (static_cast<double>(tokens_global) * D);
+    f.inv_b = 1.0 / static_cast<double>(tokens_global);
+    f.l1_coeff = c.l1_coeff;
+    f.aux_loss = aux_live ? aux_loss : nullptr;
+    f.n_dead = scal_i;
+    f.losses = losses;
+    if (launch_finalize(f, s)) return fail(h, 47, "forward: finalize launch failed%s");
+  }
+  return check_cuda(h, "forward");
+}
+
+int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t tokens_global,
+                       const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
+                       const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
+                       float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const saev_b200_cfg& c = h->cfg;
+  const Workspace& w = h->ws;
+  if (!h->last_forward_training) return fail(h, 50, "backward: the last forward was not a training forward%s");
+  if (B <= 0 || B > c.max_batch) return fail(h, 40, "backward: B out of range%s");
+  if (tokens_global <= 0) tokens_global = B;
+  const int D = c.d_model, S = c.d_sae, K = c.top_k;
+  const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+  if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
+                       at<int>(workspace, w.cursor), at<int>(workspace, w.entries), s))
+    return fail(h, 51, "backward: CSC build launch failed%s");
+  WgradArgs g;
+  g.feat_off = at<int>(workspace, w.feat_off);
+  g.entries = at<int>(workspace, w.entries);
+  g.topk_val = topk_val;
+  g.dh = at<float>(workspace, w.dh);
+  g.resid = resid;
+  g.x = x;
+  g.W_dec = W_dec;
+  g.B = B;
+  g.D = D;
+  g.S = S;
+  g.K = K;
+  g.grad_scale = grad_scale;
+  g.remove_parallel = c.remove_parallel_grads;
+  g.gW_enc_t = gW_enc_t;
+  g.gb_enc = gb_enc;
+  g.gW_dec = gW_dec;
+  if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
+  if (launch_colsum(resid, B, D, grad_scale, 0, at<float>(workspace, w.colsum_partial), gb_dec, s))
+    return fail(h, 53, "backward: bias-gradient launch failed%s");
+  if (c.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked) {
+    AuxArgs a;
+    a.x = x;
+    a.resid = resid;
+    a.W_enc_t = W_enc_t;
+    a.b_enc = b_enc;
+    a.W_dec = W_dec;
+    a.b_dec = b_dec;
+    a.dead_list = at<int>(workspace, w.dead_list);
+    a.n_dead = at<int>(workspace, w.scalars);
+    a.B = B;
+    a.D = D;
+    a.S = h->aux_cap;
+    a.k_aux = c.k_aux;
+    a.alpha = c.aux_alpha;
+    a.inv_bd = static_cast<float>(1.0 / (static_cast<double>(tokens_global) * D));
+    a.remove_parallel = c.remove_parallel_grads;
+    a.h_aux = at<float>(workspace, w.h_aux);
+    a.mask_aux = at<unsigned char>(workspace, w.mask_aux);
+    a.r_aux = at<float>(workspace, w.r_aux);
+    a.row_sse_aux = at<float>(workspace, w.row_sse_aux);
+    a.aux_loss = at<float>(workspace, w.scalars) + 2;
+    a.gW_enc_t = gW_enc_t;
+    a.gb_enc = gb_enc;
+    a.gW_dec = gW_dec;
+    a.colsum_partial = at<float>(workspace, w.colsum_partial);
+    a.gb_dec = gb_dec;
+    if (launch_aux_backward(a, s)) return fail(h, 54, "backward: AuxK launch failed%s");
+  }
+  return check_cuda(h, "backward");
+}
+
+int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,
+                         void* workspace, void* stream) {
+  if (launch_sumsq(grads_flat, n, at<double>(workspace, h->ws.sumsq_partial), sumsq_out,
+                   static_cast<cudaStream_t>(stream)))
+    return fail(h, 60, "grad_sumsq: launch failed%s");
+  return check_cuda(h, "grad_sumsq");
+}
+
+int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float* W_dec, float* b_dec,
+                        const float* grads_flat, float* m_flat, float* v_flat, float lr, float beta1,
+                        float beta2, float eps, int64_t step, float max_norm, float grad_scale,
+                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, void* workspace,
+                        void* stream) {
+  const long long S = h->cfg.d_sae, D = h->cfg.d_model;
+  if (step < 1) return fail(h, 61, "adam_step: step must be >= 1%s");
+  AdamArgs a;
+  a.W_enc_t = W_enc_t;
+  a.b_enc = b_enc;
+  a.W_dec = W_dec;
+  a.b_dec = b_dec;
+  a.gW_enc_t = grads_flat;
+  a.gb_enc = grads_flat + S * D;
+  a.gW_dec = grads_flat + S * D + S;
+  a.gb_dec = grads_flat + 2 * S * D + S;
+  a.m = m_flat;
+  a.v = v_flat;
+  a.shadow_hi = workspace ? at<__nv_bfloat16>(workspace, h->ws.shadow_hi) : nullptr;
+  a.D = static_cast<int>(D);
+  a.S = static_cast<int>(S);
+  a.lr = lr;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  // bias corrections in double on the host (torch computes 1 - beta^step the same way, train.py:294)
+  double b1p = 1.0, b2p = 1.0;
+  {
+    double x1 = beta1, x2 = beta2;
+    long long e = step;
+    while (e > 0) {
+      if (e & 1) {
+        b1p *= x1;
+        b2p *= x2;
+      }
+      x1 *= x1;
+      x2 *= x2;
+      e >>= 1;
+    }
+  }
+  a.bc1 = static_cast<float>(1.0 - b1p);
+  a.bc2_sqrt = static_cast<float>(sqrt(1.0 - b2p));
+  a.max_norm = max_norm;
+  a.grad_scale = grad_scale;
+  a.gnorm_sq = sumsq;
+  a.renorm_w_dec = renorm_w_dec;
+  a.gnorm_out = gnorm_out;
+  if (launch_adam(a, static_cast<cudaStream_t>(stream))) return fail(h, 62, "adam_step: launch failed%s");
+  return check_cuda(h, "adam_step");
+}
+
+int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,
+                      float* f_x_out, void* stream) {
+  if (launch_densify(topk_idx, topk_val, B, h->cfg.top_k, h->cfg.d_sae, f_x_out, static_cast<cudaStream_t>(stream)))
+    return fail(h, 70, "densify: launch failed%s");
+  return check_cuda(h, "densify");
+}
+
+int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hat_out,
+                    void* stream) {
+  if (launch_add_rows(resid, x, static_cast<long long>(B) * h->cfg.d_model, x_hat_out,
+                      static_cast<cudaStream_t>(stream)))
+    return fail(h, 71, "x_hat: launch failed%s");
+  return check_cuda(h, "x_hat");
+}
+
+int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
+                      int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (K % 8) return fail(h, 80, "gemm_nt: K must be a multiple of 8%s");
+  if (nterms != 1 && nterms != 3) return fail(h, 80, "gemm_nt: nterms must be 1 or 3%s");
+  __nv_bfloat16* a_hi = static_cast<__nv_bfloat16*>(scratch);
+  __nv_bfloat16* a_lo = a_hi + static_cast<size_t>(M) * K;
+  __nv_bfloat16* b_hi = a_lo + static_cast<size_t>(M) * K;
+  __nv_bfloat16* b_lo = b_hi + static_cast<size_t>(N) * K;
+  if (launch_split_bf16(A, a_hi, a_lo, static_cast<long long>(M) * K, s) ||
+      launch_split_bf16(Bt, b_hi, b_lo, static_cast<long long>(N) * K, s))
+    return fail(h, 81, "gemm_nt: split_bf16 launch failed%s");
+  EncodeGemmArgs g;
+  g.A_hi = a_hi;
+  g.A_lo = a_lo;
+  g.B_hi = b_hi;
+  g.B_lo = b_lo;
+  g.nterms = nterms;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.bias = bias;
+  g.epilogue = 1;
+  g.nsplit = 0;
+  g.num_sms = h->num_sms;
+  g.out = out;
+  g.ldo = N;
+  if (int rc = launch_encode_gemm(g, s)) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d", rc);
+    return fail(h, 82, "gemm_nt: launch failed (code %s)", buf);
+  }
+  return check_cuda(h, "gemm_nt");
+}
+
+// ---------------------------------------------------------------------------------------------
+// pinned staging ring
+// ---------------------------------------------------------------------------------------------
+struct saev_b200_ring {
+  int n_slots = 0;
+  size_t slot_bytes = 0;
+  void** host = nullptr;
+  cudaEvent_t* done = nullptr;
+  cudaStream_t copy_stream = nullptr;
+};
+
+int saev_b200_ring_create(int32_t n_slots, size_t slot_bytes, saev_b200_ring** out) {
+  if (!out || n_slots <= 0 || slot_bytes == 0) return fail(nullptr, 90, "ring_create: bad arguments%s");
+  saev_b200_ring* r = new (std::nothrow) saev_b200_ring();
+  if (!r) return fail(nullptr, 91, "ring_create: out of host memory%s");
+  r->n_slots = n_slots;
+  r->slot_bytes = slot_bytes;
+  r->host = new void*[n_slots]();
+  r->done = new cudaEvent_t[n_slots]();
+  if (cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    saev_b200_ring_destroy(r);
+    return fail(nullptr, 92, "ring_create: cudaStreamCreate failed%s");
+  }
+  for (int i = 0; i < n_slots; ++i) {
+    if (cudaHostAlloc(&r->host[i], slot_bytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->done[i], cudaEventDisableTiming) != cudaSuccess) {
+      saev_b200_ring_destroy(r);
+      return fail(nullptr, 93, "ring_create: pinned allocation failed%s");
+    }
+  }
+  *out = r;
+  return 0;
+}
+
+int saev_b200_ring_destroy(saev_b200_ring* r) {
+  if (!r) return 0;
+  if (r->copy_stream) cudaStreamSynchronize(r->copy_stream);
+  for (int i = 0; i < r->n_slots; ++i) {
+    if (r->host && r->host[i]) cudaFreeHost(r->host[i]);
+    if (r->done && r->done[i]) cudaEventDestroy(r->done[i]);
+  }
+  if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+  delete[] r->host;
+  delete[] r->done;
+  delete r;
+  return 0;
+}
+
+void* saev_b200_ring_host_ptr(saev_b200_ring* r, int32_t slot) {
+  return (r && slot >= 0 && slot < r->n_slots) ? r->host[slot] : nullptr;
+}
+
+int saev_b200_ring_submit(saev_b200_ring* r, int32_t slot, void* dst_device, size_t bytes) {
+  if (!r || slot < 0 || slot >= r->n_slots || bytes > r->slot_bytes)
+    return fail(nullptr, 94, "ring_submit: bad arguments%s");
+  if (cudaMemcpyAsync(dst_device, r->host[slot], bytes, cudaMemcpyHostToDevice, r->copy_stream) != cudaSuccess ||
+      cudaEventRecord(r->done[slot], r->copy_stream) != cudaSuccess)
+    return fail(nullptr, 95, "ring_submit: cudaMemcpyAsync failed%s");
+  return 0;
+}
+
+int saev_b200_ring_wait(saev_b200_ring* r, int32_t slot, void* consumer_stream) {
+  if (!r || slot < 0 || slot >= r->n_slots) return fail(nullptr, 94, "ring_wait: bad arguments%s");
+  if (cudaStreamWaitEvent(static_cast<cudaStream_t>(consumer_stream), r->done[slot], 0) != cudaSuccess)
+    return fail(nullptr, 96, "ring_wait: cudaStreamWaitEvent failed%s");
+  return 0;
+}
+
+int saev_b200_ring_host_sync(saev_b200_ring* r, int32_t slot) {
+  if (!r || slot < 0 || slot >= r->n_slots) return fail(nullptr, 94, "ring_host_sync: bad arguments%s");
+  if (cudaEventSynchronize(r->done[slot]) != cudaSuccess)
+    return fail(nullptr, 97, "ring_host_sync: cudaEventSynchronize failed%s");
+  return 0;
+}
+
+}  // extern "C"

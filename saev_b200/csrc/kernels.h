@@ -1,0 +1,127 @@
+// Internal launcher declarations shared by the .cu files of libsaev_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int ENCODE_MAX_NSPLIT = 8;
+
+// ---- encode_gemm.cu -------------------------------------------------------------------------------------
+struct EncodeGemmArgs {
+  const __nv_bfloat16* A_hi = nullptr;  // [M, K] row-major (K contiguous)
+  const __nv_bfloat16* A_lo = nullptr;  // residual part, nterms == 3 only
+  const __nv_bfloat16* B_hi = nullptr;  // [N, K] row-major (K contiguous)
+  const __nv_bfloat16* B_lo = nullptr;
+  int nterms = 1;                       // 1: A_hi.B_hi    3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;          // [N] or null
+  const int* n_limit_dev = nullptr;     // optional device-side column count (<= N)
+  int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store
+  int kp = 40;                          // candidate list length (epilogue 0)
+  int nsplit = 1;                       // column splits (epilogue 0: lists are [M, nsplit, kp])
+  int num_sms = 148;
+  float* cand_val = nullptr;
+  int* cand_idx = nullptr;
+  float* out = nullptr;                 // epilogue 1: [M, ldo]
+  long long ldo = 0;
+};
+int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream);
+int encode_gemm_nsplit(int M, int N, int num_sms);
+int encode_gemm_kp(int top_k);  // candidate list length for a given k, or -1 if unsupported
+
+// ---- sparse_kernels.cu ----------------------------------------------------------------------------------
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s);
+int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
+
+struct RescoreArgs {
+  const float* cand_val; const int* cand_idx; int nsplit; int kp;
+  const float* x; const float* W_enc_t; const float* b_enc;
+  int B, D, S, K;
+  int* topk_idx; float* topk_val;
+  int* feat_count;      // [S] += 1 per selected (b, j)   (may be null: eval)
+  int* active;          // [S] = 1 where a non-zero activation was selected (may be null)
+  unsigned int* unsafe_rows;  // diagnostic counter
+};
+int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s);
+
+struct DecodeArgs {
+  const float* x; const int* topk_idx; const float* topk_val;
+  const float* W_dec; const float* b_dec;
+  int B, D, K;
+  float grad_scale;     // 2 / (B_global * D)
+  float l1_over_b;      // l1_coeff / B_global (0 => NoSparsity)
+  float* resid;         // [B, D]  x_hat - x
+  float* dh;            // [B, K]  d loss / d h on the active set (null: eval, skip)
+  float* row_sse; float* row_l1; float* row_l0;  // [B]
+};
+int launch_decode(const DecodeArgs& a, cudaStream_t s);
+
+int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
+                     int* entries, cudaStream_t s);
+
+struct WgradArgs {
+  const int* feat_off; const int* entries; const float* topk_val; const float* dh;
+  const float* resid; const float* x; const float* W_dec;
+  int B, D, S, K;
+  float grad_scale; int remove_parallel;
+  float* gW_enc_t; float* gb_enc; float* gW_dec;
+};
+int launch_wgrad(const WgradArgs& a, cudaStream_t s);
+
+// gb_dec[d] (+)= scale * sum_b src[b, d]
+int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
+                  cudaStream_t s);
+int colsum_partial_rows(int B);
+
+int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);
+
+struct AdamArgs {
+  float* W_enc_t; float* b_enc; float* W_dec; float* b_dec;
+  const float* gW_enc_t; const float* gb_enc; const float* gW_dec; const float* gb_dec;
+  float* m; float* v;          // flat, same order/offsets as the gradient bucket
+  __nv_bfloat16* shadow_hi;    // bf16 copy of W_enc_t for the tensor-core screen (may be null)
+  int D, S;
+  float lr, beta1, beta2, eps, bc1, bc2_sqrt;
+  float max_norm; float grad_scale; const float* gnorm_sq;
+  int renorm_w_dec;
+  float* gnorm_out;            // optional: clipped-from norm (what clip_grad_norm_ returns)
+};
+int launch_adam(const AdamArgs& a, cudaStream_t s);
+
+struct FinalizeArgs {
+  const float* row_sse; const float* row_l1; const float* row_l0; int B; int D;
+  double inv_bd; double inv_b; float l1_coeff;
+  const float* aux_loss;   // device scalar or null
+  const int* n_dead;       // device scalar or null
+  float* losses;           // [8]: mse, aux, sparsity, l0, l1, n_dead, loss, reserved
+};
+int launch_finalize(const FinalizeArgs& a, cudaStream_t s);
+
+int launch_dead_update(long long* toks, int* active, int S, long long batch_tokens, long long threshold,
+                       int* dead_list, int* n_dead, cudaStream_t s);
+
+int launch_densify(const int* idx, const float* val, int B, int K, int S, float* out, cudaStream_t s);
+int launch_add_rows(const float* a, const float* b, long long n, float* out, cudaStream_t s);  // out = a + b
+
+// ---- aux_kernels.cu -------------------------------------------------------------------------------------
+struct AuxArgs {
+  const float* x; const float* resid; const float* W_enc_t; const float* b_enc; const float* W_dec;
+  const float* b_dec;
+  const int* dead_list; const int* n_dead;
+  int B, D, S, k_aux; float alpha; float inv_bd;   // inv_bd = 1 / (B_global * D)
+  int remove_parallel;
+  float* h_aux;            // [B, S] scratch: pre-acts of dead latents -> f_aux -> dh_aux
+  unsigned char* mask_aux; // [B, S] scratch
+  float* r_aux;            // [B, D] scratch: x_hat_aux - e, then G_aux
+  float* row_sse_aux;      // [B]
+  float* aux_loss;         // device scalar out
+  float* gW_enc_t; float* gb_enc; float* gW_dec;   // rows of dead latents are (over)written
+  float* colsum_partial; float* gb_dec;            // gb_dec += sum_b G_aux
+};
+int launch_aux_forward(const AuxArgs& a, cudaStream_t s);
+int launch_aux_backward(const AuxArgs& a, cudaStream_t s);
+
+}  // namespace sb

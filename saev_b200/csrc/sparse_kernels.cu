@@ -1,0 +1,831 @@
+// HBM/L2-bound kernels of the SAE training step (everything except the tensor-core contraction).
+//
+// Layout conventions (all fp32, row-major):
+//   x[B,D]  W_enc_t[S,D] (= saev's W_enc[D,S] transposed: one dictionary atom per row)  b_enc[S]
+//   W_dec[S,D]  b_dec[D]  topk_idx/topk_val/dh[B,K]  resid[B,D]
+// Keeping both weight matrices atom-major makes every sparse access a contiguous D-float row:
+// decode gathers K rows of W_dec per sample, the weight gradients are per-atom segmented sums of
+// rows of resid / x, Adam + decoder renorm is a per-row pass.
+//
+// Row-per-warp kernels keep a whole D-vector in registers: lane l owns float4 vectors l, l+32, ...,
+// VPL of them (VPL = ceil(D/128), D <= 2048).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+#define SB_DISPATCH_VPL(D, CALL)                                         \
+  do {                                                                   \
+    const int need_ = ((D) + 127) / 128;                                 \
+    if (need_ <= 1) { constexpr int VPL = 1; CALL; }                     \
+    else if (need_ <= 2) { constexpr int VPL = 2; CALL; }                \
+    else if (need_ <= 4) { constexpr int VPL = 4; CALL; }                \
+    else if (need_ <= 6) { constexpr int VPL = 6; CALL; }                \
+    else if (need_ <= 8) { constexpr int VPL = 8; CALL; }                \
+    else if (need_ <= 12) { constexpr int VPL = 12; CALL; }              \
+    else if (need_ <= 16) { constexpr int VPL = 16; CALL; }              \
+    else return 20;                                                      \
+  } while (0)
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
+  acc.x = fmaf(s, v.x, acc.x);
+  acc.y = fmaf(s, v.y, acc.y);
+  acc.z = fmaf(s, v.z, acc.z);
+  acc.w = fmaf(s, v.w, acc.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 (hi) [+ bf16 residual (lo)]   (operand prep for the tensor-core screen)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldg4(src + 4 * i);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(hi + 4 * i);
+    ho[0] = __nv_bfloat162(h0, h1);
+    ho[1] = __nv_bfloat162(h2, h3);
+    if (lo != nullptr) {
+      __nv_bfloat162* lo2 = reinterpret_cast<__nv_bfloat162*>(lo + 4 * i);
+      lo2[0] = __nv_bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)),
+                              __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+      lo2[1] = __nv_bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)),
+                              __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+    }
+  }
+}
+
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (n % 4) return 21;
+  const long long n4 = n / 4;
+  const int threads = 256;
+  long long want = (n4 + threads - 1) / threads;
+  const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
+  split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, n4);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// W[j,:] /= ||W[j,:]||_2      (saev modeling.py:411-417 normalize_w_dec)
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(float* __restrict__ W, int rows, int D) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= rows) return;
+  const int lane = threadIdx.x & 31, D4 = D >> 2;
+  float* row = W + static_cast<long long>(j) * D;
+  float4 w[VPL];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    w[i] = (v < D4) ? *reinterpret_cast<const float4*>(row + 4 * v) : make_float4(0, 0, 0, 0);
+    ss += dot4(w[i], w[i]);
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) {
+      float4 o = w[i];
+      o.x /= nrm; o.y /= nrm; o.z /= nrm; o.w /= nrm;
+      *reinterpret_cast<float4*>(row + 4 * v) = o;
+    }
+  }
+}
+
+int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s) {
+  if (cols % 4) return 21;
+  SB_DISPATCH_VPL(cols, (normalize_rows_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(W, rows, cols)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merge the per-split candidate lists of a row, recompute the exact fp32 pre-activation of each
+// candidate (h = <x_b, W_enc_t[j]> + b_enc[j], saev modeling.py:344-347) and select the top-k of
+// those (TopKActivation.forward, modeling.py:169-179: no ReLU, exactly k kept).  One warp per row.
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= a.B) return;
+  const int KP = a.kp, ncand = a.nsplit * a.kp, D4 = a.D >> 2;
+  float* base = smem_f + static_cast<size_t>(warp) * (2 * ncand + 3 * KP);
+  float* sv = base;
+  int* si = reinterpret_cast<int*>(base + ncand);
+  float* kv = base + 2 * ncand;
+  int* ki = reinterpret_cast<int*>(base + 2 * ncand + KP);
+  float* ke = base + 2 * ncand + 2 * KP;
+
+  const long long cbase = static_cast<long long>(b) * ncand;
+  for (int s = lane; s < ncand; s += 32) {
+    sv[s] = a.cand_val[cbase + s];
+    si[s] = a.cand_idx[cbase + s];
+  }
+  __syncwarp();
+  if (a.nsplit == 1) {
+    for (int s = lane; s < KP; s += 32) {
+      kv[s] = sv[s];
+      ki[s] = si[s];
+    }
+  } else {
+    for (int s = lane; s < ncand; s += 32) {
+      const float v = sv[s];
+      int rank = 0;
+      for (int t = 0; t < ncand; ++t) {
+        const float vt = sv[t];
+        rank += (vt > v) || (vt == v && t < s);
+      }
+      if (rank < KP) {
+        kv[rank] = v;
+        ki[rank] = si[s];
+      }
+    }
+  }
+  __syncwarp();
+
+  // exact rescoring, 4 candidates in flight
+  float4 xr[VPL];
+  const float* xrow = a.x + static_cast<long long>(b) * a.D;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
+  }
+  for (int c0 = 0; c0 < KP; c0 += 4) {
+    int j[4];
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      j[u] = (c0 + u < KP) ? ki[c0 + u] : -1;
+      acc[u] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) {
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          w[u] = (j[u] >= 0) ? ldg4(a.W_enc_t + static_cast<long long>(j[u]) * a.D + 4 * v) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += dot4(xr[i], w[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float tot = warp_sum(acc[u]);
+      if (lane == 0 && c0 + u < KP) ke[c0 + u] = (j[u] >= 0) ? tot + __ldg(a.b_enc + j[u]) : -INFINITY;
+    }
+  }
+  __syncwarp();
+
+  // final selection on exact values; order: value desc, then feature index asc, then position
+  float err = 0.f;
+  float vk = -INFINITY;
+  for (int c = lane; c < ((KP + 31) & ~31); c += 32) {
+    const bool valid = c < KP;
+    const float v = valid ? ke[c] : -INFINITY;
+    const int id = valid ? ki[c] : -1;
+    int rank = 0;
+    if (valid) {
+      for (int t = 0; t < KP; ++t) {
+        const float vt = ke[t];
+        const int it = ki[t];
+        rank += (vt > v) || (vt == v && (it < id || (it == id && t < c)));
+      }
+      if (id >= 0) err = fmaxf(err, fabsf(kv[c] - v));
+      if (rank < a.K && id >= 0) {
+        const long long o = static_cast<long long>(b) * a.K + rank;
+        a.topk_idx[o] = id;
+        a.topk_val[o] = v;
+        if (a.feat_count) atomicAdd(a.feat_count + id, 1);
+        if (a.active && v != 0.f) a.active[id] = 1;
+      }
+    }
+    const unsigned hit = __ballot_sync(FULL, valid && rank == a.K - 1);
+    if (hit) vk = __shfl_sync(FULL, v, __ffs(hit) - 1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL, err, o));
+  if (lane == 0 && a.unsafe_rows != nullptr && ki[KP - 1] >= 0) {
+    // every column outside the list has screen value <= kv[KP-1]; flag the row when the k-th exact
+    // value is not clear of that by several times the largest screen error seen on this row
+    if (vk - kv[KP - 1] < 4.f * err) atomicAdd(a.unsafe_rows, 1u);
+  }
+}
+
+int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
+  if (a.D % 4) return 21;
+  const size_t smem = static_cast<size_t>(4) * (2 * a.nsplit * a.kp + 3 * a.kp) * 4;
+  SB_DISPATCH_VPL(a.D, (rescore_topk_kernel<VPL><<<(a.B + 3) / 4, 128, smem, s>>>(a)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse decode + residual + MSE partials (+ d loss / d h on the active set).  One warp per row.
+//   x_hat = sum_k f_k W_dec[j_k] + b_dec          (saev modeling.py:386-406, single prefix)
+//   r = x_hat - x ; row_sse = sum r^2             (objectives.py:133-138, 224-237)
+//   dh_k = grad_scale * <r, W_dec[j_k]> (+ l1/B * sign(f_k))   (autograd of the above)
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= a.B) return;
+  const int D4 = a.D >> 2, K = a.K;
+  float4 acc[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    acc[i] = (v < D4) ? ldg4(a.b_dec + 4 * v) : make_float4(0, 0, 0, 0);
+  }
+  const long long kb = static_cast<long long>(b) * K;
+  float l1 = 0.f, l0 = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int kk = k0 + lane;
+    const int mj = (kk < K) ? a.topk_idx[kb + kk] : -1;
+    const float mf = (kk < K) ? a.topk_val[kb + kk] : 0.f;
+    if (kk < K && mj >= 0) {
+      l1 += fabsf(mf);
+      l0 += (mf != 0.f) ? 1.f : 0.f;
+    }
+    const int cnt = min(32, K - k0);
+#pragma unroll 4
+    for (int t = 0; t < cnt; ++t) {
+      const int j = __shfl_sync(FULL, mj, t);
+      const float f = __shfl_sync(FULL, mf, t);
+      if (j < 0) continue;
+      const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < D4) fma4(acc[i], f, ldg4(wrow + 4 * v));
+      }
+    }
+  }
+  const float* xrow = a.x + static_cast<long long>(b) * a.D;
+  float* rrow = a.resid + static_cast<long long>(b) * a.D;
+  float sse = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) {
+      const float4 xv = ldg4(xrow + 4 * v);
+      float4 r = acc[i];
+      r.x -= xv.x; r.y -= xv.y; r.z -= xv.z; r.w -= xv.w;
+      acc[i] = r;
+      *reinterpret_cast<float4*>(rrow + 4 * v) = r;
+      sse += dot4(r, r);
+    } else {
+      acc[i] = make_float4(0, 0, 0, 0);
+    }
+  }
+  sse = warp_sum(sse);
+  l1 = warp_sum(l1);
+  l0 = warp_sum(l0);
+  if (lane == 0) {
+    a.row_sse[b] = sse;
+    a.row_l1[b] = l1;
+    a.row_l0[b] = l0;
+  }
+  if (a.dh == nullptr) return;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int kk = k0 + lane;
+    const int mj = (kk < K) ? a.topk_idx[kb + kk] : -1;
+    const float mf = (kk < K) ? a.topk_val[kb + kk] : 0.f;
+    float mine = 0.f;
+    const int cnt = min(32, K - k0);
+#pragma unroll 2
+    for (int t = 0; t < cnt; ++t) {
+      const int j = __shfl_sync(FULL, mj, t);
+      float p = 0.f;
+      if (j >= 0) {
+        const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < D4) p += dot4(acc[i], ldg4(wrow + 4 * v));
+        }
+      }
+      p = warp_sum(p);
+      if (lane == t) mine = p;
+    }
+    if (kk < K) {
+      float d = a.grad_scale * mine;
+      if (a.l1_over_b != 0.f) d += a.l1_over_b * ((mf > 0.f) ? 1.f : ((mf < 0.f) ? -1.f : 0.f));
+      a.dh[kb + kk] = (mj >= 0) ? d : 0.f;
+    }
+  }
+}
+
+int launch_decode(const DecodeArgs& a, cudaStream_t s) {
+  if (a.D % 4) return 21;
+  SB_DISPATCH_VPL(a.D, (decode_kernel<VPL><<<(a.B + 7) / 8, 256, 0, s>>>(a)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSC of the active set: for every dictionary atom j the list of (b, k) slots where it fired.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ cnt, int* __restrict__ off,
+                                                           int* __restrict__ cursor, int S) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < S; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int c = (i < S) ? cnt[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;  // inclusive scan of warp totals
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl - c;
+    if (i < S) {
+      off[i] = excl;
+      cursor[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[S] = carry_s;
+}
+
+__global__ void csc_fill_kernel(const int* __restrict__ idx, long long n, const int* __restrict__ off,
+                                int* __restrict__ cursor, int* __restrict__ entries) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int j = idx[p];
+  if (j < 0) return;
+  const int pos = off[j] + atomicAdd(cursor + j, 1);
+  entries[pos] = static_cast<int>(p);
+}
+
+int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
+                     int* entries, cudaStream_t s) {
+  scan_counts_kernel<<<1, 1024, 0, s>>>(feat_count, feat_off, cursor, S);
+  const long long n = static_cast<long long>(B) * K;
+  csc_fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(topk_idx, n, feat_off, cursor, entries);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradients of the sparse path, one warp per dictionary atom j (autograd of decode/encode):
+//   gW_dec[j]   = grad_scale * sum_{(b,k): idx=j} f_bk * r_b      then minus its component along W_dec[j]
+//                 (saev modeling.py:419-445 remove_parallel_grads)
+//   gW_enc_t[j] = sum dh_bk * x_b ;  gb_enc[j] = sum dh_bk
+// Atoms that did not fire get zero rows (the dense .grad tensors saev's loop expects).
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= a.S) return;
+  const int D4 = a.D >> 2;
+  const int beg = a.feat_off[j], end = a.feat_off[j + 1];
+  float4 gd[VPL], ge[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
+  float sdh = 0.f;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    int mb = 0;
+    float mf = 0.f, md = 0.f;
+    if (e < end) {
+      const int p = a.entries[e];
+      mb = p / a.K;
+      mf = a.topk_val[p];
+      md = a.dh[p];
+      sdh += md;
+    }
+    const int cnt = min(32, end - e0);
+#pragma unroll 2
+    for (int t = 0; t < cnt; ++t) {
+      const int bb = __shfl_sync(FULL, mb, t);
+      const float f = __shfl_sync(FULL, mf, t);
+      const float d = __shfl_sync(FULL, md, t);
+      const float* rrow = a.resid + static_cast<long long>(bb) * a.D;
+      const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < D4) {
+          fma4(gd[i], f, ldg4(rrow + 4 * v));
+          fma4(ge[i], d, ldg4(xrow + 4 * v));
+        }
+      }
+    }
+  }
+  sdh = warp_sum(sdh);
+  float* gdrow = a.gW_dec + static_cast<long long>(j) * a.D;
+  float* gerow = a.gW_enc_t + static_cast<long long>(j) * a.D;
+  if (beg == end) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) {
+        *reinterpret_cast<float4*>(gdrow + 4 * v) = make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(gerow + 4 * v) = make_float4(0, 0, 0, 0);
+      }
+    }
+    if (lane == 0) a.gb_enc[j] = 0.f;
+    return;
+  }
+  const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+  float4 w[VPL];
+  float dot = 0.f, nsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    gd[i].x *= a.grad_scale; gd[i].y *= a.grad_scale; gd[i].z *= a.grad_scale; gd[i].w *= a.grad_scale;
+    w[i] = (v < D4) ? ldg4(wrow + 4 * v) : make_float4(0, 0, 0, 0);
+    dot += dot4(gd[i], w[i]);
+    nsq += dot4(w[i], w[i]);
+  }
+  if (a.remove_parallel) {
+    dot = warp_sum(dot);
+    nsq = warp_sum(nsq);
+    const float sc = (nsq > 0.f) ? dot / nsq : 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) fma4(gd[i], -sc, w[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) {
+      *reinterpret_cast<float4*>(gdrow + 4 * v) = gd[i];
+      *reinterpret_cast<float4*>(gerow + 4 * v) = ge[i];
+    }
+  }
+  if (lane == 0) a.gb_enc[j] = sdh;
+}
+
+int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
+  if (a.D % 4) return 21;
+  SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[d] (+)= scale * sum_b src[b,d]     (gb_dec; two deterministic stages)
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_ROWS_PER_BLOCK = 64;
+int colsum_partial_rows(int B) { return (B + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK; }
+
+__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ src, int B, int D,
+                                                     float* __restrict__ partial) {
+  const int r0 = blockIdx.x * COLSUM_ROWS_PER_BLOCK;
+  const int r1 = min(B, r0 + COLSUM_ROWS_PER_BLOCK);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += __ldg(src + static_cast<long long>(r) * D + d);
+    partial[static_cast<long long>(blockIdx.x) * D + d] = s;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ partial, int P, int D, float scale,
+                                                     int accumulate, float* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  for (int p = 0; p < P; ++p) s += partial[static_cast<long long>(p) * D + d];
+  const float r = static_cast<float>(s) * scale;
+  out[d] = accumulate ? out[d] + r : r;
+}
+
+int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
+                  cudaStream_t s) {
+  const int P = colsum_partial_rows(B);
+  colsum_stage1<<<P, 256, 0, s>>>(src, B, D, partial);
+  colsum_stage2<<<(D + 255) / 256, 256, 0, s>>>(partial, P, D, scale, accumulate, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum of squares of a flat fp32 buffer (global gradient norm, saev train.py:358-360), deterministic
+// ------------------------------------------------------------------------------------------------
+constexpr int SUMSQ_BLOCKS = 592;  // 4 x 148
+__global__ void __launch_bounds__(256) sumsq_stage1(const float* __restrict__ g, long long n, double* partial) {
+  __shared__ double ws[8];
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  float acc = 0.f;
+  double dacc = 0.0;
+  int since = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldg4(g + 4 * i);
+    acc += dot4(v, v);
+    if (++since == 64) {  // bound fp32 accumulation length
+      dacc += acc;
+      acc = 0.f;
+      since = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
+  dacc += acc;
+  dacc = warp_sum(dacc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = dacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_stage2(const double* partial, int n, float* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partial[i];
+    *out = static_cast<float>(t);
+  }
+}
+int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s) {
+  sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, partial);
+  sumsq_stage2<<<1, 32, 0, s>>>(partial, SUMSQ_BLOCKS, out_sumsq);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// clip-scale + Adam + decoder row renorm + bf16 shadow of W_enc_t, one warp per dictionary atom.
+//   c = min(1, max_norm / (grad_scale*||g|| + 1e-6))                 (saev train.py:358-360)
+//   m += (g-m)(1-b1); v = b2 v + (1-b2) g^2; p -= (lr/bc1) m / (sqrt(v)/sqrt(bc2) + eps)
+//                                                                    (torch Adam(fused=True), train.py:294,444-446)
+//   W_dec[j] /= ||W_dec[j]||  when renorm_w_dec                      (modeling.py:411-417, hoisted from the
+//                                                                     start of the next step: nothing reads
+//                                                                     W_dec in between)
+// ------------------------------------------------------------------------------------------------
+struct AdamScalars {
+  float lr_over_bc1, beta1, beta2, eps, inv_bc2_sqrt, gmul;
+};
+__device__ __forceinline__ AdamScalars adam_scalars(const AdamArgs& a) {
+  AdamScalars s;
+  const float gn = a.grad_scale * sqrtf(*a.gnorm_sq);
+  const float c = fminf(1.f, a.max_norm / (gn + 1e-6f));
+  s.gmul = (a.max_norm > 0.f ? c : 1.f) * a.grad_scale;
+  s.lr_over_bc1 = a.lr / a.bc1;
+  s.beta1 = a.beta1;
+  s.beta2 = a.beta2;
+  s.eps = a.eps;
+  s.inv_bc2_sqrt = 1.f / a.bc2_sqrt;
+  return s;
+}
+__device__ __forceinline__ float adam_1(float p, float g, float& m, float& v, const AdamScalars& s) {
+  g *= s.gmul;
+  m = m + (g - m) * (1.f - s.beta1);
+  v = v * s.beta2 + (1.f - s.beta2) * g * g;
+  const float denom = sqrtf(v) * s.inv_bc2_sqrt + s.eps;
+  return p - s.lr_over_bc1 * (m / denom);
+}
+__device__ __forceinline__ float4 adam_4(float4 p, float4 g, float4& m, float4& v, const AdamScalars& s) {
+  float4 o;
+  o.x = adam_1(p.x, g.x, m.x, v.x, s);
+  o.y = adam_1(p.y, g.y, m.y, v.y, s);
+  o.z = adam_1(p.z, g.z, m.z, v.z, s);
+  o.w = adam_1(p.w, g.w, m.w, v.w, s);
+  return o;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= a.S) return;
+  const AdamScalars sc = adam_scalars(a);
+  const int D4 = a.D >> 2;
+  const long long SD = static_cast<long long>(a.S) * a.D;
+  const long long ro = static_cast<long long>(j) * a.D;
+  // ---- W_enc_t row (+ bf16 shadow) ----
+  {
+    float* mrow = a.m + ro;
+    float* vrow = a.v + ro;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v4 = lane + 32 * i;
+      if (v4 < D4) {
+        const float4 g = ldg4(a.gW_enc_t + ro + 4 * v4);
+        float4 m = *reinterpret_cast<const float4*>(mrow + 4 * v4);
+        float4 v = *reinterpret_cast<const float4*>(vrow + 4 * v4);
+        const float4 p = adam_4(*reinterpret_cast<const float4*>(a.W_enc_t + ro + 4 * v4), g, m, v, sc);
+        *reinterpret_cast<float4*>(a.W_enc_t + ro + 4 * v4) = p;
+        *reinterpret_cast<float4*>(mrow + 4 * v4) = m;
+        *reinterpret_cast<float4*>(vrow + 4 * v4) = v;
+        if (a.shadow_hi != nullptr) {
+          __nv_bfloat162* so = reinterpret_cast<__nv_bfloat162*>(a.shadow_hi + ro + 4 * v4);
+          so[0] = __nv_bfloat162(__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y));
+          so[1] = __nv_bfloat162(__float2bfloat16_rn(p.z), __float2bfloat16_rn(p.w));
+        }
+      }
+    }
+  }
+  // ---- b_enc[j] ----
+  if (lane == 0) {
+    float m = a.m[SD + j], v = a.v[SD + j];
+    a.b_enc[j] = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+    a.m[SD + j] = m;
+    a.v[SD + j] = v;
+  }
+  // ---- W_dec row (+ renorm) ----
+  {
+    float* mrow = a.m + SD + a.S + ro;
+    float* vrow = a.v + SD + a.S + ro;
+    float4 p[VPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v4 = lane + 32 * i;
+      p[i] = make_float4(0, 0, 0, 0);
+      if (v4 < D4) {
+        const float4 g = ldg4(a.gW_dec + ro + 4 * v4);
+        float4 m = *reinterpret_cast<const float4*>(mrow + 4 * v4);
+        float4 v = *reinterpret_cast<const float4*>(vrow + 4 * v4);
+        p[i] = adam_4(*reinterpret_cast<const float4*>(a.W_dec + ro + 4 * v4), g, m, v, sc);
+        *reinterpret_cast<float4*>(mrow + 4 * v4) = m;
+        *reinterpret_cast<float4*>(vrow + 4 * v4) = v;
+        ss += dot4(p[i], p[i]);
+      }
+    }
+    if (a.renorm_w_dec) {
+      ss = warp_sum(ss);
+      const float nrm = sqrtf(ss);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        p[i].x /= nrm; p[i].y /= nrm; p[i].z /= nrm; p[i].w /= nrm;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v4 = lane + 32 * i;
+      if (v4 < D4) *reinterpret_cast<float4*>(a.W_dec + ro + 4 * v4) = p[i];
+    }
+  }
+}
+
+__global__ void adam_bdec_kernel(AdamArgs a) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const AdamScalars sc = adam_scalars(a);
+  if (d == 0 && a.gnorm_out != nullptr) *a.gnorm_out = a.grad_scale * sqrtf(*a.gnorm_sq);
+  if (d >= a.D) return;
+  const long long o = 2LL * a.S * a.D + a.S + d;
+  float m = a.m[o], v = a.v[o];
+  a.b_dec[d] = adam_1(a.b_dec[d], a.gb_dec[d], m, v, sc);
+  a.m[o] = m;
+  a.v[o] = v;
+}
+
+int launch_adam(const AdamArgs& a, cudaStream_t s) {
+  if (a.D % 4 || a.S % 4) return 21;
+  SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
+  adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss scalars (saev objectives.py:133-156): mse, aux, sparsity, l0, l1, n_dead, loss
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
+  __shared__ double s0[32], s1[32], s2[32];
+  double sse = 0.0, l1 = 0.0, l0 = 0.0;
+  for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+    sse += a.row_sse[b];
+    l1 += a.row_l1[b];
+    l0 += a.row_l0[b];
+  }
+  sse = warp_sum(sse);
+  l1 = warp_sum(l1);
+  l0 = warp_sum(l0);
+  if ((threadIdx.x & 31) == 0) {
+    s0[threadIdx.x >> 5] = sse;
+    s1[threadIdx.x >> 5] = l1;
+    s2[threadIdx.x >> 5] = l0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sse = l1 = l0 = 0.0;
+    for (int w = 0; w < 32; ++w) {
+      sse += s0[w];
+      l1 += s1[w];
+      l0 += s2[w];
+    }
+    const float mse = static_cast<float>(sse * a.inv_bd);
+    const float l1m = static_cast<float>(l1 * a.inv_b);
+    const float aux = a.aux_loss ? *a.aux_loss : 0.f;
+    const float sp = a.l1_coeff * l1m;
+    a.losses[0] = mse;
+    a.losses[1] = aux;
+    a.losses[2] = sp;
+    a.losses[3] = static_cast<float>(l0 * a.inv_b);
+    a.losses[4] = l1m;
+    a.losses[5] = a.n_dead ? static_cast<float>(*a.n_dead) : 0.f;
+    a.losses[6] = mse + sp + aux;
+    a.losses[7] = 0.f;
+  }
+}
+int launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
+  finalize_kernel<<<1, 1024, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dead-latent tracker (saev objectives.py:107-120): toks += tokens; toks[active] = 0;
+// dead = toks >= threshold; emits the ascending list of dead atoms and its length; clears `active`.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) dead_update_kernel(long long* __restrict__ toks, int* __restrict__ active,
+                                                           int S, long long batch_tokens, long long threshold,
+                                                           int* __restrict__ dead_list, int* __restrict__ n_dead) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < S; base += 1024) {
+    const int i = base + threadIdx.x;
+    int dead = 0;
+    if (i < S) {
+      const long long t = active[i] ? 0 : toks[i] + batch_tokens;
+      toks[i] = t;
+      active[i] = 0;
+      dead = t >= threshold;
+    }
+    const unsigned bal = __ballot_sync(FULL, dead);
+    const int incl_w = __popc(bal & (0xffffffffu >> (31 - lane)));
+    if (lane == 31) warp_tot[warp] = incl_w;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (dead) dead_list[carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl_w - 1] = i;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_dead = carry_s;
+}
+int launch_dead_update(long long* toks, int* active, int S, long long batch_tokens, long long threshold,
+                       int* dead_list, int* n_dead, cudaStream_t s) {
+  dead_update_kernel<<<1, 1024, 0, s>>>(toks, active, S, batch_tokens, threshold, dead_list, n_dead);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lazy materialisation of the dense tensors saev's logging block reads (train.py:365-442)
+// ------------------------------------------------------------------------------------------------
+__global__ void densify_kernel(const int* __restrict__ idx, const float* __restrict__ val, long long n, int K, int S,
+                               float* __restrict__ out) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int j = idx[p];
+  if (j >= 0) out[(p / K) * S + j] = val[p];
+}
+int launch_densify(const int* idx, const float* val, int B, int K, int S, float* out, cudaStream_t s) {
+  if (cudaMemsetAsync(out, 0, static_cast<size_t>(B) * S * 4, s) != cudaSuccess) return 23;
+  const long long n = static_cast<long long>(B) * K;
+  densify_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(idx, val, n, K, S, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                           float* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = a[i] + b[i];
+}
+int launch_add_rows(const float* a, const float* b, long long n, float* out, cudaStream_t s) {
+  add_kernel<<<148 * 8, 256, 0, s>>>(a, b, n, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+}  // namespace sb

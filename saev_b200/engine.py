@@ -1,0 +1,247 @@
+"""Device-side state + launch sequencing for one SAE on one B200.
+
+`Engine` owns the flat parameter / gradient / Adam-moment buffers (order
+[W_enc_t (S*D), b_enc (S), W_dec (S*D), b_dec (D)], see include/saev_b200.h), the kernel workspace and
+the library handle, and exposes the steps of saev's training loop body
+(/root/reference/src/saev/framework/train.py:332-460) as methods that only enqueue CUDA work:
+
+    normalize_w_dec -> forward -> backward -> [all-reduce] -> grad_sumsq -> adam_step
+
+PyTorch is used for memory, streams and torch.distributed only; all arithmetic happens in
+libsaev_b200.so.  There is no CPU path: constructing an Engine without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import torch
+
+from . import _lib
+
+
+@dataclasses.dataclass(frozen=True)
+class EngineConfig:
+    d_model: int
+    d_sae: int
+    top_k: int = 32
+    activation: str = "topk"  # "topk" | "relu"
+    aux: bool = True  # AuxK vs NoAux
+    k_aux: int = 512
+    aux_alpha: float = 1.0 / 32
+    l1_coeff: float = 0.0
+    dead_threshold_tokens: int = 10_000_000
+    remove_parallel_grads: bool = True
+    normalize_w_dec: bool = True
+    max_batch: int = 16384
+    aux_cols_cap: int = 0
+
+
+LOSS_KEYS = ("mse", "aux", "sparsity", "l0", "l1", "n_dead", "loss")
+
+
+class Engine:
+    def __init__(self, cfg: EngineConfig, device: torch.device | str = "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("saev_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("saev_b200.Engine only runs on CUDA devices")
+        self.lib = _lib.load()
+        S, D = cfg.d_sae, cfg.d_model
+        self.S, self.D, self.K = S, D, cfg.top_k
+        self.n_params = 2 * S * D + S + D
+        with torch.cuda.device(self.device):
+            c = _lib.Cfg(
+                d_model=D,
+                d_sae=S,
+                act_kind=_lib.ACT_TOPK if cfg.activation == "topk" else _lib.ACT_RELU,
+                top_k=cfg.top_k,
+                aux_kind=_lib.AUX_AUXK if cfg.aux else _lib.AUX_NONE,
+                k_aux=cfg.k_aux,
+                aux_alpha=cfg.aux_alpha,
+                l1_coeff=cfg.l1_coeff,
+                dead_threshold_tokens=cfg.dead_threshold_tokens,
+                remove_parallel_grads=int(cfg.remove_parallel_grads),
+                max_batch=cfg.max_batch,
+                aux_cols_cap=cfg.aux_cols_cap,
+                reserved=0,
+            )
+            h = C.c_void_p()
+            _lib.check(self.lib.saev_b200_create(C.byref(c), C.byref(h)))
+            self.h = h
+            dev = self.device
+            self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.m = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.v = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+            self.workspace = torch.empty(self.lib.saev_b200_workspace_bytes(h), dtype=torch.uint8, device=dev)
+            B, K = cfg.max_batch, cfg.top_k
+            self.topk_idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+            self.topk_val = torch.empty(B, K, dtype=torch.float32, device=dev)
+            self.resid = torch.empty(B, D, dtype=torch.float32, device=dev)
+            self.losses = torch.zeros(8, dtype=torch.float32, device=dev)
+            self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.toks_since_active = torch.zeros(S, dtype=torch.int64, device=dev)
+        self.W_enc_t, self.b_enc, self.W_dec, self.b_dec = self._views(self.params)
+        self.gW_enc_t, self.gb_enc, self.gW_dec, self.gb_dec = self._views(self.grads)
+        self.step_count = 0
+        self._last_B = 0
+
+    def _views(self, flat):
+        S, D = self.S, self.D
+        o1, o2, o3 = S * D, S * D + S, 2 * S * D + S
+        return flat[:o1].view(S, D), flat[o1:o2], flat[o2:o3].view(S, D), flat[o3:]
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and getattr(self, "lib", None) is not None:
+            self.lib.saev_b200_destroy(h)
+            self.h = None
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ck(self, rc):
+        _lib.check(rc, self.h)
+
+    def _ws_tensor(self, fn, dtype, n):
+        """Typed 1-D view of a region inside the workspace (zero-copy)."""
+        p = fn(self.h, self.workspace.data_ptr())
+        off = p - self.workspace.data_ptr()
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off : off + nbytes].view(dtype)
+
+    def active_flags(self) -> torch.Tensor:
+        return self._ws_tensor(self.lib.saev_b200_active_flags, torch.int32, self.S)
+
+    def unsafe_rows(self) -> int:
+        return int(self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 1).item())
+
+    # ---- parameters ------------------------------------------------------------------------
+    @torch.no_grad()
+    def load_params(self, W_enc, b_enc, W_dec, b_dec) -> None:
+        """Copy saev-layout parameters in (W_enc is [d_model, d_sae] as in saev; stored transposed)."""
+        self.W_enc_t.copy_(W_enc.to(self.device, torch.float32).t())
+        self.b_enc.copy_(b_enc.to(self.device, torch.float32))
+        self.W_dec.copy_(W_dec.to(self.device, torch.float32))
+        self.b_dec.copy_(b_dec.to(self.device, torch.float32))
+        self.sync_weights()
+
+    def sync_weights(self) -> None:
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_sync_weights(self.h, self.W_enc_t.data_ptr(), self.workspace.data_ptr(), self._stream())
+            )
+
+    def normalize_w_dec(self) -> None:
+        if not self.cfg.normalize_w_dec:
+            return
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_normalize_w_dec(self.h, self.W_dec.data_ptr(), self._stream()))
+
+    # ---- step pieces -------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
+        B = x.shape[0]
+        self._last_B = B
+        toks = self.toks_since_active.data_ptr() if training else None
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_forward(
+                    self.h, phase, x.data_ptr(), B, tokens_global or B,
+                    self.W_enc_t.data_ptr(), self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.b_dec.data_ptr(),
+                    toks, int(training), self.topk_idx.data_ptr(), self.topk_val.data_ptr(), self.resid.data_ptr(),
+                    self.losses.data_ptr(), self.workspace.data_ptr(), self._stream(),
+                )
+            )
+        return self.losses
+
+    def backward(self, x: torch.Tensor, *, tokens_global: int = 0) -> None:
+        B = x.shape[0]
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_backward(
+                    self.h, x.data_ptr(), B, tokens_global or B,
+                    self.W_enc_t.data_ptr(), self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.b_dec.data_ptr(),
+                    self.topk_idx.data_ptr(), self.topk_val.data_ptr(), self.resid.data_ptr(),
+                    self.gW_enc_t.data_ptr(), self.gb_enc.data_ptr(), self.gW_dec.data_ptr(), self.gb_dec.data_ptr(),
+                    self.workspace.data_ptr(), self._stream(),
+                )
+            )
+
+    def grad_sumsq(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_grad_sumsq(
+                    self.h, self.grads.data_ptr(), self.n_params, self.sumsq.data_ptr(), self.workspace.data_ptr(),
+                    self._stream(),
+                )
+            )
+        return self.sumsq
+
+    def adam_step(self, lr: float, *, max_norm: float = 1.0, grad_scale: float = 1.0, betas=(0.9, 0.999),
+                  eps: float = 1e-8, renorm_w_dec: bool = False) -> None:
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_adam_step(
+                    self.h, self.W_enc_t.data_ptr(), self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.b_dec.data_ptr(),
+                    self.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), lr, betas[0], betas[1], eps,
+                    self.step_count, max_norm, grad_scale, self.sumsq.data_ptr(), int(renorm_w_dec),
+                    self.gnorm.data_ptr(), self.workspace.data_ptr(), self._stream(),
+                )
+            )
+
+    def train_step(self, x: torch.Tensor, lr: float, *, max_norm: float = 1.0, fused_renorm: bool = False,
+                   pre_normalized: bool = False) -> torch.Tensor:
+        """One iteration of train.py:332-460 on a single GPU (no logging block)."""
+        if not pre_normalized:
+            self.normalize_w_dec()
+        self.forward(x, training=True)
+        self.backward(x)
+        self.grad_sumsq()
+        self.adam_step(lr, max_norm=max_norm, renorm_w_dec=fused_renorm and self.cfg.normalize_w_dec)
+        return self.losses
+
+    # ---- lazy dense views ------------------------------------------------------------------
+    def dense_f_x(self, B: int | None = None) -> torch.Tensor:
+        B = B or self._last_B
+        out = torch.empty(B, self.S, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_densify(
+                    self.h, self.topk_idx.data_ptr(), self.topk_val.data_ptr(), B, out.data_ptr(), self._stream()
+                )
+            )
+        return out
+
+    def x_hat(self, x: torch.Tensor) -> torch.Tensor:
+        B = x.shape[0]
+        out = torch.empty(B, self.D, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_x_hat(self.h, self.resid.data_ptr(), x.data_ptr(), B, out.data_ptr(), self._stream()))
+        return out
+
+    def loss_dict(self) -> dict:
+        vals = self.losses.tolist()  # host sync, like Loss.metrics() in saev (objectives.py:80-89)
+        return dict(zip(LOSS_KEYS, vals))
+
+    # ---- test hook -------------------------------------------------------------------------
+    def gemm_nt(self, A: torch.Tensor, Bt: torch.Tensor, bias: torch.Tensor | None, nterms: int) -> torch.Tensor:
+        M, K = A.shape
+        N = Bt.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(2 * (M + N) * K, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_gemm_nt(
+                    self.h, A.data_ptr(), Bt.data_ptr(), _lib.ptr(bias), M, N, K, nterms, out.data_ptr(),
+                    scratch.data_ptr(), self._stream(),
+                )
+            )
+        return out

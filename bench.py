@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: activations/sec of the full SAE training step (saev train.py:332-460 loop body:
+normalize -> objective forward (encode, TopK, decode, MSE + AuxK) -> backward -> remove_parallel_grads ->
+clip -> Adam) on BASELINE.json's quoted configuration (d_model=1024, d_sae=65536, K=32, batch 16384 per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md §Measurement.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (d_model, d_sae, top_k, batch per GPU)
+    "c3": (1024, 65536, 32, 16384),
+    "c2": (768, 32768, 32, 4096),
+    "c1": (128, 512, 16, 256),
+}
+METRIC = "activations/sec"
+FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            flat = {}
+
+            def walk(o):
+                if isinstance(o, dict):
+                    for k, v in o.items():
+                        if isinstance(v, (int, float)):
+                            flat.setdefault(k, float(v))
+                        else:
+                            walk(v)
+
+            walk(d)
+            if "bf16_tflops_sustained" in flat or "bf16_tflops" in flat:
+                return flat, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "n_samples": len(sm)}
+
+
+def cpu_reference_run(D, S, K, steps, warmup, batch, threads=None):
+    """Times the CPU restatement of the reference's step (oracle/sae_oracle.py, pinned against the live
+    reference) on the host cores.  Returns (acts_per_s, ms_per_step, cores)."""
+    import torch
+
+    from oracle import sae_oracle as orc
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
+    st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
+    cfg = orc.OracleConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=512, lr=4e-4, n_lr_warmup=500, n_steps=10_000)
+    xs = [torch.randn(batch, D, generator=g) for _ in range(2)]
+    for i in range(warmup):
+        orc.train_step(cfg, st, xs[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        orc.train_step(cfg, st, xs[i % 2])
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores
+
+
+def size_cpu_sample(D, S, K, steps, warmup, budget_s):
+    """Pick a per-step sample (rows) so that (steps + warmup) CPU steps fit in ~budget_s seconds."""
+    probe = 64
+    rate, _, _ = cpu_reference_run(D, S, K, 1, 1, probe)
+    rows = int(rate * budget_s / max(1, steps + warmup))
+    return max(64, min(2048, (rows // 64) * 64))
+
+
+def run_reference(args, D, S, K, B, rank, world):
+    if rank != 0:
+        return
+    rows = args.cpu_rows or size_cpu_sample(D, S, K, args.steps, args.warmup, budget_s=120.0)
+    rate, ms, cores = cpu_reference_run(D, S, K, args.steps, args.warmup, rows)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "activations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, D, S, K, B), "cpu_rows_per_step": rows},
+        "cpu_baseline": {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {rows} rows (cost is linear in rows) of the same "
+                                   f"d_model={D} d_sae={S} K={K} step; oracle/sae_oracle.py, torch CPU fp32"},
+        "e2e": {"value": rate, "unit": "activations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w, D, S, K, B):
+    return (f"{w}: d_model={D} d_sae={S} TopK k={K} batch={B}/GPU, objective MSE+AuxK(k_aux=512, alpha=1/32, "
+            f"dead_threshold=10M tokens), remove_parallel_grads, clip 1.0, Adam, lr warmup; Gaussian activations")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows per CPU-baseline step (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    D, S, K, B = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, D, S, K, B, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from saev_b200 import _lib
+    from saev_b200.engine import Engine, EngineConfig
+    from saev_b200.parallel import DataParallelTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; saev_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
+                              dead_threshold_tokens=10_000_000, max_batch=B), device=dev)
+    eng.init_params(seed=0)
+    tr = DataParallelTrainer(eng)
+    tr.broadcast_params(0)
+
+    # synthetic activations: 4 rotating batches per rank, resident in HBM (value) and in pinned host memory (e2e)
+    NB = 4
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_dev = [torch.randn(B, D, generator=gen, device=dev) for _ in range(NB)]
+    peak_lr, n_warm = 4e-4, 500
+
+    def lr_at(step):  # WarmupCosine with a long horizon: linear warm-up region (scheduling.py:58-68)
+        return peak_lr * min(step, n_warm) / n_warm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    lib = _lib.load()
+    gstep = 0
+    for _ in range(args.warmup):
+        tr.step(x_dev[gstep % NB], lr_at(gstep))
+        gstep += 1
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile_enable(True)
+    barrier()
+    launches0 = lib.saev_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tr.step(x_dev[gstep % NB], lr_at(gstep))
+        gstep += 1
+    e1.record()
+    barrier()
+    launches = lib.saev_b200_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    stages = eng.profile_read()
+    eng.profile_enable(False)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    final_losses = tr.global_losses()
+
+    # ---------------- timed region 2: end to end from pinned host buffers ----------------
+    x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    for h, d in zip(x_host, x_dev):
+        h.copy_(d)
+    stage_bufs = [torch.empty(B, D, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty(args.steps, 8, dtype=torch.float32).pin_memory()
+    main_stream = torch.cuda.current_stream(dev)
+
+    def prefetch(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            stage_bufs[slot].copy_(x_host[i % NB], non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    for s in range(2):
+        consumed[s].record(main_stream)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    prefetch(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        slot = i % 2
+        main_stream.wait_event(copied[slot])
+        tr.step(stage_bufs[slot], lr_at(gstep))
+        consumed[slot].record(main_stream)
+        loss_host[i].copy_(eng.losses, non_blocking=True)
+        gstep += 1
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks, peaks_src = load_peaks()
+        peak_tf = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        gemm_ms, gemm_n = stages["encode_gemm"]
+        gemm_avg_ms = gemm_ms / max(1, gemm_n)
+        flops = 2.0 * B * D * S  # algorithmic FLOPs of the encoder contraction per launch
+        achieved_tf = flops / (gemm_avg_ms * 1e-3) / 1e12 if gemm_avg_ms > 0 else 0.0
+        traffic = None
+        tp = ROOT / "profiles" / "encode_gemm_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "activations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args.workload, D, S, K, B),
+                "global_batch": world * B,
+                "parallelism": f"dp{world}",
+                "precision": "bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "
+                             "every value that reaches the loss / gradients / parameters is fp32",
+                "l2_policy": f"per-step working set (params+grads+Adam moments {eng.n_params * 16 / 1e9:.2f} GB, "
+                             f"{NB} rotating input batches) is far larger than the 126 MB L2; no explicit flush",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "activations/s", "h2d_bytes_per_step": B * D * 4,
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "encode_gemm_kernel (tcgen05 encoder contraction + top-k screen)",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "peak_source": f"{peaks_src} (bf16 dense, sustained)",
+                         "avg_launch_ms": gemm_avg_ms,
+                         "step_frac_of_encoder_roofline": (value / world) * 2.0 * D * S / (peak_tf * 1e12)},
+            "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+            "final": {"mse": final_losses["mse"], "loss": final_losses["loss"], "n_dead": final_losses["n_dead"],
+                      "unsafe_rows": eng.unsafe_rows()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rows = args.cpu_rows or 1024
+            rate, ms, cores = cpu_reference_run(D, S, K, steps=2, warmup=1, batch=rows)
+            line["cpu_baseline"] = {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 timed steps x {rows} rows (+1 warm-up) of the same step; "
+                                              "oracle/sae_oracle.py on torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

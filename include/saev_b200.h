@@ -64,6 +64,8 @@ typedef struct saev_b200_cfg {
 typedef struct saev_b200_handle saev_b200_handle;
 
 int saev_b200_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (all handles). */
+uint64_t saev_b200_launch_count(void);
 const char* saev_b200_last_error(const saev_b200_handle* h);
 
 int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out);
@@ -131,6 +133,26 @@ int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int
  * scratch must hold 2 * (M + N) * K bf16. */
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream);
+
+/* Optional per-stage device timing (CUDA events recorded on the caller's stream around each group of
+ * launches).  saev_b200_profile_read synchronises on the recorded events and returns, per stage, the summed
+ * milliseconds and the number of recorded intervals since the last read (host arrays of
+ * SAEV_B200_N_STAGES entries). */
+enum {
+  SAEV_B200_STAGE_PREP = 0,        /* x -> bf16 operand                       */
+  SAEV_B200_STAGE_ENCODE_GEMM = 1, /* tcgen05 encoder contraction + top-k screen */
+  SAEV_B200_STAGE_RESCORE = 2,     /* exact fp32 re-score + final top-k        */
+  SAEV_B200_STAGE_DECODE = 3,      /* sparse decode, residual, d loss / d h    */
+  SAEV_B200_STAGE_LOSS = 4,        /* dead tracker, AuxK forward, loss scalars */
+  SAEV_B200_STAGE_CSC = 5,         /* per-atom lists of the active set         */
+  SAEV_B200_STAGE_WGRAD = 6,       /* weight gradients + parallel-grad removal */
+  SAEV_B200_STAGE_BIAS_AUX = 7,    /* b_dec gradient, AuxK backward            */
+  SAEV_B200_STAGE_SUMSQ = 8,       /* global gradient norm                     */
+  SAEV_B200_STAGE_ADAM = 9,        /* clip + Adam + renorm + bf16 refresh      */
+  SAEV_B200_N_STAGES = 10
+};
+int saev_b200_profile_enable(saev_b200_handle* h, int32_t on);
+int saev_b200_profile_read(saev_b200_handle* h, float* host_ms_sum, int32_t* host_count);
 
 /* ---- pinned staging ring for activation batches (replaces the pageable-memory H2D copy of
  *      train.py:333 / buffers.py:199) ----

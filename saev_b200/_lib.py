@@ -17,6 +17,7 @@ ABI_VERSION = 1
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
 PHASE_A, PHASE_B, PHASE_ALL = 1, 2, 3
+STAGES = ("prep", "encode_gemm", "rescore", "decode", "loss", "csc", "wgrad", "bias_aux", "sumsq", "adam")
 
 
 class Cfg(C.Structure):
@@ -47,6 +48,7 @@ _f = C.c_float
 # name -> (restype, argtypes); must list every symbol include/saev_b200.h declares
 SIGNATURES = {
     "saev_b200_abi_version": (C.c_int, []),
+    "saev_b200_launch_count": (C.c_uint64, []),
     "saev_b200_last_error": (C.c_char_p, [_p]),
     "saev_b200_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(_p)]),
     "saev_b200_destroy": (C.c_int, [_p]),
@@ -68,6 +70,8 @@ SIGNATURES = {
     "saev_b200_densify": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_x_hat": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "saev_b200_profile_enable": (C.c_int, [_p, _i32]),
+    "saev_b200_profile_read": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "saev_b200_ring_create": (C.c_int, [_i32, C.c_size_t, C.POINTER(_p)]),
     "saev_b200_ring_destroy": (C.c_int, [_p]),
     "saev_b200_ring_host_ptr": (_p, [_p, _i32]),

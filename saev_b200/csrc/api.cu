@@ -10,6 +10,10 @@
 
 using namespace sb;
 
+namespace sb {
+unsigned long long g_launch_count = 0;
+}
+
 namespace {
 
 constexpr size_t ALIGN = 256;
@@ -17,7 +21,7 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
   size_t shadow_hi, x_hi, cand_val, cand_idx, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
-      entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, total;
+      entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
 };
 
 }  // namespace
@@ -32,6 +36,13 @@ struct saev_b200_handle {
   bool last_forward_training = false;
   bool last_forward_tracked = false;
   mutable char err[512];
+  // optional per-stage CUDA-event timing (saev_b200_profile_*)
+  bool prof_on = false;
+  int prof_n = 0;
+  static constexpr int PROF_CAP = 8192;
+  cudaEvent_t* prof_beg = nullptr;
+  cudaEvent_t* prof_end = nullptr;
+  unsigned char* prof_stage = nullptr;
 };
 
 namespace {
@@ -83,12 +94,33 @@ Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
     w.h_aux = take(B * static_cast<size_t>(aux_cap) * 4);
     w.mask_aux = take(B * static_cast<size_t>(aux_cap));
     w.r_aux = take(B * D * 4);
+    w.aux_colpart = take(aux_colpart_bytes(aux_cap));
   } else {
-    w.h_aux = w.mask_aux = w.r_aux = o;
+    w.h_aux = w.mask_aux = w.r_aux = w.aux_colpart = o;
   }
   w.total = o;
   return w;
 }
+
+// RAII stage timer: records an event pair around a group of launches when profiling is enabled.
+struct StageTimer {
+  saev_b200_handle* h;
+  cudaStream_t s;
+  int slot = -1;
+  StageTimer(saev_b200_handle* h_, int stage, cudaStream_t s_) : h(h_), s(s_) {
+    if (!h->prof_on || h->prof_n >= saev_b200_handle::PROF_CAP) return;
+    slot = h->prof_n++;
+    h->prof_stage[slot] = static_cast<unsigned char>(stage);
+    if (!h->prof_beg[slot]) {
+      cudaEventCreate(&h->prof_beg[slot]);
+      cudaEventCreate(&h->prof_end[slot]);
+    }
+    cudaEventRecord(h->prof_beg[slot], s);
+  }
+  ~StageTimer() {
+    if (slot >= 0) cudaEventRecord(h->prof_end[slot], s);
+  }
+};
 
 template <typename T>
 inline T* at(void* ws, size_t off) {
@@ -100,6 +132,8 @@ inline T* at(void* ws, size_t off) {
 extern "C" {
 
 int saev_b200_abi_version(void) { return SAEV_B200_ABI_VERSION; }
+
+uint64_t saev_b200_launch_count(void) { return sb::g_launch_count; }
 
 const char* saev_b200_last_error(const saev_b200_handle* h) { return h ? h->err : g_err; }
 
@@ -140,7 +174,44 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
 }
 
 int saev_b200_destroy(saev_b200_handle* h) {
+  if (h && h->prof_beg) {
+    for (int i = 0; i < saev_b200_handle::PROF_CAP; ++i) {
+      if (h->prof_beg[i]) cudaEventDestroy(h->prof_beg[i]);
+      if (h->prof_end[i]) cudaEventDestroy(h->prof_end[i]);
+    }
+    delete[] h->prof_beg;
+    delete[] h->prof_end;
+    delete[] h->prof_stage;
+  }
   delete h;
+  return 0;
+}
+
+int saev_b200_profile_enable(saev_b200_handle* h, int32_t on) {
+  if (on && !h->prof_beg) {
+    h->prof_beg = new cudaEvent_t[saev_b200_handle::PROF_CAP]();
+    h->prof_end = new cudaEvent_t[saev_b200_handle::PROF_CAP]();
+    h->prof_stage = new unsigned char[saev_b200_handle::PROF_CAP]();
+  }
+  h->prof_on = on != 0;
+  h->prof_n = 0;
+  return 0;
+}
+
+int saev_b200_profile_read(saev_b200_handle* h, float* host_ms_sum, int32_t* host_count) {
+  for (int i = 0; i < SAEV_B200_N_STAGES; ++i) {
+    host_ms_sum[i] = 0.f;
+    host_count[i] = 0;
+  }
+  for (int i = 0; i < h->prof_n; ++i) {
+    if (cudaEventSynchronize(h->prof_end[i]) != cudaSuccess) return fail(h, 110, "profile_read: event sync failed%s");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_beg[i], h->prof_end[i]) != cudaSuccess)
+      return fail(h, 110, "profile_read: elapsed time failed%s");
+    host_ms_sum[h->prof_stage[i]] += ms;
+    host_count[h->prof_stage[i]] += 1;
+  }
+  h->prof_n = 0;
   return 0;
 }
 
@@ -156,6 +227,7 @@ uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace) {
 int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n = static_cast<long long>(h->cfg.d_sae) * h->cfg.d_model;
+  cudaMemsetAsync(at<char>(workspace, h->ws.scalars), 0, 64, s);
   if (launch_split_bf16(W_enc_t, at<__nv_bfloat16>(workspace, h->ws.shadow_hi), nullptr, n, s))
     return fail(h, 30, "sync_weights: split_bf16 launch failed%s");
   return check_cuda(h, "sync_weights");
@@ -185,8 +257,11 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
     if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
     __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
-    if (launch_split_bf16(x, x_hi, nullptr, static_cast<long long>(B) * D, s))
-      return fail(h, 41, "forward: split_bf16 launch failed%s");
+    {
+      StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
+      if (launch_split_bf16(x, x_hi, nullptr, static_cast<long long>(B) * D, s))
+        return fail(h, 41, "forward: split_bf16 launch failed%s");
+    }
 
     EncodeGemmArgs g;
     g.A_hi = x_hi;
@@ -202,10 +277,13 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.num_sms = h->num_sms;
     g.cand_val = at<float>(workspace, w.cand_val);
     g.cand_idx = at<int>(workspace, w.cand_idx);
-    if (int rc = launch_encode_gemm(g, s)) {
-      char buf[64];
-      snprintf(buf, sizeof(buf), "%d", rc);
-      return fail(h, 42, "forward: encode GEMM launch failed (code %s)", buf);
+    {
+      StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
+      if (int rc = launch_encode_gemm(g, s)) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%d", rc);
+        return fail(h, 42, "forward: encode GEMM launch failed (code %s)", buf);
+      }
     }
 
     RescoreArgs r;
@@ -225,7 +303,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     r.feat_count = training ? at<int>(workspace, w.feat_count) : nullptr;
     r.active = at<int>(workspace, w.active);
     r.unsafe_rows = reinterpret_cast<unsigned int*>(scal_i + 1);
-    if (launch_rescore_topk(r, s)) return fail(h, 43, "forward: rescore launch failed%s");
+    {
+      StageTimer tm(h, SAEV_B200_STAGE_RESCORE, s);
+      if (launch_rescore_topk(r, s)) return fail(h, 43, "forward: rescore launch failed%s");
+    }
 
     DecodeArgs d;
     d.x = x;
@@ -243,12 +324,16 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     d.row_sse = at<float>(workspace, w.row_sse);
     d.row_l1 = at<float>(workspace, w.row_l1);
     d.row_l0 = at<float>(workspace, w.row_l0);
-    if (launch_decode(d, s)) return fail(h, 44, "forward: decode launch failed%s");
+    {
+      StageTimer tm(h, SAEV_B200_STAGE_DECODE, s);
+      if (launch_decode(d, s)) return fail(h, 44, "forward: decode launch failed%s");
+    }
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
   }
 
   if (phase & SAEV_B200_PHASE_B) {
+    StageTimer tm(h, SAEV_B200_STAGE_LOSS, s);
     bool aux_live = false;
     if (tracked) {
       if (launch_dead_update(reinterpret_cast<long long*>(toks_since_active), at<int>(workspace, w.active), S,
@@ -280,6 +365,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
         a.gW_enc_t = a.gb_enc = a.gW_dec = nullptr;
         a.colsum_partial = at<float>(workspace, w.colsum_partial);
         a.gb_dec = nullptr;
+        a.aux_colpart = at<float>(workspace, w.aux_colpart);
         if (launch_aux_forward(a, s)) return fail(h, 46, "forward: AuxK launch failed%s");
         aux_live = true;
       }
@@ -316,9 +402,12 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   if (tokens_global <= 0) tokens_global = B;
   const int D = c.d_model, S = c.d_sae, K = c.top_k;
   const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
-  if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
-                       at<int>(workspace, w.cursor), at<int>(workspace, w.entries), s))
-    return fail(h, 51, "backward: CSC build launch failed%s");
+  {
+    StageTimer tm(h, SAEV_B200_STAGE_CSC, s);
+    if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
+                         at<int>(workspace, w.cursor), at<int>(workspace, w.entries), s))
+      return fail(h, 51, "backward: CSC build launch failed%s");
+  }
   WgradArgs g;
   g.feat_off = at<int>(workspace, w.feat_off);
   g.entries = at<int>(workspace, w.entries);
@@ -336,7 +425,11 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   g.gW_enc_t = gW_enc_t;
   g.gb_enc = gb_enc;
   g.gW_dec = gW_dec;
-  if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
+  {
+    StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
+    if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
+  }
+  StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, s);
   if (launch_colsum(resid, B, D, grad_scale, 0, at<float>(workspace, w.colsum_partial), gb_dec, s))
     return fail(h, 53, "backward: bias-gradient launch failed%s");
   if (c.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked) {
@@ -366,6 +459,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
     a.gW_dec = gW_dec;
     a.colsum_partial = at<float>(workspace, w.colsum_partial);
     a.gb_dec = gb_dec;
+    a.aux_colpart = at<float>(workspace, w.aux_colpart);
     if (launch_aux_backward(a, s)) return fail(h, 54, "backward: AuxK launch failed%s");
   }
   return check_cuda(h, "backward");
@@ -373,6 +467,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
 
 int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,
                          void* workspace, void* stream) {
+  StageTimer tm(h, SAEV_B200_STAGE_SUMSQ, static_cast<cudaStream_t>(stream));
   if (launch_sumsq(grads_flat, n, at<double>(workspace, h->ws.sumsq_partial), sumsq_out,
                    static_cast<cudaStream_t>(stream)))
     return fail(h, 60, "grad_sumsq: launch failed%s");
@@ -426,6 +521,7 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.gnorm_sq = sumsq;
   a.renorm_w_dec = renorm_w_dec;
   a.gnorm_out = gnorm_out;
+  StageTimer tm(h, SAEV_B200_STAGE_ADAM, static_cast<cudaStream_t>(stream));
   if (launch_adam(a, static_cast<cudaStream_t>(stream))) return fail(h, 62, "adam_step: launch failed%s");
   return check_cuda(h, "adam_step");
 }

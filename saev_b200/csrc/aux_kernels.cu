@@ -1,6 +1,425 @@
+// AuxK dead-latent loss (saev src/saev/nn/modeling.py:75-103) and its gradients, restricted to the
+// compact list L of dead dictionary atoms the dead tracker produced (device-side length n_dead; the host
+// never reads it, so every kernel here takes its problem size from device memory and runs a fixed grid).
+//
+//   h_L   = x . W_enc_t[L]^T + b_enc[L]                  pre-activations of the dead atoms       [B, n_dead]
+//   f_aux = top-k_use of h_L per row, k_use = min(k_aux, n_dead)   (raw pre-acts, may be negative)
+//   x_aux = f_aux . W_dec[L] + b_dec ;  r_aux = x_aux - e,  e = x - x_hat = -resid
+//   aux   = alpha * mean(r_aux^2)
+//   G_a = 2 alpha r_aux / (B D);  gW_dec[L] = f_aux^T G_a (minus parallel part);  gb_dec += sum_b G_a
+//   dh_a = mask_a * (G_a . W_dec[L]^T);  gW_enc_t[L] = dh_a^T x;  gb_enc[L] = sum_b dh_a
+// Dead atoms never fired in this batch, so their rows of the main-path gradients are zero and are simply
+// overwritten.  Arithmetic is plain fp32 on CUDA cores (exact w.r.t. the reference's fp32): this path only
+// runs once latents have died and its contractions are n_dead wide, not d_sae wide.
 #include "common.cuh"
 #include "kernels.h"
+
 namespace sb {
-int launch_aux_forward(const AuxArgs& a, cudaStream_t s) { return 99; }
-int launch_aux_backward(const AuxArgs& a, cudaStream_t s) { return 99; }
+
+constexpr int TM = 64, TN = 64, TK = 16, TPAD = 4;
+constexpr int SGEMM_GRID = 148 * 3;
+
+struct SgemmArgs {
+  const float* A; long long lda;
+  const float* B; long long ldb;
+  float* C; long long ldc;
+  int M, N, K;
+  const int* dyn; int dyn_which;   // 0 none, 1: M = min(M,*dyn), 2: N, 3: K
+  const int* gatherM;              // row index of C
+  const int* gatherB;              // row index of B (N index when B_T, K index otherwise)
+  float alpha;
+};
+
+// C[gm(m), n] = alpha * sum_k A(m,k) B(k,n)
+//   A(m,k) = A_T ? A[k*lda + m] : A[m*lda + k]
+//   B(k,n) = B_T ? B[gb(n)*ldb + k] : B[gb(k)*ldb + n]
+template <bool A_T, bool B_T>
+__global__ void __launch_bounds__(256) sgemm_kernel(SgemmArgs a) {
+  __shared__ __align__(16) float As[TK][TM + TPAD];
+  __shared__ __align__(16) float Bs[TK][TN + TPAD];
+  int M = a.M, N = a.N, K = a.K;
+  if (a.dyn_which) {
+    const int d = *a.dyn;
+    if (a.dyn_which == 1) M = min(M, d);
+    if (a.dyn_which == 2) N = min(N, d);
+    if (a.dyn_which == 3) K = min(K, d);
+  }
+  const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + TN - 1) / TN;
+  const long long tiles = static_cast<long long>(tiles_m) * tiles_n;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const bool veca = (a.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0;
+  const bool vecb = (a.ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0;
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int m0 = static_cast<int>(tile / tiles_n) * TM, n0 = static_cast<int>(tile % tiles_n) * TN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += TK) {
+      // ---- A tile -> As[k][m] ----
+      if (!A_T) {
+        const int m = t >> 2, kq = (t & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m0 + m < M) {
+          const float* p = a.A + static_cast<long long>(m0 + m) * a.lda + k0 + kq;
+          if (veca && k0 + kq + 3 < K) {
+            const float4 q = *reinterpret_cast<const float4*>(p);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (k0 + kq + i < K) v[i] = p[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) As[kq + i][m] = v[i];
+      } else {
+        const int k = t >> 4, mq = (t & 15) * 4;
+        float4 q = make_float4(0, 0, 0, 0);
+        if (k0 + k < K) {
+          const float* p = a.A + static_cast<long long>(k0 + k) * a.lda + m0 + mq;
+          if (veca && m0 + mq + 3 < M) {
+            q = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (m0 + mq + 0 < M) q.x = p[0];
+            if (m0 + mq + 1 < M) q.y = p[1];
+            if (m0 + mq + 2 < M) q.z = p[2];
+            if (m0 + mq + 3 < M) q.w = p[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&As[k][mq]) = q;
+      }
+      // ---- B tile -> Bs[k][n] ----
+      if (B_T) {
+        const int n = t >> 2, kq = (t & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n0 + n < N) {
+          const long long r = a.gatherB ? a.gatherB[n0 + n] : (n0 + n);
+          const float* p = a.B + r * a.ldb + k0 + kq;
+          if (vecb && k0 + kq + 3 < K) {
+            const float4 q = *reinterpret_cast<const float4*>(p);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (k0 + kq + i < K) v[i] = p[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[kq + i][n] = v[i];
+      } else {
+        const int k = t >> 4, nq = (t & 15) * 4;
+        float4 q = make_float4(0, 0, 0, 0);
+        if (k0 + k < K) {
+          const long long r = a.gatherB ? a.gatherB[k0 + k] : (k0 + k);
+          const float* p = a.B + r * a.ldb + n0 + nq;
+          if (vecb && n0 + nq + 3 < N) {
+            q = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (n0 + nq + 0 < N) q.x = p[0];
+            if (n0 + nq + 1 < N) q.y = p[1];
+            if (n0 + nq + 2 < N) q.z = p[2];
+            if (n0 + nq + 3 < N) q.w = p[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[k][nq]) = q;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float am[4] = {av.x, av.y, av.z, av.w};
+        const float bn[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bn[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m >= M) continue;
+      const long long cm = a.gatherM ? a.gatherM[m] : m;
+      float* crow = a.C + cm * a.ldc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < N) crow[n] = a.alpha * acc[i][j];
+      }
+    }
+  }
 }
+
+template <bool A_T, bool B_T>
+static void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
+  sgemm_kernel<A_T, B_T><<<SGEMM_GRID, 256, 0, s>>>(a);
+  ++g_launch_count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-row top-k_use among the n_dead pre-activations: radix select on order-preserving keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int fkey(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) aux_select_kernel(float* __restrict__ h_aux, unsigned char* __restrict__ mask,
+                                                         long long ld, const float* __restrict__ b_enc,
+                                                         const int* __restrict__ dead_list,
+                                                         const int* __restrict__ n_dead_p, int B, int k_aux) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh_prefix, sh_need;
+  __shared__ int wtot[8];
+  __shared__ int sh_carry;
+  const int n = *n_dead_p;
+  if (n <= 0) return;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float* row = h_aux + static_cast<long long>(b) * ld;
+    unsigned char* mrow = mask + static_cast<long long>(b) * ld;
+    // add the bias (h = x.W + b_enc, modeling.py:344-347)
+    for (int i = t; i < n; i += 256) row[i] += __ldg(b_enc + dead_list[i]);
+    __syncthreads();
+    if (n <= k_aux) {
+      for (int i = t; i < n; i += 256) mrow[i] = 1;
+      __syncthreads();
+      continue;
+    }
+    // radix select of the k_aux-th largest key, 8 bits per pass from the top
+    if (t == 0) {
+      sh_prefix = 0;
+      sh_need = static_cast<unsigned int>(k_aux);
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      hist[t] = 0;
+      __syncthreads();
+      const unsigned int prefix = sh_prefix;
+      const unsigned int himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = t; i < n; i += 256) {
+        const unsigned int key = fkey(row[i]);
+        if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {
+        unsigned int need = sh_need, cum = 0;
+        int bin = 255;
+        for (; bin > 0; --bin) {
+          if (cum + hist[bin] >= need) break;
+          cum += hist[bin];
+        }
+        sh_need = need - cum;  // how many to take inside the chosen bin
+        sh_prefix = prefix | (static_cast<unsigned int>(bin) << shift);
+      }
+      __syncthreads();
+    }
+    const unsigned int T = sh_prefix;    // key of the k-th largest value
+    const int need_eq = static_cast<int>(sh_need);  // ties at T to keep, lowest column first
+    if (t == 0) sh_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 256) {
+      const int i = base + t;
+      unsigned int key = 0;
+      float v = 0.f;
+      if (i < n) {
+        v = row[i];
+        key = fkey(v);
+      }
+      const int eq = (i < n) && key == T;
+      const unsigned bal = __ballot_sync(FULL, eq);
+      const int incl = __popc(bal & (0xffffffffu >> (31 - lane)));
+      if (lane == 31) wtot[warp] = incl;
+      __syncthreads();
+      int before = sh_carry;
+      for (int w = 0; w < warp; ++w) before += wtot[w];
+      const int rank_eq = before + incl - 1;  // 0-based rank among ties, in column order
+      if (i < n) {
+        const bool sel = key > T || (eq && rank_eq < need_eq);
+        mrow[i] = sel ? 1 : 0;
+        if (!sel) row[i] = 0.f;
+      }
+      __syncthreads();
+      if (t == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += wtot[w];
+        sh_carry += tot;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// r_aux[b,:] += b_dec + resid[b,:]  (= x_aux - e);  row_sse_aux[b] = sum r_aux^2.   n_dead == 0 -> zeros.
+__global__ void __launch_bounds__(256) aux_resid_kernel(float* __restrict__ r_aux, const float* __restrict__ resid,
+                                                        const float* __restrict__ b_dec, int B, int D,
+                                                        const int* __restrict__ n_dead_p,
+                                                        float* __restrict__ row_sse_aux) {
+  const int n = *n_dead_p;
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += gridDim.x * 8) {
+    float* rr = r_aux + static_cast<long long>(b) * D;
+    const float* r0 = resid + static_cast<long long>(b) * D;
+    float sse = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float v = 0.f;
+      if (n > 0) v = rr[d] + b_dec[d] + r0[d];
+      rr[d] = v;
+      sse += v * v;
+    }
+    sse = warp_sum(sse);
+    if (lane == 0) row_sse_aux[b] = sse;
+  }
+}
+
+__global__ void __launch_bounds__(1024) aux_loss_kernel(const float* __restrict__ row_sse_aux, int B, float alpha,
+                                                        float inv_bd, float* __restrict__ aux_loss) {
+  __shared__ double ws[32];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += row_sse_aux[b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 32; ++w) tot += ws[w];
+    *aux_loss = static_cast<float>(static_cast<double>(alpha) * tot * static_cast<double>(inv_bd));
+  }
+}
+
+// remove the component of gW_dec[L[i]] parallel to W_dec[L[i]]  (modeling.py:419-445)
+__global__ void __launch_bounds__(256) aux_project_kernel(float* __restrict__ gW_dec, const float* __restrict__ W_dec,
+                                                          const int* __restrict__ dead_list,
+                                                          const int* __restrict__ n_dead_p, int D) {
+  const int n = *n_dead_p;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const long long j = dead_list[i];
+    float* g = gW_dec + j * D;
+    const float* w = W_dec + j * D;
+    float dot = 0.f, nsq = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      dot = fmaf(g[d], w[d], dot);
+      nsq = fmaf(w[d], w[d], nsq);
+    }
+    dot = warp_sum(dot);
+    nsq = warp_sum(nsq);
+    const float sc = nsq > 0.f ? dot / nsq : 0.f;
+    for (int d = lane; d < D; d += 32) g[d] = fmaf(-sc, w[d], g[d]);
+  }
+}
+
+// dh_aux *= mask ; partial column sums over a slab of rows
+constexpr int AUX_SLABS = 32;
+__global__ void __launch_bounds__(256) aux_mask_colsum_kernel(float* __restrict__ dh, const unsigned char* __restrict__ mask,
+                                                              long long ld, int B, const int* __restrict__ n_dead_p,
+                                                              float* __restrict__ partial /* [AUX_SLABS, ld] */) {
+  const int n = *n_dead_p;
+  const int slab = blockIdx.y;
+  const int rows = (B + AUX_SLABS - 1) / AUX_SLABS;
+  const int b0 = slab * rows, b1 = min(B, b0 + rows);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = b0; b < b1; ++b) {
+      const long long o = static_cast<long long>(b) * ld + i;
+      const float v = mask[o] ? dh[o] : 0.f;
+      dh[o] = v;
+      s += v;
+    }
+    partial[static_cast<long long>(slab) * ld + i] = s;
+  }
+}
+__global__ void __launch_bounds__(256) aux_colsum_final_kernel(const float* __restrict__ partial, long long ld,
+                                                               const int* __restrict__ dead_list,
+                                                               const int* __restrict__ n_dead_p,
+                                                               float* __restrict__ gb_enc) {
+  const int n = *n_dead_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < AUX_SLABS; ++p) s += partial[static_cast<long long>(p) * ld + i];
+    gb_enc[dead_list[i]] = s;
+  }
+}
+
+size_t aux_colpart_bytes(int cap) { return static_cast<size_t>(AUX_SLABS) * cap * 4; }
+
+int launch_aux_forward(const AuxArgs& a, cudaStream_t s) {
+  const long long ld = a.S;  // leading dimension of the [B, cap] scratch matrices
+  SgemmArgs g{};
+  // h_L = x . W_enc_t[L]^T
+  g.A = a.x; g.lda = a.D;
+  g.B = a.W_enc_t; g.ldb = a.D; g.gatherB = a.dead_list;
+  g.C = a.h_aux; g.ldc = ld;
+  g.M = a.B; g.N = a.S; g.K = a.D;
+  g.dyn = a.n_dead; g.dyn_which = 2;
+  g.gatherM = nullptr; g.alpha = 1.f;
+  launch_sgemm<false, true>(g, s);
+  aux_select_kernel<<<min(a.B, 148 * 8), 256, 0, s>>>(a.h_aux, a.mask_aux, ld, a.b_enc, a.dead_list, a.n_dead, a.B,
+                                                       a.k_aux);
+                                                       ++g_launch_count;
+  // x_aux (without bias) = f_aux . W_dec[L]
+  SgemmArgs d{};
+  d.A = a.h_aux; d.lda = ld;
+  d.B = a.W_dec; d.ldb = a.D; d.gatherB = a.dead_list;
+  d.C = a.r_aux; d.ldc = a.D;
+  d.M = a.B; d.N = a.D; d.K = a.S;
+  d.dyn = a.n_dead; d.dyn_which = 3;
+  d.gatherM = nullptr; d.alpha = 1.f;
+  launch_sgemm<false, false>(d, s);
+  aux_resid_kernel<<<min((a.B + 7) / 8, 148 * 8), 256, 0, s>>>(a.r_aux, a.resid, a.b_dec, a.B, a.D, a.n_dead,
+                                                                a.row_sse_aux);
+                                                                ++g_launch_count;
+  aux_loss_kernel<<<1, 1024, 0, s>>>(a.row_sse_aux, a.B, a.alpha, a.inv_bd, a.aux_loss);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+int launch_aux_backward(const AuxArgs& a, cudaStream_t s) {
+  const long long ld = a.S;
+  const float gscale = 2.f * a.alpha * a.inv_bd;
+  // gb_dec += sum_b G_a      (r_aux is all zeros when nothing is dead)
+  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s)) return 22;
+  // gW_dec[L] = f_aux^T G_a
+  SgemmArgs g{};
+  g.A = a.h_aux; g.lda = ld;             // A(m,k) = f_aux[k, m]
+  g.B = a.r_aux; g.ldb = a.D; g.gatherB = nullptr;
+  g.C = a.gW_dec; g.ldc = a.D; g.gatherM = a.dead_list;
+  g.M = a.S; g.N = a.D; g.K = a.B;
+  g.dyn = a.n_dead; g.dyn_which = 1;
+  g.alpha = gscale;
+  launch_sgemm<true, false>(g, s);
+  if (a.remove_parallel)
+    aux_project_kernel<<<148 * 4, 256, 0, s>>>(a.gW_dec, a.W_dec, a.dead_list, a.n_dead, a.D);
+    ++g_launch_count;
+  // dh_a = mask_a * (G_a . W_dec[L]^T)   (overwrites f_aux, which is no longer needed)
+  SgemmArgs e{};
+  e.A = a.r_aux; e.lda = a.D;
+  e.B = a.W_dec; e.ldb = a.D; e.gatherB = a.dead_list;
+  e.C = a.h_aux; e.ldc = ld; e.gatherM = nullptr;
+  e.M = a.B; e.N = a.S; e.K = a.D;
+  e.dyn = a.n_dead; e.dyn_which = 2;
+  e.alpha = gscale;
+  launch_sgemm<false, true>(e, s);
+  aux_mask_colsum_kernel<<<dim3(148, AUX_SLABS), 256, 0, s>>>(a.h_aux, a.mask_aux, ld, a.B, a.n_dead, a.aux_colpart);
+  ++g_launch_count;
+  aux_colsum_final_kernel<<<148, 256, 0, s>>>(a.aux_colpart, ld, a.dead_list, a.n_dead, a.gb_enc);
+  ++g_launch_count;
+  // gW_enc_t[L] = dh_a^T x
+  SgemmArgs w{};
+  w.A = a.h_aux; w.lda = ld;             // A(m,k) = dh_a[k, m]
+  w.B = a.x; w.ldb = a.D; w.gatherB = nullptr;
+  w.C = a.gW_enc_t; w.ldc = a.D; w.gatherM = a.dead_list;
+  w.M = a.S; w.N = a.D; w.K = a.B;
+  w.dyn = a.n_dead; w.dyn_which = 1;
+  w.alpha = 1.f;
+  launch_sgemm<true, false>(w, s);
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+}  // namespace sb

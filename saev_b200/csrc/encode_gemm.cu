@@ -384,6 +384,7 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
                                                            kblocks_per_term, a.bias, a.M, a.N, m_blocks,
                                                            tiles_per_split, nsplit, a.n_limit_dev, a.cand_val,
                                                            a.cand_idx, a.out, a.ldo);
+                                                           ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
 

@@ -9,6 +9,9 @@ namespace sb {
 
 constexpr int ENCODE_MAX_NSPLIT = 8;
 
+// number of kernels this library has launched (all handles); read through saev_b200_launch_count()
+extern unsigned long long g_launch_count;
+
 // ---- encode_gemm.cu -------------------------------------------------------------------------------------
 struct EncodeGemmArgs {
   const __nv_bfloat16* A_hi = nullptr;  // [M, K] row-major (K contiguous)
@@ -120,8 +123,10 @@ struct AuxArgs {
   float* aux_loss;         // device scalar out
   float* gW_enc_t; float* gb_enc; float* gW_dec;   // rows of dead latents are (over)written
   float* colsum_partial; float* gb_dec;            // gb_dec += sum_b G_aux
+  float* aux_colpart;      // [32, S] scratch for the gb_enc column sums
 };
 int launch_aux_forward(const AuxArgs& a, cudaStream_t s);
 int launch_aux_backward(const AuxArgs& a, cudaStream_t s);
+size_t aux_colpart_bytes(int cap);
 
 }  // namespace sb

@@ -17,6 +17,7 @@ namespace sb {
 #define SB_DISPATCH_VPL(D, CALL)                                         \
   do {                                                                   \
     const int need_ = ((D) + 127) / 128;                                 \
+    ++g_launch_count;                                                    \
     if (need_ <= 1) { constexpr int VPL = 1; CALL; }                     \
     else if (need_ <= 2) { constexpr int VPL = 2; CALL; }                \
     else if (need_ <= 4) { constexpr int VPL = 4; CALL; }                \
@@ -67,6 +68,7 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
   long long want = (n4 + threads - 1) / threads;
   const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
   split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, n4);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -390,8 +392,10 @@ __global__ void csc_fill_kernel(const int* __restrict__ idx, long long n, const 
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
                      int* entries, cudaStream_t s) {
   scan_counts_kernel<<<1, 1024, 0, s>>>(feat_count, feat_off, cursor, S);
+  ++g_launch_count;
   const long long n = static_cast<long long>(B) * K;
   csc_fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(topk_idx, n, feat_off, cursor, entries);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -522,7 +526,9 @@ int launch_colsum(const float* src, int B, int D, float scale, int accumulate, f
                   cudaStream_t s) {
   const int P = colsum_partial_rows(B);
   colsum_stage1<<<P, 256, 0, s>>>(src, B, D, partial);
+  ++g_launch_count;
   colsum_stage2<<<(D + 255) / 256, 256, 0, s>>>(partial, P, D, scale, accumulate, out);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -567,7 +573,9 @@ __global__ void sumsq_stage2(const double* partial, int n, float* out) {
 }
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s) {
   sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, partial);
+  ++g_launch_count;
   sumsq_stage2<<<1, 32, 0, s>>>(partial, SUMSQ_BLOCKS, out_sumsq);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -702,6 +710,7 @@ int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
   SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
   adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -748,6 +757,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
 }
 int launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
   finalize_kernel<<<1, 1024, 0, s>>>(a);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -797,6 +807,7 @@ __global__ void __launch_bounds__(1024) dead_update_kernel(long long* __restrict
 int launch_dead_update(long long* toks, int* active, int S, long long batch_tokens, long long threshold,
                        int* dead_list, int* n_dead, cudaStream_t s) {
   dead_update_kernel<<<1, 1024, 0, s>>>(toks, active, S, batch_tokens, threshold, dead_list, n_dead);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -814,6 +825,7 @@ int launch_densify(const int* idx, const float* val, int B, int K, int S, float*
   if (cudaMemsetAsync(out, 0, static_cast<size_t>(B) * S * 4, s) != cudaSuccess) return 23;
   const long long n = static_cast<long long>(B) * K;
   densify_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(idx, val, n, K, S, out);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -825,6 +837,7 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 }
 int launch_add_rows(const float* a, const float* b, long long n, float* out, cudaStream_t s) {
   add_kernel<<<148 * 8, 256, 0, s>>>(a, b, n, out);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

@@ -77,7 +77,7 @@ class Engine:
             self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             self.m = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             self.v = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
-            self.workspace = torch.empty(self.lib.saev_b200_workspace_bytes(h), dtype=torch.uint8, device=dev)
+            self.workspace = torch.zeros(self.lib.saev_b200_workspace_bytes(h), dtype=torch.uint8, device=dev)
             B, K = cfg.max_batch, cfg.top_k
             self.topk_idx = torch.empty(B, K, dtype=torch.int32, device=dev)
             self.topk_val = torch.empty(B, K, dtype=torch.float32, device=dev)
@@ -130,6 +130,26 @@ class Engine:
         self.b_enc.copy_(b_enc.to(self.device, torch.float32))
         self.W_dec.copy_(W_dec.to(self.device, torch.float32))
         self.b_dec.copy_(b_dec.to(self.device, torch.float32))
+        self.sync_weights()
+
+    @torch.no_grad()
+    def init_params(self, seed: int | None = None) -> None:
+        """saev's initialisation (modeling.py:306-329): W_dec = kaiming_uniform_([S, D]) (bound sqrt(6/D)),
+        row-normalised; W_enc = W_dec.T; biases zero.  saev leaves the global RNG unseeded; `seed` makes
+        it reproducible."""
+        gen = torch.Generator(device=self.device)
+        if seed is not None:
+            gen.manual_seed(seed)
+        bound = (6.0 / self.D) ** 0.5
+        self.W_dec.copy_((torch.rand(self.S, self.D, generator=gen, device=self.device) * 2 - 1) * bound)
+        self.b_dec.zero_()
+        self.b_enc.zero_()
+        self._ck(self.lib.saev_b200_normalize_w_dec(self.h, self.W_dec.data_ptr(), self._stream()))
+        self.W_enc_t.copy_(self.W_dec)
+        self.m.zero_()
+        self.v.zero_()
+        self.toks_since_active.zero_()
+        self.step_count = 0
         self.sync_weights()
 
     def sync_weights(self) -> None:
@@ -230,6 +250,18 @@ class Engine:
     def loss_dict(self) -> dict:
         vals = self.losses.tolist()  # host sync, like Loss.metrics() in saev (objectives.py:80-89)
         return dict(zip(LOSS_KEYS, vals))
+
+    # ---- per-stage device timing ------------------------------------------------------------
+    def profile_enable(self, on: bool = True) -> None:
+        self._ck(self.lib.saev_b200_profile_enable(self.h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{stage: (total_ms, n_intervals)} since the last read; synchronises on the recorded events."""
+        n = len(_lib.STAGES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        self._ck(self.lib.saev_b200_profile_read(self.h, ms, cnt))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.STAGES)}
 
     # ---- test hook -------------------------------------------------------------------------
     def gemm_nt(self, A: torch.Tensor, Bt: torch.Tensor, bias: torch.Tensor | None, nterms: int) -> torch.Tensor:

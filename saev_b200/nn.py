@@ -1,0 +1,485 @@
+"""Host-side mirror of `saev.nn` (model + objective API) on top of the CUDA engine.
+
+Same names, argument meaning and error behaviour as the reference
+(/root/reference/src/saev/nn/modeling.py, objectives.py) so that saev's training loop
+(src/saev/framework/train.py:109-618) can use these classes unchanged:
+
+    sae = SparseAutoencoder(cfg)                 # parameters W_dec, b_dec, W_enc, b_enc  (modeling.py:306-329)
+    objective = get_objective(Matryoshka(n_prefixes=1))
+    sae.normalize_w_dec()                         # train.py:334-335
+    loss, fwd = objective(sae, acts)              # train.py:341   -> saev_b200_forward
+    loss.loss.backward()                          # train.py:348   -> saev_b200_backward (writes .grad)
+    sae.remove_parallel_grads()                   # train.py:352   (already folded into backward: no-op)
+    clip_grad_norm_(sae.parameters(), c)          # train.py:358   -> saev_b200_grad_sumsq (see optim.py)
+    opt.step()                                    # train.py:444   -> saev_b200_adam_step (optim.FusedAdam)
+
+All arithmetic runs in libsaev_b200.so; modules can be constructed, saved and loaded on the CPU, but a
+forward on a CPU tensor raises (there is no CPU fallback).
+
+Differences from the reference that are deliberate and documented in DESIGN.md:
+  * `W_enc` is an nn.Parameter of shape [d_model, d_sae] as in saev, but once on the GPU it is a transposed
+    VIEW of the atom-major master copy W_enc_t[d_sae, d_model] the kernels use (state_dict keys and values
+    are unchanged, checkpoints interoperate with saev.nn.load / saev.nn.dump).
+  * `Output.h_x`, `Output.f_x`, `Output.x_hats` are materialised lazily (the fused path never writes the
+    [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
+  * Matryoshka n_prefixes > 1, BatchTopK and the dense ReLU activation have no CUDA path in this build and
+    raise NotImplementedError at forward time.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import io
+import json
+import math
+import pathlib
+import typing as tp
+
+import torch
+from torch import Tensor
+
+from . import __version__
+from .engine import LOSS_KEYS, Engine, EngineConfig
+
+SCHEMA_VERSION = 5  # modeling.py:20
+
+
+# ----------------------------------------------------------------------------------------------
+# configuration dataclasses (modeling.py:23-146, 259-284; objectives.py:13-25)
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class NoSparsity:
+    key: str = "no-sparsity"
+
+
+@dataclasses.dataclass(frozen=True)
+class L1Sparsity:
+    key: str = "l1-sparsity"
+    coeff: float = 1e-4
+
+
+@dataclasses.dataclass(frozen=True)
+class NoAux:
+    key: str = "no-aux"
+
+
+@dataclasses.dataclass(frozen=True)
+class AuxK:
+    key: str = "auxk"
+    k_aux: int = 512
+    alpha: float = 1 / 32
+
+
+@dataclasses.dataclass(frozen=True)
+class Relu:
+    key: str = "relu"
+    sparsity: tp.Any = L1Sparsity(coeff=4e-4)
+    aux: tp.Any = NoAux()
+
+
+@dataclasses.dataclass(frozen=True)
+class TopK:
+    key: str = "top-k"
+    top_k: int = 32
+    sparsity: tp.Any = NoSparsity()
+    aux: tp.Any = AuxK()
+
+    def __post_init__(self):
+        assert self.top_k > 0, "top_k must be a positive integer."
+
+
+@dataclasses.dataclass(frozen=True)
+class BatchTopK:
+    key: str = "batch-top-k"
+    top_k: int = 32
+    sparsity: tp.Any = NoSparsity()
+    momentum: float = 0.1
+    aux: tp.Any = AuxK()
+
+
+@dataclasses.dataclass(frozen=True)
+class SparseAutoencoderConfig:
+    d_model: int = 1024
+    d_sae: int = 1024 * 16
+    activation: tp.Any = TopK()
+    reinit_blend: float = 0.8
+    reinit_enc_dec_tranpose: bool = True
+    remove_parallel_grads: bool = True
+    normalize_w_dec: bool = True
+
+
+@dataclasses.dataclass(frozen=True)
+class Matryoshka:
+    n_prefixes: int = 10
+    dead_threshold_tokens: int = 10_000_000
+
+
+ObjectiveConfig = Matryoshka
+
+
+def _kind(obj) -> str:
+    """Class-name based dispatch so that saev's own config dataclasses are accepted as well as ours."""
+    return type(obj).__name__
+
+
+def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
+    act = sae_cfg.activation
+    kind = _kind(act)
+    if kind == "BatchTopK":
+        raise NotImplementedError("BatchTopK has no CUDA path in saev_b200 (global top-k does not shard; SURVEY §8e)")
+    if kind not in ("TopK", "Relu"):
+        raise TypeError(f"unknown activation config {act!r}")
+    aux = getattr(act, "aux", None)
+    sp = getattr(act, "sparsity", None)
+    return EngineConfig(
+        d_model=sae_cfg.d_model,
+        d_sae=sae_cfg.d_sae,
+        top_k=getattr(act, "top_k", 1),
+        activation="topk" if kind == "TopK" else "relu",
+        aux=_kind(aux) == "AuxK",
+        k_aux=getattr(aux, "k_aux", 512),
+        aux_alpha=getattr(aux, "alpha", 1 / 32),
+        l1_coeff=float(getattr(sp, "coeff", 0.0)) if _kind(sp) == "L1Sparsity" else 0.0,
+        dead_threshold_tokens=getattr(obj_cfg, "dead_threshold_tokens", 10_000_000),
+        remove_parallel_grads=sae_cfg.remove_parallel_grads,
+        normalize_w_dec=sae_cfg.normalize_w_dec,
+        max_batch=max_batch,
+    )
+
+
+# ----------------------------------------------------------------------------------------------
+# lazy forward outputs
+# ----------------------------------------------------------------------------------------------
+class EncodeOut(tp.NamedTuple):
+    h_x: Tensor
+    f_x: Tensor
+
+
+class Output:
+    """Mirror of SparseAutoencoder.Output (modeling.py:299-304) with lazily materialised dense fields.
+    Valid until the next forward of the same SAE (it reads the engine's top-k buffers)."""
+
+    def __init__(self, sae: "SparseAutoencoder", x: Tensor, ticket: int):
+        self._sae, self._x, self._ticket = sae, x, ticket
+        self._cache: dict[str, Tensor] = {}
+
+    def _check(self):
+        if self._sae._ticket != self._ticket:
+            raise RuntimeError("this Output refers to an earlier forward; its lazy fields are no longer available")
+
+    @property
+    def f_x(self) -> Tensor:
+        if "f_x" not in self._cache:
+            self._check()
+            self._cache["f_x"] = self._sae.engine.dense_f_x(self._x.shape[0])
+        return self._cache["f_x"]
+
+    @property
+    def x_hats(self) -> Tensor:
+        if "x_hats" not in self._cache:
+            self._check()
+            self._cache["x_hats"] = self._sae.engine.x_hat(self._x)[:, None, :]
+        return self._cache["x_hats"]
+
+    @property
+    def h_x(self) -> Tensor:
+        if "h_x" not in self._cache:
+            self._check()
+            eng = self._sae.engine
+            # dense pre-activations through the 3-term split tensor-core product (~5e-6 relative)
+            self._cache["h_x"] = eng.gemm_nt(self._x, eng.W_enc_t, eng.b_enc, 3)
+        return self._cache["h_x"]
+
+    def __iter__(self):  # NamedTuple-style unpacking: h_x, f_x, x_hats
+        return iter((self.h_x, self.f_x, self.x_hats))
+
+
+class _Activation(torch.nn.Module):
+    """Placeholder for `sae.activation` (objectives.py:149 reads `.cfg.sparsity`)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+
+
+# ----------------------------------------------------------------------------------------------
+# model
+# ----------------------------------------------------------------------------------------------
+class SparseAutoencoder(torch.nn.Module):
+    """Sparse auto-encoder with saev's parameterisation (modeling.py:288-445)."""
+
+    EncodeOut = EncodeOut
+    Output = Output
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        S, D = cfg.d_sae, cfg.d_model
+        # modeling.py:312-327: kaiming_uniform_ on [S, D] (bound sqrt(6 / D)), rows normalised, W_enc = W_dec.T
+        W_dec = torch.nn.init.kaiming_uniform_(torch.empty(S, D))
+        self.W_dec = torch.nn.Parameter(W_dec)
+        self.b_dec = torch.nn.Parameter(torch.zeros(D))
+        if cfg.normalize_w_dec:
+            self.W_dec.data /= torch.norm(self.W_dec.data, dim=1, keepdim=True)
+        # atom-major master copy, exposed with saev's [D, S] shape as a transposed view
+        self.W_enc = torch.nn.Parameter(self.W_dec.data.clone().t())
+        self.b_enc = torch.nn.Parameter(torch.zeros(S))
+        self.activation = _Activation(cfg.activation)
+        self.engine: Engine | None = None
+        self._obj_cfg = Matryoshka(n_prefixes=1)
+        self._max_batch = 0
+        self._ticket = 0
+        self._grads_fused = False
+        self._w_dec_normalized = False
+
+    # ---- engine binding --------------------------------------------------------------------
+    def _bind(self, batch: int, obj_cfg=None) -> Engine:
+        """Create (or grow) the CUDA engine and re-point the parameters at its flat buffers."""
+        dev = self.W_dec.device
+        if dev.type != "cuda":
+            raise RuntimeError("saev_b200.nn.SparseAutoencoder runs on CUDA only: move the module to a B200 "
+                               "(.to('cuda')); there is no CPU fallback")
+        if obj_cfg is not None:
+            self._obj_cfg = obj_cfg
+        eng = self.engine
+        need_new = (
+            eng is None
+            or eng.device != dev
+            or batch > eng.cfg.max_batch
+            or eng.cfg.dead_threshold_tokens != self._obj_cfg.dead_threshold_tokens
+        )
+        if need_new:
+            new = Engine(engine_config(self.cfg, self._obj_cfg, max(batch, self._max_batch)), device=dev)
+            self._max_batch = new.cfg.max_batch
+            with torch.no_grad():
+                new.W_enc_t.copy_(self.W_enc.data.t())
+                new.b_enc.copy_(self.b_enc.data)
+                new.W_dec.copy_(self.W_dec.data)
+                new.b_dec.copy_(self.b_dec.data)
+                if eng is not None:
+                    new.m.copy_(eng.m)
+                    new.v.copy_(eng.v)
+                    new.toks_since_active.copy_(eng.toks_since_active)
+                    new.step_count = eng.step_count
+            new.sync_weights()
+            self.engine = eng = new
+        # parameters must alias the engine buffers (they stop doing so after .to(), load_state_dict on a fresh
+        # module, or a `.data =` assignment); copy the current values in and re-point
+        if self.W_dec.data_ptr() != eng.W_dec.data_ptr() or self.W_enc.data_ptr() != eng.W_enc_t.data_ptr():
+            with torch.no_grad():
+                eng.W_enc_t.copy_(self.W_enc.data.t())
+                eng.b_enc.copy_(self.b_enc.data)
+                eng.W_dec.copy_(self.W_dec.data)
+                eng.b_dec.copy_(self.b_dec.data)
+            self.W_enc.data = eng.W_enc_t.t()
+            self.b_enc.data = eng.b_enc
+            self.W_dec.data = eng.W_dec
+            self.b_dec.data = eng.b_dec
+            eng.sync_weights()
+            self._w_dec_normalized = False
+        return eng
+
+    def weights_changed(self) -> None:
+        """Call after writing W_enc outside the optimizer (e.g. datapoint init, train.py:141-185) so the bf16
+        operand copy is rebuilt.  `_bind` detects re-pointed storage by itself; in-place writes need this."""
+        if self.engine is not None:
+            self.engine.sync_weights()
+        self._w_dec_normalized = False
+
+    # ---- reference API ---------------------------------------------------------------------
+    def _eval_forward(self, x: Tensor):
+        eng = self._bind(x.shape[0])
+        eng.forward(x.contiguous(), training=False)
+        self._ticket += 1
+        return Output(self, x, self._ticket)
+
+    def forward(self, x: Tensor) -> Output:
+        """modeling.py:331-341 (inference use: no dead tracking, no gradients)."""
+        self._require_topk()
+        return self._eval_forward(x)
+
+    def encode(self, x: Tensor) -> EncodeOut:
+        """modeling.py:343-349."""
+        out = self.forward(x)
+        return EncodeOut(h_x=out.h_x, f_x=out.f_x)
+
+    def decode(self, f_x: Tensor, *, prefixes: Tensor | None = None) -> Tensor:
+        """modeling.py:351-409 for the single-prefix case; dense f_x input is decoded by a (non-hot-path)
+        dense product, Matryoshka prefixes are not supported."""
+        if prefixes is not None and len(prefixes) > 1:
+            raise NotImplementedError("Matryoshka prefix decoding (n_prefixes > 1) has no CUDA path in saev_b200")
+        eng = self._bind(f_x.shape[0])
+        # x_hat = f_x . W_dec + b_dec  ==  gemm_nt(f_x, W_dec^T) ; W_dec^T [D, S] is materialised once per call
+        return eng.gemm_nt(f_x.contiguous(), eng.W_dec.t().contiguous(), eng.b_dec, 3)[:, None, :]
+
+    @torch.no_grad()
+    def normalize_w_dec(self):
+        """modeling.py:411-417.  A no-op when the fused optimizer already renormalised the rows."""
+        if not self.cfg.normalize_w_dec:
+            return
+        if self.W_dec.device.type != "cuda":
+            self.W_dec.data /= torch.norm(self.W_dec.data, dim=1, keepdim=True)  # construction-time (CPU) init only
+            return
+        if self._w_dec_normalized:
+            return
+        self._bind(max(self._max_batch, 1)).normalize_w_dec()
+
+    @torch.no_grad()
+    def remove_parallel_grads(self):
+        """modeling.py:419-445.  saev_b200_backward already removed the parallel component."""
+        if not self.cfg.remove_parallel_grads or self.W_dec.grad is None:
+            return
+        if self._grads_fused:
+            return
+        raise RuntimeError("remove_parallel_grads(): gradients were not produced by the fused backward")
+
+    def _require_topk(self):
+        if _kind(self.cfg.activation) != "TopK":
+            raise NotImplementedError(f"activation {_kind(self.cfg.activation)} has no CUDA path in this build of "
+                                      "saev_b200 (TopK only)")
+
+
+# ----------------------------------------------------------------------------------------------
+# objective
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class MatryoshkaLoss:
+    """objectives.py:59-89; fields are 0-d views into the engine's device loss vector."""
+
+    mse: Tensor
+    sparsity: Tensor
+    l0: Tensor
+    l1: Tensor
+    aux: Tensor
+    n_dead: Tensor
+    _total: Tensor = None
+
+    @property
+    def loss(self) -> Tensor:
+        return self._total
+
+    def metrics(self) -> dict[str, object]:
+        return {
+            "loss": self.loss.item(), "mse": self.mse.item(), "l0": self.l0.item(), "l1": self.l1.item(),
+            "sparsity": self.sparsity.item(), "aux": self.aux.item(), "n_dead": self.n_dead,
+        }
+
+
+class _StepFunction(torch.autograd.Function):
+    """Connects saev_b200_forward / saev_b200_backward to `loss.loss.backward()` (train.py:348)."""
+
+    @staticmethod
+    def forward(ctx, sae, x, tokens_global, W_dec, b_dec, W_enc, b_enc):
+        eng = sae.engine
+        eng.forward(x, training=True, tokens_global=tokens_global)
+        ctx.sae, ctx.x, ctx.tokens_global = sae, x, tokens_global
+        return eng.losses[6].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sae, eng = ctx.sae, ctx.sae.engine
+        eng.backward(ctx.x, tokens_global=ctx.tokens_global)
+        views = (("W_dec", eng.gW_dec), ("b_dec", eng.gb_dec), ("W_enc", eng.gW_enc_t.t()), ("b_enc", eng.gb_enc))
+        for name, g in views:
+            p = getattr(sae, name)
+            if p.grad is None:
+                p.grad = g  # alias the flat gradient bucket: no copy, the fused optimizer reads it in place
+            elif p.grad.data_ptr() != g.data_ptr():
+                p.grad.add_(g)
+        sae._grads_fused = True
+        # grad_out is 1 for `loss.backward()`; a scaled loss is not supported by the fused path
+        return None, None, None, None, None, None, None
+
+
+class MatryoshkaObjective(torch.nn.Module):
+    """objectives.py:92-156 for n_prefixes == 1."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.toks_since_active: Tensor | None = None
+
+    def forward(self, sae: SparseAutoencoder, x: Tensor):
+        if self.cfg.n_prefixes > 1:
+            raise NotImplementedError("Matryoshka(n_prefixes > 1) has no CUDA path in saev_b200; use n_prefixes=1")
+        sae._require_topk()
+        x = x.contiguous()
+        eng = sae._bind(x.shape[0], self.cfg)
+        sae._ticket += 1
+        out = Output(sae, x, sae._ticket)
+        if self.training:
+            if self.toks_since_active is None:  # objectives.py:108-111: lazily created, not in the state_dict
+                eng.toks_since_active.zero_()
+            self.toks_since_active = eng.toks_since_active
+            total = _StepFunction.apply(sae, x, x.shape[0], sae.W_dec, sae.b_dec, sae.W_enc, sae.b_enc)
+            sae._w_dec_normalized = False if not sae._w_dec_normalized else sae._w_dec_normalized
+        else:
+            eng.forward(x, training=False)
+            total = eng.losses[6].clone()
+        L = eng.losses.clone()
+        loss = MatryoshkaLoss(mse=L[0], sparsity=L[2], l0=L[3], l1=L[4], aux=L[1], n_dead=L[5].to(torch.int64),
+                              _total=total)
+        return loss, out
+
+
+def get_objective(cfg) -> MatryoshkaObjective:
+    """objectives.py:204-220."""
+    if _kind(cfg) == "Matryoshka":
+        return MatryoshkaObjective(cfg)
+    raise TypeError(f"unknown objective config {cfg!r}")
+
+
+# ----------------------------------------------------------------------------------------------
+# checkpoints (modeling.py:548-658, schema 5): one JSON header line + torch.save(state_dict)
+# ----------------------------------------------------------------------------------------------
+def _serialize_activation(act) -> dict:
+    d = {"key": act.key}
+    for f in dataclasses.fields(act):
+        if f.name == "key":
+            continue
+        v = getattr(act, f.name)
+        d[f.name] = _serialize_activation(v) if dataclasses.is_dataclass(v) else v
+    return d
+
+
+_BY_KEY = {"no-sparsity": NoSparsity, "l1-sparsity": L1Sparsity, "no-aux": NoAux, "auxk": AuxK, "relu": Relu,
+           "top-k": TopK, "batch-top-k": BatchTopK}
+
+
+def _deserialize(d: dict):
+    cls = _BY_KEY[d["key"]]
+    kw = {k: (_deserialize(v) if isinstance(v, dict) and "key" in v else v) for k, v in d.items() if k != "key"}
+    return cls(**kw)
+
+
+def dump(fpath, sae: SparseAutoencoder) -> None:
+    cfg = sae.cfg
+    cfg_dict = {f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)}
+    cfg_dict["activation"] = _serialize_activation(cfg.activation)
+    header = {"schema": SCHEMA_VERSION, "cfg": cfg_dict, "commit": "unknown", "lib": f"saev_b200-{__version__}"}
+    fpath = pathlib.Path(fpath)
+    fpath.parent.mkdir(exist_ok=True, parents=True)
+    state = {k: v.detach().cpu().contiguous() for k, v in sae.state_dict().items()}
+    with open(fpath, "wb") as fd:
+        fd.write(json.dumps(header).encode() + b"\n")
+        torch.save(state, fd)
+
+
+def load(fpath, *, device="cpu") -> SparseAutoencoder:
+    with open(fpath, "rb") as fd:
+        header = json.loads(fd.readline())
+        buffer = io.BytesIO(fd.read())
+    if header.get("schema") != SCHEMA_VERSION:
+        raise ValueError(f"saev_b200.nn.load reads schema {SCHEMA_VERSION} checkpoints; got {header.get('schema')!r} "
+                         "(convert older files with saev.nn.load + saev.nn.dump)")
+    cfg_dict = dict(header["cfg"])
+    cfg_dict["activation"] = _deserialize(cfg_dict["activation"])
+    known = {f.name for f in dataclasses.fields(SparseAutoencoderConfig)}
+    cfg = SparseAutoencoderConfig(**{k: v for k, v in cfg_dict.items() if k in known})
+    model = SparseAutoencoder(cfg)
+    model.load_state_dict(torch.load(buffer, weights_only=True, map_location="cpu"))
+    return model.to(device)
+
+
+def kaiming_bound(d_model: int) -> float:
+    return math.sqrt(6.0 / d_model)

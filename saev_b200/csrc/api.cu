@@ -20,7 +20,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand_val, cand_idx, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
 };
 
@@ -74,8 +74,13 @@ Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
   };
   w.shadow_hi = take(S * D * 2);
   w.x_hi = take(B * D * 2);
-  w.cand_val = take(B * ENCODE_MAX_NSPLIT * kp * 4);
-  w.cand_idx = take(B * ENCODE_MAX_NSPLIT * kp * 4);
+  {
+    // (row, split) candidate buffers of the top-k screen: rows are padded to whole 128-row blocks and
+    // m_blocks * nsplit never exceeds max(m_blocks, #SMs)
+    const size_t m_blocks = (B + 127) / 128;
+    const size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
+    w.cand = take(row_splits * ENCODE_CAPG * 8);
+  }
   w.dh = take(B * K * 4);
   w.row_sse = take(B * 4);
   w.row_l1 = take(B * 4);
@@ -275,8 +280,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.kp = h->kp;
     g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
     g.num_sms = h->num_sms;
-    g.cand_val = at<float>(workspace, w.cand_val);
-    g.cand_idx = at<int>(workspace, w.cand_idx);
+    g.cand = at<char>(workspace, w.cand);
     {
       StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
       if (int rc = launch_encode_gemm(g, s)) {
@@ -287,8 +291,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     }
 
     RescoreArgs r;
-    r.cand_val = g.cand_val;
-    r.cand_idx = g.cand_idx;
+    r.cand = g.cand;
+    r.cand_stride = ENCODE_CAPG;
     r.nsplit = g.nsplit;
     r.kp = h->kp;
     r.x = x;

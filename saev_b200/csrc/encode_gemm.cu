@@ -4,8 +4,10 @@
 // TopK epilogue, the `topk -> scatter -> mul` of TopKActivation.forward (modeling.py:169-179): the [B,S]
 // pre-activation matrix is never written to HBM.  Each CTA owns one 128-row block of the batch and sweeps a
 // contiguous range of 256-column tiles of the dictionary; the epilogue warps read the accumulator out of
-// TMEM (one thread = one batch row) and keep a running list of the KP largest pre-activations of their row
-// in shared memory (threshold filter + warp-cooperative compaction).  The lists are *candidates*: the bf16
+// TMEM (one thread = one batch row) and keep a running list of the KP largest pre-activations of their row:
+// a register-resident admission threshold filters each 16-column chunk (max-tree, one compare), the rare
+// survivors are appended to a per-row buffer in global memory (L2 resident), and when a buffer fills up the
+// warp cooperatively radix-selects its KP largest entries and tightens the threshold.  The lists are *candidates*: the bf16
 // products carry ~2^-9 relative error, so `rescore_topk_kernel` (sparse_kernels.cu) recomputes the exact fp32
 // pre-activation of every candidate from the fp32 master weights and picks the final top-k from those.
 //
@@ -34,20 +36,14 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 
 struct EncodeSmemLayout {
-  int stages, cap, list_stride;
-  size_t off_lists_val, off_lists_idx, off_bias, off_bars, total;
+  int stages;
+  size_t off_bias, off_bars, total;
 };
 
-__host__ __device__ inline EncodeSmemLayout encode_smem_layout(int stages, int cap) {
+__host__ __device__ inline EncodeSmemLayout encode_smem_layout(int stages) {
   EncodeSmemLayout L;
   L.stages = stages;
-  L.cap = cap;
-  L.list_stride = cap + 1;  // odd stride: lanes (=rows) appending at equal counts hit distinct banks
   size_t o = static_cast<size_t>(stages) * STAGE_BYTES;
-  L.off_lists_val = o;
-  o += static_cast<size_t>(BM) * L.list_stride * 4;
-  L.off_lists_idx = o;
-  o += static_cast<size_t>(BM) * L.list_stride * 4;
   L.off_bias = o;
   o += 2 * BN * 4;
   L.off_bars = (o + 7) & ~size_t(7);
@@ -56,64 +52,82 @@ __host__ __device__ inline EncodeSmemLayout encode_smem_layout(int stages, int c
   return L;
 }
 
-// Warp-cooperative compaction of one row's candidate list: keep the `KP` largest of `n` entries
-// (n <= CAP <= 64+32 handled with up to 3 entries per lane), sorted descending into slots [0, KP).
-// Returns the KP-th largest value (the new admission threshold) or -inf when n < KP.
-template <int KP, int CAP>
-__device__ __forceinline__ float compact_row(float* vals, int* idxs, int n, int lane) {
-  constexpr int PER = (CAP + 31) / 32;
-  float v[PER];
-  int id[PER];
-  int rank[PER];
+// order-preserving map float -> uint32 (larger float <=> larger key) and back
+__device__ __forceinline__ unsigned int fkey(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Warp-cooperative compaction of one row's candidate buffer (global memory, n <= CAPG entries of
+// {value bits, column}): keep the `kp` largest (ties at the threshold: lowest buffer position first), packed
+// to the front in arbitrary order.  Returns the kp-th largest value = the new admission threshold.
+// Bitwise binary search for the kp-th largest key over the CAPG/32 register-resident keys of each lane.
+template <int CAPG>
+__device__ __forceinline__ float compact_row_global(int2* buf, int n, int kp, int lane) {
+  constexpr int PER = CAPG / 32;
+  unsigned int key[PER];
+  int col[PER];
+  __syncwarp();  // orders the owner lane's appends before the cooperative loads below
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
-    const int s = lane + 32 * e;
-    v[e] = (s < n) ? vals[s] : -INFINITY;
-    id[e] = (s < n) ? idxs[s] : -1;
-    rank[e] = 0;
-  }
-  for (int s = 0; s < n; ++s) {
-    const float vs = vals[s];  // broadcast read
-#pragma unroll
-    for (int e = 0; e < PER; ++e) {
-      const int mine = lane + 32 * e;
-      rank[e] += (vs > v[e]) || (vs == v[e] && s < mine);
+    const int sl = lane + 32 * e;
+    key[e] = 0u;  // below every real key (fkey(-inf) = 0x007fffff)
+    col[e] = -1;
+    if (sl < n) {
+      const int2 t = __ldcg(buf + sl);
+      key[e] = fkey(__int_as_float(t.x));
+      col[e] = t.y;
     }
   }
+  unsigned int T = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
+    if (c >= kp) T = cand;
+  }
+  int n_gt = 0;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > T));
+  const int need_eq = kp - n_gt;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  int base = 0, eq_seen = 0;
   __syncwarp();
-  float kth = -INFINITY;
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
-    const int s = lane + 32 * e;
-    const bool keep = (s < n) && (rank[e] < KP);
-    if (keep) {
-      vals[rank[e]] = v[e];
-      idxs[rank[e]] = id[e];
-    }
-    const unsigned hit = __ballot_sync(FULL, (s < n) && (rank[e] == KP - 1));
-    if (hit) kth = __shfl_sync(FULL, v[e], __ffs(hit) - 1);
+    const bool gt = key[e] > T;
+    const bool eq = key[e] == T;
+    const unsigned int bal_eq = __ballot_sync(FULL, eq);
+    const bool take = gt || (eq && (eq_seen + __popc(bal_eq & lt_mask)) < need_eq);
+    const unsigned int bal_take = __ballot_sync(FULL, take);
+    if (take) buf[base + __popc(bal_take & lt_mask)] = make_int2(__float_as_int(funkey(key[e])), col[e]);
+    base += __popc(bal_take);
+    eq_seen += __popc(bal_eq);
   }
   __syncwarp();
-  return kth;
+  return funkey(T);
 }
 
 // EPI: 0 = running top-KP candidate lists, 1 = dense fp32 store of (acc + bias).
-template <int EPI, int KP, int CAP, int STAGES>
+template <int EPI, int CAPG, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int nterms, int kblocks_per_term, const float* __restrict__ bias, int M, int N, int m_blocks,
-                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev,
-                   float* __restrict__ cand_val, int* __restrict__ cand_idx, float* __restrict__ out, long long ldo) {
+                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int kp,
+                   int2* __restrict__ cand, float* __restrict__ out, long long ldo) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = raw_u32 + pad;
 
-  const EncodeSmemLayout L = encode_smem_layout(STAGES, CAP);
-  float* list_val = reinterpret_cast<float*>(smem + L.off_lists_val);
-  int* list_idx = reinterpret_cast<int*>(smem + L.off_lists_idx);
+  const EncodeSmemLayout L = encode_smem_layout(STAGES);
   float* bias_s = reinterpret_cast<float*>(smem + L.off_bias);
   const uint32_t bars = smem_base + static_cast<uint32_t>(L.off_bars);
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -219,9 +233,10 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int row_local = q * 32 + lane;    // accumulator row == TMEM lane
     const int row = m_blk * BM + row_local;
-    float* my_val = list_val + row_local * L.list_stride;
-    int* my_idx = list_idx + row_local * L.list_stride;
-    float tau = -INFINITY;
+    // candidate buffer of this thread's row (global memory, CAPG entries per (row, split))
+    int2* warp_buf = cand + (static_cast<long long>(m_blk * BM + q * 32) * nsplit + split) * CAPG;
+    int2* my_buf = warp_buf + static_cast<long long>(lane) * nsplit * CAPG;
+    float tau = (row < M) ? -INFINITY : INFINITY;  // rows past the batch never admit anything
     int cnt = 0;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
 
@@ -230,8 +245,13 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const uint32_t aphase = (t >> 1) & 1u;
       const int n0 = (tile_begin + t) * BN;
       float* bs = bias_s + as * BN;
-      // stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below)
-      for (int c = et; c < BN; c += 128) bs[c] = (bias != nullptr && n0 + c < n_cols) ? bias[n0 + c] : 0.f;
+      // Stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below).
+      // Columns past the end get -inf in the top-k epilogue so that they can never be admitted.
+      for (int c = et; c < BN; c += 128) {
+        float bv = (EPI == 0) ? -INFINITY : 0.f;
+        if (n0 + c < n_cols) bv = (bias != nullptr) ? bias[n0 + c] : 0.f;
+        bs[c] = bv;
+      }
       named_bar_sync(1, 128);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -241,47 +261,56 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // being filtered the tcgen05.ld of chunk c+1 is in flight.
       auto process = [&](uint32_t (&a)[CHUNK], int c) {
         const int col0 = n0 + c * CHUNK;
-        if (EPI == 0) {
-          // make room: every lane must be able to take CHUNK appends
-          unsigned need = __ballot_sync(FULL, cnt > CAP - CHUNK);
-          while (need) {
-            const int l = __ffs(need) - 1;
-            need &= need - 1;
-            const int n = __shfl_sync(FULL, cnt, l);
-            const float kth = compact_row<KP, CAP>(list_val + (q * 32 + l) * L.list_stride,
-                                                   list_idx + (q * 32 + l) * L.list_stride, n, lane);
-            if (lane == l) {
-              cnt = KP;
-              tau = kth;
-            }
-          }
+        float v[CHUNK];
 #pragma unroll
-          for (int i = 0; i < CHUNK; ++i) {
-            const float v = __uint_as_float(a[i]) + bs[c * CHUNK + i];
-            if (v > tau && col0 + i < n_cols) {
-              my_val[cnt] = v;
-              my_idx[cnt] = col0 + i;
-              ++cnt;
+        for (int i = 0; i < CHUNK; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + c * CHUNK + i);  // broadcast read
+          v[i] = __uint_as_float(a[i]) + b4.x;
+          v[i + 1] = __uint_as_float(a[i + 1]) + b4.y;
+          v[i + 2] = __uint_as_float(a[i + 2]) + b4.z;
+          v[i + 3] = __uint_as_float(a[i + 3]) + b4.w;
+        }
+        if (EPI == 0) {
+          // fast path: one compare of the chunk maximum against the row's admission threshold
+          float m01 = fmaxf(fmaxf(v[0], v[1]), v[2]), m02 = fmaxf(fmaxf(v[3], v[4]), v[5]);
+          float m03 = fmaxf(fmaxf(v[6], v[7]), v[8]), m04 = fmaxf(fmaxf(v[9], v[10]), v[11]);
+          float m05 = fmaxf(fmaxf(v[12], v[13]), v[14]);
+          const float mx = fmaxf(fmaxf(fmaxf(m01, m02), fmaxf(m03, m04)), fmaxf(m05, v[15]));
+          const bool hit = mx > tau;
+          if (__any_sync(FULL, hit)) {
+            if (hit) {
+#pragma unroll
+              for (int i = 0; i < CHUNK; ++i) {
+                if (v[i] > tau) {
+                  my_buf[cnt] = make_int2(__float_as_int(v[i]), col0 + i);
+                  ++cnt;
+                }
+              }
+            }
+            // keep room for one more chunk in every row buffer of this warp
+            unsigned need = __ballot_sync(FULL, cnt > CAPG - CHUNK);
+            while (need) {
+              const int l = __ffs(need) - 1;
+              need &= need - 1;
+              const int n = __shfl_sync(FULL, cnt, l);
+              const float kth = compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, kp, lane);
+              if (lane == l) {
+                cnt = kp;
+                tau = kth;
+              }
             }
           }
-          __syncwarp();
         } else {
           if (row < M) {
             float* o = out + static_cast<long long>(row) * ldo + col0;
             if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < CHUNK; i += 4) {
-                float4 w;
-                w.x = __uint_as_float(a[i]) + bs[c * CHUNK + i];
-                w.y = __uint_as_float(a[i + 1]) + bs[c * CHUNK + i + 1];
-                w.z = __uint_as_float(a[i + 2]) + bs[c * CHUNK + i + 2];
-                w.w = __uint_as_float(a[i + 3]) + bs[c * CHUNK + i + 3];
-                *reinterpret_cast<float4*>(o + i) = w;
-              }
+              for (int i = 0; i < CHUNK; i += 4)
+                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i)
-                if (col0 + i < n_cols) o[i] = __uint_as_float(a[i]) + bs[c * CHUNK + i];
+                if (col0 + i < n_cols) o[i] = v[i];
             }
           }
         }
@@ -306,21 +335,16 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
 
     if (EPI == 0) {
-      // final compaction of all 32 rows of this warp, then a coalesced write of the KP-entry lists
+      // final compaction: every row buffer ends with its <= kp best candidates at the front, padded with
+      // (-inf, -1) so that the re-score kernel can read exactly kp entries per (row, split)
       for (int l = 0; l < 32; ++l) {
         const int n = __shfl_sync(FULL, cnt, l);
-        float* rv = list_val + (q * 32 + l) * L.list_stride;
-        int* ri = list_idx + (q * 32 + l) * L.list_stride;
-        compact_row<KP, CAP>(rv, ri, n, lane);
-        const int keep = min(n, KP);
         const int grow = m_blk * BM + q * 32 + l;
-        if (grow < M) {
-          const long long base = (static_cast<long long>(grow) * nsplit + split) * KP;
-          for (int s = lane; s < KP; s += 32) {
-            cand_val[base + s] = (s < keep) ? rv[s] : -INFINITY;
-            cand_idx[base + s] = (s < keep) ? ri[s] : -1;
-          }
-        }
+        if (grow >= M) continue;  // warp-uniform
+        int2* rb = warp_buf + static_cast<long long>(l) * nsplit * CAPG;
+        if (n > kp) compact_row_global<CAPG>(rb, n, kp, lane);
+        __syncwarp();
+        for (int sl = min(n, kp) + lane; sl < kp; sl += 32) rb[sl] = make_int2(__float_as_int(-INFINITY), -1);
       }
     }
   }
@@ -367,11 +391,11 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, lon
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-template <int EPI, int KP, int CAP, int STAGES>
+template <int EPI, int CAPG, int STAGES>
 static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int m_blocks, int tiles_per_split,
                           int nsplit, cudaStream_t stream) {
-  auto kern = encode_gemm_kernel<EPI, KP, CAP, STAGES>;
-  const EncodeSmemLayout L = encode_smem_layout(STAGES, CAP);
+  auto kern = encode_gemm_kernel<EPI, CAPG, STAGES>;
+  const EncodeSmemLayout L = encode_smem_layout(STAGES);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.total)) !=
@@ -382,8 +406,8 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
   const int kblocks_per_term = (a.K + BK - 1) / BK;
   kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], a.nterms,
                                                            kblocks_per_term, a.bias, a.M, a.N, m_blocks,
-                                                           tiles_per_split, nsplit, a.n_limit_dev, a.cand_val,
-                                                           a.cand_idx, a.out, a.ldo);
+                                                           tiles_per_split, nsplit, a.n_limit_dev, a.kp,
+                                                           reinterpret_cast<int2*>(a.cand), a.out, a.ldo);
                                                            ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
@@ -401,9 +425,9 @@ int encode_gemm_nsplit(int M, int N, int num_sms) {
 }
 
 int encode_gemm_kp(int top_k) {
-  if (top_k <= 32) return 40;
-  if (top_k <= 64) return 72;
-  return -1;
+  // candidate list length: k plus a margin for rank changes between the bf16 screen and the exact re-score
+  if (top_k + 8 > ENCODE_CAPG / 2) return -1;
+  return top_k + 8;
 }
 
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
@@ -427,13 +451,12 @@ int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
     int nsplit = a.nsplit > 0 ? a.nsplit : encode_gemm_nsplit(a.M, a.N, a.num_sms);
     const int tps = (n_tiles + nsplit - 1) / nsplit;
     nsplit = (n_tiles + tps - 1) / tps;
-    return launch_variant<1, 8, 8, 4>(a, maps, m_blocks, tps, nsplit, stream);
+    return launch_variant<1, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
   }
   const int nsplit = a.nsplit;
   const int tps = (n_tiles + nsplit - 1) / nsplit;
-  if (a.kp == 40) return launch_variant<0, 40, 64, 3>(a, maps, m_blocks, tps, nsplit, stream);
-  if (a.kp == 72) return launch_variant<0, 72, 96, 2>(a, maps, m_blocks, tps, nsplit, stream);
-  return 12;
+  if (a.kp <= 0 || a.kp > ENCODE_CAPG / 2 || a.cand == nullptr) return 12;
+  return launch_variant<0, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
 }
 
 }  // namespace sb

@@ -8,6 +8,7 @@
 namespace sb {
 
 constexpr int ENCODE_MAX_NSPLIT = 8;
+constexpr int ENCODE_CAPG = 256;  // entries per (row, split) candidate buffer of the top-k screen
 
 // number of kernels this library has launched (all handles); read through saev_b200_launch_count()
 extern unsigned long long g_launch_count;
@@ -26,8 +27,7 @@ struct EncodeGemmArgs {
   int kp = 40;                          // candidate list length (epilogue 0)
   int nsplit = 1;                       // column splits (epilogue 0: lists are [M, nsplit, kp])
   int num_sms = 148;
-  float* cand_val = nullptr;
-  int* cand_idx = nullptr;
+  void* cand = nullptr;                 // epilogue 0: [M(rounded up to 128), nsplit, ENCODE_CAPG] x {value bits, column}
   float* out = nullptr;                 // epilogue 1: [M, ldo]
   long long ldo = 0;
 };
@@ -40,7 +40,7 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
 
 struct RescoreArgs {
-  const float* cand_val; const int* cand_idx; int nsplit; int kp;
+  const void* cand; int cand_stride; int nsplit; int kp;   // kp entries at the front of each (row, split) buffer
   const float* x; const float* W_enc_t; const float* b_enc;
   int B, D, S, K;
   int* topk_idx; float* topk_val;

@@ -127,10 +127,12 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
   int* ki = reinterpret_cast<int*>(base + 2 * ncand + KP);
   float* ke = base + 2 * ncand + 2 * KP;
 
-  const long long cbase = static_cast<long long>(b) * ncand;
+  // candidates: the first kp entries of each (row, split) buffer written by the screening GEMM
+  const int2* cbuf = reinterpret_cast<const int2*>(a.cand) + static_cast<long long>(b) * a.nsplit * a.cand_stride;
   for (int s = lane; s < ncand; s += 32) {
-    sv[s] = a.cand_val[cbase + s];
-    si[s] = a.cand_idx[cbase + s];
+    const int2 e = cbuf[static_cast<long long>(s / KP) * a.cand_stride + (s % KP)];
+    sv[s] = __int_as_float(e.x);
+    si[s] = e.y;
   }
   __syncwarp();
   if (a.nsplit == 1) {
@@ -191,7 +193,9 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
   __syncwarp();
 
   // final selection on exact values; order: value desc, then feature index asc, then position
-  float err = 0.f;
+  float err2 = 0.f;            // sum of squared screen errors over the valid candidates
+  float tmin = INFINITY;       // smallest screen value among the kept candidates
+  int nvalid = 0;
   float vk = -INFINITY;
   for (int c = lane; c < ((KP + 31) & ~31); c += 32) {
     const bool valid = c < KP;
@@ -204,7 +208,12 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
         const int it = ki[t];
         rank += (vt > v) || (vt == v && (it < id || (it == id && t < c)));
       }
-      if (id >= 0) err = fmaxf(err, fabsf(kv[c] - v));
+      if (id >= 0) {
+        const float d = kv[c] - v;
+        err2 += d * d;
+        tmin = fminf(tmin, kv[c]);
+        ++nvalid;
+      }
       if (rank < a.K && id >= 0) {
         const long long o = static_cast<long long>(b) * a.K + rank;
         a.topk_idx[o] = id;
@@ -216,12 +225,16 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
     const unsigned hit = __ballot_sync(FULL, valid && rank == a.K - 1);
     if (hit) vk = __shfl_sync(FULL, v, __ffs(hit) - 1);
   }
+  err2 = warp_sum(err2);
+  nvalid = warp_sum(nvalid);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL, err, o));
-  if (lane == 0 && a.unsafe_rows != nullptr && ki[KP - 1] >= 0) {
-    // every column outside the list has screen value <= kv[KP-1]; flag the row when the k-th exact
-    // value is not clear of that by several times the largest screen error seen on this row
-    if (vk - kv[KP - 1] < 4.f * err) atomicAdd(a.unsafe_rows, 1u);
+  for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(FULL, tmin, o));
+  if (lane == 0 && a.unsafe_rows != nullptr && nvalid == KP) {
+    // Every column outside the list has a screen value <= tmin.  Flag the row when the k-th exact value is
+    // not clear of tmin by 6 sigma of the screen error observed on this row's own candidates (diagnostic:
+    // a flagged row is still almost surely right; an unflagged one is wrong with probability ~1e-9).
+    const float sigma = sqrtf(err2 / static_cast<float>(KP));
+    if (vk - tmin < 6.f * sigma) atomicAdd(a.unsafe_rows, 1u);
   }
 }
 

@@ -20,7 +20,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
 };
 
@@ -30,7 +30,6 @@ struct saev_b200_handle {
   saev_b200_cfg cfg;
   int device = 0;
   int num_sms = 148;
-  int kp = 40;
   int aux_cap = 0;
   Workspace ws;
   bool last_forward_training = false;
@@ -63,7 +62,7 @@ int check_cuda(const saev_b200_handle* h, const char* where) {
   return fail(h, 100, "CUDA error at %s", buf);
 }
 
-Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
+Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap) {
   Workspace w;
   const size_t S = c.d_sae, D = c.d_model, B = c.max_batch, K = c.top_k;
   size_t o = 0;
@@ -80,6 +79,8 @@ Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
     const size_t m_blocks = (B + 127) / 128;
     const size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
     w.cand = take(row_splits * ENCODE_CAPG * 8);
+    w.cand_cnt = take(row_splits * 4);
+    w.row_margin = take(128 * m_blocks * 4);
   }
   w.dh = take(B * K * 4);
   w.row_sse = take(B * 4);
@@ -92,7 +93,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int kp, int aux_cap) {
   w.entries = take(B * K * 4);
   w.active = take(S * 4);
   w.dead_list = take(S * 4);
-  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] sumsq scratch
+  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [4] max_j ||W_enc_t[j]||^2
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
   w.sumsq_partial = take(1024 * 8);
   if (c.aux_kind == SAEV_B200_AUX_AUXK) {
@@ -154,8 +155,8 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     return fail(nullptr, 3, "saev_b200_create: only the TopK activation has a CUDA path in this build%s");
   if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
     return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
-  const int kp = encode_gemm_kp(cfg->top_k);
-  if (kp < 0) return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
+  if (cfg->top_k > encode_gemm_max_top_k())
+    return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
   int dev = 0, cc_major = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
     cudaGetLastError();
@@ -170,9 +171,8 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   h->cfg = *cfg;
   h->device = dev;
   h->num_sms = sms;
-  h->kp = kp;
   h->aux_cap = (cfg->aux_cols_cap > 0 && cfg->aux_cols_cap < cfg->d_sae) ? cfg->aux_cols_cap : cfg->d_sae;
-  h->ws = plan_workspace(h->cfg, kp, h->aux_cap);
+  h->ws = plan_workspace(h->cfg, h->aux_cap);
   h->err[0] = 0;
   *out = h;
   return 0;
@@ -235,6 +235,8 @@ int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* work
   cudaMemsetAsync(at<char>(workspace, h->ws.scalars), 0, 64, s);
   if (launch_split_bf16(W_enc_t, at<__nv_bfloat16>(workspace, h->ws.shadow_hi), nullptr, n, s))
     return fail(h, 30, "sync_weights: split_bf16 launch failed%s");
+  if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + 4, s))
+    return fail(h, 30, "sync_weights: row-norm launch failed%s");
   return check_cuda(h, "sync_weights");
 }
 
@@ -264,8 +266,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
     {
       StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
-      if (launch_split_bf16(x, x_hi, nullptr, static_cast<long long>(B) * D, s))
-        return fail(h, 41, "forward: split_bf16 launch failed%s");
+      if (launch_prep_x(x, B, D, x_hi, at<float>(workspace, w.row_margin), s))
+        return fail(h, 41, "forward: prep_x launch failed%s");
     }
 
     EncodeGemmArgs g;
@@ -277,7 +279,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.K = D;
     g.bias = b_enc;
     g.epilogue = 0;
-    g.kp = h->kp;
+    g.top_k = K;
+    g.row_margin = at<float>(workspace, w.row_margin);
+    g.wnorm_sq_max = at<float>(workspace, w.scalars) + 4;
+    g.cand_cnt = at<int>(workspace, w.cand_cnt);
     g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
@@ -292,9 +297,11 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
 
     RescoreArgs r;
     r.cand = g.cand;
+    r.cand_cnt = g.cand_cnt;
     r.cand_stride = ENCODE_CAPG;
     r.nsplit = g.nsplit;
-    r.kp = h->kp;
+    r.row_margin = g.row_margin;
+    r.wnorm_sq_max = g.wnorm_sq_max;
     r.x = x;
     r.W_enc_t = W_enc_t;
     r.b_enc = b_enc;
@@ -497,6 +504,7 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.m = m_flat;
   a.v = v_flat;
   a.shadow_hi = workspace ? at<__nv_bfloat16>(workspace, h->ws.shadow_hi) : nullptr;
+  a.wnorm_sq_max = workspace ? at<float>(workspace, h->ws.scalars) + 4 : nullptr;
   a.D = static_cast<int>(D);
   a.S = static_cast<int>(S);
   a.lr = lr;

@@ -7,9 +7,14 @@
 // TMEM (one thread = one batch row) and keep a running list of the KP largest pre-activations of their row:
 // a register-resident admission threshold filters each 16-column chunk (max-tree, one compare), the rare
 // survivors are appended to a per-row buffer in global memory (L2 resident), and when a buffer fills up the
-// warp cooperatively radix-selects its KP largest entries and tightens the threshold.  The lists are *candidates*: the bf16
-// products carry ~2^-9 relative error, so `rescore_topk_kernel` (sparse_kernels.cu) recomputes the exact fp32
+// warp cooperatively radix-selects and tightens the threshold.  The lists are *candidates*: the bf16 products
+// carry ~2^-9 relative error, so `rescore_topk_kernel` (sparse_kernels.cu) recomputes the exact fp32
 // pre-activation of every candidate from the fp32 master weights and picks the final top-k from those.
+//
+// Admission rule (what makes the candidate set provably cover the exact top-k): a column is kept iff its screen
+// value exceeds  (k-th largest screen value of the row so far) - margin_b,  margin_b = 2 * E_b, where E_b bounds
+// the screen error |h~ - h| of row b (6 sigma of the bf16 rounding noise, from ||x_b||_inf and max_j ||W_enc_t[j]||).
+// If every error is <= E_b then every exact top-k column has h~ >= h_k - E_b > (h~)_k - 2 E_b, i.e. is kept.
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Pipelines: STAGES-deep smem ring (TMA <-> MMA),
@@ -61,12 +66,28 @@ __device__ __forceinline__ float funkey(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// k-th largest key among the register-resident keys of the warp (bitwise binary search; 0 if fewer than k).
+template <int PER>
+__device__ __forceinline__ unsigned int warp_kth_largest(const unsigned int (&key)[PER], int k) {
+  unsigned int T = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
+    if (c >= k) T = cand;
+  }
+  return T;
+}
+
 // Warp-cooperative compaction of one row's candidate buffer (global memory, n <= CAPG entries of
-// {value bits, column}): keep the `kp` largest (ties at the threshold: lowest buffer position first), packed
-// to the front in arbitrary order.  Returns the kp-th largest value = the new admission threshold.
-// Bitwise binary search for the kp-th largest key over the CAPG/32 register-resident keys of each lane.
+// {value bits, column}): keep every entry whose value exceeds (k-th largest value) - margin, packed to the
+// front in arbitrary order; if more than CAPG/2 entries qualify, keep the CAPG/2 largest and report overflow.
+// Returns the new admission threshold; n_out = entries kept (ovf set on overflow).
 template <int CAPG>
-__device__ __forceinline__ float compact_row_global(int2* buf, int n, int kp, int lane) {
+__device__ __forceinline__ float compact_row_global(int2* buf, int n, int k, float margin, int lane, int& n_out,
+                                                    bool& ovf) {
   constexpr int PER = CAPG / 32;
   unsigned int key[PER];
   int col[PER];
@@ -82,35 +103,42 @@ __device__ __forceinline__ float compact_row_global(int2* buf, int n, int kp, in
       col[e] = t.y;
     }
   }
-  unsigned int T = 0u;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const unsigned int cand = T | (1u << bit);
-    int c = 0;
+  ovf = false;
+  float thr = funkey(warp_kth_largest<PER>(key, k)) - margin;
+  unsigned int tkey = fkey(thr);
+  int n_ge = 0, n_gt = 0;
 #pragma unroll
-    for (int e = 0; e < PER; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
-    if (c >= kp) T = cand;
+  for (int e = 0; e < PER; ++e) {
+    n_ge += __popc(__ballot_sync(FULL, key[e] >= tkey));
+    n_gt += __popc(__ballot_sync(FULL, key[e] > tkey));
   }
-  int n_gt = 0;
+  int need_eq = n_ge - n_gt;  // normal case: keep every entry >= threshold
+  if (n_ge > CAPG / 2) {      // pathological row: more near-ties than the buffer can carry
+    ovf = true;
+    tkey = warp_kth_largest<PER>(key, CAPG / 2);
+    thr = funkey(tkey);
+    n_gt = 0;
 #pragma unroll
-  for (int e = 0; e < PER; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > T));
-  const int need_eq = kp - n_gt;
+    for (int e = 0; e < PER; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > tkey));
+    need_eq = CAPG / 2 - n_gt;  // ties at the cut: lowest buffer position first
+  }
   const unsigned int lt_mask = (1u << lane) - 1u;
   int base = 0, eq_seen = 0;
   __syncwarp();
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
-    const bool gt = key[e] > T;
-    const bool eq = key[e] == T;
+    const bool gt = key[e] > tkey;
+    const bool eq = key[e] == tkey;
     const unsigned int bal_eq = __ballot_sync(FULL, eq);
     const bool take = gt || (eq && (eq_seen + __popc(bal_eq & lt_mask)) < need_eq);
-    const unsigned int bal_take = __ballot_sync(FULL, take);
-    if (take) buf[base + __popc(bal_take & lt_mask)] = make_int2(__float_as_int(funkey(key[e])), col[e]);
-    base += __popc(bal_take);
+    const unsigned int bal = __ballot_sync(FULL, take);
+    if (take) buf[base + __popc(bal & lt_mask)] = make_int2(__float_as_int(funkey(key[e])), col[e]);
+    base += __popc(bal);
     eq_seen += __popc(bal_eq);
   }
   __syncwarp();
-  return funkey(T);
+  n_out = base;
+  return thr;
 }
 
 // EPI: 0 = running top-KP candidate lists, 1 = dense fp32 store of (acc + bias).
@@ -119,8 +147,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    int nterms, int kblocks_per_term, const float* __restrict__ bias, int M, int N, int m_blocks,
-                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int kp,
-                   int2* __restrict__ cand, float* __restrict__ out, long long ldo) {
+                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int top_k,
+                   const float* __restrict__ row_margin, const float* __restrict__ wnorm_sq_max,
+                   int2* __restrict__ cand, int* __restrict__ cand_cnt, float* __restrict__ out, long long ldo) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
@@ -238,6 +267,9 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     int2* my_buf = warp_buf + static_cast<long long>(lane) * nsplit * CAPG;
     float tau = (row < M) ? -INFINITY : INFINITY;  // rows past the batch never admit anything
     int cnt = 0;
+    bool overflowed = false;
+    // margin_b = 2 E_b:  row_margin[b] = c * ||x_b||_inf (prep kernel), times the largest encoder-row norm
+    const float margin = (EPI == 0 && row < M) ? row_margin[row] * sqrtf(*wnorm_sq_max) : 0.f;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
 
     for (int t = 0; t < num_tiles; ++t) {
@@ -293,10 +325,15 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               const int l = __ffs(need) - 1;
               need &= need - 1;
               const int n = __shfl_sync(FULL, cnt, l);
-              const float kth = compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, kp, lane);
+              const float mg = __shfl_sync(FULL, margin, l);
+              int n_out;
+              bool ovf;
+              const float thr = compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, top_k,
+                                                         mg, lane, n_out, ovf);
               if (lane == l) {
-                cnt = kp;
-                tau = kth;
+                cnt = n_out;
+                tau = thr;
+                overflowed |= ovf;
               }
             }
           }
@@ -335,16 +372,21 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
 
     if (EPI == 0) {
-      // final compaction: every row buffer ends with its <= kp best candidates at the front, padded with
-      // (-inf, -1) so that the re-score kernel can read exactly kp entries per (row, split)
+      // final compaction: trim every row buffer to the columns within the margin of its k-th largest screen
+      // value and publish the count (negative = the buffer overflowed at some point: the row is not covered)
       for (int l = 0; l < 32; ++l) {
         const int n = __shfl_sync(FULL, cnt, l);
+        const float mg = __shfl_sync(FULL, margin, l);
         const int grow = m_blk * BM + q * 32 + l;
         if (grow >= M) continue;  // warp-uniform
-        int2* rb = warp_buf + static_cast<long long>(l) * nsplit * CAPG;
-        if (n > kp) compact_row_global<CAPG>(rb, n, kp, lane);
-        __syncwarp();
-        for (int sl = min(n, kp) + lane; sl < kp; sl += 32) rb[sl] = make_int2(__float_as_int(-INFINITY), -1);
+        int n_out = n;
+        bool ovf = false;
+        if (n > top_k)
+          compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, top_k, mg, lane, n_out, ovf);
+        if (lane == l) {
+          overflowed |= ovf;
+          cand_cnt[static_cast<long long>(grow) * nsplit + split] = overflowed ? -n_out : n_out;
+        }
       }
     }
   }
@@ -406,8 +448,9 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
   const int kblocks_per_term = (a.K + BK - 1) / BK;
   kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], a.nterms,
                                                            kblocks_per_term, a.bias, a.M, a.N, m_blocks,
-                                                           tiles_per_split, nsplit, a.n_limit_dev, a.kp,
-                                                           reinterpret_cast<int2*>(a.cand), a.out, a.ldo);
+                                                           tiles_per_split, nsplit, a.n_limit_dev, a.top_k,
+                                                           a.row_margin, a.wnorm_sq_max,
+                                                           reinterpret_cast<int2*>(a.cand), a.cand_cnt, a.out, a.ldo);
                                                            ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
@@ -424,11 +467,7 @@ int encode_gemm_nsplit(int M, int N, int num_sms) {
   return (n_tiles + tps - 1) / tps;
 }
 
-int encode_gemm_kp(int top_k) {
-  // candidate list length: k plus a margin for rank changes between the bf16 screen and the exact re-score
-  if (top_k + 8 > ENCODE_CAPG / 2) return -1;
-  return top_k + 8;
-}
+int encode_gemm_max_top_k() { return ENCODE_CAPG / 4; }
 
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return 0;
@@ -455,7 +494,9 @@ int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
   }
   const int nsplit = a.nsplit;
   const int tps = (n_tiles + nsplit - 1) / nsplit;
-  if (a.kp <= 0 || a.kp > ENCODE_CAPG / 2 || a.cand == nullptr) return 12;
+  if (a.top_k <= 0 || a.top_k > encode_gemm_max_top_k() || a.cand == nullptr || a.cand_cnt == nullptr ||
+      a.row_margin == nullptr || a.wnorm_sq_max == nullptr)
+    return 12;
   return launch_variant<0, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
 }
 

@@ -24,23 +24,31 @@ struct EncodeGemmArgs {
   const float* bias = nullptr;          // [N] or null
   const int* n_limit_dev = nullptr;     // optional device-side column count (<= N)
   int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store
-  int kp = 40;                          // candidate list length (epilogue 0)
-  int nsplit = 1;                       // column splits (epilogue 0: lists are [M, nsplit, kp])
+  int top_k = 32;                       // epilogue 0: k of the final selection
+  const float* row_margin = nullptr;    // epilogue 0: [M] admission margin per row / max encoder-row norm
+  const float* wnorm_sq_max = nullptr;  // epilogue 0: device scalar, max_j ||B[j]||^2 of the fp32 weights
+  int nsplit = 1;                       // column splits (epilogue 0: one candidate buffer per (row, split))
   int num_sms = 148;
+  int* cand_cnt = nullptr;              // epilogue 0: [M, nsplit] entries kept (negative: overflowed)
   void* cand = nullptr;                 // epilogue 0: [M(rounded up to 128), nsplit, ENCODE_CAPG] x {value bits, column}
   float* out = nullptr;                 // epilogue 1: [M, ldo]
   long long ldo = 0;
 };
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream);
 int encode_gemm_nsplit(int M, int N, int num_sms);
-int encode_gemm_kp(int top_k);  // candidate list length for a given k, or -1 if unsupported
+int encode_gemm_max_top_k();
 
 // ---- sparse_kernels.cu ----------------------------------------------------------------------------------
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s);
+// x[B,D] -> bf16 copy + per-row admission margin factor  c * ||x_b||_inf   (see encode_gemm.cu)
+int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s);
+// *out = max_j ||W[j,:]||^2
+int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s);
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
 
 struct RescoreArgs {
-  const void* cand; int cand_stride; int nsplit; int kp;   // kp entries at the front of each (row, split) buffer
+  const void* cand; const int* cand_cnt; int cand_stride; int nsplit;  // (row, split) candidate buffers
+  const float* row_margin; const float* wnorm_sq_max;
   const float* x; const float* W_enc_t; const float* b_enc;
   int B, D, S, K;
   int* topk_idx; float* topk_val;
@@ -86,6 +94,7 @@ struct AdamArgs {
   const float* gW_enc_t; const float* gb_enc; const float* gW_dec; const float* gb_dec;
   float* m; float* v;          // flat, same order/offsets as the gradient bucket
   __nv_bfloat16* shadow_hi;    // bf16 copy of W_enc_t for the tensor-core screen (may be null)
+  float* wnorm_sq_max;         // device scalar: max_j ||W_enc_t[j]||^2 after the update (zeroed by the launcher)
   int D, S;
   float lr, beta1, beta2, eps, bc1, bc2_sqrt;
   float max_norm; float grad_scale; const float* gnorm_sq;

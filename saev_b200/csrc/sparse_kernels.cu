@@ -73,6 +73,65 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// x[B,D] -> bf16 operand + admission-margin factor of the top-k screen, one warp per row.
+//   The screen computes h~ = <bf16(x), bf16(w)>; with relative roundings eps in [-2^-9, 2^-9] (variance 2^-18/3
+//   each) its error has sigma_e = 2^-9 sqrt(2/3) sqrt(sum_d x_d^2 w_d^2) <= 2^-9 sqrt(2/3) ||x||_inf ||w||_2.
+//   E_b = 6 sigma_e bounds it, the admission margin is 2 E_b:
+//       row_margin[b] = 12 * sqrt(2/3) * 2^-9 * ||x_b||_inf        (times max_j ||w_j||_2 in the GEMM)
+// ------------------------------------------------------------------------------------------------
+constexpr float MARGIN_C = 12.0f * 0.81649658f * 0.001953125f;
+
+__global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, int B, int D,
+                                                     __nv_bfloat16* __restrict__ x_hi, float* __restrict__ row_margin) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31, D4 = D >> 2;
+  const float* row = x + static_cast<long long>(b) * D;
+  __nv_bfloat16* orow = x_hi + static_cast<long long>(b) * D;
+  float mx = 0.f;
+  for (int v = lane; v < D4; v += 32) {
+    const float4 q = ldg4(row + 4 * v);
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(orow + 4 * v);
+    o[0] = __nv_bfloat162(__float2bfloat16_rn(q.x), __float2bfloat16_rn(q.y));
+    o[1] = __nv_bfloat162(__float2bfloat16_rn(q.z), __float2bfloat16_rn(q.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+  if (lane == 0) row_margin[b] = MARGIN_C * mx;
+}
+int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s) {
+  if (D % 4) return 21;
+  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x_hi, row_margin);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// *out = max_j ||W[j,:]||^2   (non-negative floats order like their bit patterns: atomicMax on int)
+__global__ void __launch_bounds__(256) row_sumsq_max_kernel(const float* __restrict__ W, int rows, int D,
+                                                            float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  float best = 0.f;
+  for (int j = blockIdx.x * 8 + (threadIdx.x >> 5); j < rows; j += gridDim.x * 8) {
+    const float* row = W + static_cast<long long>(j) * D;
+    float ss = 0.f;
+    for (int v = lane; v < (D >> 2); v += 32) {
+      const float4 q = ldg4(row + 4 * v);
+      ss += dot4(q, q);
+    }
+    best = fmaxf(best, warp_sum(ss));
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
+}
+int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s) {
+  if (cols % 4) return 21;
+  if (cudaMemsetAsync(out, 0, 4, s) != cudaSuccess) return 23;
+  row_sumsq_max_kernel<<<148 * 4, 256, 0, s>>>(W, rows, cols, out);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
 // W[j,:] /= ||W[j,:]||_2      (saev modeling.py:411-417 normalize_w_dec)
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
@@ -109,54 +168,84 @@ int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Merge the per-split candidate lists of a row, recompute the exact fp32 pre-activation of each
+// Merge the per-split candidate buffers of a row, recompute the exact fp32 pre-activation of each
 // candidate (h = <x_b, W_enc_t[j]> + b_enc[j], saev modeling.py:344-347) and select the top-k of
 // those (TopKActivation.forward, modeling.py:169-179: no ReLU, exactly k kept).  One warp per row.
 // ------------------------------------------------------------------------------------------------
+constexpr int RESCORE_WARPS = 4;
+
+__device__ __forceinline__ unsigned int fkey_s(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey_s(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 template <int VPL>
-__global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
+__global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(RescoreArgs a) {
   extern __shared__ float smem_f[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + warp;
+  const int b = blockIdx.x * RESCORE_WARPS + warp;
   if (b >= a.B) return;
-  const int KP = a.kp, ncand = a.nsplit * a.kp, D4 = a.D >> 2;
-  float* base = smem_f + static_cast<size_t>(warp) * (2 * ncand + 3 * KP);
-  float* sv = base;
-  int* si = reinterpret_cast<int*>(base + ncand);
-  float* kv = base + 2 * ncand;
-  int* ki = reinterpret_cast<int*>(base + 2 * ncand + KP);
-  float* ke = base + 2 * ncand + 2 * KP;
+  const int D4 = a.D >> 2;
+  const int cap = a.nsplit * (a.cand_stride / 2);  // most candidates a row can bring
+  float* base = smem_f + static_cast<size_t>(warp) * (3 * cap);
+  float* sv = base;                                  // screen values
+  int* si = reinterpret_cast<int*>(base + cap);      // columns
+  float* se = base + 2 * cap;                        // exact values
 
-  // candidates: the first kp entries of each (row, split) buffer written by the screening GEMM
+  // ---- gather the candidates of all splits ----
   const int2* cbuf = reinterpret_cast<const int2*>(a.cand) + static_cast<long long>(b) * a.nsplit * a.cand_stride;
-  for (int s = lane; s < ncand; s += 32) {
-    const int2 e = cbuf[static_cast<long long>(s / KP) * a.cand_stride + (s % KP)];
-    sv[s] = __int_as_float(e.x);
-    si[s] = e.y;
+  int n = 0;
+  bool overflow = false;
+  for (int sp = 0; sp < a.nsplit; ++sp) {
+    int c = a.cand_cnt[static_cast<long long>(b) * a.nsplit + sp];
+    if (c < 0) {
+      overflow = true;
+      c = -c;
+    }
+    for (int e = lane; e < c; e += 32) {
+      const int2 t = cbuf[static_cast<long long>(sp) * a.cand_stride + e];
+      sv[n + e] = __int_as_float(t.x);
+      si[n + e] = t.y;
+    }
+    n += c;
   }
   __syncwarp();
-  if (a.nsplit == 1) {
-    for (int s = lane; s < KP; s += 32) {
-      kv[s] = sv[s];
-      ki[s] = si[s];
+  const float margin = a.row_margin[b] * sqrtf(*a.wnorm_sq_max);
+  if (a.nsplit > 1 && n > a.K) {
+    // each split applied the margin to ITS k-th largest; re-apply it to the row's k-th largest
+    unsigned int T = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned int cand = T | (1u << bit);
+      int c = 0;
+      for (int e = lane; e < n; e += 32) c += fkey_s(sv[e]) >= cand;
+      c = warp_sum(c);
+      if (c >= a.K) T = cand;
     }
-  } else {
-    for (int s = lane; s < ncand; s += 32) {
-      const float v = sv[s];
-      int rank = 0;
-      for (int t = 0; t < ncand; ++t) {
-        const float vt = sv[t];
-        rank += (vt > v) || (vt == v && t < s);
+    const float thr = funkey_s(T) - margin;
+    // in-place stable compaction (reads run ahead of writes)
+    int kept = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      const float v = (e < n) ? sv[e] : 0.f;
+      const int id = (e < n) ? si[e] : -1;
+      const bool take = (e < n) && v >= thr;
+      const unsigned bal = __ballot_sync(FULL, take);
+      __syncwarp();
+      if (take) {
+        const int o = kept + __popc(bal & ((1u << lane) - 1u));
+        sv[o] = v;
+        si[o] = id;
       }
-      if (rank < KP) {
-        kv[rank] = v;
-        ki[rank] = si[s];
-      }
+      kept += __popc(bal);
+      __syncwarp();
     }
+    n = kept;
   }
-  __syncwarp();
 
-  // exact rescoring, 4 candidates in flight
+  // ---- exact re-score, 4 candidates in flight ----
   float4 xr[VPL];
   const float* xrow = a.x + static_cast<long long>(b) * a.D;
 #pragma unroll
@@ -164,12 +253,12 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
     const int v = lane + 32 * i;
     xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
   }
-  for (int c0 = 0; c0 < KP; c0 += 4) {
+  for (int c0 = 0; c0 < n; c0 += 4) {
     int j[4];
     float acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      j[u] = (c0 + u < KP) ? ki[c0 + u] : -1;
+      j[u] = (c0 + u < n) ? si[c0 + u] : -1;
       acc[u] = 0.f;
     }
 #pragma unroll
@@ -187,34 +276,26 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float tot = warp_sum(acc[u]);
-      if (lane == 0 && c0 + u < KP) ke[c0 + u] = (j[u] >= 0) ? tot + __ldg(a.b_enc + j[u]) : -INFINITY;
+      if (lane == 0 && c0 + u < n) se[c0 + u] = tot + __ldg(a.b_enc + j[u]);
     }
   }
   __syncwarp();
 
-  // final selection on exact values; order: value desc, then feature index asc, then position
-  float err2 = 0.f;            // sum of squared screen errors over the valid candidates
-  float tmin = INFINITY;       // smallest screen value among the kept candidates
-  int nvalid = 0;
-  float vk = -INFINITY;
-  for (int c = lane; c < ((KP + 31) & ~31); c += 32) {
-    const bool valid = c < KP;
-    const float v = valid ? ke[c] : -INFINITY;
-    const int id = valid ? ki[c] : -1;
-    int rank = 0;
-    if (valid) {
-      for (int t = 0; t < KP; ++t) {
-        const float vt = ke[t];
-        const int it = ki[t];
-        rank += (vt > v) || (vt == v && (it < id || (it == id && t < c)));
+  // ---- final selection on exact values; order: value desc, then column asc ----
+  float maxerr = 0.f;
+  const int k_eff = min(a.K, n);
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + lane;
+    if (c < n) {
+      const float v = se[c];
+      const int id = si[c];
+      int rank = 0;
+      for (int t = 0; t < n; ++t) {
+        const float vt = se[t];
+        rank += (vt > v) || (vt == v && si[t] < id);
       }
-      if (id >= 0) {
-        const float d = kv[c] - v;
-        err2 += d * d;
-        tmin = fminf(tmin, kv[c]);
-        ++nvalid;
-      }
-      if (rank < a.K && id >= 0) {
+      maxerr = fmaxf(maxerr, fabsf(sv[c] - v));
+      if (rank < a.K) {
         const long long o = static_cast<long long>(b) * a.K + rank;
         a.topk_idx[o] = id;
         a.topk_val[o] = v;
@@ -222,26 +303,38 @@ __global__ void __launch_bounds__(128) rescore_topk_kernel(RescoreArgs a) {
         if (a.active && v != 0.f) a.active[id] = 1;
       }
     }
-    const unsigned hit = __ballot_sync(FULL, valid && rank == a.K - 1);
-    if (hit) vk = __shfl_sync(FULL, v, __ffs(hit) - 1);
   }
-  err2 = warp_sum(err2);
-  nvalid = warp_sum(nvalid);
+  for (int r = k_eff + lane; r < a.K; r += 32) {  // fewer candidates than k (d_sae < k never happens; defensive)
+    a.topk_idx[static_cast<long long>(b) * a.K + r] = -1;
+    a.topk_val[static_cast<long long>(b) * a.K + r] = 0.f;
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(FULL, tmin, o));
-  if (lane == 0 && a.unsafe_rows != nullptr && nvalid == KP) {
-    // Every column outside the list has a screen value <= tmin.  Flag the row when the k-th exact value is
-    // not clear of tmin by 6 sigma of the screen error observed on this row's own candidates (diagnostic:
-    // a flagged row is still almost surely right; an unflagged one is wrong with probability ~1e-9).
-    const float sigma = sqrtf(err2 / static_cast<float>(KP));
-    if (vk - tmin < 6.f * sigma) atomicAdd(a.unsafe_rows, 1u);
-  }
+  for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(FULL, maxerr, o));
+  // The candidate set covers the exact top-k when every screen error is <= margin / 2.  Count the rows where
+  // that cannot be certified: buffer overflow, or an observed error above the bound the margin assumes.
+  if (lane == 0 && a.unsafe_rows != nullptr && (overflow || maxerr > 0.5f * margin)) atomicAdd(a.unsafe_rows, 1u);
 }
 
 int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
-  const size_t smem = static_cast<size_t>(4) * (2 * a.nsplit * a.kp + 3 * a.kp) * 4;
-  SB_DISPATCH_VPL(a.D, (rescore_topk_kernel<VPL><<<(a.B + 3) / 4, 128, smem, s>>>(a)));
+  const size_t smem = static_cast<size_t>(RESCORE_WARPS) * 3 * a.nsplit * (a.cand_stride / 2) * 4;
+  ++g_launch_count;
+  const int need_ = (a.D + 127) / 128;
+#define SB_RESCORE(V)                                                                                          \
+  {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                      \
+      cudaFuncSetAttribute(rescore_topk_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    rescore_topk_kernel<V><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, smem, s>>>(a);     \
+  }
+  if (need_ <= 1) SB_RESCORE(1)
+  else if (need_ <= 2) SB_RESCORE(2)
+  else if (need_ <= 4) SB_RESCORE(4)
+  else if (need_ <= 6) SB_RESCORE(6)
+  else if (need_ <= 8) SB_RESCORE(8)
+  else if (need_ <= 12) SB_RESCORE(12)
+  else if (need_ <= 16) SB_RESCORE(16)
+  else return 20;
+#undef SB_RESCORE
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -641,10 +734,11 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   const int D4 = a.D >> 2;
   const long long SD = static_cast<long long>(a.S) * a.D;
   const long long ro = static_cast<long long>(j) * a.D;
-  // ---- W_enc_t row (+ bf16 shadow) ----
+  // ---- W_enc_t row (+ bf16 shadow, + max row norm for the screen's admission margin) ----
   {
     float* mrow = a.m + ro;
     float* vrow = a.v + ro;
+    float ssq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v4 = lane + 32 * i;
@@ -656,12 +750,17 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
         *reinterpret_cast<float4*>(a.W_enc_t + ro + 4 * v4) = p;
         *reinterpret_cast<float4*>(mrow + 4 * v4) = m;
         *reinterpret_cast<float4*>(vrow + 4 * v4) = v;
+        ssq += dot4(p, p);
         if (a.shadow_hi != nullptr) {
           __nv_bfloat162* so = reinterpret_cast<__nv_bfloat162*>(a.shadow_hi + ro + 4 * v4);
           so[0] = __nv_bfloat162(__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y));
           so[1] = __nv_bfloat162(__float2bfloat16_rn(p.z), __float2bfloat16_rn(p.w));
         }
       }
+    }
+    if (a.wnorm_sq_max != nullptr) {
+      ssq = warp_sum(ssq);
+      if (lane == 0) atomicMax(reinterpret_cast<int*>(a.wnorm_sq_max), __float_as_int(ssq));
     }
   }
   // ---- b_enc[j] ----
@@ -721,6 +820,7 @@ __global__ void adam_bdec_kernel(AdamArgs a) {
 
 int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
+  if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
   SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
   adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
   ++g_launch_count;

@@ -14,6 +14,8 @@
  *   src/saev/framework/train.py:294,444-446  torch.optim.Adam(fused=True).step -> saev_b200_adam_step
  *   src/saev/nn/modeling.py:411-417    normalize_w_dec                   -> saev_b200_normalize_w_dec / adam_step(renorm)
  *   src/saev/framework/train.py:333    batch["act"].to(device)           -> saev_b200_ring_* (pinned staging ring)
+ *   src/saev/data/shuffled.py:133-363,380-699 ShuffledDataLoader (manager, I/O workers, __iter__)
+ *   src/saev/data/buffers.py:91-231    ReservoirBuffer (shuffle pool)    -> saev_b200_loader_* (pool in HBM)
  *
  * Conventions
  *   - Plain C types only.  Every `float*` / `int*` below is a DEVICE pointer owned by the caller
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 1
+#define SAEV_B200_ABI_VERSION 2
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -166,6 +168,60 @@ void* saev_b200_ring_host_ptr(saev_b200_ring* r, int32_t slot);
 int saev_b200_ring_submit(saev_b200_ring* r, int32_t slot, void* dst_device, size_t bytes);
 int saev_b200_ring_wait(saev_b200_ring* r, int32_t slot, void* consumer_stream);
 int saev_b200_ring_host_sync(saev_b200_ring* r, int32_t slot); /* block host until the slot's copy is done */
+
+/* ---- shuffled activation loader with the shuffle pool in HBM (replaces saev's ShuffledDataLoader +
+ *      ReservoirBuffer: src/saev/data/shuffled.py:133-363, 380-699; src/saev/data/buffers.py:91-231) ----
+ * Shards are saev's `acts%06d.bin` files, fp32 [examples_per_shard, n_layers, tokens_per_example, d_model]
+ * (src/saev/data/shards.py:168-180).  I/O threads pread whole examples into pinned staging chunks, a feeder
+ * thread appends them to a device-resident pool and prepares shuffled batches ahead of the consumer with a
+ * gather kernel; saev_b200_loader_next returns DEVICE pointers, valid until the call after the next one.
+ * Each (example, content token) row of the listed shards is delivered exactly once per epoch. */
+typedef struct saev_b200_loader_cfg {
+  const char* shards_dir;         /* directory holding acts%06d.bin                      shuffled.py:189-196 */
+  int32_t examples_per_shard;     /* Metadata.examples_per_shard                         shards.py:158-166 */
+  int32_t n_layers;               /* len(Metadata.layers) */
+  int32_t tokens_per_example;     /* content tokens + [CLS]                              shards.py:136-144 */
+  int32_t d_model;
+  int32_t layer_index;            /* Metadata.layers.index(cfg.layer)                    shuffled.py:160 */
+  int32_t cls_token;              /* 1: token 0 is [CLS], content starts at token 1      shuffled.py:204 */
+  int32_t content_tokens;         /* Metadata.content_tokens_per_example */
+  const int32_t* shard_order;     /* [n_order] shard ids this rank visits, in order      shuffled.py:326-328 */
+  const int32_t* shard_examples;  /* [n_order] valid examples of each (shards.json)      shuffled.py:200-202 */
+  int32_t n_order;
+  int32_t batch_size;             /* Config.batch_size */
+  int32_t pool_batches;           /* Config.buffer_size: pool capacity in batches        shuffled.py:459-468 */
+  int32_t n_threads;              /* Config.n_threads */
+  int32_t n_out_slots;            /* device batch buffers handed out round-robin (>= 2; 0 = 3) */
+  int32_t chunk_examples;         /* examples per I/O chunk, 0 = about 8 MB */
+  float min_buffer_fill;          /* Config.min_buffer_fill                              shuffled.py:578-633 */
+  int32_t reserved;
+  int64_t n_rows_limit;           /* unused by the library (the epoch length is passed to start_epoch) */
+  uint64_t seed;                  /* Config.seed */
+  const uint8_t* labels;          /* optional labels.bin [n_examples, content_tokens] (host pointer) or NULL */
+  const uint8_t* ignore_lut;      /* optional [256]: 1 = drop rows carrying this label   shuffled.py:206-236 */
+} saev_b200_loader_cfg;
+typedef struct saev_b200_loader saev_b200_loader;
+
+int saev_b200_loader_create(const saev_b200_loader_cfg* cfg, saev_b200_loader** out);
+int saev_b200_loader_destroy(saev_b200_loader* l);
+/* Starts the I/O + feeder threads for one pass over the configured shards; the epoch ends after `rows_expected`
+ * rows were handed out.  Buffers still in use on `consumer_stream` from the previous epoch are protected. */
+int saev_b200_loader_start_epoch(saev_b200_loader* l, int64_t rows_expected, uint64_t seed, void* consumer_stream);
+/* Next shuffled batch (device pointers; *n_rows = 0 once the epoch is exhausted).  Work later enqueued on
+ * `consumer_stream` sees the batch (event wait, no host sync).  Returns 131 if nothing arrived within
+ * `timeout_s` seconds (the call can simply be repeated: nothing is consumed), 130 if a loader thread failed. */
+int saev_b200_loader_next(saev_b200_loader* l, void* consumer_stream, double timeout_s, float** act,
+                          int32_t** example_idx, int32_t** token_idx, int32_t* n_rows);
+int saev_b200_loader_stats(saev_b200_loader* l, int64_t* pool_rows, int64_t* pool_capacity, int64_t* rows_delivered,
+                           int64_t* bytes_read);
+int saev_b200_loader_stop(saev_b200_loader* l);
+const char* saev_b200_loader_last_error(const saev_b200_loader* l);
+/* Host-only pieces, exported for tests: the chunk reader (returns rows kept, < 0 on error) and the draw /
+ * compaction planner (`need` distinct positions of [0, fill) + the moves that re-pack the pool). */
+int64_t saev_b200_loader_read_chunk(const saev_b200_loader_cfg* cfg, int32_t shard, int32_t ex_begin, int32_t n_ex,
+                                    float* host_act, int32_t* host_meta);
+int saev_b200_loader_plan_draw(uint64_t seed, int64_t fill, int32_t need, int32_t* sel, int32_t* mv_src,
+                               int32_t* mv_dst, int32_t* n_moves);
 
 #ifdef __cplusplus
 }

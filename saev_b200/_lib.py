@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -37,6 +37,35 @@ class Cfg(C.Structure):
         ("max_batch", C.c_int32),
         ("aux_cols_cap", C.c_int32),
         ("reserved", C.c_int32),
+    ]
+
+
+class LoaderCfg(C.Structure):
+    """Mirror of `saev_b200_loader_cfg` (include/saev_b200.h)."""
+
+    _fields_ = [
+        ("shards_dir", C.c_char_p),
+        ("examples_per_shard", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("tokens_per_example", C.c_int32),
+        ("d_model", C.c_int32),
+        ("layer_index", C.c_int32),
+        ("cls_token", C.c_int32),
+        ("content_tokens", C.c_int32),
+        ("shard_order", C.POINTER(C.c_int32)),
+        ("shard_examples", C.POINTER(C.c_int32)),
+        ("n_order", C.c_int32),
+        ("batch_size", C.c_int32),
+        ("pool_batches", C.c_int32),
+        ("n_threads", C.c_int32),
+        ("n_out_slots", C.c_int32),
+        ("chunk_examples", C.c_int32),
+        ("min_buffer_fill", C.c_float),
+        ("reserved", C.c_int32),
+        ("n_rows_limit", C.c_int64),
+        ("seed", C.c_uint64),
+        ("labels", C.c_void_p),
+        ("ignore_lut", C.c_void_p),
     ]
 
 
@@ -78,6 +107,17 @@ SIGNATURES = {
     "saev_b200_ring_submit": (C.c_int, [_p, _i32, _p, C.c_size_t]),
     "saev_b200_ring_wait": (C.c_int, [_p, _i32, _p]),
     "saev_b200_ring_host_sync": (C.c_int, [_p, _i32]),
+    "saev_b200_loader_create": (C.c_int, [C.POINTER(LoaderCfg), C.POINTER(_p)]),
+    "saev_b200_loader_destroy": (C.c_int, [_p]),
+    "saev_b200_loader_start_epoch": (C.c_int, [_p, _i64, C.c_uint64, _p]),
+    "saev_b200_loader_next": (
+        C.c_int, [_p, _p, C.c_double, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i32)]),
+    "saev_b200_loader_stats": (
+        C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "saev_b200_loader_stop": (C.c_int, [_p]),
+    "saev_b200_loader_last_error": (C.c_char_p, [_p]),
+    "saev_b200_loader_read_chunk": (_i64, [C.POINTER(LoaderCfg), _i32, _i32, _i32, _p, _p]),
+    "saev_b200_loader_plan_draw": (C.c_int, [C.c_uint64, _i64, _i32, _p, _p, _p, C.POINTER(_i32)]),
 }
 
 _lib = None

@@ -34,8 +34,10 @@ import json
 import math
 import pathlib
 import typing as tp
+import weakref
 
 import torch
+import torch.distributed as dist
 from torch import Tensor
 
 from . import __version__
@@ -212,7 +214,7 @@ class SparseAutoencoder(torch.nn.Module):
     Output = Output
 
     def __init__(self, cfg):
-        super().__init__()
+        torch.nn.Module.__init__(self)  # explicit: dropin.dropin_class() also inherits from saev's class
         self.cfg = cfg
         S, D = cfg.d_sae, cfg.d_model
         # modeling.py:312-327: kaiming_uniform_ on [S, D] (bound sqrt(6 / D)), rows normalised, W_enc = W_dec.T
@@ -231,6 +233,25 @@ class SparseAutoencoder(torch.nn.Module):
         self._ticket = 0
         self._grads_fused = False
         self._w_dec_normalized = False
+        self._pending_clip: float | None = None  # max_norm recorded by saev_b200.optim.clip_grad_norm_
+        # Fold normalize_w_dec (train.py:334-335) into the tail of the Adam kernel.  Off by default: the reference
+        # normalises at the START of the next step, so its checkpoints hold un-normalised rows.
+        self.fuse_renorm = False
+        self._dp_group = None
+        self._dp_world = 1
+        ref = weakref.ref(self)
+        for p in (self.W_dec, self.b_dec, self.W_enc, self.b_enc):
+            p._b200_owner = ref
+
+    def data_parallel(self, group=None) -> "SparseAutoencoder":
+        """Opt in to data-parallel training over `group` (default process group): every rank holds a full replica,
+        feeds its own rows, and the objective's backward all-reduces the flat gradient bucket once per step
+        (saev itself is single-GPU; semantics are N ranks x B rows == 1 rank x N*B rows, see parallel.py)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("data_parallel(): torch.distributed is not initialised")
+        self._dp_group = group
+        self._dp_world = dist.get_world_size(group)
+        return self
 
     # ---- engine binding --------------------------------------------------------------------
     def _bind(self, batch: int, obj_cfg=None) -> Engine:
@@ -371,7 +392,18 @@ class _StepFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sae, x, tokens_global, W_dec, b_dec, W_enc, b_enc):
         eng = sae.engine
-        eng.forward(x, training=True, tokens_global=tokens_global)
+        if sae._dp_world > 1:
+            from . import _lib
+
+            eng.forward(x, training=True, phase=_lib.PHASE_A, tokens_global=tokens_global)
+            dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=sae._dp_group)
+            eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
+            # every rank's scalars are partial sums over the GLOBAL denominator; n_dead is identical on all ranks
+            n_dead = eng.losses[5].clone()
+            dist.all_reduce(eng.losses, op=dist.ReduceOp.SUM, group=sae._dp_group)
+            eng.losses[5] = n_dead
+        else:
+            eng.forward(x, training=True, tokens_global=tokens_global)
         ctx.sae, ctx.x, ctx.tokens_global = sae, x, tokens_global
         return eng.losses[6].clone()
 
@@ -379,6 +411,8 @@ class _StepFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         sae, eng = ctx.sae, ctx.sae.engine
         eng.backward(ctx.x, tokens_global=ctx.tokens_global)
+        if sae._dp_world > 1:
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=sae._dp_group)
         views = (("W_dec", eng.gW_dec), ("b_dec", eng.gb_dec), ("W_enc", eng.gW_enc_t.t()), ("b_enc", eng.gb_enc))
         for name, g in views:
             p = getattr(sae, name)
@@ -411,8 +445,8 @@ class MatryoshkaObjective(torch.nn.Module):
             if self.toks_since_active is None:  # objectives.py:108-111: lazily created, not in the state_dict
                 eng.toks_since_active.zero_()
             self.toks_since_active = eng.toks_since_active
-            total = _StepFunction.apply(sae, x, x.shape[0], sae.W_dec, sae.b_dec, sae.W_enc, sae.b_enc)
-            sae._w_dec_normalized = False if not sae._w_dec_normalized else sae._w_dec_normalized
+            total = _StepFunction.apply(sae, x, x.shape[0] * sae._dp_world, sae.W_dec, sae.b_dec, sae.W_enc,
+                                        sae.b_enc)
         else:
             eng.forward(x, training=False)
             total = eng.losses[6].clone()

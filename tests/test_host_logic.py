@@ -1,0 +1,274 @@
+"""CPU tests of the host-side logic around the CUDA path, against fixtures recorded from the LIVE reference by
+oracle/gen_golden_host.py: lr schedules and BatchLimiter (scheduling.py), the shard chunk reader and the
+draw/compaction planner of the native loader, the loader's sizes/validation, and the optimizer shims' fall-through
+behaviour.  No compute entry point of the library is called here (there is no GPU)."""
+import ctypes as C
+import json
+import pathlib
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from saev_b200 import _lib, data, optim, scheduling
+
+GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
+SCHED = json.loads((GOLDEN / "host_schedules.json").read_text())
+CENSUS = json.loads((GOLDEN / "shards_census.json").read_text())
+SHARDS = GOLDEN / CENSUS["dir"]
+
+
+# ---- schedules ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", SCHED["warmup_cosine"], ids=lambda c: str(c["args"]))
+def test_warmup_cosine_matches_reference(case):
+    s = scheduling.WarmupCosine(*case["args"])
+    assert repr(s) == case["repr"]
+    assert [s.step() for _ in case["values"]] == case["values"]  # same float ops: bit-exact
+
+
+@pytest.mark.parametrize("case", SCHED["warmup"], ids=lambda c: str(c["args"]))
+def test_warmup_matches_reference(case):
+    s = scheduling.Warmup(*case["args"])
+    assert repr(s) == case["repr"]
+    assert [s.step() for _ in case["values"]] == case["values"]
+
+
+class _FakeLoader:
+    def __init__(self, sizes, batch_size, drop_last):
+        self.sizes, self.batch_size, self.drop_last = sizes, batch_size, drop_last
+        self.extra_attr = "passthrough"
+
+    def __iter__(self):
+        for n in self.sizes:
+            yield {"act": torch.zeros(n, 2)}
+
+
+@pytest.mark.parametrize("case", SCHED["batch_limiter"], ids=lambda c: f"{c['sizes']}-{c['n_samples']}")
+def test_batch_limiter_matches_reference(case):
+    bl = scheduling.BatchLimiter(_FakeLoader(case["sizes"], case["batch_size"], case["drop_last"]), case["n_samples"])
+    assert len(bl) == case["len"]
+    assert [len(b["act"]) for b in bl] == case["yielded"]
+    assert bl.n_seen == case["n_seen"]
+    assert bl.extra_attr == case["extra_attr"]
+    with pytest.raises(AttributeError, match="wrapped dataloader"):
+        bl.no_such_attribute
+
+
+def test_infer_batch_size_rules():
+    f = scheduling._infer_batch_size
+    assert f({"act": torch.zeros(3, 2)}, 9) == 3
+    assert f({}, 9) == 9
+    assert f(torch.zeros(5, 2), 9) == 5
+    assert f(7, 9) == 9  # no __len__
+    assert f({"act": torch.zeros(0, 2)}, 9) == 9  # empty -> fallback
+
+
+# ---- native loader: host-only entry points --------------------------------------------------------
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def _loader_cfg(md, layer, keep):
+    order = np.arange(md.n_shards, dtype=np.int32)
+    n_ex = np.array([n for _, n in data._load_shard_examples(SHARDS)], dtype=np.int32)
+    keep.extend([order, n_ex, str(SHARDS).encode()])
+    return _lib.LoaderCfg(
+        shards_dir=keep[-1], examples_per_shard=md.examples_per_shard, n_layers=len(md.layers),
+        tokens_per_example=md.tokens_per_example, d_model=md.d_model, layer_index=md.layers.index(layer),
+        cls_token=int(md.cls_token), content_tokens=md.content_tokens_per_example,
+        shard_order=order.ctypes.data_as(C.POINTER(C.c_int32)), shard_examples=n_ex.ctypes.data_as(C.POINTER(C.c_int32)),
+        n_order=len(order), batch_size=4, pool_batches=2, n_threads=1, n_out_slots=3, chunk_examples=0,
+        min_buffer_fill=0.0, reserved=0, n_rows_limit=-1, seed=0, labels=None, ignore_lut=None)
+
+
+@pytest.mark.parametrize("case", CENSUS["cases"], ids=lambda c: f"layer{c['layer']}-ignore{c['ignore_labels']}")
+def test_chunk_reader_reproduces_the_reference_loaders_rows(lib, case):
+    """Union of all chunks == the multiset of rows saev's ShuffledDataLoader delivered for the same directory."""
+    md = data.Metadata.load(SHARDS)
+    keep = []
+    c = _loader_cfg(md, case["layer"], keep)
+    if case["ignore_labels"]:
+        labels = np.fromfile(SHARDS / "labels.bin", dtype=np.uint8)
+        lut = np.zeros(256, dtype=np.uint8)
+        lut[case["ignore_labels"]] = 1
+        keep.extend([labels, lut])
+        c.labels, c.ignore_lut = labels.ctypes.data, lut.ctypes.data
+    T, D = md.content_tokens_per_example, md.d_model
+    rows = []
+    for shard, (_, n_ex) in enumerate(data._load_shard_examples(SHARDS)):
+        for ex0 in range(0, n_ex, 3):  # ragged chunks on purpose
+            n = min(3, n_ex - ex0)
+            act = np.full((n * T, D), np.nan, dtype=np.float32)
+            meta = np.zeros((n * T, 2), dtype=np.int32)
+            got = lib.saev_b200_loader_read_chunk(C.byref(c), shard, ex0, n, act.ctypes.data, meta.ctypes.data)
+            assert 0 <= got <= n * T
+            rows += [[int(meta[i, 0]), int(meta[i, 1]), zlib.crc32(act[i].tobytes())] for i in range(got)]
+    assert sorted(rows) == case["rows"]
+    assert len(rows) == case["n_samples"]
+
+
+def test_chunk_reader_matches_the_written_activations(lib):
+    md = data.Metadata.load(SHARDS)
+    acts = np.load(GOLDEN / "shards_acts.npy")  # [example, layer, token (CLS first), d_model] as handed to ShardWriter
+    keep = []
+    c = _loader_cfg(md, 3, keep)
+    T, D = md.content_tokens_per_example, md.d_model
+    act = np.zeros((2 * T, D), dtype=np.float32)
+    meta = np.zeros((2 * T, 2), dtype=np.int32)
+    assert lib.saev_b200_loader_read_chunk(C.byref(c), 1, 1, 2, act.ctypes.data, meta.ctypes.data) == 2 * T
+    np.testing.assert_array_equal(act.reshape(2, T, D), acts[5:7, 1, 1:, :])  # shard 1 holds examples 4..7
+    assert meta[:, 0].tolist() == [5] * T + [6] * T and meta[:, 1].tolist() == list(range(T)) * 2
+    assert lib.saev_b200_loader_read_chunk(C.byref(c), 7, 0, 1, act.ctypes.data, meta.ctypes.data) < 0  # no such shard
+    assert b"cannot open" in lib.saev_b200_loader_last_error(None)
+
+
+@pytest.mark.parametrize("fill,need", [(1, 1), (8, 8), (10, 3), (1000, 64), (65, 64), (4096, 1), (300, 299)])
+def test_plan_draw_is_a_sample_without_replacement_and_repacks_the_pool(lib, fill, need):
+    sel = np.zeros(need, dtype=np.int32)
+    src = np.zeros(need, dtype=np.int32)
+    dst = np.zeros(need, dtype=np.int32)
+    n = C.c_int32()
+    assert lib.saev_b200_loader_plan_draw(1234, fill, need, sel.ctypes.data, src.ctypes.data, dst.ctypes.data, C.byref(n)) == 0
+    assert len(set(sel.tolist())) == need and sel.min() >= 0 and sel.max() < fill
+    pool = np.arange(fill)
+    drawn = pool[sel]
+    m = n.value
+    assert m == int((sel < fill - need).sum())
+    assert set(dst[:m].tolist()) == set(sel[sel < fill - need].tolist())  # every hole is filled exactly once
+    assert all(s >= fill - need and s not in set(sel.tolist()) for s in src[:m].tolist())
+    assert len(set(src[:m].tolist())) == m
+    pool[dst[:m]] = pool[src[:m]]
+    assert sorted(pool[: fill - need].tolist() + drawn.tolist()) == list(range(fill))  # nothing lost, nothing doubled
+
+
+def test_plan_draw_simulated_epoch_delivers_every_row_exactly_once(lib):
+    """Numpy simulation of the device pool driven by the planner: ragged appends, draws, a short last batch."""
+    rng = np.random.default_rng(0)
+    total, batch, cap = 1003, 64, 256
+    pool = np.full(cap, -1)
+    fill, appended, out, seed = 0, 0, [], 0
+    while len(out) < total:
+        while appended < total and fill + 37 <= cap and (fill < batch or rng.random() < 0.5):
+            n = min(37, total - appended)
+            pool[fill : fill + n] = np.arange(appended, appended + n)
+            fill += n
+            appended += n
+        need = min(batch, total - len(out))
+        if fill < need:
+            continue
+        sel, src, dst = (np.zeros(need, dtype=np.int32) for _ in range(3))
+        m = C.c_int32()
+        seed += 1
+        assert lib.saev_b200_loader_plan_draw(seed, fill, need, sel.ctypes.data, src.ctypes.data, dst.ctypes.data, C.byref(m)) == 0
+        out += pool[sel].tolist()
+        pool[dst[: m.value]] = pool[src[: m.value]]
+        fill -= need
+    assert sorted(out) == list(range(total))
+    assert out != sorted(out)  # and it is shuffled
+
+
+def test_plan_draw_rejects_bad_arguments(lib):
+    buf = np.zeros(4, dtype=np.int32)
+    n = C.c_int32()
+    assert lib.saev_b200_loader_plan_draw(0, 3, 4, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, C.byref(n)) != 0
+    assert lib.saev_b200_loader_plan_draw(0, 3, 0, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, C.byref(n)) != 0
+
+
+# ---- loader front end ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CENSUS["cases"], ids=lambda c: f"layer{c['layer']}-bs{c['batch_size']}")
+def test_loader_sizes_match_reference(case):
+    cfg = data.ShuffledConfig(shards=SHARDS, layer=case["layer"], batch_size=case["batch_size"],
+                              ignore_labels=case["ignore_labels"], seed=3)
+    dl = data.ShuffledDataLoader(cfg)
+    assert dl.n_samples == case["n_samples"]
+    assert len(dl) == case["len"] == dl.n_batches
+    assert dl.batch_size == case["batch_size"] and dl.drop_last is False
+    assert dl.manager_pid == -1 and dl.reservoir is None  # nothing running before iteration (shuffled.py:452-456)
+    assert dl.metadata.n_examples == 10 and dl.metadata.content_tokens_per_example == 5
+
+
+def test_loader_rank_sharding_is_a_partition_of_the_seeded_permutation():
+    cfg = data.ShuffledConfig(shards=SHARDS, layer=0, batch_size=4, seed=3)
+    parts = [data.ShuffledDataLoader(cfg, rank=r, world_size=2) for r in range(2)]
+    orders = [p._orders[p.rank].tolist() for p in parts]
+    assert sorted(orders[0] + orders[1]) == [0, 1, 2]
+    assert orders[0] + orders[1] != [] and set(orders[0]).isdisjoint(orders[1])
+    full = np.random.default_rng(3).permutation(3).tolist()  # shuffled.py:326-328
+    assert orders[0] == full[0::2] and orders[1] == full[1::2]
+    # both ranks deliver the same number of rows per epoch (lock step)
+    assert parts[0].n_samples == parts[1].n_samples == min(parts[0]._rows_per_rank)
+
+
+def test_loader_validation_errors_mirror_the_reference(tmp_path):
+    with pytest.raises(RuntimeError, match="Activations are not saved"):
+        data.ShuffledDataLoader(data.ShuffledConfig(shards=tmp_path / "nope", layer=0))
+    with pytest.raises(NotImplementedError, match="scale_norm"):
+        data.ShuffledDataLoader(data.ShuffledConfig(shards=SHARDS, layer=0, scale_norm=True))
+    with pytest.raises(NotImplementedError, match="content"):
+        data.ShuffledDataLoader(data.ShuffledConfig(shards=SHARDS, layer="all"))
+    with pytest.raises(ValueError, match="not in"):
+        data.ShuffledDataLoader(data.ShuffledConfig(shards=SHARDS, layer=5))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_loader_has_no_host_only_mode():
+    dl = data.ShuffledDataLoader(data.ShuffledConfig(shards=SHARDS, layer=0, batch_size=4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        next(iter(dl))
+
+
+# ---- optimizer shims: everything that is not a fused SAE goes to stock torch ------------------------
+def test_clip_and_adam_fall_through_for_ordinary_parameters():
+    torch.manual_seed(0)
+    a = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(3))]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    for ps in (a, b):
+        for i, p in enumerate(ps):
+            p.grad = torch.full_like(p, 0.5 + i)
+    n1 = optim.clip_grad_norm_(a, 1.0)
+    n2 = torch.nn.utils.clip_grad_norm_(b, 1.0)
+    assert torch.equal(n1, n2)
+    o1, o2 = optim.FusedAdam([{"params": a, "lr": 1e-2}]), torch.optim.Adam([{"params": b, "lr": 1e-2}])
+    for _ in range(3):
+        o1.step()
+        o2.step()
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
+
+
+def test_install_rebinds_and_restores_saev_names():
+    import sys
+
+    ref_src = pathlib.Path("/root/reference/src")
+    if not ref_src.exists():
+        pytest.skip("needs the reference checkout (build container only)")
+    stubs = str(pathlib.Path(__file__).resolve().parent.parent / "oracle" / "ref_stubs")
+    sys.path[:0] = [stubs, str(ref_src)]
+    try:
+        import saev.data
+        import saev.nn
+        import saev.nn.modeling as M
+
+        import saev_b200
+        from saev_b200 import dropin as inst
+
+        orig = (saev.nn.SparseAutoencoder, saev.nn.get_objective, torch.optim.Adam, torch.nn.utils.clip_grad_norm_,
+                saev.data.ShuffledDataLoader)
+        saev_b200.install()
+        try:
+            assert torch.optim.Adam is optim.FusedAdam and torch.nn.utils.clip_grad_norm_ is optim.clip_grad_norm_
+            assert saev.data.ShuffledDataLoader is data.ShuffledDataLoader
+            sae = saev.nn.SparseAutoencoder(M.SparseAutoencoderConfig(d_model=16, d_sae=64, reinit_blend=0.0))
+            assert isinstance(sae, M.SparseAutoencoder) and isinstance(sae, inst.dropin_class())
+            assert list(sae.state_dict()) == ["W_dec", "b_dec", "W_enc", "b_enc"]  # checkpoint keys, modeling.py:312-327
+            assert sae.W_enc.shape == (16, 64) and sae.W_dec.shape == (64, 16)
+            with pytest.raises(RuntimeError, match="CUDA"):
+                sae(torch.zeros(2, 16))  # no CPU fallback
+        finally:
+            saev_b200.uninstall()
+        assert (saev.nn.SparseAutoencoder, saev.nn.get_objective, torch.optim.Adam, torch.nn.utils.clip_grad_norm_,
+                saev.data.ShuffledDataLoader) == orig
+    finally:
+        del sys.path[:2]

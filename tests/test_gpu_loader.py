@@ -119,9 +119,10 @@ def test_two_ranks_read_disjoint_shards(tmp_path):
     assert got[0].isdisjoint(got[1]) and len(got[0] | got[1]) == 96 * 4
 
 
-def test_next_times_out_without_consuming_anything(tmp_path):
-    """ReservoirBuffer.get(bsz, timeout) raises TimeoutError and leaves qsize intact (tests/test_reservoir_buffer.py:
-    375-410); the native call reports 131 and the following call still delivers everything."""
+def test_next_without_producers_reports_exhausted_not_a_hang(tmp_path):
+    """The reference's reservoir get() blocks (with a timeout) while producers may still deliver
+    (tests/test_reservoir_buffer.py:173-221, 375-410); with no epoch running the native call must return at once
+    with n_rows = 0, and a following epoch still delivers everything."""
     import ctypes as C
 
     d, _ = _write_dir(tmp_path, 8, 4, 32, ex_per_shard=8)

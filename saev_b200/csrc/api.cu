@@ -1,6 +1,7 @@
 // extern "C" surface of libsaev_b200.so (see include/saev_b200.h for the contract).
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include <new>
@@ -31,6 +32,7 @@ struct saev_b200_handle {
   int device = 0;
   int num_sms = 148;
   int aux_cap = 0;
+  int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen (0 => single-CTA kernel)
   Workspace ws;
   bool last_forward_training = false;
   bool last_forward_tracked = false;
@@ -62,7 +64,7 @@ int check_cuda(const saev_b200_handle* h, const char* where) {
   return fail(h, 100, "CUDA error at %s", buf);
 }
 
-Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap) {
+Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   Workspace w;
   const size_t S = c.d_sae, D = c.d_model, B = c.max_batch, K = c.top_k;
   size_t o = 0;
@@ -77,7 +79,16 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap) {
     // (row, split) candidate buffers of the top-k screen: rows are padded to whole 128-row blocks and
     // m_blocks * nsplit never exceeds max(m_blocks, #SMs)
     const size_t m_blocks = (B + 127) / 128;
-    const size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
+    size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
+    if (max_pairs > 0) {
+      // pair kernel: rows padded to 256, `nlists` lists per row; the list count depends on the batch size
+      const int mp_max = static_cast<int>((B + 255) / 256);
+      for (int mp = 1; mp <= mp_max; ++mp) {
+        const Encode2Plan pl = encode2_plan(mp * 256, static_cast<int>(S), max_pairs);
+        const size_t need = static_cast<size_t>(mp) * 256 * pl.nlists;
+        if (need > row_splits) row_splits = need;
+      }
+    }
     w.cand = take(row_splits * ENCODE_CAPG * 8);
     w.cand_cnt = take(row_splits * 4);
     w.row_margin = take(128 * m_blocks * 4);
@@ -172,7 +183,11 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   h->device = dev;
   h->num_sms = sms;
   h->aux_cap = (cfg->aux_cols_cap > 0 && cfg->aux_cols_cap < cfg->d_sae) ? cfg->aux_cols_cap : cfg->d_sae;
-  h->ws = plan_workspace(h->cfg, h->aux_cap);
+  {
+    const char* v = getenv("SAEV_B200_ENCODE");  // "1": force the single-CTA screen (A/B comparison)
+    h->max_pairs = (v && v[0] == '1') ? 0 : encode2_max_pairs();
+  }
+  h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs);
   h->err[0] = 0;
   *out = h;
   return 0;
@@ -286,9 +301,14 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
+    Encode2Plan pl;
+    if (h->max_pairs > 0) {
+      pl = encode2_plan(B, S, h->max_pairs);
+      g.nsplit = pl.nlists;  // what the re-score kernel merges per row
+    }
     {
       StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
-      if (int rc = launch_encode_gemm(g, s)) {
+      if (int rc = h->max_pairs > 0 ? launch_encode_gemm2(g, pl, s) : launch_encode_gemm(g, s)) {
         char buf[64];
         snprintf(buf, sizeof(buf), "%d", rc);
         return fail(h, 42, "forward: encode GEMM launch failed (code %s)", buf);

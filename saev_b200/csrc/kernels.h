@@ -35,6 +35,21 @@ struct EncodeGemmArgs {
   long long ldo = 0;
 };
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream);
+
+// ---- encode_gemm2.cu: CTA-pair (cta_group::2) top-k screen ------------------------------------------------
+struct Encode2Plan {
+  int m_pairs = 0;   // 256-row blocks of the batch
+  int n_tiles = 0;   // 256-column tiles of the dictionary
+  int q = 1;         // tile-steps per CTA pair (contiguous range of the linearised (row block, tile) space)
+  int n_pairs = 1;   // CTA pairs launched
+  int nsplit = 1;    // most ranges touching one row block
+  int nlists = 2;    // candidate lists per row = 2 * nsplit (two column halves per range)
+};
+int encode2_max_pairs();                                  // co-resident CTA pairs on this device (0: unavailable)
+Encode2Plan encode2_plan(int M, int N, int max_pairs);
+// uses A_hi, B_hi, M, N, K, bias, top_k, row_margin, wnorm_sq_max, cand ([rows padded to 256][nlists][ENCODE_CAPG]),
+// cand_cnt ([rows padded to 256][nlists]) of `a`
+int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStream_t stream);
 int encode_gemm_nsplit(int M, int N, int num_sms);
 int encode_gemm_max_top_k();
 

@@ -248,6 +248,7 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
     final_losses = tr.global_losses()
+    screen = eng.screen_stats()
 
     # ---------------- timed region 2: end to end from pinned host buffers ----------------
     x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
@@ -328,7 +329,7 @@ def main():
                          "step_frac_of_encoder_roofline": (value / world) * 2.0 * D * S / (peak_tf * 1e12)},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
             "final": {"mse": final_losses["mse"], "loss": final_losses["loss"], "n_dead": final_losses["n_dead"],
-                      "unsafe_rows": eng.unsafe_rows()},
+                      "unsafe_rows": eng.unsafe_rows(), "screen": screen},
         }
         if world == 1 and not args.no_cpu_baseline:
             rows = args.cpu_rows or 1024

@@ -21,7 +21,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
 };
 
@@ -80,6 +80,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
     // m_blocks * nsplit never exceeds max(m_blocks, #SMs)
     const size_t m_blocks = (B + 127) / 128;
     size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
+    size_t cand_bytes = row_splits * ENCODE_CAPG * 8;
     if (max_pairs > 0) {
       // pair kernel: rows padded to 256, `nlists` lists per row; the list count depends on the batch size
       const int mp_max = static_cast<int>((B + 255) / 256);
@@ -87,9 +88,11 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
         const Encode2Plan pl = encode2_plan(mp * 256, static_cast<int>(S), max_pairs);
         const size_t need = static_cast<size_t>(mp) * 256 * pl.nlists;
         if (need > row_splits) row_splits = need;
+        if (need * ENCODE2_CAPG * 8 > cand_bytes) cand_bytes = need * ENCODE2_CAPG * 8;
       }
     }
-    w.cand = take(row_splits * ENCODE_CAPG * 8);
+    w.cand = take(cand_bytes);
+    w.tau_keys = take((B + 255) / 256 * 256 * 4);
     w.cand_cnt = take(row_splits * 4);
     w.row_margin = take(128 * m_blocks * 4);
   }
@@ -104,7 +107,8 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   w.entries = take(B * K * 4);
   w.active = take(S * 4);
   w.dead_list = take(S * 4);
-  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [4] max_j ||W_enc_t[j]||^2
+  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] re-scored candidates (uint)
+                         // [4] max_j ||W_enc_t[j]||^2 [5] merged list entries (uint)
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
   w.sumsq_partial = take(1024 * 8);
   if (c.aux_kind == SAEV_B200_AUX_AUXK) {
@@ -301,6 +305,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
+    g.tau_keys = at<unsigned int>(workspace, w.tau_keys);
     Encode2Plan pl;
     if (h->max_pairs > 0) {
       pl = encode2_plan(B, S, h->max_pairs);
@@ -318,7 +323,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     RescoreArgs r;
     r.cand = g.cand;
     r.cand_cnt = g.cand_cnt;
-    r.cand_stride = ENCODE_CAPG;
+    r.cand_stride = h->max_pairs > 0 ? ENCODE2_CAPG : ENCODE_CAPG;
     r.nsplit = g.nsplit;
     r.row_margin = g.row_margin;
     r.wnorm_sq_max = g.wnorm_sq_max;

@@ -38,7 +38,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int HALF = BN / 2;   // columns per epilogue warp per tile
-constexpr int CAPG = ENCODE_CAPG;
+constexpr int CAPG = ENCODE2_CAPG;             // entries per candidate list
+constexpr int TRIGGER = CAPG - HALF;            // compact a list once it could not absorb a whole further tile
 
 constexpr size_t OFF_BIAS = static_cast<size_t>(STAGES) * STAGE_BYTES;            // [8 warps][2 acc stages][128] f32
 constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * 2 * HALF * 4;  // [2 halves][128 rows] f32
@@ -258,6 +259,7 @@ struct Params {
   const float* wnorm_sq_max;
   int2* cand;
   int* cand_cnt;
+  unsigned int* tau_g;  // [rows padded to 256] order-preserving key of the best admission threshold known per row
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -389,6 +391,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       *my_tau_s = -INFINITY;
       named_bar_sync(2 + q, 64);  // both column halves of this quadrant start the row block together
 
+      unsigned int* my_tau_g = p.tau_g + (row - lane) + lane;  // == p.tau_g + row (rows are padded to 256)
       for (int n = nb; n < ne; ++n, ++tc) {
         const int as = static_cast<int>(tc & 1);
         const uint32_t aphase = static_cast<uint32_t>(tc >> 1) & 1u;
@@ -403,10 +406,13 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           bv.w = (c + 3 < p.N) ? __ldg(p.bias + c + 3) : -INFINITY;
           *reinterpret_cast<float4*>(bs + lane * 4) = bv;
         }
+        // thresholds other warps / other CTA pairs have already proven for this row (its other column ranges)
+        const unsigned int gkey = __ldcg(my_tau_g);
         __syncwarp();
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        tau = fmaxf(tau, *other_tau_s);  // the other half's threshold bounds the row's k-th largest from below too
+        tau = fmaxf(tau, *other_tau_s);
+        if (live && gkey != 0u) tau = fmaxf(tau, funkey(gkey));
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * HALF;
 
         auto process = [&](uint32_t (&a)[CHUNK], int c) {
@@ -430,28 +436,14 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (__any_sync(FULL, gm[g] > tau)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  if (v[4 * g + i] > tau) {
-                    my_buf[cnt] = make_int2(__float_as_int(v[4 * g + i]), col0 + 4 * g + i);
-                    ++cnt;
+                  const bool hit = v[4 * g + i] > tau;
+                  if (__any_sync(FULL, hit)) {  // warp-uniform: usually a single lane of a single column
+                    if (hit) {
+                      my_buf[cnt] = make_int2(__float_as_int(v[4 * g + i]), col0 + 4 * g + i);
+                      ++cnt;
+                    }
                   }
                 }
-              }
-            }
-            unsigned need = __ballot_sync(FULL, cnt > CAPG - CHUNK);
-            while (need) {
-              const int l = __ffs(need) - 1;
-              need &= need - 1;
-              const int nn = __shfl_sync(FULL, cnt, l);
-              const float mg = __shfl_sync(FULL, margin, l);
-              const float fl = __shfl_sync(FULL, tau, l);
-              int n_out;
-              bool ovf;
-              const float thr = compact_list(warp_buf + l * lane_stride, nn, p.top_k, mg, fl, lane, hist_w, n_out, ovf);
-              if (lane == l) {
-                cnt = n_out;
-                tau = fmaxf(tau, thr);
-                overflowed |= ovf;
-                *my_tau_s = tau;
               }
             }
           }
@@ -467,9 +459,32 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (c + 2 < HALF / CHUNK) tmem_ld_32x32b_x16(taddr + (c + 2) * CHUNK, acc0);
           process(acc1, c + 1);
         }
+        // the accumulator stage is drained: hand it back BEFORE any list maintenance, so that a slow compaction
+        // in one of the 16 epilogue warps of the pair does not hold up the next MMA
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);  // the leader's MMA warp owns this barrier
+
+        // A list may grow by at most HALF entries per tile (one per column), so compacting every list that is
+        // above CAPG - HALF here guarantees that appends never overflow.
+        unsigned need = __ballot_sync(FULL, cnt > TRIGGER);
+        while (need) {
+          const int l = __ffs(need) - 1;
+          need &= need - 1;
+          const int nn = __shfl_sync(FULL, cnt, l);
+          const float mg = __shfl_sync(FULL, margin, l);
+          const float fl = __shfl_sync(FULL, tau, l);
+          int n_out;
+          bool ovf;
+          const float thr = compact_list(warp_buf + l * lane_stride, nn, p.top_k, mg, fl, lane, hist_w, n_out, ovf);
+          if (lane == l) {
+            cnt = n_out;
+            tau = fmaxf(tau, thr);
+            overflowed |= ovf;
+            *my_tau_s = tau;
+            atomicMax(my_tau_g, fkey(tau));
+          }
+        }
       }
 
       // publish this (row block, range, half): trim each list to the margin band of its k-th largest
@@ -608,6 +623,9 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
   p.wnorm_sq_max = a.wnorm_sq_max;
   p.cand = reinterpret_cast<int2*>(a.cand);
   p.cand_cnt = a.cand_cnt;
+  p.tau_g = a.tau_keys;
+  if (!a.tau_keys) return 12;
+  if (cudaMemsetAsync(a.tau_keys, 0, static_cast<size_t>(pl.m_pairs) * 2 * BM * 4, stream) != cudaSuccess) return 23;
   // lists that no range covers for a given row block must read as empty
   if (cudaMemsetAsync(a.cand_cnt, 0, static_cast<size_t>(pl.m_pairs) * 2 * BM * pl.nlists * 4, stream) != cudaSuccess)
     return 23;

@@ -8,7 +8,8 @@
 namespace sb {
 
 constexpr int ENCODE_MAX_NSPLIT = 8;
-constexpr int ENCODE_CAPG = 256;  // entries per (row, split) candidate buffer of the top-k screen
+constexpr int ENCODE_CAPG = 256;   // entries per (row, split) candidate buffer of the single-CTA top-k screen
+constexpr int ENCODE2_CAPG = 384;  // entries per candidate list of the CTA-pair screen (encode_gemm2.cu)
 
 // number of kernels this library has launched (all handles); read through saev_b200_launch_count()
 extern unsigned long long g_launch_count;
@@ -31,6 +32,7 @@ struct EncodeGemmArgs {
   int num_sms = 148;
   int* cand_cnt = nullptr;              // epilogue 0: [M, nsplit] entries kept (negative: overflowed)
   void* cand = nullptr;                 // epilogue 0: [M(rounded up to 128), nsplit, ENCODE_CAPG] x {value bits, column}
+  unsigned int* tau_keys = nullptr;     // pair kernel: [rows padded to 256] shared admission thresholds (scratch)
   float* out = nullptr;                 // epilogue 1: [M, ldo]
   long long ldo = 0;
 };
@@ -47,7 +49,7 @@ struct Encode2Plan {
 };
 int encode2_max_pairs();                                  // co-resident CTA pairs on this device (0: unavailable)
 Encode2Plan encode2_plan(int M, int N, int max_pairs);
-// uses A_hi, B_hi, M, N, K, bias, top_k, row_margin, wnorm_sq_max, cand ([rows padded to 256][nlists][ENCODE_CAPG]),
+// uses A_hi, B_hi, M, N, K, bias, top_k, row_margin, wnorm_sq_max, cand ([rows padded to 256][nlists][ENCODE2_CAPG]),
 // cand_cnt ([rows padded to 256][nlists]) of `a`
 int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStream_t stream);
 int encode_gemm_nsplit(int M, int N, int num_sms);

@@ -172,7 +172,8 @@ int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s) {
 // candidate (h = <x_b, W_enc_t[j]> + b_enc[j], saev modeling.py:344-347) and select the top-k of
 // those (TopKActivation.forward, modeling.py:169-179: no ReLU, exactly k kept).  One warp per row.
 // ------------------------------------------------------------------------------------------------
-constexpr int RESCORE_WARPS = 4;
+constexpr int RESCORE_WARPS = 8;
+constexpr int RESCORE_CAP = 192;  // most candidates of one row that survive the merged threshold
 
 __device__ __forceinline__ unsigned int fkey_s(float f) {
   const unsigned int u = __float_as_uint(f);
@@ -182,68 +183,108 @@ __device__ __forceinline__ float funkey_s(unsigned int k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// One radix pass of the warp-wide k-th-largest search over a row's candidate lists: histogram of the 8-bit digit
+// at `shift` of every screen key whose higher digits equal `prefix`, then the bin holding the `need`-th largest.
+__device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* cnts, int nlists, int stride, int shift,
+                                                   unsigned int& prefix, int& need, int* hist, int lane) {
+  int4* h4 = reinterpret_cast<int4*>(hist);
+  h4[2 * lane] = make_int4(0, 0, 0, 0);
+  h4[2 * lane + 1] = make_int4(0, 0, 0, 0);
+  __syncwarp();
+  for (int l = 0; l < nlists; ++l) {
+    const int c = abs(cnts[l]);
+    const int2* lb = cbuf + static_cast<long long>(l) * stride;
+    for (int e = lane; e < c; e += 32) {
+      const unsigned int key = fkey_s(__int_as_float(__ldg(&lb[e].x)));
+      if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(hist + ((key >> shift) & 255u), 1);
+    }
+  }
+  __syncwarp();
+  const int4 a = h4[2 * lane], b = h4[2 * lane + 1];
+  const int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const int mine = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  int suf = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(FULL, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  const unsigned int bal = __ballot_sync(FULL, suf >= need);
+  const int L = 31 - __clz(bal);
+  int cum = suf - mine, j = 7;
+#pragma unroll
+  for (int jj = 7; jj > 0; --jj) {
+    if (j == jj && cum + c[jj] < need) {
+      cum += c[jj];
+      j = jj - 1;
+    }
+  }
+  const int bin = __shfl_sync(FULL, 8 * lane + j, L);
+  need = __shfl_sync(FULL, need - cum, L);
+  prefix = (prefix << 8) | static_cast<unsigned int>(bin);
+  __syncwarp();
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(RescoreArgs a) {
-  extern __shared__ float smem_f[];
+  __shared__ int hist_s[RESCORE_WARPS][256];
+  __shared__ float sv_s[RESCORE_WARPS][RESCORE_CAP];
+  __shared__ int si_s[RESCORE_WARPS][RESCORE_CAP];
+  __shared__ float se_s[RESCORE_WARPS][RESCORE_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * RESCORE_WARPS + warp;
   if (b >= a.B) return;
   const int D4 = a.D >> 2;
-  const int cap = a.nsplit * (a.cand_stride / 2);  // most candidates a row can bring
-  float* base = smem_f + static_cast<size_t>(warp) * (3 * cap);
-  float* sv = base;                                  // screen values
-  int* si = reinterpret_cast<int*>(base + cap);      // columns
-  float* se = base + 2 * cap;                        // exact values
+  float* sv = sv_s[warp];  // screen values
+  int* si = si_s[warp];    // columns
+  float* se = se_s[warp];  // exact values
+  int* hist = hist_s[warp];
 
-  // ---- gather the candidates of all splits ----
   const int2* cbuf = reinterpret_cast<const int2*>(a.cand) + static_cast<long long>(b) * a.nsplit * a.cand_stride;
-  int n = 0;
+  const int* cnts = a.cand_cnt + static_cast<long long>(b) * a.nsplit;
+  int n_total = 0;
   bool overflow = false;
-  for (int sp = 0; sp < a.nsplit; ++sp) {
-    int c = a.cand_cnt[static_cast<long long>(b) * a.nsplit + sp];
-    if (c < 0) {
-      overflow = true;
-      c = -c;
+  for (int l = 0; l < a.nsplit; ++l) {
+    const int c = cnts[l];
+    overflow |= c < 0;
+    n_total += abs(c);
+  }
+  const float margin = a.row_margin[b] * sqrtf(*a.wnorm_sq_max);
+
+  // ---- merged admission threshold: (k-th largest screen value of the row, to 16 bits) - margin ----
+  // Every list was trimmed against ITS k-th largest; the row's k-th largest is at least as large.
+  unsigned int tkey = 0u;  // below every real key
+  if (n_total > a.K) {
+    unsigned int prefix = 0u;
+    int need = a.K;
+    rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 24, prefix, need, hist, lane);
+    rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 16, prefix, need, hist, lane);
+    tkey = fkey_s(funkey_s(prefix << 16) - margin);
+  }
+  // ---- collect the survivors ----
+  int n = 0;
+  for (int l = 0; l < a.nsplit; ++l) {
+    const int c = abs(cnts[l]);
+    const int2* lb = cbuf + static_cast<long long>(l) * a.cand_stride;
+    for (int e0 = 0; e0 < c; e0 += 32) {
+      const int e = e0 + lane;
+      int2 t = make_int2(0, -1);
+      if (e < c) t = __ldg(lb + e);
+      const bool take = (e < c) && fkey_s(__int_as_float(t.x)) >= tkey;
+      const unsigned bal = __ballot_sync(FULL, take);
+      const int o = n + __popc(bal & ((1u << lane) - 1u));
+      if (take && o < RESCORE_CAP) {
+        sv[o] = __int_as_float(t.x);
+        si[o] = t.y;
+      }
+      n += __popc(bal);
     }
-    for (int e = lane; e < c; e += 32) {
-      const int2 t = cbuf[static_cast<long long>(sp) * a.cand_stride + e];
-      sv[n + e] = __int_as_float(t.x);
-      si[n + e] = t.y;
-    }
-    n += c;
+  }
+  if (n > RESCORE_CAP) {  // pathological near-tie row: cannot be certified
+    overflow = true;
+    n = RESCORE_CAP;
   }
   __syncwarp();
-  const float margin = a.row_margin[b] * sqrtf(*a.wnorm_sq_max);
-  if (a.nsplit > 1 && n > a.K) {
-    // each split applied the margin to ITS k-th largest; re-apply it to the row's k-th largest
-    unsigned int T = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
-      const unsigned int cand = T | (1u << bit);
-      int c = 0;
-      for (int e = lane; e < n; e += 32) c += fkey_s(sv[e]) >= cand;
-      c = warp_sum(c);
-      if (c >= a.K) T = cand;
-    }
-    const float thr = funkey_s(T) - margin;
-    // in-place stable compaction (reads run ahead of writes)
-    int kept = 0;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      const float v = (e < n) ? sv[e] : 0.f;
-      const int id = (e < n) ? si[e] : -1;
-      const bool take = (e < n) && v >= thr;
-      const unsigned bal = __ballot_sync(FULL, take);
-      __syncwarp();
-      if (take) {
-        const int o = kept + __popc(bal & ((1u << lane) - 1u));
-        sv[o] = v;
-        si[o] = id;
-      }
-      kept += __popc(bal);
-      __syncwarp();
-    }
-    n = kept;
-  }
 
   // ---- exact re-score, 4 candidates in flight ----
   float4 xr[VPL];
@@ -312,20 +353,19 @@ __global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(Rescor
   for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(FULL, maxerr, o));
   // The candidate set covers the exact top-k when every screen error is <= margin / 2.  Count the rows where
   // that cannot be certified: buffer overflow, or an observed error above the bound the margin assumes.
-  if (lane == 0 && a.unsafe_rows != nullptr && (overflow || maxerr > 0.5f * margin)) atomicAdd(a.unsafe_rows, 1u);
+  if (lane == 0 && a.unsafe_rows != nullptr) {
+    if (overflow || maxerr > 0.5f * margin) atomicAdd(a.unsafe_rows, 1u);
+    atomicAdd(a.unsafe_rows + 2, static_cast<unsigned int>(n));        // diagnostics: candidates re-scored
+    atomicAdd(a.unsafe_rows + 4, static_cast<unsigned int>(n_total));  //              list entries merged
+  }
 }
 
 int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
-  const size_t smem = static_cast<size_t>(RESCORE_WARPS) * 3 * a.nsplit * (a.cand_stride / 2) * 4;
   ++g_launch_count;
   const int need_ = (a.D + 127) / 128;
-#define SB_RESCORE(V)                                                                                          \
-  {                                                                                                            \
-    if (smem > 48 * 1024)                                                                                      \
-      cudaFuncSetAttribute(rescore_topk_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    rescore_topk_kernel<V><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, smem, s>>>(a);     \
-  }
+#define SB_RESCORE(V) \
+  rescore_topk_kernel<V><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, 0, s>>>(a);
   if (need_ <= 1) SB_RESCORE(1)
   else if (need_ <= 2) SB_RESCORE(2)
   else if (need_ <= 4) SB_RESCORE(4)

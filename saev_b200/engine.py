@@ -122,6 +122,12 @@ class Engine:
     def unsafe_rows(self) -> int:
         return int(self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 1).item())
 
+    def screen_stats(self) -> dict:
+        """Cumulative diagnostics of the top-k screen since the last sync_weights(): rows that could not be
+        certified, candidates re-scored in fp32, candidate-list entries merged."""
+        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 5).tolist()
+        return {"unsafe_rows": t[0], "rescored": t[2] & 0xFFFFFFFF, "merged": t[4] & 0xFFFFFFFF}
+
     # ---- parameters ------------------------------------------------------------------------
     @torch.no_grad()
     def load_params(self, W_enc, b_enc, W_dec, b_dec) -> None:

@@ -4,6 +4,7 @@
  * reference checkout):
  *   src/saev/nn/modeling.py:343-349    SparseAutoencoder.encode          -> saev_b200_forward (phase A)
  *   src/saev/nn/modeling.py:169-179    TopKActivation.forward            -> saev_b200_forward (phase A)
+ *   src/saev/nn/modeling.py:150-156    ReluActivation.forward (dense)    -> saev_b200_forward (phase A, act_kind RELU)
  *   src/saev/nn/modeling.py:351-409    SparseAutoencoder.decode          -> saev_b200_forward (phase A)
  *   src/saev/nn/objectives.py:101-156  MatryoshkaObjective.forward       -> saev_b200_forward (A + B)
  *   src/saev/nn/objectives.py:107-122  dead-latent tracker               -> saev_b200_forward (phase B)
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 2
+#define SAEV_B200_ABI_VERSION 3
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -127,6 +128,10 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
 /* Lazy dense views for saev's logging block (train.py:365-442). */
 int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,
                       float* f_x_out /* [B, d_sae] */, void* stream);
+/* Same for either activation: TopK scatters (topk_idx, topk_val); ReLU joins the bf16 (hi, lo) pair the dense path
+ * keeps in the workspace (f to ~2^-17 relative). */
+int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,
+                      float* f_x_out /* [B, d_sae] */, void* workspace, void* stream);
 int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B,
                     float* x_hat_out /* [B, d_model] */, void* stream);
 

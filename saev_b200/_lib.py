@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -97,6 +97,7 @@ SIGNATURES = {
         [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _p, _p],
     ),
     "saev_b200_densify": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "saev_b200_dense_f": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "saev_b200_x_hat": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "saev_b200_profile_enable": (C.c_int, [_p, _i32]),

@@ -23,6 +23,10 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
+  // dense (ReLU) path: bf16 (hi, lo) operand pairs
+  size_t w_enc_lo, w_dec_hi, w_dec_lo, w_decT_hi, w_decT_lo, x_lo, xT_hi, xT_lo, g_hi, g_lo, gT_hi, gT_lo, f_hi, f_lo,
+      fT_hi, fT_lo, dhT_hi, dhT_lo;
+  long long ldb = 0;  // row pitch of the batch-major transposed operands (max_batch rounded up to 8)
 };
 
 }  // namespace
@@ -75,7 +79,33 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   };
   w.shadow_hi = take(S * D * 2);
   w.x_hi = take(B * D * 2);
-  {
+  const bool relu = c.act_kind == SAEV_B200_ACT_RELU;
+  w.ldb = static_cast<long long>((B + 7) / 8 * 8);
+  if (relu) {
+    const size_t LB = static_cast<size_t>(w.ldb);
+    w.w_enc_lo = take(S * D * 2);
+    w.w_dec_hi = take(S * D * 2);
+    w.w_dec_lo = take(S * D * 2);
+    w.w_decT_hi = take(D * S * 2);
+    w.w_decT_lo = take(D * S * 2);
+    w.x_lo = take(B * D * 2);
+    w.xT_hi = take((D + 16) * LB * 2);
+    w.xT_lo = take((D + 16) * LB * 2);
+    w.g_hi = take(B * D * 2);
+    w.g_lo = take(B * D * 2);
+    w.gT_hi = take(D * LB * 2);
+    w.gT_lo = take(D * LB * 2);
+    w.f_hi = take(B * S * 2);
+    w.f_lo = take(B * S * 2);
+    w.fT_hi = take(S * LB * 2);
+    w.fT_lo = take(S * LB * 2);
+    w.dhT_hi = take(S * LB * 2);
+    w.dhT_lo = take(S * LB * 2);
+  }
+  if (relu) {
+    w.cand = w.tau_keys = w.cand_cnt = o;
+    w.row_margin = take(128 * ((B + 127) / 128) * 4);
+  } else {
     // (row, split) candidate buffers of the top-k screen: rows are padded to whole 128-row blocks and
     // m_blocks * nsplit never exceeds max(m_blocks, #SMs)
     const size_t m_blocks = (B + 127) / 128;
@@ -148,6 +178,127 @@ inline T* at(void* ws, size_t off) {
   return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
 }
 
+// Error-compensated bf16 split product on the tcgen05 kernel: out-of-line helper for the dense (ReLU) path.
+EncodeGemmArgs dense_gemm(const saev_b200_handle* h, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, long long lda,
+                          const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, long long ldb, int M, int N, int K,
+                          int epilogue) {
+  EncodeGemmArgs g;
+  g.A_hi = A_hi;
+  g.A_lo = A_lo;
+  g.B_hi = B_hi;
+  g.B_lo = B_lo;
+  g.lda = lda;
+  g.ldb = ldb;
+  g.nterms = 3;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epilogue = epilogue;
+  g.nsplit = 0;
+  g.num_sms = h->num_sms;
+  return g;
+}
+
+// Phase A of the objective forward for the ReLU activation (saev modeling.py:150-156, 343-409; objectives.py:133-151)
+int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long tokens_global, const float* W_enc_t,
+                         const float* b_enc, const float* W_dec, const float* b_dec, int training, float* resid,
+                         void* workspace, cudaStream_t s) {
+  const saev_b200_cfg& c = h->cfg;
+  const Workspace& w = h->ws;
+  const int D = c.d_model, S = c.d_sae;
+  auto bf = [&](size_t off) { return at<__nv_bfloat16>(workspace, off); };
+  const long long SD = static_cast<long long>(S) * D;
+  {
+    StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
+    // operands of this step's contractions from the fp32 master weights (W_dec is already normalised)
+    if (launch_split_bf16(W_enc_t, bf(w.shadow_hi), bf(w.w_enc_lo), SD, s) ||
+        launch_split_bf16(W_dec, bf(w.w_dec_hi), bf(w.w_dec_lo), SD, s) ||
+        launch_transpose_split(W_dec, S, D, 1.f, bf(w.w_decT_hi), bf(w.w_decT_lo), S, 0, D, s) ||
+        launch_split_bf16(x, bf(w.x_hi), bf(w.x_lo), static_cast<long long>(B) * D, s))
+      return fail(h, 41, "forward(relu): operand split launch failed%s");
+    cudaMemsetAsync(at<float>(workspace, w.row_l1), 0, static_cast<size_t>(B) * 4, s);
+    cudaMemsetAsync(at<float>(workspace, w.row_l0), 0, static_cast<size_t>(B) * 4, s);
+  }
+  {
+    StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
+    // f = relu(x W_enc + b_enc)
+    EncodeGemmArgs g = dense_gemm(h, bf(w.x_hi), bf(w.x_lo), D, bf(w.shadow_hi), bf(w.w_enc_lo), D, B, S, D, 2);
+    g.bias = b_enc;
+    g.f_hi = bf(w.f_hi);
+    g.f_lo = bf(w.f_lo);
+    g.ldf = S;
+    g.t_hi = training ? bf(w.fT_hi) : nullptr;
+    g.t_lo = training ? bf(w.fT_lo) : nullptr;
+    g.ldt = w.ldb;
+    g.row_l1 = at<float>(workspace, w.row_l1);
+    g.row_l0 = at<float>(workspace, w.row_l0);
+    g.active = at<int>(workspace, w.active);
+    if (int rc = launch_encode_gemm(g, s)) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%d", rc);
+      return fail(h, 42, "forward(relu): encoder contraction launch failed (code %s)", buf);
+    }
+  }
+  {
+    StageTimer tm(h, SAEV_B200_STAGE_DECODE, s);
+    // x_hat = f W_dec + b_dec, then r = x_hat - x, SSE partials and G = 2 r / (B D)
+    EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), S, bf(w.w_decT_hi), bf(w.w_decT_lo), S, B, D, S, 1);
+    g.bias = b_dec;
+    g.out = resid;
+    g.ldo = D;
+    if (int rc = launch_encode_gemm(g, s)) {
+      char buf[64];
+      snprintf(buf, sizeof(buf), "%d", rc);
+      return fail(h, 44, "forward(relu): decoder contraction launch failed (code %s)", buf);
+    }
+    const float gs = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+    if (launch_dense_resid(resid, x, B, D, gs, at<float>(workspace, w.row_sse), training ? bf(w.g_hi) : nullptr,
+                           training ? bf(w.g_lo) : nullptr, s))
+      return fail(h, 44, "forward(relu): residual launch failed%s");
+    if (training && launch_transpose_split(resid, B, D, gs, bf(w.gT_hi), bf(w.gT_lo), w.ldb, 0, D, s))
+      return fail(h, 44, "forward(relu): G^T launch failed%s");
+  }
+  return 0;
+}
+
+// Dense gradients of the ReLU path (autograd of the above; explicit formulas in SURVEY.md appendix A step 9)
+int backward_relu(saev_b200_handle* h, const float* x, int B, long long tokens_global, const float* W_dec,
+                  float* gW_enc_t, float* gb_enc, float* gW_dec, void* workspace, cudaStream_t s) {
+  const saev_b200_cfg& c = h->cfg;
+  const Workspace& w = h->ws;
+  const int D = c.d_model, S = c.d_sae;
+  auto bf = [&](size_t off) { return at<__nv_bfloat16>(workspace, off); };
+  StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
+  // dh = (f > 0) * (G W_dec^T + l1 / B), stored transposed as the operand of the W_enc gradient
+  EncodeGemmArgs g3 = dense_gemm(h, bf(w.g_hi), bf(w.g_lo), D, bf(w.w_dec_hi), bf(w.w_dec_lo), D, B, S, D, 3);
+  g3.f_hi = bf(w.f_hi);
+  g3.ldf = S;
+  g3.t_hi = bf(w.dhT_hi);
+  g3.t_lo = bf(w.dhT_lo);
+  g3.ldt = w.ldb;
+  g3.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
+  if (launch_encode_gemm(g3, s)) return fail(h, 52, "backward(relu): dh contraction launch failed%s");
+  // x^T with an extra row of ones: column D of the next product is sum_b dh = gb_enc
+  if (launch_transpose_split(x, B, D, 1.f, bf(w.xT_hi), bf(w.xT_lo), w.ldb, 1, D + 16, s))
+    return fail(h, 52, "backward(relu): x^T launch failed%s");
+  // gW_dec = f^T G
+  EncodeGemmArgs g4 = dense_gemm(h, bf(w.fT_hi), bf(w.fT_lo), w.ldb, bf(w.gT_hi), bf(w.gT_lo), w.ldb, S, D, B, 4);
+  g4.out = gW_dec;
+  g4.ldo = D;
+  g4.n_main = D;
+  if (launch_encode_gemm(g4, s)) return fail(h, 52, "backward(relu): gW_dec contraction launch failed%s");
+  if (c.remove_parallel_grads && launch_project_rows(gW_dec, W_dec, S, D, s))
+    return fail(h, 52, "backward(relu): projection launch failed%s");
+  // gW_enc_t = dh^T x ; gb_enc = dh^T 1
+  EncodeGemmArgs g5 = dense_gemm(h, bf(w.dhT_hi), bf(w.dhT_lo), w.ldb, bf(w.xT_hi), bf(w.xT_lo), w.ldb, S, D + 1, B, 4);
+  g5.out = gW_enc_t;
+  g5.ldo = D;
+  g5.n_main = D;
+  g5.extra = gb_enc;
+  if (launch_encode_gemm(g5, s)) return fail(h, 52, "backward(relu): gW_enc contraction launch failed%s");
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -166,12 +317,16 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   if (cfg->d_model % 8 != 0 || cfg->d_model > 2048)
     return fail(nullptr, 2, "saev_b200_create: d_model must be a multiple of 8 and <= 2048%s");
   if (cfg->d_sae % 4 != 0) return fail(nullptr, 2, "saev_b200_create: d_sae must be a multiple of 4%s");
-  if (cfg->act_kind != SAEV_B200_ACT_TOPK)
-    return fail(nullptr, 3, "saev_b200_create: only the TopK activation has a CUDA path in this build%s");
-  if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
-    return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
-  if (cfg->top_k > encode_gemm_max_top_k())
-    return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
+  if (cfg->act_kind != SAEV_B200_ACT_TOPK && cfg->act_kind != SAEV_B200_ACT_RELU)
+    return fail(nullptr, 3, "saev_b200_create: unknown activation (TopK and ReLU have CUDA paths)%s");
+  if (cfg->act_kind == SAEV_B200_ACT_TOPK) {
+    if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
+      return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
+    if (cfg->top_k > encode_gemm_max_top_k())
+      return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
+  } else if (cfg->d_sae % 8 != 0) {
+    return fail(nullptr, 2, "saev_b200_create: the dense (ReLU) path needs d_sae to be a multiple of 8%s");
+  }
   int dev = 0, cc_major = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
     cudaGetLastError();
@@ -279,7 +434,13 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   float* aux_loss = at<float>(workspace, w.scalars) + 2;
   const bool tracked = training && toks_since_active != nullptr;
 
-  if (phase & SAEV_B200_PHASE_A) {
+  if ((phase & SAEV_B200_PHASE_A) && c.act_kind == SAEV_B200_ACT_RELU) {
+    cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
+    if (int rc = forward_relu_phase_a(h, x, B, tokens_global, W_enc_t, b_enc, W_dec, b_dec, training, resid, workspace, s))
+      return rc;
+    h->last_forward_training = training != 0;
+    h->last_forward_tracked = false;
+  } else if (phase & SAEV_B200_PHASE_A) {
     cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
     if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
     __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
@@ -438,6 +599,9 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   if (tokens_global <= 0) tokens_global = B;
   const int D = c.d_model, S = c.d_sae, K = c.top_k;
   const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+  if (c.act_kind == SAEV_B200_ACT_RELU) {
+    if (int rc = backward_relu(h, x, B, tokens_global, W_dec, gW_enc_t, gb_enc, gW_dec, workspace, s)) return rc;
+  } else {
   {
     StageTimer tm(h, SAEV_B200_STAGE_CSC, s);
     if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
@@ -464,6 +628,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   {
     StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
     if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
+  }
   }
   StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, s);
   if (launch_colsum(resid, B, D, grad_scale, 0, at<float>(workspace, w.colsum_partial), gb_dec, s))
@@ -568,6 +733,19 @@ int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float*
   if (launch_densify(topk_idx, topk_val, B, h->cfg.top_k, h->cfg.d_sae, f_x_out, static_cast<cudaStream_t>(stream)))
     return fail(h, 70, "densify: launch failed%s");
   return check_cuda(h, "densify");
+}
+
+int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B, float* f_x_out,
+                      void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->cfg.act_kind == SAEV_B200_ACT_RELU) {
+    if (!workspace) return fail(h, 70, "dense_f: the ReLU path needs the workspace%s");
+    if (launch_join_bf16(at<__nv_bfloat16>(workspace, h->ws.f_hi), at<__nv_bfloat16>(workspace, h->ws.f_lo),
+                         static_cast<long long>(B) * h->cfg.d_sae, f_x_out, s))
+      return fail(h, 70, "dense_f: launch failed%s");
+    return check_cuda(h, "dense_f");
+  }
+  return saev_b200_densify(h, topk_idx, topk_val, B, f_x_out, stream);
 }
 
 int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hat_out,

@@ -40,6 +40,20 @@ constexpr int CHUNK = 16;     // accumulator columns per tcgen05.ld
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 
+struct EpiExtra {
+  __nv_bfloat16* f_hi;   // EPI 2: out, EPI 3: in   [M, ldf]
+  __nv_bfloat16* f_lo;   // EPI 2: out
+  __nv_bfloat16* t_hi;   // EPI 2/3: transposed out  [N, ldt]
+  __nv_bfloat16* t_lo;
+  long long ldf, ldt;
+  float* row_l1;         // EPI 2: += sum_cols f
+  float* row_l0;         // EPI 2: += count_cols (f > 0)
+  int* active;           // EPI 2: [N] = 1 where some row fired
+  float l1_over_b;       // EPI 3
+  int n_main;            // EPI 4
+  float* extra;          // EPI 4: [M]
+};
+
 struct EncodeSmemLayout {
   int stages;
   size_t off_bias, off_bars, total;
@@ -141,7 +155,13 @@ __device__ __forceinline__ float compact_row_global(int2* buf, int n, int k, flo
   return thr;
 }
 
-// EPI: 0 = running top-KP candidate lists, 1 = dense fp32 store of (acc + bias).
+// EPI: 0 = running top-KP candidate lists
+//      1 = dense fp32 store of (acc + bias)
+//      2 = ReLU forward (dense SAE path): f = relu(acc + bias) written as a bf16 hi/lo pair both row-major
+//          [M, ldf] (operand of the decoder contraction) and transposed [N, ldt] (operand of the weight-gradient
+//          contraction); per-row sum f / count f>0, per-column "fired" flags
+//      3 = ReLU backward: dh = (f > 0) ? acc + l1_over_b : 0, written transposed as a bf16 hi/lo pair [N, ldt]
+//      4 = weight gradient: out[row, col] = acc for col < n_main, extra[row] = acc for col == n_main
 template <int EPI, int CAPG, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -149,7 +169,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    int nterms, int kblocks_per_term, const float* __restrict__ bias, int M, int N, int m_blocks,
                    int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int top_k,
                    const float* __restrict__ row_margin, const float* __restrict__ wnorm_sq_max,
-                   int2* __restrict__ cand, int* __restrict__ cand_cnt, float* __restrict__ out, long long ldo) {
+                   int2* __restrict__ cand, int* __restrict__ cand_cnt, float* __restrict__ out, long long ldo,
+                   const EpiExtra ex) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
@@ -271,6 +292,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // margin_b = 2 E_b:  row_margin[b] = c * ||x_b||_inf (prep kernel), times the largest encoder-row norm
     const float margin = (EPI == 0 && row < M) ? row_margin[row] * sqrtf(*wnorm_sq_max) : 0.f;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
+    float acc_l1 = 0.f, acc_l0 = 0.f;  // EPI 2
 
     for (int t = 0; t < num_tiles; ++t) {
       const int as = t & 1;
@@ -280,7 +302,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // Stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below).
       // Columns past the end get -inf in the top-k epilogue so that they can never be admitted.
       for (int c = et; c < BN; c += 128) {
-        float bv = (EPI == 0) ? -INFINITY : 0.f;
+        float bv = (EPI == 0) ? -INFINITY : 0.f;  // (columns past the end are never stored by EPI >= 1)
         if (n0 + c < n_cols) bv = (bias != nullptr) ? bias[n0 + c] : 0.f;
         bs[c] = bv;
       }
@@ -337,7 +359,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               }
             }
           }
-        } else {
+        } else if (EPI == 1) {
           if (row < M) {
             float* o = out + static_cast<long long>(row) * ldo + col0;
             if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
@@ -348,6 +370,80 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i)
                 if (col0 + i < n_cols) o[i] = v[i];
+            }
+          }
+        } else if (EPI == 2) {
+          const bool rv = row < M;
+          __nv_bfloat16 hi[CHUNK], lo[CHUNK];
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) {
+            const float f = (rv && col0 + i < n_cols) ? fmaxf(v[i], 0.f) : 0.f;
+            hi[i] = __float2bfloat16_rn(f);
+            lo[i] = __float2bfloat16_rn(f - __bfloat162float(hi[i]));
+            acc_l1 += f;
+            acc_l0 += (f > 0.f) ? 1.f : 0.f;
+            const bool fired = __any_sync(FULL, f > 0.f);
+            if (fired && lane == 0 && ex.active != nullptr) ex.active[col0 + i] = 1;
+          }
+          if (rv) {
+            __nv_bfloat16* fh = ex.f_hi + static_cast<long long>(row) * ex.ldf + col0;
+            __nv_bfloat16* fl = ex.f_lo + static_cast<long long>(row) * ex.ldf + col0;
+            if (col0 + CHUNK <= n_cols && (ex.ldf & 7) == 0) {
+              *reinterpret_cast<uint4*>(fh) = *reinterpret_cast<const uint4*>(&hi[0]);
+              *reinterpret_cast<uint4*>(fh + 8) = *reinterpret_cast<const uint4*>(&hi[8]);
+              *reinterpret_cast<uint4*>(fl) = *reinterpret_cast<const uint4*>(&lo[0]);
+              *reinterpret_cast<uint4*>(fl + 8) = *reinterpret_cast<const uint4*>(&lo[8]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < CHUNK; ++i)
+                if (col0 + i < n_cols) {
+                  fh[i] = hi[i];
+                  fl[i] = lo[i];
+                }
+            }
+            if (ex.t_hi != nullptr) {
+#pragma unroll
+              for (int i = 0; i < CHUNK; ++i)
+                if (col0 + i < n_cols) {
+                  ex.t_hi[static_cast<long long>(col0 + i) * ex.ldt + row] = hi[i];
+                  ex.t_lo[static_cast<long long>(col0 + i) * ex.ldt + row] = lo[i];
+                }
+            }
+          }
+        } else if (EPI == 3) {
+          if (row < M) {
+            __align__(16) __nv_bfloat16 fh[CHUNK];
+            const __nv_bfloat16* fp = ex.f_hi + static_cast<long long>(row) * ex.ldf + col0;
+            if (col0 + CHUNK <= n_cols && (ex.ldf & 7) == 0) {
+              *reinterpret_cast<uint4*>(&fh[0]) = __ldg(reinterpret_cast<const uint4*>(fp));
+              *reinterpret_cast<uint4*>(&fh[8]) = __ldg(reinterpret_cast<const uint4*>(fp + 8));
+            } else {
+#pragma unroll
+              for (int i = 0; i < CHUNK; ++i) fh[i] = (col0 + i < n_cols) ? fp[i] : __float2bfloat16_rn(0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) {
+              if (col0 + i < n_cols) {
+                const float d = (__bfloat162float(fh[i]) > 0.f) ? v[i] + ex.l1_over_b : 0.f;
+                const __nv_bfloat16 h = __float2bfloat16_rn(d);
+                ex.t_hi[static_cast<long long>(col0 + i) * ex.ldt + row] = h;
+                ex.t_lo[static_cast<long long>(col0 + i) * ex.ldt + row] = __float2bfloat16_rn(d - __bfloat162float(h));
+              }
+            }
+          }
+        } else {  // EPI == 4
+          if (row < M) {
+            float* o = out + static_cast<long long>(row) * ldo + col0;
+            if (col0 + CHUNK <= ex.n_main && (ldo & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < CHUNK; i += 4)
+                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < CHUNK; ++i) {
+                if (col0 + i < ex.n_main) o[i] = v[i];
+                else if (col0 + i == ex.n_main && ex.extra != nullptr) ex.extra[row] = v[i];
+              }
             }
           }
         }
@@ -371,6 +467,10 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // named barrier of tile t+1, which every warp reaches only after finishing tile t.
     }
 
+    if (EPI == 2 && row < M && num_tiles > 0) {
+      atomicAdd(ex.row_l1 + row, acc_l1);
+      atomicAdd(ex.row_l0 + row, acc_l0);
+    }
     if (EPI == 0) {
       // final compaction: trim every row buffer to the columns within the margin of its k-th largest screen
       // value and publish the count (negative = the buffer overflowed at some point: the row is not covered)
@@ -446,11 +546,15 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
     attr_set = true;
   }
   const int kblocks_per_term = (a.K + BK - 1) / BK;
+  EpiExtra ex;
+  ex.f_hi = a.f_hi; ex.f_lo = a.f_lo; ex.t_hi = a.t_hi; ex.t_lo = a.t_lo; ex.ldf = a.ldf; ex.ldt = a.ldt;
+  ex.row_l1 = a.row_l1; ex.row_l0 = a.row_l0; ex.active = a.active; ex.l1_over_b = a.l1_over_b;
+  ex.n_main = a.n_main; ex.extra = a.extra;
   kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], a.nterms,
                                                            kblocks_per_term, a.bias, a.M, a.N, m_blocks,
                                                            tiles_per_split, nsplit, a.n_limit_dev, a.top_k,
                                                            a.row_margin, a.wnorm_sq_max,
-                                                           reinterpret_cast<int2*>(a.cand), a.cand_cnt, a.out, a.ldo);
+                                                           reinterpret_cast<int2*>(a.cand), a.cand_cnt, a.out, a.ldo, ex);
                                                            ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
@@ -471,26 +575,33 @@ int encode_gemm_max_top_k() { return ENCODE_CAPG / 4; }
 
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return 0;
-  if ((a.K % 8) != 0) return 10;  // TMA needs 16-byte aligned row pitch
+  if (a.lda <= 0 && a.ldb <= 0 && (a.K % 8) != 0) return 10;  // TMA needs 16-byte aligned row pitch
   CUtensorMap maps[4];
-  const long long ldk = a.K;
-  if (make_tmap_bf16(&maps[0], a.A_hi, a.M, a.K, ldk, BM)) return 11;
-  if (make_tmap_bf16(&maps[2], a.B_hi, a.N, a.K, ldk, BN)) return 11;
+  const long long lda = a.lda > 0 ? a.lda : a.K, ldb = a.ldb > 0 ? a.ldb : a.K;
+  if ((lda % 8) != 0 || (ldb % 8) != 0) return 10;
+  if (make_tmap_bf16(&maps[0], a.A_hi, a.M, a.K, lda, BM)) return 11;
+  if (make_tmap_bf16(&maps[2], a.B_hi, a.N, a.K, ldb, BN)) return 11;
   if (a.nterms == 3) {
-    if (make_tmap_bf16(&maps[1], a.A_lo, a.M, a.K, ldk, BM)) return 11;
-    if (make_tmap_bf16(&maps[3], a.B_lo, a.N, a.K, ldk, BN)) return 11;
+    if (make_tmap_bf16(&maps[1], a.A_lo, a.M, a.K, lda, BM)) return 11;
+    if (make_tmap_bf16(&maps[3], a.B_lo, a.N, a.K, ldb, BN)) return 11;
   } else {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
   const int m_blocks = (a.M + BM - 1) / BM;
   const int n_tiles = (a.N + BN - 1) / BN;
-  if (a.epilogue == 1) {
-    // dense store: any split works; use enough CTAs to fill the GPU
+  if (a.epilogue >= 1) {
+    // dense epilogues: any column split works; use enough CTAs to fill the GPU
     int nsplit = a.nsplit > 0 ? a.nsplit : encode_gemm_nsplit(a.M, a.N, a.num_sms);
     const int tps = (n_tiles + nsplit - 1) / nsplit;
     nsplit = (n_tiles + tps - 1) / tps;
-    return launch_variant<1, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+    switch (a.epilogue) {
+      case 1: return launch_variant<1, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+      case 2: return launch_variant<2, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+      case 3: return launch_variant<3, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+      case 4: return launch_variant<4, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+      default: return 12;
+    }
   }
   const int nsplit = a.nsplit;
   const int tps = (n_tiles + nsplit - 1) / nsplit;

@@ -22,9 +22,22 @@ struct EncodeGemmArgs {
   const __nv_bfloat16* B_lo = nullptr;
   int nterms = 1;                       // 1: A_hi.B_hi    3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
   int M = 0, N = 0, K = 0;
+  long long lda = 0, ldb = 0;           // row pitch of A / B in elements (0 = K); must be multiples of 8
   const float* bias = nullptr;          // [N] or null
   const int* n_limit_dev = nullptr;     // optional device-side column count (<= N)
-  int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store
+  int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store, 2: ReLU forward,
+                                        // 3: ReLU backward, 4: weight gradient (see encode_gemm.cu)
+  __nv_bfloat16* f_hi = nullptr;        // epilogue 2 (out) / 3 (in): relu(h) as bf16 hi [M, ldf]
+  __nv_bfloat16* f_lo = nullptr;        // epilogue 2: bf16 residual
+  __nv_bfloat16* t_hi = nullptr;        // epilogue 2/3: transposed bf16 hi/lo outputs [N, ldt]
+  __nv_bfloat16* t_lo = nullptr;
+  long long ldf = 0, ldt = 0;
+  float* row_l1 = nullptr;              // epilogue 2: [M] += sum f   (caller zeroes)
+  float* row_l0 = nullptr;              // epilogue 2: [M] += count f > 0
+  int* active = nullptr;                // epilogue 2: [N] = 1 where a row fired
+  float l1_over_b = 0.f;                // epilogue 3
+  int n_main = 0;                       // epilogue 4: columns < n_main go to out, column n_main to extra[row]
+  float* extra = nullptr;
   int top_k = 32;                       // epilogue 0: k of the final selection
   const float* row_margin = nullptr;    // epilogue 0: [M] admission margin per row / max encoder-row norm
   const float* wnorm_sq_max = nullptr;  // epilogue 0: device scalar, max_j ||B[j]||^2 of the fp32 weights
@@ -134,6 +147,14 @@ int launch_dead_update(long long* toks, int* active, int S, long long batch_toke
 
 int launch_densify(const int* idx, const float* val, int B, int K, int S, float* out, cudaStream_t s);
 int launch_add_rows(const float* a, const float* b, long long n, float* out, cudaStream_t s);  // out = a + b
+
+// ---- dense_kernels.cu (ReLU / dense path) ----------------------------------------------------------------
+int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
+                           long long ldr, int ones_row, int C_pad, cudaStream_t s);
+int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
+                       __nv_bfloat16* g_lo, cudaStream_t s);
+int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t s);
+int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s);
 
 // ---- aux_kernels.cu -------------------------------------------------------------------------------------
 struct AuxArgs {

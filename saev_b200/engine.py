@@ -78,7 +78,7 @@ class Engine:
             self.m = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             self.v = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
             self.workspace = torch.zeros(self.lib.saev_b200_workspace_bytes(h), dtype=torch.uint8, device=dev)
-            B, K = cfg.max_batch, cfg.top_k
+            B, K = cfg.max_batch, max(cfg.top_k, 1)
             self.topk_idx = torch.empty(B, K, dtype=torch.int32, device=dev)
             self.topk_val = torch.empty(B, K, dtype=torch.float32, device=dev)
             self.resid = torch.empty(B, D, dtype=torch.float32, device=dev)
@@ -240,8 +240,9 @@ class Engine:
         out = torch.empty(B, self.S, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._ck(
-                self.lib.saev_b200_densify(
-                    self.h, self.topk_idx.data_ptr(), self.topk_val.data_ptr(), B, out.data_ptr(), self._stream()
+                self.lib.saev_b200_dense_f(
+                    self.h, self.topk_idx.data_ptr(), self.topk_val.data_ptr(), B, out.data_ptr(),
+                    self.workspace.data_ptr(), self._stream()
                 )
             )
         return out

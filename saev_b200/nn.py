@@ -22,8 +22,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     are unchanged, checkpoints interoperate with saev.nn.load / saev.nn.dump).
   * `Output.h_x`, `Output.f_x`, `Output.x_hats` are materialised lazily (the fused path never writes the
     [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
-  * Matryoshka n_prefixes > 1, BatchTopK and the dense ReLU activation have no CUDA path in this build and
-    raise NotImplementedError at forward time.
+  * Matryoshka n_prefixes > 1 and BatchTopK have no CUDA path in this build and raise NotImplementedError at
+    forward time.  Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05).
 """
 
 from __future__ import annotations
@@ -355,9 +355,10 @@ class SparseAutoencoder(torch.nn.Module):
         raise RuntimeError("remove_parallel_grads(): gradients were not produced by the fused backward")
 
     def _require_topk(self):
-        if _kind(self.cfg.activation) != "TopK":
-            raise NotImplementedError(f"activation {_kind(self.cfg.activation)} has no CUDA path in this build of "
-                                      "saev_b200 (TopK only)")
+        """TopK (sparse path) and Relu (dense path) have CUDA paths; BatchTopK does not."""
+        if _kind(self.cfg.activation) not in ("TopK", "Relu"):
+            raise NotImplementedError(f"activation {_kind(self.cfg.activation)} has no CUDA path in saev_b200 "
+                                      "(TopK and Relu only)")
 
 
 # ----------------------------------------------------------------------------------------------

@@ -10,13 +10,18 @@ from tests.golden_util import CASES, load_case, rel_l2, t
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-5
-TOPK_CASES = [c for c in CASES if "relu" not in c]
+TOL_DENSE = 6e-5  # ReLU: bf16 split contractions, see test_gpu_golden.py
 
 
 def _make(z, meta, cfg):
     aux = nn.AuxK(k_aux=cfg.k_aux, alpha=cfg.aux_alpha) if cfg.aux else nn.NoAux()
+    if cfg.activation == "relu":
+        sp = nn.L1Sparsity(coeff=cfg.l1_coeff) if cfg.l1_coeff else nn.NoSparsity()
+        act = nn.Relu(sparsity=sp, aux=aux)
+    else:
+        act = nn.TopK(top_k=cfg.top_k, aux=aux)
     sae_cfg = nn.SparseAutoencoderConfig(
-        d_model=cfg.d_model, d_sae=cfg.d_sae, activation=nn.TopK(top_k=cfg.top_k, aux=aux), reinit_blend=0.0,
+        d_model=cfg.d_model, d_sae=cfg.d_sae, activation=act, reinit_blend=0.0,
         remove_parallel_grads=cfg.remove_parallel_grads, normalize_w_dec=cfg.normalize_w_dec)
     sae = nn.SparseAutoencoder(sae_cfg)
     sae.load_state_dict({k: t(z[f"init_{k}"]) for k in ("W_dec", "b_dec", "W_enc", "b_enc")})
@@ -24,9 +29,10 @@ def _make(z, meta, cfg):
     return sae, objective
 
 
-@pytest.mark.parametrize("name", TOPK_CASES)
+@pytest.mark.parametrize("name", CASES)
 def test_loop_body_through_the_nn_api(name):
     z, meta, cfg = load_case(name)
+    TOL = TOL_DENSE if cfg.activation == "relu" else globals()["TOL"]
     sae, objective = _make(z, meta, cfg)
     param_group = {"params": sae.parameters(), "lr": 0.0}  # train.py:118
     opt = optim.FusedAdam([param_group], fused=True)  # train.py:294 (constructed while the module is on the CPU)
@@ -58,7 +64,11 @@ def test_loop_body_through_the_nn_api(name):
                 assert g.shape == getattr(sae, k).shape
                 assert rel_l2((g * coef).cpu(), z[f"grads_{k}"][i]) < TOL, (step, k)
             assert rel_l2(fwd.x_hats[:, -1, :].cpu(), z["x_hat"][i]) < TOL
-            assert fwd.f_x.shape == (meta["B"], cfg.d_sae) and int((fwd.f_x != 0).sum(1).max()) <= cfg.top_k
+            assert fwd.f_x.shape == (meta["B"], cfg.d_sae)
+            if cfg.activation == "topk":
+                assert int((fwd.f_x != 0).sum(1).max()) <= cfg.top_k
+            else:
+                assert bool((fwd.f_x >= 0).all())
         opt.step()
         opt.param_groups[0]["lr"] = sched.step()
         opt.zero_grad()

@@ -13,6 +13,9 @@ from tests.golden_util import CASES, load_case, rel_l2, t
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-5
+# the dense ReLU path computes its five contractions as bf16 split products (~2^-17 relative per product) instead of
+# fp32 FMAs: still an order of magnitude inside the 1e-4 bar, but not at summation-order level
+TOL_DENSE = 6e-5
 TOPK_CASES = [c for c in CASES if "relu" not in c]
 
 
@@ -29,9 +32,10 @@ def _engine_for(meta, cfg, B):
     )
 
 
-@pytest.mark.parametrize("name", TOPK_CASES)
+@pytest.mark.parametrize("name", CASES)
 def test_cuda_path_replays_reference_run(name):
     z, meta, cfg = load_case(name)
+    TOL = TOL_DENSE if cfg.activation == "relu" else globals()["TOL"]
     B = meta["B"]
     eng = _engine_for(meta, cfg, B)
     eng.load_params(t(z["init_W_enc"]), t(z["init_b_enc"]), t(z["init_W_dec"]), t(z["init_b_dec"]))
@@ -76,7 +80,8 @@ def test_cuda_path_replays_reference_run(name):
     assert ld["l0"] == pytest.approx(float(z["eval_l0"]), rel=TOL)
     assert ld["aux"] == 0.0 and ld["n_dead"] == 0.0
     assert rel_l2(eng.x_hat(x).cpu(), z["eval_x_hat"]) < TOL
-    assert eng.unsafe_rows() == 0
+    if cfg.activation == "topk":
+        assert eng.unsafe_rows() == 0
 
 
 def test_fused_renorm_equals_start_of_step_normalize():

@@ -25,10 +25,11 @@ ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (d_model, d_sae, top_k, batch per GPU)
+    # name: (d_model, d_sae, top_k, batch per GPU)      top_k == 0: ReLU activation + L1Sparsity(4e-4) (dense path)
     "c3": (1024, 65536, 32, 16384),
     "c2": (768, 32768, 32, 4096),
     "c1": (128, 512, 16, 256),
+    "c5": (1536, 131072, 0, 8192),
 }
 METRIC = "activations/sec"
 FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
@@ -101,6 +102,13 @@ class ClockSampler:
                 "reasons": reasons, "n_samples": len(sm)}
 
 
+def oracle_cfg(orc, D, S, K):
+    if K == 0:
+        return orc.OracleConfig(d_model=D, d_sae=S, activation="relu", top_k=1, l1_coeff=4e-4, aux=True, k_aux=512,
+                                lr=4e-4, n_lr_warmup=500, n_steps=10_000)
+    return orc.OracleConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=512, lr=4e-4, n_lr_warmup=500, n_steps=10_000)
+
+
 def cpu_reference_run(D, S, K, steps, warmup, batch, threads=None):
     """Times the CPU restatement of the reference's step (oracle/sae_oracle.py, pinned against the live
     reference) on the host cores.  Returns (acts_per_s, ms_per_step, cores)."""
@@ -113,7 +121,7 @@ def cpu_reference_run(D, S, K, steps, warmup, batch, threads=None):
     g = torch.Generator().manual_seed(0)
     W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
     st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
-    cfg = orc.OracleConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=512, lr=4e-4, n_lr_warmup=500, n_steps=10_000)
+    cfg = oracle_cfg(orc, D, S, K)
     xs = [torch.randn(batch, D, generator=g) for _ in range(2)]
     for i in range(warmup):
         orc.train_step(cfg, st, xs[i % 2])
@@ -152,7 +160,8 @@ def run_reference(args, D, S, K, B, rank, world):
 
 
 def workload_name(w, D, S, K, B):
-    return (f"{w}: d_model={D} d_sae={S} TopK k={K} batch={B}/GPU, objective MSE+AuxK(k_aux=512, alpha=1/32, "
+    act = f"TopK k={K}" if K else "ReLU + L1Sparsity(4e-4)"
+    return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective MSE+AuxK(k_aux=512, alpha=1/32, "
             f"dead_threshold=10M tokens), remove_parallel_grads, clip 1.0, Adam, lr warmup; Gaussian activations")
 
 
@@ -196,7 +205,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation="topk" if K else "relu",
+                              l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
                               dead_threshold_tokens=10_000_000, max_batch=B), device=dev)
     eng.init_params(seed=0)
     tr = DataParallelTrainer(eng)
@@ -312,8 +322,10 @@ def main():
                 "workload": workload_name(args.workload, D, S, K, B),
                 "global_batch": world * B,
                 "parallelism": f"dp{world}",
-                "precision": "bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "
-                             "every value that reaches the loss / gradients / parameters is fp32",
+                "precision": ("bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "
+                              "every value that reaches the loss / gradients / parameters is fp32") if K else
+                             ("dense path: all five contractions as 3-term bf16 split products on tcgen05 (~2^-17 "
+                              "relative), fp32 accumulation; everything else fp32"),
                 "l2_policy": f"per-step working set (params+grads+Adam moments {eng.n_params * 16 / 1e9:.2f} GB, "
                              f"{NB} rotating input batches) is far larger than the 126 MB L2; no explicit flush",
             },
@@ -321,7 +333,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "activations/s", "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": 32},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "encode_gemm_kernel (tcgen05 encoder contraction + top-k screen)",
+            "roofline": {"bound": "tensor", "kernel": "encode_gemm2_kernel (tcgen05 cta_group::2 encoder contraction + "
+                         "top-k screen)" if K else "encode_gemm_kernel<2> (tcgen05 encoder contraction, 3-term split, ReLU)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "peak_source": f"{peaks_src} (bf16 dense, sustained)",

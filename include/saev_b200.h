@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 3
+#define SAEV_B200_ABI_VERSION 4
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -114,6 +114,12 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
 /* sumsq_out[0] = sum of squares over the flat gradient bucket of `n` floats (after any all-reduce). */
 int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,
                          void* workspace, void* stream);
+
+/* Same value for the gradient saev_b200_backward has just written (TopK path, single rank: nothing may have
+ * modified the bucket in between), from the per-atom partials the backward kernels left in the workspace -- saves
+ * the extra pass over the bucket.  gb_dec = the b_dec slice of the bucket. */
+int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
+                               void* stream);
 
 /* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + bf16 operand refresh.
  *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)

@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -92,6 +92,7 @@ SIGNATURES = {
     "saev_b200_unsafe_rows": (_p, [_p, _p]),
     "saev_b200_backward": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "saev_b200_grad_sumsq": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
+    "saev_b200_grad_sumsq_local": (C.c_int, [_p, _p, _p, _p, _p]),
     "saev_b200_adam_step": (
         C.c_int,
         [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _p, _p],

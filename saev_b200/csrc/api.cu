@@ -22,7 +22,7 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
-      entries, active, dead_list, scalars, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
+      entries, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   // dense (ReLU) path: bf16 (hi, lo) operand pairs
   size_t w_enc_lo, w_dec_hi, w_dec_lo, w_decT_hi, w_decT_lo, x_lo, xT_hi, xT_lo, g_hi, g_lo, gT_hi, gT_lo, f_hi, f_lo,
       fT_hi, fT_lo, dhT_hi, dhT_lo;
@@ -40,6 +40,7 @@ struct saev_b200_handle {
   Workspace ws;
   bool last_forward_training = false;
   bool last_forward_tracked = false;
+  bool row_gsq_valid = false;  // the last backward left per-atom ||g||^2 partials in the workspace
   mutable char err[512];
   // optional per-stage CUDA-event timing (saev_b200_profile_*)
   bool prof_on = false;
@@ -139,6 +140,8 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   w.dead_list = take(S * 4);
   w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] re-scored candidates (uint)
                          // [4] max_j ||W_enc_t[j]||^2 [5] merged list entries (uint)
+  w.block_totals = take(((S + 1023) / 1024) * 4);
+  w.row_gsq = take(S * 4);
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
   w.sumsq_partial = take(1024 * 8);
   if (c.aux_kind == SAEV_B200_AUX_AUXK) {
@@ -429,6 +432,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   const Workspace& w = h->ws;
   if (B <= 0 || B > c.max_batch) return fail(h, 40, "forward: B out of range (0 < B <= cfg.max_batch)%s");
   if (tokens_global <= 0) tokens_global = B;
+  h->row_gsq_valid = false;
   const int D = c.d_model, S = c.d_sae, K = c.top_k;
   int* scal_i = at<int>(workspace, w.scalars);
   float* aux_loss = at<float>(workspace, w.scalars) + 2;
@@ -534,7 +538,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     bool aux_live = false;
     if (tracked) {
       if (launch_dead_update(reinterpret_cast<long long*>(toks_since_active), at<int>(workspace, w.active), S,
-                             tokens_global, c.dead_threshold_tokens, at<int>(workspace, w.dead_list), scal_i, s))
+                             tokens_global, c.dead_threshold_tokens, at<int>(workspace, w.dead_list), scal_i,
+                             at<int>(workspace, w.block_totals), s))
         return fail(h, 45, "forward: dead tracker launch failed%s");
       h->last_forward_tracked = true;
       if (c.aux_kind == SAEV_B200_AUX_AUXK) {
@@ -563,6 +568,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
         a.colsum_partial = at<float>(workspace, w.colsum_partial);
         a.gb_dec = nullptr;
         a.aux_colpart = at<float>(workspace, w.aux_colpart);
+        a.row_gsq = nullptr;
         if (launch_aux_forward(a, s)) return fail(h, 46, "forward: AuxK launch failed%s");
         aux_live = true;
       }
@@ -605,7 +611,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   {
     StageTimer tm(h, SAEV_B200_STAGE_CSC, s);
     if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
-                         at<int>(workspace, w.cursor), at<int>(workspace, w.entries), s))
+                         at<int>(workspace, w.cursor), at<int>(workspace, w.entries), at<int>(workspace, w.block_totals), s))
       return fail(h, 51, "backward: CSC build launch failed%s");
   }
   WgradArgs g;
@@ -625,6 +631,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
   g.gW_enc_t = gW_enc_t;
   g.gb_enc = gb_enc;
   g.gW_dec = gW_dec;
+  g.row_gsq = at<float>(workspace, w.row_gsq);
   {
     StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
     if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
@@ -661,9 +668,21 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
     a.colsum_partial = at<float>(workspace, w.colsum_partial);
     a.gb_dec = gb_dec;
     a.aux_colpart = at<float>(workspace, w.aux_colpart);
+    a.row_gsq = c.act_kind == SAEV_B200_ACT_TOPK ? at<float>(workspace, w.row_gsq) : nullptr;
     if (launch_aux_backward(a, s)) return fail(h, 54, "backward: AuxK launch failed%s");
   }
+  h->row_gsq_valid = c.act_kind == SAEV_B200_ACT_TOPK;
   return check_cuda(h, "backward");
+}
+
+int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
+                               void* stream) {
+  if (!h->row_gsq_valid) return fail(h, 63, "grad_sumsq_local: no per-atom partials (call right after backward; TopK only)%s");
+  StageTimer tm(h, SAEV_B200_STAGE_SUMSQ, static_cast<cudaStream_t>(stream));
+  if (launch_sumsq_fused(at<float>(workspace, h->ws.row_gsq), h->cfg.d_sae, gb_dec, h->cfg.d_model, sumsq_out,
+                         static_cast<cudaStream_t>(stream)))
+    return fail(h, 60, "grad_sumsq_local: launch failed%s");
+  return check_cuda(h, "grad_sumsq_local");
 }
 
 int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,

@@ -347,6 +347,23 @@ __global__ void __launch_bounds__(256) aux_colsum_final_kernel(const float* __re
   }
 }
 
+// row_gsq[L[i]] = ||gW_dec[L[i]]||^2 + ||gW_enc_t[L[i]]||^2 + gb_enc[L[i]]^2 for the dead atoms (their rows were rewritten)
+__global__ void __launch_bounds__(256) aux_rows_gsq_kernel(const float* __restrict__ gW_dec, const float* __restrict__ gW_enc_t,
+                                                           const float* __restrict__ gb_enc, const int* __restrict__ dead_list,
+                                                           const int* __restrict__ n_dead_p, int D, float* __restrict__ row_gsq) {
+  const int n = *n_dead_p;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const long long j = dead_list[i];
+    const float* a = gW_dec + j * D;
+    const float* b = gW_enc_t + j * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) ss += a[d] * a[d] + b[d] * b[d];
+    ss = warp_sum(ss);
+    if (lane == 0) row_gsq[j] = ss + gb_enc[j] * gb_enc[j];
+  }
+}
+
 size_t aux_colpart_bytes(int cap) { return static_cast<size_t>(AUX_SLABS) * cap * 4; }
 
 int launch_aux_forward(const AuxArgs& a, cudaStream_t s) {
@@ -419,6 +436,10 @@ int launch_aux_backward(const AuxArgs& a, cudaStream_t s) {
   w.dyn = a.n_dead; w.dyn_which = 1;
   w.alpha = 1.f;
   launch_sgemm<true, false>(w, s);
+  if (a.row_gsq != nullptr) {
+    aux_rows_gsq_kernel<<<148 * 2, 256, 0, s>>>(a.gW_dec, a.gW_enc_t, a.gb_enc, a.dead_list, a.n_dead, a.D, a.row_gsq);
+    ++g_launch_count;
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

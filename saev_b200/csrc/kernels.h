@@ -101,7 +101,7 @@ struct DecodeArgs {
 int launch_decode(const DecodeArgs& a, cudaStream_t s);
 
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
-                     int* entries, cudaStream_t s);
+                     int* entries, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s);
 
 struct WgradArgs {
   const int* feat_off; const int* entries; const float* topk_val; const float* dh;
@@ -109,6 +109,7 @@ struct WgradArgs {
   int B, D, S, K;
   float grad_scale; int remove_parallel;
   float* gW_enc_t; float* gb_enc; float* gW_dec;
+  float* row_gsq;   // optional [S]: this atom's ||gW_enc_t[j]||^2 + ||gW_dec[j]||^2 + gb_enc[j]^2
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 
@@ -118,6 +119,7 @@ int launch_colsum(const float* src, int B, int D, float scale, int accumulate, f
 int colsum_partial_rows(int B);
 
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);
+int launch_sumsq_fused(const float* row_gsq, int S, const float* gb_dec, int D, float* out_sumsq, cudaStream_t s);
 
 struct AdamArgs {
   float* W_enc_t; float* b_enc; float* W_dec; float* b_dec;
@@ -143,7 +145,7 @@ struct FinalizeArgs {
 int launch_finalize(const FinalizeArgs& a, cudaStream_t s);
 
 int launch_dead_update(long long* toks, int* active, int S, long long batch_tokens, long long threshold,
-                       int* dead_list, int* n_dead, cudaStream_t s);
+                       int* dead_list, int* n_dead, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s);
 
 int launch_densify(const int* idx, const float* val, int B, int K, int S, float* out, cudaStream_t s);
 int launch_add_rows(const float* a, const float* b, long long n, float* out, cudaStream_t s);  // out = a + b
@@ -171,6 +173,7 @@ struct AuxArgs {
   float* gW_enc_t; float* gb_enc; float* gW_dec;   // rows of dead latents are (over)written
   float* colsum_partial; float* gb_dec;            // gb_dec += sum_b G_aux
   float* aux_colpart;      // [32, S] scratch for the gb_enc column sums
+  float* row_gsq;          // optional [d_sae]: refreshed for the dead atoms whose gradient rows are overwritten
 };
 int launch_aux_forward(const AuxArgs& a, cudaStream_t s);
 int launch_aux_backward(const AuxArgs& a, cudaStream_t s);

@@ -484,45 +484,80 @@ int launch_decode(const DecodeArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // CSC of the active set: for every dictionary atom j the list of (b, k) slots where it fired.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ cnt, int* __restrict__ off,
-                                                           int* __restrict__ cursor, int S) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry_s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+// Two-level exclusive scan of the per-atom counts (1024 atoms per block): block totals first, then every block
+// adds the totals of the blocks before it to its local scan.
+__global__ void __launch_bounds__(1024) block_totals_kernel(const int* __restrict__ cnt, int S, int* __restrict__ totals) {
+  __shared__ int ws[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int c = (i < S) ? cnt[i] : 0;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
   __syncthreads();
-  for (int base = 0; base < S; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int c = (i < S) ? cnt[i] : 0;
-    int incl = c;
+  if (threadIdx.x < 32) {
+    int t = ws[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) totals[blockIdx.x] = t;
+  }
+}
+
+// prefix = sum of totals[0 .. blockIdx.x), computed by the whole block
+__device__ __forceinline__ int block_prefix(const int* __restrict__ totals, int* ws) {
+  int t = 0;
+  for (int b = threadIdx.x; b < static_cast<int>(blockIdx.x); b += 1024) t += totals[b];
+  t = warp_sum(t);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+  __syncthreads();
+  int r = 0;
+  if (threadIdx.x < 32) r = warp_sum(ws[threadIdx.x]);
+  __syncthreads();
+  if (threadIdx.x == 0) ws[0] = r;
+  __syncthreads();
+  r = ws[0];
+  __syncthreads();
+  return r;
+}
+
+// inclusive scan of `v` over the 1024 threads of the block; returns this thread's inclusive value, block total in *tot
+__device__ __forceinline__ int block_scan_incl(int v, int* ws, int* tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = ws[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += t;
+      const int t = __shfl_up_sync(FULL, w, o);
+      if (lane >= o) w += t;
     }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, w, o);
-        if (lane >= o) w += t;
-      }
-      warp_tot[lane] = w;  // inclusive scan of warp totals
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    const int excl = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl - c;
-    if (i < S) {
-      off[i] = excl;
-      cursor[i] = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
-    __syncthreads();
+    ws[lane] = w;
   }
-  if (threadIdx.x == 0) off[S] = carry_s;
+  __syncthreads();
+  const int base = warp > 0 ? ws[warp - 1] : 0;
+  *tot = ws[31];
+  __syncthreads();
+  return base + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ cnt, const int* __restrict__ totals,
+                                                           int* __restrict__ off, int* __restrict__ cursor, int S) {
+  __shared__ int ws[32];
+  const int prefix = block_prefix(totals, ws);
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int c = (i < S) ? cnt[i] : 0;
+  int tot;
+  const int incl = block_scan_incl(c, ws, &tot);
+  if (i < S) {
+    off[i] = prefix + incl - c;
+    cursor[i] = 0;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) off[S] = prefix + tot;
 }
 
 __global__ void csc_fill_kernel(const int* __restrict__ idx, long long n, const int* __restrict__ off,
@@ -536,8 +571,11 @@ __global__ void csc_fill_kernel(const int* __restrict__ idx, long long n, const 
 }
 
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
-                     int* entries, cudaStream_t s) {
-  scan_counts_kernel<<<1, 1024, 0, s>>>(feat_count, feat_off, cursor, S);
+                     int* entries, int* block_totals, cudaStream_t s) {
+  const int nb = (S + 1023) / 1024;
+  block_totals_kernel<<<nb, 1024, 0, s>>>(feat_count, S, block_totals);
+  ++g_launch_count;
+  scan_counts_kernel<<<nb, 1024, 0, s>>>(feat_count, block_totals, feat_off, cursor, S);
   ++g_launch_count;
   const long long n = static_cast<long long>(B) * K;
   csc_fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(topk_idx, n, feat_off, cursor, entries);
@@ -604,7 +642,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
         *reinterpret_cast<float4*>(gerow + 4 * v) = make_float4(0, 0, 0, 0);
       }
     }
-    if (lane == 0) a.gb_enc[j] = 0.f;
+    if (lane == 0) {
+      a.gb_enc[j] = 0.f;
+      if (a.row_gsq) a.row_gsq[j] = 0.f;
+    }
     return;
   }
   const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
@@ -632,6 +673,13 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
       *reinterpret_cast<float4*>(gdrow + 4 * v) = gd[i];
       *reinterpret_cast<float4*>(gerow + 4 * v) = ge[i];
     }
+  }
+  if (a.row_gsq != nullptr) {  // this atom's share of ||g||^2 (saves the separate pass of clip_grad_norm_)
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) ss += dot4(gd[i], gd[i]) + dot4(ge[i], ge[i]);
+    ss = warp_sum(ss);
+    if (lane == 0) a.row_gsq[j] = ss + sdh * sdh;
   }
   if (lane == 0) a.gb_enc[j] = sdh;
 }
@@ -717,6 +765,28 @@ __global__ void sumsq_stage2(const double* partial, int n, float* out) {
     *out = static_cast<float>(t);
   }
 }
+// ||g||^2 from the per-atom partials the weight-gradient kernels left behind, plus the b_dec gradient
+__global__ void __launch_bounds__(1024) sumsq_fused_kernel(const float* __restrict__ row_gsq, int S,
+                                                           const float* __restrict__ gb_dec, int D, float* __restrict__ out) {
+  __shared__ double ws[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < S; i += 1024) acc += row_gsq[i];
+  for (int d = threadIdx.x; d < D; d += 1024) acc += static_cast<double>(gb_dec[d]) * gb_dec[d];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += ws[w];
+    *out = static_cast<float>(t);
+  }
+}
+int launch_sumsq_fused(const float* row_gsq, int S, const float* gb_dec, int D, float* out_sumsq, cudaStream_t s) {
+  sumsq_fused_kernel<<<1, 1024, 0, s>>>(row_gsq, S, gb_dec, D, out_sumsq);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s) {
   sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, partial);
   ++g_launch_count;
@@ -918,48 +988,44 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
 // dead-latent tracker (saev objectives.py:107-120): toks += tokens; toks[active] = 0;
 // dead = toks >= threshold; emits the ascending list of dead atoms and its length; clears `active`.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) dead_update_kernel(long long* __restrict__ toks, int* __restrict__ active,
-                                                           int S, long long batch_tokens, long long threshold,
-                                                           int* __restrict__ dead_list, int* __restrict__ n_dead) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry_s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < S; base += 1024) {
-    const int i = base + threadIdx.x;
-    int dead = 0;
-    if (i < S) {
-      const long long t = active[i] ? 0 : toks[i] + batch_tokens;
-      toks[i] = t;
-      active[i] = 0;
-      dead = t >= threshold;
-    }
-    const unsigned bal = __ballot_sync(FULL, dead);
-    const int incl_w = __popc(bal & (0xffffffffu >> (31 - lane)));
-    if (lane == 31) warp_tot[warp] = incl_w;
-    __syncthreads();
-    if (warp == 0) {
-      int w = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, w, o);
-        if (lane >= o) w += t;
-      }
-      warp_tot[lane] = w;
-    }
-    __syncthreads();
-    const int carry = carry_s;
-    if (dead) dead_list[carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl_w - 1] = i;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
-    __syncthreads();
+__global__ void __launch_bounds__(1024) dead_update_kernel(long long* __restrict__ toks, int* __restrict__ active, int S,
+                                                           long long batch_tokens, long long threshold,
+                                                           int* __restrict__ totals) {
+  __shared__ int ws[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int dead = 0;
+  if (i < S) {
+    const long long t = active[i] ? 0 : toks[i] + batch_tokens;
+    toks[i] = t;
+    active[i] = 0;
+    dead = t >= threshold;
   }
-  if (threadIdx.x == 0) *n_dead = carry_s;
+  dead = warp_sum(dead);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = dead;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = warp_sum(ws[threadIdx.x]);
+    if (threadIdx.x == 0) totals[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) dead_list_kernel(const long long* __restrict__ toks, int S, long long threshold,
+                                                         const int* __restrict__ totals, int* __restrict__ dead_list,
+                                                         int* __restrict__ n_dead) {
+  __shared__ int ws[32];
+  const int prefix = block_prefix(totals, ws);
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int dead = (i < S) && toks[i] >= threshold;
+  int tot;
+  const int incl = block_scan_incl(dead, ws, &tot);
+  if (dead) dead_list[prefix + incl - 1] = i;  // ascending atom order
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_dead = prefix + tot;
 }
 int launch_dead_update(long long* toks, int* active, int S, long long batch_tokens, long long threshold,
-                       int* dead_list, int* n_dead, cudaStream_t s) {
-  dead_update_kernel<<<1, 1024, 0, s>>>(toks, active, S, batch_tokens, threshold, dead_list, n_dead);
+                       int* dead_list, int* n_dead, int* block_totals, cudaStream_t s) {
+  const int nb = (S + 1023) / 1024;
+  dead_update_kernel<<<nb, 1024, 0, s>>>(toks, active, S, batch_tokens, threshold, block_totals);
+  ++g_launch_count;
+  dead_list_kernel<<<nb, 1024, 0, s>>>(toks, S, threshold, block_totals, dead_list, n_dead);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -200,7 +200,14 @@ class Engine:
                 )
             )
 
-    def grad_sumsq(self) -> torch.Tensor:
+    def grad_sumsq(self, *, local: bool = False) -> torch.Tensor:
+        """||g||^2 of the gradient bucket.  `local=True`: the bucket still holds exactly what backward() wrote (single
+        rank, no all-reduce in between) -> use the per-atom partials of the backward kernels (TopK path)."""
+        if local and self.cfg.activation == "topk":
+            with torch.cuda.device(self.device):
+                self._ck(self.lib.saev_b200_grad_sumsq_local(self.h, self.gb_dec.data_ptr(), self.sumsq.data_ptr(),
+                                                             self.workspace.data_ptr(), self._stream()))
+            return self.sumsq
         with torch.cuda.device(self.device):
             self._ck(
                 self.lib.saev_b200_grad_sumsq(
@@ -230,7 +237,7 @@ class Engine:
             self.normalize_w_dec()
         self.forward(x, training=True)
         self.backward(x)
-        self.grad_sumsq()
+        self.grad_sumsq(local=True)
         self.adam_step(lr, max_norm=max_norm, renorm_w_dec=fused_renorm and self.cfg.normalize_w_dec)
         return self.losses
 

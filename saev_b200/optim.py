@@ -55,7 +55,7 @@ def clip_grad_norm_(parameters, max_norm, norm_type: float = 2.0, error_if_nonfi
         return _torch_clip_grad_norm_(params, max_norm, norm_type=norm_type, error_if_nonfinite=error_if_nonfinite,
                                       foreach=foreach)
     eng = sae.engine
-    eng.grad_sumsq()
+    eng.grad_sumsq(local=sae._dp_world == 1)
     sae._pending_clip = float(max_norm)
     total = eng.sumsq.sqrt().reshape(())
     if error_if_nonfinite and not bool(torch.isfinite(total)):

@@ -48,7 +48,7 @@ class DataParallelTrainer:
         eng.backward(x, tokens_global=tokens_global)
         if self.world > 1:
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.group)
-        eng.grad_sumsq()
+        eng.grad_sumsq(local=self.world == 1)
         renorm = fused_renorm and eng.cfg.normalize_w_dec
         eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
         self._w_dec_normalized = renorm

@@ -83,7 +83,8 @@ class OracleEngine:
         flat = torch.cat([g["W_enc"].t().reshape(-1), g["b_enc"], g["W_dec"].reshape(-1), g["b_dec"]]) * scale
         self.grads.copy_(flat)
 
-    def grad_sumsq(self):
+    def grad_sumsq(self, *, local=False):
+        assert not local, "with more than one rank the norm must be taken on the all-reduced bucket"
         self.calls.append("sumsq")
         self.sumsq[0] = self.grads.double().pow(2).sum()
 

@@ -203,7 +203,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL kernels on a high-priority stream: the chunked gradient all-reduce then really runs beside the
+        # weight-gradient kernel instead of queueing behind its blocks (measured: 0.33 ms/step at 2 GPUs)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation="topk" if K else "relu",
                               l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 4
+#define SAEV_B200_ABI_VERSION 6
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -111,6 +111,17 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
                        const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
                        float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream);
 
+/* Staged form of saev_b200_backward (TopK path), for overlapping the data-parallel gradient exchange with the
+ * weight-gradient kernel.  stage 0: per-atom lists, gb_dec and the AuxK gradients (the rows of the dead atoms);
+ * stage 1: the weight-gradient rows [row_begin, row_end) of every atom that is not dead.  Rows [r0, r1) of
+ * gW_enc_t / gW_dec are final once stage 0 and the stage-1 call covering them have been enqueued; gb_enc / gb_dec are
+ * final after the last stage-1 call.  `toks_since_active` is the tracker state the forward updated. */
+int saev_b200_backward_stage(saev_b200_handle* h, int32_t stage, int32_t row_begin, int32_t row_end, const float* x,
+                             int32_t B, int64_t tokens_global, const float* W_enc_t, const float* b_enc,
+                             const float* W_dec, const float* b_dec, const int64_t* toks_since_active,
+                             const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
+                             float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream);
+
 /* sumsq_out[0] = sum of squares over the flat gradient bucket of `n` floats (after any all-reduce). */
 int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n, float* sumsq_out,
                          void* workspace, void* stream);
@@ -120,6 +131,19 @@ int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n
  * the extra pass over the bucket.  gb_dec = the b_dec slice of the bucket. */
 int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
                                void* stream);
+
+/* ---- sharded optimizer for data parallelism (no counterpart in saev, which is single-GPU) ----
+ * After saev_b200_set_optimizer_shard(h, r0, r1) every saev_b200_adam_step updates only dictionary rows [r0, r1) of
+ * W_enc_t / W_dec (and their Adam moments, bf16 operand rows and row-norm maximum), plus both bias vectors in full.
+ * The caller reduce-scatters the two weight-gradient regions, all-reduces the bias gradients, takes the norm with
+ * saev_b200_grad_sumsq_ranges over what it owns (+ an all-reduce of that scalar), and all-gathers the updated rows,
+ * the bf16 operand (saev_b200_shadow_weights, [d_sae, d_model] bf16) and the row-norm maximum (MAX). */
+int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end);
+int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, int32_t n_ranges,
+                                const int64_t* host_begins, const int64_t* host_ends, float* sumsq_out,
+                                void* workspace, void* stream);
+void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace);
+float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace);
 
 /* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + bf16 operand refresh.
  *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)

@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 6
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -91,8 +91,14 @@ SIGNATURES = {
     "saev_b200_active_flags": (_p, [_p, _p]),
     "saev_b200_unsafe_rows": (_p, [_p, _p]),
     "saev_b200_backward": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "saev_b200_backward_stage": (
+        C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "saev_b200_grad_sumsq": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "saev_b200_grad_sumsq_local": (C.c_int, [_p, _p, _p, _p, _p]),
+    "saev_b200_set_optimizer_shard": (C.c_int, [_p, _i32, _i32]),
+    "saev_b200_grad_sumsq_ranges": (C.c_int, [_p, _p, _i32, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p]),
+    "saev_b200_shadow_weights": (_p, [_p, _p]),
+    "saev_b200_wnorm_scalar": (_p, [_p, _p]),
     "saev_b200_adam_step": (
         C.c_int,
         [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _p, _p],

@@ -40,7 +40,8 @@ struct saev_b200_handle {
   Workspace ws;
   bool last_forward_training = false;
   bool last_forward_tracked = false;
-  bool row_gsq_valid = false;  // the last backward left per-atom ||g||^2 partials in the workspace
+  bool row_gsq_valid = false;
+  int shard_begin = 0, shard_end = 0;  // optimizer shard (rows of the dictionary); end == 0 => all rows  // the last backward left per-atom ||g||^2 partials in the workspace
   mutable char err[512];
   // optional per-stage CUDA-event timing (saev_b200_profile_*)
   bool prof_on = false;
@@ -143,7 +144,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   w.block_totals = take(((S + 1023) / 1024) * 4);
   w.row_gsq = take(S * 4);
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
-  w.sumsq_partial = take(1024 * 8);
+  w.sumsq_partial = take(SUMSQ_MAX_RANGES * 1024 * 8);
   if (c.aux_kind == SAEV_B200_AUX_AUXK) {
     w.h_aux = take(B * static_cast<size_t>(aux_cap) * 4);
     w.mask_aux = take(B * static_cast<size_t>(aux_cap));
@@ -593,86 +594,194 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   return check_cuda(h, "forward");
 }
 
+}  // extern "C" (re-opened below)
+
+namespace {
+
+struct BwdCtx {
+  saev_b200_handle* h;
+  const float* x; int B; long long tokens_global;
+  const float* W_enc_t; const float* b_enc; const float* W_dec; const float* b_dec;
+  const int32_t* topk_idx; const float* topk_val; const float* resid;
+  float* gW_enc_t; float* gb_enc; float* gW_dec; float* gb_dec;
+  void* workspace; cudaStream_t s;
+};
+
+int bwd_csc(const BwdCtx& c) {
+  saev_b200_handle* h = c.h;
+  const Workspace& w = h->ws;
+  StageTimer tm(h, SAEV_B200_STAGE_CSC, c.s);
+  if (launch_csc_build(c.topk_idx, c.B, h->cfg.top_k, h->cfg.d_sae, at<int>(c.workspace, w.feat_count),
+                       at<int>(c.workspace, w.feat_off), at<int>(c.workspace, w.cursor), at<int>(c.workspace, w.entries),
+                       at<int>(c.workspace, w.block_totals), c.s))
+    return fail(h, 51, "backward: CSC build launch failed%s");
+  return 0;
+}
+
+int bwd_wgrad(const BwdCtx& c, int row_begin, int row_end, const long long* skip_toks) {
+  saev_b200_handle* h = c.h;
+  const Workspace& w = h->ws;
+  const int D = h->cfg.d_model;
+  WgradArgs g;
+  g.feat_off = at<int>(c.workspace, w.feat_off);
+  g.entries = at<int>(c.workspace, w.entries);
+  g.topk_val = c.topk_val;
+  g.dh = at<float>(c.workspace, w.dh);
+  g.resid = c.resid;
+  g.x = c.x;
+  g.W_dec = c.W_dec;
+  g.B = c.B;
+  g.D = D;
+  g.S = h->cfg.d_sae;
+  g.K = h->cfg.top_k;
+  g.grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * D));
+  g.remove_parallel = h->cfg.remove_parallel_grads;
+  g.gW_enc_t = c.gW_enc_t;
+  g.gb_enc = c.gb_enc;
+  g.gW_dec = c.gW_dec;
+  g.row_gsq = at<float>(c.workspace, w.row_gsq);
+  g.row_begin = row_begin;
+  g.row_end = row_end;
+  g.skip_toks = skip_toks;
+  g.skip_threshold = h->cfg.dead_threshold_tokens;
+  StageTimer tm(h, SAEV_B200_STAGE_WGRAD, c.s);
+  if (launch_wgrad(g, c.s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
+  return 0;
+}
+
+// gb_dec = grad_scale * sum_b resid, then the AuxK gradients (rows of the dead atoms, gb_dec += ...)
+int bwd_bias_aux(const BwdCtx& c) {
+  saev_b200_handle* h = c.h;
+  const saev_b200_cfg& cf = h->cfg;
+  const Workspace& w = h->ws;
+  const int D = cf.d_model;
+  const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * D));
+  StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, c.s);
+  if (launch_colsum(c.resid, c.B, D, grad_scale, 0, at<float>(c.workspace, w.colsum_partial), c.gb_dec, c.s))
+    return fail(h, 53, "backward: bias-gradient launch failed%s");
+  if (cf.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked) {
+    AuxArgs a;
+    a.x = c.x;
+    a.resid = c.resid;
+    a.W_enc_t = c.W_enc_t;
+    a.b_enc = c.b_enc;
+    a.W_dec = c.W_dec;
+    a.b_dec = c.b_dec;
+    a.dead_list = at<int>(c.workspace, w.dead_list);
+    a.n_dead = at<int>(c.workspace, w.scalars);
+    a.B = c.B;
+    a.D = D;
+    a.S = h->aux_cap;
+    a.k_aux = cf.k_aux;
+    a.alpha = cf.aux_alpha;
+    a.inv_bd = static_cast<float>(1.0 / (static_cast<double>(c.tokens_global) * D));
+    a.remove_parallel = cf.remove_parallel_grads;
+    a.h_aux = at<float>(c.workspace, w.h_aux);
+    a.mask_aux = at<unsigned char>(c.workspace, w.mask_aux);
+    a.r_aux = at<float>(c.workspace, w.r_aux);
+    a.row_sse_aux = at<float>(c.workspace, w.row_sse_aux);
+    a.aux_loss = at<float>(c.workspace, w.scalars) + 2;
+    a.gW_enc_t = c.gW_enc_t;
+    a.gb_enc = c.gb_enc;
+    a.gW_dec = c.gW_dec;
+    a.colsum_partial = at<float>(c.workspace, w.colsum_partial);
+    a.gb_dec = c.gb_dec;
+    a.aux_colpart = at<float>(c.workspace, w.aux_colpart);
+    a.row_gsq = cf.act_kind == SAEV_B200_ACT_TOPK ? at<float>(c.workspace, w.row_gsq) : nullptr;
+    if (launch_aux_backward(a, c.s)) return fail(h, 54, "backward: AuxK launch failed%s");
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t tokens_global,
                        const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
                        const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
                        float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const saev_b200_cfg& c = h->cfg;
-  const Workspace& w = h->ws;
   if (!h->last_forward_training) return fail(h, 50, "backward: the last forward was not a training forward%s");
   if (B <= 0 || B > c.max_batch) return fail(h, 40, "backward: B out of range%s");
   if (tokens_global <= 0) tokens_global = B;
-  const int D = c.d_model, S = c.d_sae, K = c.top_k;
-  const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+  const BwdCtx ctx{h, x, B, tokens_global, W_enc_t, b_enc, W_dec, b_dec, topk_idx, topk_val, resid,
+                   gW_enc_t, gb_enc, gW_dec, gb_dec, workspace, s};
   if (c.act_kind == SAEV_B200_ACT_RELU) {
     if (int rc = backward_relu(h, x, B, tokens_global, W_dec, gW_enc_t, gb_enc, gW_dec, workspace, s)) return rc;
   } else {
-  {
-    StageTimer tm(h, SAEV_B200_STAGE_CSC, s);
-    if (launch_csc_build(topk_idx, B, K, S, at<int>(workspace, w.feat_count), at<int>(workspace, w.feat_off),
-                         at<int>(workspace, w.cursor), at<int>(workspace, w.entries), at<int>(workspace, w.block_totals), s))
-      return fail(h, 51, "backward: CSC build launch failed%s");
+    if (int rc = bwd_csc(ctx)) return rc;
+    if (int rc = bwd_wgrad(ctx, 0, c.d_sae, nullptr)) return rc;
   }
-  WgradArgs g;
-  g.feat_off = at<int>(workspace, w.feat_off);
-  g.entries = at<int>(workspace, w.entries);
-  g.topk_val = topk_val;
-  g.dh = at<float>(workspace, w.dh);
-  g.resid = resid;
-  g.x = x;
-  g.W_dec = W_dec;
-  g.B = B;
-  g.D = D;
-  g.S = S;
-  g.K = K;
-  g.grad_scale = grad_scale;
-  g.remove_parallel = c.remove_parallel_grads;
-  g.gW_enc_t = gW_enc_t;
-  g.gb_enc = gb_enc;
-  g.gW_dec = gW_dec;
-  g.row_gsq = at<float>(workspace, w.row_gsq);
-  {
-    StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
-    if (launch_wgrad(g, s)) return fail(h, 52, "backward: weight-gradient launch failed%s");
-  }
-  }
-  StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, s);
-  if (launch_colsum(resid, B, D, grad_scale, 0, at<float>(workspace, w.colsum_partial), gb_dec, s))
-    return fail(h, 53, "backward: bias-gradient launch failed%s");
-  if (c.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked) {
-    AuxArgs a;
-    a.x = x;
-    a.resid = resid;
-    a.W_enc_t = W_enc_t;
-    a.b_enc = b_enc;
-    a.W_dec = W_dec;
-    a.b_dec = b_dec;
-    a.dead_list = at<int>(workspace, w.dead_list);
-    a.n_dead = at<int>(workspace, w.scalars);
-    a.B = B;
-    a.D = D;
-    a.S = h->aux_cap;
-    a.k_aux = c.k_aux;
-    a.alpha = c.aux_alpha;
-    a.inv_bd = static_cast<float>(1.0 / (static_cast<double>(tokens_global) * D));
-    a.remove_parallel = c.remove_parallel_grads;
-    a.h_aux = at<float>(workspace, w.h_aux);
-    a.mask_aux = at<unsigned char>(workspace, w.mask_aux);
-    a.r_aux = at<float>(workspace, w.r_aux);
-    a.row_sse_aux = at<float>(workspace, w.row_sse_aux);
-    a.aux_loss = at<float>(workspace, w.scalars) + 2;
-    a.gW_enc_t = gW_enc_t;
-    a.gb_enc = gb_enc;
-    a.gW_dec = gW_dec;
-    a.colsum_partial = at<float>(workspace, w.colsum_partial);
-    a.gb_dec = gb_dec;
-    a.aux_colpart = at<float>(workspace, w.aux_colpart);
-    a.row_gsq = c.act_kind == SAEV_B200_ACT_TOPK ? at<float>(workspace, w.row_gsq) : nullptr;
-    if (launch_aux_backward(a, s)) return fail(h, 54, "backward: AuxK launch failed%s");
-  }
+  if (int rc = bwd_bias_aux(ctx)) return rc;
   h->row_gsq_valid = c.act_kind == SAEV_B200_ACT_TOPK;
   return check_cuda(h, "backward");
+}
+
+/* Staged form of saev_b200_backward for overlapping the gradient exchange with the weight-gradient kernel (TopK
+ * path).  stage 0: per-atom lists + gb_dec + AuxK gradients (rows of the dead atoms); stage 1: the weight-gradient
+ * rows [row_begin, row_end) of every atom that is not dead -- so rows [r0, r1) of gW_enc_t / gW_dec are final once
+ * the stage-1 call covering them has run, and may be all-reduced while later rows are still being computed. */
+int saev_b200_backward_stage(saev_b200_handle* h, int32_t stage, int32_t row_begin, int32_t row_end, const float* x,
+                             int32_t B, int64_t tokens_global, const float* W_enc_t, const float* b_enc,
+                             const float* W_dec, const float* b_dec, const int64_t* toks_since_active,
+                             const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
+                             float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const saev_b200_cfg& c = h->cfg;
+  if (c.act_kind != SAEV_B200_ACT_TOPK) return fail(h, 55, "backward_stage: TopK path only%s");
+  if (!h->last_forward_training) return fail(h, 50, "backward_stage: the last forward was not a training forward%s");
+  if (B <= 0 || B > c.max_batch) return fail(h, 40, "backward_stage: B out of range%s");
+  if (tokens_global <= 0) tokens_global = B;
+  const BwdCtx ctx{h, x, B, tokens_global, W_enc_t, b_enc, W_dec, b_dec, topk_idx, topk_val, resid,
+                   gW_enc_t, gb_enc, gW_dec, gb_dec, workspace, s};
+  if (stage == 0) {
+    if (int rc = bwd_csc(ctx)) return rc;
+    if (int rc = bwd_bias_aux(ctx)) return rc;
+    h->row_gsq_valid = false;
+  } else if (stage == 1) {
+    if (row_begin < 0 || row_end > c.d_sae || row_begin > row_end) return fail(h, 55, "backward_stage: bad row range%s");
+    const bool aux_live = c.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked;
+    if (aux_live && toks_since_active == nullptr)
+      return fail(h, 55, "backward_stage: toks_since_active is needed to leave the AuxK rows alone%s");
+    if (int rc = bwd_wgrad(ctx, row_begin, row_end, aux_live ? reinterpret_cast<const long long*>(toks_since_active) : nullptr))
+      return rc;
+  } else {
+    return fail(h, 55, "backward_stage: stage must be 0 or 1%s");
+  }
+  return check_cuda(h, "backward_stage");
+}
+
+int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end) {
+  if (row_begin < 0 || row_end > h->cfg.d_sae || (row_end != 0 && row_begin >= row_end))
+    return fail(h, 64, "set_optimizer_shard: need 0 <= row_begin < row_end <= d_sae (or 0, 0 to reset)%s");
+  h->shard_begin = row_begin;
+  h->shard_end = row_end;
+  return 0;
+}
+
+int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, int32_t n_ranges, const int64_t* begins,
+                                const int64_t* ends, float* sumsq_out, void* workspace, void* stream) {
+  StageTimer tm(h, SAEV_B200_STAGE_SUMSQ, static_cast<cudaStream_t>(stream));
+  long long b[SUMSQ_MAX_RANGES], e[SUMSQ_MAX_RANGES];
+  if (n_ranges < 1 || n_ranges > SUMSQ_MAX_RANGES) return fail(h, 65, "grad_sumsq_ranges: 1..4 ranges%s");
+  for (int r = 0; r < n_ranges; ++r) {
+    if (begins[r] % 4 != 0 || ends[r] < begins[r]) return fail(h, 65, "grad_sumsq_ranges: begins must be multiples of 4%s");
+    b[r] = begins[r];
+    e[r] = ends[r];
+  }
+  if (launch_sumsq_ranges(grads_flat, n_ranges, b, e, at<double>(workspace, h->ws.sumsq_partial), sumsq_out,
+                          static_cast<cudaStream_t>(stream)))
+    return fail(h, 60, "grad_sumsq_ranges: launch failed%s");
+  return check_cuda(h, "grad_sumsq_ranges");
+}
+
+void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace) {
+  return at<char>(workspace, h->ws.shadow_hi);
+}
+float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace) {
+  return at<float>(workspace, h->ws.scalars) + 4;
 }
 
 int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
@@ -742,6 +851,10 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.gnorm_sq = sumsq;
   a.renorm_w_dec = renorm_w_dec;
   a.gnorm_out = gnorm_out;
+  const bool sharded = h->shard_end > 0;
+  a.row_begin = sharded ? h->shard_begin : 0;
+  a.row_end = sharded ? h->shard_end : static_cast<int>(S);
+  a.b_enc_separately = sharded ? 1 : 0;
   StageTimer tm(h, SAEV_B200_STAGE_ADAM, static_cast<cudaStream_t>(stream));
   if (launch_adam(a, static_cast<cudaStream_t>(stream))) return fail(h, 62, "adam_step: launch failed%s");
   return check_cuda(h, "adam_step");

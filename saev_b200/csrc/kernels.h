@@ -110,6 +110,9 @@ struct WgradArgs {
   float grad_scale; int remove_parallel;
   float* gW_enc_t; float* gb_enc; float* gW_dec;
   float* row_gsq;   // optional [S]: this atom's ||gW_enc_t[j]||^2 + ||gW_dec[j]||^2 + gb_enc[j]^2
+  int row_begin, row_end;              // atoms handled by this launch
+  const long long* skip_toks;          // optional: leave atoms with no entries and toks >= threshold untouched
+  long long skip_threshold;
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 
@@ -119,6 +122,11 @@ int launch_colsum(const float* src, int B, int D, float scale, int accumulate, f
 int colsum_partial_rows(int B);
 
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);
+constexpr int SUMSQ_MAX_RANGES = 4;
+// sum of squares over up to SUMSQ_MAX_RANGES sub-ranges [begin, end) (element offsets, begins multiples of 4) of g;
+// partial must hold SUMSQ_MAX_RANGES * 592 doubles
+int launch_sumsq_ranges(const float* g, int n_ranges, const long long* begins, const long long* ends, double* partial,
+                        float* out_sumsq, cudaStream_t s);
 int launch_sumsq_fused(const float* row_gsq, int S, const float* gb_dec, int D, float* out_sumsq, cudaStream_t s);
 
 struct AdamArgs {
@@ -132,6 +140,8 @@ struct AdamArgs {
   float max_norm; float grad_scale; const float* gnorm_sq;
   int renorm_w_dec;
   float* gnorm_out;            // optional: clipped-from norm (what clip_grad_norm_ returns)
+  int row_begin, row_end;      // dictionary rows this call updates (sharded optimizer; default all)
+  int b_enc_separately;        // 1: update the whole b_enc vector with a separate kernel (not only [row_begin, row_end))
 };
 int launch_adam(const AdamArgs& a, cudaStream_t s);
 

@@ -593,10 +593,12 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
 template <int VPL>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= a.S) return;
+  const int j = a.row_begin + blockIdx.x * 8 + warp;
+  if (j >= a.row_end) return;
   const int D4 = a.D >> 2;
   const int beg = a.feat_off[j], end = a.feat_off[j + 1];
+  // staged backward: the AuxK kernels have already written the rows of the dead atoms (which never fire)
+  if (a.skip_toks != nullptr && beg == end && a.skip_toks[j] >= a.skip_threshold) return;
   float4 gd[VPL], ge[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
@@ -686,7 +688,9 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
 
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
-  SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
+  const int rows = a.row_end - a.row_begin;
+  if (rows <= 0) return 0;
+  SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
@@ -787,6 +791,18 @@ int launch_sumsq_fused(const float* row_gsq, int S, const float* gb_dec, int D, 
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
+int launch_sumsq_ranges(const float* g, int n_ranges, const long long* begins, const long long* ends, double* partial,
+                        float* out_sumsq, cudaStream_t s) {
+  if (n_ranges < 1 || n_ranges > SUMSQ_MAX_RANGES) return 21;
+  for (int r = 0; r < n_ranges; ++r) {
+    sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g + begins[r], ends[r] - begins[r], partial + r * SUMSQ_BLOCKS);
+    ++g_launch_count;
+  }
+  sumsq_stage2<<<1, 32, 0, s>>>(partial, n_ranges * SUMSQ_BLOCKS, out_sumsq);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s) {
   sumsq_stage1<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, partial);
   ++g_launch_count;
@@ -838,8 +854,8 @@ __device__ __forceinline__ float4 adam_4(float4 p, float4 g, float4& m, float4& 
 template <int VPL>
 __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= a.S) return;
+  const int j = a.row_begin + blockIdx.x * 8 + warp;
+  if (j >= a.row_end) return;
   const AdamScalars sc = adam_scalars(a);
   const int D4 = a.D >> 2;
   const long long SD = static_cast<long long>(a.S) * a.D;
@@ -873,8 +889,8 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
       if (lane == 0) atomicMax(reinterpret_cast<int*>(a.wnorm_sq_max), __float_as_int(ssq));
     }
   }
-  // ---- b_enc[j] ----
-  if (lane == 0) {
+  // ---- b_enc[j] (a sharded optimizer updates the whole bias vector on every rank instead) ----
+  if (lane == 0 && !a.b_enc_separately) {
     float m = a.m[SD + j], v = a.v[SD + j];
     a.b_enc[j] = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
     a.m[SD + j] = m;
@@ -916,6 +932,18 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   }
 }
 
+// plain vector Adam over b_enc[S] (sharded optimizer: the bias gradients are all-reduced, not scattered)
+__global__ void adam_benc_kernel(AdamArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.S) return;
+  const AdamScalars sc = adam_scalars(a);
+  const long long o = static_cast<long long>(a.S) * a.D + j;
+  float m = a.m[o], v = a.v[o];
+  a.b_enc[j] = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+  a.m[o] = m;
+  a.v[o] = v;
+}
+
 __global__ void adam_bdec_kernel(AdamArgs a) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const AdamScalars sc = adam_scalars(a);
@@ -931,7 +959,12 @@ __global__ void adam_bdec_kernel(AdamArgs a) {
 int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
   if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
-  SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(a.S + 7) / 8, 256, 0, s>>>(a)));
+  const int rows = a.row_end - a.row_begin;
+  if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
+  if (a.b_enc_separately) {
+    adam_benc_kernel<<<(a.S + 255) / 256, 256, 0, s>>>(a);
+    ++g_launch_count;
+  }
   adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;

@@ -200,6 +200,22 @@ class Engine:
                 )
             )
 
+    def backward_stage(self, x: torch.Tensor, stage: int, row_begin: int = 0, row_end: int = 0, *,
+                       tokens_global: int = 0) -> None:
+        """Staged backward (see saev_b200_backward_stage): stage 0 once, then stage 1 over row ranges that together
+        cover [0, d_sae)."""
+        B = x.shape[0]
+        with torch.cuda.device(self.device):
+            self._ck(
+                self.lib.saev_b200_backward_stage(
+                    self.h, stage, row_begin, row_end, x.data_ptr(), B, tokens_global or B,
+                    self.W_enc_t.data_ptr(), self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.b_dec.data_ptr(),
+                    self.toks_since_active.data_ptr(), self.topk_idx.data_ptr(), self.topk_val.data_ptr(),
+                    self.resid.data_ptr(), self.gW_enc_t.data_ptr(), self.gb_enc.data_ptr(), self.gW_dec.data_ptr(),
+                    self.gb_dec.data_ptr(), self.workspace.data_ptr(), self._stream(),
+                )
+            )
+
     def grad_sumsq(self, *, local: bool = False) -> torch.Tensor:
         """||g||^2 of the gradient bucket.  `local=True`: the bucket still holds exactly what backward() wrote (single
         rank, no all-reduce in between) -> use the per-atom partials of the backward kernels (TopK path)."""
@@ -216,6 +232,30 @@ class Engine:
                 )
             )
         return self.sumsq
+
+    # ---- sharded optimizer (data parallel) -------------------------------------------------------
+    def set_optimizer_shard(self, row_begin: int, row_end: int) -> None:
+        """adam_step() then only updates dictionary rows [row_begin, row_end) (+ both bias vectors); see
+        include/saev_b200.h.  (0, 0) restores the full update."""
+        self._ck(self.lib.saev_b200_set_optimizer_shard(self.h, row_begin, row_end))
+
+    def grad_sumsq_ranges(self, ranges) -> torch.Tensor:
+        """||g||^2 over up to four [begin, end) element ranges of the flat gradient bucket."""
+        n = len(ranges)
+        b = (C.c_int64 * n)(*[r[0] for r in ranges])
+        e = (C.c_int64 * n)(*[r[1] for r in ranges])
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_grad_sumsq_ranges(self.h, self.grads.data_ptr(), n, b, e, self.sumsq.data_ptr(),
+                                                          self.workspace.data_ptr(), self._stream()))
+        return self.sumsq
+
+    def shadow_weights(self) -> torch.Tensor:
+        """The bf16 tensor-core operand copy of W_enc_t, [d_sae, d_model], inside the workspace."""
+        return self._ws_tensor(self.lib.saev_b200_shadow_weights, torch.bfloat16, self.S * self.D).view(self.S, self.D)
+
+    def wnorm_scalar(self) -> torch.Tensor:
+        """Device scalar max_j ||W_enc_t[j]||^2 the top-k screen derives its admission margin from."""
+        return self._ws_tensor(self.lib.saev_b200_wnorm_scalar, torch.float32, 1)
 
     def adam_step(self, lr: float, *, max_norm: float = 1.0, grad_scale: float = 1.0, betas=(0.9, 0.999),
                   eps: float = 1e-8, renorm_w_dec: bool = False) -> None:

@@ -1,11 +1,23 @@
-"""Data-parallel training step: one process per GPU, full parameter + Adam replica per rank, batch rows
-sharded across ranks, ONE gradient all-reduce per step (NCCL over NVLink) plus a 4*d_sae-byte MAX
-all-reduce of the activity flags so every rank keeps an identical dead-latent tracker.
+"""Data-parallel training step: one process per GPU, full parameter replica per rank, batch rows sharded across
+ranks, Adam state sharded by dictionary rows.
 
-saev itself has no multi-GPU path; the semantics implemented here are "N ranks x B rows
-behave exactly like one rank x (N*B) rows": every kernel divides by the GLOBAL batch (`tokens_global`), so
-per-rank gradients/loss partials simply add up, `remove_parallel_grads` is linear and is applied before the
-reduction, and the clip norm is taken on the reduced gradient.
+saev itself has no multi-GPU path; the semantics implemented here are "N ranks x B rows behave
+exactly like one rank x (N*B) rows": every kernel divides by the GLOBAL batch (`tokens_global`), so per-rank
+gradients / loss partials simply add up, `remove_parallel_grads` is linear and is applied before the reduction, and
+the clip norm is taken on the reduced gradient.
+
+Exchange per step (NCCL over NVLink):
+  * 4*d_sae bytes MAX all-reduce of the activity flags between forward phases A and B, so that every rank keeps an
+    identical dead-latent tracker;
+  * the gradient bucket, once, in one of two ways:
+      - default: all-reduce (sum), issued in `n_chunks` row chunks that OVERLAP the weight-gradient kernel: the
+        staged backward (saev_b200_backward_stage) finishes rows [r0, r1) of both weight gradients, their all-reduce
+        starts on NCCL's stream while the kernel for the next rows runs; only the last chunk and the two bias
+        vectors are exposed.  Every rank then runs the same norm / clip / Adam pass.
+      - `sharded=True` (d_sae divisible by the world size): the two weight-gradient regions are REDUCE-SCATTERED by
+        dictionary rows, each rank runs the norm / clip / Adam / renorm kernel on its S/N rows only (Adam moments
+        exist only for those rows), and the updated rows, their bf16 operand copy and the row-norm maximum are
+        ALL-GATHERED.  Same bytes on the wire, the 28 B/param optimizer pass shrinks by N, but nothing overlaps.
 """
 
 from __future__ import annotations
@@ -14,16 +26,36 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .engine import Engine
+from .engine import LOSS_KEYS, Engine
 
 
 class DataParallelTrainer:
-    def __init__(self, engine: Engine, group=None):
+    def __init__(self, engine: Engine, group=None, sharded: bool | None = None, n_chunks: int = 4):
         self.eng = engine
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self._w_dec_normalized = False
+        S = getattr(engine, "S", 0)
+        can_shard = (self.world > 1 and S > 0 and S % self.world == 0 and hasattr(engine, "set_optimizer_shard")
+                     and getattr(engine.cfg, "activation", "topk") == "topk")
+        self.sharded = bool(sharded) and can_shard
+        # row chunks of the overlapped all-reduce (multiples of 8 rows: one warp per row, 8 rows per block)
+        self.chunks = []
+        if (self.world > 1 and not self.sharded and n_chunks > 1 and hasattr(engine, "backward_stage")
+                and getattr(engine.cfg, "activation", "topk") == "topk"):
+            step_rows = -(-S // n_chunks)
+            step_rows = (step_rows + 7) // 8 * 8
+            self.chunks = [(r, min(S, r + step_rows)) for r in range(0, S, step_rows)]
+        if self.sharded:
+            rows = S // self.world
+            self.j0, self.j1 = self.rank * rows, (self.rank + 1) * rows
+            engine.set_optimizer_shard(self.j0, self.j1)
+            D = engine.D
+            SD = S * D
+            self._ranges = [(self.j0 * D, self.j1 * D), (SD + S + self.j0 * D, SD + S + self.j1 * D)]
+            if self.rank == 0:  # the (all-reduced) bias gradients are counted once
+                self._ranges += [(SD, SD + S), (2 * SD + S, 2 * SD + S + D)]
 
     def broadcast_params(self, src: int = 0) -> None:
         """Make every replica start from rank `src`'s parameters (model init is unseeded in saev)."""
@@ -35,7 +67,7 @@ class DataParallelTrainer:
     def step(self, x: torch.Tensor, lr: float, *, max_norm: float = 1.0, fused_renorm: bool = True) -> torch.Tensor:
         """One iteration of saev's loop body (train.py:332-460) on this rank's rows `x[B_local, D]`.
         Returns the device tensor of this rank's loss partials (see `global_losses`)."""
-        eng = self.eng
+        eng, g = self.eng, self.group
         tokens_global = x.shape[0] * self.world  # equal per-rank batches (the loader guarantees it)
         if not self._w_dec_normalized:
             eng.normalize_w_dec()
@@ -43,14 +75,44 @@ class DataParallelTrainer:
             eng.forward(x, training=True, tokens_global=tokens_global)
         else:
             eng.forward(x, training=True, phase=_lib.PHASE_A, tokens_global=tokens_global)
-            dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g)
             eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
-        eng.backward(x, tokens_global=tokens_global)
-        if self.world > 1:
-            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=self.group)
-        eng.grad_sumsq(local=self.world == 1)
         renorm = fused_renorm and eng.cfg.normalize_w_dec
-        eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
+        if self.chunks:
+            eng.backward_stage(x, 0, tokens_global=tokens_global)
+            works = []
+            for r0, r1 in self.chunks:
+                eng.backward_stage(x, 1, r0, r1, tokens_global=tokens_global)
+                works.append(dist.all_reduce(eng.gW_enc_t[r0:r1], op=dist.ReduceOp.SUM, group=g, async_op=True))
+                works.append(dist.all_reduce(eng.gW_dec[r0:r1], op=dist.ReduceOp.SUM, group=g, async_op=True))
+            works.append(dist.all_reduce(eng.gb_enc, op=dist.ReduceOp.SUM, group=g, async_op=True))
+            works.append(dist.all_reduce(eng.gb_dec, op=dist.ReduceOp.SUM, group=g, async_op=True))
+            for wk in works:
+                wk.wait()  # stream-level wait (NCCL): the norm / Adam kernels below see the reduced bucket
+            eng.grad_sumsq()
+            eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
+            self._w_dec_normalized = renorm
+            return eng.losses
+        eng.backward(x, tokens_global=tokens_global)
+        if not self.sharded:
+            if self.world > 1:
+                dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=g)
+            eng.grad_sumsq(local=self.world == 1)
+            eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
+        else:
+            j0, j1 = self.j0, self.j1
+            dist.reduce_scatter_tensor(eng.gW_enc_t[j0:j1], eng.gW_enc_t, op=dist.ReduceOp.SUM, group=g)
+            dist.reduce_scatter_tensor(eng.gW_dec[j0:j1], eng.gW_dec, op=dist.ReduceOp.SUM, group=g)
+            dist.all_reduce(eng.gb_enc, op=dist.ReduceOp.SUM, group=g)
+            dist.all_reduce(eng.gb_dec, op=dist.ReduceOp.SUM, group=g)
+            eng.grad_sumsq_ranges(self._ranges)
+            dist.all_reduce(eng.sumsq, op=dist.ReduceOp.SUM, group=g)
+            eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)  # rows [j0, j1) + both bias vectors
+            shadow = eng.shadow_weights()
+            dist.all_gather_into_tensor(shadow, shadow[j0:j1], group=g)
+            dist.all_reduce(eng.wnorm_scalar(), op=dist.ReduceOp.MAX, group=g)
+            dist.all_gather_into_tensor(eng.W_enc_t, eng.W_enc_t[j0:j1], group=g)
+            dist.all_gather_into_tensor(eng.W_dec, eng.W_dec[j0:j1], group=g)
         self._w_dec_normalized = renorm
         return eng.losses
 
@@ -63,6 +125,4 @@ class DataParallelTrainer:
             vals[5] = 0
             dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=self.group)
             vals[5] = n_dead  # identical on every rank, not additive
-        from .engine import LOSS_KEYS
-
         return dict(zip(LOSS_KEYS, vals.tolist()))

@@ -1,0 +1,67 @@
+"""Multi-GPU parity check, run under torchrun: N ranks x (B/N) rows through DataParallelTrainer (sharded optimizer and
+plain all-reduce) must give what ONE engine gives on the full B rows (the same kernels, global denominators).
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/gpu_dp_check.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import torch.distributed as dist
+
+from saev_b200.engine import Engine, EngineConfig
+from saev_b200.parallel import DataParallelTrainer
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+D, S, K, B = 256, 4096, 16, 512 * world
+cfg = EngineConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=64, dead_threshold_tokens=2 * B, max_batch=B)
+g = torch.Generator(device="cpu").manual_seed(0)
+basis = torch.randn(8, D, generator=g)
+xs = [(torch.randn(B, 8, generator=g) @ basis + 0.05 * torch.randn(B, D, generator=g)).to(dev) for _ in range(4)]
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30))
+
+
+ref = Engine(cfg, device=dev)
+ref.init_params(seed=7)
+lrs = [0.0, 5e-4, 1e-3, 1e-3]
+ref_losses = []
+for x, lr in zip(xs, lrs):
+    ref.train_step(x, lr, fused_renorm=True, pre_normalized=False)
+    ref_losses.append(ref.loss_dict())
+ok = True
+per = B // world
+for sharded, n_chunks in ((False, 4), (False, 1), (True, 1)):
+    eng = Engine(cfg, device=dev)
+    eng.init_params(seed=7)
+    tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks)
+    tr.broadcast_params(0)
+    assert tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1)
+    sharded = f"{sharded}/chunks={n_chunks}"
+    for i, (x, lr) in enumerate(zip(xs, lrs)):
+        tr.step(x[rank * per:(rank + 1) * per].contiguous(), lr, fused_renorm=True)
+        gl = tr.global_losses()
+        for k in ("mse", "aux", "l0", "loss"):
+            if abs(gl[k] - ref_losses[i][k]) > 2e-5 * max(abs(ref_losses[i][k]), 1e-6) + 1e-7:
+                ok = False
+                print(f"[rank {rank}] sharded={sharded} step {i} {k}: {gl[k]} vs {ref_losses[i][k]}")
+        if int(gl["n_dead"]) != int(ref_losses[i]["n_dead"]):
+            ok = False
+            print(f"[rank {rank}] sharded={sharded} step {i} n_dead {gl['n_dead']} vs {ref_losses[i]['n_dead']}")
+    errs = {n: rel(a, b) for n, a, b in (("W_enc_t", eng.W_enc_t, ref.W_enc_t), ("b_enc", eng.b_enc, ref.b_enc),
+                                         ("W_dec", eng.W_dec, ref.W_dec), ("b_dec", eng.b_dec, ref.b_dec))}
+    sh = rel(eng.shadow_weights().float(), ref.shadow_weights().float())
+    if max(errs.values()) > 2e-5 or sh > 1e-6 or eng.unsafe_rows() != 0:
+        ok = False
+    if rank == 0:
+        print(f"sharded={sharded}: param rel-L2 vs single-GPU {errs}, bf16 operand {sh:.2e}, n_dead(last)={ref_losses[-1]['n_dead']}")
+flag = torch.tensor([0 if ok else 1], device=dev)
+dist.all_reduce(flag)
+if rank == 0:
+    print("DP CHECK", "OK" if int(flag) == 0 else "FAILED")
+dist.destroy_process_group()
+sys.exit(0 if int(flag) == 0 else 1)

@@ -24,34 +24,62 @@ CFG = orc.OracleConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=8, dead_thre
 
 
 class OracleEngine:
-    """Engine look-alike (only what DataParallelTrainer touches); math from oracle/sae_oracle.py."""
+    """Engine look-alike (only what DataParallelTrainer touches) over flat parameter / gradient / moment buffers in the
+    engine's order [W_enc_t, b_enc, W_dec, b_dec]; forward / backward math from oracle/sae_oracle.py."""
 
     def __init__(self, W_enc, b_enc, W_dec, b_dec):
-        self.cfg = type("C", (), {"normalize_w_dec": True})()
-        self.st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
+        self.cfg = type("C", (), {"normalize_w_dec": True, "activation": "topk"})()
+        self.S, self.D = S, D
         self.n = 2 * S * D + S + D
-        self.params = torch.zeros(self.n)
-        self.grads = torch.zeros(self.n)
-        self.losses = torch.zeros(8)
-        self.sumsq = torch.zeros(1)
+        self.params, self.grads = torch.zeros(self.n), torch.zeros(self.n)
+        self.m, self.v = torch.zeros(self.n), torch.zeros(self.n)
+        self.W_enc_t, self.b_enc, self.W_dec, self.b_dec = self._views(self.params)
+        self.gW_enc_t, self.gb_enc, self.gW_dec, self.gb_dec = self._views(self.grads)
+        self.W_enc_t.copy_(W_enc.t()); self.b_enc.copy_(b_enc); self.W_dec.copy_(W_dec); self.b_dec.copy_(b_dec)
+        self.losses, self.sumsq = torch.zeros(8), torch.zeros(1)
         self._flags = torch.zeros(S, dtype=torch.int32)
         self.toks = torch.zeros(S, dtype=torch.int64)
+        self._shadow = torch.zeros(S, D, dtype=torch.bfloat16)
+        self._wnorm = torch.zeros(1)
+        self.shard = None
+        self.t = 0
         self.calls = []
+
+    def _views(self, flat):
+        o1, o2, o3 = S * D, S * D + S, 2 * S * D + S
+        return flat[:o1].view(S, D), flat[o1:o2], flat[o2:o3].view(S, D), flat[o3:]
+
+    def _state(self):
+        return orc.OracleState.from_params(self.W_enc_t.t(), self.b_enc, self.W_dec, self.b_dec)
 
     def active_flags(self):
         return self._flags
 
+    def shadow_weights(self):
+        return self._shadow
+
+    def wnorm_scalar(self):
+        return self._wnorm
+
     def sync_weights(self):
-        pass
+        self._shadow.copy_(self.W_enc_t.bfloat16())
+        self._wnorm[0] = self.W_enc_t.pow(2).sum(1).max()
+
+    def set_optimizer_shard(self, j0, j1):
+        self.shard = (j0, j1)
 
     def normalize_w_dec(self):
-        self.st.W_dec = orc.normalize_w_dec(self.st.W_dec)
+        self.W_dec.copy_(orc.normalize_w_dec(self.W_dec))
 
     def forward(self, x, *, training=True, phase=_lib.PHASE_ALL, tokens_global=0):
-        st, Bl = self.st, x.shape[0]
+        Bl = x.shape[0]
         tg = tokens_global or Bl
         if phase & _lib.PHASE_A:
             self.calls.append("A")
+            # the screen runs on the bf16 operand copy: it must be complete and current on every rank
+            assert torch.equal(self._shadow, self.W_enc_t.bfloat16()), "stale bf16 operand rows"
+            assert float(self._wnorm) == pytest.approx(float(self.W_enc_t.pow(2).sum(1).max()), rel=1e-6)
+            st = self._st = self._state()
             h = orc.encode_pre(x, st.W_enc, st.b_enc)
             f, mask = orc.topk_activation(h, K)
             x_hat = orc.decode(f, st.W_dec, st.b_dec)
@@ -59,7 +87,7 @@ class OracleEngine:
             self._flags.copy_((f.abs() > 0).any(0).to(torch.int32))
         if phase & _lib.PHASE_B:
             self.calls.append("B")
-            fw = self._fw
+            fw, st = self._fw, self._st
             self.toks = torch.where(self._flags > 0, torch.zeros_like(self.toks), self.toks + tg)
             dead = self.toks >= CFG.dead_threshold_tokens
             aux, fa, r_aux = orc.auxk(fw["h"], fw["r"], dead, st.W_dec, st.b_dec, CFG.k_aux, CFG.aux_alpha)
@@ -74,7 +102,7 @@ class OracleEngine:
 
     def backward(self, x, *, tokens_global=0):
         self.calls.append("bwd")
-        fw, st, Bl = self._fw, self.st, x.shape[0]
+        fw, st, Bl = self._fw, self._st, x.shape[0]
         out = orc.ForwardOut(fw["h"], fw["f"], fw["mask"], fw["x_hat"], fw["r"], None, None, None, None, None, 0,
                              fw["f_aux"], fw["mask_aux"], fw["r_aux"])
         g = orc.backward(CFG, st, x, out)
@@ -83,22 +111,47 @@ class OracleEngine:
         flat = torch.cat([g["W_enc"].t().reshape(-1), g["b_enc"], g["W_dec"].reshape(-1), g["b_dec"]]) * scale
         self.grads.copy_(flat)
 
+    def backward_stage(self, x, stage, row_begin=0, row_end=0, *, tokens_global=0):
+        """Staged backward: stage 0 = bias gradient (+ AuxK rows), stage 1 = weight-gradient rows [row_begin, row_end)."""
+        if stage == 0:
+            self.backward(x, tokens_global=tokens_global)
+            self.calls[-1] = "bwd0"
+            self._staged = self.grads.clone()
+            self.grads.fill_(float("nan"))  # anything a later stage forgets to produce poisons the result
+            self.gb_dec.copy_(self._views(self._staged)[3])
+        else:
+            self.calls.append("bwd1")
+            st = self._views(self._staged)
+            self.gW_enc_t[row_begin:row_end] = st[0][row_begin:row_end]
+            self.gb_enc[row_begin:row_end] = st[1][row_begin:row_end]
+            self.gW_dec[row_begin:row_end] = st[2][row_begin:row_end]
+
     def grad_sumsq(self, *, local=False):
         assert not local, "with more than one rank the norm must be taken on the all-reduced bucket"
         self.calls.append("sumsq")
         self.sumsq[0] = self.grads.double().pow(2).sum()
 
+    def grad_sumsq_ranges(self, ranges):
+        self.calls.append("sumsq")
+        self.sumsq[0] = sum(self.grads[b:e].double().pow(2).sum() for b, e in ranges)
+
     def adam_step(self, lr, *, max_norm=1.0, renorm_w_dec=False, **kw):
+        """torch Adam(fused) formulas (oracle.adam_step) on the rows of the shard + both bias vectors."""
         self.calls.append("adam")
-        st = self.st
-        o1, o2, o3 = S * D, S * D + S, 2 * S * D + S
-        g = dict(W_enc=self.grads[:o1].view(S, D).t(), b_enc=self.grads[o1:o2], W_dec=self.grads[o2:o3].view(S, D),
-                 b_dec=self.grads[o3:])
+        self.t += 1
+        j0, j1 = self.shard or (0, S)
         coef = min(1.0, max_norm / (float(self.sumsq.sqrt()) + 1e-6))
-        st.lr = lr
-        orc.adam_step(CFG, st, {k: v * coef for k, v in g.items()})
+        bc1, bc2s = 1.0 - CFG.beta1**self.t, (1.0 - CFG.beta2**self.t) ** 0.5
+        ps, gs, ms, vs = self._views(self.params), self._views(self.grads), self._views(self.m), self._views(self.v)
+        for i, rows in enumerate((slice(j0, j1), slice(None), slice(j0, j1), slice(None))):
+            p, g, m, v = ps[i][rows], gs[i][rows] * coef, ms[i][rows], vs[i][rows]
+            m.copy_(m + (g - m) * (1.0 - CFG.beta1))
+            v.copy_(v * CFG.beta2 + (1.0 - CFG.beta2) * g * g)
+            p.sub_((lr / bc1) * (m / (v.sqrt() / bc2s + CFG.eps)))
         if renorm_w_dec:
-            st.W_dec = orc.normalize_w_dec(st.W_dec)
+            self.W_dec[j0:j1] = orc.normalize_w_dec(self.W_dec[j0:j1])
+        self._shadow[j0:j1] = self.W_enc_t[j0:j1].bfloat16()
+        self._wnorm[0] = self.W_enc_t[j0:j1].pow(2).sum(1).max()
 
 
 def _data():
@@ -109,14 +162,14 @@ def _data():
     return params, xs
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, sharded, n_chunks):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         params, xs = _data()
         eng = OracleEngine(*params)
-        tr = DataParallelTrainer(eng)
-        assert tr.world == world and tr.rank == rank
+        tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks)
+        assert tr.world == world and tr.rank == rank and tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1)
         tr.broadcast_params(0)
         per = B // world
         rec = []
@@ -125,10 +178,15 @@ def _worker(rank, world, port, out_dir):
             tr.step(x[rank * per : (rank + 1) * per], lr, max_norm=CFG.grad_clip, fused_renorm=True)
             rec.append(tr.global_losses())
             lr = orc.warmup_cosine(step + 1, CFG.n_lr_warmup, CFG.lr, CFG.n_steps)
-        # phase A -> flags all-reduce -> phase B -> backward -> grads all-reduce -> norm -> Adam, every step
-        assert eng.calls == ["A", "B", "bwd", "sumsq", "adam"] * len(xs)
-        torch.save(dict(rec=rec, W_enc=eng.st.W_enc, W_dec=eng.st.W_dec, b_enc=eng.st.b_enc, b_dec=eng.st.b_dec,
-                        toks=eng.toks), os.path.join(out_dir, f"rank{rank}.pt"))
+        # phase A -> flags all-reduce -> phase B -> backward (-> grads exchange) -> norm -> Adam, every step
+        bwd = ["bwd0"] + ["bwd1"] * len(tr.chunks) if tr.chunks else ["bwd"]
+        assert eng.calls == (["A", "B"] + bwd + ["sumsq", "adam"]) * len(xs)
+        if sharded:  # Adam moments exist for the rank's own rows only
+            j0, j1 = eng.shard
+            mW = eng._views(eng.m)[0]
+            assert bool((mW[j0:j1] != 0).any()) and not bool((torch.cat([mW[:j0], mW[j1:]]) != 0).any())
+        torch.save(dict(rec=rec, W_enc=eng.W_enc_t.t().clone(), W_dec=eng.W_dec.clone(), b_enc=eng.b_enc.clone(),
+                        b_dec=eng.b_dec.clone(), toks=eng.toks), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -140,8 +198,10 @@ def _free_port():
 
 
 @pytest.mark.timeout(120)
-def test_two_ranks_equal_one_rank_on_the_full_batch(tmp_path):
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("sharded,n_chunks", [(False, 1), (False, 3), (True, 1)],
+                         ids=["allreduce", "chunked-overlapped-allreduce", "sharded-optimizer"])
+def test_two_ranks_equal_one_rank_on_the_full_batch(tmp_path, sharded, n_chunks):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), sharded, n_chunks), nprocs=2, join=True)
     r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))
     # single-process reference on the full batches
     params, xs = _data()

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 6
+#define SAEV_B200_ABI_VERSION 7
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -61,7 +61,7 @@ typedef struct saev_b200_cfg {
   int32_t remove_parallel_grads; /* SparseAutoencoderConfig              modeling.py:281 */
   int32_t max_batch;             /* largest B any call will pass */
   int32_t aux_cols_cap;          /* max dead latents AuxK scratch is sized for; 0 = d_sae */
-  int32_t reserved;
+  int32_t max_prefixes;          /* Matryoshka.n_prefixes the workspace is sized for (0/1 = single prefix)  objectives.py:22 */
 } saev_b200_cfg;
 
 typedef struct saev_b200_handle saev_b200_handle;
@@ -158,6 +158,15 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
 /* Lazy dense views for saev's logging block (train.py:365-442). */
 int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,
                       float* f_x_out /* [B, d_sae] */, void* stream);
+/* Matryoshka prefix cuts for the following forward/backward calls (saev samples them per step on the host,
+ * objectives.py:125,158-201): n strictly increasing column counts, the last one == d_sae.  n == 1 (or NULL) selects
+ * the plain single-prefix objective.  x_hat_i = b_dec + sum of the active columns below cut i; the MSE is the mean
+ * over batch x prefixes x d_model; AuxK and `resid` refer to the last (full) prefix. */
+int saev_b200_set_prefixes(saev_b200_handle* h, const int32_t* host_prefixes, int32_t n);
+/* x_hats[B, n_prefixes, d_model] of the last forward (modeling.py:406); n_prefixes == 1 reduces to saev_b200_x_hat. */
+int saev_b200_x_hats(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hats_out,
+                     void* workspace, void* stream);
+
 /* Same for either activation: TopK scatters (topk_idx, topk_val); ReLU joins the bf16 (hi, lo) pair the dense path
  * keeps in the workspace (f to ~2^-17 relative). */
 int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float* topk_val, int32_t B,

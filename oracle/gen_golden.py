@@ -42,7 +42,8 @@ def planted_batches(gen, n_steps, B, D, n_atoms, k_active, noise):
 
 
 def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sched_steps, grad_clip=1.0,
-             data="gauss", seed=0, save_grads_every=1, normalize=True, remove_parallel=True, b_enc_shift=0.0):
+             data="gauss", seed=0, save_grads_every=1, normalize=True, remove_parallel=True, b_enc_shift=0.0,
+             n_prefixes=1):
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed + 1)
     sae_cfg = M.SparseAutoencoderConfig(
@@ -50,7 +51,17 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
         normalize_w_dec=normalize, remove_parallel_grads=remove_parallel,
     )
     sae = saev.nn.SparseAutoencoder(sae_cfg)
-    objective = saev.nn.get_objective(O.Matryoshka(n_prefixes=1, dead_threshold_tokens=dead_thr))
+    objective = saev.nn.get_objective(O.Matryoshka(n_prefixes=n_prefixes, dead_threshold_tokens=dead_thr))
+    # record the prefix cuts the reference draws (torch.multinomial on the global RNG, objectives.py:125,189-191)
+    drawn = []
+    orig_sample = O.sample_prefixes
+
+    def recording_sample(*a, **k):
+        out = orig_sample(*a, **k)
+        drawn.append(out.clone().numpy())
+        return out
+
+    O.sample_prefixes = recording_sample
     if b_enc_shift != 0.0:  # push the upper half of the latents negative so that they die (ReLU case)
         with torch.no_grad():
             sae.b_enc[S // 2 :] = b_enc_shift
@@ -117,10 +128,13 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
     out["eval_l0"] = np.array(float(eloss.l0))
     out["eval_l1"] = np.array(float(eloss.l1))
     out["eval_x_hat"] = efwd.x_hats[:, -1, :].numpy()
+    O.sample_prefixes = orig_sample
+    out["prefixes"] = np.stack(drawn)  # [n_steps + 1 (eval), n_prefixes]
+    out["eval_x_hats_all"] = efwd.x_hats.numpy()
 
     meta = dict(D=D, S=S, B=B, n_steps=n_steps, dead_thr=dead_thr, lr=lr, n_warmup=n_warmup,
                 sched_steps=sched_steps, grad_clip=grad_clip, normalize=int(normalize),
-                remove_parallel=int(remove_parallel))
+                remove_parallel=int(remove_parallel), n_prefixes=n_prefixes, seed=seed)
     if isinstance(activation, M.TopK):
         meta.update(act=0, top_k=activation.top_k)
     else:
@@ -139,6 +153,16 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
 
 
 def main():
+    import sys
+
+    only = set(sys.argv[1:])
+    global run_case
+    _run = run_case
+
+    def run_case(name, **kw):  # `python oracle/gen_golden.py <name> ...` regenerates only the named cases
+        if not only or name in only:
+            _run(name, **kw)
+
     # (1) survey appendix-A case: AuxK live from step 3, clipping active.
     run_case("tiny_topk_auxk", D=32, S=256, B=64, n_steps=12,
              activation=M.TopK(top_k=8, aux=M.AuxK(k_aux=16, alpha=1 / 32)),
@@ -164,6 +188,15 @@ def main():
     run_case("c1_topk_auxk_live", D=128, S=512, B=256, n_steps=8,
              activation=M.TopK(top_k=16, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
              dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=8, data="planted", save_grads_every=7, seed=13)
+    # (7) the reference's DEFAULT objective family: Matryoshka with several random prefix cuts per step
+    #     (objectives.py:22,124-138; modeling.py:377-406), AuxK live, clipping active
+    run_case("tiny_topk_matryoshka", D=32, S=256, B=64, n_steps=10,
+             activation=M.TopK(top_k=8, aux=M.AuxK(k_aux=16, alpha=1 / 32)),
+             dead_thr=3 * 64, lr=1e-2, n_warmup=4, sched_steps=10, data="planted", seed=17, n_prefixes=5)
+    run_case("c1_topk_matryoshka", D=128, S=512, B=256, n_steps=6,
+             activation=M.TopK(top_k=16, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
+             dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=6, data="planted", save_grads_every=5, seed=19,
+             n_prefixes=10)
 
 
 if __name__ == "__main__":

@@ -135,6 +135,31 @@ def decode(f: Tensor, W_dec: Tensor, b_dec: Tensor) -> Tensor:
     return f @ W_dec + b_dec
 
 
+def decode_prefixes(f: Tensor, W_dec: Tensor, b_dec: Tensor, prefixes) -> Tensor:
+    """modeling.py:364-406 (Matryoshka): blocks [0,p1), [p1,p2), ...; block i contributes f[:, blk] @ W_dec[blk]
+    (+ b_dec on block 0); x_hats[:, i] = cumulative sum over blocks <= i.  Returns [B, P, D]."""
+    cuts = [0] + [int(c) for c in prefixes]
+    outs = []
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        o = f[:, a:b] @ W_dec[a:b]
+        outs.append(o + b_dec if i == 0 else o)
+    return torch.cumsum(torch.stack(outs, dim=-2), dim=-2)
+
+
+def sample_prefixes(d_sae: int, n_prefixes: int, min_prefix_length: int = 1, pareto_power: float = 0.5) -> Tensor:
+    """objectives.py:158-201: n_prefixes - 1 cut points drawn without replacement (torch.multinomial on the GLOBAL CPU
+    generator) from a Pareto-shaped distribution over 1..d_sae-1, plus d_sae itself, sorted ascending."""
+    if n_prefixes <= 1:
+        return torch.tensor([d_sae], dtype=torch.int64)
+    assert n_prefixes <= d_sae
+    lengths = torch.arange(1, d_sae)
+    cdf = 1 - ((min_prefix_length / lengths.float()) ** pareto_power)
+    pdf = torch.cat([cdf[:1], cdf[1:] - cdf[:-1]])
+    idx = torch.multinomial(pdf / pdf.sum(), num_samples=n_prefixes - 1, replacement=False)
+    out = torch.cat((lengths[idx].detach().clone(), torch.tensor([d_sae])))
+    return torch.sort(out, descending=False)[0].to(torch.int64)
+
+
 def mean_squared_err(x_hat: Tensor, x: Tensor) -> Tensor:
     """objectives.py:224-237 followed by .mean() (objectives.py:133-138):
     u = max|x| clamped at 1e-12; ((x_hat/u - x/u)^2) * u^2, mean over all elements."""
@@ -179,6 +204,8 @@ class ForwardOut:
     f_aux: Tensor | None
     mask_aux: Tensor | None
     r_aux: Tensor | None
+    x_hats: Tensor | None = None  # [B, P, D] when Matryoshka prefixes are in use
+    prefixes: list | None = None
 
     @property
     def loss(self) -> Tensor:
@@ -186,8 +213,9 @@ class ForwardOut:
         return self.mse + self.sparsity + self.aux
 
 
-def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True) -> ForwardOut:
-    """objectives.py:101-156 with Matryoshka(n_prefixes=1)."""
+def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True, prefixes=None) -> ForwardOut:
+    """objectives.py:101-156.  `prefixes` = the sorted cut points sample_prefixes() drew for this step (last one =
+    d_sae); None / a single cut is the Matryoshka(n_prefixes=1) case."""
     h = encode_pre(x, st.W_enc, st.b_enc)
     if cfg.activation == "topk":
         f, mask = topk_activation(h, cfg.top_k)
@@ -200,9 +228,18 @@ def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True
     if training:
         st.toks_since_active, dead = dead_tracker_update(st.toks_since_active, f, cfg.dead_threshold_tokens)
 
-    x_hat = decode(f, st.W_dec, st.b_dec)
-    r = x_hat - x
-    mse = mean_squared_err(x_hat, x)
+    x_hats = None
+    if prefixes is not None and len(prefixes) > 1:
+        prefixes = [int(c) for c in prefixes]
+        x_hats = decode_prefixes(f, st.W_dec, st.b_dec, prefixes)
+        x_hat = x_hats[:, -1, :]  # AuxK and the logged reconstruction use the last (full) prefix, modeling.py:96
+        r = x_hat - x
+        mse = mean_squared_err(x_hats, x[:, None, :].expand_as(x_hats))  # objectives.py:133-138
+    else:
+        prefixes = None
+        x_hat = decode(f, st.W_dec, st.b_dec)
+        r = x_hat - x
+        mse = mean_squared_err(x_hat, x)
 
     # modeling.py:30-31, 40-42
     l1 = f.abs().sum(dim=1).mean(dim=0)
@@ -217,7 +254,7 @@ def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True
         if cfg.aux:
             aux, fa, r_aux = auxk(h, r, dead, st.W_dec, st.b_dec, cfg.k_aux, cfg.aux_alpha)
     f_aux, mask_aux = fa if fa is not None else (None, None)
-    return ForwardOut(h, f, mask, x_hat, r, mse, sparsity, l0, l1, aux, n_dead, f_aux, mask_aux, r_aux)
+    return ForwardOut(h, f, mask, x_hat, r, mse, sparsity, l0, l1, aux, n_dead, f_aux, mask_aux, r_aux, x_hats, prefixes)
 
 
 # --------------------------------------------------------------------------------------
@@ -230,10 +267,24 @@ def backward(cfg: OracleConfig, st: OracleState, x: Tensor, out: ForwardOut) -> 
     dh = mask*(G W_dec^T) + mask_a*(G_a W_dec^T) (+ coeff*sign(f)/B on the active set for L1)
     gW_enc = x^T dh ; gb_enc = sum_b dh."""
     B, D = x.shape
-    G = out.r * (2.0 / (B * D))
-    gW_dec = out.f.T @ G
-    gb_dec = G.sum(dim=0)
-    df = G @ st.W_dec.T
+    if out.x_hats is not None:
+        # Matryoshka: loss_mse = mean over B*P*D of (x_hats - x)^2.  d/d x_hats[:, i] = G_i = 2 r_i / (B P D); column j
+        # (in block c(j)) feeds every prefix i >= c(j), so it sees the suffix sum Gs_c = sum_{i >= c} G_i.
+        P = out.x_hats.shape[1]
+        Gi = (out.x_hats - x[:, None, :]) * (2.0 / (B * P * D))
+        Gs = torch.flip(torch.cumsum(torch.flip(Gi, dims=[1]), dim=1), dims=[1])  # [B, P, D] suffix sums
+        cuts = [0] + out.prefixes
+        gW_dec = torch.zeros_like(st.W_dec)
+        df = torch.zeros_like(out.f)
+        for c, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+            gW_dec[a:b] = out.f[:, a:b].T @ Gs[:, c]
+            df[:, a:b] = Gs[:, c] @ st.W_dec[a:b].T
+        gb_dec = Gs[:, 0].sum(dim=0)
+    else:
+        G = out.r * (2.0 / (B * D))
+        gW_dec = out.f.T @ G
+        gb_dec = G.sum(dim=0)
+        df = G @ st.W_dec.T
     if cfg.l1_coeff != 0.0:
         df = df + (cfg.l1_coeff / B) * torch.sign(out.f)
     dh = out.mask * df
@@ -293,12 +344,12 @@ def warmup_cosine(step: int, n_warmup: int, peak: float, n_steps: int, init: flo
     return final
 
 
-def train_step(cfg: OracleConfig, st: OracleState, x: Tensor) -> dict:
+def train_step(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None) -> dict:
     """One iteration of train.py:332-460 (log block excluded).  Mutates `st`; returns scalars and,
     for parity tests, the clipped gradients."""
     if cfg.normalize_w_dec:
         st.W_dec = normalize_w_dec(st.W_dec)  # train.py:334-335
-    out = forward(cfg, st, x, training=True)  # train.py:341
+    out = forward(cfg, st, x, training=True, prefixes=prefixes)  # train.py:341
     grads = backward(cfg, st, x, out)  # train.py:348
     if cfg.remove_parallel_grads:
         grads["W_dec"] = remove_parallel_grads(grads["W_dec"], st.W_dec)  # train.py:352
@@ -312,6 +363,6 @@ def train_step(cfg: OracleConfig, st: OracleState, x: Tensor) -> dict:
     )
 
 
-def eval_forward(cfg: OracleConfig, st: OracleState, x: Tensor) -> ForwardOut:
+def eval_forward(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None) -> ForwardOut:
     """Objective in eval mode (train.py:526-527,559): no dead tracking, aux = 0."""
-    return forward(cfg, st, x, training=False)
+    return forward(cfg, st, x, training=False, prefixes=prefixes)

@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -36,7 +36,7 @@ class Cfg(C.Structure):
         ("remove_parallel_grads", C.c_int32),
         ("max_batch", C.c_int32),
         ("aux_cols_cap", C.c_int32),
-        ("reserved", C.c_int32),
+        ("max_prefixes", C.c_int32),
     ]
 
 
@@ -106,6 +106,8 @@ SIGNATURES = {
     "saev_b200_densify": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_dense_f": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "saev_b200_x_hat": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
+    "saev_b200_set_prefixes": (C.c_int, [_p, C.POINTER(_i32), _i32]),
+    "saev_b200_x_hats": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "saev_b200_profile_enable": (C.c_int, [_p, _i32]),
     "saev_b200_profile_read": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

@@ -23,6 +23,7 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
+  size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // dense (ReLU) path: bf16 (hi, lo) operand pairs
   size_t w_enc_lo, w_dec_hi, w_dec_lo, w_decT_hi, w_decT_lo, x_lo, xT_hi, xT_lo, g_hi, g_lo, gT_hi, gT_lo, f_hi, f_lo,
       fT_hi, fT_lo, dhT_hi, dhT_lo;
@@ -41,7 +42,10 @@ struct saev_b200_handle {
   bool last_forward_training = false;
   bool last_forward_tracked = false;
   bool row_gsq_valid = false;
-  int shard_begin = 0, shard_end = 0;  // optimizer shard (rows of the dictionary); end == 0 => all rows  // the last backward left per-atom ||g||^2 partials in the workspace
+  int shard_begin = 0, shard_end = 0;  // optimizer shard (rows of the dictionary); end == 0 => all rows
+  int max_prefixes = 1;                // Matryoshka: most prefix cuts a step may use (cfg.max_prefixes)
+  PrefixCuts pf;                       // cuts of the current step (pf.n == 1: plain single-prefix objective)
+  PrefixCuts pf_fwd;                   // cuts the last forward used (what backward must use)  // the last backward left per-atom ||g||^2 partials in the workspace
   mutable char err[512];
   // optional per-stage CUDA-event timing (saev_b200_profile_*)
   bool prof_on = false;
@@ -141,6 +145,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
   w.dead_list = take(S * 4);
   w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] re-scored candidates (uint)
                          // [4] max_j ||W_enc_t[j]||^2 [5] merged list entries (uint)
+  w.sfx = take(c.max_prefixes > 1 ? B * static_cast<size_t>(c.max_prefixes) * D * 4 : 0);
   w.block_totals = take(((S + 1023) / 1024) * 4);
   w.row_gsq = take(S * 4);
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
@@ -343,6 +348,19 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   saev_b200_handle* h = new (std::nothrow) saev_b200_handle();
   if (!h) return fail(nullptr, 5, "saev_b200_create: out of host memory%s");
   h->cfg = *cfg;
+  if (h->cfg.max_prefixes < 1) h->cfg.max_prefixes = 1;
+  if (h->cfg.max_prefixes > MAX_PREFIXES) {
+    delete h;
+    return fail(nullptr, 2, "saev_b200_create: max_prefixes must be <= 32%s");
+  }
+  if (h->cfg.max_prefixes > 1 && (cfg->act_kind != SAEV_B200_ACT_TOPK || cfg->top_k > 64)) {
+    delete h;
+    return fail(nullptr, 3, "saev_b200_create: Matryoshka prefixes need the TopK path with top_k <= 64%s");
+  }
+  h->max_prefixes = h->cfg.max_prefixes;
+  h->pf.n = 1;
+  h->pf.cut[0] = cfg->d_sae;
+  h->pf_fwd = h->pf;
   h->device = dev;
   h->num_sms = sms;
   h->aux_cap = (cfg->aux_cols_cap > 0 && cfg->aux_cols_cap < cfg->d_sae) ? cfg->aux_cols_cap : cfg->d_sae;
@@ -519,7 +537,9 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     d.B = B;
     d.D = D;
     d.K = K;
-    d.grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
+    const int P = h->pf.n;
+    h->pf_fwd = h->pf;
+    d.grad_scale = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * P * D));
     d.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
     d.resid = resid;
     d.dh = training ? at<float>(workspace, w.dh) : nullptr;
@@ -528,7 +548,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     d.row_l0 = at<float>(workspace, w.row_l0);
     {
       StageTimer tm(h, SAEV_B200_STAGE_DECODE, s);
-      if (launch_decode(d, s)) return fail(h, 44, "forward: decode launch failed%s");
+      if (P > 1 ? launch_decode_prefix(d, h->pf, at<float>(workspace, w.sfx), s) : launch_decode(d, s))
+        return fail(h, 44, "forward: decode launch failed%s");
     }
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
@@ -583,7 +604,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     f.B = B;
     f.D = D;
     // per-rank partial means compose: each rank divides by the GLOBAL batch
-    f.inv_bd = 1.0 / (static_cast<double>(tokens_global) * D);
+    f.inv_bd = 1.0 / (static_cast<double>(tokens_global) * h->pf_fwd.n * D);  // mean over B * P * D (objectives.py:133-138)
     f.inv_b = 1.0 / static_cast<double>(tokens_global);
     f.l1_coeff = c.l1_coeff;
     f.aux_loss = aux_live ? aux_loss : nullptr;
@@ -634,7 +655,9 @@ int bwd_wgrad(const BwdCtx& c, int row_begin, int row_end, const long long* skip
   g.D = D;
   g.S = h->cfg.d_sae;
   g.K = h->cfg.top_k;
-  g.grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * D));
+  g.grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * h->pf_fwd.n * D));
+  g.sfx = h->pf_fwd.n > 1 ? at<float>(c.workspace, w.sfx) : nullptr;
+  g.pf = h->pf_fwd;
   g.remove_parallel = h->cfg.remove_parallel_grads;
   g.gW_enc_t = c.gW_enc_t;
   g.gb_enc = c.gb_enc;
@@ -655,9 +678,12 @@ int bwd_bias_aux(const BwdCtx& c) {
   const saev_b200_cfg& cf = h->cfg;
   const Workspace& w = h->ws;
   const int D = cf.d_model;
-  const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * D));
+  const int P = cf.act_kind == SAEV_B200_ACT_TOPK ? h->pf_fwd.n : 1;
+  const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * P * D));
   StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, c.s);
-  if (launch_colsum(c.resid, c.B, D, grad_scale, 0, at<float>(c.workspace, w.colsum_partial), c.gb_dec, c.s))
+  // gb_dec = sum_b sum_i G_i: with prefixes that is the column sum of the block-0 suffix sums
+  if (launch_colsum(P > 1 ? at<float>(c.workspace, w.sfx) : c.resid, c.B, D, grad_scale, 0,
+                    at<float>(c.workspace, w.colsum_partial), c.gb_dec, c.s, P > 1 ? static_cast<long long>(P) * D : 0))
     return fail(h, 53, "backward: bias-gradient launch failed%s");
   if (cf.aux_kind == SAEV_B200_AUX_AUXK && h->last_forward_tracked) {
     AuxArgs a;
@@ -878,6 +904,35 @@ int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float*
     return check_cuda(h, "dense_f");
   }
   return saev_b200_densify(h, topk_idx, topk_val, B, f_x_out, stream);
+}
+
+int saev_b200_set_prefixes(saev_b200_handle* h, const int32_t* host_prefixes, int32_t n) {
+  if (n < 1 || n > h->max_prefixes) return fail(h, 72, "set_prefixes: 1 <= n <= cfg.max_prefixes%s");
+  if (host_prefixes == nullptr) {
+    if (n != 1) return fail(h, 72, "set_prefixes: null prefixes%s");
+    h->pf.n = 1;
+    h->pf.cut[0] = h->cfg.d_sae;
+    return 0;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (host_prefixes[i] < 1 || (i > 0 && host_prefixes[i] <= host_prefixes[i - 1]))
+      return fail(h, 72, "set_prefixes: cuts must be strictly increasing and >= 1 (modeling.py:372-373)%s");
+    h->pf.cut[i] = host_prefixes[i];
+  }
+  if (host_prefixes[n - 1] != h->cfg.d_sae) return fail(h, 72, "set_prefixes: the last cut must be d_sae%s");
+  h->pf.n = n;
+  return 0;
+}
+
+int saev_b200_x_hats(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hats_out,
+                     void* workspace, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int P = h->cfg.act_kind == SAEV_B200_ACT_TOPK ? h->pf_fwd.n : 1;
+  if (P <= 1) return saev_b200_x_hat(h, resid, x, B, x_hats_out, stream);
+  if (!workspace) return fail(h, 71, "x_hats: workspace needed%s");
+  if (launch_x_hats_prefix(at<float>(workspace, h->ws.sfx), x, B, h->cfg.d_model, P, x_hats_out, s))
+    return fail(h, 71, "x_hats: launch failed%s");
+  return check_cuda(h, "x_hats");
 }
 
 int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hat_out,

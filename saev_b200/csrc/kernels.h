@@ -100,6 +100,19 @@ struct DecodeArgs {
 };
 int launch_decode(const DecodeArgs& a, cudaStream_t s);
 
+// Matryoshka prefix cuts of one step (saev objectives.py:158-201; modeling.py:364-406): sorted, cut[n - 1] == d_sae.
+constexpr int MAX_PREFIXES = 32;
+struct PrefixCuts {
+  int n;
+  int cut[MAX_PREFIXES];
+};
+// Decode with prefixes: x_hat_i = b_dec + sum over the active columns below cut[i]; r_i = x_hat_i - x.
+// Writes resid = r_{n-1}, sfx[b, c, :] = sum_{i >= c} r_i (what column block c sees in the backward pass),
+// row_sse[b] = sum_i ||r_i||^2, and dh (scaled by a.grad_scale = 2 / (B_global * n * D)).
+int launch_decode_prefix(const DecodeArgs& a, const PrefixCuts& pf, float* sfx, cudaStream_t s);
+// x_hats[b, i, :] = x[b, :] + r_i = x + sfx[b, i] - sfx[b, i + 1]
+int launch_x_hats_prefix(const float* sfx, const float* x, int B, int D, int P, float* out, cudaStream_t s);
+
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
                      int* entries, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s);
 
@@ -110,6 +123,8 @@ struct WgradArgs {
   float grad_scale; int remove_parallel;
   float* gW_enc_t; float* gb_enc; float* gW_dec;
   float* row_gsq;   // optional [S]: this atom's ||gW_enc_t[j]||^2 + ||gW_dec[j]||^2 + gb_enc[j]^2
+  const float* sfx;                    // Matryoshka: [B, pf.n, D] suffix sums of residuals (null: single prefix)
+  PrefixCuts pf;
   int row_begin, row_end;              // atoms handled by this launch
   const long long* skip_toks;          // optional: leave atoms with no entries and toks >= threshold untouched
   long long skip_threshold;
@@ -118,7 +133,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 
 // gb_dec[d] (+)= scale * sum_b src[b, d]
 int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
-                  cudaStream_t s);
+                  cudaStream_t s, long long row_stride = 0 /* elements between rows of src; 0 = D */);
 int colsum_partial_rows(int B);
 
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);

@@ -482,6 +482,198 @@ int launch_decode(const DecodeArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Matryoshka decode (saev modeling.py:364-406, objectives.py:124-138): the active columns of a row are walked in
+// ascending column order; whenever the walk crosses a prefix cut the running reconstruction is that prefix's x_hat.
+// One warp per row; K <= 64 (two top-k slots per lane).
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, PrefixCuts pf, float* __restrict__ sfx) {
+  __shared__ int order_s[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= a.B) return;
+  const int D4 = a.D >> 2, K = a.K, P = pf.n;
+  const long long kb = static_cast<long long>(b) * K;
+  // this lane's (up to) two slots
+  int mj[2];
+  float mf[2];
+  float l1 = 0.f, l0 = 0.f;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int kk = lane + 32 * u;
+    mj[u] = (kk < K) ? a.topk_idx[kb + kk] : -1;
+    mf[u] = (kk < K) ? a.topk_val[kb + kk] : 0.f;
+    if (mj[u] >= 0) {
+      l1 += fabsf(mf[u]);
+      l0 += (mf[u] != 0.f) ? 1.f : 0.f;
+    }
+  }
+  // rank of every slot by column (empty slots last, ties among them by slot)
+  int* order = order_s[warp];
+  {
+    int rank[2] = {0, 0};
+    const unsigned int key0 = mj[0] < 0 ? 0x7fffffffu : static_cast<unsigned int>(mj[0]);
+    const unsigned int key1 = mj[1] < 0 ? 0x7fffffffu : static_cast<unsigned int>(mj[1]);
+    for (int t = 0; t < K; ++t) {
+      const int src = t & 31;
+      const unsigned int k0 = __shfl_sync(FULL, key0, src), k1 = __shfl_sync(FULL, key1, src);
+      const unsigned int kt = (t < 32) ? k0 : k1;
+      rank[0] += (kt < key0) || (kt == key0 && t < lane);
+      rank[1] += (kt < key1) || (kt == key1 && t < lane + 32);
+    }
+    if (lane < K) order[rank[0]] = lane;
+    if (lane + 32 < K) order[rank[1]] = lane + 32;
+  }
+  __syncwarp();
+
+  float4 acc[VPL], xr[VPL];
+  const float* xrow = a.x + static_cast<long long>(b) * a.D;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    acc[i] = (v < D4) ? ldg4(a.b_dec + 4 * v) : make_float4(0, 0, 0, 0);
+    xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
+  }
+  float* srow = sfx + static_cast<long long>(b) * P * a.D;
+  float sse = 0.f;
+  auto emit = [&](int c) {  // r_c = running x_hat - x
+    float* o = srow + static_cast<long long>(c) * a.D;
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) {
+        float4 r = acc[i];
+        r.x -= xr[i].x; r.y -= xr[i].y; r.z -= xr[i].z; r.w -= xr[i].w;
+        *reinterpret_cast<float4*>(o + 4 * v) = r;
+        part += dot4(r, r);
+      }
+    }
+    sse += part;
+  };
+  int cur = 0;
+  for (int t = 0; t < K; ++t) {
+    const int k = order[t];
+    const int j0 = __shfl_sync(FULL, mj[0], k & 31), j1 = __shfl_sync(FULL, mj[1], k & 31);
+    const float f0 = __shfl_sync(FULL, mf[0], k & 31), f1 = __shfl_sync(FULL, mf[1], k & 31);
+    const int j = (k < 32) ? j0 : j1;
+    const float f = (k < 32) ? f0 : f1;
+    if (j < 0) break;  // empty slots sort last
+    while (cur < P - 1 && j >= pf.cut[cur]) {
+      emit(cur);
+      ++cur;
+    }
+    const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) fma4(acc[i], f, ldg4(wrow + 4 * v));
+    }
+  }
+  while (cur < P) {
+    emit(cur);
+    ++cur;
+  }
+  // last prefix = the full reconstruction: residual for AuxK / logging
+  {
+    float* rrow = a.resid + static_cast<long long>(b) * a.D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) {
+        float4 r = acc[i];
+        r.x -= xr[i].x; r.y -= xr[i].y; r.z -= xr[i].z; r.w -= xr[i].w;
+        *reinterpret_cast<float4*>(rrow + 4 * v) = r;
+      }
+    }
+  }
+  sse = warp_sum(sse);
+  l1 = warp_sum(l1);
+  l0 = warp_sum(l0);
+  if (lane == 0) {
+    a.row_sse[b] = sse;
+    a.row_l1[b] = l1;
+    a.row_l0[b] = l0;
+  }
+  // suffix sums in place: sfx[c] = sum_{i >= c} r_i   (each lane re-reads only what it wrote itself)
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) acc[i] = make_float4(0, 0, 0, 0);
+  for (int c = P - 1; c >= 0; --c) {
+    float* o = srow + static_cast<long long>(c) * a.D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < D4) {
+        const float4 r = *reinterpret_cast<const float4*>(o + 4 * v);
+        acc[i].x += r.x; acc[i].y += r.y; acc[i].z += r.z; acc[i].w += r.w;
+        *reinterpret_cast<float4*>(o + 4 * v) = acc[i];
+      }
+    }
+  }
+  if (a.dh == nullptr) return;
+  // dh_k = grad_scale * <sfx[c(j_k)], W_dec[j_k]>  (acc holds sfx[0] now; reload when the block changes)
+  cur = 0;
+  for (int t = 0; t < K; ++t) {
+    const int k = order[t];
+    const int j0 = __shfl_sync(FULL, mj[0], k & 31), j1 = __shfl_sync(FULL, mj[1], k & 31);
+    const float f0 = __shfl_sync(FULL, mf[0], k & 31), f1 = __shfl_sync(FULL, mf[1], k & 31);
+    const int j = (k < 32) ? j0 : j1;
+    const float f = (k < 32) ? f0 : f1;
+    float d = 0.f;
+    if (j >= 0) {
+      int c = cur;
+      while (c < P - 1 && j >= pf.cut[c]) ++c;
+      if (c != cur) {
+        cur = c;
+        const float* o = srow + static_cast<long long>(c) * a.D;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < D4) acc[i] = *reinterpret_cast<const float4*>(o + 4 * v);
+        }
+      }
+      const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < D4) p += dot4(acc[i], ldg4(wrow + 4 * v));
+      }
+      p = warp_sum(p);
+      d = a.grad_scale * p;
+      if (a.l1_over_b != 0.f) d += a.l1_over_b * ((f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f));
+    }
+    if (lane == 0) a.dh[kb + k] = d;
+  }
+}
+
+int launch_decode_prefix(const DecodeArgs& a, const PrefixCuts& pf, float* sfx, cudaStream_t s) {
+  if (a.D % 4) return 21;
+  if (a.K > 64 || pf.n < 1 || pf.n > MAX_PREFIXES) return 24;
+  SB_DISPATCH_VPL(a.D, (decode_prefix_kernel<VPL><<<(a.B + 7) / 8, 256, 0, s>>>(a, pf, sfx)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+__global__ void x_hats_prefix_kernel(const float* __restrict__ sfx, const float* __restrict__ x, int B, int D, int P,
+                                     float* __restrict__ out) {
+  const long long n = static_cast<long long>(B) * P * D;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int d = static_cast<int>(i % D);
+    const long long bp = i / D;
+    const int c = static_cast<int>(bp % P);
+    const long long b = bp / P;
+    const float nxt = (c + 1 < P) ? sfx[i + D] : 0.f;
+    out[i] = x[b * D + d] + sfx[i] - nxt;
+  }
+}
+int launch_x_hats_prefix(const float* sfx, const float* x, int B, int D, int P, float* out, cudaStream_t s) {
+  x_hats_prefix_kernel<<<148 * 8, 256, 0, s>>>(sfx, x, B, D, P, out);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CSC of the active set: for every dictionary atom j the list of (b, k) slots where it fired.
 // ------------------------------------------------------------------------------------------------
 // Two-level exclusive scan of the per-atom counts (1024 atoms per block): block totals first, then every block
@@ -603,6 +795,15 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
 #pragma unroll
   for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
   float sdh = 0.f;
+  // Matryoshka: column j sits in prefix block c(j) and sees the suffix sum of the residuals of prefixes >= c(j)
+  const float* rbase = a.resid;
+  long long rstride = a.D;
+  if (a.sfx != nullptr) {
+    int c = 0;
+    while (c < a.pf.n - 1 && j >= a.pf.cut[c]) ++c;
+    rbase = a.sfx + static_cast<long long>(c) * a.D;
+    rstride = static_cast<long long>(a.pf.n) * a.D;
+  }
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     int mb = 0;
@@ -620,7 +821,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
       const int bb = __shfl_sync(FULL, mb, t);
       const float f = __shfl_sync(FULL, mf, t);
       const float d = __shfl_sync(FULL, md, t);
-      const float* rrow = a.resid + static_cast<long long>(bb) * a.D;
+      const float* rrow = rbase + static_cast<long long>(bb) * rstride;
       const float* xrow = a.x + static_cast<long long>(bb) * a.D;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
@@ -700,13 +901,13 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
 constexpr int COLSUM_ROWS_PER_BLOCK = 64;
 int colsum_partial_rows(int B) { return (B + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK; }
 
-__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ src, int B, int D,
+__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ src, int B, int D, long long row_stride,
                                                      float* __restrict__ partial) {
   const int r0 = blockIdx.x * COLSUM_ROWS_PER_BLOCK;
   const int r1 = min(B, r0 + COLSUM_ROWS_PER_BLOCK);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += __ldg(src + static_cast<long long>(r) * D + d);
+    for (int r = r0; r < r1; ++r) s += __ldg(src + static_cast<long long>(r) * row_stride + d);
     partial[static_cast<long long>(blockIdx.x) * D + d] = s;
   }
 }
@@ -721,9 +922,9 @@ __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ p
 }
 
 int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
-                  cudaStream_t s) {
+                  cudaStream_t s, long long row_stride) {
   const int P = colsum_partial_rows(B);
-  colsum_stage1<<<P, 256, 0, s>>>(src, B, D, partial);
+  colsum_stage1<<<P, 256, 0, s>>>(src, B, D, row_stride > 0 ? row_stride : D, partial);
   ++g_launch_count;
   colsum_stage2<<<(D + 255) / 256, 256, 0, s>>>(partial, P, D, scale, accumulate, out);
   ++g_launch_count;

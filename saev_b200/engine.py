@@ -36,6 +36,7 @@ class EngineConfig:
     normalize_w_dec: bool = True
     max_batch: int = 16384
     aux_cols_cap: int = 0
+    max_prefixes: int = 1  # Matryoshka.n_prefixes the workspace is sized for
 
 
 LOSS_KEYS = ("mse", "aux", "sparsity", "l0", "l1", "n_dead", "loss")
@@ -67,7 +68,7 @@ class Engine:
                 remove_parallel_grads=int(cfg.remove_parallel_grads),
                 max_batch=cfg.max_batch,
                 aux_cols_cap=cfg.aux_cols_cap,
-                reserved=0,
+                max_prefixes=cfg.max_prefixes,
             )
             h = C.c_void_p()
             _lib.check(self.lib.saev_b200_create(C.byref(c), C.byref(h)))
@@ -292,6 +293,25 @@ class Engine:
                     self.workspace.data_ptr(), self._stream()
                 )
             )
+        return out
+
+    def set_prefixes(self, prefixes=None) -> None:
+        """Matryoshka cut points for the following forward/backward calls (sorted, last == d_sae); None = single prefix."""
+        if prefixes is None or len(prefixes) <= 1:
+            self._ck(self.lib.saev_b200_set_prefixes(self.h, None, 1))
+            self._n_prefixes = 1
+            return
+        arr = (C.c_int32 * len(prefixes))(*[int(c) for c in prefixes])
+        self._ck(self.lib.saev_b200_set_prefixes(self.h, arr, len(prefixes)))
+        self._n_prefixes = len(prefixes)
+
+    def x_hats(self, x: torch.Tensor) -> torch.Tensor:
+        """[B, n_prefixes, d_model] reconstructions of the last forward (modeling.py:406)."""
+        B, P = x.shape[0], getattr(self, "_n_prefixes", 1)
+        out = torch.empty(B, P, self.D, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_x_hats(self.h, self.resid.data_ptr(), x.data_ptr(), B, out.data_ptr(),
+                                               self.workspace.data_ptr(), self._stream()))
         return out
 
     def x_hat(self, x: torch.Tensor) -> torch.Tensor:

@@ -22,8 +22,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     are unchanged, checkpoints interoperate with saev.nn.load / saev.nn.dump).
   * `Output.h_x`, `Output.f_x`, `Output.x_hats` are materialised lazily (the fused path never writes the
     [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
-  * Matryoshka n_prefixes > 1 and BatchTopK have no CUDA path in this build and raise NotImplementedError at
-    forward time.  Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05).
+  * BatchTopK, and Matryoshka n_prefixes > 1 combined with Relu, have no CUDA path in this build and raise
+    NotImplementedError at forward time (TopK + Matryoshka prefixes is supported).  Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05).
 """
 
 from __future__ import annotations
@@ -124,6 +124,23 @@ def _kind(obj) -> str:
     return type(obj).__name__
 
 
+def sample_prefixes(d_sae: int, n_prefixes: int, min_prefix_length: int = 1, pareto_power: float = 0.5) -> Tensor:
+    """objectives.py:158-201, same torch CPU ops on the same (global) generator, so a seeded run draws the cuts the
+    reference would: n_prefixes - 1 lengths without replacement from a Pareto-shaped distribution over 1..d_sae-1,
+    plus d_sae, sorted ascending."""
+    if n_prefixes <= 1:
+        return torch.tensor([d_sae], dtype=torch.int64)
+    assert n_prefixes <= d_sae
+    lengths = torch.arange(1, d_sae)
+    pareto_cdf = 1 - ((min_prefix_length / lengths.float()) ** pareto_power)
+    pareto_pdf = torch.cat([pareto_cdf[:1], pareto_cdf[1:] - pareto_cdf[:-1]])
+    probability_dist = pareto_pdf / pareto_pdf.sum()
+    sampled = torch.multinomial(probability_dist, num_samples=n_prefixes - 1, replacement=False)
+    prefixes = torch.cat((lengths[sampled].detach().clone(), torch.tensor([d_sae])))
+    prefixes, _ = torch.sort(prefixes, descending=False)
+    return prefixes.to(torch.int64)
+
+
 def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
     act = sae_cfg.activation
     kind = _kind(act)
@@ -146,6 +163,7 @@ def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
         remove_parallel_grads=sae_cfg.remove_parallel_grads,
         normalize_w_dec=sae_cfg.normalize_w_dec,
         max_batch=max_batch,
+        max_prefixes=max(1, min(int(getattr(obj_cfg, "n_prefixes", 1)), sae_cfg.d_sae)) if kind == "TopK" else 1,
     )
 
 
@@ -180,7 +198,7 @@ class Output:
     def x_hats(self) -> Tensor:
         if "x_hats" not in self._cache:
             self._check()
-            self._cache["x_hats"] = self._sae.engine.x_hat(self._x)[:, None, :]
+            self._cache["x_hats"] = self._sae.engine.x_hats(self._x)
         return self._cache["x_hats"]
 
     @property
@@ -268,6 +286,7 @@ class SparseAutoencoder(torch.nn.Module):
             or eng.device != dev
             or batch > eng.cfg.max_batch
             or eng.cfg.dead_threshold_tokens != self._obj_cfg.dead_threshold_tokens
+            or eng.cfg.max_prefixes < min(int(getattr(self._obj_cfg, "n_prefixes", 1)), self.cfg.d_sae)
         )
         if need_new:
             new = Engine(engine_config(self.cfg, self._obj_cfg, max(batch, self._max_batch)), device=dev)
@@ -310,6 +329,7 @@ class SparseAutoencoder(torch.nn.Module):
     # ---- reference API ---------------------------------------------------------------------
     def _eval_forward(self, x: Tensor):
         eng = self._bind(x.shape[0])
+        eng.set_prefixes(None)  # SparseAutoencoder.forward decodes with the single full prefix (modeling.py:331-341)
         eng.forward(x.contiguous(), training=False)
         self._ticket += 1
         return Output(self, x, self._ticket)
@@ -435,11 +455,14 @@ class MatryoshkaObjective(torch.nn.Module):
         self.toks_since_active: Tensor | None = None
 
     def forward(self, sae: SparseAutoencoder, x: Tensor):
-        if self.cfg.n_prefixes > 1:
-            raise NotImplementedError("Matryoshka(n_prefixes > 1) has no CUDA path in saev_b200; use n_prefixes=1")
         sae._require_topk()
+        if self.cfg.n_prefixes > 1 and _kind(sae.cfg.activation) != "TopK":
+            raise NotImplementedError("Matryoshka(n_prefixes > 1) has a CUDA path for the TopK activation only; "
+                                      "use n_prefixes=1 with Relu")
         x = x.contiguous()
         eng = sae._bind(x.shape[0], self.cfg)
+        # objectives.py:125: the cuts are drawn on the host from the global torch generator, every forward
+        eng.set_prefixes(sample_prefixes(sae.cfg.d_sae, self.cfg.n_prefixes).tolist() if self.cfg.n_prefixes > 1 else None)
         sae._ticket += 1
         out = Output(sae, x, sae._ticket)
         if self.training:

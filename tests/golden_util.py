@@ -8,7 +8,7 @@ from oracle import sae_oracle as orc
 
 GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 CASES = ["tiny_topk_auxk", "tiny_topk_auxk_clamp", "tiny_topk_noaux_noproj", "tiny_relu_l1_auxk", "c1_topk",
-         "c1_topk_auxk_live"]
+         "c1_topk_auxk_live", "tiny_topk_matryoshka", "c1_topk_matryoshka"]
 
 
 def load_case(name):
@@ -22,6 +22,13 @@ def load_case(name):
         n_steps=meta["sched_steps"], grad_clip=meta["grad_clip"],
     )
     return z, meta, cfg
+
+
+def prefixes_of(z, step):
+    """The Matryoshka cut points the reference drew for forward number `step` (None for single-prefix runs)."""
+    if "prefixes" not in z.files or z["prefixes"].shape[1] <= 1:
+        return None
+    return [int(c) for c in z["prefixes"][step]]
 
 
 def t(a):

@@ -62,7 +62,7 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(RuntimeError, match="CUDA"):
         Engine(EngineConfig(d_model=128, d_sae=512, top_k=16, max_batch=256))
     cfg = _lib.Cfg(d_model=128, d_sae=512, act_kind=0, top_k=16, aux_kind=0, k_aux=0, aux_alpha=0.0, l1_coeff=0.0,
-                   dead_threshold_tokens=1, remove_parallel_grads=1, max_batch=256, aux_cols_cap=0, reserved=0)
+                   dead_threshold_tokens=1, remove_parallel_grads=1, max_batch=256, aux_cols_cap=0, max_prefixes=0)
     h = C.c_void_p()
     rc = lib.saev_b200_create(C.byref(cfg), C.byref(h))
     assert rc != 0 and not h.value
@@ -74,7 +74,7 @@ def test_create_rejects_bad_configs(lib):
 
     def rc(**kw):
         base = dict(d_model=128, d_sae=512, act_kind=0, top_k=16, aux_kind=0, k_aux=0, aux_alpha=0.0, l1_coeff=0.0,
-                    dead_threshold_tokens=1, remove_parallel_grads=1, max_batch=256, aux_cols_cap=0, reserved=0)
+                    dead_threshold_tokens=1, remove_parallel_grads=1, max_batch=256, aux_cols_cap=0, max_prefixes=0)
         base.update(kw)
         h = C.c_void_p()
         return lib.saev_b200_create(C.byref(_lib.Cfg(**base)), C.byref(h)), lib.saev_b200_last_error(None)

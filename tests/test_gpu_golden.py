@@ -8,7 +8,7 @@ fp32 summation order, so the assertions use TOL = 2e-5 for vectors and scalars (
 import pytest
 import torch
 
-from tests.golden_util import CASES, load_case, rel_l2, t
+from tests.golden_util import CASES, load_case, prefixes_of, rel_l2, t
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,7 @@ def _engine_for(meta, cfg, B):
             d_model=cfg.d_model, d_sae=cfg.d_sae, top_k=cfg.top_k, activation=cfg.activation, aux=cfg.aux,
             k_aux=cfg.k_aux, aux_alpha=cfg.aux_alpha, l1_coeff=cfg.l1_coeff,
             dead_threshold_tokens=cfg.dead_threshold_tokens, remove_parallel_grads=cfg.remove_parallel_grads,
-            normalize_w_dec=cfg.normalize_w_dec, max_batch=B,
+            normalize_w_dec=cfg.normalize_w_dec, max_batch=B, max_prefixes=max(1, meta.get("n_prefixes", 1)),
         )
     )
 
@@ -45,6 +45,7 @@ def test_cuda_path_replays_reference_run(name):
         x = xs[step].contiguous()
         lr = float(z["rec_lr"][step])
         eng.normalize_w_dec()
+        eng.set_prefixes(prefixes_of(z, step))
         eng.forward(x, training=True)
         eng.backward(x)
         eng.grad_sumsq()
@@ -74,8 +75,11 @@ def test_cuda_path_replays_reference_run(name):
     assert torch.equal(eng.toks_since_active.cpu(), t(z["toks_since_active"]))
     # eval-mode forward (train.py:526-527,559): no dead tracking, aux = 0
     x = xs[-1].contiguous()
+    eng.set_prefixes(prefixes_of(z, meta["n_steps"]))
     eng.forward(x, training=False)
     ld = eng.loss_dict()
+    if prefixes_of(z, 0) is not None:
+        assert rel_l2(eng.x_hats(x).cpu(), z["eval_x_hats_all"]) < 10 * TOL  # r_i recovered as a difference of suffix sums
     assert ld["mse"] == pytest.approx(float(z["eval_mse"]), rel=TOL)
     assert ld["l0"] == pytest.approx(float(z["eval_l0"]), rel=TOL)
     assert ld["aux"] == 0.0 and ld["n_dead"] == 0.0

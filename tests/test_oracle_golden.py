@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import sae_oracle as orc
-from tests.golden_util import CASES, load_case, rel_l2, t
+from tests.golden_util import CASES, load_case, prefixes_of, rel_l2, t
 
 TOL = 2e-5  # fp32, same op order up to reduction order; measured ~1e-7..3e-6
 
@@ -21,7 +21,7 @@ def test_oracle_replays_reference_run(name):
     grad_steps = list(z["grad_steps"])
     for step in range(meta["n_steps"]):
         assert st.lr == pytest.approx(z["rec_lr"][step], rel=1e-12, abs=0)
-        out = orc.train_step(cfg, st, xs[step])
+        out = orc.train_step(cfg, st, xs[step], prefixes=prefixes_of(z, step))
         for key in ("mse", "aux", "sparsity", "l0", "l1", "grad_norm", "loss"):
             assert out[key] == pytest.approx(float(z[f"rec_{key}"][step]), rel=TOL, abs=1e-7), (step, key)
         assert out["n_dead"] == int(z["rec_n_dead"][step]), step
@@ -35,10 +35,28 @@ def test_oracle_replays_reference_run(name):
         assert rel_l2(st.m[k], z[f"m_{k}"]) < TOL, k
         assert rel_l2(st.v[k], z[f"v_{k}"]) < 10 * TOL, k
     assert torch.equal(st.toks_since_active, t(z["toks_since_active"]))
-    ev = orc.eval_forward(cfg, st, xs[-1])
+    ev = orc.eval_forward(cfg, st, xs[-1], prefixes=prefixes_of(z, meta["n_steps"]))
+    if ev.x_hats is not None:
+        assert rel_l2(ev.x_hats, z["eval_x_hats_all"]) < TOL
     assert float(ev.mse) == pytest.approx(float(z["eval_mse"]), rel=TOL)
     assert float(ev.l0) == pytest.approx(float(z["eval_l0"]), rel=TOL)
     assert rel_l2(ev.x_hat, z["eval_x_hat"]) < TOL
+
+
+def test_sample_prefixes_reproduces_the_reference_draws():
+    """Same torch CPU ops on the same global generator state => the same cuts the reference drew (objectives.py:158-201);
+    the golden run seeded torch with meta['seed'] and drew once per forward."""
+    from saev_b200 import nn as bnn
+
+    for name in ("tiny_topk_matryoshka", "c1_topk_matryoshka"):
+        z, meta, cfg = load_case(name)
+        for fn in (orc.sample_prefixes, bnn.sample_prefixes):
+            # reference order: manual_seed(seed); SparseAutoencoder(cfg) consumes kaiming_uniform_([S, D]) first
+            torch.manual_seed(meta["seed"])
+            torch.nn.init.kaiming_uniform_(torch.empty(meta["S"], meta["D"]))
+            draws = [fn(meta["S"], meta["n_prefixes"]).tolist() for _ in range(meta["n_steps"] + 1)]
+            assert draws == z["prefixes"].tolist(), (name, fn.__module__)
+    assert orc.sample_prefixes(64, 1).tolist() == [64]
 
 
 # ---- known answers restated from the reference's tests ---------------------------------------

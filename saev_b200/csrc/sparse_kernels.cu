@@ -294,30 +294,32 @@ __global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(Rescor
     const int v = lane + 32 * i;
     xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
   }
-  for (int c0 = 0; c0 < n; c0 += 4) {
-    int j[4];
-    float acc[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      j[u] = (c0 + u < n) ? si[c0 + u] : -1;
-      acc[u] = 0.f;
-    }
+  // Two candidates per round; all 2 x VPL row loads are issued before the first multiply so that a warp keeps
+  // 2 x D x 4 bytes in flight (the loop is bound by the latency of these gathers, not by their volume).
+  for (int c0 = 0; c0 < n; c0 += 2) {
+    const int j0 = si[c0];
+    const int j1 = (c0 + 1 < n) ? si[c0 + 1] : j0;
+    const float* r0 = a.W_enc_t + static_cast<long long>(j0) * a.D;
+    const float* r1 = a.W_enc_t + static_cast<long long>(j1) * a.D;
+    float4 w0[VPL], w1[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < D4) {
-        float4 w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          w[u] = (j[u] >= 0) ? ldg4(a.W_enc_t + static_cast<long long>(j[u]) * a.D + 4 * v) : make_float4(0, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += dot4(xr[i], w[u]);
-      }
+      const bool ok = v < D4;
+      w0[i] = ok ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
+      w1[i] = ok ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
     }
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float tot = warp_sum(acc[u]);
-      if (lane == 0 && c0 + u < n) se[c0 + u] = tot + __ldg(a.b_enc + j[u]);
+    for (int i = 0; i < VPL; ++i) {
+      a0 += dot4(xr[i], w0[i]);
+      a1 += dot4(xr[i], w1[i]);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      se[c0] = a0 + __ldg(a.b_enc + j0);
+      if (c0 + 1 < n) se[c0 + 1] = a1 + __ldg(a.b_enc + j1);
     }
   }
   __syncwarp();
@@ -783,7 +785,7 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
 // Atoms that did not fire get zero rows (the dense .grad tensors saev's loop expects).
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = a.row_begin + blockIdx.x * 8 + warp;
   if (j >= a.row_end) return;
@@ -841,8 +843,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < D4) {
-        *reinterpret_cast<float4*>(gdrow + 4 * v) = make_float4(0, 0, 0, 0);
-        *reinterpret_cast<float4*>(gerow + 4 * v) = make_float4(0, 0, 0, 0);
+        __stcs(reinterpret_cast<float4*>(gdrow + 4 * v), make_float4(0, 0, 0, 0));
+        __stcs(reinterpret_cast<float4*>(gerow + 4 * v), make_float4(0, 0, 0, 0));
       }
     }
     if (lane == 0) {
@@ -858,7 +860,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     gd[i].x *= a.grad_scale; gd[i].y *= a.grad_scale; gd[i].z *= a.grad_scale; gd[i].w *= a.grad_scale;
-    w[i] = (v < D4) ? ldg4(wrow + 4 * v) : make_float4(0, 0, 0, 0);
+    w[i] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow + 4 * v)) : make_float4(0, 0, 0, 0);
     dot += dot4(gd[i], w[i]);
     nsq += dot4(w[i], w[i]);
   }
@@ -872,9 +874,9 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
-    if (v < D4) {
-      *reinterpret_cast<float4*>(gdrow + 4 * v) = gd[i];
-      *reinterpret_cast<float4*>(gerow + 4 * v) = ge[i];
+    if (v < D4) {  // streaming stores: the 537 MB of gradients must not evict x / resid (the gather set) from L2
+      __stcs(reinterpret_cast<float4*>(gdrow + 4 * v), gd[i]);
+      __stcs(reinterpret_cast<float4*>(gerow + 4 * v), ge[i]);
     }
   }
   if (a.row_gsq != nullptr) {  // this atom's share of ||g||^2 (saves the separate pass of clip_grad_norm_)

@@ -159,6 +159,47 @@ def run_reference(args, D, S, K, B, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def make_bench_shards(D, B, n_batches, rank):
+    """Synthetic Gaussian activation shards in saev's on-disk format (fp32 [examples, layers=1, tokens, d_model] +
+    metadata.json + shards.json, src/saev/data/shards.py:43-180, 575-636) on local scratch storage."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    T = 256  # tokens per example (ViT-L/14 at 224 px)
+    n_examples = -(-n_batches * B // T)
+    per_shard = min(n_examples, max(1, (1 << 28) // (T * D * 4)))  # ~256 MB shards
+    need = n_examples * T * D * 4
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if shutil.disk_usage(cand).free > need * 1.2 + (1 << 30):
+                base = cand
+                break
+        except OSError:
+            continue
+    if base is None:
+        raise RuntimeError("no scratch space for the benchmark shards")
+    root = pathlib.Path(tempfile.mkdtemp(prefix=f"saev_b200_bench_r{rank}_", dir=base)) / "saev" / "shards" / "bench0000"
+    root.mkdir(parents=True)
+    md = dict(family="fake-clip", ckpt="synthetic", layers=[0], content_tokens_per_example=T, cls_token=False, d_model=D,
+              n_examples=n_examples, max_tokens_per_shard=per_shard * T, data="", dataset="synthetic",
+              pixel_agg="majority", dtype="float32", protocol="2.1")
+    (root / "metadata.json").write_text(json.dumps(md))
+    gen = torch.Generator().manual_seed(99 + rank)
+    info = []
+    for s0 in range(0, n_examples, per_shard):
+        n = min(per_shard, n_examples - s0)
+        block = torch.randn(per_shard * T, D, generator=gen)  # fixed-size shard files, tail rows unused
+        name = f"acts{s0 // per_shard:06d}.bin"
+        block.numpy().tofile(root / name)
+        info.append({"name": name, "n_examples": n})
+    (root / "shards.json").write_text(json.dumps(info))
+    return root
+
+
 def workload_name(w, D, S, K, B):
     act = f"TopK k={K}" if K else "ReLU + L1Sparsity(4e-4)"
     return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective MSE+AuxK(k_aux=512, alpha=1/32, "
@@ -176,6 +217,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
+    ap.add_argument("--loader-threads", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -263,45 +306,94 @@ def main():
     final_losses = tr.global_losses()
     screen = eng.screen_stats()
 
-    # ---------------- timed region 2: end to end from pinned host buffers ----------------
-    x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
-    for h, d in zip(x_host, x_dev):
-        h.copy_(d)
-    stage_bufs = [torch.empty(B, D, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    # ---------------- timed region 2: end to end ----------------
+    # Preferred: the loader a saev user would construct -- activation shards on local storage (tmpfs) are read by the
+    # native I/O threads into PINNED staging chunks, copied to the HBM shuffle pool on the loader's stream, gathered
+    # into batches on the device, and every step's loss vector is read back to pinned host memory.  Fallback (no
+    # writable scratch space): a two-slot pinned ring fed from host tensors.
+    e2e_path, e2e_note = "loader", ""
+    e2e_value = None
     loss_host = torch.empty(args.steps, 8, dtype=torch.float32).pin_memory()
-    main_stream = torch.cuda.current_stream(dev)
+    shards_root = None
+    try:
+        if args.e2e != "loader":
+            raise RuntimeError("ring requested")
+        from saev_b200 import data as bdata
+        from saev_b200.scheduling import BatchLimiter
 
-    def prefetch(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            stage_bufs[slot].copy_(x_host[i % NB], non_blocking=True)
-            copied[slot].record(copy_stream)
+        n_batches = args.steps + 6
+        shards_root = make_bench_shards(D, B, n_batches, rank)
+        lcfg = bdata.ShuffledConfig(shards=shards_root, layer=0, batch_size=B, n_threads=args.loader_threads,
+                                    buffer_size=4, seed=17 + rank, batch_timeout_s=60.0)
+        loader = bdata.ShuffledDataLoader(lcfg, device=dev, rank=0, world_size=1)  # every rank owns its directory
+        limiter = BatchLimiter(loader, args.steps * B + 2 * B)
+        it = iter(limiter)
+        for _ in range(2):  # pool fill + first batches are warm-up
+            tr.step(next(it)["act"], lr_at(gstep))
+            gstep += 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            batch = next(it)
+            tr.step(batch["act"], lr_at(gstep))
+            loss_host[i].copy_(eng.losses, non_blocking=True)
+            gstep += 1
+        e1.record()
+        barrier()
+        it.close()
+        loader.shutdown()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+        e2e_note = (f"ShuffledDataLoader over {n_batches} batches of fp32 shards under {shards_root.parents[3]} "
+                    f"({args.loader_threads} I/O threads, pinned staging -> HBM pool -> gather)")
+    except Exception as err:  # noqa: BLE001
+        e2e_path, e2e_note = "pinned-ring", f"loader path unavailable ({type(err).__name__}: {str(err)[:80]})"
+    finally:
+        if shards_root is not None:
+            import shutil
 
-    for s in range(2):
-        consumed[s].record(main_stream)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    prefetch(0)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            prefetch(i + 1)
-        slot = i % 2
-        main_stream.wait_event(copied[slot])
-        tr.step(stage_bufs[slot], lr_at(gstep))
-        consumed[slot].record(main_stream)
-        loss_host[i].copy_(eng.losses, non_blocking=True)
-        gstep += 1
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+            shutil.rmtree(shards_root.parents[2], ignore_errors=True)
+    if e2e_value is None:
+        x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
+        for h, d in zip(x_host, x_dev):
+            h.copy_(d)
+        stage_bufs = [torch.empty(B, D, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream(dev)
+
+        def prefetch(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                stage_bufs[slot].copy_(x_host[i % NB], non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        for s in range(2):
+            consumed[s].record(main_stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prefetch(0)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                prefetch(i + 1)
+            slot = i % 2
+            main_stream.wait_event(copied[slot])
+            tr.step(stage_bufs[slot], lr_at(gstep))
+            consumed[slot].record(main_stream)
+            loss_host[i].copy_(eng.losses, non_blocking=True)
+            gstep += 1
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
 
     if rank == 0:
         peaks, peaks_src = load_peaks()
@@ -333,8 +425,9 @@ def main():
                              f"{NB} rotating input batches) is far larger than the 126 MB L2; no explicit flush",
             },
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "activations/s", "h2d_bytes_per_step": B * D * 4,
-                    "d2h_bytes_per_step": 32},
+            "e2e": {"value": e2e_value, "unit": "activations/s",
+                    "h2d_bytes_per_step": B * D * 4 + (B * 8 if e2e_path == "loader" else 0), "d2h_bytes_per_step": 32,
+                    "path": e2e_path, "note": e2e_note},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "encode_gemm2_kernel (tcgen05 cta_group::2 encoder contraction + "
                          "top-k screen)" if K else "encode_gemm_kernel<2> (tcgen05 encoder contraction, 3-term split, ReLU)",

@@ -386,7 +386,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool live = row < p.M;
       float tau = live ? -INFINITY : INFINITY;
       const float margin = live ? p.row_margin[row] * wn : 0.f;
-      int cnt = 0;
+      int2* wp = my_buf;  // append cursor (a running pointer keeps the per-hit address arithmetic to one add)
       bool overflowed = false;
       *my_tau_s = -INFINITY;
       named_bar_sync(2 + q, 64);  // both column halves of this quadrant start the row block together
@@ -439,8 +439,8 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   const bool hit = v[4 * g + i] > tau;
                   if (__any_sync(FULL, hit)) {  // warp-uniform: usually a single lane of a single column
                     if (hit) {
-                      my_buf[cnt] = make_int2(__float_as_int(v[4 * g + i]), col0 + 4 * g + i);
-                      ++cnt;
+                      *wp = make_int2(__float_as_int(v[4 * g + i]), col0 + 4 * g + i);
+                      ++wp;
                     }
                   }
                 }
@@ -467,6 +467,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         // A list may grow by at most HALF entries per tile (one per column), so compacting every list that is
         // above CAPG - HALF here guarantees that appends never overflow.
+        const int cnt = static_cast<int>(wp - my_buf);
         unsigned need = __ballot_sync(FULL, cnt > TRIGGER);
         while (need) {
           const int l = __ffs(need) - 1;
@@ -478,7 +479,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           bool ovf;
           const float thr = compact_list(warp_buf + l * lane_stride, nn, p.top_k, mg, fl, lane, hist_w, n_out, ovf);
           if (lane == l) {
-            cnt = n_out;
+            wp = my_buf + n_out;
             tau = fmaxf(tau, thr);
             overflowed |= ovf;
             *my_tau_s = tau;
@@ -488,8 +489,9 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
 
       // publish this (row block, range, half): trim each list to the margin band of its k-th largest
+      const int cnt_end = static_cast<int>(wp - my_buf);
       for (int l = 0; l < 32; ++l) {
-        const int nn = __shfl_sync(FULL, cnt, l);
+        const int nn = __shfl_sync(FULL, cnt_end, l);
         const float mg = __shfl_sync(FULL, margin, l);
         const float fl = __shfl_sync(FULL, tau, l);
         const int grow = row - lane + l;

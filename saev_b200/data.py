@@ -323,7 +323,8 @@ class ShuffledDataLoader:
                 }
         finally:
             self._iterating = False
-            lib.saev_b200_loader_stop(h)
+            if self._h is h:  # shutdown() may already have destroyed the native loader
+                lib.saev_b200_loader_stop(h)
 
     def shutdown(self) -> None:
         """shuffled.py:555-575: stop the producer side and release the pool."""

@@ -19,6 +19,8 @@
 // allocator, warps 4-11 = epilogue.  Barriers: full/empty per smem stage (full lives in the leader, both CTAs'
 // TMA transactions complete on it; empty is multicast to both CTAs by tcgen05.commit), tfull (multicast commit)
 // / tempty (leader, 16 arrivals: 8 warps x 2 CTAs) per TMEM accumulator stage.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -39,7 +41,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int HALF = BN / 2;   // columns per epilogue warp per tile
 constexpr int CAPG = ENCODE2_CAPG;             // entries per candidate list
-constexpr int TRIGGER = CAPG - HALF;            // compact a list once it could not absorb a whole further tile
+constexpr int TRIGGER_MAX = CAPG - HALF;        // a list above this could not absorb a whole further tile
 
 constexpr size_t OFF_BIAS = static_cast<size_t>(STAGES) * STAGE_BYTES;            // [8 warps][2 acc stages][128] f32
 constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * 2 * HALF * 4;  // [2 halves][128 rows] f32
@@ -254,6 +256,7 @@ struct Params {
   int q;                // tile-steps per CTA pair
   int nlists;           // candidate lists per row = 2 * nsplit
   int top_k;
+  int trigger;          // compact a list once it holds more than this many entries (<= TRIGGER_MAX)
   const float* bias;
   const float* row_margin;
   const float* wnorm_sq_max;
@@ -468,7 +471,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // A list may grow by at most HALF entries per tile (one per column), so compacting every list that is
         // above CAPG - HALF here guarantees that appends never overflow.
         const int cnt = static_cast<int>(wp - my_buf);
-        unsigned need = __ballot_sync(FULL, cnt > TRIGGER);
+        unsigned need = __ballot_sync(FULL, cnt > p.trigger);
         while (need) {
           const int l = __ffs(need) - 1;
           need &= need - 1;
@@ -620,6 +623,17 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
   p.q = pl.q;
   p.nlists = pl.nlists;
   p.top_k = a.top_k;
+  {
+    // Lists are compacted (and the row's admission threshold tightened) after every tile that leaves them above
+    // `trigger`.  Appends made under a stale threshold cost more than the compaction, so the trigger sits well
+    // below the capacity bound; it must leave room for k entries plus the margin band.
+    static int trig = -1;
+    if (trig < 0) {
+      const char* e = getenv("SAEV_B200_TRIGGER");
+      trig = e ? atoi(e) : 192;
+    }
+    p.trigger = max(2 * a.top_k, min(trig, TRIGGER_MAX));
+  }
   p.bias = a.bias;
   p.row_margin = a.row_margin;
   p.wnorm_sq_max = a.wnorm_sq_max;

@@ -226,7 +226,7 @@ __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* 
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(RescoreArgs a) {
+__global__ void __launch_bounds__(32 * RESCORE_WARPS, 3) rescore_topk_kernel(RescoreArgs a) {
   __shared__ int hist_s[RESCORE_WARPS][256];
   __shared__ float sv_s[RESCORE_WARPS][RESCORE_CAP];
   __shared__ int si_s[RESCORE_WARPS][RESCORE_CAP];
@@ -294,32 +294,34 @@ __global__ void __launch_bounds__(32 * RESCORE_WARPS) rescore_topk_kernel(Rescor
     const int v = lane + 32 * i;
     xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
   }
-  // Two candidates per round; all 2 x VPL row loads are issued before the first multiply so that a warp keeps
-  // 2 x D x 4 bytes in flight (the loop is bound by the latency of these gathers, not by their volume).
-  for (int c0 = 0; c0 < n; c0 += 2) {
-    const int j0 = si[c0];
-    const int j1 = (c0 + 1 < n) ? si[c0 + 1] : j0;
-    const float* r0 = a.W_enc_t + static_cast<long long>(j0) * a.D;
-    const float* r1 = a.W_enc_t + static_cast<long long>(j1) * a.D;
-    float4 w0[VPL], w1[VPL];
+  // RB candidates per round; all RB x VPL row loads are issued before the first multiply so that a warp keeps
+  // RB x D x 4 bytes in flight (the loop is bound by the latency of these gathers, not by their volume).
+  constexpr int RB = 2;
+  for (int c0 = 0; c0 < n; c0 += RB) {
+    int jj[RB];
+    float4 w[RB][VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      const bool ok = v < D4;
-      w0[i] = ok ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
-      w1[i] = ok ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
-    }
-    float a0 = 0.f, a1 = 0.f;
+    for (int u = 0; u < RB; ++u) {
+      jj[u] = si[min(c0 + u, n - 1)];
+      const float* r = a.W_enc_t + static_cast<long long>(jj[u]) * a.D;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      a0 += dot4(xr[i], w0[i]);
-      a1 += dot4(xr[i], w1[i]);
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        w[u][i] = (v < D4) ? ldg4(r + 4 * v) : make_float4(0, 0, 0, 0);
+      }
     }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
+    float acc[RB];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      acc[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[u] += dot4(xr[i], w[u][i]);
+      acc[u] = warp_sum(acc[u]);
+    }
     if (lane == 0) {
-      se[c0] = a0 + __ldg(a.b_enc + j0);
-      if (c0 + 1 < n) se[c0 + 1] = a1 + __ldg(a.b_enc + j1);
+#pragma unroll
+      for (int u = 0; u < RB; ++u)
+        if (c0 + u < n) se[c0 + u] = acc[u] + __ldg(a.b_enc + jj[u]);
     }
   }
   __syncwarp();

@@ -389,7 +389,7 @@ int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
 //   dh_k = grad_scale * <r, W_dec[j_k]> (+ l1/B * sign(f_k))   (autograd of the above)
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(256, 2) decode_kernel(DecodeArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
   if (b >= a.B) return;
@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
   }
   const long long kb = static_cast<long long>(b) * K;
   float l1 = 0.f, l0 = 0.f;
+  // Both passes gather dictionary rows whose addresses are known up front; every round issues the 2 x VPL loads of two
+  // rows before the first FMA so that a warp keeps 2 x D x 4 bytes in flight (the kernel is bound by gather latency).
   for (int k0 = 0; k0 < K; k0 += 32) {
     const int kk = k0 + lane;
     const int mj = (kk < K) ? a.topk_idx[kb + kk] : -1;
@@ -411,16 +413,22 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
       l0 += (mf != 0.f) ? 1.f : 0.f;
     }
     const int cnt = min(32, K - k0);
-#pragma unroll 4
-    for (int t = 0; t < cnt; ++t) {
-      const int j = __shfl_sync(FULL, mj, t);
-      const float f = __shfl_sync(FULL, mf, t);
-      if (j < 0) continue;
-      const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+    for (int t = 0; t < cnt; t += 2) {
+      const int j0 = __shfl_sync(FULL, mj, t), j1 = (t + 1 < cnt) ? __shfl_sync(FULL, mj, t + 1) : -1;
+      const float f0 = __shfl_sync(FULL, mf, t), f1 = __shfl_sync(FULL, mf, (t + 1) & 31);
+      const float* r0 = a.W_dec + static_cast<long long>(max(j0, 0)) * a.D;
+      const float* r1 = a.W_dec + static_cast<long long>(max(j1, 0)) * a.D;
+      float4 w0[VPL], w1[VPL];
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
-        if (v < D4) fma4(acc[i], f, ldg4(wrow + 4 * v));
+        w0[i] = (v < D4 && j0 >= 0) ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
+        w1[i] = (v < D4 && j1 >= 0) ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        fma4(acc[i], f0, w0[i]);
+        fma4(acc[i], f1, w1[i]);
       }
     }
   }
@@ -456,20 +464,27 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
     const float mf = (kk < K) ? a.topk_val[kb + kk] : 0.f;
     float mine = 0.f;
     const int cnt = min(32, K - k0);
-#pragma unroll 2
-    for (int t = 0; t < cnt; ++t) {
-      const int j = __shfl_sync(FULL, mj, t);
-      float p = 0.f;
-      if (j >= 0) {
-        const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+    for (int t = 0; t < cnt; t += 2) {
+      const int j0 = __shfl_sync(FULL, mj, t), j1 = (t + 1 < cnt) ? __shfl_sync(FULL, mj, t + 1) : -1;
+      const float* r0 = a.W_dec + static_cast<long long>(max(j0, 0)) * a.D;
+      const float* r1 = a.W_dec + static_cast<long long>(max(j1, 0)) * a.D;
+      float4 w0[VPL], w1[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          const int v = lane + 32 * i;
-          if (v < D4) p += dot4(acc[i], ldg4(wrow + 4 * v));
-        }
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        w0[i] = (v < D4 && j0 >= 0) ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
+        w1[i] = (v < D4 && j1 >= 0) ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
       }
-      p = warp_sum(p);
-      if (lane == t) mine = p;
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        p0 += dot4(acc[i], w0[i]);
+        p1 += dot4(acc[i], w1[i]);
+      }
+      p0 = warp_sum(p0);
+      p1 = warp_sum(p1);
+      if (lane == t) mine = p0;
+      if (lane == t + 1) mine = p1;
     }
     if (kk < K) {
       float d = a.grad_scale * mine;

@@ -217,6 +217,10 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap"],
+                    help="gradient exchange for N > 1 (see saev_b200/parallel.py)")
+    ap.add_argument("--gather-ctas", type=int, default=16)
+    ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
     ap.add_argument("--loader-threads", type=int, default=8)
     args = ap.parse_args()
@@ -255,7 +259,20 @@ def main():
                               l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
                               dead_threshold_tokens=10_000_000, max_batch=B), device=dev)
     eng.init_params(seed=0)
-    tr = DataParallelTrainer(eng)
+    if args.dp_mode == "auto":
+        # measured on B200 (profiles/README.md): at 2 ranks the chunked all-reduce hidden behind the weight-gradient
+        # kernel wins (5.47 ms); from 4 ranks on the row-sharded optimizer whose fp32 all-gathers run beside the next
+        # step's screen wins (N=4: 5.40 vs 5.91 ms plain; N=8: 5.28 vs 5.92 ms)
+        args.dp_mode = "chunked" if world <= 2 else "sharded-overlap"
+    gather_group = None
+    if world > 1 and args.dp_mode == "sharded-overlap":
+        gopts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        gopts.config.max_ctas = args.gather_ctas
+        gopts.config.min_ctas = 1
+        gather_group = dist.new_group(backend="nccl", pg_options=gopts)
+    tr = DataParallelTrainer(eng, sharded=args.dp_mode.startswith("sharded"),
+                             n_chunks=4 if args.dp_mode == "chunked" else 1, gather_group=gather_group,
+                             reserved_sms=args.reserved_sms)
     tr.broadcast_params(0)
 
     # synthetic activations: 4 rotating batches per rank, resident in HBM (value) and in pinned host memory (e2e)
@@ -303,6 +320,7 @@ def main():
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+    tr.finish()
     final_losses = tr.global_losses()
     screen = eng.screen_stats()
 
@@ -416,7 +434,7 @@ def main():
             "config": {
                 "workload": workload_name(args.workload, D, S, K, B),
                 "global_batch": world * B,
-                "parallelism": f"dp{world}",
+                "parallelism": f"dp{world}" + (f" ({args.dp_mode} gradient exchange)" if world > 1 else ""),
                 "precision": ("bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "
                               "every value that reaches the loss / gradients / parameters is fp32") if K else
                              ("dense path: all five contractions as 3-term bf16 split products on tcgen05 (~2^-17 "

@@ -42,11 +42,17 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 7
+#define SAEV_B200_ABI_VERSION 8
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
-enum { SAEV_B200_PHASE_A = 1, SAEV_B200_PHASE_B = 2, SAEV_B200_PHASE_ALL = 3 };
+enum {
+  SAEV_B200_PHASE_A = 1,        /* all of phase A */
+  SAEV_B200_PHASE_B = 2,
+  SAEV_B200_PHASE_ALL = 3,
+  SAEV_B200_PHASE_A_SCREEN = 4, /* first half of A: operand prep + tcgen05 screen (reads only the bf16 operand copy) */
+  SAEV_B200_PHASE_A_REST = 8    /* second half of A: exact re-score + decode (reads the fp32 W_enc_t / W_dec) */
+};
 
 typedef struct saev_b200_cfg {
   int32_t d_model;               /* SparseAutoencoderConfig.d_model      modeling.py:265 */
@@ -139,6 +145,10 @@ int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* 
  * saev_b200_grad_sumsq_ranges over what it owns (+ an all-reduce of that scalar), and all-gathers the updated rows,
  * the bf16 operand (saev_b200_shadow_weights, [d_sae, d_model] bf16) and the row-norm maximum (MAX). */
 int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end);
+/* Leave `n_sms` SMs (rounded up to pairs) out of the top-k screen's persistent grid, so that NCCL kernels (the
+ * all-gather of the fp32 rows a sharded optimizer step leaves behind) can run BESIDE the screen of the next step;
+ * the split phase A (SCREEN, then REST after the gathers have landed) is the other half of that overlap. */
+int saev_b200_set_reserved_sms(saev_b200_handle* h, int32_t n_sms);
 int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, int32_t n_ranges,
                                 const int64_t* host_begins, const int64_t* host_ends, float* sumsq_out,
                                 void* workspace, void* stream);

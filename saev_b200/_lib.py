@@ -12,11 +12,12 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
 PHASE_A, PHASE_B, PHASE_ALL = 1, 2, 3
+PHASE_A_SCREEN, PHASE_A_REST = 4, 8
 STAGES = ("prep", "encode_gemm", "rescore", "decode", "loss", "csc", "wgrad", "bias_aux", "sumsq", "adam")
 
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "saev_b200_grad_sumsq": (C.c_int, [_p, _p, _i64, _p, _p, _p]),
     "saev_b200_grad_sumsq_local": (C.c_int, [_p, _p, _p, _p, _p]),
     "saev_b200_set_optimizer_shard": (C.c_int, [_p, _i32, _i32]),
+    "saev_b200_set_reserved_sms": (C.c_int, [_p, _i32]),
     "saev_b200_grad_sumsq_ranges": (C.c_int, [_p, _p, _i32, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p]),
     "saev_b200_shadow_weights": (_p, [_p, _p]),
     "saev_b200_wnorm_scalar": (_p, [_p, _p]),

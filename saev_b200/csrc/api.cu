@@ -38,6 +38,7 @@ struct saev_b200_handle {
   int num_sms = 148;
   int aux_cap = 0;
   int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen (0 => single-CTA kernel)
+  int reserved_pairs = 0;  // SM pairs the screen leaves idle (saev_b200_set_reserved_sms)
   Workspace ws;
   bool last_forward_training = false;
   bool last_forward_tracked = false;
@@ -457,17 +458,19 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   float* aux_loss = at<float>(workspace, w.scalars) + 2;
   const bool tracked = training && toks_since_active != nullptr;
 
+  const bool do_screen = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_SCREEN)) != 0;
+  const bool do_rest = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_REST)) != 0;
+  if ((phase & (SAEV_B200_PHASE_A_SCREEN | SAEV_B200_PHASE_A_REST)) && c.act_kind == SAEV_B200_ACT_RELU)
+    return fail(h, 40, "forward: the split phase A (screen / rest) exists for the TopK path only%s");
   if ((phase & SAEV_B200_PHASE_A) && c.act_kind == SAEV_B200_ACT_RELU) {
     cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
     if (int rc = forward_relu_phase_a(h, x, B, tokens_global, W_enc_t, b_enc, W_dec, b_dec, training, resid, workspace, s))
       return rc;
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
-  } else if (phase & SAEV_B200_PHASE_A) {
-    cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
-    if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
+  } else if (do_screen || do_rest) {
     __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
-    {
+    if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
       if (launch_prep_x(x, B, D, x_hi, at<float>(workspace, w.row_margin), s))
         return fail(h, 41, "forward: prep_x launch failed%s");
@@ -492,10 +495,11 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.tau_keys = at<unsigned int>(workspace, w.tau_keys);
     Encode2Plan pl;
     if (h->max_pairs > 0) {
-      pl = encode2_plan(B, S, h->max_pairs);
+      // `reserved_pairs` SM pairs are left idle (a data-parallel caller runs NCCL all-gathers beside this kernel)
+      pl = encode2_plan(B, S, h->max_pairs > h->reserved_pairs ? h->max_pairs - h->reserved_pairs : 1);
       g.nsplit = pl.nlists;  // what the re-score kernel merges per row
     }
-    {
+    if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
       if (int rc = h->max_pairs > 0 ? launch_encode_gemm2(g, pl, s) : launch_encode_gemm(g, s)) {
         char buf[64];
@@ -504,6 +508,9 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
       }
     }
 
+    if (do_rest) {
+    cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
+    if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
     RescoreArgs r;
     r.cand = g.cand;
     r.cand_cnt = g.cand_cnt;
@@ -553,6 +560,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     }
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
+    }  // do_rest
   }
 
   if (phase & SAEV_B200_PHASE_B) {
@@ -777,6 +785,12 @@ int saev_b200_backward_stage(saev_b200_handle* h, int32_t stage, int32_t row_beg
     return fail(h, 55, "backward_stage: stage must be 0 or 1%s");
   }
   return check_cuda(h, "backward_stage");
+}
+
+int saev_b200_set_reserved_sms(saev_b200_handle* h, int32_t n_sms) {
+  if (n_sms < 0 || n_sms > h->num_sms / 2) return fail(h, 66, "set_reserved_sms: 0 <= n_sms <= #SMs / 2%s");
+  h->reserved_pairs = (n_sms + 1) / 2;
+  return 0;
 }
 
 int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end) {

@@ -240,6 +240,10 @@ class Engine:
         include/saev_b200.h.  (0, 0) restores the full update."""
         self._ck(self.lib.saev_b200_set_optimizer_shard(self.h, row_begin, row_end))
 
+    def set_reserved_sms(self, n_sms: int) -> None:
+        """Keep `n_sms` SMs out of the top-k screen's persistent grid (room for concurrent NCCL kernels)."""
+        self._ck(self.lib.saev_b200_set_reserved_sms(self.h, n_sms))
+
     def grad_sumsq_ranges(self, ranges) -> torch.Tensor:
         """||g||^2 over up to four [begin, end) element ranges of the flat gradient bucket."""
         n = len(ranges)

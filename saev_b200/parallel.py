@@ -30,12 +30,18 @@ from .engine import LOSS_KEYS, Engine
 
 
 class DataParallelTrainer:
-    def __init__(self, engine: Engine, group=None, sharded: bool | None = None, n_chunks: int = 4):
+    def __init__(self, engine: Engine, group=None, sharded: bool | None = None, n_chunks: int = 4,
+                 gather_group=None, reserved_sms: int = 0):
+        """`gather_group` (sharded mode): a second process group (ideally created with few NCCL CTAs, e.g.
+        `ProcessGroupNCCL.Options().config.max_ctas = 4`) on which the all-gathers of the fp32 rows run in the
+        background, beside the top-k screen of the NEXT step, which then leaves `reserved_sms` SMs idle for them."""
         self.eng = engine
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self._w_dec_normalized = False
+        self.gather_group = gather_group
+        self._pending = []  # background all-gathers of the previous step
         S = getattr(engine, "S", 0)
         can_shard = (self.world > 1 and S > 0 and S % self.world == 0 and hasattr(engine, "set_optimizer_shard")
                      and getattr(engine.cfg, "activation", "topk") == "topk")
@@ -56,6 +62,8 @@ class DataParallelTrainer:
             self._ranges = [(self.j0 * D, self.j1 * D), (SD + S + self.j0 * D, SD + S + self.j1 * D)]
             if self.rank == 0:  # the (all-reduced) bias gradients are counted once
                 self._ranges += [(SD, SD + S), (2 * SD + S, 2 * SD + S + D)]
+            if gather_group is not None and reserved_sms > 0:
+                engine.set_reserved_sms(reserved_sms)
 
     def broadcast_params(self, src: int = 0) -> None:
         """Make every replica start from rank `src`'s parameters (model init is unseeded in saev)."""
@@ -74,7 +82,14 @@ class DataParallelTrainer:
         if self.world == 1:
             eng.forward(x, training=True, tokens_global=tokens_global)
         else:
-            eng.forward(x, training=True, phase=_lib.PHASE_A, tokens_global=tokens_global)
+            if self._pending:
+                # the screen needs only the bf16 operand copy (gathered synchronously at the end of the last step);
+                # the fp32 rows are still arriving on the gather group's stream
+                eng.forward(x, training=True, phase=_lib.PHASE_A_SCREEN, tokens_global=tokens_global)
+                self.finish()
+                eng.forward(x, training=True, phase=_lib.PHASE_A_REST, tokens_global=tokens_global)
+            else:
+                eng.forward(x, training=True, phase=_lib.PHASE_A, tokens_global=tokens_global)
             dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g)
             eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
         renorm = fused_renorm and eng.cfg.normalize_w_dec
@@ -111,10 +126,22 @@ class DataParallelTrainer:
             shadow = eng.shadow_weights()
             dist.all_gather_into_tensor(shadow, shadow[j0:j1], group=g)
             dist.all_reduce(eng.wnorm_scalar(), op=dist.ReduceOp.MAX, group=g)
-            dist.all_gather_into_tensor(eng.W_enc_t, eng.W_enc_t[j0:j1], group=g)
-            dist.all_gather_into_tensor(eng.W_dec, eng.W_dec[j0:j1], group=g)
+            if self.gather_group is not None:
+                gg = self.gather_group
+                self._pending = [dist.all_gather_into_tensor(eng.W_enc_t, eng.W_enc_t[j0:j1], group=gg, async_op=True),
+                                 dist.all_gather_into_tensor(eng.W_dec, eng.W_dec[j0:j1], group=gg, async_op=True)]
+            else:
+                dist.all_gather_into_tensor(eng.W_enc_t, eng.W_enc_t[j0:j1], group=g)
+                dist.all_gather_into_tensor(eng.W_dec, eng.W_dec[j0:j1], group=g)
         self._w_dec_normalized = renorm
         return eng.losses
+
+    def finish(self) -> None:
+        """Make the current stream wait for the background all-gathers of the last step (call before anything reads
+        the fp32 parameters: checkpointing, evaluation, the next step does it itself)."""
+        for wk in self._pending:
+            wk.wait()
+        self._pending = []
 
     def global_losses(self) -> dict:
         """Loss scalars of the global batch (host sync; call on log steps only)."""

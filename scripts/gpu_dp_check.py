@@ -35,13 +35,16 @@ for x, lr in zip(xs, lrs):
     ref_losses.append(ref.loss_dict())
 ok = True
 per = B // world
-for sharded, n_chunks in ((False, 4), (False, 1), (True, 1)):
+gopts = dist.ProcessGroupNCCL.Options()
+gopts.config.max_ctas = 4
+bg = dist.new_group(backend="nccl", pg_options=gopts)
+for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None), (True, 1, bg)):
     eng = Engine(cfg, device=dev)
     eng.init_params(seed=7)
-    tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks)
+    tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks, gather_group=gg, reserved_sms=4 if gg else 0)
     tr.broadcast_params(0)
     assert tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1)
-    sharded = f"{sharded}/chunks={n_chunks}"
+    sharded = f"{sharded}/chunks={n_chunks}/background-gather={gg is not None}"
     for i, (x, lr) in enumerate(zip(xs, lrs)):
         tr.step(x[rank * per:(rank + 1) * per].contiguous(), lr, fused_renorm=True)
         gl = tr.global_losses()
@@ -52,6 +55,7 @@ for sharded, n_chunks in ((False, 4), (False, 1), (True, 1)):
         if int(gl["n_dead"]) != int(ref_losses[i]["n_dead"]):
             ok = False
             print(f"[rank {rank}] sharded={sharded} step {i} n_dead {gl['n_dead']} vs {ref_losses[i]['n_dead']}")
+    tr.finish()
     errs = {n: rel(a, b) for n, a, b in (("W_enc_t", eng.W_enc_t, ref.W_enc_t), ("b_enc", eng.b_enc, ref.b_enc),
                                          ("W_dec", eng.W_dec, ref.W_dec), ("b_dec", eng.b_dec, ref.b_dec))}
     sh = rel(eng.shadow_weights().float(), ref.shadow_weights().float())

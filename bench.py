@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--gather-ctas", type=int, default=16)
     ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
-    ap.add_argument("--loader-threads", type=int, default=8)
+    ap.add_argument("--loader-threads", type=int, default=0, help="I/O threads per rank (0 = cores / ranks - 1, 2..8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -339,6 +339,8 @@ def main():
         from saev_b200 import data as bdata
         from saev_b200.scheduling import BatchLimiter
 
+        if args.loader_threads <= 0:  # do not oversubscribe the host: every rank also runs a feeder + the Python loop
+            args.loader_threads = max(2, min(8, (os.cpu_count() or 8) // world - 1))
         n_batches = args.steps + 6
         shards_root = make_bench_shards(D, B, n_batches, rank)
         lcfg = bdata.ShuffledConfig(shards=shards_root, layer=0, batch_size=B, n_threads=args.loader_threads,

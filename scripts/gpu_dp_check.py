@@ -28,6 +28,7 @@ def rel(a, b):
 
 ref = Engine(cfg, device=dev)
 ref.init_params(seed=7)
+ref0 = {k: getattr(ref, k).clone() for k in ("W_enc_t", "b_enc", "W_dec", "b_dec")}
 lrs = [0.0, 5e-4, 1e-3, 1e-3]
 ref_losses = []
 for x, lr in zip(xs, lrs):
@@ -63,6 +64,39 @@ for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None
         ok = False
     if rank == 0:
         print(f"sharded={sharded}: param rel-L2 vs single-GPU {errs}, bf16 operand {sh:.2e}, n_dead(last)={ref_losses[-1]['n_dead']}")
+# ---- the drop-in surface under data parallelism: saev_b200.nn objective + optim shims, `sae.data_parallel()` ----
+from saev_b200 import nn as bnn, optim as boptim
+
+torch.manual_seed(7)
+sae_cfg = bnn.SparseAutoencoderConfig(d_model=D, d_sae=S, activation=bnn.TopK(top_k=K, aux=bnn.AuxK(k_aux=64)),
+                                      reinit_blend=0.0)
+sae = bnn.SparseAutoencoder(sae_cfg)
+with torch.no_grad():  # same start as the engines above
+    sae.W_dec.copy_(ref0["W_dec"]); sae.b_dec.copy_(ref0["b_dec"]); sae.W_enc.copy_(ref0["W_enc_t"].t()); sae.b_enc.copy_(ref0["b_enc"])
+obj = bnn.get_objective(bnn.Matryoshka(n_prefixes=1, dead_threshold_tokens=2 * B))
+opt = boptim.FusedAdam([{"params": sae.parameters(), "lr": 0.0}], fused=True)
+sae.train(); sae = sae.to(dev); obj.train(); sae.data_parallel()
+for i, (x, lr) in enumerate(zip(xs, lrs)):
+    opt.param_groups[0]["lr"] = lr
+    sae.normalize_w_dec()
+    loss, fwd = obj(sae, x[rank * per:(rank + 1) * per].contiguous())
+    loss.loss.backward()
+    sae.remove_parallel_grads()
+    gn = boptim.clip_grad_norm_(sae.parameters(), max_norm=1.0)
+    m = loss.metrics()
+    for k in ("mse", "aux", "l0", "loss"):
+        if abs(m[k] - ref_losses[i][k]) > 2e-5 * max(abs(ref_losses[i][k]), 1e-6) + 1e-7:
+            ok = False
+            print(f"[rank {rank}] nn-API step {i} {k}: {m[k]} vs {ref_losses[i][k]}")
+    opt.step()
+    opt.zero_grad()
+sae.normalize_w_dec()  # the engines above renormalised inside the Adam kernel
+errs = {n: rel(a, b) for n, a, b in (("W_enc", sae.W_enc.t(), ref.W_enc_t), ("b_enc", sae.b_enc, ref.b_enc),
+                                     ("W_dec", sae.W_dec, ref.W_dec), ("b_dec", sae.b_dec, ref.b_dec))}
+if max(errs.values()) > 2e-5:
+    ok = False
+if rank == 0:
+    print(f"nn API + data_parallel(): param rel-L2 vs single-GPU {errs}")
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 if rank == 0:

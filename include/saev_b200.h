@@ -185,8 +185,8 @@ int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int
                     float* x_hat_out /* [B, d_model] */, void* stream);
 
 /* Test hook for the tensor-core contraction alone: out[M, N] = A[M, K] . Bt[N, K]^T + bias[N], computed
- * from bf16 copies of the operands (nterms = 1) or the 3-term split product (nterms = 3).
- * scratch must hold 2 * (M + N) * K bf16. */
+ * from bf16 copies of the operands (nterms = 1), the 3-term two-piece split (nterms = 3, ~2^-16 of sum |a b|) or the
+ * 6-term three-piece split (nterms = 6, fp32-class).  scratch must hold 3 * (M + N) * K bf16. */
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream);
 

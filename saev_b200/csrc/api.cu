@@ -27,6 +27,8 @@ struct Workspace {
   // dense (ReLU) path: bf16 (hi, lo) operand pairs
   size_t w_enc_lo, w_dec_hi, w_dec_lo, w_decT_hi, w_decT_lo, x_lo, xT_hi, xT_lo, g_hi, g_lo, gT_hi, gT_lo, f_hi, f_lo,
       fT_hi, fT_lo, dhT_hi, dhT_lo;
+  // third pieces of the same operands (6-term split, fp32-class accuracy)
+  size_t w_enc_l2, w_dec_l2, w_decT_l2, x_l2, xT_l2, g_l2, gT_l2, f_l2, fT_l2, dhT_l2;
   long long ldb = 0;  // row pitch of the batch-major transposed operands (max_batch rounded up to 8)
 };
 
@@ -39,6 +41,8 @@ struct saev_b200_handle {
   int aux_cap = 0;
   int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen (0 => single-CTA kernel)
   int reserved_pairs = 0;  // SM pairs the screen leaves idle (saev_b200_set_reserved_sms)
+  int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
+                           // accuracy), 3 = two pieces (~2^-16 of sum |a b|, half the tensor work); SAEV_B200_DENSE_TERMS
   Workspace ws;
   bool last_forward_training = false;
   bool last_forward_tracked = false;
@@ -75,7 +79,7 @@ int check_cuda(const saev_b200_handle* h, const char* where) {
   return fail(h, 100, "CUDA error at %s", buf);
 }
 
-Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
+Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int dense_terms) {
   Workspace w;
   const size_t S = c.d_sae, D = c.d_model, B = c.max_batch, K = c.top_k;
   size_t o = 0;
@@ -108,6 +112,17 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs) {
     w.fT_lo = take(S * LB * 2);
     w.dhT_hi = take(S * LB * 2);
     w.dhT_lo = take(S * LB * 2);
+    const bool third = dense_terms == 6;
+    w.w_enc_l2 = take(third ? S * D * 2 : 0);
+    w.w_dec_l2 = take(third ? S * D * 2 : 0);
+    w.w_decT_l2 = take(third ? D * S * 2 : 0);
+    w.x_l2 = take(third ? B * D * 2 : 0);
+    w.xT_l2 = take(third ? (D + 16) * LB * 2 : 0);
+    w.g_l2 = take(third ? B * D * 2 : 0);
+    w.gT_l2 = take(third ? D * LB * 2 : 0);
+    w.f_l2 = take(third ? B * S * 2 : 0);
+    w.fT_l2 = take(third ? S * LB * 2 : 0);
+    w.dhT_l2 = take(third ? S * LB * 2 : 0);
   }
   if (relu) {
     w.cand = w.tau_keys = w.cand_cnt = o;
@@ -189,17 +204,20 @@ inline T* at(void* ws, size_t off) {
 }
 
 // Error-compensated bf16 split product on the tcgen05 kernel: out-of-line helper for the dense (ReLU) path.
-EncodeGemmArgs dense_gemm(const saev_b200_handle* h, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, long long lda,
-                          const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, long long ldb, int M, int N, int K,
-                          int epilogue) {
+EncodeGemmArgs dense_gemm(const saev_b200_handle* h, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+                          const __nv_bfloat16* A_l2, long long lda, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo,
+                          const __nv_bfloat16* B_l2, long long ldb, int M, int N, int K, int epilogue) {
   EncodeGemmArgs g;
   g.A_hi = A_hi;
   g.A_lo = A_lo;
+  g.A_lo2 = A_l2;
   g.B_hi = B_hi;
   g.B_lo = B_lo;
+  g.B_lo2 = B_l2;
   g.lda = lda;
   g.ldb = ldb;
-  g.nterms = 3;
+  g.nterms = h->dense_terms;
+  g.k_chunk_blocks = 8;  // 512-wide K chunks: bounds the truncation bias of the tensor-core accumulator (encode_gemm.cu)
   g.M = M;
   g.N = N;
   g.K = K;
@@ -217,14 +235,16 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
   const Workspace& w = h->ws;
   const int D = c.d_model, S = c.d_sae;
   auto bf = [&](size_t off) { return at<__nv_bfloat16>(workspace, off); };
+  const bool third = h->dense_terms == 6;
+  auto b3 = [&](size_t off) { return third ? at<__nv_bfloat16>(workspace, off) : nullptr; };
   const long long SD = static_cast<long long>(S) * D;
   {
     StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
     // operands of this step's contractions from the fp32 master weights (W_dec is already normalised)
-    if (launch_split_bf16(W_enc_t, bf(w.shadow_hi), bf(w.w_enc_lo), SD, s) ||
-        launch_split_bf16(W_dec, bf(w.w_dec_hi), bf(w.w_dec_lo), SD, s) ||
-        launch_transpose_split(W_dec, S, D, 1.f, bf(w.w_decT_hi), bf(w.w_decT_lo), S, 0, D, s) ||
-        launch_split_bf16(x, bf(w.x_hi), bf(w.x_lo), static_cast<long long>(B) * D, s))
+    if (launch_split_bf16(W_enc_t, bf(w.shadow_hi), bf(w.w_enc_lo), SD, s, b3(w.w_enc_l2)) ||
+        launch_split_bf16(W_dec, bf(w.w_dec_hi), bf(w.w_dec_lo), SD, s, b3(w.w_dec_l2)) ||
+        launch_transpose_split(W_dec, S, D, 1.f, bf(w.w_decT_hi), bf(w.w_decT_lo), S, 0, D, s, b3(w.w_decT_l2)) ||
+        launch_split_bf16(x, bf(w.x_hi), bf(w.x_lo), static_cast<long long>(B) * D, s, b3(w.x_l2)))
       return fail(h, 41, "forward(relu): operand split launch failed%s");
     cudaMemsetAsync(at<float>(workspace, w.row_l1), 0, static_cast<size_t>(B) * 4, s);
     cudaMemsetAsync(at<float>(workspace, w.row_l0), 0, static_cast<size_t>(B) * 4, s);
@@ -232,13 +252,16 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
   {
     StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
     // f = relu(x W_enc + b_enc)
-    EncodeGemmArgs g = dense_gemm(h, bf(w.x_hi), bf(w.x_lo), D, bf(w.shadow_hi), bf(w.w_enc_lo), D, B, S, D, 2);
+    EncodeGemmArgs g = dense_gemm(h, bf(w.x_hi), bf(w.x_lo), b3(w.x_l2), D, bf(w.shadow_hi), bf(w.w_enc_lo),
+                                  b3(w.w_enc_l2), D, B, S, D, 2);
     g.bias = b_enc;
     g.f_hi = bf(w.f_hi);
     g.f_lo = bf(w.f_lo);
+    g.f_lo2 = b3(w.f_l2);
     g.ldf = S;
     g.t_hi = training ? bf(w.fT_hi) : nullptr;
     g.t_lo = training ? bf(w.fT_lo) : nullptr;
+    g.t_lo2 = training ? b3(w.fT_l2) : nullptr;
     g.ldt = w.ldb;
     g.row_l1 = at<float>(workspace, w.row_l1);
     g.row_l0 = at<float>(workspace, w.row_l0);
@@ -252,7 +275,8 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
   {
     StageTimer tm(h, SAEV_B200_STAGE_DECODE, s);
     // x_hat = f W_dec + b_dec, then r = x_hat - x, SSE partials and G = 2 r / (B D)
-    EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), S, bf(w.w_decT_hi), bf(w.w_decT_lo), S, B, D, S, 1);
+    EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, bf(w.w_decT_hi), bf(w.w_decT_lo),
+                                  b3(w.w_decT_l2), S, B, D, S, 1);
     g.bias = b_dec;
     g.out = resid;
     g.ldo = D;
@@ -263,9 +287,9 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
     }
     const float gs = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
     if (launch_dense_resid(resid, x, B, D, gs, at<float>(workspace, w.row_sse), training ? bf(w.g_hi) : nullptr,
-                           training ? bf(w.g_lo) : nullptr, s))
+                           training ? bf(w.g_lo) : nullptr, s, training ? b3(w.g_l2) : nullptr))
       return fail(h, 44, "forward(relu): residual launch failed%s");
-    if (training && launch_transpose_split(resid, B, D, gs, bf(w.gT_hi), bf(w.gT_lo), w.ldb, 0, D, s))
+    if (training && launch_transpose_split(resid, B, D, gs, bf(w.gT_hi), bf(w.gT_lo), w.ldb, 0, D, s, b3(w.gT_l2)))
       return fail(h, 44, "forward(relu): G^T launch failed%s");
   }
   return 0;
@@ -278,21 +302,26 @@ int backward_relu(saev_b200_handle* h, const float* x, int B, long long tokens_g
   const Workspace& w = h->ws;
   const int D = c.d_model, S = c.d_sae;
   auto bf = [&](size_t off) { return at<__nv_bfloat16>(workspace, off); };
+  const bool third = h->dense_terms == 6;
+  auto b3 = [&](size_t off) { return third ? at<__nv_bfloat16>(workspace, off) : nullptr; };
   StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
   // dh = (f > 0) * (G W_dec^T + l1 / B), stored transposed as the operand of the W_enc gradient
-  EncodeGemmArgs g3 = dense_gemm(h, bf(w.g_hi), bf(w.g_lo), D, bf(w.w_dec_hi), bf(w.w_dec_lo), D, B, S, D, 3);
+  EncodeGemmArgs g3 = dense_gemm(h, bf(w.g_hi), bf(w.g_lo), b3(w.g_l2), D, bf(w.w_dec_hi), bf(w.w_dec_lo), b3(w.w_dec_l2),
+                                 D, B, S, D, 3);
   g3.f_hi = bf(w.f_hi);
   g3.ldf = S;
   g3.t_hi = bf(w.dhT_hi);
   g3.t_lo = bf(w.dhT_lo);
+  g3.t_lo2 = b3(w.dhT_l2);
   g3.ldt = w.ldb;
   g3.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
   if (launch_encode_gemm(g3, s)) return fail(h, 52, "backward(relu): dh contraction launch failed%s");
   // x^T with an extra row of ones: column D of the next product is sum_b dh = gb_enc
-  if (launch_transpose_split(x, B, D, 1.f, bf(w.xT_hi), bf(w.xT_lo), w.ldb, 1, D + 16, s))
+  if (launch_transpose_split(x, B, D, 1.f, bf(w.xT_hi), bf(w.xT_lo), w.ldb, 1, D + 16, s, b3(w.xT_l2)))
     return fail(h, 52, "backward(relu): x^T launch failed%s");
   // gW_dec = f^T G
-  EncodeGemmArgs g4 = dense_gemm(h, bf(w.fT_hi), bf(w.fT_lo), w.ldb, bf(w.gT_hi), bf(w.gT_lo), w.ldb, S, D, B, 4);
+  EncodeGemmArgs g4 = dense_gemm(h, bf(w.fT_hi), bf(w.fT_lo), b3(w.fT_l2), w.ldb, bf(w.gT_hi), bf(w.gT_lo), b3(w.gT_l2),
+                                 w.ldb, S, D, B, 4);
   g4.out = gW_dec;
   g4.ldo = D;
   g4.n_main = D;
@@ -300,7 +329,8 @@ int backward_relu(saev_b200_handle* h, const float* x, int B, long long tokens_g
   if (c.remove_parallel_grads && launch_project_rows(gW_dec, W_dec, S, D, s))
     return fail(h, 52, "backward(relu): projection launch failed%s");
   // gW_enc_t = dh^T x ; gb_enc = dh^T 1
-  EncodeGemmArgs g5 = dense_gemm(h, bf(w.dhT_hi), bf(w.dhT_lo), w.ldb, bf(w.xT_hi), bf(w.xT_lo), w.ldb, S, D + 1, B, 4);
+  EncodeGemmArgs g5 = dense_gemm(h, bf(w.dhT_hi), bf(w.dhT_lo), b3(w.dhT_l2), w.ldb, bf(w.xT_hi), bf(w.xT_lo),
+                                 b3(w.xT_l2), w.ldb, S, D + 1, B, 4);
   g5.out = gW_enc_t;
   g5.ldo = D;
   g5.n_main = D;
@@ -369,7 +399,11 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     const char* v = getenv("SAEV_B200_ENCODE");  // "1": force the single-CTA screen (A/B comparison)
     h->max_pairs = (v && v[0] == '1') ? 0 : encode2_max_pairs();
   }
-  h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs);
+  {
+    const char* v = getenv("SAEV_B200_DENSE_TERMS");
+    h->dense_terms = (v && v[0] == '3') ? 3 : 6;
+  }
+  h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs, h->dense_terms);
   h->err[0] = 0;
   *out = h;
   return 0;
@@ -913,7 +947,8 @@ int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float*
   if (h->cfg.act_kind == SAEV_B200_ACT_RELU) {
     if (!workspace) return fail(h, 70, "dense_f: the ReLU path needs the workspace%s");
     if (launch_join_bf16(at<__nv_bfloat16>(workspace, h->ws.f_hi), at<__nv_bfloat16>(workspace, h->ws.f_lo),
-                         static_cast<long long>(B) * h->cfg.d_sae, f_x_out, s))
+                         static_cast<long long>(B) * h->cfg.d_sae, f_x_out, s,
+                         h->dense_terms == 6 ? at<__nv_bfloat16>(workspace, h->ws.f_l2) : nullptr))
       return fail(h, 70, "dense_f: launch failed%s");
     return check_cuda(h, "dense_f");
   }
@@ -961,20 +996,25 @@ int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, cons
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (K % 8) return fail(h, 80, "gemm_nt: K must be a multiple of 8%s");
-  if (nterms != 1 && nterms != 3) return fail(h, 80, "gemm_nt: nterms must be 1 or 3%s");
+  if (nterms != 1 && nterms != 3 && nterms != 6) return fail(h, 80, "gemm_nt: nterms must be 1, 3 or 6%s");
   __nv_bfloat16* a_hi = static_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* a_lo = a_hi + static_cast<size_t>(M) * K;
-  __nv_bfloat16* b_hi = a_lo + static_cast<size_t>(M) * K;
+  __nv_bfloat16* a_l2 = a_lo + static_cast<size_t>(M) * K;
+  __nv_bfloat16* b_hi = a_l2 + static_cast<size_t>(M) * K;
   __nv_bfloat16* b_lo = b_hi + static_cast<size_t>(N) * K;
-  if (launch_split_bf16(A, a_hi, a_lo, static_cast<long long>(M) * K, s) ||
-      launch_split_bf16(Bt, b_hi, b_lo, static_cast<long long>(N) * K, s))
+  __nv_bfloat16* b_l2 = b_lo + static_cast<size_t>(N) * K;
+  if (launch_split_bf16(A, a_hi, a_lo, static_cast<long long>(M) * K, s, nterms == 6 ? a_l2 : nullptr) ||
+      launch_split_bf16(Bt, b_hi, b_lo, static_cast<long long>(N) * K, s, nterms == 6 ? b_l2 : nullptr))
     return fail(h, 81, "gemm_nt: split_bf16 launch failed%s");
   EncodeGemmArgs g;
   g.A_hi = a_hi;
   g.A_lo = a_lo;
+  g.A_lo2 = a_l2;
   g.B_hi = b_hi;
   g.B_lo = b_lo;
+  g.B_lo2 = b_l2;
   g.nterms = nterms;
+  g.k_chunk_blocks = nterms == 6 ? 8 : 0;
   g.M = M;
   g.N = N;
   g.K = K;

@@ -13,6 +13,9 @@ __device__ __forceinline__ void split1(float v, __nv_bfloat16& hi, __nv_bfloat16
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+__device__ __forceinline__ __nv_bfloat16 split_third(float v, __nv_bfloat16 hi, __nv_bfloat16 lo) {
+  return __float2bfloat16_rn((v - __bfloat162float(hi)) - __bfloat162float(lo));
+}
 
 // dst_hi/lo[c, r] = split(scale * src[r, c]) for r < R, c < C (dst row pitch ldr).  When ones_row != 0, row C of dst
 // is set to 1.0 (hi) / 0 (lo) over r < R and rows C+1 .. C_pad-1 to zero: the extra "ones" operand row that makes
@@ -20,7 +23,8 @@ __device__ __forceinline__ void split1(float v, __nv_bfloat16& hi, __nv_bfloat16
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, int R, int C, float scale,
                                                               __nv_bfloat16* __restrict__ dst_hi,
                                                               __nv_bfloat16* __restrict__ dst_lo, long long ldr,
-                                                              int ones_row, int C_pad) {
+                                                              int ones_row, int C_pad,
+                                                              __nv_bfloat16* __restrict__ dst_lo2) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -37,6 +41,7 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
         split1(tile[tx][i], h, l);
         dst_hi[static_cast<long long>(c) * ldr + r] = h;
         dst_lo[static_cast<long long>(c) * ldr + r] = l;
+        if (dst_lo2 != nullptr) dst_lo2[static_cast<long long>(c) * ldr + r] = split_third(tile[tx][i], h, l);
       }
     }
   }
@@ -46,16 +51,17 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
       if (r < R) {
         dst_hi[static_cast<long long>(c) * ldr + r] = __float2bfloat16_rn(c == C ? 1.f : 0.f);
         dst_lo[static_cast<long long>(c) * ldr + r] = __float2bfloat16_rn(0.f);
+        if (dst_lo2 != nullptr) dst_lo2[static_cast<long long>(c) * ldr + r] = __float2bfloat16_rn(0.f);
       }
     }
   }
 }
 
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
-                           long long ldr, int ones_row, int C_pad, cudaStream_t s) {
+                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2) {
   if (R <= 0 || C <= 0) return 0;
   dim3 grid((R + 31) / 32, (C + 31) / 32 + (ones_row ? 1 : 0));
-  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad);
+  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad, dst_lo2);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -65,7 +71,8 @@ int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfl
 __global__ void __launch_bounds__(256) dense_resid_kernel(float* __restrict__ xhat, const float* __restrict__ x, int B,
                                                           int D, float grad_scale, float* __restrict__ row_sse,
                                                           __nv_bfloat16* __restrict__ g_hi,
-                                                          __nv_bfloat16* __restrict__ g_lo) {
+                                                          __nv_bfloat16* __restrict__ g_lo,
+                                                          __nv_bfloat16* __restrict__ g_lo2) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -80,6 +87,7 @@ __global__ void __launch_bounds__(256) dense_resid_kernel(float* __restrict__ xh
       split1(r * grad_scale, h, l);
       g_hi[o + d] = h;
       g_lo[o + d] = l;
+      if (g_lo2 != nullptr) g_lo2[o + d] = split_third(r * grad_scale, h, l);
     }
   }
   sse = warp_sum(sse);
@@ -87,8 +95,8 @@ __global__ void __launch_bounds__(256) dense_resid_kernel(float* __restrict__ xh
 }
 
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
-                       __nv_bfloat16* g_lo, cudaStream_t s) {
-  dense_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(xhat, x, B, D, grad_scale, row_sse, g_hi, g_lo);
+                       __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2) {
+  dense_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(xhat, x, B, D, grad_scale, row_sse, g_hi, g_lo, g_lo2);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -121,14 +129,15 @@ int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t 
 }
 
 // f[b, s] = hi + lo   (lazy dense f_x for saev's logging block / evaluate; exact to ~2^-17 relative)
-__global__ void join_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
-                                 float* __restrict__ out) {
+__global__ void join_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                 const __nv_bfloat16* __restrict__ lo2, long long n, float* __restrict__ out) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+    out[i] = __bfloat162float(hi[i]) + (__bfloat162float(lo[i]) + (lo2 ? __bfloat162float(lo2[i]) : 0.f));
 }
-int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s) {
-  join_bf16_kernel<<<148 * 8, 256, 0, s>>>(hi, lo, n, out);
+int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s,
+                     const __nv_bfloat16* lo2) {
+  join_bf16_kernel<<<148 * 8, 256, 0, s>>>(hi, lo, lo2, n, out);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

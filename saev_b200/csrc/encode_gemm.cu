@@ -20,7 +20,8 @@
 // warps 4-7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Pipelines: STAGES-deep smem ring (TMA <-> MMA),
 // 2-deep TMEM accumulator ring (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Operands are K-major bf16 with 128-byte swizzle.  `nterms == 3` runs the error-compensated split product
+// Operands are K-major bf16 with 128-byte swizzle.  `nterms == 6` adds a third piece per operand (hi + lo + lo2 = 24 bits:
+// fp32-class accuracy, terms hi.hi, hi.lo, lo.hi, hi.lo2, lo2.hi, lo.lo).  `nterms == 3` runs the error-compensated split product
 // (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, ~2^-17 relative) by walking three (A,B) tensor-map pairs along K;
 // that mode + the dense-store epilogue are used for the dense (ReLU / AuxK) paths and for testing the
 // contraction itself.
@@ -45,6 +46,8 @@ struct EpiExtra {
   __nv_bfloat16* f_lo;   // EPI 2: out
   __nv_bfloat16* t_hi;   // EPI 2/3: transposed out  [N, ldt]
   __nv_bfloat16* t_lo;
+  __nv_bfloat16* f_lo2;  // optional third pieces (6-term split: value = hi + lo + lo2 to ~2^-24)
+  __nv_bfloat16* t_lo2;
   long long ldf, ldt;
   float* row_l1;         // EPI 2: += sum_cols f
   float* row_l0;         // EPI 2: += count_cols (f > 0)
@@ -166,7 +169,8 @@ template <int EPI, int CAPG, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   int nterms, int kblocks_per_term, const float* __restrict__ bias, int M, int N, int m_blocks,
+                   const __grid_constant__ CUtensorMap tmA_lo2, const __grid_constant__ CUtensorMap tmB_lo2,
+                   int nterms, int kblocks_per_term, int kchunk, const float* __restrict__ bias, int M, int N, int m_blocks,
                    int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int top_k,
                    const float* __restrict__ row_margin, const float* __restrict__ wnorm_sq_max,
                    int2* __restrict__ cand, int* __restrict__ cand_cnt, float* __restrict__ out, long long ldo,
@@ -197,11 +201,20 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int tile_begin = split * tiles_per_split;
   const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
   const int num_tiles = max(0, tile_end - tile_begin);
-  const int kblocks = nterms * kblocks_per_term;
+  // K chunking (dense epilogues 1 / 4): the contraction of one output tile is cut into chunks of `kchunk` k-blocks per
+  // term, each accumulated in its own TMEM stage and added to the fp32 output by the epilogue.  Tensor-core
+  // accumulation truncates (rounds toward zero) at every MMA, a bias that grows linearly with the number of
+  // accumulator updates; short chunks + round-to-nearest fp32 adds keep it at the 1e-5 level for any K.
+  const int n_chunks = (kblocks_per_term + kchunk - 1) / kchunk;
+  const int num_vtiles = num_tiles * n_chunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB_hi);
+    if (nterms > 3) {
+      tma_prefetch_desc(&tmA_lo2);
+      tma_prefetch_desc(&tmB_lo2);
+    }
     if (nterms > 1) {
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
@@ -227,13 +240,16 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < num_tiles; ++t) {
+      for (int vt = 0; vt < num_vtiles; ++vt) {
+        const int t = vt / n_chunks, kc = vt - t * n_chunks;
         const int n0 = (tile_begin + t) * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int term = kb / kblocks_per_term;
-          const int k0 = (kb - term * kblocks_per_term) * BK;
-          const CUtensorMap* ma = (term == 2) ? &tmA_lo : &tmA_hi;
-          const CUtensorMap* mb = (term == 1) ? &tmB_lo : &tmB_hi;
+        const int clen = min(kchunk, kblocks_per_term - kc * kchunk);
+        for (int kb = 0; kb < nterms * clen; ++kb) {
+          const int term = kb / clen;
+          const int k0 = (kc * kchunk + kb - term * clen) * BK;
+          // (A piece, B piece) per term: 0:(hi,hi) 1:(hi,lo) 2:(lo,hi) 3:(hi,lo2) 4:(lo2,hi) 5:(lo,lo)
+          const CUtensorMap* ma = (term == 2 || term == 5) ? &tmA_lo : (term == 4 ? &tmA_lo2 : &tmA_hi);
+          const CUtensorMap* mb = (term == 1 || term == 5) ? &tmB_lo : (term == 3 ? &tmB_lo2 : &tmB_hi);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -252,9 +268,11 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < num_tiles; ++t) {
-        const int as = t & 1;
-        const uint32_t aphase = (t >> 1) & 1u;
+      for (int vt = 0; vt < num_vtiles; ++vt) {
+        const int as = vt & 1;
+        const uint32_t aphase = (vt >> 1) & 1u;
+        const int kc = vt % n_chunks;
+        const int kblocks = nterms * min(kchunk, kblocks_per_term - kc * kchunk);
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -294,16 +312,18 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     float acc_l1 = 0.f, acc_l0 = 0.f;  // EPI 2
 
-    for (int t = 0; t < num_tiles; ++t) {
-      const int as = t & 1;
-      const uint32_t aphase = (t >> 1) & 1u;
+    for (int vt = 0; vt < num_vtiles; ++vt) {
+      const int t = vt / n_chunks;
+      const bool accum = (vt - t * n_chunks) > 0;  // later K chunks of the same output tile are added to it
+      const int as = vt & 1;
+      const uint32_t aphase = (vt >> 1) & 1u;
       const int n0 = (tile_begin + t) * BN;
       float* bs = bias_s + as * BN;
       // Stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below).
       // Columns past the end get -inf in the top-k epilogue so that they can never be admitted.
       for (int c = et; c < BN; c += 128) {
         float bv = (EPI == 0) ? -INFINITY : 0.f;  // (columns past the end are never stored by EPI >= 1)
-        if (n0 + c < n_cols) bv = (bias != nullptr) ? bias[n0 + c] : 0.f;
+        if (n0 + c < n_cols) bv = (bias != nullptr && !accum) ? bias[n0 + c] : 0.f;
         bs[c] = bv;
       }
       named_bar_sync(1, 128);
@@ -364,22 +384,30 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             float* o = out + static_cast<long long>(row) * ldo + col0;
             if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < CHUNK; i += 4)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < CHUNK; i += 4) {
+                float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (accum) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + i);
+                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + i) = w4;
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i)
-                if (col0 + i < n_cols) o[i] = v[i];
+                if (col0 + i < n_cols) o[i] = accum ? o[i] + v[i] : v[i];
             }
           }
         } else if (EPI == 2) {
           const bool rv = row < M;
-          __nv_bfloat16 hi[CHUNK], lo[CHUNK];
+          __nv_bfloat16 hi[CHUNK], lo[CHUNK], lo2[CHUNK];
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) {
             const float f = (rv && col0 + i < n_cols) ? fmaxf(v[i], 0.f) : 0.f;
             hi[i] = __float2bfloat16_rn(f);
-            lo[i] = __float2bfloat16_rn(f - __bfloat162float(hi[i]));
+            const float r1 = f - __bfloat162float(hi[i]);
+            lo[i] = __float2bfloat16_rn(r1);
+            lo2[i] = __float2bfloat16_rn(r1 - __bfloat162float(lo[i]));
             acc_l1 += f;
             acc_l0 += (f > 0.f) ? 1.f : 0.f;
             const bool fired = __any_sync(FULL, f > 0.f);
@@ -393,12 +421,18 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               *reinterpret_cast<uint4*>(fh + 8) = *reinterpret_cast<const uint4*>(&hi[8]);
               *reinterpret_cast<uint4*>(fl) = *reinterpret_cast<const uint4*>(&lo[0]);
               *reinterpret_cast<uint4*>(fl + 8) = *reinterpret_cast<const uint4*>(&lo[8]);
+              if (ex.f_lo2 != nullptr) {
+                __nv_bfloat16* f2 = ex.f_lo2 + static_cast<long long>(row) * ex.ldf + col0;
+                *reinterpret_cast<uint4*>(f2) = *reinterpret_cast<const uint4*>(&lo2[0]);
+                *reinterpret_cast<uint4*>(f2 + 8) = *reinterpret_cast<const uint4*>(&lo2[8]);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i)
                 if (col0 + i < n_cols) {
                   fh[i] = hi[i];
                   fl[i] = lo[i];
+                  if (ex.f_lo2 != nullptr) ex.f_lo2[static_cast<long long>(row) * ex.ldf + col0 + i] = lo2[i];
                 }
             }
             if (ex.t_hi != nullptr) {
@@ -407,6 +441,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 if (col0 + i < n_cols) {
                   ex.t_hi[static_cast<long long>(col0 + i) * ex.ldt + row] = hi[i];
                   ex.t_lo[static_cast<long long>(col0 + i) * ex.ldt + row] = lo[i];
+                  if (ex.t_lo2 != nullptr) ex.t_lo2[static_cast<long long>(col0 + i) * ex.ldt + row] = lo2[i];
                 }
             }
           }
@@ -426,8 +461,12 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               if (col0 + i < n_cols) {
                 const float d = (__bfloat162float(fh[i]) > 0.f) ? v[i] + ex.l1_over_b : 0.f;
                 const __nv_bfloat16 h = __float2bfloat16_rn(d);
+                const float r1 = d - __bfloat162float(h);
+                const __nv_bfloat16 l = __float2bfloat16_rn(r1);
                 ex.t_hi[static_cast<long long>(col0 + i) * ex.ldt + row] = h;
-                ex.t_lo[static_cast<long long>(col0 + i) * ex.ldt + row] = __float2bfloat16_rn(d - __bfloat162float(h));
+                ex.t_lo[static_cast<long long>(col0 + i) * ex.ldt + row] = l;
+                if (ex.t_lo2 != nullptr)
+                  ex.t_lo2[static_cast<long long>(col0 + i) * ex.ldt + row] = __float2bfloat16_rn(r1 - __bfloat162float(l));
               }
             }
           }
@@ -436,13 +475,19 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             float* o = out + static_cast<long long>(row) * ldo + col0;
             if (col0 + CHUNK <= ex.n_main && (ldo & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < CHUNK; i += 4)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < CHUNK; i += 4) {
+                float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (accum) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + i);
+                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + i) = w4;
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i) {
-                if (col0 + i < ex.n_main) o[i] = v[i];
-                else if (col0 + i == ex.n_main && ex.extra != nullptr) ex.extra[row] = v[i];
+                if (col0 + i < ex.n_main) o[i] = accum ? o[i] + v[i] : v[i];
+                else if (col0 + i == ex.n_main && ex.extra != nullptr) ex.extra[row] = accum ? ex.extra[row] + v[i] : v[i];
               }
             }
           }
@@ -548,10 +593,14 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
   const int kblocks_per_term = (a.K + BK - 1) / BK;
   EpiExtra ex;
   ex.f_hi = a.f_hi; ex.f_lo = a.f_lo; ex.t_hi = a.t_hi; ex.t_lo = a.t_lo; ex.ldf = a.ldf; ex.ldt = a.ldt;
+  ex.f_lo2 = a.f_lo2; ex.t_lo2 = a.t_lo2;
   ex.row_l1 = a.row_l1; ex.row_l0 = a.row_l0; ex.active = a.active; ex.l1_over_b = a.l1_over_b;
   ex.n_main = a.n_main; ex.extra = a.extra;
-  kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], a.nterms,
-                                                           kblocks_per_term, a.bias, a.M, a.N, m_blocks,
+  // K chunking only where the epilogue can add partial results (dense store / weight gradient); 8 k-blocks = 512
+  // bf16 per term per chunk
+  const int kchunk = ((EPI == 1 || EPI == 4) && a.k_chunk_blocks > 0) ? a.k_chunk_blocks : kblocks_per_term;
+  kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a.nterms,
+                                                           kblocks_per_term, kchunk, a.bias, a.M, a.N, m_blocks,
                                                            tiles_per_split, nsplit, a.n_limit_dev, a.top_k,
                                                            a.row_margin, a.wnorm_sq_max,
                                                            reinterpret_cast<int2*>(a.cand), a.cand_cnt, a.out, a.ldo, ex);
@@ -576,12 +625,20 @@ int encode_gemm_max_top_k() { return ENCODE_CAPG / 4; }
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return 0;
   if (a.lda <= 0 && a.ldb <= 0 && (a.K % 8) != 0) return 10;  // TMA needs 16-byte aligned row pitch
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];
   const long long lda = a.lda > 0 ? a.lda : a.K, ldb = a.ldb > 0 ? a.ldb : a.K;
   if ((lda % 8) != 0 || (ldb % 8) != 0) return 10;
   if (make_tmap_bf16(&maps[0], a.A_hi, a.M, a.K, lda, BM)) return 11;
   if (make_tmap_bf16(&maps[2], a.B_hi, a.N, a.K, ldb, BN)) return 11;
-  if (a.nterms == 3) {
+  if (a.nterms == 6) {
+    if (!a.A_lo2 || !a.B_lo2) return 12;
+    if (make_tmap_bf16(&maps[4], a.A_lo2, a.M, a.K, lda, BM)) return 11;
+    if (make_tmap_bf16(&maps[5], a.B_lo2, a.N, a.K, ldb, BN)) return 11;
+  } else {
+    maps[4] = maps[0];
+    maps[5] = maps[2];
+  }
+  if (a.nterms >= 3) {
     if (make_tmap_bf16(&maps[1], a.A_lo, a.M, a.K, lda, BM)) return 11;
     if (make_tmap_bf16(&maps[3], a.B_lo, a.N, a.K, ldb, BN)) return 11;
   } else {

@@ -20,9 +20,13 @@ struct EncodeGemmArgs {
   const __nv_bfloat16* A_lo = nullptr;  // residual part, nterms == 3 only
   const __nv_bfloat16* B_hi = nullptr;  // [N, K] row-major (K contiguous)
   const __nv_bfloat16* B_lo = nullptr;
-  int nterms = 1;                       // 1: A_hi.B_hi    3: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+  const __nv_bfloat16* A_lo2 = nullptr; // third pieces, nterms == 6 only
+  const __nv_bfloat16* B_lo2 = nullptr;
+  int nterms = 1;                       // 1: A_hi.B_hi    3: + A_hi.B_lo + A_lo.B_hi    6: + A_hi.B_lo2 + A_lo2.B_hi + A_lo.B_lo
   int M = 0, N = 0, K = 0;
   long long lda = 0, ldb = 0;           // row pitch of A / B in elements (0 = K); must be multiples of 8
+  int k_chunk_blocks = 0;               // epilogues 1 / 4: accumulate K in chunks of this many 64-wide k-blocks per term
+                                        // (partial results added in fp32 by the epilogue); 0 = one chunk
   const float* bias = nullptr;          // [N] or null
   const int* n_limit_dev = nullptr;     // optional device-side column count (<= N)
   int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store, 2: ReLU forward,
@@ -31,6 +35,8 @@ struct EncodeGemmArgs {
   __nv_bfloat16* f_lo = nullptr;        // epilogue 2: bf16 residual
   __nv_bfloat16* t_hi = nullptr;        // epilogue 2/3: transposed bf16 hi/lo outputs [N, ldt]
   __nv_bfloat16* t_lo = nullptr;
+  __nv_bfloat16* f_lo2 = nullptr;       // optional third pieces (written when non-null)
+  __nv_bfloat16* t_lo2 = nullptr;
   long long ldf = 0, ldt = 0;
   float* row_l1 = nullptr;              // epilogue 2: [M] += sum f   (caller zeroes)
   float* row_l0 = nullptr;              // epilogue 2: [M] += count f > 0
@@ -69,7 +75,8 @@ int encode_gemm_nsplit(int M, int N, int num_sms);
 int encode_gemm_max_top_k();
 
 // ---- sparse_kernels.cu ----------------------------------------------------------------------------------
-int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s);
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
+                      __nv_bfloat16* lo2 = nullptr);
 // x[B,D] -> bf16 copy + per-row admission margin factor  c * ||x_b||_inf   (see encode_gemm.cu)
 int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s);
 // *out = max_j ||W[j,:]||^2
@@ -177,11 +184,12 @@ int launch_add_rows(const float* a, const float* b, long long n, float* out, cud
 
 // ---- dense_kernels.cu (ReLU / dense path) ----------------------------------------------------------------
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
-                           long long ldr, int ones_row, int C_pad, cudaStream_t s);
+                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2 = nullptr);
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
-                       __nv_bfloat16* g_lo, cudaStream_t s);
+                       __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2 = nullptr);
 int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t s);
-int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s);
+int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s,
+                     const __nv_bfloat16* lo2 = nullptr);
 
 // ---- aux_kernels.cu -------------------------------------------------------------------------------------
 struct AuxArgs {

@@ -41,7 +41,7 @@ __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
 // fp32 -> bf16 (hi) [+ bf16 residual (lo)]   (operand prep for the tensor-core screen)
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+                                  __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2_out, long long n4) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = ldg4(src + 4 * i);
@@ -56,18 +56,29 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
                               __float2bfloat16_rn(v.y - __bfloat162float(h1)));
       lo2[1] = __nv_bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)),
                               __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+      if (lo2_out != nullptr) {  // third piece: what hi + lo still miss
+        const float r[4] = {v.x - __bfloat162float(h0), v.y - __bfloat162float(h1), v.z - __bfloat162float(h2),
+                            v.w - __bfloat162float(h3)};
+        const __nv_bfloat162 l01 = lo2[0], l23 = lo2[1];
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(lo2_out + 4 * i);
+        o[0] = __nv_bfloat162(__float2bfloat16_rn(r[0] - __bfloat162float(l01.x)),
+                              __float2bfloat16_rn(r[1] - __bfloat162float(l01.y)));
+        o[1] = __nv_bfloat162(__float2bfloat16_rn(r[2] - __bfloat162float(l23.x)),
+                              __float2bfloat16_rn(r[3] - __bfloat162float(l23.y)));
+      }
     }
   }
 }
 
-int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s) {
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
+                      __nv_bfloat16* lo2) {
   if (n <= 0) return 0;
   if (n % 4) return 21;
   const long long n4 = n / 4;
   const int threads = 256;
   long long want = (n4 + threads - 1) / threads;
   const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
-  split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, n4);
+  split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, lo2, n4);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -346,7 +346,7 @@ class Engine:
         M, K = A.shape
         N = Bt.shape[0]
         out = torch.empty(M, N, dtype=torch.float32, device=self.device)
-        scratch = torch.empty(2 * (M + N) * K, dtype=torch.bfloat16, device=self.device)
+        scratch = torch.empty(3 * (M + N) * K, dtype=torch.bfloat16, device=self.device)
         with torch.cuda.device(self.device):
             self._ck(
                 self.lib.saev_b200_gemm_nt(

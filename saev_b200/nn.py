@@ -206,8 +206,8 @@ class Output:
         if "h_x" not in self._cache:
             self._check()
             eng = self._sae.engine
-            # dense pre-activations through the 3-term split tensor-core product (~5e-6 relative)
-            self._cache["h_x"] = eng.gemm_nt(self._x, eng.W_enc_t, eng.b_enc, 3)
+            # dense pre-activations through the 6-term (three-piece) split tensor-core product (fp32-class accuracy)
+            self._cache["h_x"] = eng.gemm_nt(self._x, eng.W_enc_t, eng.b_enc, 6)
         return self._cache["h_x"]
 
     def __iter__(self):  # NamedTuple-style unpacking: h_x, f_x, x_hats
@@ -351,7 +351,7 @@ class SparseAutoencoder(torch.nn.Module):
             raise NotImplementedError("Matryoshka prefix decoding (n_prefixes > 1) has no CUDA path in saev_b200")
         eng = self._bind(f_x.shape[0])
         # x_hat = f_x . W_dec + b_dec  ==  gemm_nt(f_x, W_dec^T) ; W_dec^T [D, S] is materialised once per call
-        return eng.gemm_nt(f_x.contiguous(), eng.W_dec.t().contiguous(), eng.b_dec, 3)[:, None, :]
+        return eng.gemm_nt(f_x.contiguous(), eng.W_dec.t().contiguous(), eng.b_dec, 6)[:, None, :]
 
     @torch.no_grad()
     def normalize_w_dec(self):

@@ -67,7 +67,10 @@ thread_local char g_err[512] = "";
 
 int fail(const saev_b200_handle* h, int code, const char* fmt, const char* detail = "") {
   char* dst = h ? h->err : g_err;
-  snprintf(dst, 512, fmt, detail);
+  const int n = snprintf(dst, 400, fmt, detail);
+  // a failed launch usually has a CUDA error behind it: say which (and clear it, it has been reported)
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess && n > 0 && n < 400) snprintf(dst + n, 512 - n, " [CUDA: %s]", cudaGetErrorString(e));
   return code;
 }
 
@@ -198,6 +201,10 @@ struct StageTimer {
   }
 };
 
+// PyTorch runs backward passes on autograd worker threads where no CUDA context may be current yet; the driver-API
+// tensor-map encoder (unlike runtime launches) needs one.  cudaSetDevice binds the primary context to this thread.
+inline void bind_context(const saev_b200_handle* h) { cudaSetDevice(h->device); }
+
 template <typename T>
 inline T* at(void* ws, size_t off) {
   return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
@@ -315,7 +322,11 @@ int backward_relu(saev_b200_handle* h, const float* x, int B, long long tokens_g
   g3.t_lo2 = b3(w.dhT_l2);
   g3.ldt = w.ldb;
   g3.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
-  if (launch_encode_gemm(g3, s)) return fail(h, 52, "backward(relu): dh contraction launch failed%s");
+  if (int rc = launch_encode_gemm(g3, s)) {
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%d", rc);
+    return fail(h, 52, "backward(relu): dh contraction launch failed (code %s)", buf);
+  }
   // x^T with an extra row of ones: column D of the next product is sum_b dh = gb_enc
   if (launch_transpose_split(x, B, D, 1.f, bf(w.xT_hi), bf(w.xT_lo), w.ldb, 1, D + 16, s, b3(w.xT_l2)))
     return fail(h, 52, "backward(relu): x^T launch failed%s");
@@ -482,6 +493,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
                       int64_t* toks_since_active, int32_t training, int32_t* topk_idx, float* topk_val,
                       float* resid, float* losses, void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
   const saev_b200_cfg& c = h->cfg;
   const Workspace& w = h->ws;
   if (B <= 0 || B > c.max_batch) return fail(h, 40, "forward: B out of range (0 < B <= cfg.max_batch)%s");
@@ -770,6 +782,7 @@ int saev_b200_backward(saev_b200_handle* h, const float* x, int32_t B, int64_t t
                        const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
                        float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
   const saev_b200_cfg& c = h->cfg;
   if (!h->last_forward_training) return fail(h, 50, "backward: the last forward was not a training forward%s");
   if (B <= 0 || B > c.max_batch) return fail(h, 40, "backward: B out of range%s");
@@ -797,6 +810,8 @@ int saev_b200_backward_stage(saev_b200_handle* h, int32_t stage, int32_t row_beg
                              const int32_t* topk_idx, const float* topk_val, const float* resid, float* gW_enc_t,
                              float* gb_enc, float* gW_dec, float* gb_dec, void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
+  bind_context(h);
   const saev_b200_cfg& c = h->cfg;
   if (c.act_kind != SAEV_B200_ACT_TOPK) return fail(h, 55, "backward_stage: TopK path only%s");
   if (!h->last_forward_training) return fail(h, 50, "backward_stage: the last forward was not a training forward%s");
@@ -995,6 +1010,7 @@ int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
   if (K % 8) return fail(h, 80, "gemm_nt: K must be a multiple of 8%s");
   if (nterms != 1 && nterms != 3 && nterms != 6) return fail(h, 80, "gemm_nt: nterms must be 1, 3 or 6%s");
   __nv_bfloat16* a_hi = static_cast<__nv_bfloat16*>(scratch);

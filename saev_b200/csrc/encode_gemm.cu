@@ -25,6 +25,8 @@
 // (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, ~2^-17 relative) by walking three (A,B) tensor-map pairs along K;
 // that mode + the dense-store epilogue are used for the dense (ReLU / AuxK) paths and for testing the
 // contraction itself.
+#include <stdio.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -72,6 +74,12 @@ __host__ __device__ inline EncodeSmemLayout encode_smem_layout(int stages) {
   o = L.off_bars + (2 * stages + 4) * 8 + 16;
   L.total = o + 1024;  // slack for the manual 1024-byte alignment of the dynamic smem base
   return L;
+}
+
+// fire-and-forget fp32 vector add to global memory (performed by the L2 with round-to-nearest): how the epilogue
+// folds the K chunks of one output tile together without a read-modify-write round trip
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // order-preserving map float -> uint32 (larger float <=> larger key) and back
@@ -385,17 +393,16 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 4) {
-                float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (accum) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + i);
-                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o + i) = w4;
+                if (accum) red_add_f32x4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                else *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i)
-                if (col0 + i < n_cols) o[i] = accum ? o[i] + v[i] : v[i];
+                if (col0 + i < n_cols) {
+                  if (accum) atomicAdd(o + i, v[i]);
+                  else o[i] = v[i];
+                }
             }
           }
         } else if (EPI == 2) {
@@ -476,18 +483,19 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (col0 + CHUNK <= ex.n_main && (ldo & 3) == 0) {
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 4) {
-                float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (accum) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + i);
-                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o + i) = w4;
+                if (accum) red_add_f32x4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                else *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < CHUNK; ++i) {
-                if (col0 + i < ex.n_main) o[i] = accum ? o[i] + v[i] : v[i];
-                else if (col0 + i == ex.n_main && ex.extra != nullptr) ex.extra[row] = accum ? ex.extra[row] + v[i] : v[i];
+                if (col0 + i < ex.n_main) {
+                  if (accum) atomicAdd(o + i, v[i]);
+                  else o[i] = v[i];
+                } else if (col0 + i == ex.n_main && ex.extra != nullptr) {
+                  if (accum) atomicAdd(ex.extra + row, v[i]);
+                  else ex.extra[row] = v[i];
+                }
               }
             }
           }
@@ -575,6 +583,9 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, lon
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "saev_b200: cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d\n",
+            static_cast<int>(r), ptr, rows, cols, ld_elems, box_rows);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 

@@ -28,10 +28,14 @@ namespace sb {
 namespace g2 {
 
 constexpr int BM = 128;        // rows per CTA (pair: 256 = UMMA M)
-constexpr int BN = 256;        // dictionary columns per tile (UMMA N)
+#ifndef SB_G2_BN
+#define SB_G2_BN 256
+#endif
+constexpr int BN = SB_G2_BN;   // dictionary columns per tile (UMMA N): 256 (2 accumulator stages) or 128 (4 stages)
+constexpr int ACC = 512 / BN;  // TMEM accumulator stages (512 columns of TMEM per SM)
 constexpr int BK = 64;         // bf16 per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int STAGES = BN == 256 ? 6 : 8;
 constexpr int A_BYTES = BM * BK * 2;         // 16 KB: this CTA's rows
 constexpr int B_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the tile's columns
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -44,10 +48,10 @@ constexpr int CAPG = ENCODE2_CAPG;             // entries per candidate list
 constexpr int TRIGGER_MAX = CAPG - HALF;        // a list above this could not absorb a whole further tile
 
 constexpr size_t OFF_BIAS = static_cast<size_t>(STAGES) * STAGE_BYTES;            // [8 warps][2 acc stages][128] f32
-constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * 2 * HALF * 4;  // [2 halves][128 rows] f32
+constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * ACC * HALF * 4;  // [2 halves][128 rows] f32
 constexpr size_t OFF_HIST = OFF_TAU + 2 * BM * 4;                                    // [8 warps][256] i32
 constexpr size_t OFF_BARS = OFF_HIST + static_cast<size_t>(EPI_WARPS) * 256 * 4;
-constexpr size_t SMEM_TOTAL = OFF_BARS + (2 * STAGES + 4) * 8 + 16 + 1024;
+constexpr size_t SMEM_TOTAL = OFF_BARS + (2 * STAGES + 2 * ACC) * 8 + 16 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -279,8 +283,8 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_BARS + (2 * STAGES + 4) * 8);
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC + s); };
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + OFF_BARS + (2 * STAGES + 2 * ACC) * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,7 +302,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ACC; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 2 * EPI_WARPS);
     }
@@ -343,8 +347,8 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       const long long n_steps = t_end - t_begin;
       for (long long tc = 0; tc < n_steps; ++tc) {
-        const int as = static_cast<int>(tc & 1);
-        const uint32_t aphase = static_cast<uint32_t>(tc >> 1) & 1u;
+        const int as = static_cast<int>(tc % ACC);
+        const uint32_t aphase = static_cast<uint32_t>(tc / ACC) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -396,18 +400,20 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       unsigned int* my_tau_g = p.tau_g + (row - lane) + lane;  // == p.tau_g + row (rows are padded to 256)
       for (int n = nb; n < ne; ++n, ++tc) {
-        const int as = static_cast<int>(tc & 1);
-        const uint32_t aphase = static_cast<uint32_t>(tc >> 1) & 1u;
+        const int as = static_cast<int>(tc % ACC);
+        const uint32_t aphase = static_cast<uint32_t>(tc / ACC) & 1u;
         const int n0 = n * BN + half * HALF;
-        float* bs = bias_s + (w * 2 + as) * HALF;
+        float* bs = bias_s + (w * ACC + as) * HALF;
         {  // warp-private bias slice; columns past the end get -inf so that they can never be admitted
-          float4 bv;
-          const int c = n0 + lane * 4;
-          bv.x = (c + 0 < p.N) ? __ldg(p.bias + c + 0) : -INFINITY;
-          bv.y = (c + 1 < p.N) ? __ldg(p.bias + c + 1) : -INFINITY;
-          bv.z = (c + 2 < p.N) ? __ldg(p.bias + c + 2) : -INFINITY;
-          bv.w = (c + 3 < p.N) ? __ldg(p.bias + c + 3) : -INFINITY;
-          *reinterpret_cast<float4*>(bs + lane * 4) = bv;
+          if (lane * 4 < HALF) {
+            float4 bv;
+            const int c = n0 + lane * 4;
+            bv.x = (c + 0 < p.N) ? __ldg(p.bias + c + 0) : -INFINITY;
+            bv.y = (c + 1 < p.N) ? __ldg(p.bias + c + 1) : -INFINITY;
+            bv.z = (c + 2 < p.N) ? __ldg(p.bias + c + 2) : -INFINITY;
+            bv.w = (c + 3 < p.N) ? __ldg(p.bias + c + 3) : -INFINITY;
+            *reinterpret_cast<float4*>(bs + lane * 4) = bv;
+          }
         }
         // thresholds other warps / other CTA pairs have already proven for this row (its other column ranges)
         const unsigned int gkey = __ldcg(my_tau_g);

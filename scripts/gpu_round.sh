@@ -13,6 +13,6 @@ tail -3 gpurun_out/ncu_bench.log | cut -c1-300
 fi
 if [ "${NCUFULL:-0}" = "1" ]; then
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:encode_gemm -s 3 -c 2 -o gpurun_out/prof_encode -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"encode_gemm2_kernel|wgrad_kernel|rescore_topk_kernel|decode_kernel|adam_rows_kernel" -s 15 -c 5 -o gpurun_out/prof_step_final -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log | cut -c1-300
 fi

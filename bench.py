@@ -200,9 +200,10 @@ def make_bench_shards(D, B, n_batches, rank):
     return root
 
 
-def workload_name(w, D, S, K, B):
+def workload_name(w, D, S, K, B, n_prefixes=1):
     act = f"TopK k={K}" if K else "ReLU + L1Sparsity(4e-4)"
-    return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective MSE+AuxK(k_aux=512, alpha=1/32, "
+    mat = f"Matryoshka({n_prefixes} prefixes) " if n_prefixes > 1 else ""
+    return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective {mat}MSE+AuxK(k_aux=512, alpha=1/32, "
             f"dead_threshold=10M tokens), remove_parallel_grads, clip 1.0, Adam, lr warmup; Gaussian activations")
 
 
@@ -219,6 +220,8 @@ def main():
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap"],
                     help="gradient exchange for N > 1 (see saev_b200/parallel.py)")
+    ap.add_argument("--n-prefixes", type=int, default=1,
+                    help="Matryoshka prefixes (1 = the north-star objective; 10 = saev's default objective)")
     ap.add_argument("--gather-ctas", type=int, default=16)
     ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
@@ -257,7 +260,8 @@ def main():
 
     eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation="topk" if K else "relu",
                               l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
-                              dead_threshold_tokens=10_000_000, max_batch=B), device=dev)
+                              dead_threshold_tokens=10_000_000, max_batch=B, max_prefixes=max(1, args.n_prefixes)),
+                 device=dev)
     eng.init_params(seed=0)
     if args.dp_mode == "auto":
         # measured on B200 (profiles/README.md): at 2 ranks the chunked all-reduce hidden behind the weight-gradient
@@ -290,6 +294,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     lib = _lib.load()
+    if args.n_prefixes > 1:
+        # saev draws new cuts every step on the host (objectives.py:125); one fixed draw keeps the benchmark repeatable
+        import torch as _t
+
+        from saev_b200.nn import sample_prefixes
+
+        _t.manual_seed(0)
+        eng.set_prefixes(sample_prefixes(S, args.n_prefixes).tolist())
     gstep = 0
     for _ in range(args.warmup):
         tr.step(x_dev[gstep % NB], lr_at(gstep))
@@ -434,7 +446,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload_name(args.workload, D, S, K, B),
+                "workload": workload_name(args.workload, D, S, K, B, args.n_prefixes),
                 "global_batch": world * B,
                 "parallelism": f"dp{world}" + (f" ({args.dp_mode} gradient exchange)" if world > 1 else ""),
                 "precision": ("bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "

@@ -517,7 +517,7 @@ int launch_decode(const DecodeArgs& a, cudaStream_t s) {
 // One warp per row; K <= 64 (two top-k slots per lane).
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, PrefixCuts pf, float* __restrict__ sfx) {
+__global__ void __launch_bounds__(256, 2) decode_prefix_kernel(DecodeArgs a, PrefixCuts pf, float* __restrict__ sfx) {
   __shared__ int order_s[8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
@@ -556,13 +556,12 @@ __global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, Prefix
   }
   __syncwarp();
 
-  float4 acc[VPL], xr[VPL];
-  const float* xrow = a.x + static_cast<long long>(b) * a.D;
+  float4 acc[VPL];
+  const float* xrow = a.x + static_cast<long long>(b) * a.D;  // re-read (L1) at every cut instead of held in registers
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     acc[i] = (v < D4) ? ldg4(a.b_dec + 4 * v) : make_float4(0, 0, 0, 0);
-    xr[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
   }
   float* srow = sfx + static_cast<long long>(b) * P * a.D;
   float sse = 0.f;
@@ -573,8 +572,9 @@ __global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, Prefix
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < D4) {
+        const float4 xv = ldg4(xrow + 4 * v);
         float4 r = acc[i];
-        r.x -= xr[i].x; r.y -= xr[i].y; r.z -= xr[i].z; r.w -= xr[i].w;
+        r.x -= xv.x; r.y -= xv.y; r.z -= xv.z; r.w -= xv.w;
         *reinterpret_cast<float4*>(o + 4 * v) = r;
         part += dot4(r, r);
       }
@@ -582,22 +582,43 @@ __global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, Prefix
     sse += part;
   };
   int cur = 0;
-  for (int t = 0; t < K; ++t) {
-    const int k = order[t];
+  // slot -> (column, value) of the t-th active in ascending column order (empty slots sort last)
+  auto entry = [&](int t, int& j, float& f) {
+    const int k = order[min(t, K - 1)];
     const int j0 = __shfl_sync(FULL, mj[0], k & 31), j1 = __shfl_sync(FULL, mj[1], k & 31);
     const float f0 = __shfl_sync(FULL, mf[0], k & 31), f1 = __shfl_sync(FULL, mf[1], k & 31);
-    const int j = (k < 32) ? j0 : j1;
-    const float f = (k < 32) ? f0 : f1;
-    if (j < 0) break;  // empty slots sort last
-    while (cur < P - 1 && j >= pf.cut[cur]) {
-      emit(cur);
-      ++cur;
-    }
-    const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+    j = (t < K) ? ((k < 32) ? j0 : j1) : -1;
+    f = (k < 32) ? f0 : f1;
+  };
+  // two dictionary rows per round, all 2 x VPL loads issued before the first FMA (gather latency, see decode_kernel)
+  for (int t = 0; t < K; t += 2) {
+    int ja, jb;
+    float fa, fb;
+    entry(t, ja, fa);
+    entry(t + 1, jb, fb);
+    if (ja < 0) break;
+    const float* r0 = a.W_dec + static_cast<long long>(ja) * a.D;
+    const float* r1 = a.W_dec + static_cast<long long>(max(jb, 0)) * a.D;
+    float4 w0[VPL], w1[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < D4) fma4(acc[i], f, ldg4(wrow + 4 * v));
+      w0[i] = (v < D4) ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
+      w1[i] = (v < D4 && jb >= 0) ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
+    }
+    while (cur < P - 1 && ja >= pf.cut[cur]) {
+      emit(cur);
+      ++cur;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) fma4(acc[i], fa, w0[i]);
+    if (jb >= 0) {
+      while (cur < P - 1 && jb >= pf.cut[cur]) {
+        emit(cur);
+        ++cur;
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) fma4(acc[i], fb, w1[i]);
     }
   }
   while (cur < P) {
@@ -611,8 +632,9 @@ __global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, Prefix
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < D4) {
+        const float4 xv = ldg4(xrow + 4 * v);
         float4 r = acc[i];
-        r.x -= xr[i].x; r.y -= xr[i].y; r.z -= xr[i].z; r.w -= xr[i].w;
+        r.x -= xv.x; r.y -= xv.y; r.z -= xv.z; r.w -= xv.w;
         *reinterpret_cast<float4*>(rrow + 4 * v) = r;
       }
     }
@@ -643,37 +665,46 @@ __global__ void __launch_bounds__(256) decode_prefix_kernel(DecodeArgs a, Prefix
   if (a.dh == nullptr) return;
   // dh_k = grad_scale * <sfx[c(j_k)], W_dec[j_k]>  (acc holds sfx[0] now; reload when the block changes)
   cur = 0;
-  for (int t = 0; t < K; ++t) {
-    const int k = order[t];
-    const int j0 = __shfl_sync(FULL, mj[0], k & 31), j1 = __shfl_sync(FULL, mj[1], k & 31);
-    const float f0 = __shfl_sync(FULL, mf[0], k & 31), f1 = __shfl_sync(FULL, mf[1], k & 31);
-    const int j = (k < 32) ? j0 : j1;
-    const float f = (k < 32) ? f0 : f1;
-    float d = 0.f;
-    if (j >= 0) {
-      int c = cur;
-      while (c < P - 1 && j >= pf.cut[c]) ++c;
-      if (c != cur) {
-        cur = c;
-        const float* o = srow + static_cast<long long>(c) * a.D;
+  for (int t = 0; t < K; t += 2) {
+    int jj[2];
+    float ff[2];
+    entry(t, jj[0], ff[0]);
+    entry(t + 1, jj[1], ff[1]);
+    float4 w0[VPL], w1[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-          const int v = lane + 32 * i;
-          if (v < D4) acc[i] = *reinterpret_cast<const float4*>(o + 4 * v);
-        }
-      }
-      const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
-      float p = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < D4) p += dot4(acc[i], ldg4(wrow + 4 * v));
-      }
-      p = warp_sum(p);
-      d = a.grad_scale * p;
-      if (a.l1_over_b != 0.f) d += a.l1_over_b * ((f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f));
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      w0[i] = (v < D4 && jj[0] >= 0) ? ldg4(a.W_dec + static_cast<long long>(jj[0]) * a.D + 4 * v) : make_float4(0, 0, 0, 0);
+      w1[i] = (v < D4 && jj[1] >= 0) ? ldg4(a.W_dec + static_cast<long long>(jj[1]) * a.D + 4 * v) : make_float4(0, 0, 0, 0);
     }
-    if (lane == 0) a.dh[kb + k] = d;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t + u >= K) break;
+      const int j = jj[u];
+      float d = 0.f;
+      if (j >= 0) {
+        int c = cur;
+        while (c < P - 1 && j >= pf.cut[c]) ++c;
+        if (c != cur) {  // the walk entered a new prefix block: its suffix sum replaces the one in registers
+          cur = c;
+          const float* o = srow + static_cast<long long>(c) * a.D;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < D4) acc[i] = *reinterpret_cast<const float4*>(o + 4 * v);
+          }
+        }
+        float pdot = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) pdot += dot4(acc[i], u == 0 ? w0[i] : w1[i]);
+        pdot = warp_sum(pdot);
+        d = a.grad_scale * pdot;
+        const float f = ff[u];
+        if (a.l1_over_b != 0.f) d += a.l1_over_b * ((f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f));
+      }
+      const int k = order[t + u];
+      if (lane == 0) a.dh[kb + k] = d;
+    }
   }
 }
 

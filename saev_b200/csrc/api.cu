@@ -24,6 +24,10 @@ struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
+  // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
+  size_t tc_we[3], tc_wd[3], tc_wdT[3], tc_x[3], tc_xT[3], tc_f[3], tc_fT[3], tc_r[3], tc_rT[3];
+  long long ldc = 0;
+  bool aux_tc = false;
   // dense (ReLU) path: bf16 (hi, lo) operand pairs
   size_t w_enc_lo, w_dec_hi, w_dec_lo, w_decT_hi, w_decT_lo, x_lo, xT_hi, xT_lo, g_hi, g_lo, gT_hi, gT_lo, f_hi, f_lo,
       fT_hi, fT_lo, dhT_hi, dhT_lo;
@@ -174,6 +178,23 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.mask_aux = take(B * static_cast<size_t>(aux_cap));
     w.r_aux = take(B * D * 4);
     w.aux_colpart = take(aux_colpart_bytes(aux_cap));
+    const char* e = getenv("SAEV_B200_AUX");  // "sgemm": the fp32 CUDA-core tiles (debug / comparison)
+    w.aux_tc = !(e && e[0] == 's');
+    w.ldc = (static_cast<long long>(aux_cap) + 63) / 64 * 64;
+    if (w.aux_tc) {
+      const size_t CAP = static_cast<size_t>(aux_cap), LC = static_cast<size_t>(w.ldc), LB = static_cast<size_t>(w.ldb);
+      for (int i = 0; i < 3; ++i) {
+        w.tc_we[i] = take(CAP * D * 2);
+        w.tc_wd[i] = take(CAP * D * 2);
+        w.tc_wdT[i] = take(D * LC * 2);
+        w.tc_x[i] = take(B * D * 2);
+        w.tc_xT[i] = take(D * LB * 2);
+        w.tc_f[i] = take(B * LC * 2);
+        w.tc_fT[i] = take(CAP * LB * 2);
+        w.tc_r[i] = take(B * D * 2);
+        w.tc_rT[i] = take(D * LB * 2);
+      }
+    }
   } else {
     w.h_aux = w.mask_aux = w.r_aux = w.aux_colpart = o;
   }
@@ -208,6 +229,27 @@ inline void bind_context(const saev_b200_handle* h) { cudaSetDevice(h->device); 
 template <typename T>
 inline T* at(void* ws, size_t off) {
   return reinterpret_cast<T*>(static_cast<char*>(ws) + off);
+}
+
+// piece buffers / settings of the tensor-core AuxK path
+void fill_aux_tc(const saev_b200_handle* h, void* workspace, AuxArgs& a) {
+  const Workspace& w = h->ws;
+  a.nterms = h->dense_terms;
+  a.num_sms = h->num_sms;
+  a.ldb = w.ldb;
+  a.ldc = w.ldc;
+  for (int i = 0; i < 3; ++i) {
+    auto p = [&](const size_t (&off)[3]) { return w.aux_tc ? at<__nv_bfloat16>(workspace, off[i]) : nullptr; };
+    a.tc_we[i] = p(w.tc_we);
+    a.tc_wd[i] = p(w.tc_wd);
+    a.tc_wdT[i] = p(w.tc_wdT);
+    a.tc_x[i] = p(w.tc_x);
+    a.tc_xT[i] = p(w.tc_xT);
+    a.tc_f[i] = p(w.tc_f);
+    a.tc_fT[i] = p(w.tc_fT);
+    a.tc_r[i] = p(w.tc_r);
+    a.tc_rT[i] = p(w.tc_rT);
+  }
 }
 
 // Error-compensated bf16 split product on the tcgen05 kernel: out-of-line helper for the dense (ReLU) path.
@@ -645,6 +687,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
         a.gb_dec = nullptr;
         a.aux_colpart = at<float>(workspace, w.aux_colpart);
         a.row_gsq = nullptr;
+        fill_aux_tc(h, workspace, a);
         if (launch_aux_forward(a, s)) return fail(h, 46, "forward: AuxK launch failed%s");
         aux_live = true;
       }
@@ -768,6 +811,7 @@ int bwd_bias_aux(const BwdCtx& c) {
     a.gb_dec = c.gb_dec;
     a.aux_colpart = at<float>(c.workspace, w.aux_colpart);
     a.row_gsq = cf.act_kind == SAEV_B200_ACT_TOPK ? at<float>(c.workspace, w.row_gsq) : nullptr;
+    fill_aux_tc(h, c.workspace, a);
     if (launch_aux_backward(a, c.s)) return fail(h, 54, "backward: AuxK launch failed%s");
   }
   return 0;

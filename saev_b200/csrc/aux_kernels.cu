@@ -364,9 +364,255 @@ __global__ void __launch_bounds__(256) aux_rows_gsq_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Operand preparation for the tensor-core AuxK path: bf16 (hi, lo, lo2) pieces of everything the five n_dead-wide
+// contractions read, in K-major layout.  Sizes come from device memory (n_dead), grids are fixed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+  p0 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r1);
+  p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+}
+
+// rows of W[S, D] listed in dead_list -> pieces [cap, D] (row i = atom dead_list[i])
+__global__ void __launch_bounds__(256) aux_gather_rows_kernel(const float* __restrict__ W, const int* __restrict__ dead_list,
+                                                              const int* __restrict__ n_dead_p, int D,
+                                                              __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
+                                                              __nv_bfloat16* __restrict__ p2) {
+  const int n = *n_dead_p;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const float* src = W + static_cast<long long>(dead_list[i]) * D;
+    const long long o = static_cast<long long>(i) * D;
+    for (int d = lane; d < D; d += 32) {
+      __nv_bfloat16 a, b, c;
+      split3(__ldg(src + d), a, b, c);
+      p0[o + d] = a;
+      p1[o + d] = b;
+      p2[o + d] = c;
+    }
+  }
+}
+
+// W[dead_list[i], d] -> pieces T[d, i] ([D, ldc]); columns n .. roundup64(n) are zero-filled (they sit inside the last
+// k-block of a contraction over the dead latents)
+__global__ void __launch_bounds__(256) aux_gather_rows_T_kernel(const float* __restrict__ W, const int* __restrict__ dead_list,
+                                                                const int* __restrict__ n_dead_p, int D, long long ldc,
+                                                                __nv_bfloat16* __restrict__ p0, __nv_bfloat16* __restrict__ p1,
+                                                                __nv_bfloat16* __restrict__ p2) {
+  __shared__ float tile[32][33];
+  const int n = *n_dead_p;
+  const int n_pad = (n + 63) / 64 * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int d_tiles = (D + 31) / 32;
+  for (long long blk = blockIdx.x; blk < static_cast<long long>((n_pad + 31) / 32) * d_tiles; blk += gridDim.x) {
+    const int i0 = static_cast<int>(blk / d_tiles) * 32, d0 = static_cast<int>(blk % d_tiles) * 32;
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r, d = d0 + tx;
+      tile[r][tx] = (i < n && d < D) ? __ldg(W + static_cast<long long>(dead_list[i]) * D + d) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int d = d0 + r, i = i0 + tx;
+      if (d < D && i < n_pad) {
+        __nv_bfloat16 a, b, c;
+        split3(tile[tx][r], a, b, c);
+        const long long o = static_cast<long long>(d) * ldc + i;
+        p0[o] = a;
+        p1[o] = b;
+        p2[o] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// src[B, ld] (fp32, first n columns valid) -> row-major pieces [B, ldc] (optional; columns n .. roundup64(n) zero)
+// and transposed pieces T[i, b] ([cap, ldb], rows i < n)
+__global__ void __launch_bounds__(256) aux_split_cols_kernel(const float* __restrict__ src, long long ld, int B,
+                                                             const int* __restrict__ n_dead_p, long long ldc, long long ldb,
+                                                             __nv_bfloat16* __restrict__ r0, __nv_bfloat16* __restrict__ r1,
+                                                             __nv_bfloat16* __restrict__ r2, __nv_bfloat16* __restrict__ t0,
+                                                             __nv_bfloat16* __restrict__ t1, __nv_bfloat16* __restrict__ t2) {
+  __shared__ float tile[32][33];
+  const int n = *n_dead_p;
+  const int n_pad = (n + 63) / 64 * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c_tiles = (n_pad + 31) / 32, b_tiles = (B + 31) / 32;
+  for (long long blk = blockIdx.x; blk < static_cast<long long>(c_tiles) * b_tiles; blk += gridDim.x) {
+    const int b0 = static_cast<int>(blk / c_tiles) * 32, c0 = static_cast<int>(blk % c_tiles) * 32;
+    for (int r = ty; r < 32; r += 8) {
+      const int b = b0 + r, c = c0 + tx;
+      const float val = (b < B && c < n) ? src[static_cast<long long>(b) * ld + c] : 0.f;
+      tile[r][tx] = val;
+      if (r0 != nullptr && b < B && c < n_pad) {
+        __nv_bfloat16 p, q, s;
+        split3(val, p, q, s);
+        const long long o = static_cast<long long>(b) * ldc + c;
+        r0[o] = p;
+        r1[o] = q;
+        r2[o] = s;
+      }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int c = c0 + r, b = b0 + tx;
+      if (c < n && b < B) {
+        __nv_bfloat16 p, q, s;
+        split3(tile[tx][r], p, q, s);
+        const long long o = static_cast<long long>(c) * ldb + b;
+        t0[o] = p;
+        t1[o] = q;
+        t2[o] = s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// zero the gradient rows of the dead atoms (the K-split weight-gradient contractions add into them)
+__global__ void __launch_bounds__(256) aux_zero_rows_kernel(float* __restrict__ g0, float* __restrict__ g1,
+                                                            const int* __restrict__ dead_list,
+                                                            const int* __restrict__ n_dead_p, int D) {
+  const int n = *n_dead_p;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const long long o = static_cast<long long>(dead_list[i]) * D;
+    for (int d = lane; d < D; d += 32) {
+      g0[o + d] = 0.f;
+      g1[o + d] = 0.f;
+    }
+  }
+}
+
 size_t aux_colpart_bytes(int cap) { return static_cast<size_t>(AUX_SLABS) * cap * 4; }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core path: the five n_dead-wide contractions as bf16 split products on the tcgen05 kernel of encode_gemm.cu
+// (dynamic row / column / contraction limits read from device memory).  Measured need: with the fp32 CUDA-core
+// tiles 2 k dead latents already cost 16 ms per step at c3, 32 k cost 210 ms.
+// ------------------------------------------------------------------------------------------------
+static EncodeGemmArgs aux_gemm(const AuxArgs& a, __nv_bfloat16* const A[3], long long lda, __nv_bfloat16* const Bp[3],
+                               long long ldb, int M, int N, int K, int epilogue) {
+  EncodeGemmArgs g;
+  g.A_hi = A[0];
+  g.A_lo = A[1];
+  g.A_lo2 = A[2];
+  g.B_hi = Bp[0];
+  g.B_lo = Bp[1];
+  g.B_lo2 = Bp[2];
+  g.lda = lda;
+  g.ldb = ldb;
+  g.nterms = a.nterms;
+  g.k_chunk_blocks = 8;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epilogue = epilogue;
+  g.nsplit = 0;
+  g.num_sms = a.num_sms;
+  return g;
+}
+
+static int launch_aux_forward_tc(const AuxArgs& a, cudaStream_t s) {
+  const long long ld = a.S;
+  const int cap = a.S;
+  aux_gather_rows_kernel<<<148 * 4, 256, 0, s>>>(a.W_enc_t, a.dead_list, a.n_dead, a.D, a.tc_we[0], a.tc_we[1], a.tc_we[2]);
+  aux_gather_rows_kernel<<<148 * 4, 256, 0, s>>>(a.W_dec, a.dead_list, a.n_dead, a.D, a.tc_wd[0], a.tc_wd[1], a.tc_wd[2]);
+  aux_gather_rows_T_kernel<<<148 * 8, 256, 0, s>>>(a.W_dec, a.dead_list, a.n_dead, a.D, a.ldc, a.tc_wdT[0], a.tc_wdT[1],
+                                                   a.tc_wdT[2]);
+  g_launch_count += 3;
+  if (launch_split_bf16(a.x, a.tc_x[0], a.tc_x[1], static_cast<long long>(a.B) * a.D, s, a.tc_x[2])) return 22;
+  // h_L = x . W_enc_t[L]^T   (the bias is added by the selection kernel)
+  EncodeGemmArgs g = aux_gemm(a, a.tc_x, a.D, a.tc_we, a.D, a.B, cap, a.D, 1);
+  g.n_limit_dev = a.n_dead;
+  g.out = a.h_aux;
+  g.ldo = ld;
+  if (launch_encode_gemm(g, s)) return 22;
+  aux_select_kernel<<<min(a.B, 148 * 8), 256, 0, s>>>(a.h_aux, a.mask_aux, ld, a.b_enc, a.dead_list, a.n_dead, a.B,
+                                                       a.k_aux);
+  ++g_launch_count;
+  // f_aux as operand pieces: row-major for the decode, transposed for gW_dec
+  aux_split_cols_kernel<<<148 * 8, 256, 0, s>>>(a.h_aux, ld, a.B, a.n_dead, a.ldc, a.ldb, a.tc_f[0], a.tc_f[1], a.tc_f[2],
+                                                a.tc_fT[0], a.tc_fT[1], a.tc_fT[2]);
+  ++g_launch_count;
+  // x_aux (without bias) = f_aux . W_dec[L]   (contraction over the dead latents: dynamic K)
+  EncodeGemmArgs d = aux_gemm(a, a.tc_f, a.ldc, a.tc_wdT, a.ldc, a.B, a.D, static_cast<int>(a.ldc), 1);
+  d.k_limit_dev = a.n_dead;
+  d.out = a.r_aux;
+  d.ldo = a.D;
+  if (launch_encode_gemm(d, s)) return 22;
+  aux_resid_kernel<<<min((a.B + 7) / 8, 148 * 8), 256, 0, s>>>(a.r_aux, a.resid, a.b_dec, a.B, a.D, a.n_dead,
+                                                                a.row_sse_aux);
+  ++g_launch_count;
+  aux_loss_kernel<<<1, 1024, 0, s>>>(a.row_sse_aux, a.B, a.alpha, a.inv_bd, a.aux_loss);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+static int launch_aux_backward_tc(const AuxArgs& a, cudaStream_t s) {
+  const long long ld = a.S;
+  const int cap = a.S;
+  const float gscale = 2.f * a.alpha * a.inv_bd;
+  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s)) return 22;
+  if (launch_split_bf16(a.r_aux, a.tc_r[0], a.tc_r[1], static_cast<long long>(a.B) * a.D, s, a.tc_r[2]) ||
+      launch_transpose_split(a.r_aux, a.B, a.D, 1.f, a.tc_rT[0], a.tc_rT[1], a.ldb, 0, a.D, s, a.tc_rT[2]) ||
+      launch_transpose_split(a.x, a.B, a.D, 1.f, a.tc_xT[0], a.tc_xT[1], a.ldb, 0, a.D, s, a.tc_xT[2]))
+    return 22;
+  // The two weight-gradient contractions run over K = B with as few as one 128-row block of output when only a
+  // handful of latents is dead: their K chunks are spread over 8 CTAs per tile, adding into zeroed rows.
+  aux_zero_rows_kernel<<<148 * 2, 256, 0, s>>>(a.gW_dec, a.gW_enc_t, a.dead_list, a.n_dead, a.D);
+  ++g_launch_count;
+  const int n_tiles_d = (a.D + 255) / 256;
+  // gW_dec[L] = gscale * f_aux^T r_aux, scattered to the rows of the dead atoms
+  EncodeGemmArgs g = aux_gemm(a, a.tc_fT, a.ldb, a.tc_rT, a.ldb, cap, a.D, a.B, 4);
+  g.ksplit = 8;
+  g.nsplit = n_tiles_d;
+  g.m_limit_dev = a.n_dead;
+  g.row_map = a.dead_list;
+  g.out = a.gW_dec;
+  g.ldo = a.D;
+  g.n_main = a.D;
+  g.alpha = gscale;
+  if (launch_encode_gemm(g, s)) return 22;
+  if (a.remove_parallel) {
+    aux_project_kernel<<<148 * 4, 256, 0, s>>>(a.gW_dec, a.W_dec, a.dead_list, a.n_dead, a.D);
+    ++g_launch_count;
+  }
+  // dh_a = mask_a * gscale * (r_aux . W_dec[L]^T)   (overwrites f_aux)
+  EncodeGemmArgs e = aux_gemm(a, a.tc_r, a.D, a.tc_wd, a.D, a.B, cap, a.D, 1);
+  e.n_limit_dev = a.n_dead;
+  e.out = a.h_aux;
+  e.ldo = ld;
+  e.alpha = gscale;
+  if (launch_encode_gemm(e, s)) return 22;
+  aux_mask_colsum_kernel<<<dim3(148, AUX_SLABS), 256, 0, s>>>(a.h_aux, a.mask_aux, ld, a.B, a.n_dead, a.aux_colpart);
+  ++g_launch_count;
+  aux_colsum_final_kernel<<<148, 256, 0, s>>>(a.aux_colpart, ld, a.dead_list, a.n_dead, a.gb_enc);
+  ++g_launch_count;
+  aux_split_cols_kernel<<<148 * 8, 256, 0, s>>>(a.h_aux, ld, a.B, a.n_dead, a.ldc, a.ldb, nullptr, nullptr, nullptr,
+                                                a.tc_fT[0], a.tc_fT[1], a.tc_fT[2]);
+  ++g_launch_count;
+  // gW_enc_t[L] = dh_a^T x
+  EncodeGemmArgs w = aux_gemm(a, a.tc_fT, a.ldb, a.tc_xT, a.ldb, cap, a.D, a.B, 4);
+  w.ksplit = 8;
+  w.nsplit = n_tiles_d;
+  w.m_limit_dev = a.n_dead;
+  w.row_map = a.dead_list;
+  w.out = a.gW_enc_t;
+  w.ldo = a.D;
+  w.n_main = a.D;
+  if (launch_encode_gemm(w, s)) return 22;
+  if (a.row_gsq != nullptr) {
+    aux_rows_gsq_kernel<<<148 * 2, 256, 0, s>>>(a.gW_dec, a.gW_enc_t, a.gb_enc, a.dead_list, a.n_dead, a.D, a.row_gsq);
+    ++g_launch_count;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 int launch_aux_forward(const AuxArgs& a, cudaStream_t s) {
+  if (a.tc_we[0] != nullptr) return launch_aux_forward_tc(a, s);
   const long long ld = a.S;  // leading dimension of the [B, cap] scratch matrices
   SgemmArgs g{};
   // h_L = x . W_enc_t[L]^T
@@ -398,6 +644,7 @@ int launch_aux_forward(const AuxArgs& a, cudaStream_t s) {
 }
 
 int launch_aux_backward(const AuxArgs& a, cudaStream_t s) {
+  if (a.tc_we[0] != nullptr) return launch_aux_backward_tc(a, s);
   const long long ld = a.S;
   const float gscale = 2.f * a.alpha * a.inv_bd;
   // gb_dec += sum_b G_a      (r_aux is all zeros when nothing is dead)

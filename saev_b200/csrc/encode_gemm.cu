@@ -57,6 +57,11 @@ struct EpiExtra {
   float l1_over_b;       // EPI 3
   int n_main;            // EPI 4
   float* extra;          // EPI 4: [M]
+  const int* m_limit_dev;  // optional device-side row count (<= M) and contraction length (<= K): the AuxK path
+  const int* k_limit_dev;  // works on the dead latents, whose number the host never reads
+  const int* row_map;      // EPI 4: output row index of accumulator row r (scatter into the full gradient)
+  float alpha;             // EPI 1 / 4: scale of the accumulator
+  int ksplit;              // EPI 1 / 4: CTAs sharing the K chunks of one output tile (>= 1)
 };
 
 struct EncodeSmemLayout {
@@ -202,9 +207,14 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int lane = threadIdx.x & 31;
 
   const int m_blk = blockIdx.x % m_blocks;
-  const int split = blockIdx.x / m_blocks;
+  const int split = (blockIdx.x / m_blocks) % nsplit;
+  const int ks = blockIdx.x / (m_blocks * nsplit);  // K split (dense epilogues 1 / 4 with RED accumulation)
   // The column count may live on the device (AuxK dead-latent list whose length the host never reads).
   const int n_cols = n_limit_dev ? min(N, *n_limit_dev) : N;
+  if (ex.m_limit_dev != nullptr) M = min(M, *ex.m_limit_dev);
+  if (ex.k_limit_dev != nullptr) kblocks_per_term = min(kblocks_per_term, (*ex.k_limit_dev + BK - 1) / BK);
+  // nothing to do (no dead latents / rows past the dynamic row count): leave before any barrier or TMEM is touched
+  if (n_cols <= 0 || kblocks_per_term <= 0 || (blockIdx.x % m_blocks) * BM >= M) return;
   const int n_tiles_total = (n_cols + BN - 1) / BN;
   const int tile_begin = split * tiles_per_split;
   const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
@@ -213,7 +223,12 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   // term, each accumulated in its own TMEM stage and added to the fp32 output by the epilogue.  Tensor-core
   // accumulation truncates (rounds toward zero) at every MMA, a bias that grows linearly with the number of
   // accumulator updates; short chunks + round-to-nearest fp32 adds keep it at the 1e-5 level for any K.
-  const int n_chunks = (kblocks_per_term + kchunk - 1) / kchunk;
+  const int n_chunks_all = (kblocks_per_term + kchunk - 1) / kchunk;
+  // with ex.ksplit > 1 the chunks of one output tile are spread over ksplit CTAs, all of which ADD into a
+  // pre-zeroed output (the contraction is long and the tile count small: AuxK weight gradients of a few dead atoms)
+  const int chunks_per_ks = (n_chunks_all + ex.ksplit - 1) / ex.ksplit;
+  const int chunk_begin = ks * chunks_per_ks;
+  const int n_chunks = max(0, min(n_chunks_all, chunk_begin + chunks_per_ks) - chunk_begin);
   const int num_vtiles = num_tiles * n_chunks;
 
   if (threadIdx.x == 0) {
@@ -249,7 +264,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int vt = 0; vt < num_vtiles; ++vt) {
-        const int t = vt / n_chunks, kc = vt - t * n_chunks;
+        const int t = vt / n_chunks, kc = chunk_begin + vt - t * n_chunks;
         const int n0 = (tile_begin + t) * BN;
         const int clen = min(kchunk, kblocks_per_term - kc * kchunk);
         for (int kb = 0; kb < nterms * clen; ++kb) {
@@ -279,7 +294,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       for (int vt = 0; vt < num_vtiles; ++vt) {
         const int as = vt & 1;
         const uint32_t aphase = (vt >> 1) & 1u;
-        const int kc = vt % n_chunks;
+        const int kc = chunk_begin + vt % n_chunks;
         const int kblocks = nterms * min(kchunk, kblocks_per_term - kc * kchunk);
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -322,7 +337,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
     for (int vt = 0; vt < num_vtiles; ++vt) {
       const int t = vt / n_chunks;
-      const bool accum = (vt - t * n_chunks) > 0;  // later K chunks of the same output tile are added to it
+      // later K chunks of the same output tile are added to it; with a K split every chunk is added (pre-zeroed output)
+      const bool accum = (vt - t * n_chunks) > 0 || ex.ksplit > 1;
       const int as = vt & 1;
       const uint32_t aphase = (vt >> 1) & 1u;
       const int n0 = (tile_begin + t) * BN;
@@ -331,7 +347,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // Columns past the end get -inf in the top-k epilogue so that they can never be admitted.
       for (int c = et; c < BN; c += 128) {
         float bv = (EPI == 0) ? -INFINITY : 0.f;  // (columns past the end are never stored by EPI >= 1)
-        if (n0 + c < n_cols) bv = (bias != nullptr && !accum) ? bias[n0 + c] : 0.f;
+        if (n0 + c < n_cols) bv = (bias != nullptr && !accum && ks == 0) ? bias[n0 + c] : 0.f;
         bs[c] = bv;
       }
       named_bar_sync(1, 128);
@@ -351,6 +367,10 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           v[i + 1] = __uint_as_float(a[i + 1]) + b4.y;
           v[i + 2] = __uint_as_float(a[i + 2]) + b4.z;
           v[i + 3] = __uint_as_float(a[i + 3]) + b4.w;
+        }
+        if (EPI == 1 || EPI == 4) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) v[i] *= ex.alpha;
         }
         if (EPI == 0) {
           // fast path: one compare of the chunk maximum against the row's admission threshold
@@ -479,7 +499,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
         } else {  // EPI == 4
           if (row < M) {
-            float* o = out + static_cast<long long>(row) * ldo + col0;
+            const long long orow = ex.row_map != nullptr ? ex.row_map[row] : row;
+            float* o = out + orow * ldo + col0;
             if (col0 + CHUNK <= ex.n_main && (ldo & 3) == 0) {
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 4) {
@@ -493,8 +514,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                   if (accum) atomicAdd(o + i, v[i]);
                   else o[i] = v[i];
                 } else if (col0 + i == ex.n_main && ex.extra != nullptr) {
-                  if (accum) atomicAdd(ex.extra + row, v[i]);
-                  else ex.extra[row] = v[i];
+                  if (accum) atomicAdd(ex.extra + orow, v[i]);
+                  else ex.extra[orow] = v[i];
                 }
               }
             }
@@ -607,10 +628,12 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
   ex.f_lo2 = a.f_lo2; ex.t_lo2 = a.t_lo2;
   ex.row_l1 = a.row_l1; ex.row_l0 = a.row_l0; ex.active = a.active; ex.l1_over_b = a.l1_over_b;
   ex.n_main = a.n_main; ex.extra = a.extra;
+  ex.m_limit_dev = a.m_limit_dev; ex.k_limit_dev = a.k_limit_dev; ex.row_map = a.row_map; ex.alpha = a.alpha;
+  ex.ksplit = ((EPI == 1 || EPI == 4) && a.ksplit > 1 && a.k_chunk_blocks > 0) ? a.ksplit : 1;
   // K chunking only where the epilogue can add partial results (dense store / weight gradient); 8 k-blocks = 512
   // bf16 per term per chunk
   const int kchunk = ((EPI == 1 || EPI == 4) && a.k_chunk_blocks > 0) ? a.k_chunk_blocks : kblocks_per_term;
-  kern<<<m_blocks * nsplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a.nterms,
+  kern<<<m_blocks * nsplit * ex.ksplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a.nterms,
                                                            kblocks_per_term, kchunk, a.bias, a.M, a.N, m_blocks,
                                                            tiles_per_split, nsplit, a.n_limit_dev, a.top_k,
                                                            a.row_margin, a.wnorm_sq_max,

@@ -29,6 +29,12 @@ struct EncodeGemmArgs {
                                         // (partial results added in fp32 by the epilogue); 0 = one chunk
   const float* bias = nullptr;          // [N] or null
   const int* n_limit_dev = nullptr;     // optional device-side column count (<= N)
+  const int* m_limit_dev = nullptr;     // optional device-side row count (<= M)          (dense epilogues)
+  const int* k_limit_dev = nullptr;     // optional device-side contraction length (<= K; operands zero beyond it)
+  const int* row_map = nullptr;         // epilogue 4: output row of accumulator row r
+  float alpha = 1.f;                    // epilogues 1 / 4: out = alpha * (acc + bias)
+  int ksplit = 1;                       // epilogues 1 / 4 with k_chunk_blocks > 0: spread the K chunks of one output tile
+                                        // over this many CTAs, all adding into a PRE-ZEROED output (bias must be null)
   int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store, 2: ReLU forward,
                                         // 3: ReLU backward, 4: weight gradient (see encode_gemm.cu)
   __nv_bfloat16* f_hi = nullptr;        // epilogue 2 (out) / 3 (in): relu(h) as bf16 hi [M, ldf]
@@ -207,6 +213,20 @@ struct AuxArgs {
   float* colsum_partial; float* gb_dec;            // gb_dec += sum_b G_aux
   float* aux_colpart;      // [32, S] scratch for the gb_enc column sums
   float* row_gsq;          // optional [d_sae]: refreshed for the dead atoms whose gradient rows are overwritten
+  // tensor-core path (null tc_we[0] => the fp32 CUDA-core tiles): bf16 piece buffers, 3 pieces each
+  int nterms;              // 3 or 6
+  int num_sms;
+  long long ldb;           // row pitch of the batch-major transposed operands (>= B, multiple of 8)
+  long long ldc;           // row pitch of the [B, cap] piece matrices (cap rounded up to 64)
+  __nv_bfloat16* tc_we[3];   // W_enc_t[L]      [cap, D]
+  __nv_bfloat16* tc_wd[3];   // W_dec[L]        [cap, D]
+  __nv_bfloat16* tc_wdT[3];  // W_dec[L]^T      [D, ldc]
+  __nv_bfloat16* tc_x[3];    // x               [B, D]
+  __nv_bfloat16* tc_xT[3];   // x^T             [D, ldb]
+  __nv_bfloat16* tc_f[3];    // f_aux           [B, ldc]
+  __nv_bfloat16* tc_fT[3];   // f_aux^T, later dh_aux^T   [cap, ldb]
+  __nv_bfloat16* tc_r[3];    // r_aux           [B, D]
+  __nv_bfloat16* tc_rT[3];   // r_aux^T         [D, ldb]
 };
 int launch_aux_forward(const AuxArgs& a, cudaStream_t s);
 int launch_aux_backward(const AuxArgs& a, cudaStream_t s);

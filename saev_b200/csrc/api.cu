@@ -45,6 +45,14 @@ struct saev_b200_handle {
   int aux_cap = 0;
   int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen (0 => single-CTA kernel)
   int reserved_pairs = 0;  // SM pairs the screen leaves idle (saev_b200_set_reserved_sms)
+  // AuxK path selection: the dead-latent count of an EARLIER step, read back asynchronously (never waited for).  Both
+  // AuxK implementations are correct for any count; the lagged value only picks the cheaper one (the tensor-core
+  // path launches worst-case grids, ~0.2 ms per step of empty CTAs when nothing is dead).
+  int* nd_host = nullptr;        // pinned
+  cudaEvent_t nd_event = nullptr;
+  bool nd_pending = false;
+  int n_dead_lagged = 0;
+  bool aux_tc_step = false;      // path chosen by the last forward (backward must match)
   int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
                            // accuracy), 3 = two pieces (~2^-16 of sum |a b|, half the tensor work); SAEV_B200_DENSE_TERMS
   Workspace ws;
@@ -239,7 +247,7 @@ void fill_aux_tc(const saev_b200_handle* h, void* workspace, AuxArgs& a) {
   a.ldb = w.ldb;
   a.ldc = w.ldc;
   for (int i = 0; i < 3; ++i) {
-    auto p = [&](const size_t (&off)[3]) { return w.aux_tc ? at<__nv_bfloat16>(workspace, off[i]) : nullptr; };
+    auto p = [&](const size_t (&off)[3]) { return h->aux_tc_step ? at<__nv_bfloat16>(workspace, off[i]) : nullptr; };
     a.tc_we[i] = p(w.tc_we);
     a.tc_wd[i] = p(w.tc_wd);
     a.tc_wdT[i] = p(w.tc_wdT);
@@ -457,12 +465,21 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     h->dense_terms = (v && v[0] == '3') ? 3 : 6;
   }
   h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs, h->dense_terms);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&h->nd_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->nd_event, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    h->nd_host = nullptr;  // selection falls back to "always tensor-core"
+  } else {
+    *h->nd_host = 0;
+  }
   h->err[0] = 0;
   *out = h;
   return 0;
 }
 
 int saev_b200_destroy(saev_b200_handle* h) {
+  if (h && h->nd_host) cudaFreeHost(h->nd_host);
+  if (h && h->nd_event) cudaEventDestroy(h->nd_event);
   if (h && h->prof_beg) {
     for (int i = 0; i < saev_b200_handle::PROF_CAP; ++i) {
       if (h->prof_beg[i]) cudaEventDestroy(h->prof_beg[i]);
@@ -660,6 +677,20 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
                              at<int>(workspace, w.block_totals), s))
         return fail(h, 45, "forward: dead tracker launch failed%s");
       h->last_forward_tracked = true;
+      if (h->nd_host != nullptr) {
+        if (h->nd_pending && cudaEventQuery(h->nd_event) == cudaSuccess) {
+          h->n_dead_lagged = *h->nd_host;
+          h->nd_pending = false;
+        } else {
+          cudaGetLastError();  // cudaErrorNotReady is not an error
+        }
+        if (!h->nd_pending) {
+          cudaMemcpyAsync(h->nd_host, scal_i, sizeof(int), cudaMemcpyDeviceToHost, s);
+          cudaEventRecord(h->nd_event, s);
+          h->nd_pending = true;
+        }
+      }
+      h->aux_tc_step = w.aux_tc && (h->nd_host == nullptr || h->n_dead_lagged > 32);
       if (c.aux_kind == SAEV_B200_AUX_AUXK) {
         AuxArgs a;
         a.x = x;

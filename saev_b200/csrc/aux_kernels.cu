@@ -523,7 +523,7 @@ static int launch_aux_forward_tc(const AuxArgs& a, cudaStream_t s) {
   aux_gather_rows_T_kernel<<<148 * 8, 256, 0, s>>>(a.W_dec, a.dead_list, a.n_dead, a.D, a.ldc, a.tc_wdT[0], a.tc_wdT[1],
                                                    a.tc_wdT[2]);
   g_launch_count += 3;
-  if (launch_split_bf16(a.x, a.tc_x[0], a.tc_x[1], static_cast<long long>(a.B) * a.D, s, a.tc_x[2])) return 22;
+  if (launch_split_bf16(a.x, a.tc_x[0], a.tc_x[1], static_cast<long long>(a.B) * a.D, s, a.tc_x[2], a.n_dead)) return 22;
   // h_L = x . W_enc_t[L]^T   (the bias is added by the selection kernel)
   EncodeGemmArgs g = aux_gemm(a, a.tc_x, a.D, a.tc_we, a.D, a.B, cap, a.D, 1);
   g.n_limit_dev = a.n_dead;
@@ -556,9 +556,9 @@ static int launch_aux_backward_tc(const AuxArgs& a, cudaStream_t s) {
   const int cap = a.S;
   const float gscale = 2.f * a.alpha * a.inv_bd;
   if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s)) return 22;
-  if (launch_split_bf16(a.r_aux, a.tc_r[0], a.tc_r[1], static_cast<long long>(a.B) * a.D, s, a.tc_r[2]) ||
-      launch_transpose_split(a.r_aux, a.B, a.D, 1.f, a.tc_rT[0], a.tc_rT[1], a.ldb, 0, a.D, s, a.tc_rT[2]) ||
-      launch_transpose_split(a.x, a.B, a.D, 1.f, a.tc_xT[0], a.tc_xT[1], a.ldb, 0, a.D, s, a.tc_xT[2]))
+  if (launch_split_bf16(a.r_aux, a.tc_r[0], a.tc_r[1], static_cast<long long>(a.B) * a.D, s, a.tc_r[2], a.n_dead) ||
+      launch_transpose_split(a.r_aux, a.B, a.D, 1.f, a.tc_rT[0], a.tc_rT[1], a.ldb, 0, a.D, s, a.tc_rT[2], a.n_dead) ||
+      launch_transpose_split(a.x, a.B, a.D, 1.f, a.tc_xT[0], a.tc_xT[1], a.ldb, 0, a.D, s, a.tc_xT[2], a.n_dead))
     return 22;
   // The two weight-gradient contractions run over K = B with as few as one 128-row block of output when only a
   // handful of latents is dead: their K chunks are spread over 8 CTAs per tile, adding into zeroed rows.

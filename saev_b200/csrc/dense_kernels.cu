@@ -24,8 +24,10 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ dst_hi,
                                                               __nv_bfloat16* __restrict__ dst_lo, long long ldr,
                                                               int ones_row, int C_pad,
-                                                              __nv_bfloat16* __restrict__ dst_lo2) {
+                                                              __nv_bfloat16* __restrict__ dst_lo2,
+                                                              const int* __restrict__ gate) {
   __shared__ float tile[32][33];
+  if (gate != nullptr && *gate == 0) return;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   if (c0 < C) {
@@ -58,10 +60,11 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
 }
 
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
-                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2) {
+                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2,
+                           const int* gate) {
   if (R <= 0 || C <= 0) return 0;
   dim3 grid((R + 31) / 32, (C + 31) / 32 + (ones_row ? 1 : 0));
-  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad, dst_lo2);
+  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad, dst_lo2, gate);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -81,8 +81,9 @@ int encode_gemm_nsplit(int M, int N, int num_sms);
 int encode_gemm_max_top_k();
 
 // ---- sparse_kernels.cu ----------------------------------------------------------------------------------
+// `gate` (optional, device): the kernel does nothing when *gate == 0 (AuxK operand prep with no dead latents)
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
-                      __nv_bfloat16* lo2 = nullptr);
+                      __nv_bfloat16* lo2 = nullptr, const int* gate = nullptr);
 // x[B,D] -> bf16 copy + per-row admission margin factor  c * ||x_b||_inf   (see encode_gemm.cu)
 int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s);
 // *out = max_j ||W[j,:]||^2
@@ -190,7 +191,8 @@ int launch_add_rows(const float* a, const float* b, long long n, float* out, cud
 
 // ---- dense_kernels.cu (ReLU / dense path) ----------------------------------------------------------------
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
-                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2 = nullptr);
+                           long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2 = nullptr,
+                           const int* gate = nullptr);
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
                        __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2 = nullptr);
 int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t s);

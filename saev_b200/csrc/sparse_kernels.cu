@@ -41,7 +41,9 @@ __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
 // fp32 -> bf16 (hi) [+ bf16 residual (lo)]   (operand prep for the tensor-core screen)
 // ------------------------------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2_out, long long n4) {
+                                  __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2_out, long long n4,
+                                  const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = ldg4(src + 4 * i);
@@ -71,14 +73,14 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
 }
 
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
-                      __nv_bfloat16* lo2) {
+                      __nv_bfloat16* lo2, const int* gate) {
   if (n <= 0) return 0;
   if (n % 4) return 21;
   const long long n4 = n / 4;
   const int threads = 256;
   long long want = (n4 + threads - 1) / threads;
   const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
-  split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, lo2, n4);
+  split_bf16_kernel<<<blocks, threads, 0, s>>>(src, hi, lo, lo2, n4, gate);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -53,6 +53,7 @@ struct saev_b200_handle {
   bool nd_pending = false;
   int n_dead_lagged = 0;
   bool aux_tc_step = false;      // path chosen by the last forward (backward must match)
+  bool aux_tc_always = false;    // SAEV_B200_AUX=tc: no selection (tests pin each path)
   int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
                            // accuracy), 3 = two pieces (~2^-16 of sum |a b|, half the tensor work); SAEV_B200_DENSE_TERMS
   Workspace ws;
@@ -186,7 +187,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.mask_aux = take(B * static_cast<size_t>(aux_cap));
     w.r_aux = take(B * D * 4);
     w.aux_colpart = take(aux_colpart_bytes(aux_cap));
-    const char* e = getenv("SAEV_B200_AUX");  // "sgemm": the fp32 CUDA-core tiles (debug / comparison)
+    const char* e = getenv("SAEV_B200_AUX");  // "sgemm": only the fp32 CUDA-core tiles (no tensor-core scratch)
     w.aux_tc = !(e && e[0] == 's');
     w.ldc = (static_cast<long long>(aux_cap) + 63) / 64 * 64;
     if (w.aux_tc) {
@@ -465,6 +466,10 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     h->dense_terms = (v && v[0] == '3') ? 3 : 6;
   }
   h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs, h->dense_terms);
+  {
+    const char* v = getenv("SAEV_B200_AUX");  // "sgemm" / "tc": pin one AuxK implementation; default: pick per step
+    h->aux_tc_always = v && v[0] == 't';
+  }
   if (cudaHostAlloc(reinterpret_cast<void**>(&h->nd_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->nd_event, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
@@ -690,7 +695,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
           h->nd_pending = true;
         }
       }
-      h->aux_tc_step = w.aux_tc && (h->nd_host == nullptr || h->n_dead_lagged > 32);
+      h->aux_tc_step = w.aux_tc && (h->aux_tc_always || h->nd_host == nullptr || h->n_dead_lagged > 32);
       if (c.aux_kind == SAEV_B200_AUX_AUXK) {
         AuxArgs a;
         a.x = x;

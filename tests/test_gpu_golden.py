@@ -108,10 +108,19 @@ def test_fused_renorm_equals_start_of_step_normalize():
 # ---- mid-size parity against the oracle on seeded inputs (sizes the CPU oracle finishes in seconds) ----
 @pytest.mark.parametrize("act,D,S,K,B", [("topk", 256, 4096, 32, 1024), ("topk", 768, 8192, 32, 640), ("relu", 192, 2048, 0, 520),
                                           ("topk", 128, 1000, 16, 300)])
-def test_midsize_steps_match_oracle(act, D, S, K, B):
-    """Three steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile)."""
+@pytest.mark.parametrize("aux_path", ["tc", "sgemm", "auto"])
+def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
+    """Four steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile).
+
+    The library has two AuxK implementations (tensor-core split contractions / fp32 tiles) and picks one per step from
+    a lagged dead-latent count; SAEV_B200_AUX (read at create) pins either so that both are held to the oracle."""
     from oracle import sae_oracle as orc
     from saev_b200.engine import Engine, EngineConfig
+
+    if aux_path == "auto":
+        monkeypatch.delenv("SAEV_B200_AUX", raising=False)
+    else:
+        monkeypatch.setenv("SAEV_B200_AUX", aux_path)
 
     g = torch.Generator().manual_seed(D + S)
     W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
@@ -130,7 +139,7 @@ def test_midsize_steps_match_oracle(act, D, S, K, B):
     # oracle itself is only good to 4e-6 here; the two-piece split, SAEV_B200_DENSE_TERMS=3, is at 1.7e-4)
     tol_g = TOL
     lr = 0.0
-    for step in range(3):
+    for step in range(4):  # dead latents appear at step 2; in "auto" step 3 is the first on the tensor-core path
         x = torch.randn(B, 24, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)
         if act == "relu":
             x = x - 0.5  # push many pre-activations negative so that latents die

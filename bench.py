@@ -132,6 +132,37 @@ def cpu_reference_run(D, S, K, steps, warmup, batch, threads=None):
     return batch * steps / dt, dt / steps * 1e3, cores
 
 
+def torch_gpu_reference_run(D, S, K, B, steps, warmup):
+    """The same restatement of the reference's step (dense torch ops, the [B, S] matrices materialised, TF32 matmuls
+    as the reference enables them, train.py:257) on the SAME GPU: what a saev user gets on a B200 today (SURVEY 8d,
+    baseline 2).  Timed with CUDA events after our own timed region; reported beside the CPU baseline, never as
+    part of `value`."""
+    import torch
+
+    from oracle import sae_oracle as orc
+
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    g = torch.Generator().manual_seed(0)
+    W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
+    st = orc.OracleState.from_params(W_enc.cuda(), b_enc.cuda(), W_dec.cuda(), b_dec.cuda())
+    cfg = oracle_cfg(orc, D, S, K)
+    xs = [torch.randn(B, D, generator=g).cuda() for _ in range(2)]
+    for i in range(warmup):
+        orc.train_step(cfg, st, xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        orc.train_step(cfg, st, xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del st, xs
+    torch.cuda.empty_cache()
+    return B / ms * 1e3, ms
+
+
 def size_cpu_sample(D, S, K, steps, warmup, budget_s):
     """Pick a per-step sample (rows) so that (steps + warmup) CPU steps fit in ~budget_s seconds."""
     probe = 64
@@ -217,6 +248,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the dense torch restatement of the reference step on this GPU (TF32)")
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap"],
                     help="gradient exchange for N > 1 (see saev_b200/parallel.py)")
@@ -478,6 +511,14 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
                                     "sample": f"2 timed steps x {rows} rows (+1 warm-up) of the same step; "
                                               "oracle/sae_oracle.py on torch CPU fp32"}
+        if world == 1 and args.torch_gpu_baseline:
+            try:
+                rate, ms = torch_gpu_reference_run(D, S, K, B, steps=5, warmup=2)
+                line["torch_gpu_baseline"] = {"value": rate, "unit": "activations/s", "ms_per_step": ms, "kind": "port",
+                                              "sample": f"5 timed steps x {B} rows (+2 warm-up); oracle/sae_oracle.py "
+                                                        "on this GPU: dense torch ops, TF32 matmuls (train.py:257)"}
+            except Exception as e:  # reported, never fatal for the bench line
+                line["torch_gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 8
+#define SAEV_B200_ABI_VERSION 9
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -183,6 +183,30 @@ int saev_b200_dense_f(saev_b200_handle* h, const int32_t* topk_idx, const float*
                       float* f_x_out /* [B, d_sae] */, void* workspace, void* stream);
 int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int32_t B,
                     float* x_hat_out /* [B, d_model] */, void* stream);
+
+/* Dictionary coherence of the log block, saev train.py:415-421:
+ *     W_norm = W / W.norm(dim=1);  coherence = (W_norm @ W_norm.T).abs().triu(1).max()
+ * without the [d_sae, d_sae] Gram matrix: the upper triangle is screened on the tensor cores (two-piece bf16 split,
+ * ~2^-16 absolute on unit rows) and the pairs within 1e-3 of the screen maximum are recomputed from the fp32 rows
+ * with fp64 accumulation.  out[0] = coherence, out[1] = screen maximum, out[2], out[3] = the pair (i < j, as floats).
+ * scratch: saev_b200_coherence_scratch_bytes(h) bytes of device memory.  d_model must be a multiple of 8. */
+size_t saev_b200_coherence_scratch_bytes(const saev_b200_handle* h);
+int saev_b200_dictionary_coherence(saev_b200_handle* h, const float* W_dec, void* scratch, size_t scratch_bytes,
+                                   float* out /* [4] */, void* stream);
+
+/* The per-SAE metrics of saev's log block (train.py:380-423) for the batch of the LAST forward on this handle:
+ *   out[0] explained_variance   1 - var(x - x_hat) / var(x)            (:407)
+ *   out[1] dead_unit_pct        fraction of atoms that did not fire in the batch (:410; from the activity flags of
+ *                               phase A, i.e. |f| > 0 where the reference tests |f| > 1e-12)
+ *   out[2] dictionary_coherence (:415-418, as saev_b200_dictionary_coherence)
+ *   out[3] avg_decoder_row_norm (:420)
+ *   out[4] sse_sae   out[5] sse_baseline = sum x^2 - |sum_b x|^2 / B   out[6] normalized_mse   (:380-406, fp64)
+ *   out[7] coherence screen maximum (diagnostic)
+ * x[B, d_model] and resid[B, d_model] (= x_hat - x, as written by saev_b200_forward) are read once; nothing of size
+ * [B, d_sae] or [d_sae, d_sae] is formed.  out: device double[8].  scratch: saev_b200_log_scratch_bytes(h). */
+size_t saev_b200_log_scratch_bytes(const saev_b200_handle* h);
+int saev_b200_log_metrics(saev_b200_handle* h, const float* x, const float* resid, int32_t B, const float* W_dec,
+                          void* workspace, void* scratch, size_t scratch_bytes, double* out /* [8] */, void* stream);
 
 /* Test hook for the tensor-core contraction alone: out[M, N] = A[M, K] . Bt[N, K]^T + bias[N], computed
  * from bf16 copies of the operands (nterms = 1), the 3-term two-piece split (nterms = 3, ~2^-16 of sum |a b|) or the

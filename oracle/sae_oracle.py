@@ -123,7 +123,7 @@ def dead_tracker_update(toks: Tensor | None, f: Tensor, dead_threshold_tokens: i
     dead = toks >= threshold.  Returns (toks_new int64[S], dead bool[S])."""
     B, S = f.shape
     if toks is None:
-        toks = torch.zeros(S, dtype=torch.int64)
+        toks = torch.zeros(S, dtype=torch.int64, device=f.device)
     active = (f.abs() > 0).any(dim=0)
     toks = toks + B
     toks = torch.where(active, torch.zeros_like(toks), toks)
@@ -366,3 +366,39 @@ def train_step(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None) -> 
 def eval_forward(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None) -> ForwardOut:
     """Objective in eval mode (train.py:526-527,559): no dead tracking, aux = 0."""
     return forward(cfg, st, x, training=False, prefixes=prefixes)
+
+
+# --------------------------------------------------------------------------------------
+# log block (train.py:365-442): metrics computed every `log_every` steps from the batch, the forward outputs and W_dec
+# --------------------------------------------------------------------------------------
+def dictionary_coherence(W_dec: Tensor, block: int = 1024) -> Tensor:
+    """train.py:415-421: W_norm = W / W.norm(dim=1, keepdim=True); (W_norm @ W_norm.T).abs().triu(1).max().
+    Evaluated block-row by block-row so that the [S, S] matrix never exists; same fp32 arithmetic per element."""
+    S = W_dec.shape[0]
+    Wn = W_dec / W_dec.norm(dim=1, keepdim=True)
+    best = torch.zeros((), dtype=W_dec.dtype, device=W_dec.device)
+    cols = torch.arange(S, device=W_dec.device)[None, :]
+    for a in range(0, S, block):
+        G = (Wn[a:a + block] @ Wn.T).abs()
+        rows = torch.arange(a, min(a + block, S), device=W_dec.device)[:, None]
+        best = torch.maximum(best, torch.where(cols > rows, G, torch.zeros_like(G)).max())
+    return best
+
+
+def log_block_metrics(x: Tensor, x_hat: Tensor, f_x: Tensor, W_dec: Tensor) -> dict:
+    """train.py:380-423 for one SAE: `x` = acts_BD, `x_hat` = fwd.x_hats[:, -1, :], `f_x` = fwd.f_x."""
+    x64 = x.to(torch.float64)
+    n = x64.shape[0]
+    sum_vec = x64.sum(dim=0)
+    sse_baseline = float(torch.sum(x64 * x64) - torch.dot(sum_vec, sum_vec) / n)  # train.py:381-391
+    residual = x - x_hat
+    sse_sae = float(torch.sum(residual.to(torch.float64) ** 2))  # train.py:401-403
+    return dict(
+        explained_variance=float(1 - residual.var() / x.var()),  # train.py:407 (unbiased var over all elements)
+        dead_unit_pct=float(((f_x.abs() > 1e-12).sum(0) == 0).float().mean()),  # train.py:410
+        dictionary_coherence=float(dictionary_coherence(W_dec)),
+        avg_decoder_row_norm=float(W_dec.norm(dim=1).mean()),  # train.py:420
+        sse_sae=sse_sae,
+        sse_baseline=sse_baseline,
+        normalized_mse=sse_sae / sse_baseline,  # train.py:404-406
+    )

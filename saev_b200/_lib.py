@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -110,6 +110,10 @@ SIGNATURES = {
     "saev_b200_x_hat": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_set_prefixes": (C.c_int, [_p, C.POINTER(_i32), _i32]),
     "saev_b200_x_hats": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
+    "saev_b200_coherence_scratch_bytes": (C.c_size_t, [_p]),
+    "saev_b200_dictionary_coherence": (C.c_int, [_p, _p, _p, C.c_size_t, _p, _p]),
+    "saev_b200_log_scratch_bytes": (C.c_size_t, [_p]),
+    "saev_b200_log_metrics": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, C.c_size_t, _p, _p]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "saev_b200_profile_enable": (C.c_int, [_p, _i32]),
     "saev_b200_profile_read": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

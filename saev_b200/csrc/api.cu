@@ -1087,6 +1087,73 @@ int saev_b200_x_hat(saev_b200_handle* h, const float* resid, const float* x, int
   return check_cuda(h, "x_hat");
 }
 
+size_t saev_b200_coherence_scratch_bytes(const saev_b200_handle* h) {
+  if (!h) return 0;
+  const size_t S = static_cast<size_t>(h->cfg.d_sae), D = static_cast<size_t>(h->cfg.d_model);
+  return 2 * align_up(S * D * 2) + 2 * align_up(S * ENCODE_MAX_NSPLIT * 4);
+}
+
+int saev_b200_dictionary_coherence(saev_b200_handle* h, const float* W_dec, void* scratch, size_t scratch_bytes,
+                                   float* out, void* stream) {
+  if (!h || !W_dec || !scratch || !out) return fail(h, 85, "dictionary_coherence: null argument%s");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
+  const int S = h->cfg.d_sae, D = h->cfg.d_model;
+  if (D % 8) return fail(h, 85, "dictionary_coherence: d_model must be a multiple of 8%s");
+  if (scratch_bytes < saev_b200_coherence_scratch_bytes(h)) return fail(h, 85, "dictionary_coherence: scratch too small%s");
+  const size_t piece = align_up(static_cast<size_t>(S) * D * 2), col = align_up(static_cast<size_t>(S) * ENCODE_MAX_NSPLIT * 4);
+  uint8_t* base = static_cast<uint8_t*>(scratch);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(base + piece);
+  float* row_best = reinterpret_cast<float*>(base + 2 * piece);
+  int* row_col = reinterpret_cast<int*>(base + 2 * piece + col);
+  if (launch_unit_rows_split(W_dec, S, D, hi, lo, s)) return fail(h, 86, "dictionary_coherence: split launch failed%s");
+  EncodeGemmArgs g;
+  g.A_hi = hi;
+  g.A_lo = lo;
+  g.B_hi = hi;
+  g.B_lo = lo;
+  g.nterms = 3;
+  g.M = S;
+  g.N = S;
+  g.K = D;
+  g.epilogue = 5;
+  g.num_sms = h->num_sms;
+  g.nsplit = encode_gemm_nsplit(S, S, h->num_sms);
+  g.extra = row_best;
+  g.active = row_col;
+  if (int rc = launch_encode_gemm(g, s)) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d", rc);
+    return fail(h, 86, "dictionary_coherence: screen launch failed (code %s)", buf);
+  }
+  if (launch_coherence_finish(W_dec, D, row_best, row_col, S * g.nsplit, g.nsplit, 1e-3f, out, s))
+    return fail(h, 86, "dictionary_coherence: finish launch failed%s");
+  return check_cuda(h, "dictionary_coherence");
+}
+
+size_t saev_b200_log_scratch_bytes(const saev_b200_handle* h) {
+  if (!h) return 0;
+  return saev_b200_coherence_scratch_bytes(h) + align_up((8 + static_cast<size_t>(h->cfg.d_model)) * 8) + align_up(16);
+}
+
+int saev_b200_log_metrics(saev_b200_handle* h, const float* x, const float* resid, int32_t B, const float* W_dec,
+                          void* workspace, void* scratch, size_t scratch_bytes, double* out, void* stream) {
+  if (!h || !x || !resid || !W_dec || !workspace || !scratch || !out) return fail(h, 87, "log_metrics: null argument%s");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, 87, "log_metrics: bad batch size%s");
+  if (scratch_bytes < saev_b200_log_scratch_bytes(h)) return fail(h, 87, "log_metrics: scratch too small%s");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t coh_bytes = saev_b200_coherence_scratch_bytes(h);
+  uint8_t* base = static_cast<uint8_t*>(scratch);
+  double* acc = reinterpret_cast<double*>(base + coh_bytes);
+  float* coh = reinterpret_cast<float*>(base + coh_bytes + align_up((8 + static_cast<size_t>(h->cfg.d_model)) * 8));
+  if (int rc = saev_b200_dictionary_coherence(h, W_dec, scratch, coh_bytes, coh, stream)) return rc;
+  if (launch_log_metrics(x, resid, B, h->cfg.d_model, W_dec, h->cfg.d_sae, saev_b200_active_flags(h, workspace), acc, coh,
+                         out, s))
+    return fail(h, 88, "log_metrics: launch failed%s");
+  return check_cuda(h, "log_metrics");
+}
+
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -145,4 +145,203 @@ int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dictionary coherence  max_{i<j} |<w_i, w_j>| / (||w_i|| ||w_j||)   (saev train.py:415-421, the log block).
+// The reference forms the whole [S, S] Gram matrix in fp32 (17 GB at S = 65536, + abs / triu copies); here the
+// upper triangle is screened on the tensor cores as a two-piece bf16 split product (epilogue 5 of encode_gemm.cu:
+// per row the largest |.| right of the diagonal and its column), and the few pairs within `slack` of the screen
+// maximum are recomputed exactly below.
+// ------------------------------------------------------------------------------------------------
+// hi/lo[j, :] = split(W[j, :] / ||W[j, :]||)     (one warp per row; any D)
+__global__ void __launch_bounds__(256) unit_rows_split_kernel(const float* __restrict__ W, int rows, int D,
+                                                              __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= rows) return;
+  const float* w = W + static_cast<long long>(j) * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) ss = fmaf(__ldg(w + d), __ldg(w + d), ss);
+  const float nrm = sqrtf(warp_sum(ss));
+  for (int d = lane; d < D; d += 32) {
+    __nv_bfloat16 h, l;
+    split1(__ldg(w + d) / nrm, h, l);
+    hi[static_cast<long long>(j) * D + d] = h;
+    lo[static_cast<long long>(j) * D + d] = l;
+  }
+}
+
+// One block.  out[0] = coherence (exact fp32 inputs, fp64 accumulation over the candidate pairs), out[1] = screen
+// maximum, out[2], out[3] = the pair (as floats).  row_best / row_col: [n_entries] screen results (col < 0: none).
+__global__ void __launch_bounds__(1024) coherence_finish_kernel(const float* __restrict__ W, int D,
+                                                                const float* __restrict__ row_best,
+                                                                const int* __restrict__ row_col, int n_entries,
+                                                                int nsplit, float slack, float* __restrict__ out) {
+  __shared__ float s_max[32];
+  __shared__ double s_val[32];
+  __shared__ int s_i[32], s_j[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -1.f;
+  for (int e = threadIdx.x; e < n_entries; e += blockDim.x)
+    if (row_col[e] >= 0) m = fmaxf(m, row_best[e]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if (lane == 0) s_max[warp] = m;
+  __syncthreads();
+  float gmax = s_max[0];
+  for (int w = 1; w < 32; ++w) gmax = fmaxf(gmax, s_max[w]);
+  double best = -1.0;
+  int bi = -1, bj = -1;
+  for (int e = warp; e < n_entries; e += 32) {  // warp-uniform
+    const int j = row_col[e];
+    if (j < 0 || row_best[e] < gmax - slack) continue;
+    const int i = e / nsplit;
+    const float* wi = W + static_cast<long long>(i) * D;
+    const float* wj = W + static_cast<long long>(j) * D;
+    double dot = 0.0, ni = 0.0, nj = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double a = wi[d], b = wj[d];
+      dot += a * b;
+      ni += a * a;
+      nj += b * b;
+    }
+    for (int o = 16; o; o >>= 1) {
+      dot += __shfl_xor_sync(FULL, dot, o);
+      ni += __shfl_xor_sync(FULL, ni, o);
+      nj += __shfl_xor_sync(FULL, nj, o);
+    }
+    const double c = fabs(dot) / (sqrt(ni) * sqrt(nj));
+    if (c > best) {
+      best = c;
+      bi = i;
+      bj = j;
+    }
+  }
+  if (lane == 0) {
+    s_val[warp] = best;
+    s_i[warp] = bi;
+    s_j[warp] = bj;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w)
+      if (s_val[w] > best) {
+        best = s_val[w];
+        bi = s_i[w];
+        bj = s_j[w];
+      }
+    out[0] = bi >= 0 ? static_cast<float>(best) : 0.f;  // fewer than two rows: triu(1) is empty
+    out[1] = gmax;
+    out[2] = static_cast<float>(bi);
+    out[3] = static_cast<float>(bj);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The other metrics of the log block (train.py:380-423) in one pass over x / residual and one over W_dec.
+// acc (double): [0] sum x^2  [1] sum r^2  [2] sum r  [3] sum x  [4] sum_j ||w_j||  [5] atoms that did not fire
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) log_sums_kernel(const float* __restrict__ x, const float* __restrict__ r, int B,
+                                                       int D, double* __restrict__ acc, double* __restrict__ colsum) {
+  __shared__ double red[4][4];
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  double cs = 0.0, sx2 = 0.0, sr2 = 0.0, sr = 0.0;
+  if (col < D) {
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+      const double xv = __ldg(x + static_cast<long long>(b) * D + col);
+      const double rv = __ldg(r + static_cast<long long>(b) * D + col);
+      cs += xv;
+      sx2 += xv * xv;
+      sr2 += rv * rv;
+      sr += rv;
+    }
+    atomicAdd(colsum + col, cs);
+  }
+  double v[4] = {sx2, sr2, sr, cs};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(acc + threadIdx.x, red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
+}
+
+__global__ void __launch_bounds__(256) log_rows_kernel(const float* __restrict__ W, int S, int D,
+                                                       const int* __restrict__ fired, double* __restrict__ acc) {
+  __shared__ double red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double nsum = 0.0, idle = 0.0;
+  for (int j = blockIdx.x * 8 + warp; j < S; j += gridDim.x * 8) {
+    const float* w = W + static_cast<long long>(j) * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) ss = fmaf(__ldg(w + d), __ldg(w + d), ss);
+    ss = warp_sum(ss);
+    nsum += sqrtf(ss);
+    if (fired != nullptr && fired[j] == 0) idle += 1.0;
+  }
+  if (lane == 0) {
+    red[0][warp] = nsum;
+    red[1][warp] = idle;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(acc + 4 + threadIdx.x, t);
+  }
+}
+
+// out (double[8]): explained_variance, dead_unit_pct, dictionary_coherence, avg_decoder_row_norm, sse_sae,
+// sse_baseline, normalized_mse, coherence screen maximum
+__global__ void log_finish_kernel(const double* __restrict__ acc, const double* __restrict__ colsum, int B, int D, int S,
+                                  const float* __restrict__ coh, double* __restrict__ out) {
+  __shared__ double red[32];
+  double t = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) t += colsum[d] * colsum[d];
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cc = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) cc += red[w];
+    const double n = static_cast<double>(B) * D;
+    const double sse_base = acc[0] - cc / B;                       // train.py:384-391
+    const double var_r = (acc[1] - acc[2] * acc[2] / n) / (n - 1);  // torch .var(): unbiased, over all elements
+    const double var_x = (acc[0] - acc[3] * acc[3] / n) / (n - 1);
+    out[0] = 1.0 - var_r / var_x;
+    out[1] = acc[5] / S;
+    out[2] = coh[0];
+    out[3] = acc[4] / S;
+    out[4] = acc[1];
+    out[5] = sse_base;
+    out[6] = acc[1] / sse_base;
+    out[7] = coh[1];
+  }
+}
+
+int launch_log_metrics(const float* x, const float* r, int B, int D, const float* W, int S, const int* fired,
+                       double* acc /* [8 + D], zeroed here */, const float* coh, double* out, cudaStream_t s) {
+  if (cudaMemsetAsync(acc, 0, (8 + static_cast<size_t>(D)) * sizeof(double), s) != cudaSuccess) return 22;
+  dim3 grid((D + 127) / 128, 148);
+  log_sums_kernel<<<grid, 128, 0, s>>>(x, r, B, D, acc, acc + 8);
+  log_rows_kernel<<<148 * 4, 256, 0, s>>>(W, S, D, fired, acc);
+  log_finish_kernel<<<1, 256, 0, s>>>(acc, acc + 8, B, D, S, coh, out);
+  g_launch_count += 3;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+int launch_unit_rows_split(const float* W, int rows, int D, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
+  unit_rows_split_kernel<<<(rows + 7) / 8, 256, 0, s>>>(W, rows, D, hi, lo);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+int launch_coherence_finish(const float* W, int D, const float* row_best, const int* row_col, int n_entries, int nsplit,
+                            float slack, float* out, cudaStream_t s) {
+  coherence_finish_kernel<<<1, 1024, 0, s>>>(W, D, row_best, row_col, n_entries, nsplit, slack, out);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 }  // namespace sb

@@ -178,6 +178,9 @@ __device__ __forceinline__ float compact_row_global(int2* buf, int n, int k, flo
 //          contraction); per-row sum f / count f>0, per-column "fired" flags
 //      3 = ReLU backward: dh = (f > 0) ? acc + l1_over_b : 0, written transposed as a bf16 hi/lo pair [N, ldt]
 //      4 = weight gradient: out[row, col] = acc for col < n_main, extra[row] = acc for col == n_main
+//      5 = dictionary coherence screen (A == B == unit rows of W_dec): per (row, split) the largest |acc| over the
+//          columns col > row and its column, into extra / active [M, nsplit]; tiles wholly below the diagonal are
+//          skipped by all three roles
 template <int EPI, int CAPG, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -216,8 +219,9 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   // nothing to do (no dead latents / rows past the dynamic row count): leave before any barrier or TMEM is touched
   if (n_cols <= 0 || kblocks_per_term <= 0 || (blockIdx.x % m_blocks) * BM >= M) return;
   const int n_tiles_total = (n_cols + BN - 1) / BN;
-  const int tile_begin = split * tiles_per_split;
+  int tile_begin = split * tiles_per_split;
   const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
+  if (EPI == 5) tile_begin = max(tile_begin, (m_blk * BM + 1) / BN);  // first tile holding a column > row
   const int num_tiles = max(0, tile_end - tile_begin);
   // K chunking (dense epilogues 1 / 4): the contraction of one output tile is cut into chunks of `kchunk` k-blocks per
   // term, each accumulated in its own TMEM stage and added to the fp32 output by the epilogue.  Tensor-core
@@ -334,6 +338,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const float margin = (EPI == 0 && row < M) ? row_margin[row] * sqrtf(*wnorm_sq_max) : 0.f;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     float acc_l1 = 0.f, acc_l0 = 0.f;  // EPI 2
+    float best = -1.f;                 // EPI 5
+    int best_col = -1;
 
     for (int vt = 0; vt < num_vtiles; ++vt) {
       const int t = vt / n_chunks;
@@ -497,6 +503,15 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               }
             }
           }
+        } else if (EPI == 5) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) {
+            const float a_abs = fabsf(v[i]);
+            if (col0 + i > row && col0 + i < n_cols && a_abs > best) {
+              best = a_abs;
+              best_col = col0 + i;
+            }
+          }
         } else {  // EPI == 4
           if (row < M) {
             const long long orow = ex.row_map != nullptr ? ex.row_map[row] : row;
@@ -541,6 +556,10 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       // named barrier of tile t+1, which every warp reaches only after finishing tile t.
     }
 
+    if (EPI == 5 && row < M) {
+      ex.extra[static_cast<long long>(row) * nsplit + split] = best;
+      ex.active[static_cast<long long>(row) * nsplit + split] = best_col;
+    }
     if (EPI == 2 && row < M && num_tiles > 0) {
       atomicAdd(ex.row_l1 + row, acc_l1);
       atomicAdd(ex.row_l0 + row, acc_l0);
@@ -691,6 +710,7 @@ int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
       case 2: return launch_variant<2, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
       case 3: return launch_variant<3, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
       case 4: return launch_variant<4, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+      case 5: return launch_variant<5, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
       default: return 12;
     }
   }

@@ -36,7 +36,7 @@ struct EncodeGemmArgs {
   int ksplit = 1;                       // epilogues 1 / 4 with k_chunk_blocks > 0: spread the K chunks of one output tile
                                         // over this many CTAs, all adding into a PRE-ZEROED output (bias must be null)
   int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store, 2: ReLU forward,
-                                        // 3: ReLU backward, 4: weight gradient (see encode_gemm.cu)
+                                        // 3: ReLU backward, 4: weight gradient, 5: coherence screen (see encode_gemm.cu)
   __nv_bfloat16* f_hi = nullptr;        // epilogue 2 (out) / 3 (in): relu(h) as bf16 hi [M, ldf]
   __nv_bfloat16* f_lo = nullptr;        // epilogue 2: bf16 residual
   __nv_bfloat16* t_hi = nullptr;        // epilogue 2/3: transposed bf16 hi/lo outputs [N, ldt]
@@ -89,6 +89,11 @@ int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_
 // *out = max_j ||W[j,:]||^2
 int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s);
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
+int launch_log_metrics(const float* x, const float* r, int B, int D, const float* W, int S, const int* fired,
+                       double* acc, const float* coh, double* out, cudaStream_t s);
+int launch_unit_rows_split(const float* W, int rows, int D, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s);
+int launch_coherence_finish(const float* W, int D, const float* row_best, const int* row_col, int n_entries, int nsplit,
+                            float slack, float* out, cudaStream_t s);
 
 struct RescoreArgs {
   const void* cand; const int* cand_cnt; int cand_stride; int nsplit;  // (row, split) candidate buffers

@@ -1293,8 +1293,7 @@ __global__ void __launch_bounds__(1024) dead_update_kernel(long long* __restrict
   int dead = 0;
   if (i < S) {
     const long long t = active[i] ? 0 : toks[i] + batch_tokens;
-    toks[i] = t;
-    active[i] = 0;
+    toks[i] = t;  // (the flags stay valid until the next forward re-zeroes them: the log block reads them)
     dead = t >= threshold;
   }
   dead = warp_sum(dead);

@@ -341,6 +341,41 @@ class Engine:
         self._ck(self.lib.saev_b200_profile_read(self.h, ms, cnt))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.STAGES)}
 
+    # ---- log-block metrics (saev train.py:365-442) -------------------------------------------
+    def dictionary_coherence(self, W_dec: torch.Tensor | None = None) -> torch.Tensor:
+        """max_{i<j} |cos(w_i, w_j)| over the decoder rows (train.py:415-421) without the [S, S] Gram matrix.
+        Returns a device float32[4]: coherence, tensor-core screen maximum, i, j.  No host sync."""
+        W = self.W_dec if W_dec is None else W_dec
+        assert W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and tuple(W.shape) == (self.S, self.D)
+        n = int(self.lib.saev_b200_coherence_scratch_bytes(self.h))
+        scratch = torch.empty(n, dtype=torch.uint8, device=self.device)
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_dictionary_coherence(self.h, W.data_ptr(), scratch.data_ptr(), n, out.data_ptr(),
+                                                             self._stream()))
+        return out
+
+    LOG_KEYS = ("explained_variance", "dead_unit_pct", "dictionary_coherence", "avg_decoder_row_norm", "sse_sae",
+                "sse_baseline", "normalized_mse")
+
+    def log_metrics(self, x: torch.Tensor) -> torch.Tensor:
+        """The per-SAE `metrics/*` of saev's log block (train.py:380-423) for the batch of the last forward, as a
+        device float64[8] in LOG_KEYS order (+ the coherence screen maximum).  No host sync; nothing of size [B, S]
+        or [S, S] is formed."""
+        B = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
+        n = int(self.lib.saev_b200_log_scratch_bytes(self.h))
+        scratch = torch.empty(n, dtype=torch.uint8, device=self.device)
+        out = torch.empty(8, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_log_metrics(self.h, x.data_ptr(), self.resid.data_ptr(), B, self.W_dec.data_ptr(),
+                                                    self.workspace.data_ptr(), scratch.data_ptr(), n, out.data_ptr(),
+                                                    self._stream()))
+        return out
+
+    def log_metrics_dict(self, x: torch.Tensor) -> dict:
+        return dict(zip(self.LOG_KEYS, self.log_metrics(x).tolist()))
+
     # ---- test hook -------------------------------------------------------------------------
     def gemm_nt(self, A: torch.Tensor, Bt: torch.Tensor, bias: torch.Tensor | None, nterms: int) -> torch.Tensor:
         M, K = A.shape

@@ -213,6 +213,14 @@ class Output:
     def __iter__(self):  # NamedTuple-style unpacking: h_x, f_x, x_hats
         return iter((self.h_x, self.f_x, self.x_hats))
 
+    def log_metrics(self) -> dict[str, float]:
+        """What saev's log block (train.py:380-423) derives from `acts_BD`, `fwd.x_hats`, `fwd.f_x` and `sae.W_dec`
+        -- explained_variance, dead_unit_pct, dictionary_coherence, avg_decoder_row_norm, sse_sae, sse_baseline,
+        normalized_mse -- computed from the sparse forward state without the dense [B, S] / [S, S] matrices the
+        reference forms there (one host sync, like the `.item()` calls it replaces)."""
+        self._check()
+        return self._sae.engine.log_metrics_dict(self._x)
+
 
 class _Activation(torch.nn.Module):
     """Placeholder for `sae.activation` (objectives.py:149 reads `.cfg.sparsity`)."""

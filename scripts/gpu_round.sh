@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt
 echo "== pytest"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-echo "== bench c3"; timeout 900 python bench.py --steps 30 --warmup 5 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json | tail -2; tail -5 gpurun_out/bench_c3.err
+echo "== bench c3"; timeout 900 python bench.py --steps 30 --warmup 5 --torch-gpu-baseline 2>gpurun_out/bench_c3.err | tee gpurun_out/bench_c3.json | tail -2; tail -5 gpurun_out/bench_c3.err
 echo "== bench c2"; timeout 600 python bench.py --workload c2 --steps 30 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_c2.err | tee gpurun_out/bench_c2.json | tail -2
 if [ "${NCU:-1}" = "1" ]; then
 echo "== ncu launch list"

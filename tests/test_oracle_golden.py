@@ -149,3 +149,27 @@ def test_warmup_cosine_matches_reference_formula():
     assert vals[0] == 0.25 and vals[2] == 0.75 and vals[3] == 1.0
     assert vals[11] == 0.0 and vals[12] == 0.0
     assert vals[7] == pytest.approx((1 + math.cos(math.pi * 4 / 8)) / 2)
+
+
+def test_log_block_matches_reference_capture():
+    """oracle.log_block_metrics against the metric dicts the live reference logged (train.py:380-423), captured with
+    their inputs by oracle/gen_golden_log.py."""
+    import numpy as np
+
+    from tests.golden_util import GOLDEN
+
+    z = np.load(GOLDEN / "log_block.npz")
+    assert int(z["n"]) >= 3
+    for i in range(int(z["n"])):
+        got = orc.log_block_metrics(*(torch.from_numpy(z[f"{k}_{i}"]) for k in ("x", "x_hat", "f_x", "W_dec")))
+        for k, ref in zip([str(k) for k in z["keys"]], z[f"metrics_{i}"]):
+            assert got[k] == pytest.approx(float(ref), rel=1e-6, abs=1e-9), (i, k)
+
+
+def test_dictionary_coherence_blocked_equals_direct():
+    g = torch.Generator().manual_seed(3)
+    W = torch.randn(300, 24, generator=g) * torch.rand(300, 1, generator=g)
+    Wn = W / W.norm(dim=1, keepdim=True)
+    direct = (Wn @ Wn.T).abs().triu(1).max()  # train.py:417-418 verbatim
+    assert float(orc.dictionary_coherence(W, block=64)) == pytest.approx(float(direct), rel=1e-6)
+    assert float(orc.dictionary_coherence(W[:1])) == 0.0

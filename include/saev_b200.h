@@ -208,6 +208,19 @@ size_t saev_b200_log_scratch_bytes(const saev_b200_handle* h);
 int saev_b200_log_metrics(saev_b200_handle* h, const float* x, const float* resid, int32_t B, const float* W_dec,
                           void* workspace, void* scratch, size_t scratch_bytes, double* out /* [8] */, void* stream);
 
+/* One batch of saev's evaluate() loop (train.py:546-566), from the state of the LAST forward on this handle, without
+ * the dense fwd.f_x[B, d_sae]:
+ *   n_fired[j] += #(f[b, j] > 0)          (:560-562)      values[j] += sum_b f[b, j]      (:563)
+ *   acc[0] += sum x^2   acc[8 + d] += sum_b x[b, d]       (:548-549, fp64)      acc[1] += sum (x - x_hat)^2   (:558-559)
+ *   acc[4] += l0 * B    acc[5] += l1 * B    acc[6] += mse * B    acc[7] += B     (:564-566; acc[2], acc[3]: sums of
+ *   the residual and of x, used by the log block only)
+ * acc: device double[8 + d_model], n_fired / values: device float[d_sae]; all three are ACCUMULATED into (the caller
+ * zeroes them before the first batch).  topk_idx / topk_val: as written by saev_b200_forward (ignored for ReLU, whose
+ * dense activations live in the workspace).  losses: the device float[8] of the same forward. */
+int saev_b200_eval_accumulate(saev_b200_handle* h, const float* x, const float* resid, int32_t B,
+                              const int32_t* topk_idx, const float* topk_val, const float* losses, double* acc,
+                              float* n_fired, float* values, void* workspace, void* stream);
+
 /* Test hook for the tensor-core contraction alone: out[M, N] = A[M, K] . Bt[N, K]^T + bias[N], computed
  * from bf16 copies of the operands (nterms = 1), the 3-term two-piece split (nterms = 3, ~2^-16 of sum |a b|) or the
  * 6-term three-piece split (nterms = 6, fp32-class).  scratch must hold 3 * (M + N) * K bf16. */

@@ -1,12 +1,14 @@
-"""Generate tests/golden/log_block.npz: inputs and outputs of the reference's LOG BLOCK
-(/root/reference/src/saev/framework/train.py:365-442) captured from a live run of the unmodified
-`saev.framework.train.worker_fn` on CPU.  TEST INFRASTRUCTURE ONLY; runs in the build container.
+"""Generate tests/golden/log_block.npz and tests/golden/evaluate.npz: inputs and outputs of the reference's LOG BLOCK
+(/root/reference/src/saev/framework/train.py:365-442) and of its `evaluate()` (train.py:510-618), captured from a live
+run of the unmodified `saev.framework.train.worker_fn` on CPU.  TEST INFRASTRUCTURE ONLY; runs in the build container.
 
     python oracle/gen_golden_log.py
 
 The block is inline code of `train()`, not a callable, so it is pinned by observation: `ParallelWandbRun.log` is
 wrapped, and at every call made from `train()` the wrapper reads the caller's locals (`acts_BD`, `saes`, `fwds`) and
-the metric dicts the reference just computed from them.  Nothing from this repository is on that path.
+the metric dicts the reference just computed from them.  `train.evaluate` is wrapped the same way: its `EvalMetrics`
+result is stored with the parameters of the SAE it was given and the full validation set (n_val >= n_samples, so the
+result does not depend on the loader's random order).  Nothing from this repository is on that path.
 """
 
 import base64
@@ -52,6 +54,15 @@ def main():
         return orig_log(self, metrics, step=step)
 
     saev.utils.wandb.ParallelWandbRun.log = capturing_log
+    evals = []
+    orig_eval = train.evaluate
+
+    def capturing_eval(cfgs, saes, objectives):
+        out = orig_eval(cfgs, saes, objectives)
+        evals.append((out[0], {k: v.detach().clone() for k, v in saes[0].state_dict().items()}))
+        return out
+
+    train.evaluate = capturing_eval
     with tempfile.TemporaryDirectory() as tmp:
         tmp = pathlib.Path(tmp)
         root = tmp / "saev" / "shards"
@@ -71,8 +82,8 @@ def main():
             w.write_batch(acts, 0)
         d = root / md.hash
         cfg = train.Config(
-            n_train=n_examples * T, n_val=64, device="cpu", track=False, log_every=2, lr=3e-3, n_lr_warmup=2,
-            runs_root=tmp / "saev" / "runs",
+            n_train=n_examples * T, n_val=100_000, device="cpu", track=False, log_every=2, lr=3e-3, n_lr_warmup=2,
+            runs_root=tmp / "saev" / "runs", objective=saev.nn.objectives.Matryoshka(n_prefixes=1),
             train_data=saev.data.ShuffledConfig(shards=d, layer=0, batch_size=48),
             val_data=saev.data.ShuffledConfig(shards=d, layer=0, batch_size=48),
             sae=saev.nn.SparseAutoencoderConfig(d_model=D, d_sae=4 * D, activation=TopK(top_k=4), reinit_blend=0.0),
@@ -90,6 +101,17 @@ def main():
     np.savez_compressed(GOLDEN / "log_block.npz", **out)
     for c in captured:
         print(c["step"], c["metrics"])
+    em, sd = evals[0]
+    ev = {f"param_{k}": v.numpy() for k, v in sd.items()}
+    ev["acts"] = acts[:, 0].reshape(-1, D).numpy()  # every (example, token) row of layer 0 = the validation set
+    for f in ("l0", "l1", "mse", "normalized_mse", "sse_sae", "sse_baseline"):
+        ev[f] = np.float64(getattr(em, f))
+    for f in ("n_dead", "n_almost_dead", "n_dense"):
+        ev[f] = np.int64(getattr(em, f))
+    ev["freqs"], ev["mean_values"] = em.freqs.numpy(), em.mean_values.numpy()
+    ev["top_k"], ev["batch_size"] = np.int64(4), np.int64(48)
+    np.savez_compressed(GOLDEN / "evaluate.npz", **ev)
+    print("evaluate:", {f: float(ev[f]) for f in ("l0", "l1", "mse", "normalized_mse", "n_dead", "n_almost_dead", "n_dense")})
 
 
 if __name__ == "__main__":

@@ -402,3 +402,38 @@ def log_block_metrics(x: Tensor, x_hat: Tensor, f_x: Tensor, W_dec: Tensor) -> d
         sse_baseline=sse_baseline,
         normalized_mse=sse_sae / sse_baseline,  # train.py:404-406
     )
+
+
+# --------------------------------------------------------------------------------------
+# evaluate() (train.py:510-618)
+# --------------------------------------------------------------------------------------
+def evaluate(cfg: OracleConfig, st: OracleState, batches, almost_dead_lim: float = 1e-7, dense_lim: float = 1e-2) -> dict:
+    """train.py:536-616 for one SAE over an iterable of x[B, D] batches (eval-mode objective forward per batch)."""
+    S, D = st.W_dec.shape
+    n_fired = torch.zeros(S)
+    values = torch.zeros(S)
+    l0_sum = l1_sum = mse_sum = 0.0
+    sse_sae = torch.zeros((), dtype=torch.float64)
+    sum_sq = torch.zeros((), dtype=torch.float64)
+    sum_vec = torch.zeros(D, dtype=torch.float64)
+    n_tokens = 0
+    for x in batches:
+        x64 = x.to(torch.float64)
+        sum_sq += torch.sum(x64 * x64)  # train.py:548
+        sum_vec += x64.sum(dim=0)  # train.py:549
+        n_tokens += x.shape[0]
+        out = eval_forward(cfg, st, x)
+        sse_sae += torch.sum((x - out.x_hat).to(torch.float64) ** 2)  # train.py:558-559
+        n_fired += (out.f > 0).sum(dim=0)  # train.py:560-562
+        values += out.f.sum(dim=0)  # train.py:563
+        l0_sum += float(out.l0) * x.shape[0]  # train.py:564-566
+        l1_sum += float(out.l1) * x.shape[0]
+        mse_sum += float(out.mse) * x.shape[0]
+    sse_baseline = float(sum_sq - torch.dot(sum_vec, sum_vec) / n_tokens)  # train.py:570-571
+    freqs = n_fired / n_tokens
+    return dict(
+        l0=l0_sum / n_tokens, l1=l1_sum / n_tokens, mse=mse_sum / n_tokens, normalized_mse=float(sse_sae) / sse_baseline,
+        sse_sae=float(sse_sae), sse_baseline=sse_baseline, n_dead=int((freqs == 0).sum()),
+        n_almost_dead=int((freqs < almost_dead_lim).sum()), n_dense=int((freqs > dense_lim).sum()), freqs=freqs,
+        mean_values=values / n_fired,
+    )

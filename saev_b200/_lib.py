@@ -114,6 +114,7 @@ SIGNATURES = {
     "saev_b200_dictionary_coherence": (C.c_int, [_p, _p, _p, C.c_size_t, _p, _p]),
     "saev_b200_log_scratch_bytes": (C.c_size_t, [_p]),
     "saev_b200_log_metrics": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, C.c_size_t, _p, _p]),
+    "saev_b200_eval_accumulate": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "saev_b200_profile_enable": (C.c_int, [_p, _i32]),
     "saev_b200_profile_read": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

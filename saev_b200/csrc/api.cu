@@ -1154,6 +1154,29 @@ int saev_b200_log_metrics(saev_b200_handle* h, const float* x, const float* resi
   return check_cuda(h, "log_metrics");
 }
 
+int saev_b200_eval_accumulate(saev_b200_handle* h, const float* x, const float* resid, int32_t B,
+                              const int32_t* topk_idx, const float* topk_val, const float* losses, double* acc,
+                              float* n_fired, float* values, void* workspace, void* stream) {
+  if (!h || !x || !resid || !losses || !acc || !n_fired || !values) return fail(h, 89, "eval_accumulate: null argument%s");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(h, 89, "eval_accumulate: bad batch size%s");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bind_context(h);
+  const int S = h->cfg.d_sae, D = h->cfg.d_model;
+  if (launch_eval_accumulate(x, resid, B, D, losses, acc, s)) return fail(h, 89, "eval_accumulate: launch failed%s");
+  if (h->cfg.act_kind == SAEV_B200_ACT_RELU) {
+    if (!workspace) return fail(h, 89, "eval_accumulate: the ReLU path needs the workspace%s");
+    if (launch_feature_stats_dense(at<__nv_bfloat16>(workspace, h->ws.f_hi), at<__nv_bfloat16>(workspace, h->ws.f_lo),
+                                   h->dense_terms == 6 ? at<__nv_bfloat16>(workspace, h->ws.f_l2) : nullptr, B, S, S,
+                                   n_fired, values, s))
+      return fail(h, 89, "eval_accumulate: launch failed%s");
+  } else {
+    if (!topk_idx || !topk_val) return fail(h, 89, "eval_accumulate: null top-k buffers%s");
+    if (launch_feature_stats_topk(topk_idx, topk_val, static_cast<long long>(B) * h->cfg.top_k, n_fired, values, s))
+      return fail(h, 89, "eval_accumulate: launch failed%s");
+  }
+  return check_cuda(h, "eval_accumulate");
+}
+
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,
                       int32_t N, int32_t K, int32_t nterms, float* out, void* scratch, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);

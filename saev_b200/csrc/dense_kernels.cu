@@ -331,6 +331,77 @@ int launch_log_metrics(const float* x, const float* r, int B, int D, const float
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluate() accumulators (saev train.py:546-566): per-atom firing counts and value sums from the sparse forward
+// state, the batch sums of the normalised-MSE baseline, and the batch-weighted loss scalars.
+// ------------------------------------------------------------------------------------------------
+// n_fired[j] += #(f[b, j] > 0), values[j] += sum_b f[b, j] over the B*K (index, value) slots (index < 0: empty)
+__global__ void __launch_bounds__(256) feature_stats_topk_kernel(const int* __restrict__ idx, const float* __restrict__ val,
+                                                                 long long n, float* __restrict__ n_fired,
+                                                                 float* __restrict__ values) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int j = __ldg(idx + i);
+    if (j < 0) continue;
+    const float v = __ldg(val + i);
+    if (v > 0.f) atomicAdd(n_fired + j, 1.f);
+    if (v != 0.f) atomicAdd(values + j, v);
+  }
+}
+
+// same from the dense ReLU activations kept as bf16 pieces [B, ld]
+__global__ void __launch_bounds__(128) feature_stats_dense_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                                  const __nv_bfloat16* __restrict__ lo,
+                                                                  const __nv_bfloat16* __restrict__ lo2, int B, int S,
+                                                                  long long ld, float* __restrict__ n_fired,
+                                                                  float* __restrict__ values) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= S) return;
+  float cnt = 0.f, sum = 0.f;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const long long o = static_cast<long long>(b) * ld + j;
+    const float f = __bfloat162float(hi[o]) + (__bfloat162float(lo[o]) + (lo2 ? __bfloat162float(lo2[o]) : 0.f));
+    cnt += (f > 0.f) ? 1.f : 0.f;
+    sum += f;
+  }
+  if (cnt > 0.f) atomicAdd(n_fired + j, cnt);
+  if (sum != 0.f) atomicAdd(values + j, sum);
+}
+
+// acc[4..7] += {l0, l1, mse} * B, B        (train.py:564-566: batch-weighted means, fp64)
+__global__ void eval_scalars_kernel(const float* __restrict__ losses, int B, double* __restrict__ acc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    acc[4] += static_cast<double>(losses[3]) * B;
+    acc[5] += static_cast<double>(losses[4]) * B;
+    acc[6] += static_cast<double>(losses[0]) * B;
+    acc[7] += B;
+  }
+}
+
+int launch_eval_accumulate(const float* x, const float* r, int B, int D, const float* losses, double* acc,
+                           cudaStream_t s) {
+  dim3 grid((D + 127) / 128, 148);
+  log_sums_kernel<<<grid, 128, 0, s>>>(x, r, B, D, acc, acc + 8);
+  eval_scalars_kernel<<<1, 32, 0, s>>>(losses, B, acc);
+  g_launch_count += 2;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+int launch_feature_stats_topk(const int* idx, const float* val, long long n, float* n_fired, float* values,
+                              cudaStream_t s) {
+  feature_stats_topk_kernel<<<148 * 4, 256, 0, s>>>(idx, val, n, n_fired, values);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+int launch_feature_stats_dense(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const __nv_bfloat16* lo2, int B, int S,
+                               long long ld, float* n_fired, float* values, cudaStream_t s) {
+  dim3 grid((S + 127) / 128, 8);
+  feature_stats_dense_kernel<<<grid, 128, 0, s>>>(hi, lo, lo2, B, S, ld, n_fired, values);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 int launch_unit_rows_split(const float* W, int rows, int D, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
   unit_rows_split_kernel<<<(rows + 7) / 8, 256, 0, s>>>(W, rows, D, hi, lo);
   ++g_launch_count;

@@ -91,6 +91,12 @@ int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStr
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
 int launch_log_metrics(const float* x, const float* r, int B, int D, const float* W, int S, const int* fired,
                        double* acc, const float* coh, double* out, cudaStream_t s);
+int launch_eval_accumulate(const float* x, const float* r, int B, int D, const float* losses, double* acc,
+                           cudaStream_t s);
+int launch_feature_stats_topk(const int* idx, const float* val, long long n, float* n_fired, float* values,
+                              cudaStream_t s);
+int launch_feature_stats_dense(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const __nv_bfloat16* lo2, int B, int S,
+                               long long ld, float* n_fired, float* values, cudaStream_t s);
 int launch_unit_rows_split(const float* W, int rows, int D, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s);
 int launch_coherence_finish(const float* W, int D, const float* row_best, const int* row_col, int n_entries, int nsplit,
                             float slack, float* out, cudaStream_t s);

@@ -2,7 +2,8 @@
 
 saev's loop looks every hot-path name up by attribute at call time
 (/root/reference/src/saev/framework/train.py): `nn.SparseAutoencoder` (:115), `nn.get_objective` (:119),
-`saev.data.ShuffledDataLoader` (:259, :534), `torch.optim.Adam` (:294), `torch.nn.utils.clip_grad_norm_` (:358).
+`saev.data.ShuffledDataLoader` (:259, :534), `torch.optim.Adam` (:294), `torch.nn.utils.clip_grad_norm_` (:358),
+`evaluate` (:198, a module global of saev.framework.train).
 `install()` rebinds exactly those names to the classes of this package and `uninstall()` restores them, so
 
     import saev.framework.train, saev_b200
@@ -47,7 +48,8 @@ def dropin_class():
     return _dropin_cls
 
 
-def install(*, model: bool = True, optimizer: bool = True, loader: bool = True, data_parallel: bool | str = "auto"):
+def install(*, model: bool = True, optimizer: bool = True, loader: bool = True, evaluate: bool = True,
+            data_parallel: bool | str = "auto"):
     """Rebind saev's hot-path names to saev_b200 (idempotent).  Needs `saev` importable; raises ImportError
     otherwise.  `data_parallel="auto"` turns the gradient all-reduce on when torch.distributed is initialised
     with more than one rank."""
@@ -76,6 +78,20 @@ def install(*, model: bool = True, optimizer: bool = True, loader: bool = True, 
 
         saev_data = importlib.import_module("saev.data")
         _bind(saev_data, "ShuffledDataLoader", _data.ShuffledDataLoader)
+    if evaluate and model:
+        # train.py:198 looks `evaluate` up as a module global; ours accumulates the per-atom statistics from the sparse
+        # forward state and returns saev's own EvalMetrics
+        from . import evaluate as _eval
+
+        ref_train = importlib.import_module("saev.framework.train")
+        saev_data = importlib.import_module("saev.data")
+
+        def evaluate_b200(cfgs, saes, objectives):
+            return _eval.evaluate(cfgs, saes, objectives, metrics_cls=ref_train.EvalMetrics,
+                                  loader_cls=saev_data.ShuffledDataLoader)
+
+        evaluate_b200.__doc__ = _eval.evaluate.__doc__
+        _bind(ref_train, "evaluate", evaluate_b200)
     return None
 
 

@@ -376,6 +376,23 @@ class Engine:
     def log_metrics_dict(self, x: torch.Tensor) -> dict:
         return dict(zip(self.LOG_KEYS, self.log_metrics(x).tolist()))
 
+    # ---- evaluate() accumulators (saev train.py:546-566) -------------------------------------
+    def new_eval_state(self) -> dict:
+        """Zeroed device accumulators for `eval_accumulate`: acc float64[8 + D], n_fired / values float32[S]."""
+        return dict(acc=torch.zeros(8 + self.D, dtype=torch.float64, device=self.device),
+                    n_fired=torch.zeros(self.S, dtype=torch.float32, device=self.device),
+                    values=torch.zeros(self.S, dtype=torch.float32, device=self.device))
+
+    def eval_accumulate(self, x: torch.Tensor, state: dict) -> None:
+        """Fold the batch of the last forward into `state` (no host sync, no dense f_x)."""
+        B = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_eval_accumulate(
+                self.h, x.data_ptr(), self.resid.data_ptr(), B, self.topk_idx.data_ptr(), self.topk_val.data_ptr(),
+                self.losses.data_ptr(), state["acc"].data_ptr(), state["n_fired"].data_ptr(), state["values"].data_ptr(),
+                self.workspace.data_ptr(), self._stream()))
+
     # ---- test hook -------------------------------------------------------------------------
     def gemm_nt(self, A: torch.Tensor, Bt: torch.Tensor, bias: torch.Tensor | None, nterms: int) -> torch.Tensor:
         M, K = A.shape

@@ -104,3 +104,65 @@ def test_log_metrics_after_real_forward():
     assert got["explained_variance"] == pytest.approx(ref["explained_variance"], abs=2e-5)
     assert got["dead_unit_pct"] == pytest.approx(ref["dead_unit_pct"], abs=1e-7)
     assert got["dictionary_coherence"] == pytest.approx(ref["dictionary_coherence"], abs=COH_TOL)
+
+
+def _check_eval(m, ref, rel):
+    for k in ("l0", "l1", "mse", "normalized_mse", "sse_sae", "sse_baseline"):
+        assert getattr(m, k) == pytest.approx(float(ref[k]), rel=rel), k
+    for k in ("n_dead", "n_almost_dead", "n_dense"):
+        assert getattr(m, k) == int(ref[k]), k
+    ref_f, ref_mv = torch.as_tensor(ref["freqs"]), torch.as_tensor(ref["mean_values"])
+    assert torch.equal(m.freqs, ref_f)
+    fired = ref_f > 0
+    assert torch.allclose(m.mean_values[fired], ref_mv[fired], rtol=1e-4, atol=1e-6)
+    assert torch.isnan(m.mean_values[~fired]).all()
+
+
+def test_evaluate_matches_reference_capture():
+    """saev_b200.evaluate over the validation set the live reference evaluated (oracle/gen_golden_log.py), through the
+    nn mirror: same SAE parameters, all rows once -> the EvalMetrics the reference returned (train.py:510-618)."""
+    from saev_b200 import evaluate as ev
+    from saev_b200 import nn
+
+    z = np.load(GOLDEN / "evaluate.npz")
+    D, S = z["param_W_enc"].shape
+    sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=D, d_sae=S, activation=nn.TopK(top_k=int(z["top_k"])),
+                                                          reinit_blend=0.0))
+    sae.load_state_dict({k: torch.from_numpy(z[f"param_{k}"]) for k in ("W_dec", "b_dec", "W_enc", "b_enc")})
+    sae = sae.to("cuda")
+    obj = nn.get_objective(nn.Matryoshka(n_prefixes=1))
+    acts, bs = torch.from_numpy(z["acts"]), int(z["batch_size"])
+    batches = [{"act": acts[i:i + bs]} for i in range(0, acts.shape[0], bs)]
+    (m,) = ev.evaluate_batches(batches, [sae], [obj])
+    _check_eval(m, z, rel=2e-5)
+
+
+@pytest.mark.parametrize("act", ["topk", "relu"])
+def test_eval_accumulate_matches_oracle(act):
+    """Engine-level, ragged last batch, both activations (ReLU reads the dense bf16 pieces of the workspace)."""
+    from oracle import sae_oracle as orc
+    from saev_b200 import evaluate as ev
+    from saev_b200.engine import Engine, EngineConfig
+
+    D, S, K, B = 64, 768, 8, 200
+    g = torch.Generator().manual_seed(21)
+    W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
+    b_enc = 0.05 * torch.randn(S, generator=g) - (0.3 if act == "relu" else 0.0)
+    xs = [torch.randn(n, D, generator=g) for n in (B, B, 77)]
+    cfg = orc.OracleConfig(d_model=D, d_sae=S, activation=act, top_k=K, l1_coeff=4e-4 if act == "relu" else 0.0)
+    ref = orc.evaluate(cfg, orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec), xs)
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, activation=act, l1_coeff=cfg.l1_coeff, aux=False, max_batch=B))
+    eng.load_params(W_enc, b_enc, W_dec, b_dec)
+    st = eng.new_eval_state()
+    for x in xs:
+        xd = x.cuda()
+        eng.forward(xd, training=False)
+        eng.eval_accumulate(xd, st)
+    m = ev.finish_metrics(st)
+    if act == "relu":  # pre-activations within fp32 rounding of 0 may flip sign: counts can differ by a few
+        assert abs(m.n_dead - ref["n_dead"]) <= 1 and abs(m.n_dense - ref["n_dense"]) <= 2
+        assert (m.freqs - ref["freqs"]).abs().max() <= 2.5 / 477
+        for k in ("l0", "l1", "mse", "normalized_mse", "sse_sae", "sse_baseline"):
+            assert getattr(m, k) == pytest.approx(ref[k], rel=1e-3 if k == "l0" else 2e-5), k
+    else:
+        _check_eval(m, ref, rel=2e-5)

@@ -248,6 +248,7 @@ def test_install_rebinds_and_restores_saev_names():
     sys.path[:0] = [stubs, str(ref_src)]
     try:
         import saev.data
+        import saev.framework.train as ref_train
         import saev.nn
         import saev.nn.modeling as M
 
@@ -256,8 +257,10 @@ def test_install_rebinds_and_restores_saev_names():
 
         orig = (saev.nn.SparseAutoencoder, saev.nn.get_objective, torch.optim.Adam, torch.nn.utils.clip_grad_norm_,
                 saev.data.ShuffledDataLoader)
+        orig_eval = ref_train.evaluate
         saev_b200.install()
         try:
+            assert ref_train.evaluate is not orig_eval and ref_train.evaluate.__name__ == "evaluate_b200"
             assert torch.optim.Adam is optim.FusedAdam and torch.nn.utils.clip_grad_norm_ is optim.clip_grad_norm_
             assert saev.data.ShuffledDataLoader is data.ShuffledDataLoader
             sae = saev.nn.SparseAutoencoder(M.SparseAutoencoderConfig(d_model=16, d_sae=64, reinit_blend=0.0))
@@ -270,5 +273,40 @@ def test_install_rebinds_and_restores_saev_names():
             saev_b200.uninstall()
         assert (saev.nn.SparseAutoencoder, saev.nn.get_objective, torch.optim.Adam, torch.nn.utils.clip_grad_norm_,
                 saev.data.ShuffledDataLoader) == orig
+        assert ref_train.evaluate is orig_eval
     finally:
         del sys.path[:2]
+
+
+def test_finish_metrics_builds_saev_evalmetrics_from_accumulators():
+    """saev_b200.evaluate.finish_metrics = train.py:568-616 on the accumulator layout of saev_b200_eval_accumulate;
+    in drop-in mode the result is saev's own (beartype-checked) EvalMetrics."""
+    from saev_b200 import evaluate as ev
+
+    D, S, n_tok = 4, 6, 10
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n_tok, D, generator=g, dtype=torch.float64)
+    acc = torch.zeros(8 + D, dtype=torch.float64)
+    acc[0], acc[1], acc[4], acc[5], acc[6], acc[7] = (x * x).sum(), 3.5, 2.0 * n_tok, 7.0 * n_tok, 0.25 * n_tok, n_tok
+    acc[8:] = x.sum(0)
+    state = dict(acc=acc, n_fired=torch.tensor([0.0, 1.0, 10.0, 0.0, 3.0, 5.0]), values=torch.tensor([0.0, 2.0, 5.0, 0.0, -3.0, 1.0]))
+    m = ev.finish_metrics(state)
+    base = float((x * x).sum() - x.sum(0).dot(x.sum(0)) / n_tok)
+    assert m.sse_baseline == pytest.approx(base) and m.normalized_mse == pytest.approx(3.5 / base)
+    assert (m.l0, m.l1, m.mse) == pytest.approx((2.0, 7.0, 0.25))
+    assert (m.n_dead, m.n_almost_dead, m.n_dense) == (2, 2, 4)
+    assert torch.allclose(m.freqs, torch.tensor([0.0, 0.1, 1.0, 0.0, 0.3, 0.5]))
+    assert torch.isnan(m.mean_values[0]) and m.mean_values[2] == 0.5 and m.mean_values[4] == -1.0
+    ref_src = pathlib.Path("/root/reference/src")
+    if ref_src.exists():
+        import sys
+
+        stubs = str(pathlib.Path(__file__).resolve().parent.parent / "oracle" / "ref_stubs")
+        sys.path[:0] = [stubs, str(ref_src)]
+        try:
+            import saev.framework.train as ref_train
+
+            r = ev.finish_metrics(state, ref_train.EvalMetrics)
+            assert isinstance(r, ref_train.EvalMetrics) and r.n_dense == 4 and r.l1 == pytest.approx(7.0)
+        finally:
+            del sys.path[:2]

@@ -173,3 +173,28 @@ def test_dictionary_coherence_blocked_equals_direct():
     direct = (Wn @ Wn.T).abs().triu(1).max()  # train.py:417-418 verbatim
     assert float(orc.dictionary_coherence(W, block=64)) == pytest.approx(float(direct), rel=1e-6)
     assert float(orc.dictionary_coherence(W[:1])) == 0.0
+
+
+def test_evaluate_matches_reference_capture():
+    """oracle.evaluate against the EvalMetrics the live reference returned (train.py:510-618) for the same SAE
+    parameters and validation set (oracle/gen_golden_log.py)."""
+    import numpy as np
+
+    from tests.golden_util import GOLDEN
+
+    z = np.load(GOLDEN / "evaluate.npz")
+    acts = torch.from_numpy(z["acts"])
+    D, S = z["param_W_enc"].shape
+    cfg = orc.OracleConfig(d_model=D, d_sae=S, top_k=int(z["top_k"]))
+    st = orc.OracleState.from_params(*(torch.from_numpy(z[f"param_{k}"]) for k in ("W_enc", "b_enc", "W_dec", "b_dec")))
+    bs = int(z["batch_size"])
+    got = orc.evaluate(cfg, st, [acts[i:i + bs] for i in range(0, acts.shape[0], bs)])
+    for k in ("l0", "l1", "mse", "normalized_mse", "sse_sae", "sse_baseline"):
+        assert got[k] == pytest.approx(float(z[k]), rel=1e-5), k  # batch composition differs (random loader order)
+    for k in ("n_dead", "n_almost_dead", "n_dense"):
+        assert got[k] == int(z[k]), k
+    assert torch.equal(got["freqs"], torch.from_numpy(z["freqs"]))
+    ref_mean = torch.from_numpy(z["mean_values"])
+    fired = got["freqs"] > 0
+    assert torch.allclose(got["mean_values"][fired], ref_mean[fired], rtol=1e-4, atol=1e-6)
+    assert torch.isnan(got["mean_values"][~fired]).all() and torch.isnan(ref_mean[~fired]).all()  # 0 / 0 as in the reference

@@ -142,7 +142,10 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
                      int* entries, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s);
 
 struct WgradArgs {
-  const int* feat_off; const int* entries; const float* topk_val; const float* dh;
+  const int* feat_off; const int* entries; const float* topk_val;
+  const float* dh;                     // null: computed in the kernel from resid / W_dec (single prefix, d_model <= 1024)
+  float l1_over_b = 0.f;               // only read when dh == null
+  int l2_hint = 0;                     // bit 0: x rows, bit 1: residual rows gathered with L2 evict_last priority
   const float* resid; const float* x; const float* W_dec;
   int B, D, S, K;
   float grad_scale; int remove_parallel;

@@ -29,6 +29,20 @@ namespace sb {
   } while (0)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 16-byte read-only load with an L2 eviction-priority hint (policy from l2_policy_evict_last / _first): used to keep a
+// gather set (x / residual rows) resident against the streaming traffic of the same kernel
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* p, unsigned long long pol) {
+  float4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
   acc.x = fmaf(s, v.x, acc.x);
@@ -845,8 +859,12 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
 //   gW_enc_t[j] = sum dh_bk * x_b ;  gb_enc[j] = sum dh_bk
 // Atoms that did not fire get zero rows (the dense .grad tensors saev's loop expects).
 // ------------------------------------------------------------------------------------------------
-template <int VPL>
+// FUSE_DH: d loss / d h of every active entry is computed here, dh_bk = grad_scale * <r_b, W_dec[j]> (+ l1 / B * sign f),
+// from the residual row the entry gathers anyway and this atom's dictionary row (staged in shared memory) -- which
+// removes the second gather pass of the decode kernel (K dictionary rows per sample).
+template <int VPL, bool FUSE_DH, int HINT>
 __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
+  __shared__ float4 wsm[FUSE_DH ? 8 * VPL * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = a.row_begin + blockIdx.x * 8 + warp;
   if (j >= a.row_end) return;
@@ -858,6 +876,17 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
 #pragma unroll
   for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
   float sdh = 0.f;
+  const unsigned long long pol = l2_policy_evict_last();
+  float4* wmine = wsm + (FUSE_DH ? warp * VPL * 32 : 0);
+  if (FUSE_DH && beg != end) {
+    const float* wrow0 = a.W_dec + static_cast<long long>(j) * a.D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      wmine[v] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow0 + 4 * v)) : make_float4(0, 0, 0, 0);
+    }
+    __syncwarp();
+  }
   // Matryoshka: column j sits in prefix block c(j) and sees the suffix sum of the residuals of prefixes >= c(j)
   const float* rbase = a.resid;
   long long rstride = a.D;
@@ -875,23 +904,57 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
       const int p = a.entries[e];
       mb = p / a.K;
       mf = a.topk_val[p];
-      md = a.dh[p];
-      sdh += md;
+      if (!FUSE_DH) {
+        md = a.dh[p];
+        sdh += md;
+      }
     }
     const int cnt = min(32, end - e0);
+    if (FUSE_DH) {
+      // (measured at c3: decode 0.47 -> 0.27 ms, this kernel 0.69 -> 0.88 ms; a two-loop variant that separates the
+      //  residual and the x gathers was slower still, 0.99 ms -- the option stays off by default)
+      float sd = 0.f;
 #pragma unroll 2
-    for (int t = 0; t < cnt; ++t) {
-      const int bb = __shfl_sync(FULL, mb, t);
-      const float f = __shfl_sync(FULL, mf, t);
-      const float d = __shfl_sync(FULL, md, t);
-      const float* rrow = rbase + static_cast<long long>(bb) * rstride;
-      const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+      for (int t = 0; t < cnt; ++t) {
+        const int bb = __shfl_sync(FULL, mb, t);
+        const float f = __shfl_sync(FULL, mf, t);
+        const float* rrow = rbase + static_cast<long long>(bb) * rstride;
+        const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+        float4 xv[VPL];
+        float pd = 0.f;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < D4) {
-          fma4(gd[i], f, ldg4(rrow + 4 * v));
-          fma4(ge[i], d, ldg4(xrow + 4 * v));
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          xv[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);  // issued before the reduction below
+          if (v < D4) {
+            const float4 rv = ldg4(rrow + 4 * v);
+            fma4(gd[i], f, rv);
+            pd += dot4(rv, wmine[v]);
+          }
+        }
+        pd = warp_sum(pd);
+        float d = a.grad_scale * pd;
+        if (a.l1_over_b != 0.f) d += a.l1_over_b * ((f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f));
+        sd += d;  // warp-uniform
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) fma4(ge[i], d, xv[i]);
+      }
+      if (lane == 0) sdh += sd;
+    } else {
+#pragma unroll 2
+      for (int t = 0; t < cnt; ++t) {
+        const int bb = __shfl_sync(FULL, mb, t);
+        const float f = __shfl_sync(FULL, mf, t);
+        const float d = __shfl_sync(FULL, md, t);
+        const float* rrow = rbase + static_cast<long long>(bb) * rstride;
+        const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < D4) {
+            fma4(gd[i], f, (HINT & 2) ? ldg4_hint(rrow + 4 * v, pol) : ldg4(rrow + 4 * v));
+            fma4(ge[i], d, (HINT & 1) ? ldg4_hint(xrow + 4 * v, pol) : ldg4(xrow + 4 * v));
+          }
         }
       }
     }
@@ -921,7 +984,8 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     gd[i].x *= a.grad_scale; gd[i].y *= a.grad_scale; gd[i].z *= a.grad_scale; gd[i].w *= a.grad_scale;
-    w[i] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow + 4 * v)) : make_float4(0, 0, 0, 0);
+    if (FUSE_DH) w[i] = wmine[v];
+    else w[i] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow + 4 * v)) : make_float4(0, 0, 0, 0);
     dot += dot4(gd[i], w[i]);
     nsq += dot4(w[i], w[i]);
   }
@@ -954,7 +1018,21 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
   const int rows = a.row_end - a.row_begin;
   if (rows <= 0) return 0;
-  SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
+  if (a.dh == nullptr) {  // fused dh: dictionary row staged in (static) shared memory, d_model <= 1024
+    const int need = (a.D + 127) / 128;
+    ++g_launch_count;
+    if (need <= 1) wgrad_kernel<1, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    else if (need <= 2) wgrad_kernel<2, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    else if (need <= 4) wgrad_kernel<4, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    else if (need <= 6) wgrad_kernel<6, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    else if (need <= 8) wgrad_kernel<8, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    else return 20;
+    return cudaGetLastError() == cudaSuccess ? 0 : 22;
+  }
+  if (a.l2_hint == 1) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 1><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
+  else if (a.l2_hint == 2) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 2><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
+  else if (a.l2_hint == 3) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 3><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
+  else { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 0><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

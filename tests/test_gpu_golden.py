@@ -88,6 +88,14 @@ def test_cuda_path_replays_reference_run(name):
         assert eng.unsafe_rows() == 0
 
 
+@pytest.mark.parametrize("name", ["c1_topk_auxk_live", "tiny_topk_auxk_clamp"])
+def test_dh_inside_weight_gradient_kernel_replays_reference_run(name, monkeypatch):
+    """SAEV_B200_FUSE_DH=1 (read at create): d loss / d h is computed by the weight-gradient kernel instead of the
+    decode kernel's second pass; same golden run, same tolerances."""
+    monkeypatch.setenv("SAEV_B200_FUSE_DH", "1")
+    test_cuda_path_replays_reference_run(name)
+
+
 def test_fused_renorm_equals_start_of_step_normalize():
     """Hoisting normalize_w_dec (train.py:334-335) into the Adam tail gives the same next-step state."""
     z, meta, cfg = load_case("c1_topk")

@@ -253,6 +253,9 @@ def main():
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap"],
                     help="gradient exchange for N > 1 (see saev_b200/parallel.py)")
+    ap.add_argument("--dense-features", type=int, default=0,
+                    help="diagnostic (not the headline workload): give this many atoms a large encoder bias so that they "
+                         "fire on every row, like the dense features of a real run")
     ap.add_argument("--n-prefixes", type=int, default=1,
                     help="Matryoshka prefixes (1 = the north-star objective; 10 = saev's default objective)")
     ap.add_argument("--gather-ctas", type=int, default=16)
@@ -296,6 +299,8 @@ def main():
                               dead_threshold_tokens=10_000_000, max_batch=B, max_prefixes=max(1, args.n_prefixes)),
                  device=dev)
     eng.init_params(seed=0)
+    if args.dense_features > 0:
+        eng.b_enc[:: max(1, S // args.dense_features)][: args.dense_features] = 8.0
     if args.dp_mode == "auto":
         # measured on B200 (profiles/README.md): at 2 ranks the chunked all-reduce hidden behind the weight-gradient
         # kernel wins (5.47 ms); from 4 ranks on the row-sharded optimizer whose fp32 all-gathers run beside the next

@@ -22,7 +22,7 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
-      entries, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
+      entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
   size_t tc_we[3], tc_wd[3], tc_wdT[3], tc_x[3], tc_xT[3], tc_f[3], tc_fT[3], tc_r[3], tc_rT[3];
@@ -182,6 +182,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
                          // [4] max_j ||W_enc_t[j]||^2 [5] merged list entries (uint)
   w.sfx = take(c.max_prefixes > 1 ? B * static_cast<size_t>(c.max_prefixes) * D * 4 : 0);
   w.block_totals = take(((S + 1023) / 1024) * 4);
+  w.heavy_list = take((B * K / WGRAD_HEAVY_ENTRIES + 2) * 4);  // [0] = count, then the atoms
   w.row_gsq = take(S * 4);
   w.colsum_partial = take(static_cast<size_t>(colsum_partial_rows(static_cast<int>(B))) * D * 4);
   w.sumsq_partial = take(SUMSQ_MAX_RANGES * 1024 * 8);
@@ -775,7 +776,8 @@ int bwd_csc(const BwdCtx& c) {
   StageTimer tm(h, SAEV_B200_STAGE_CSC, c.s);
   if (launch_csc_build(c.topk_idx, c.B, h->cfg.top_k, h->cfg.d_sae, at<int>(c.workspace, w.feat_count),
                        at<int>(c.workspace, w.feat_off), at<int>(c.workspace, w.cursor), at<int>(c.workspace, w.entries),
-                       at<int>(c.workspace, w.block_totals), c.s))
+                       at<int>(c.workspace, w.block_totals), c.s, at<int>(c.workspace, w.heavy_list) + 1,
+                       at<int>(c.workspace, w.heavy_list)))
     return fail(h, 51, "backward: CSC build launch failed%s");
   return 0;
 }
@@ -791,8 +793,12 @@ int bwd_wgrad(const BwdCtx& c, int row_begin, int row_end, const long long* skip
   g.dh = h->dh_fused_fwd ? nullptr : at<float>(c.workspace, w.dh);
   g.l1_over_b = h->cfg.l1_coeff != 0.f ? static_cast<float>(h->cfg.l1_coeff / static_cast<double>(c.tokens_global)) : 0.f;
   {
-    static const int hint = [] { const char* v = getenv("SAEV_B200_WGRAD_HINT"); return v ? atoi(v) : 0; }();
-    g.l2_hint = hint;
+    static const int wpb = [] { const char* v = getenv("SAEV_B200_WGRAD_WPB"); return v ? atoi(v) : 1; }();
+    g.warps_per_block = wpb;
+    static const bool heavy = [] { const char* v = getenv("SAEV_B200_WGRAD_HEAVY"); return !(v && v[0] == '0'); }();
+    g.heavy_list = (heavy && !h->dh_fused_fwd) ? at<int>(c.workspace, w.heavy_list) + 1 : nullptr;
+    g.n_heavy = at<int>(c.workspace, w.heavy_list);
+    g.heavy_ticket = at<int>(c.workspace, w.cursor);
   }
   g.resid = c.resid;
   g.x = c.x;

@@ -138,14 +138,19 @@ int launch_decode_prefix(const DecodeArgs& a, const PrefixCuts& pf, float* sfx, 
 // x_hats[b, i, :] = x[b, :] + r_i = x + sfx[b, i] - sfx[b, i + 1]
 int launch_x_hats_prefix(const float* sfx, const float* x, int B, int D, int P, float* out, cudaStream_t s);
 
+constexpr int WGRAD_HEAVY_ENTRIES = 512;
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
-                     int* entries, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s);
+                     int* entries, int* block_totals /* [ceil(S/1024)] scratch */, cudaStream_t s,
+                     int* heavy_list = nullptr /* [B K / WGRAD_HEAVY_ENTRIES + 1] */, int* n_heavy = nullptr);
 
 struct WgradArgs {
   const int* feat_off; const int* entries; const float* topk_val;
   const float* dh;                     // null: computed in the kernel from resid / W_dec (single prefix, d_model <= 1024)
   float l1_over_b = 0.f;               // only read when dh == null
-  int l2_hint = 0;                     // bit 0: x rows, bit 1: residual rows gathered with L2 evict_last priority
+  const int* heavy_list = nullptr;     // atoms with more than WGRAD_HEAVY_ENTRIES entries (built with the CSC), handled by
+  int* heavy_ticket = nullptr;         // [S] ints (the CSC fill cursor, free by then): slices of a heavy atom finished
+  const int* n_heavy = nullptr;        // a block each; null: every atom by one warp
+  int warps_per_block = 1;             // atoms (warps) per block of wgrad_kernel, 1..8
   const float* resid; const float* x; const float* W_dec;
   int B, D, S, K;
   float grad_scale; int remove_parallel;

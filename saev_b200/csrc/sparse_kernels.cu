@@ -29,20 +29,6 @@ namespace sb {
   } while (0)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-// 16-byte read-only load with an L2 eviction-priority hint (policy from l2_policy_evict_last / _first): used to keep a
-// gather set (x / residual rows) resident against the streaming traffic of the same kernel
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-  unsigned long long pol;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ float4 ldg4_hint(const float* p, unsigned long long pol) {
-  float4 v;
-  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p), "l"(pol));
-  return v;
-}
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
   acc.x = fmaf(s, v.x, acc.x);
@@ -755,8 +741,10 @@ int launch_x_hats_prefix(const float* sfx, const float* x, int B, int D, int P, 
 // ------------------------------------------------------------------------------------------------
 // Two-level exclusive scan of the per-atom counts (1024 atoms per block): block totals first, then every block
 // adds the totals of the blocks before it to its local scan.
-__global__ void __launch_bounds__(1024) block_totals_kernel(const int* __restrict__ cnt, int S, int* __restrict__ totals) {
+__global__ void __launch_bounds__(1024) block_totals_kernel(const int* __restrict__ cnt, int S, int* __restrict__ totals,
+                                                            int* __restrict__ n_heavy) {
   __shared__ int ws[32];
+  if (n_heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *n_heavy = 0;  // appended to by scan_counts_kernel
   const int i = blockIdx.x * 1024 + threadIdx.x;
   int c = (i < S) ? cnt[i] : 0;
   c = warp_sum(c);
@@ -815,11 +803,15 @@ __device__ __forceinline__ int block_scan_incl(int v, int* ws, int* tot) {
 }
 
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict__ cnt, const int* __restrict__ totals,
-                                                           int* __restrict__ off, int* __restrict__ cursor, int S) {
+                                                           int* __restrict__ off, int* __restrict__ cursor, int S,
+                                                           int heavy_thr, int* __restrict__ heavy_list,
+                                                           int* __restrict__ n_heavy) {
   __shared__ int ws[32];
   const int prefix = block_prefix(totals, ws);
   const int i = blockIdx.x * 1024 + threadIdx.x;
   const int c = (i < S) ? cnt[i] : 0;
+  // atoms with very long lists ("dense" features) get a whole block in wgrad_heavy_kernel instead of one warp
+  if (heavy_list != nullptr && c > heavy_thr) heavy_list[atomicAdd(n_heavy, 1)] = i;
   int tot;
   const int incl = block_scan_incl(c, ws, &tot);
   if (i < S) {
@@ -840,11 +832,12 @@ __global__ void csc_fill_kernel(const int* __restrict__ idx, long long n, const 
 }
 
 int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_count, int* feat_off, int* cursor,
-                     int* entries, int* block_totals, cudaStream_t s) {
+                     int* entries, int* block_totals, cudaStream_t s, int* heavy_list, int* n_heavy) {
   const int nb = (S + 1023) / 1024;
-  block_totals_kernel<<<nb, 1024, 0, s>>>(feat_count, S, block_totals);
+  block_totals_kernel<<<nb, 1024, 0, s>>>(feat_count, S, block_totals, n_heavy);
   ++g_launch_count;
-  scan_counts_kernel<<<nb, 1024, 0, s>>>(feat_count, block_totals, feat_off, cursor, S);
+  scan_counts_kernel<<<nb, 1024, 0, s>>>(feat_count, block_totals, feat_off, cursor, S, WGRAD_HEAVY_ENTRIES, heavy_list,
+                                         n_heavy);
   ++g_launch_count;
   const long long n = static_cast<long long>(B) * K;
   csc_fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(topk_idx, n, feat_off, cursor, entries);
@@ -862,21 +855,35 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
 // FUSE_DH: d loss / d h of every active entry is computed here, dh_bk = grad_scale * <r_b, W_dec[j]> (+ l1 / B * sign f),
 // from the residual row the entry gathers anyway and this atom's dictionary row (staged in shared memory) -- which
 // removes the second gather pass of the decode kernel (K dictionary rows per sample).
-template <int VPL, bool FUSE_DH, int HINT>
+template <int VPL, bool FUSE_DH>
 __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
   __shared__ float4 wsm[FUSE_DH ? 8 * VPL * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = a.row_begin + blockIdx.x * 8 + warp;
+  // warps of a block hold their SM slot until the slowest one is done and the list lengths vary (Poisson around
+  // B K / S), so small blocks (a.warps_per_block, default 1) keep more warps busy
+  const int j = a.row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
   if (j >= a.row_end) return;
   const int D4 = a.D >> 2;
   const int beg = a.feat_off[j], end = a.feat_off[j + 1];
   // staged backward: the AuxK kernels have already written the rows of the dead atoms (which never fire)
   if (a.skip_toks != nullptr && beg == end && a.skip_toks[j] >= a.skip_threshold) return;
+  if (a.heavy_list != nullptr && end - beg > WGRAD_HEAVY_ENTRIES) {  // wgrad_heavy_kernel's: hand it zeroed rows
+    float* gdrow0 = a.gW_dec + static_cast<long long>(j) * a.D;
+    float* gerow0 = a.gW_enc_t + static_cast<long long>(j) * a.D;
+    for (int v = lane; v < D4; v += 32) {
+      *reinterpret_cast<float4*>(gdrow0 + 4 * v) = make_float4(0, 0, 0, 0);
+      *reinterpret_cast<float4*>(gerow0 + 4 * v) = make_float4(0, 0, 0, 0);
+    }
+    if (lane == 0) {
+      a.gb_enc[j] = 0.f;
+      a.heavy_ticket[j] = 0;
+    }
+    return;
+  }
   float4 gd[VPL], ge[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
   float sdh = 0.f;
-  const unsigned long long pol = l2_policy_evict_last();
   float4* wmine = wsm + (FUSE_DH ? warp * VPL * 32 : 0);
   if (FUSE_DH && beg != end) {
     const float* wrow0 = a.W_dec + static_cast<long long>(j) * a.D;
@@ -952,8 +959,8 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
         for (int i = 0; i < VPL; ++i) {
           const int v = lane + 32 * i;
           if (v < D4) {
-            fma4(gd[i], f, (HINT & 2) ? ldg4_hint(rrow + 4 * v, pol) : ldg4(rrow + 4 * v));
-            fma4(ge[i], d, (HINT & 1) ? ldg4_hint(xrow + 4 * v, pol) : ldg4(xrow + 4 * v));
+            fma4(gd[i], f, ldg4(rrow + 4 * v));
+            fma4(ge[i], d, ldg4(xrow + 4 * v));
           }
         }
       }
@@ -1014,29 +1021,189 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
   if (lane == 0) a.gb_enc[j] = sdh;
 }
 
-int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
+// Atoms whose list is longer than WGRAD_HEAVY_ENTRIES ("dense" features that fire on a large share of the batch).  One
+// warp per atom would stream the whole list alone (a feature firing on every row of a 16 k batch = 134 MB of gathers;
+// measured 14 ms for 8 such atoms at c3), so the list is cut into slices of WGRAD_SLICE entries and every
+// (atom, slice) is one block: its 8 warps take interleaved 32-entry chunks, fold their partial rows in a fixed order
+// through shared memory and warp 0 adds the slice's row into the gradient rows with vector RED (wgrad_kernel zeroed
+// them and the atom's ticket when it skipped the atom).  The block that draws the last ticket finishes the row
+// (scale, projection, ||g||^2) as wgrad_kernel does.
+constexpr int WGRAD_SLICE = 1024;
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, 2) wgrad_heavy_kernel(WgradArgs a) {
+  __shared__ float4 sgd[VPL * 32], sge[VPL * 32];
+  __shared__ float ssd[8];
+  __shared__ int s_ticket;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D4 = a.D >> 2;
+  const int n_heavy = *a.n_heavy;
+  int slice_base = 0;  // slices of the atoms walked so far: slice g of the whole list goes to block g % gridDim.x
+  for (int hi = 0; hi < n_heavy; ++hi) {
+    const int j = a.heavy_list[hi];
+    if (j < a.row_begin || j >= a.row_end) continue;  // block-uniform
+    const int beg = a.feat_off[j], end = a.feat_off[j + 1];
+    const int n_slices = (end - beg + WGRAD_SLICE - 1) / WGRAD_SLICE;
+    const int first = static_cast<int>((blockIdx.x + gridDim.x - slice_base % gridDim.x) % gridDim.x);
+    slice_base += n_slices;
+    const float* rbase = a.resid;
+    long long rstride = a.D;
+    if (a.sfx != nullptr) {
+      int c = 0;
+      while (c < a.pf.n - 1 && j >= a.pf.cut[c]) ++c;
+      rbase = a.sfx + static_cast<long long>(c) * a.D;
+      rstride = static_cast<long long>(a.pf.n) * a.D;
+    }
+    float* gdrow = a.gW_dec + static_cast<long long>(j) * a.D;
+    float* gerow = a.gW_enc_t + static_cast<long long>(j) * a.D;
+    for (int sl = first; sl < n_slices; sl += gridDim.x) {
+      const int sbeg = beg + sl * WGRAD_SLICE, send = min(end, sbeg + WGRAD_SLICE);
+      float4 gd[VPL], ge[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) gd[i] = ge[i] = make_float4(0, 0, 0, 0);
+      float sdh = 0.f;
+      for (int e0 = sbeg + warp * 32; e0 < send; e0 += 8 * 32) {
+        const int e = e0 + lane;
+        int mb = 0;
+        float mf = 0.f, md = 0.f;
+        if (e < send) {
+          const int p = a.entries[e];
+          mb = p / a.K;
+          mf = a.topk_val[p];
+          md = a.dh[p];
+          sdh += md;
+        }
+        const int cnt = min(32, send - e0);
+#pragma unroll 2
+        for (int t = 0; t < cnt; ++t) {
+          const int bb = __shfl_sync(FULL, mb, t);
+          const float f = __shfl_sync(FULL, mf, t);
+          const float d = __shfl_sync(FULL, md, t);
+          const float* rrow = rbase + static_cast<long long>(bb) * rstride;
+          const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < D4) {
+              fma4(gd[i], f, ldg4(rrow + 4 * v));
+              fma4(ge[i], d, ldg4(xrow + 4 * v));
+            }
+          }
+        }
+      }
+      sdh = warp_sum(sdh);
+      if (lane == 0) ssd[warp] = sdh;
+      for (int w = 7; w >= 0; --w) {  // warp 7 stores, 6 .. 1 add, warp 0 ends up with the slice total in registers
+        if (warp == w) {
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (w < 7) {
+              const float4 pd = sgd[v], pe = sge[v];
+              gd[i].x += pd.x; gd[i].y += pd.y; gd[i].z += pd.z; gd[i].w += pd.w;
+              ge[i].x += pe.x; ge[i].y += pe.y; ge[i].z += pe.z; ge[i].w += pe.w;
+            }
+            if (w > 0) {
+              sgd[v] = gd[i];
+              sge[v] = ge[i];
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < D4) {
+            red_add4(gdrow + 4 * v, gd[i]);
+            red_add4(gerow + 4 * v, ge[i]);
+          }
+        }
+        if (lane == 0) atomicAdd(a.gb_enc + j, ((ssd[0] + ssd[1]) + (ssd[2] + ssd[3])) + ((ssd[4] + ssd[5]) + (ssd[6] + ssd[7])));
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) s_ticket = atomicAdd(a.heavy_ticket + j, 1);
+      }
+      __syncthreads();
+      const bool last = s_ticket == n_slices - 1;
+      __syncthreads();  // s_ticket / ssd / sgd are reused by the next slice of this block
+      if (last && warp == 0) {
+        __threadfence();
+        const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+        float4 w[VPL];
+        float dot = 0.f, nsq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          gd[i] = (v < D4) ? __ldcg(reinterpret_cast<const float4*>(gdrow + 4 * v)) : make_float4(0, 0, 0, 0);
+          ge[i] = (v < D4) ? __ldcg(reinterpret_cast<const float4*>(gerow + 4 * v)) : make_float4(0, 0, 0, 0);
+          gd[i].x *= a.grad_scale; gd[i].y *= a.grad_scale; gd[i].z *= a.grad_scale; gd[i].w *= a.grad_scale;
+          w[i] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow + 4 * v)) : make_float4(0, 0, 0, 0);
+          dot += dot4(gd[i], w[i]);
+          nsq += dot4(w[i], w[i]);
+        }
+        if (a.remove_parallel) {
+          dot = warp_sum(dot);
+          nsq = warp_sum(nsq);
+          const float sc = (nsq > 0.f) ? dot / nsq : 0.f;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) fma4(gd[i], -sc, w[i]);
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < D4) {
+            __stcs(reinterpret_cast<float4*>(gdrow + 4 * v), gd[i]);
+            ss += dot4(gd[i], gd[i]) + dot4(ge[i], ge[i]);
+          }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0 && a.row_gsq != nullptr) {
+          const float sd = __ldcg(a.gb_enc + j);
+          a.row_gsq[j] = ss + sd * sd;
+        }
+      }
+    }
+  }
+}
+
+static int launch_wgrad_light(const WgradArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
   const int rows = a.row_end - a.row_begin;
   if (rows <= 0) return 0;
+  const int wpb = (a.warps_per_block >= 1 && a.warps_per_block <= 8) ? a.warps_per_block : 1;
+  const int nthr = 32 * wpb, nblk = (rows + wpb - 1) / wpb;
   if (a.dh == nullptr) {  // fused dh: dictionary row staged in (static) shared memory, d_model <= 1024
     const int need = (a.D + 127) / 128;
+    const int nthr = 256, nblk = (rows + 7) / 8;  // (the shared-memory stage is sized for 8 warps)
     ++g_launch_count;
-    if (need <= 1) wgrad_kernel<1, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
-    else if (need <= 2) wgrad_kernel<2, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
-    else if (need <= 4) wgrad_kernel<4, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
-    else if (need <= 6) wgrad_kernel<6, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
-    else if (need <= 8) wgrad_kernel<8, true, 0><<<(rows + 7) / 8, 256, 0, s>>>(a);
+    if (need <= 1) wgrad_kernel<1, true><<<nblk, nthr, 0, s>>>(a);
+    else if (need <= 2) wgrad_kernel<2, true><<<nblk, nthr, 0, s>>>(a);
+    else if (need <= 4) wgrad_kernel<4, true><<<nblk, nthr, 0, s>>>(a);
+    else if (need <= 6) wgrad_kernel<6, true><<<nblk, nthr, 0, s>>>(a);
+    else if (need <= 8) wgrad_kernel<8, true><<<nblk, nthr, 0, s>>>(a);
     else return 20;
     return cudaGetLastError() == cudaSuccess ? 0 : 22;
   }
-  if (a.l2_hint == 1) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 1><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
-  else if (a.l2_hint == 2) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 2><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
-  else if (a.l2_hint == 3) { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 3><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
-  else { SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false, 0><<<(rows + 7) / 8, 256, 0, s>>>(a))); }
+  SB_DISPATCH_VPL(a.D, (wgrad_kernel<VPL, false><<<nblk, nthr, 0, s>>>(a)));
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
 // ------------------------------------------------------------------------------------------------
+
+int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
+  if (int rc = launch_wgrad_light(a, s)) return rc;
+  if (a.heavy_list == nullptr || a.dh == nullptr || a.row_end <= a.row_begin) return 0;
+  const int grid = 148 * 2;  // every block walks the (device-side) heavy list and takes its slices; exits at once if empty
+  SB_DISPATCH_VPL(a.D, (wgrad_heavy_kernel<VPL><<<grid, 256, 0, s>>>(a)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 // out[d] (+)= scale * sum_b src[b,d]     (gb_dec; two deterministic stages)
 // ------------------------------------------------------------------------------------------------
 constexpr int COLSUM_ROWS_PER_BLOCK = 64;

@@ -118,6 +118,16 @@ def test_fused_renorm_equals_start_of_step_normalize():
                                           ("topk", 128, 1000, 16, 300)])
 @pytest.mark.parametrize("aux_path", ["tc", "sgemm", "auto"])
 def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
+    _midsize_run(act, D, S, K, B, aux_path, monkeypatch)
+
+
+def test_dense_features_take_the_block_per_atom_path(monkeypatch):
+    """Three atoms with a large encoder bias fire on every row of a 1400-row batch: their lists (> 512 entries) are
+    handled by wgrad_heavy_kernel (one block per atom) instead of one warp; same oracle, same tolerances."""
+    _midsize_run("topk", 256, 4096, 32, 1400, "auto", monkeypatch, dense_atoms=(5, 2049, 4095))
+
+
+def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=()):
     """Four steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile).
 
     The library has two AuxK implementations (tensor-core split contractions / fp32 tiles) and picks one per step from
@@ -134,6 +144,8 @@ def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
     W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
     b_enc = 0.02 * torch.randn(S, generator=g)
     b_dec = 0.02 * torch.randn(D, generator=g)
+    for j in dense_atoms:
+        b_enc[j] = 4.0
     l1 = 4e-4 if act == "relu" else 0.0
     ocfg = orc.OracleConfig(d_model=D, d_sae=S, activation=act, top_k=max(K, 1), l1_coeff=l1, aux=True, k_aux=64,
                             dead_threshold_tokens=2 * B, lr=1e-3, n_lr_warmup=2, n_steps=10)

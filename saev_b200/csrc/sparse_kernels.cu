@@ -238,14 +238,16 @@ __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* 
   __syncwarp();
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(32 * RESCORE_WARPS, 3) rescore_topk_kernel(RescoreArgs a) {
-  __shared__ int hist_s[RESCORE_WARPS][256];
-  __shared__ float sv_s[RESCORE_WARPS][RESCORE_CAP];
-  __shared__ int si_s[RESCORE_WARPS][RESCORE_CAP];
-  __shared__ float se_s[RESCORE_WARPS][RESCORE_CAP];
+// WPB rows (warps) per block; the rows of a block hold their SM slot until the slowest one (longest candidate list)
+// is done, so small blocks keep more warps busy (same 24 resident warps per SM either way)
+template <int VPL, int WPB>
+__global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(RescoreArgs a) {
+  __shared__ int hist_s[WPB][256];
+  __shared__ float sv_s[WPB][RESCORE_CAP];
+  __shared__ int si_s[WPB][RESCORE_CAP];
+  __shared__ float se_s[WPB][RESCORE_CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * RESCORE_WARPS + warp;
+  const int b = blockIdx.x * WPB + warp;
   if (b >= a.B) return;
   const int D4 = a.D >> 2;
   float* sv = sv_s[warp];  // screen values
@@ -381,8 +383,13 @@ int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
   ++g_launch_count;
   const int need_ = (a.D + 127) / 128;
-#define SB_RESCORE(V) \
-  rescore_topk_kernel<V><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, 0, s>>>(a);
+  static const int wpb = [] { const char* v = getenv("SAEV_B200_RESCORE_WPB"); return v ? atoi(v) : 1; }();
+#define SB_RESCORE(V)                                                                        \
+  {                                                                                          \
+    if (wpb == 1) rescore_topk_kernel<V, 1><<<a.B, 32, 0, s>>>(a);                           \
+    else if (wpb == 2) rescore_topk_kernel<V, 2><<<(a.B + 1) / 2, 64, 0, s>>>(a);            \
+    else rescore_topk_kernel<V, RESCORE_WARPS><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, 0, s>>>(a); \
+  }
   if (need_ <= 1) SB_RESCORE(1)
   else if (need_ <= 2) SB_RESCORE(2)
   else if (need_ <= 4) SB_RESCORE(4)
@@ -404,7 +411,7 @@ int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
 template <int VPL>
 __global__ void __launch_bounds__(256, 2) decode_kernel(DecodeArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 8 + warp;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= a.B) return;
   const int D4 = a.D >> 2, K = a.K;
   float4 acc[VPL];
@@ -509,7 +516,8 @@ __global__ void __launch_bounds__(256, 2) decode_kernel(DecodeArgs a) {
 
 int launch_decode(const DecodeArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
-  SB_DISPATCH_VPL(a.D, (decode_kernel<VPL><<<(a.B + 7) / 8, 256, 0, s>>>(a)));
+  static const int wpb = [] { const char* v = getenv("SAEV_B200_DECODE_WPB"); const int w = v ? atoi(v) : 8; return (w >= 1 && w <= 8) ? w : 8; }();
+  SB_DISPATCH_VPL(a.D, (decode_kernel<VPL><<<(a.B + wpb - 1) / wpb, 32 * wpb, 0, s>>>(a)));
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

@@ -53,8 +53,9 @@ struct saev_b200_handle {
   bool nd_pending = false;
   int n_dead_lagged = 0;
   bool aux_tc_step = false;      // path chosen by the last forward (backward must match)
-  bool fuse_dh = false;          // SAEV_B200_FUSE_DH=1: d loss / d h computed inside the weight-gradient kernel instead of
-                                 // a second gather pass of the decode kernel (measured neutral at c3: 4.42 vs 4.44 ms)
+  bool fuse_dh = true;           // d loss / d h computed inside the weight-gradient kernel instead of a second gather pass
+                                 // of the decode kernel (c3: decode 0.47 -> 0.27 ms, wgrad 0.62 -> 0.74 ms);
+                                 // SAEV_B200_FUSE_DH=0 restores the two-pass decode
   bool dh_fused_fwd = false;     // the last training forward left dh to the backward
   bool aux_tc_always = false;    // SAEV_B200_AUX=tc: no selection (tests pin each path)
   int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
@@ -472,7 +473,7 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   h->ws = plan_workspace(h->cfg, h->aux_cap, h->max_pairs, h->dense_terms);
   {
     const char* v = getenv("SAEV_B200_FUSE_DH");
-    h->fuse_dh = h->cfg.d_model <= 1024 && v && v[0] == '1';
+    h->fuse_dh = h->cfg.d_model <= 1024 && !(v && v[0] == '0');
   }
   {
     const char* v = getenv("SAEV_B200_AUX");  // "sgemm" / "tc": pin one AuxK implementation; default: pick per step
@@ -796,7 +797,7 @@ int bwd_wgrad(const BwdCtx& c, int row_begin, int row_end, const long long* skip
     static const int wpb = [] { const char* v = getenv("SAEV_B200_WGRAD_WPB"); return v ? atoi(v) : 1; }();
     g.warps_per_block = wpb;
     static const bool heavy = [] { const char* v = getenv("SAEV_B200_WGRAD_HEAVY"); return !(v && v[0] == '0'); }();
-    g.heavy_list = (heavy && !h->dh_fused_fwd) ? at<int>(c.workspace, w.heavy_list) + 1 : nullptr;
+    g.heavy_list = heavy ? at<int>(c.workspace, w.heavy_list) + 1 : nullptr;
     g.n_heavy = at<int>(c.workspace, w.heavy_list);
     g.heavy_ticket = at<int>(c.workspace, w.cursor);
   }

@@ -863,9 +863,9 @@ int launch_csc_build(const int* topk_idx, int B, int K, int S, const int* feat_c
 // FUSE_DH: d loss / d h of every active entry is computed here, dh_bk = grad_scale * <r_b, W_dec[j]> (+ l1 / B * sign f),
 // from the residual row the entry gathers anyway and this atom's dictionary row (staged in shared memory) -- which
 // removes the second gather pass of the decode kernel (K dictionary rows per sample).
-template <int VPL, bool FUSE_DH>
+template <int VPL, bool FUSE_DH, int FUSE_WPB = 8>
 __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
-  __shared__ float4 wsm[FUSE_DH ? 8 * VPL * 32 : 1];
+  __shared__ float4 wsm[FUSE_DH ? FUSE_WPB * VPL * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps of a block hold their SM slot until the slowest one is done and the list lengths vary (Poisson around
   // B K / S), so small blocks (a.warps_per_block, default 1) keep more warps busy
@@ -926,8 +926,8 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
     }
     const int cnt = min(32, end - e0);
     if (FUSE_DH) {
-      // (measured at c3: decode 0.47 -> 0.27 ms, this kernel 0.69 -> 0.88 ms; a two-loop variant that separates the
-      //  residual and the x gathers was slower still, 0.99 ms -- the option stays off by default)
+      // (measured at c3 with one atom per block: decode 0.47 -> 0.27 ms, this kernel 0.62 -> 0.74 ms; a two-loop variant
+      //  that separates the residual and the x gathers was slower, as were two warps per atom and L2 evict_last hints)
       float sd = 0.f;
 #pragma unroll 2
       for (int t = 0; t < cnt; ++t) {
@@ -1041,9 +1041,10 @@ __device__ __forceinline__ void red_add4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int VPL>
+template <int VPL, bool FUSE_DH>
 __global__ void __launch_bounds__(256, 2) wgrad_heavy_kernel(WgradArgs a) {
   __shared__ float4 sgd[VPL * 32], sge[VPL * 32];
+  __shared__ float4 swr[FUSE_DH ? VPL * 32 : 1];  // this atom's dictionary row (dh computed here, see wgrad_kernel)
   __shared__ float ssd[8];
   __shared__ int s_ticket;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1067,6 +1068,12 @@ __global__ void __launch_bounds__(256, 2) wgrad_heavy_kernel(WgradArgs a) {
     }
     float* gdrow = a.gW_dec + static_cast<long long>(j) * a.D;
     float* gerow = a.gW_enc_t + static_cast<long long>(j) * a.D;
+    if (FUSE_DH && first < n_slices) {
+      const float* wrow0 = a.W_dec + static_cast<long long>(j) * a.D;
+      for (int v = threadIdx.x; v < VPL * 32; v += 256)
+        swr[v] = (v < D4) ? __ldg(reinterpret_cast<const float4*>(wrow0 + 4 * v)) : make_float4(0, 0, 0, 0);
+      __syncthreads();
+    }
     for (int sl = first; sl < n_slices; sl += gridDim.x) {
       const int sbeg = beg + sl * WGRAD_SLICE, send = min(end, sbeg + WGRAD_SLICE);
       float4 gd[VPL], ge[VPL];
@@ -1081,26 +1088,51 @@ __global__ void __launch_bounds__(256, 2) wgrad_heavy_kernel(WgradArgs a) {
           const int p = a.entries[e];
           mb = p / a.K;
           mf = a.topk_val[p];
-          md = a.dh[p];
-          sdh += md;
+          if (!FUSE_DH) {
+            md = a.dh[p];
+            sdh += md;
+          }
         }
         const int cnt = min(32, send - e0);
+        float sd = 0.f;
 #pragma unroll 2
         for (int t = 0; t < cnt; ++t) {
           const int bb = __shfl_sync(FULL, mb, t);
           const float f = __shfl_sync(FULL, mf, t);
-          const float d = __shfl_sync(FULL, md, t);
           const float* rrow = rbase + static_cast<long long>(bb) * rstride;
           const float* xrow = a.x + static_cast<long long>(bb) * a.D;
+          if (FUSE_DH) {
+            float4 xv[VPL];
+            float pd = 0.f;
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) {
-            const int v = lane + 32 * i;
-            if (v < D4) {
-              fma4(gd[i], f, ldg4(rrow + 4 * v));
-              fma4(ge[i], d, ldg4(xrow + 4 * v));
+            for (int i = 0; i < VPL; ++i) {
+              const int v = lane + 32 * i;
+              xv[i] = (v < D4) ? ldg4(xrow + 4 * v) : make_float4(0, 0, 0, 0);
+              if (v < D4) {
+                const float4 rv = ldg4(rrow + 4 * v);
+                fma4(gd[i], f, rv);
+                pd += dot4(rv, swr[v]);
+              }
+            }
+            pd = warp_sum(pd);
+            float d = a.grad_scale * pd;
+            if (a.l1_over_b != 0.f) d += a.l1_over_b * ((f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f));
+            sd += d;  // warp-uniform
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) fma4(ge[i], d, xv[i]);
+          } else {
+            const float d = __shfl_sync(FULL, md, t);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+              const int v = lane + 32 * i;
+              if (v < D4) {
+                fma4(gd[i], f, ldg4(rrow + 4 * v));
+                fma4(ge[i], d, ldg4(xrow + 4 * v));
+              }
             }
           }
         }
+        if (FUSE_DH && lane == 0) sdh += sd;
       }
       sdh = warp_sum(sdh);
       if (lane == 0) ssd[warp] = sdh;
@@ -1188,13 +1220,14 @@ static int launch_wgrad_light(const WgradArgs& a, cudaStream_t s) {
   const int nthr = 32 * wpb, nblk = (rows + wpb - 1) / wpb;
   if (a.dh == nullptr) {  // fused dh: dictionary row staged in (static) shared memory, d_model <= 1024
     const int need = (a.D + 127) / 128;
-    const int nthr = 256, nblk = (rows + 7) / 8;  // (the shared-memory stage is sized for 8 warps)
+    const int nthr = 256, nblk = (rows + 7) / 8;  // (the shared-memory stage is sized for 8 warps, or for 1)
+    const int fw = wpb == 1 ? 1 : 8;
     ++g_launch_count;
-    if (need <= 1) wgrad_kernel<1, true><<<nblk, nthr, 0, s>>>(a);
-    else if (need <= 2) wgrad_kernel<2, true><<<nblk, nthr, 0, s>>>(a);
-    else if (need <= 4) wgrad_kernel<4, true><<<nblk, nthr, 0, s>>>(a);
-    else if (need <= 6) wgrad_kernel<6, true><<<nblk, nthr, 0, s>>>(a);
-    else if (need <= 8) wgrad_kernel<8, true><<<nblk, nthr, 0, s>>>(a);
+    if (need <= 1) { if (fw == 1) wgrad_kernel<1, true, 1><<<rows, 32, 0, s>>>(a); else wgrad_kernel<1, true, 8><<<nblk, nthr, 0, s>>>(a); }
+    else if (need <= 2) { if (fw == 1) wgrad_kernel<2, true, 1><<<rows, 32, 0, s>>>(a); else wgrad_kernel<2, true, 8><<<nblk, nthr, 0, s>>>(a); }
+    else if (need <= 4) { if (fw == 1) wgrad_kernel<4, true, 1><<<rows, 32, 0, s>>>(a); else wgrad_kernel<4, true, 8><<<nblk, nthr, 0, s>>>(a); }
+    else if (need <= 6) { if (fw == 1) wgrad_kernel<6, true, 1><<<rows, 32, 0, s>>>(a); else wgrad_kernel<6, true, 8><<<nblk, nthr, 0, s>>>(a); }
+    else if (need <= 8) { if (fw == 1) wgrad_kernel<8, true, 1><<<rows, 32, 0, s>>>(a); else wgrad_kernel<8, true, 8><<<nblk, nthr, 0, s>>>(a); }
     else return 20;
     return cudaGetLastError() == cudaSuccess ? 0 : 22;
   }
@@ -1206,9 +1239,10 @@ static int launch_wgrad_light(const WgradArgs& a, cudaStream_t s) {
 
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
   if (int rc = launch_wgrad_light(a, s)) return rc;
-  if (a.heavy_list == nullptr || a.dh == nullptr || a.row_end <= a.row_begin) return 0;
+  if (a.heavy_list == nullptr || a.row_end <= a.row_begin) return 0;
   const int grid = 148 * 2;  // every block walks the (device-side) heavy list and takes its slices; exits at once if empty
-  SB_DISPATCH_VPL(a.D, (wgrad_heavy_kernel<VPL><<<grid, 256, 0, s>>>(a)));
+  if (a.dh == nullptr) { SB_DISPATCH_VPL(a.D, (wgrad_heavy_kernel<VPL, true><<<grid, 256, 0, s>>>(a))); }
+  else { SB_DISPATCH_VPL(a.D, (wgrad_heavy_kernel<VPL, false><<<grid, 256, 0, s>>>(a))); }
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

@@ -89,10 +89,10 @@ def test_cuda_path_replays_reference_run(name):
 
 
 @pytest.mark.parametrize("name", ["c1_topk_auxk_live", "tiny_topk_auxk_clamp"])
-def test_dh_inside_weight_gradient_kernel_replays_reference_run(name, monkeypatch):
-    """SAEV_B200_FUSE_DH=1 (read at create): d loss / d h is computed by the weight-gradient kernel instead of the
-    decode kernel's second pass; same golden run, same tolerances."""
-    monkeypatch.setenv("SAEV_B200_FUSE_DH", "1")
+def test_two_pass_decode_replays_reference_run(name, monkeypatch):
+    """By default d loss / d h is computed inside the weight-gradient kernel; SAEV_B200_FUSE_DH=0 (read at create) brings
+    back the decode kernel's second gather pass (also what d_model > 1024 and Matryoshka use).  Same golden run."""
+    monkeypatch.setenv("SAEV_B200_FUSE_DH", "0")
     test_cuda_path_replays_reference_run(name)
 
 
@@ -124,6 +124,11 @@ def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
 def test_dense_features_take_the_block_per_atom_path(monkeypatch):
     """Three atoms with a large encoder bias fire on every row of a 1400-row batch: their lists (> 512 entries) are
     handled by wgrad_heavy_kernel (one block per atom) instead of one warp; same oracle, same tolerances."""
+    _midsize_run("topk", 256, 4096, 32, 1400, "auto", monkeypatch, dense_atoms=(5, 2049, 4095))
+
+
+def test_dense_features_with_two_pass_decode(monkeypatch):
+    monkeypatch.setenv("SAEV_B200_FUSE_DH", "0")
     _midsize_run("topk", 256, 4096, 32, 1400, "auto", monkeypatch, dense_atoms=(5, 2049, 4095))
 
 

@@ -214,3 +214,46 @@ def test_split_contraction_accuracy(nterms, tol):
     ref = A.double() @ Bt.double().t() + bias.double()
     out = eng.gemm_nt(A, Bt, bias, nterms)
     assert rel_l2(out.cpu(), ref.cpu()) < tol
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_staged_backward_equals_one_shot_backward(fuse, monkeypatch):
+    """saev_b200_backward_stage (stage 0, then the weight-gradient rows in chunks -- what the overlapped data-parallel
+    exchange drives) must leave the same gradient bucket as saev_b200_backward, including atoms on the block-per-slice
+    path (dense features) and the AuxK rows of dead atoms, which the row chunks must leave alone."""
+    from oracle import sae_oracle as orc
+    from saev_b200.engine import Engine, EngineConfig
+
+    monkeypatch.setenv("SAEV_B200_FUSE_DH", fuse)
+    D, S, K, B = 256, 4096, 32, 1400
+    g = torch.Generator().manual_seed(77)
+    W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
+    b_enc = 0.02 * torch.randn(S, generator=g)
+    for j in (3, 1111, 4090):
+        b_enc[j] = 4.0
+    basis = torch.randn(24, D, generator=g)
+    engs = []
+    for _ in range(2):
+        e = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, activation="topk", aux=True, k_aux=64,
+                                dead_threshold_tokens=2 * B, max_batch=B))
+        e.load_params(W_enc, b_enc, W_dec, b_dec)
+        engs.append(e)
+    a, b = engs
+    chunks = [(0, 1000), (1000, 1008), (1008, 3000), (3000, S)]
+    for step in range(3):  # dead latents (AuxK live) from step 2
+        x = (torch.randn(B, 24, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)).cuda()
+        for e in (a, b):
+            e.normalize_w_dec()
+            e.forward(x, training=True)
+        a.backward(x)
+        b.backward_stage(x, 0)
+        for r0, r1 in chunks:
+            b.backward_stage(x, 1, r0, r1)
+        assert float(a.losses[5]) == float(b.losses[5])
+        for name in ("gW_enc_t", "gb_enc", "gW_dec", "gb_dec"):
+            ga, gb = getattr(a, name), getattr(b, name)
+            assert rel_l2(gb.cpu(), ga.cpu()) < 1e-6, (step, name)  # summation order inside an atom's list may differ
+        for e in (a, b):
+            e.grad_sumsq()
+            e.adam_step(1e-3, max_norm=1.0)
+    assert int(a.losses[5]) > 0, "the case must exercise AuxK"

@@ -213,6 +213,21 @@ class Output:
     def __iter__(self):  # NamedTuple-style unpacking: h_x, f_x, x_hats
         return iter((self.h_x, self.f_x, self.x_hats))
 
+    def f_x_csr(self, row_mask: Tensor | None = None):
+        """`scipy.sparse.csr_array(fwd.f_x)` (inference.py:236) without the dense matrix: built from the top-k lists of
+        the forward (TopK); the ReLU path, whose f_x is dense, converts it the reference's way."""
+        self._check()
+        eng = self._sae.engine
+        B = self._x.shape[0]
+        if eng.cfg.activation == "topk":
+            from .sparse import topk_to_csr
+
+            return topk_to_csr(eng.topk_idx[:B], eng.topk_val[:B], eng.S, row_mask)
+        import scipy.sparse
+
+        f = self.f_x if row_mask is None else self.f_x * row_mask.to(self.f_x.device)[:, None]
+        return scipy.sparse.csr_array(f.cpu().numpy())
+
     def log_metrics(self) -> dict[str, float]:
         """What saev's log block (train.py:380-423) derives from `acts_BD`, `fwd.x_hats`, `fwd.f_x` and `sae.W_dec`
         -- explained_variance, dead_unit_pct, dictionary_coherence, avg_decoder_row_norm, sse_sae, sse_baseline,

@@ -166,3 +166,30 @@ def test_eval_accumulate_matches_oracle(act):
             assert getattr(m, k) == pytest.approx(ref[k], rel=1e-3 if k == "l0" else 2e-5), k
     else:
         _check_eval(m, ref, rel=2e-5)
+
+
+def test_f_x_csr_equals_scipy_on_dense_f_x():
+    """Output.f_x_csr() (from the [B, K] lists) against scipy.sparse.csr_array of the dense f_x, as the reference's
+    inference dump builds it (inference.py:236), with masked rows (:234)."""
+    import scipy.sparse
+
+    from saev_b200 import nn
+
+    D, S, K, B = 64, 1024, 8, 200
+    torch.manual_seed(2)
+    sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=D, d_sae=S, activation=nn.TopK(top_k=K), reinit_blend=0.0))
+    sae = sae.to("cuda").eval()
+    x = torch.randn(B, D, device="cuda")
+    out = sae(x)
+    mask = torch.rand(B) > 0.2
+    dense = out.f_x.cpu().clone()
+    ref = scipy.sparse.csr_array(dense.numpy())
+    got = out.f_x_csr()
+    assert got.nnz == ref.nnz == B * K
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    assert np.array_equal(got.data, ref.data)
+    dense[~mask] = 0.0
+    ref_m = scipy.sparse.csr_array(dense.numpy())
+    got_m = out.f_x_csr(mask)
+    assert np.array_equal(got_m.indptr, ref_m.indptr) and np.array_equal(got_m.indices, ref_m.indices)
+    assert np.array_equal(got_m.data, ref_m.data)

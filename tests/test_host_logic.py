@@ -310,3 +310,35 @@ def test_finish_metrics_builds_saev_evalmetrics_from_accumulators():
             assert isinstance(r, ref_train.EvalMetrics) and r.n_dense == 4 and r.l1 == pytest.approx(7.0)
         finally:
             del sys.path[:2]
+
+
+def test_topk_lists_to_csr_equals_scipy_on_dense():
+    """saev_b200.sparse.topk_to_csr == scipy.sparse.csr_array(dense f_x) (inference.py:236), incl. empty slots,
+    exact zeros among the selected values, negative values, and masked rows (:234)."""
+    import numpy as np
+    import scipy.sparse
+
+    from saev_b200.sparse import topk_to_csr
+
+    g = torch.Generator().manual_seed(4)
+    B, K, S = 37, 8, 300
+    idx = torch.stack([torch.randperm(S, generator=g)[:K] for _ in range(B)]).to(torch.int32)
+    val = torch.randn(B, K, generator=g)
+    val[3, 2] = 0.0  # an exact zero that TopK happened to select is not stored by scipy either
+    idx[5, 6:] = -1  # empty slots (k > number of candidates)
+    val[5, 6:] = 0.0
+    mask = torch.ones(B, dtype=torch.bool)
+    mask[[0, 11]] = False
+    for m in (None, mask):
+        dense = torch.zeros(B, S)
+        for b in range(B):
+            for k in range(K):
+                if idx[b, k] >= 0:
+                    dense[b, idx[b, k]] = val[b, k]
+        if m is not None:
+            dense[~m] = 0.0
+        ref = scipy.sparse.csr_array(dense.numpy())
+        got = topk_to_csr(idx, val, S, m)
+        assert got.shape == ref.shape and got.nnz == ref.nnz
+        assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+        assert np.array_equal(got.data, ref.data) and got.has_canonical_format

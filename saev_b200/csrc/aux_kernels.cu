@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(SgemmArgs a) {
     if (a.dyn_which == 1) M = min(M, d);
     if (a.dyn_which == 2) N = min(N, d);
     if (a.dyn_which == 3) K = min(K, d);
+    // empty contraction (no dead latents): the only such call decodes into r_aux, which nobody reads in that case
+    if (a.dyn_which == 3 && K == 0) return;
   }
   const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + TN - 1) / TN;
   const long long tiles = static_cast<long long>(tiles_m) * tiles_n;
@@ -263,6 +265,10 @@ __global__ void __launch_bounds__(256) aux_resid_kernel(float* __restrict__ r_au
                                                         float* __restrict__ row_sse_aux) {
   const int n = *n_dead_p;
   const int lane = threadIdx.x & 31;
+  if (n == 0) {  // aux = 0 (modeling.py:92-94); r_aux is not read by the backward either (gated on n_dead)
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < B; b += gridDim.x * 256) row_sse_aux[b] = 0.f;
+    return;
+  }
   for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < B; b += gridDim.x * 8) {
     float* rr = r_aux + static_cast<long long>(b) * D;
     const float* r0 = resid + static_cast<long long>(b) * D;
@@ -555,7 +561,7 @@ static int launch_aux_backward_tc(const AuxArgs& a, cudaStream_t s) {
   const long long ld = a.S;
   const int cap = a.S;
   const float gscale = 2.f * a.alpha * a.inv_bd;
-  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s)) return 22;
+  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s, 0, a.n_dead)) return 22;
   if (launch_split_bf16(a.r_aux, a.tc_r[0], a.tc_r[1], static_cast<long long>(a.B) * a.D, s, a.tc_r[2], a.n_dead) ||
       launch_transpose_split(a.r_aux, a.B, a.D, 1.f, a.tc_rT[0], a.tc_rT[1], a.ldb, 0, a.D, s, a.tc_rT[2], a.n_dead) ||
       launch_transpose_split(a.x, a.B, a.D, 1.f, a.tc_xT[0], a.tc_xT[1], a.ldb, 0, a.D, s, a.tc_xT[2], a.n_dead))
@@ -648,7 +654,7 @@ int launch_aux_backward(const AuxArgs& a, cudaStream_t s) {
   const long long ld = a.S;
   const float gscale = 2.f * a.alpha * a.inv_bd;
   // gb_dec += sum_b G_a      (r_aux is all zeros when nothing is dead)
-  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s)) return 22;
+  if (launch_colsum(a.r_aux, a.B, a.D, gscale, 1, a.colsum_partial, a.gb_dec, s, 0, a.n_dead)) return 22;
   // gW_dec[L] = f_aux^T G_a
   SgemmArgs g{};
   g.A = a.h_aux; g.lda = ld;             // A(m,k) = f_aux[k, m]

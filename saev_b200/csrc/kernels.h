@@ -166,7 +166,8 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 
 // gb_dec[d] (+)= scale * sum_b src[b, d]
 int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
-                  cudaStream_t s, long long row_stride = 0 /* elements between rows of src; 0 = D */);
+                  cudaStream_t s, long long row_stride = 0 /* elements between rows of src; 0 = D */,
+                  const int* gate = nullptr /* accumulate mode: device flag, 0 = skip */);
 int colsum_partial_rows(int B);
 
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);

@@ -1248,11 +1248,13 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
 
 // out[d] (+)= scale * sum_b src[b,d]     (gb_dec; two deterministic stages)
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_ROWS_PER_BLOCK = 64;
+constexpr int COLSUM_ROWS_PER_BLOCK = 16;
 int colsum_partial_rows(int B) { return (B + COLSUM_ROWS_PER_BLOCK - 1) / COLSUM_ROWS_PER_BLOCK; }
 
+// `gate` (optional, accumulate mode only): device flag, 0 = nothing to add (AuxK with no dead latents)
 __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ src, int B, int D, long long row_stride,
-                                                     float* __restrict__ partial) {
+                                                     float* __restrict__ partial, const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   const int r0 = blockIdx.x * COLSUM_ROWS_PER_BLOCK;
   const int r1 = min(B, r0 + COLSUM_ROWS_PER_BLOCK);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -1261,22 +1263,35 @@ __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ s
     partial[static_cast<long long>(blockIdx.x) * D + d] = s;
   }
 }
+// 32 columns per block; warp w sums the partial rows w, w + 8, ... in fp64, the 8 warp sums are added in a fixed order
 __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ partial, int P, int D, float scale,
-                                                     int accumulate, float* __restrict__ out) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+                                                     int accumulate, float* __restrict__ out,
+                                                     const int* __restrict__ gate) {
+  __shared__ double ws[8][32];
+  if (gate != nullptr && *gate == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int p = 0; p < P; ++p) s += partial[static_cast<long long>(p) * D + d];
-  const float r = static_cast<float>(s) * scale;
-  out[d] = accumulate ? out[d] + r : r;
+  if (d < D)
+    for (int p = warp; p < P; p += 8) s += partial[static_cast<long long>(p) * D + d];
+  ws[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && d < D) {
+    double tot = ws[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) tot += ws[w][lane];
+    const float r = static_cast<float>(tot) * scale;
+    out[d] = accumulate ? out[d] + r : r;
+  }
 }
 
 int launch_colsum(const float* src, int B, int D, float scale, int accumulate, float* partial, float* out,
-                  cudaStream_t s, long long row_stride) {
+                  cudaStream_t s, long long row_stride, const int* gate) {
   const int P = colsum_partial_rows(B);
-  colsum_stage1<<<P, 256, 0, s>>>(src, B, D, row_stride > 0 ? row_stride : D, partial);
+  if (gate != nullptr && !accumulate) return 23;  // a gated launch may leave `out` untouched: only valid when adding
+  colsum_stage1<<<P, 256, 0, s>>>(src, B, D, row_stride > 0 ? row_stride : D, partial, gate);
   ++g_launch_count;
-  colsum_stage2<<<(D + 255) / 256, 256, 0, s>>>(partial, P, D, scale, accumulate, out);
+  colsum_stage2<<<(D + 31) / 32, 256, 0, s>>>(partial, P, D, scale, accumulate, out, gate);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

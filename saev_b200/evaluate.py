@@ -70,11 +70,9 @@ def evaluate_batches(batches, saes, objectives, metrics_cls=EvalMetrics) -> list
     for m in (*saes, *objectives):
         m.eval()
     states: list[dict | None] = [None] * len(saes)
+    dev = saes[0].W_dec.device
     for batch in batches:
-        x = batch["act"]
-        if not x.is_cuda:
-            x = x.cuda(non_blocking=True)
-        x = x.contiguous()
+        x = batch["act"].to(dev, non_blocking=True).contiguous()  # train.py:547
         for i, (sae, objective) in enumerate(zip(saes, objectives)):
             objective(sae, x)
             if states[i] is None:

@@ -342,3 +342,80 @@ def test_topk_lists_to_csr_equals_scipy_on_dense():
         assert got.shape == ref.shape and got.nnz == ref.nnz
         assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
         assert np.array_equal(got.data, ref.data) and got.has_canonical_format
+
+
+def test_evaluate_loop_against_the_oracle_with_a_stand_in_engine():
+    """saev_b200.evaluate.evaluate (loader construction, BatchLimiter(n_val), per-batch accumulate, closing formulas)
+    with an engine stand-in that fills the accumulator layout of saev_b200_eval_accumulate from the oracle's
+    eval-mode forward; the result must equal oracle.evaluate (train.py:510-618) on the batches that were drawn."""
+    import types
+
+    from oracle import sae_oracle as orc
+    from saev_b200 import evaluate as ev
+
+    D, S, K = 16, 64, 4
+    g = torch.Generator().manual_seed(12)
+    W_enc, b_enc, W_dec, b_dec = orc.init_params(D, S, g)
+    b_enc = 0.1 * torch.randn(S, generator=g)
+    ocfg = orc.OracleConfig(d_model=D, d_sae=S, top_k=K)
+    st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
+    data = torch.randn(100, D, generator=g)
+
+    class Loader:  # 100 rows in batches of 32 (short last batch), like ShuffledDataLoader with drop_last=False
+        batch_size, drop_last, n_samples = 32, False, 100
+        made = 0
+
+        def __init__(self, cfg):
+            Loader.made += 1
+
+        def __iter__(self):
+            for i in range(0, 100, 32):
+                yield {"act": data[i:i + 32]}
+
+        def shutdown(self):
+            Loader.closed = True
+
+    class Engine:
+        def __init__(self):
+            self.out = None
+
+        def new_eval_state(self):
+            return dict(acc=torch.zeros(8 + D, dtype=torch.float64), n_fired=torch.zeros(S), values=torch.zeros(S))
+
+        def eval_accumulate(self, x, state):  # include/saev_b200.h: saev_b200_eval_accumulate
+            o, acc, B = self.out, state["acc"], x.shape[0]
+            x64 = x.double()
+            acc[0] += (x64 * x64).sum()
+            acc[1] += ((o.x_hat - x).double() ** 2).sum()
+            acc[4] += float(o.l0) * B
+            acc[5] += float(o.l1) * B
+            acc[6] += float(o.mse) * B
+            acc[7] += B
+            acc[8:] += x64.sum(0)
+            state["n_fired"] += (o.f > 0).sum(0)
+            state["values"] += o.f.sum(0)
+
+    class SAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.W_dec = torch.nn.Parameter(W_dec.clone())
+            self.engine = Engine()
+
+    class Objective(torch.nn.Module):
+        def forward(self, sae, x):
+            assert not self.training and not sae.training  # train.py:526-527
+            sae.engine.out = orc.eval_forward(ocfg, st, x)
+            return None, None
+
+    cfg = types.SimpleNamespace(val_data="val", n_val=70, device="cpu", log_every=1)
+    (m,) = ev.evaluate([cfg], [SAE()], [Objective()], loader_cls=Loader)
+    assert Loader.made == 1 and Loader.closed
+    ref = orc.evaluate(ocfg, st, [data[0:32], data[32:64], data[64:96]])  # BatchLimiter stops once >= 70 rows were seen
+    for k in ("l0", "l1", "mse", "normalized_mse", "sse_sae", "sse_baseline"):
+        assert getattr(m, k) == pytest.approx(ref[k], rel=1e-6), k
+    assert (m.n_dead, m.n_almost_dead, m.n_dense) == (ref["n_dead"], ref["n_almost_dead"], ref["n_dense"])
+    assert torch.equal(m.freqs, ref["freqs"])
+    fired = ref["freqs"] > 0
+    assert torch.allclose(m.mean_values[fired], ref["mean_values"][fired], rtol=1e-5)
+    with pytest.raises(ValueError):
+        ev.evaluate([cfg, types.SimpleNamespace(val_data="other", n_val=1)], [SAE()] * 2, [Objective()] * 2, loader_cls=Loader)

@@ -6,7 +6,12 @@ clip -> Adam) on BASELINE.json's quoted configuration (d_model=1024, d_sae=65536
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
 
-Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md §Measurement.
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md section 5 (Measurement).
+
+Diagnostics that are NOT part of the headline line's workload (each changes `config` or adds a key, never `value`
+of the default run): `--torch-gpu-baseline` (dense torch restatement of the reference step on the same GPU, TF32,
+added as `torch_gpu_baseline`), `--workload c1|c2|c5`, `--n-prefixes P` (Matryoshka), `--dense-features N` (N atoms
+that fire on every row), `--dp-mode`, `--e2e ring|loader`.
 """
 
 from __future__ import annotations
@@ -486,6 +491,7 @@ def main():
             "config": {
                 "workload": workload_name(args.workload, D, S, K, B, args.n_prefixes),
                 "global_batch": world * B,
+                **({"dense_features": args.dense_features} if args.dense_features > 0 else {}),
                 "parallelism": f"dp{world}" + (f" ({args.dp_mode} gradient exchange)" if world > 1 else ""),
                 "precision": ("bf16 tcgen05 screen of the encoder contraction + exact fp32 re-score of the candidates; "
                               "every value that reaches the loss / gradients / parameters is fp32") if K else

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 9
+#define SAEV_B200_ABI_VERSION 10
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -50,7 +50,7 @@ enum {
   SAEV_B200_PHASE_A = 1,        /* all of phase A */
   SAEV_B200_PHASE_B = 2,
   SAEV_B200_PHASE_ALL = 3,
-  SAEV_B200_PHASE_A_SCREEN = 4, /* first half of A: operand prep + tcgen05 screen (reads only the bf16 operand copy) */
+  SAEV_B200_PHASE_A_SCREEN = 4, /* first half of A: operand prep + tcgen05 screen (reads only the fp16 operand copy) */
   SAEV_B200_PHASE_A_REST = 8    /* second half of A: exact re-score + decode (reads the fp32 W_enc_t / W_dec) */
 };
 
@@ -83,9 +83,11 @@ int saev_b200_destroy(saev_b200_handle* h);
 /* Bytes of scratch the caller must provide (256-byte aligned) for batches up to cfg.max_batch. */
 size_t saev_b200_workspace_bytes(const saev_b200_handle* h);
 
-/* (Re)build the bf16 operand copy of W_enc_t kept in the workspace.  Call after the weights were
- * written by anything other than saev_b200_adam_step (init, load_state_dict, datapoint init). */
-int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* workspace, void* stream);
+/* (Re)build what the top-k screen keeps of the encoder in the workspace: the fp16 operand copy of W_enc_t, the largest
+ * row norm and the largest |b_enc| (inputs of its error bound), and reset the screen counters.  Call after the
+ * weights were written by anything other than saev_b200_adam_step (init, load_state_dict, datapoint init). */
+int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const float* b_enc, void* workspace,
+                           void* stream);
 
 /* W_dec[j,:] /= ||W_dec[j,:]||_2    (modeling.py:411-417) */
 int saev_b200_normalize_w_dec(saev_b200_handle* h, float* W_dec, void* stream);
@@ -106,7 +108,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
 
 /* int32[d_sae] activity flags written by phase A (device pointer inside the workspace). */
 int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace);
-/* uint32 diagnostic counter: rows whose top-k could not be proven from the screen margin. */
+/* Screen diagnostics, cumulative since the last saev_b200_sync_weights (device pointer to uint32 counters):
+ *   [0] rows the tensor-core screen could not certify (candidate list overflow, observed error above the bound);
+ *       every one of them was re-done by the exact fp32 path inside the same forward      [2] candidates re-scored
+ *   [4] candidate-list entries merged      [7] rows re-done by the exact path ( == [0] once the forward has run) */
 uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace);
 
 /* Gradients of loss = mse + sparsity + aux for the batch of the last training forward
@@ -140,10 +145,10 @@ int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* 
 
 /* ---- sharded optimizer for data parallelism (no counterpart in saev, which is single-GPU) ----
  * After saev_b200_set_optimizer_shard(h, r0, r1) every saev_b200_adam_step updates only dictionary rows [r0, r1) of
- * W_enc_t / W_dec (and their Adam moments, bf16 operand rows and row-norm maximum), plus both bias vectors in full.
+ * W_enc_t / W_dec (and their Adam moments, fp16 operand rows and row-norm maximum), plus both bias vectors in full.
  * The caller reduce-scatters the two weight-gradient regions, all-reduces the bias gradients, takes the norm with
  * saev_b200_grad_sumsq_ranges over what it owns (+ an all-reduce of that scalar), and all-gathers the updated rows,
- * the bf16 operand (saev_b200_shadow_weights, [d_sae, d_model] bf16) and the row-norm maximum (MAX). */
+ * the fp16 operand (saev_b200_shadow_weights, [d_sae, d_model] fp16) and the row-norm maximum (MAX). */
 int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end);
 /* Leave `n_sms` SMs (rounded up to pairs) out of the top-k screen's persistent grid, so that NCCL kernels (the
  * all-gather of the fp32 rows a sharded optimizer step leaves behind) can run BESIDE the screen of the next step;
@@ -152,10 +157,10 @@ int saev_b200_set_reserved_sms(saev_b200_handle* h, int32_t n_sms);
 int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, int32_t n_ranges,
                                 const int64_t* host_begins, const int64_t* host_ends, float* sumsq_out,
                                 void* workspace, void* stream);
-void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace);
+void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace); /* fp16 [d_sae, d_model] */
 float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace);
 
-/* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + bf16 operand refresh.
+/* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + fp16 operand refresh.
  *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)
  *   `step` is the 1-based Adam step count AFTER this update (bias corrections use it).
  *   gnorm_out (optional, device) receives ||g_eff||, the value clip_grad_norm_ returns. */
@@ -232,7 +237,7 @@ int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, cons
  * milliseconds and the number of recorded intervals since the last read (host arrays of
  * SAEV_B200_N_STAGES entries). */
 enum {
-  SAEV_B200_STAGE_PREP = 0,        /* x -> bf16 operand                       */
+  SAEV_B200_STAGE_PREP = 0,        /* x -> fp16 operand (row-scaled)           */
   SAEV_B200_STAGE_ENCODE_GEMM = 1, /* tcgen05 encoder contraction + top-k screen */
   SAEV_B200_STAGE_RESCORE = 2,     /* exact fp32 re-score + final top-k        */
   SAEV_B200_STAGE_DECODE = 3,      /* sparse decode, residual, d loss / d h    */
@@ -241,7 +246,7 @@ enum {
   SAEV_B200_STAGE_WGRAD = 6,       /* weight gradients + parallel-grad removal */
   SAEV_B200_STAGE_BIAS_AUX = 7,    /* b_dec gradient, AuxK backward            */
   SAEV_B200_STAGE_SUMSQ = 8,       /* global gradient norm                     */
-  SAEV_B200_STAGE_ADAM = 9,        /* clip + Adam + renorm + bf16 refresh      */
+  SAEV_B200_STAGE_ADAM = 9,        /* clip + Adam + renorm + fp16 refresh      */
   SAEV_B200_N_STAGES = 10
 };
 int saev_b200_profile_enable(saev_b200_handle* h, int32_t on);

@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -83,7 +83,7 @@ SIGNATURES = {
     "saev_b200_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(_p)]),
     "saev_b200_destroy": (C.c_int, [_p]),
     "saev_b200_workspace_bytes": (C.c_size_t, [_p]),
-    "saev_b200_sync_weights": (C.c_int, [_p, _p, _p, _p]),
+    "saev_b200_sync_weights": (C.c_int, [_p, _p, _p, _p, _p]),
     "saev_b200_normalize_w_dec": (C.c_int, [_p, _p, _p]),
     "saev_b200_forward": (
         C.c_int,

@@ -21,7 +21,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_margin, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_scale, unsafe_list, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
@@ -43,7 +43,7 @@ struct saev_b200_handle {
   int device = 0;
   int num_sms = 148;
   int aux_cap = 0;
-  int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen (0 => single-CTA kernel)
+  int max_pairs = 0;       // co-resident CTA pairs for the cta_group::2 screen
   int reserved_pairs = 0;  // SM pairs the screen leaves idle (saev_b200_set_reserved_sms)
   // AuxK path selection: the dead-latent count of an EARLIER step, read back asynchronously (never waited for).  Both
   // AuxK implementations are correct for any count; the lagged value only picks the cheaper one (the tensor-core
@@ -58,6 +58,7 @@ struct saev_b200_handle {
                                  // SAEV_B200_FUSE_DH=0 restores the two-pass decode
   bool dh_fused_fwd = false;     // the last training forward left dh to the backward
   bool aux_tc_always = false;    // SAEV_B200_AUX=tc: no selection (tests pin each path)
+  bool force_repair = false;     // SAEV_B200_FORCE_REPAIR=1: every row is re-done by the exact top-k path (tests)
   int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
                            // accuracy), 3 = two pieces (~2^-16 of sum |a b|, half the tensor work); SAEV_B200_DENSE_TERMS
   Workspace ws;
@@ -145,28 +146,24 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.dhT_l2 = take(third ? S * LB * 2 : 0);
   }
   if (relu) {
-    w.cand = w.tau_keys = w.cand_cnt = o;
-    w.row_margin = take(128 * ((B + 127) / 128) * 4);
+    w.cand = w.tau_keys = w.cand_cnt = w.row_norm = w.row_scale = w.unsafe_list = o;
   } else {
-    // (row, split) candidate buffers of the top-k screen: rows are padded to whole 128-row blocks and
-    // m_blocks * nsplit never exceeds max(m_blocks, #SMs)
-    const size_t m_blocks = (B + 127) / 128;
-    size_t row_splits = 128 * (m_blocks > 160 ? m_blocks : 160);
-    size_t cand_bytes = row_splits * ENCODE_CAPG * 8;
-    if (max_pairs > 0) {
-      // pair kernel: rows padded to 256, `nlists` lists per row; the list count depends on the batch size
-      const int mp_max = static_cast<int>((B + 255) / 256);
-      for (int mp = 1; mp <= mp_max; ++mp) {
-        const Encode2Plan pl = encode2_plan(mp * 256, static_cast<int>(S), max_pairs);
-        const size_t need = static_cast<size_t>(mp) * 256 * pl.nlists;
-        if (need > row_splits) row_splits = need;
-        if (need * ENCODE2_CAPG * 8 > cand_bytes) cand_bytes = need * ENCODE2_CAPG * 8;
-      }
+    // candidate lists of the top-k screen: rows padded to 256, `nlists` lists per row; the list count depends on the
+    // batch size (how many CTA-pair ranges touch one row block)
+    size_t row_lists = 256, cand_bytes = 0;
+    const int mp_max = static_cast<int>((B + 255) / 256);
+    for (int mp = 1; mp <= mp_max; ++mp) {
+      const Encode2Plan pl = encode2_plan(mp * 256, static_cast<int>(S), max_pairs > 0 ? max_pairs : 1);
+      const size_t need = static_cast<size_t>(mp) * 256 * pl.nlists;
+      if (need > row_lists) row_lists = need;
+      if (need * ENCODE2_CAPG * 8 > cand_bytes) cand_bytes = need * ENCODE2_CAPG * 8;
     }
     w.cand = take(cand_bytes);
     w.tau_keys = take((B + 255) / 256 * 256 * 4);
-    w.cand_cnt = take(row_splits * 4);
-    w.row_margin = take(128 * m_blocks * 4);
+    w.cand_cnt = take(row_lists * 4);
+    w.row_norm = take((B + 255) / 256 * 256 * 4);
+    w.row_scale = take((B + 255) / 256 * 256 * 4);
+    w.unsafe_list = take(B * 4);
   }
   w.dh = take(B * K * 4);
   w.row_sse = take(B * 4);
@@ -179,8 +176,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
   w.entries = take(B * K * 4);
   w.active = take(S * 4);
   w.dead_list = take(S * 4);
-  w.scalars = take(64);  // [0] n_dead (int) [1] unsafe_rows (uint) [2] aux_loss (float) [3] re-scored candidates (uint)
-                         // [4] max_j ||W_enc_t[j]||^2 [5] merged list entries (uint)
+  w.scalars = take(SC_SLOTS * 4);  // see ScalarSlot (kernels.h)
   w.sfx = take(c.max_prefixes > 1 ? B * static_cast<size_t>(c.max_prefixes) * D * 4 : 0);
   w.block_totals = take(((S + 1023) / 1024) * 4);
   w.heavy_list = take((B * K / WGRAD_HEAVY_ENTRIES + 2) * 4);  // [0] = count, then the atoms
@@ -429,7 +425,7 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   if (cfg->act_kind == SAEV_B200_ACT_TOPK) {
     if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
       return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
-    if (cfg->top_k > encode_gemm_max_top_k())
+    if (cfg->top_k > encode2_max_top_k())
       return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
   } else if (cfg->d_sae % 8 != 0) {
     return fail(nullptr, 2, "saev_b200_create: the dense (ReLU) path needs d_sae to be a multiple of 8%s");
@@ -462,9 +458,10 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   h->device = dev;
   h->num_sms = sms;
   h->aux_cap = (cfg->aux_cols_cap > 0 && cfg->aux_cols_cap < cfg->d_sae) ? cfg->aux_cols_cap : cfg->d_sae;
-  {
-    const char* v = getenv("SAEV_B200_ENCODE");  // "1": force the single-CTA screen (A/B comparison)
-    h->max_pairs = (v && v[0] == '1') ? 0 : encode2_max_pairs();
+  h->max_pairs = encode2_max_pairs();
+  if (cfg->act_kind == SAEV_B200_ACT_TOPK && h->max_pairs <= 0) {
+    delete h;
+    return fail(nullptr, 4, "saev_b200_create: the cta_group::2 screen kernel cannot be made resident on this device%s");
   }
   {
     const char* v = getenv("SAEV_B200_DENSE_TERMS");
@@ -478,6 +475,10 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
   {
     const char* v = getenv("SAEV_B200_AUX");  // "sgemm" / "tc": pin one AuxK implementation; default: pick per step
     h->aux_tc_always = v && v[0] == 't';
+  }
+  {
+    const char* v = getenv("SAEV_B200_FORCE_REPAIR");  // test switch: every row takes the exact repair path
+    h->force_repair = v && v[0] == '1';
   }
   if (cudaHostAlloc(reinterpret_cast<void**>(&h->nd_host), sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->nd_event, cudaEventDisableTiming) != cudaSuccess) {
@@ -541,17 +542,22 @@ int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace) {
   return at<int32_t>(workspace, h->ws.active);
 }
 uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace) {
-  return at<uint32_t>(workspace, h->ws.scalars) + 1;
+  return at<uint32_t>(workspace, h->ws.scalars) + SC_UNSAFE_TOTAL;
 }
 
-int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, void* workspace, void* stream) {
+int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const float* b_enc, void* workspace,
+                           void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n = static_cast<long long>(h->cfg.d_sae) * h->cfg.d_model;
-  cudaMemsetAsync(at<char>(workspace, h->ws.scalars), 0, 64, s);
-  if (launch_split_bf16(W_enc_t, at<__nv_bfloat16>(workspace, h->ws.shadow_hi), nullptr, n, s))
-    return fail(h, 30, "sync_weights: split_bf16 launch failed%s");
-  if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + 4, s))
-    return fail(h, 30, "sync_weights: row-norm launch failed%s");
+  cudaMemsetAsync(at<char>(workspace, h->ws.scalars), 0, SC_SLOTS * 4, s);
+  if (h->cfg.act_kind == SAEV_B200_ACT_TOPK) {  // (the dense path re-splits its operands every forward)
+    if (launch_to_half(W_enc_t, at<__half>(workspace, h->ws.shadow_hi), n, s))
+      return fail(h, 30, "sync_weights: fp16 copy launch failed%s");
+    if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX, s))
+      return fail(h, 30, "sync_weights: row-norm launch failed%s");
+    if (launch_abs_max(b_enc, h->cfg.d_sae, at<float>(workspace, h->ws.scalars) + SC_BIAS_ABS_MAX, s))
+      return fail(h, 30, "sync_weights: bias-max launch failed%s");
+  }
   return check_cuda(h, "sync_weights");
 }
 
@@ -574,7 +580,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   h->row_gsq_valid = false;
   const int D = c.d_model, S = c.d_sae, K = c.top_k;
   int* scal_i = at<int>(workspace, w.scalars);
-  float* aux_loss = at<float>(workspace, w.scalars) + 2;
+  float* aux_loss = at<float>(workspace, w.scalars) + SC_AUX_LOSS;
   const bool tracked = training && toks_since_active != nullptr;
 
   const bool do_screen = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_SCREEN)) != 0;
@@ -588,39 +594,36 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
   } else if (do_screen || do_rest) {
-    __nv_bfloat16* x_hi = at<__nv_bfloat16>(workspace, w.x_hi);
+    __half* x16 = at<__half>(workspace, w.x_hi);
+    float* scal_f = at<float>(workspace, w.scalars);
     if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
-      if (launch_prep_x(x, B, D, x_hi, at<float>(workspace, w.row_margin), s))
+      if (launch_prep_x(x, B, D, x16, at<float>(workspace, w.row_norm), at<float>(workspace, w.row_scale), s))
         return fail(h, 41, "forward: prep_x launch failed%s");
     }
 
     EncodeGemmArgs g;
-    g.A_hi = x_hi;
+    g.A_hi = reinterpret_cast<const __nv_bfloat16*>(x16);  // (16-bit operands; the pair kernel reads them as fp16)
     g.B_hi = at<__nv_bfloat16>(workspace, w.shadow_hi);
     g.nterms = 1;
     g.M = B;
     g.N = S;
     g.K = D;
     g.bias = b_enc;
-    g.epilogue = 0;
     g.top_k = K;
-    g.row_margin = at<float>(workspace, w.row_margin);
-    g.wnorm_sq_max = at<float>(workspace, w.scalars) + 4;
+    g.row_norm = at<float>(workspace, w.row_norm);
+    g.row_scale = at<float>(workspace, w.row_scale);
+    g.scalars = scal_f;
     g.cand_cnt = at<int>(workspace, w.cand_cnt);
-    g.nsplit = encode_gemm_nsplit(B, S, h->num_sms);
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
     g.tau_keys = at<unsigned int>(workspace, w.tau_keys);
-    Encode2Plan pl;
-    if (h->max_pairs > 0) {
-      // `reserved_pairs` SM pairs are left idle (a data-parallel caller runs NCCL all-gathers beside this kernel)
-      pl = encode2_plan(B, S, h->max_pairs > h->reserved_pairs ? h->max_pairs - h->reserved_pairs : 1);
-      g.nsplit = pl.nlists;  // what the re-score kernel merges per row
-    }
+    // `reserved_pairs` SM pairs are left idle (a data-parallel caller runs NCCL all-gathers beside this kernel)
+    const Encode2Plan pl = encode2_plan(B, S, h->max_pairs > h->reserved_pairs ? h->max_pairs - h->reserved_pairs : 1);
+    g.nsplit = pl.nlists;  // what the re-score kernel merges per row
     if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
-      if (int rc = h->max_pairs > 0 ? launch_encode_gemm2(g, pl, s) : launch_encode_gemm(g, s)) {
+      if (int rc = launch_encode_gemm2(g, pl, s)) {
         char buf[64];
         snprintf(buf, sizeof(buf), "%d", rc);
         return fail(h, 42, "forward: encode GEMM launch failed (code %s)", buf);
@@ -633,10 +636,13 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     RescoreArgs r;
     r.cand = g.cand;
     r.cand_cnt = g.cand_cnt;
-    r.cand_stride = h->max_pairs > 0 ? ENCODE2_CAPG : ENCODE_CAPG;
+    r.cand_stride = ENCODE2_CAPG;
     r.nsplit = g.nsplit;
-    r.row_margin = g.row_margin;
-    r.wnorm_sq_max = g.wnorm_sq_max;
+    r.row_norm = g.row_norm;
+    r.row_scale = g.row_scale;
+    r.scalars = scal_f;
+    r.unsafe_list = at<int>(workspace, w.unsafe_list);
+    r.force_unsafe = h->force_repair ? 1 : 0;
     r.x = x;
     r.W_enc_t = W_enc_t;
     r.b_enc = b_enc;
@@ -648,10 +654,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     r.topk_val = topk_val;
     r.feat_count = training ? at<int>(workspace, w.feat_count) : nullptr;
     r.active = at<int>(workspace, w.active);
-    r.unsafe_rows = reinterpret_cast<unsigned int*>(scal_i + 1);
     {
       StageTimer tm(h, SAEV_B200_STAGE_RESCORE, s);
       if (launch_rescore_topk(r, s)) return fail(h, 43, "forward: rescore launch failed%s");
+      if (launch_repair_topk(r, s)) return fail(h, 43, "forward: exact repair launch failed%s");
     }
 
     DecodeArgs d;
@@ -859,7 +865,7 @@ int bwd_bias_aux(const BwdCtx& c) {
     a.mask_aux = at<unsigned char>(c.workspace, w.mask_aux);
     a.r_aux = at<float>(c.workspace, w.r_aux);
     a.row_sse_aux = at<float>(c.workspace, w.row_sse_aux);
-    a.aux_loss = at<float>(c.workspace, w.scalars) + 2;
+    a.aux_loss = at<float>(c.workspace, w.scalars) + SC_AUX_LOSS;
     a.gW_enc_t = c.gW_enc_t;
     a.gb_enc = c.gb_enc;
     a.gW_dec = c.gW_dec;
@@ -970,7 +976,7 @@ void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace) {
   return at<char>(workspace, h->ws.shadow_hi);
 }
 float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace) {
-  return at<float>(workspace, h->ws.scalars) + 4;
+  return at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX;
 }
 
 int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
@@ -1010,8 +1016,10 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.gb_dec = grads_flat + 2 * S * D + S;
   a.m = m_flat;
   a.v = v_flat;
-  a.shadow_hi = workspace ? at<__nv_bfloat16>(workspace, h->ws.shadow_hi) : nullptr;
-  a.wnorm_sq_max = workspace ? at<float>(workspace, h->ws.scalars) + 4 : nullptr;
+  const bool screen = workspace != nullptr && h->cfg.act_kind == SAEV_B200_ACT_TOPK;
+  a.shadow16 = screen ? at<__half>(workspace, h->ws.shadow_hi) : nullptr;
+  a.wnorm_sq_max = screen ? at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX : nullptr;
+  a.bias_abs_max = screen ? at<float>(workspace, h->ws.scalars) + SC_BIAS_ABS_MAX : nullptr;
   a.D = static_cast<int>(D);
   a.S = static_cast<int>(S);
   a.lr = lr;

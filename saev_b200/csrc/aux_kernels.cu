@@ -167,11 +167,6 @@ static void launch_sgemm(const SgemmArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // per-row top-k_use among the n_dead pre-activations: radix select on order-preserving keys
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int fkey(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
 __global__ void __launch_bounds__(256) aux_select_kernel(float* __restrict__ h_aux, unsigned char* __restrict__ mask,
                                                          long long ld, const float* __restrict__ b_enc,
                                                          const int* __restrict__ dead_list,

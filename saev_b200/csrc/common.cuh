@@ -7,6 +7,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -43,6 +44,22 @@ __device__ __forceinline__ int warp_sum(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
+}
+
+// <x, w> over a D-vector held as VPL float4 per lane: one FMA chain per lane, then the xor-shuffle tree (every lane
+// gets the same bits).  The re-score and the repair kernels both use it, so a row's exact pre-activations do not depend
+// on which of the two paths produced them.
+template <int VPL>
+__device__ __forceinline__ float row_dot(const float4 (&x)[VPL], const float4 (&w)[VPL]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    acc = fmaf(x[i].x, w[i].x, acc);
+    acc = fmaf(x[i].y, w[i].y, acc);
+    acc = fmaf(x[i].z, w[i].z, acc);
+    acc = fmaf(x[i].w, w[i].w, acc);
+  }
+  return warp_sum(acc);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -170,6 +187,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// same with fp16 operands (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// order-preserving map float -> uint32 (larger float <=> larger key) and back
+__device__ __forceinline__ unsigned int fkey(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

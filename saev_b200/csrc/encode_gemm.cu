@@ -1,30 +1,18 @@
-// Encoder contraction on tcgen05 tensor cores:  h~ = x_bf16 . W_enc_bf16^T (+ b_enc), fp32 accumulate in TMEM.
+// Dense contractions on tcgen05 tensor cores:  out = A . B^T (+ bias), bf16 operand pieces, fp32 accumulate in TMEM.
 //
-// Replaces the dense `einsum(x, W_enc) + b_enc` of saev (src/saev/nn/modeling.py:343-347) and, in the
-// TopK epilogue, the `topk -> scatter -> mul` of TopKActivation.forward (modeling.py:169-179): the [B,S]
-// pre-activation matrix is never written to HBM.  Each CTA owns one 128-row block of the batch and sweeps a
-// contiguous range of 256-column tiles of the dictionary; the epilogue warps read the accumulator out of
-// TMEM (one thread = one batch row) and keep a running list of the KP largest pre-activations of their row:
-// a register-resident admission threshold filters each 16-column chunk (max-tree, one compare), the rare
-// survivors are appended to a per-row buffer in global memory (L2 resident), and when a buffer fills up the
-// warp cooperatively radix-selects and tightens the threshold.  The lists are *candidates*: the bf16 products
-// carry ~2^-9 relative error, so `rescore_topk_kernel` (sparse_kernels.cu) recomputes the exact fp32
-// pre-activation of every candidate from the fp32 master weights and picks the final top-k from those.
-//
-// Admission rule (what makes the candidate set provably cover the exact top-k): a column is kept iff its screen
-// value exceeds  (k-th largest screen value of the row so far) - margin_b,  margin_b = 2 * E_b, where E_b bounds
-// the screen error |h~ - h| of row b (6 sigma of the bf16 rounding noise, from ||x_b||_inf and max_j ||W_enc_t[j]||).
-// If every error is <= E_b then every exact top-k column has h~ >= h_k - E_b > (h~)_k - 2 E_b, i.e. is kept.
+// One kernel, five fused epilogues (template parameter EPI, see below) for the dense (ReLU) path of the SAE step
+// (saev src/saev/nn/modeling.py:150-156, 343-409 and their autograd), the AuxK contractions over the dead latents
+// (modeling.py:75-103), the dictionary-coherence screen of the log block (train.py:411-417) and the test hook
+// saev_b200_gemm_nt.  The TopK screen of the encoder contraction is the CTA-pair kernel in encode_gemm2.cu.
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Pipelines: STAGES-deep smem ring (TMA <-> MMA),
 // 2-deep TMEM accumulator ring (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Operands are K-major bf16 with 128-byte swizzle.  `nterms == 6` adds a third piece per operand (hi + lo + lo2 = 24 bits:
-// fp32-class accuracy, terms hi.hi, hi.lo, lo.hi, hi.lo2, lo2.hi, lo.lo).  `nterms == 3` runs the error-compensated split product
-// (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, ~2^-17 relative) by walking three (A,B) tensor-map pairs along K;
-// that mode + the dense-store epilogue are used for the dense (ReLU / AuxK) paths and for testing the
-// contraction itself.
+// Operands are K-major bf16 with 128-byte swizzle.  `nterms == 3` runs the error-compensated split product
+// (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, ~2^-17 relative) by walking three (A,B) tensor-map pairs along K; `nterms == 6`
+// adds a third piece per operand (hi + lo + lo2 = 24 bits: fp32-class accuracy, terms hi.hi, hi.lo, lo.hi, hi.lo2,
+// lo2.hi, lo.lo).
 #include <stdio.h>
 
 #include "common.cuh"
@@ -87,92 +75,7 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// order-preserving map float -> uint32 (larger float <=> larger key) and back
-__device__ __forceinline__ unsigned int fkey(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float funkey(unsigned int k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-// k-th largest key among the register-resident keys of the warp (bitwise binary search; 0 if fewer than k).
-template <int PER>
-__device__ __forceinline__ unsigned int warp_kth_largest(const unsigned int (&key)[PER], int k) {
-  unsigned int T = 0u;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const unsigned int cand = T | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int e = 0; e < PER; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
-    if (c >= k) T = cand;
-  }
-  return T;
-}
-
-// Warp-cooperative compaction of one row's candidate buffer (global memory, n <= CAPG entries of
-// {value bits, column}): keep every entry whose value exceeds (k-th largest value) - margin, packed to the
-// front in arbitrary order; if more than CAPG/2 entries qualify, keep the CAPG/2 largest and report overflow.
-// Returns the new admission threshold; n_out = entries kept (ovf set on overflow).
-template <int CAPG>
-__device__ __forceinline__ float compact_row_global(int2* buf, int n, int k, float margin, int lane, int& n_out,
-                                                    bool& ovf) {
-  constexpr int PER = CAPG / 32;
-  unsigned int key[PER];
-  int col[PER];
-  __syncwarp();  // orders the owner lane's appends before the cooperative loads below
-#pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const int sl = lane + 32 * e;
-    key[e] = 0u;  // below every real key (fkey(-inf) = 0x007fffff)
-    col[e] = -1;
-    if (sl < n) {
-      const int2 t = __ldcg(buf + sl);
-      key[e] = fkey(__int_as_float(t.x));
-      col[e] = t.y;
-    }
-  }
-  ovf = false;
-  float thr = funkey(warp_kth_largest<PER>(key, k)) - margin;
-  unsigned int tkey = fkey(thr);
-  int n_ge = 0, n_gt = 0;
-#pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    n_ge += __popc(__ballot_sync(FULL, key[e] >= tkey));
-    n_gt += __popc(__ballot_sync(FULL, key[e] > tkey));
-  }
-  int need_eq = n_ge - n_gt;  // normal case: keep every entry >= threshold
-  if (n_ge > CAPG / 2) {      // pathological row: more near-ties than the buffer can carry
-    ovf = true;
-    tkey = warp_kth_largest<PER>(key, CAPG / 2);
-    thr = funkey(tkey);
-    n_gt = 0;
-#pragma unroll
-    for (int e = 0; e < PER; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > tkey));
-    need_eq = CAPG / 2 - n_gt;  // ties at the cut: lowest buffer position first
-  }
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  int base = 0, eq_seen = 0;
-  __syncwarp();
-#pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const bool gt = key[e] > tkey;
-    const bool eq = key[e] == tkey;
-    const unsigned int bal_eq = __ballot_sync(FULL, eq);
-    const bool take = gt || (eq && (eq_seen + __popc(bal_eq & lt_mask)) < need_eq);
-    const unsigned int bal = __ballot_sync(FULL, take);
-    if (take) buf[base + __popc(bal & lt_mask)] = make_int2(__float_as_int(funkey(key[e])), col[e]);
-    base += __popc(bal);
-    eq_seen += __popc(bal_eq);
-  }
-  __syncwarp();
-  n_out = base;
-  return thr;
-}
-
-// EPI: 0 = running top-KP candidate lists
-//      1 = dense fp32 store of (acc + bias)
+// EPI: 1 = dense fp32 store of (acc + bias)
 //      2 = ReLU forward (dense SAE path): f = relu(acc + bias) written as a bf16 hi/lo pair both row-major
 //          [M, ldf] (operand of the decoder contraction) and transposed [N, ldt] (operand of the weight-gradient
 //          contraction); per-row sum f / count f>0, per-column "fired" flags
@@ -187,10 +90,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const __grid_constant__ CUtensorMap tmA_lo2, const __grid_constant__ CUtensorMap tmB_lo2,
                    int nterms, int kblocks_per_term, int kchunk, const float* __restrict__ bias, int M, int N, int m_blocks,
-                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, int top_k,
-                   const float* __restrict__ row_margin, const float* __restrict__ wnorm_sq_max,
-                   int2* __restrict__ cand, int* __restrict__ cand_cnt, float* __restrict__ out, long long ldo,
-                   const EpiExtra ex) {
+                   int tiles_per_split, int nsplit, const int* __restrict__ n_limit_dev, float* __restrict__ out,
+                   long long ldo, const EpiExtra ex) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_u32 & 1023u)) & 1023u;
@@ -328,14 +229,6 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int row_local = q * 32 + lane;    // accumulator row == TMEM lane
     const int row = m_blk * BM + row_local;
-    // candidate buffer of this thread's row (global memory, CAPG entries per (row, split))
-    int2* warp_buf = cand + (static_cast<long long>(m_blk * BM + q * 32) * nsplit + split) * CAPG;
-    int2* my_buf = warp_buf + static_cast<long long>(lane) * nsplit * CAPG;
-    float tau = (row < M) ? -INFINITY : INFINITY;  // rows past the batch never admit anything
-    int cnt = 0;
-    bool overflowed = false;
-    // margin_b = 2 E_b:  row_margin[b] = c * ||x_b||_inf (prep kernel), times the largest encoder-row norm
-    const float margin = (EPI == 0 && row < M) ? row_margin[row] * sqrtf(*wnorm_sq_max) : 0.f;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     float acc_l1 = 0.f, acc_l0 = 0.f;  // EPI 2
     float best = -1.f;                 // EPI 5
@@ -350,9 +243,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const int n0 = (tile_begin + t) * BN;
       float* bs = bias_s + as * BN;
       // Stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below).
-      // Columns past the end get -inf in the top-k epilogue so that they can never be admitted.
       for (int c = et; c < BN; c += 128) {
-        float bv = (EPI == 0) ? -INFINITY : 0.f;  // (columns past the end are never stored by EPI >= 1)
+        float bv = 0.f;  // (columns past the end are never stored)
         if (n0 + c < n_cols) bv = (bias != nullptr && !accum && ks == 0) ? bias[n0 + c] : 0.f;
         bs[c] = bv;
       }
@@ -378,42 +270,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] *= ex.alpha;
         }
-        if (EPI == 0) {
-          // fast path: one compare of the chunk maximum against the row's admission threshold
-          float m01 = fmaxf(fmaxf(v[0], v[1]), v[2]), m02 = fmaxf(fmaxf(v[3], v[4]), v[5]);
-          float m03 = fmaxf(fmaxf(v[6], v[7]), v[8]), m04 = fmaxf(fmaxf(v[9], v[10]), v[11]);
-          float m05 = fmaxf(fmaxf(v[12], v[13]), v[14]);
-          const float mx = fmaxf(fmaxf(fmaxf(m01, m02), fmaxf(m03, m04)), fmaxf(m05, v[15]));
-          const bool hit = mx > tau;
-          if (__any_sync(FULL, hit)) {
-            if (hit) {
-#pragma unroll
-              for (int i = 0; i < CHUNK; ++i) {
-                if (v[i] > tau) {
-                  my_buf[cnt] = make_int2(__float_as_int(v[i]), col0 + i);
-                  ++cnt;
-                }
-              }
-            }
-            // keep room for one more chunk in every row buffer of this warp
-            unsigned need = __ballot_sync(FULL, cnt > CAPG - CHUNK);
-            while (need) {
-              const int l = __ffs(need) - 1;
-              need &= need - 1;
-              const int n = __shfl_sync(FULL, cnt, l);
-              const float mg = __shfl_sync(FULL, margin, l);
-              int n_out;
-              bool ovf;
-              const float thr = compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, top_k,
-                                                         mg, lane, n_out, ovf);
-              if (lane == l) {
-                cnt = n_out;
-                tau = thr;
-                overflowed |= ovf;
-              }
-            }
-          }
-        } else if (EPI == 1) {
+        if (EPI == 1) {
           if (row < M) {
             float* o = out + static_cast<long long>(row) * ldo + col0;
             if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
@@ -564,24 +421,6 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       atomicAdd(ex.row_l1 + row, acc_l1);
       atomicAdd(ex.row_l0 + row, acc_l0);
     }
-    if (EPI == 0) {
-      // final compaction: trim every row buffer to the columns within the margin of its k-th largest screen
-      // value and publish the count (negative = the buffer overflowed at some point: the row is not covered)
-      for (int l = 0; l < 32; ++l) {
-        const int n = __shfl_sync(FULL, cnt, l);
-        const float mg = __shfl_sync(FULL, margin, l);
-        const int grow = m_blk * BM + q * 32 + l;
-        if (grow >= M) continue;  // warp-uniform
-        int n_out = n;
-        bool ovf = false;
-        if (n > top_k)
-          compact_row_global<CAPG>(warp_buf + static_cast<long long>(l) * nsplit * CAPG, n, top_k, mg, lane, n_out, ovf);
-        if (lane == l) {
-          overflowed |= ovf;
-          cand_cnt[static_cast<long long>(grow) * nsplit + split] = overflowed ? -n_out : n_out;
-        }
-      }
-    }
   }
 
   tc_fence_before();
@@ -654,9 +493,7 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
   const int kchunk = ((EPI == 1 || EPI == 4) && a.k_chunk_blocks > 0) ? a.k_chunk_blocks : kblocks_per_term;
   kern<<<m_blocks * nsplit * ex.ksplit, NUM_THREADS, L.total, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a.nterms,
                                                            kblocks_per_term, kchunk, a.bias, a.M, a.N, m_blocks,
-                                                           tiles_per_split, nsplit, a.n_limit_dev, a.top_k,
-                                                           a.row_margin, a.wnorm_sq_max,
-                                                           reinterpret_cast<int2*>(a.cand), a.cand_cnt, a.out, a.ldo, ex);
+                                                           tiles_per_split, nsplit, a.n_limit_dev, a.out, a.ldo, ex);
                                                            ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 4;
 }
@@ -672,8 +509,6 @@ int encode_gemm_nsplit(int M, int N, int num_sms) {
   const int tps = (n_tiles + nsplit - 1) / nsplit;
   return (n_tiles + tps - 1) / tps;
 }
-
-int encode_gemm_max_top_k() { return ENCODE_CAPG / 4; }
 
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return 0;
@@ -714,12 +549,7 @@ int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
       default: return 12;
     }
   }
-  const int nsplit = a.nsplit;
-  const int tps = (n_tiles + nsplit - 1) / nsplit;
-  if (a.top_k <= 0 || a.top_k > encode_gemm_max_top_k() || a.cand == nullptr || a.cand_cnt == nullptr ||
-      a.row_margin == nullptr || a.wnorm_sq_max == nullptr)
-    return 12;
-  return launch_variant<0, ENCODE_CAPG, 4>(a, maps, m_blocks, tps, nsplit, stream);
+  return 12;  // the top-k screen lives in encode_gemm2.cu
 }
 
 }  // namespace sb

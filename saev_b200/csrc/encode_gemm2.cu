@@ -1,8 +1,19 @@
-// Encoder contraction + streaming top-k screen, CTA-pair version (tcgen05.mma.cta_group::2).
+// Encoder contraction + streaming top-k screen (tcgen05.mma.cta_group::2 on CTA pairs).
 //
-// Same contract as encode_gemm.cu's top-k epilogue (h~ = x_bf16 . W_enc_bf16^T + b_enc is never written to HBM; each
-// row of the batch leaves candidate lists that provably cover its exact top-k, see the admission rule there), but
-// organised for the two things the single-CTA kernel was losing time on (profiles/r01_encode_gemm_full.md):
+// Replaces the dense `einsum(x, W_enc) + b_enc` of saev (src/saev/nn/modeling.py:343-347) and the
+// `topk -> scatter -> mul` of TopKActivation.forward (modeling.py:169-179): the [B, S] pre-activation matrix is never
+// written to HBM.  The tensor cores compute a SCREEN value  h~ = 2^e_b <fp16(x_b 2^-e_b), fp16(w_j)> + b_j  (fp16
+// operands: 11 significant bits at the bf16 rate; the power-of-two row scale keeps every row inside the fp16 range
+// without rounding) and every row of the batch leaves candidate lists that PROVABLY cover its exact top-k:
+//
+//   admission rule: a column is kept iff its screen value exceeds (k-th largest screen value of the row so far)
+//   - 2 E_b, where E_b is the deterministic bound on |h~ - h| of kernels.h (screen_bound: Cauchy-Schwarz on the fp16
+//   roundings, plus the accumulation terms).  With every error <= E_b each exact top-k column has
+//   h~ >= h_k - E_b >= (h~)_k - 2 E_b, i.e. is kept.  `rescore_topk_kernel` (sparse_kernels.cu) recomputes the
+//   candidates in fp32 from the fp32 master weights, picks the final top-k, and hands rows whose lists overflowed
+//   (or whose observed error contradicts the bound) to the exact repair path.
+//
+// Organisation (profiles/r01_encode_gemm_full.md has the measurements that led here):
 //
 //   * operand feed: a CTA pair (two SMs of one TPC) computes a 256 x 256 tile; each CTA stages only ITS 128 rows of
 //     x and ITS 128 of the 256 dictionary columns (32 KB per k-block instead of 48 KB), the tensor cores of both SMs
@@ -105,13 +116,6 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 
-__device__ __forceinline__ unsigned int fkey(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float funkey(unsigned int k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 template <int PER>
 __device__ __forceinline__ unsigned int warp_kth_largest(const unsigned int (&key)[PER], int k) {
   unsigned int T = 0u;
@@ -262,8 +266,10 @@ struct Params {
   int top_k;
   int trigger;          // compact a list once it holds more than this many entries (<= TRIGGER_MAX)
   const float* bias;
-  const float* row_margin;
-  const float* wnorm_sq_max;
+  const float* row_norm;   // [M] ||x_b||_2
+  const float* row_scale;  // [M] 2^e_b (the screen value is acc * 2^e_b + bias)
+  const float* scalars;    // workspace scalar block: SC_WNORM_SQ_MAX, SC_BIAS_ABS_MAX
+  int D;                   // contraction length (for the error bound)
   int2* cand;
   int* cand_cnt;
   unsigned int* tau_g;  // [rows padded to 256] order-preserving key of the best admission threshold known per row
@@ -342,7 +348,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16_f32(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       const long long n_steps = t_end - t_begin;
@@ -378,7 +384,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row_local = q * 32 + lane;
     float* my_tau_s = tau_s + half * BM + row_local;
     const float* other_tau_s = tau_s + (half ^ 1) * BM + row_local;
-    const float wn = sqrtf(*p.wnorm_sq_max);
+    const ScreenBound sbd = screen_bound(p.D, sqrtf(p.scalars[SC_WNORM_SQ_MAX]), p.scalars[SC_BIAS_ABS_MAX]);
     int* hist_w = reinterpret_cast<int*>(smem + OFF_HIST) + w * 256;
     long long tc = 0;
     for (int uj = 0; uj < n_units; ++uj) {
@@ -392,7 +398,8 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int2* my_buf = warp_buf + lane * lane_stride;
       const bool live = row < p.M;
       float tau = live ? -INFINITY : INFINITY;
-      const float margin = live ? p.row_margin[row] * wn : 0.f;
+      const float rs = live ? p.row_scale[row] : 1.f;
+      const float margin = live ? 2.f * (p.row_norm[row] * sbd.A + rs * sbd.Bc + sbd.C) : 0.f;
       int2* wp = my_buf;  // append cursor (a running pointer keeps the per-hit address arithmetic to one add)
       bool overflowed = false;
       *my_tau_s = -INFINITY;
@@ -430,10 +437,10 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int i = 0; i < CHUNK; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bs + c * CHUNK + i);
-            v[i] = __uint_as_float(a[i]) + b4.x;
-            v[i + 1] = __uint_as_float(a[i + 1]) + b4.y;
-            v[i + 2] = __uint_as_float(a[i + 2]) + b4.z;
-            v[i + 3] = __uint_as_float(a[i + 3]) + b4.w;
+            v[i] = fmaf(__uint_as_float(a[i]), rs, b4.x);
+            v[i + 1] = fmaf(__uint_as_float(a[i + 1]), rs, b4.y);
+            v[i + 2] = fmaf(__uint_as_float(a[i + 2]), rs, b4.z);
+            v[i + 3] = fmaf(__uint_as_float(a[i + 3]), rs, b4.w);
           }
           float gm[4];
 #pragma unroll
@@ -545,13 +552,15 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
   cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
 }  // namespace g2
+
+int encode2_max_top_k() { return 64; }
 
 // Number of CTA pairs that can be co-resident (one per TPC with both SMs free); 0 on failure.
 int encode2_max_pairs() {
@@ -609,7 +618,8 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
   using namespace g2;
   if (a.M <= 0 || a.N <= 0) return 0;
   if ((a.K % 8) != 0) return 10;
-  if (a.top_k <= 0 || a.top_k > CAPG / 4 || !a.cand || !a.cand_cnt || !a.row_margin || !a.wnorm_sq_max) return 12;
+  if (a.top_k <= 0 || a.top_k > encode2_max_top_k() || !a.cand || !a.cand_cnt || !a.row_norm || !a.row_scale || !a.scalars)
+    return 12;
   CUtensorMap maps[2];
   if (make_tmap(&maps[0], a.A_hi, a.M, a.K, BM)) return 11;
   if (make_tmap(&maps[1], a.B_hi, a.N, a.K, BN / 2)) return 11;
@@ -641,8 +651,10 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
     p.trigger = max(2 * a.top_k, min(trig, TRIGGER_MAX));
   }
   p.bias = a.bias;
-  p.row_margin = a.row_margin;
-  p.wnorm_sq_max = a.wnorm_sq_max;
+  p.row_norm = a.row_norm;
+  p.row_scale = a.row_scale;
+  p.scalars = a.scalars;
+  p.D = a.K;
   p.cand = reinterpret_cast<int2*>(a.cand);
   p.cand_cnt = a.cand_cnt;
   p.tau_g = a.tau_keys;

@@ -2,17 +2,77 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace sb {
 
 constexpr int ENCODE_MAX_NSPLIT = 8;
-constexpr int ENCODE_CAPG = 256;   // entries per (row, split) candidate buffer of the single-CTA top-k screen
+constexpr int ENCODE_CAPG = 256;   // (template parameter of the dense tcgen05 kernel; no candidate lists there any more)
 constexpr int ENCODE2_CAPG = 384;  // entries per candidate list of the CTA-pair screen (encode_gemm2.cu)
+
+// ---- slots of the 128-byte scalar block in the workspace (Workspace::scalars), 4 bytes each ----------------------
+enum ScalarSlot {
+  SC_N_DEAD = 0,        // int    dead latents after the tracker update of the last training forward
+  SC_UNSAFE_TOTAL = 1,  // uint   rows the screen could not certify (cumulative since sync_weights); all were repaired
+  SC_AUX_LOSS = 2,      // float
+  SC_RESCORED = 3,      // uint   candidates re-scored in fp32 (cumulative)
+  SC_WNORM_SQ_MAX = 4,  // float  max_j ||W_enc_t[j]||^2
+  SC_MERGED = 5,        // uint   candidate-list entries merged (cumulative)
+  SC_BIAS_ABS_MAX = 6,  // float  max_j |b_enc[j]|
+  SC_N_UNSAFE = 7,      // int    rows of the CURRENT forward handed to the exact repair path
+  SC_REPAIRED = 8,      // uint   rows re-done by the exact path (cumulative)
+  SC_SLOTS = 32
+};
+
+// ---- deterministic error bound of the fp16 top-k screen -----------------------------------------------------------
+// The screen computes  h~ = 2^e * sum_d fp16(x_d 2^-e) fp16(w_d) + b  on the tensor cores (fp32 accumulation), the
+// re-score kernel  he = fl32(sum_d x_d w_d) + b.  With u = 2^-11 (fp16 unit roundoff), s = 2^-25 (fp16 round-off in
+// the subnormal range), every |fp16(a) - a| <= u |a| + s, so by Cauchy-Schwarz
+//   |h~ - he| <= ||x||_2 ||w||_2 (2u + u^2 + g)  +  s' sqrt(D) (2^e ||w||_2 + ||x||_2)  +  2^-22 (||x|| ||w|| + |b|)
+// where g bounds both accumulation errors (tensor core: one truncating fp32 update per 16 products, doubled for
+// safety; re-score: D/32 sequential FMAs per lane + 5 shuffle levels) and the last term the two final roundings.
+//   E_b = xnorm_b * A + 2^e_b * Bc + C
+struct ScreenBound {
+  float A, Bc, C;
+};
+__host__ __device__ inline ScreenBound screen_bound(int D, float wnorm_max, float bias_abs_max) {
+  const float u = 4.8828125e-4f;           // 2^-11
+  const float s = 2.9802322e-8f * 1.001f;  // 2^-25 (+ cross terms)
+  const float g = (2.f * (D / 16 + 16) + (D / 32 + 8)) * 1.1920929e-7f;  // * 2^-23
+  const float rnd = 2.3841858e-7f;         // 2^-22
+  const float sqd = sqrtf(static_cast<float>(D));
+  ScreenBound b;
+  b.A = wnorm_max * (2.f * u + u * u + g + rnd) + s * sqd;
+  b.Bc = s * sqd * wnorm_max;
+  b.C = rnd * bias_abs_max;
+  // everything above is evaluated in fp32 itself: 1 % head room
+  b.A *= 1.01f;
+  b.Bc *= 1.01f;
+  b.C *= 1.01f;
+  return b;
+}
+constexpr float FP16_MAX = 65504.f;  // encoder rows with a larger norm cannot be screened in fp16 (all rows repaired)
 
 // number of kernels this library has launched (all handles); read through saev_b200_launch_count()
 extern unsigned long long g_launch_count;
+
+// Row-per-warp kernels keep a whole D-vector in registers: lane l owns float4 vectors l, l + 32, ..., VPL of them.
+#define SB_DISPATCH_VPL(D, CALL)                                         \
+  do {                                                                   \
+    const int need_ = ((D) + 127) / 128;                                 \
+    ++g_launch_count;                                                    \
+    if (need_ <= 1) { constexpr int VPL = 1; CALL; }                     \
+    else if (need_ <= 2) { constexpr int VPL = 2; CALL; }                \
+    else if (need_ <= 4) { constexpr int VPL = 4; CALL; }                \
+    else if (need_ <= 6) { constexpr int VPL = 6; CALL; }                \
+    else if (need_ <= 8) { constexpr int VPL = 8; CALL; }                \
+    else if (need_ <= 12) { constexpr int VPL = 12; CALL; }              \
+    else if (need_ <= 16) { constexpr int VPL = 16; CALL; }              \
+    else return 20;                                                      \
+  } while (0)
 
 // ---- encode_gemm.cu -------------------------------------------------------------------------------------
 struct EncodeGemmArgs {
@@ -35,8 +95,8 @@ struct EncodeGemmArgs {
   float alpha = 1.f;                    // epilogues 1 / 4: out = alpha * (acc + bias)
   int ksplit = 1;                       // epilogues 1 / 4 with k_chunk_blocks > 0: spread the K chunks of one output tile
                                         // over this many CTAs, all adding into a PRE-ZEROED output (bias must be null)
-  int epilogue = 0;                     // 0: top-KP candidate lists, 1: dense fp32 store, 2: ReLU forward,
-                                        // 3: ReLU backward, 4: weight gradient, 5: coherence screen (see encode_gemm.cu)
+  int epilogue = 1;                     // 1: dense fp32 store, 2: ReLU forward, 3: ReLU backward, 4: weight gradient,
+                                        // 5: coherence screen (see encode_gemm.cu); the top-k screen is encode_gemm2.cu
   __nv_bfloat16* f_hi = nullptr;        // epilogue 2 (out) / 3 (in): relu(h) as bf16 hi [M, ldf]
   __nv_bfloat16* f_lo = nullptr;        // epilogue 2: bf16 residual
   __nv_bfloat16* t_hi = nullptr;        // epilogue 2/3: transposed bf16 hi/lo outputs [N, ldt]
@@ -50,14 +110,15 @@ struct EncodeGemmArgs {
   float l1_over_b = 0.f;                // epilogue 3
   int n_main = 0;                       // epilogue 4: columns < n_main go to out, column n_main to extra[row]
   float* extra = nullptr;
-  int top_k = 32;                       // epilogue 0: k of the final selection
-  const float* row_margin = nullptr;    // epilogue 0: [M] admission margin per row / max encoder-row norm
-  const float* wnorm_sq_max = nullptr;  // epilogue 0: device scalar, max_j ||B[j]||^2 of the fp32 weights
-  int nsplit = 1;                       // column splits (epilogue 0: one candidate buffer per (row, split))
+  int top_k = 32;                       // screen (pair kernel): k of the final selection
+  const float* row_norm = nullptr;      // screen: [M] ||x_b||_2
+  const float* row_scale = nullptr;     // screen: [M] 2^e_b, the power of two the fp16 operand row was divided by
+  const float* scalars = nullptr;       // screen: the workspace scalar block (SC_WNORM_SQ_MAX, SC_BIAS_ABS_MAX)
+  int nsplit = 1;                       // column splits of the dense epilogues
   int num_sms = 148;
-  int* cand_cnt = nullptr;              // epilogue 0: [M, nsplit] entries kept (negative: overflowed)
-  void* cand = nullptr;                 // epilogue 0: [M(rounded up to 128), nsplit, ENCODE_CAPG] x {value bits, column}
-  unsigned int* tau_keys = nullptr;     // pair kernel: [rows padded to 256] shared admission thresholds (scratch)
+  int* cand_cnt = nullptr;              // screen: [rows, nlists] entries kept (negative: overflowed)
+  void* cand = nullptr;                 // screen: [rows padded to 256, nlists, ENCODE2_CAPG] x {value bits, column}
+  unsigned int* tau_keys = nullptr;     // screen: [rows padded to 256] shared admission thresholds (scratch)
   float* out = nullptr;                 // epilogue 1: [M, ldo]
   long long ldo = 0;
 };
@@ -74,20 +135,25 @@ struct Encode2Plan {
 };
 int encode2_max_pairs();                                  // co-resident CTA pairs on this device (0: unavailable)
 Encode2Plan encode2_plan(int M, int N, int max_pairs);
-// uses A_hi, B_hi, M, N, K, bias, top_k, row_margin, wnorm_sq_max, cand ([rows padded to 256][nlists][ENCODE2_CAPG]),
-// cand_cnt ([rows padded to 256][nlists]) of `a`
+// uses A_hi / B_hi (FP16 operands here: x 2^-e and W_enc_t), M, N, K, bias, top_k, row_norm, row_scale, scalars, cand
+// ([rows padded to 256][nlists][ENCODE2_CAPG]), cand_cnt ([rows padded to 256][nlists]), tau_keys of `a`
 int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStream_t stream);
 int encode_gemm_nsplit(int M, int N, int num_sms);
-int encode_gemm_max_top_k();
+int encode2_max_top_k();
 
 // ---- sparse_kernels.cu ----------------------------------------------------------------------------------
 // `gate` (optional, device): the kernel does nothing when *gate == 0 (AuxK operand prep with no dead latents)
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
                       __nv_bfloat16* lo2 = nullptr, const int* gate = nullptr);
-// x[B,D] -> bf16 copy + per-row admission margin factor  c * ||x_b||_inf   (see encode_gemm.cu)
-int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s);
+// x[B,D] -> fp16 operand x16[b] = fp16(x[b] * 2^-e_b) (2^e_b: power of two just above ||x_b||_inf, exact scaling),
+// row_norm[b] = ||x_b||_2 (rounded up), row_scale[b] = 2^e_b        (operand of the top-k screen, encode_gemm2.cu)
+int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_scale, cudaStream_t s);
+// fp32 -> fp16 (round to nearest): the screen's copy of W_enc_t
+int launch_to_half(const float* src, __half* dst, long long n, cudaStream_t s);
 // *out = max_j ||W[j,:]||^2
 int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s);
+// *out = max_i |v[i]|
+int launch_abs_max(const float* v, int n, float* out, cudaStream_t s);
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
 int launch_log_metrics(const float* x, const float* r, int B, int D, const float* W, int S, const int* fired,
                        double* acc, const float* coh, double* out, cudaStream_t s);
@@ -102,16 +168,24 @@ int launch_coherence_finish(const float* W, int D, const float* row_best, const 
                             float slack, float* out, cudaStream_t s);
 
 struct RescoreArgs {
-  const void* cand; const int* cand_cnt; int cand_stride; int nsplit;  // (row, split) candidate buffers
-  const float* row_margin; const float* wnorm_sq_max;
+  void* cand; const int* cand_cnt; int cand_stride; int nsplit;  // (row, list) candidate buffers
+  const float* row_norm; const float* row_scale;
+  float* scalars;       // workspace scalar block (ScalarSlot): bounds in, counters out
   const float* x; const float* W_enc_t; const float* b_enc;
   int B, D, S, K;
   int* topk_idx; float* topk_val;
   int* feat_count;      // [S] += 1 per selected (b, j)   (may be null: eval)
   int* active;          // [S] = 1 where a non-zero activation was selected (may be null)
-  unsigned int* unsafe_rows;  // diagnostic counter
+  int* unsafe_list;     // [B] rows handed to the exact path (count in scalars[SC_N_UNSAFE], zeroed by the launcher)
+  int force_unsafe;     // test switch: treat every row as uncertified
 };
+// Exact fp32 re-score of the screen's candidates and the final top-k; rows that cannot be certified (list overflow,
+// observed screen error above the bound, encoder norm outside the fp16 range) are appended to unsafe_list instead.
 int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s);
+// Exact path for the rows in unsafe_list: every pre-activation of the row in fp32 (same arithmetic as the re-score),
+// block-wide radix selection; writes what launch_rescore_topk would have.  Fixed grids that read the row count from
+// the device (no host sync); uses the rows' own (already consumed) candidate lists as scratch.
+int launch_repair_topk(const RescoreArgs& a, cudaStream_t s);
 
 struct DecodeArgs {
   const float* x; const int* topk_idx; const float* topk_val;
@@ -182,8 +256,9 @@ struct AdamArgs {
   float* W_enc_t; float* b_enc; float* W_dec; float* b_dec;
   const float* gW_enc_t; const float* gb_enc; const float* gW_dec; const float* gb_dec;
   float* m; float* v;          // flat, same order/offsets as the gradient bucket
-  __nv_bfloat16* shadow_hi;    // bf16 copy of W_enc_t for the tensor-core screen (may be null)
+  __half* shadow16;            // fp16 copy of W_enc_t for the tensor-core screen (may be null)
   float* wnorm_sq_max;         // device scalar: max_j ||W_enc_t[j]||^2 after the update (zeroed by the launcher)
+  float* bias_abs_max;         // device scalar: max_j |b_enc[j]| after the update (zeroed by the launcher)
   int D, S;
   float lr, beta1, beta2, eps, bc1, bc2_sqrt;
   float max_norm; float grad_scale; const float* gnorm_sq;

@@ -14,20 +14,6 @@
 
 namespace sb {
 
-#define SB_DISPATCH_VPL(D, CALL)                                         \
-  do {                                                                   \
-    const int need_ = ((D) + 127) / 128;                                 \
-    ++g_launch_count;                                                    \
-    if (need_ <= 1) { constexpr int VPL = 1; CALL; }                     \
-    else if (need_ <= 2) { constexpr int VPL = 2; CALL; }                \
-    else if (need_ <= 4) { constexpr int VPL = 4; CALL; }                \
-    else if (need_ <= 6) { constexpr int VPL = 6; CALL; }                \
-    else if (need_ <= 8) { constexpr int VPL = 8; CALL; }                \
-    else if (need_ <= 12) { constexpr int VPL = 12; CALL; }              \
-    else if (need_ <= 16) { constexpr int VPL = 16; CALL; }              \
-    else return 20;                                                      \
-  } while (0)
-
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
@@ -86,36 +72,79 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// x[B,D] -> bf16 operand + admission-margin factor of the top-k screen, one warp per row.
-//   The screen computes h~ = <bf16(x), bf16(w)>; with relative roundings eps in [-2^-9, 2^-9] (variance 2^-18/3
-//   each) its error has sigma_e = 2^-9 sqrt(2/3) sqrt(sum_d x_d^2 w_d^2) <= 2^-9 sqrt(2/3) ||x||_inf ||w||_2.
-//   E_b = 6 sigma_e bounds it, the admission margin is 2 E_b:
-//       row_margin[b] = 12 * sqrt(2/3) * 2^-9 * ||x_b||_inf        (times max_j ||w_j||_2 in the GEMM)
+// x[B,D] -> fp16 operand of the top-k screen, one warp per row.  The row is divided by 2^e_b, the power of two just
+// above ||x_b||_inf (exact: only the exponent changes), so that every row uses the fp16 range [2^-14, 1) whatever its
+// magnitude; row_scale[b] = 2^e_b goes back on in the GEMM epilogue, row_norm[b] = ||x_b||_2 feeds the error bound
+// (kernels.h, screen_bound).
 // ------------------------------------------------------------------------------------------------
-constexpr float MARGIN_C = 12.0f * 0.81649658f * 0.001953125f;
-
 __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, int B, int D,
-                                                     __nv_bfloat16* __restrict__ x_hi, float* __restrict__ row_margin) {
+                                                     __half* __restrict__ x16, float* __restrict__ row_norm,
+                                                     float* __restrict__ row_scale) {
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31, D4 = D >> 2;
   const float* row = x + static_cast<long long>(b) * D;
-  __nv_bfloat16* orow = x_hi + static_cast<long long>(b) * D;
-  float mx = 0.f;
+  __half* orow = x16 + static_cast<long long>(b) * D;
+  float mx = 0.f, ss = 0.f;
   for (int v = lane; v < D4; v += 32) {
     const float4 q = ldg4(row + 4 * v);
     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))));
-    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(orow + 4 * v);
-    o[0] = __nv_bfloat162(__float2bfloat16_rn(q.x), __float2bfloat16_rn(q.y));
-    o[1] = __nv_bfloat162(__float2bfloat16_rn(q.z), __float2bfloat16_rn(q.w));
+    ss += dot4(q, q);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-  if (lane == 0) row_margin[b] = MARGIN_C * mx;
+  ss = warp_sum(ss);
+  int e = 0;
+  if (mx > 0.f && mx <= 3.0e38f) frexpf(mx, &e);  // mx = m 2^e, m in [0.5, 1)
+  e = max(-100, min(e, 126));
+  const float down = ldexpf(1.f, -e);
+  for (int v = lane; v < D4; v += 32) {
+    const float4 q = ldg4(row + 4 * v);  // L1 hit
+    __half2* o = reinterpret_cast<__half2*>(orow + 4 * v);
+    o[0] = __floats2half2_rn(q.x * down, q.y * down);
+    o[1] = __floats2half2_rn(q.z * down, q.w * down);
+  }
+  if (lane == 0) {
+    row_norm[b] = sqrtf(ss) * 1.00001f;  // (rounded up: it scales an upper bound)
+    row_scale[b] = ldexpf(1.f, e);
+  }
 }
-int launch_prep_x(const float* x, int B, int D, __nv_bfloat16* x_hi, float* row_margin, cudaStream_t s) {
+int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_scale, cudaStream_t s) {
   if (D % 4) return 21;
-  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x_hi, row_margin);
+  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x16, row_norm, row_scale);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n4) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ldg4(src + 4 * i);
+    __half2* o = reinterpret_cast<__half2*>(dst + 4 * i);
+    o[0] = __floats2half2_rn(v.x, v.y);
+    o[1] = __floats2half2_rn(v.z, v.w);
+  }
+}
+int launch_to_half(const float* src, __half* dst, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (n % 4) return 21;
+  const long long n4 = n / 4;
+  const long long want = (n4 + 255) / 256;
+  to_half_kernel<<<static_cast<int>(want < 148LL * 16 ? want : 148LL * 16), 256, 0, s>>>(src, dst, n4);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+__global__ void __launch_bounds__(256) abs_max_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+int launch_abs_max(const float* v, int n, float* out, cudaStream_t s) {
+  if (cudaMemsetAsync(out, 0, 4, s) != cudaSuccess) return 23;
+  abs_max_kernel<<<64, 256, 0, s>>>(v, n, out);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -188,14 +217,6 @@ int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s) {
 constexpr int RESCORE_WARPS = 8;
 constexpr int RESCORE_CAP = 192;  // most candidates of one row that survive the merged threshold
 
-__device__ __forceinline__ unsigned int fkey_s(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float funkey_s(unsigned int k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 // One radix pass of the warp-wide k-th-largest search over a row's candidate lists: histogram of the 8-bit digit
 // at `shift` of every screen key whose higher digits equal `prefix`, then the bin holding the `need`-th largest.
 __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* cnts, int nlists, int stride, int shift,
@@ -208,7 +229,7 @@ __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* 
     const int c = abs(cnts[l]);
     const int2* lb = cbuf + static_cast<long long>(l) * stride;
     for (int e = lane; e < c; e += 32) {
-      const unsigned int key = fkey_s(__int_as_float(__ldg(&lb[e].x)));
+      const unsigned int key = fkey(__int_as_float(__ldg(&lb[e].x)));
       if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(hist + ((key >> shift) & 255u), 1);
     }
   }
@@ -264,7 +285,12 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
     overflow |= c < 0;
     n_total += abs(c);
   }
-  const float margin = a.row_margin[b] * sqrtf(*a.wnorm_sq_max);
+  const float wn = sqrtf(a.scalars[SC_WNORM_SQ_MAX]);
+  const ScreenBound sbd = screen_bound(a.D, wn, a.scalars[SC_BIAS_ABS_MAX]);
+  const float err_bound = a.row_norm[b] * sbd.A + a.row_scale[b] * sbd.Bc + sbd.C;  // E_b
+  const float margin = 2.f * err_bound;
+  // an encoder row outside the fp16 range makes the whole screen meaningless (inf / nan operands)
+  overflow |= !(wn < FP16_MAX) || a.force_unsafe != 0;
 
   // ---- merged admission threshold: (k-th largest screen value of the row, to 16 bits) - margin ----
   // Every list was trimmed against ITS k-th largest; the row's k-th largest is at least as large.
@@ -274,7 +300,7 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
     int need = a.K;
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 24, prefix, need, hist, lane);
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 16, prefix, need, hist, lane);
-    tkey = fkey_s(funkey_s(prefix << 16) - margin);
+    tkey = fkey(funkey(prefix << 16) - margin);
   }
   // ---- collect the survivors ----
   int n = 0;
@@ -285,7 +311,7 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       const int e = e0 + lane;
       int2 t = make_int2(0, -1);
       if (e < c) t = __ldg(lb + e);
-      const bool take = (e < c) && fkey_s(__int_as_float(t.x)) >= tkey;
+      const bool take = (e < c) && fkey(__int_as_float(t.x)) >= tkey;
       const unsigned bal = __ballot_sync(FULL, take);
       const int o = n + __popc(bal & ((1u << lane) - 1u));
       if (take && o < RESCORE_CAP) {
@@ -295,13 +321,14 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       n += __popc(bal);
     }
   }
-  if (n > RESCORE_CAP) {  // pathological near-tie row: cannot be certified
+  if (n > RESCORE_CAP) {  // more near-ties than one warp re-scores: the exact path takes the row
     overflow = true;
     n = RESCORE_CAP;
   }
+  if (n < min(a.K, a.S)) overflow = true;  // (cannot happen with a healthy screen: every list keeps >= k entries)
   __syncwarp();
 
-  // ---- exact re-score, 4 candidates in flight ----
+  // ---- exact re-score, RB candidates in flight ----
   float4 xr[VPL];
   const float* xrow = a.x + static_cast<long long>(b) * a.D;
 #pragma unroll
@@ -312,37 +339,52 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   // RB candidates per round; all RB x VPL row loads are issued before the first multiply so that a warp keeps
   // RB x D x 4 bytes in flight (the loop is bound by the latency of these gathers, not by their volume).
   constexpr int RB = 2;
-  for (int c0 = 0; c0 < n; c0 += RB) {
-    int jj[RB];
-    float4 w[RB][VPL];
+  if (!overflow) {
+    for (int c0 = 0; c0 < n; c0 += RB) {
+      int jj[RB];
+      float4 w[RB][VPL];
 #pragma unroll
-    for (int u = 0; u < RB; ++u) {
-      jj[u] = si[min(c0 + u, n - 1)];
-      const float* r = a.W_enc_t + static_cast<long long>(jj[u]) * a.D;
+      for (int u = 0; u < RB; ++u) {
+        jj[u] = si[min(c0 + u, n - 1)];
+        const float* r = a.W_enc_t + static_cast<long long>(jj[u]) * a.D;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        w[u][i] = (v < D4) ? ldg4(r + 4 * v) : make_float4(0, 0, 0, 0);
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          w[u][i] = (v < D4) ? ldg4(r + 4 * v) : make_float4(0, 0, 0, 0);
+        }
+      }
+      float acc[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) acc[u] = row_dot<VPL>(xr, w[u]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+          if (c0 + u < n) se[c0 + u] = acc[u] + __ldg(a.b_enc + jj[u]);
       }
     }
-    float acc[RB];
+    __syncwarp();
+    // The candidate set covers the exact top-k when every screen error is <= E_b.  The bound is deterministic; the
+    // check below guards its assumptions (accumulation model of the tensor core) on the columns we can see.
+    float maxerr = 0.f;
+    for (int c = lane; c < n; c += 32) maxerr = fmaxf(maxerr, fabsf(sv[c] - se[c]));
 #pragma unroll
-    for (int u = 0; u < RB; ++u) {
-      acc[u] = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) acc[u] += dot4(xr[i], w[u][i]);
-      acc[u] = warp_sum(acc[u]);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int u = 0; u < RB; ++u)
-        if (c0 + u < n) se[c0 + u] = acc[u] + __ldg(a.b_enc + jj[u]);
-    }
+    for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(FULL, maxerr, o));
+    overflow = !(maxerr <= err_bound);  // (also catches NaN)
   }
-  __syncwarp();
+  if (lane == 0) {
+    unsigned int* cnt_u = reinterpret_cast<unsigned int*>(a.scalars);
+    atomicAdd(cnt_u + SC_RESCORED, static_cast<unsigned int>(n));
+    atomicAdd(cnt_u + SC_MERGED, static_cast<unsigned int>(n_total));
+  }
+  if (overflow) {  // warp-uniform: leave the row to launch_repair_topk (nothing of it has been written)
+    if (lane == 0) {
+      atomicAdd(reinterpret_cast<unsigned int*>(a.scalars) + SC_UNSAFE_TOTAL, 1u);
+      a.unsafe_list[atomicAdd(reinterpret_cast<int*>(a.scalars) + SC_N_UNSAFE, 1)] = b;
+    }
+    return;
+  }
 
   // ---- final selection on exact values; order: value desc, then column asc ----
-  float maxerr = 0.f;
   const int k_eff = min(a.K, n);
   for (int c0 = 0; c0 < n; c0 += 32) {
     const int c = c0 + lane;
@@ -354,7 +396,6 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
         const float vt = se[t];
         rank += (vt > v) || (vt == v && si[t] < id);
       }
-      maxerr = fmaxf(maxerr, fabsf(sv[c] - v));
       if (rank < a.K) {
         const long long o = static_cast<long long>(b) * a.K + rank;
         a.topk_idx[o] = id;
@@ -364,23 +405,15 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       }
     }
   }
-  for (int r = k_eff + lane; r < a.K; r += 32) {  // fewer candidates than k (d_sae < k never happens; defensive)
+  for (int r = k_eff + lane; r < a.K; r += 32) {  // d_sae < k is rejected at create; defensive
     a.topk_idx[static_cast<long long>(b) * a.K + r] = -1;
     a.topk_val[static_cast<long long>(b) * a.K + r] = 0.f;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(FULL, maxerr, o));
-  // The candidate set covers the exact top-k when every screen error is <= margin / 2.  Count the rows where
-  // that cannot be certified: buffer overflow, or an observed error above the bound the margin assumes.
-  if (lane == 0 && a.unsafe_rows != nullptr) {
-    if (overflow || maxerr > 0.5f * margin) atomicAdd(a.unsafe_rows, 1u);
-    atomicAdd(a.unsafe_rows + 2, static_cast<unsigned int>(n));        // diagnostics: candidates re-scored
-    atomicAdd(a.unsafe_rows + 4, static_cast<unsigned int>(n_total));  //              list entries merged
   }
 }
 
 int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
   if (a.D % 4) return 21;
+  if (cudaMemsetAsync(reinterpret_cast<int*>(a.scalars) + SC_N_UNSAFE, 0, 4, s) != cudaSuccess) return 23;
   ++g_launch_count;
   const int need_ = (a.D + 127) / 128;
   static const int wpb = [] { const char* v = getenv("SAEV_B200_RESCORE_WPB"); return v ? atoi(v) : 1; }();
@@ -1378,7 +1411,7 @@ int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq,
 }
 
 // ------------------------------------------------------------------------------------------------
-// clip-scale + Adam + decoder row renorm + bf16 shadow of W_enc_t, one warp per dictionary atom.
+// clip-scale + Adam + decoder row renorm + fp16 screen copy of W_enc_t, one warp per dictionary atom.
 //   c = min(1, max_norm / (grad_scale*||g|| + 1e-6))                 (saev train.py:358-360)
 //   m += (g-m)(1-b1); v = b2 v + (1-b2) g^2; p -= (lr/bc1) m / (sqrt(v)/sqrt(bc2) + eps)
 //                                                                    (torch Adam(fused=True), train.py:294,444-446)
@@ -1426,7 +1459,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   const int D4 = a.D >> 2;
   const long long SD = static_cast<long long>(a.S) * a.D;
   const long long ro = static_cast<long long>(j) * a.D;
-  // ---- W_enc_t row (+ bf16 shadow, + max row norm for the screen's admission margin) ----
+  // ---- W_enc_t row (+ fp16 screen copy, + max row norm for the screen's error bound) ----
   {
     float* mrow = a.m + ro;
     float* vrow = a.v + ro;
@@ -1443,10 +1476,10 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
         *reinterpret_cast<float4*>(mrow + 4 * v4) = m;
         *reinterpret_cast<float4*>(vrow + 4 * v4) = v;
         ssq += dot4(p, p);
-        if (a.shadow_hi != nullptr) {
-          __nv_bfloat162* so = reinterpret_cast<__nv_bfloat162*>(a.shadow_hi + ro + 4 * v4);
-          so[0] = __nv_bfloat162(__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y));
-          so[1] = __nv_bfloat162(__float2bfloat16_rn(p.z), __float2bfloat16_rn(p.w));
+        if (a.shadow16 != nullptr) {
+          __half2* so = reinterpret_cast<__half2*>(a.shadow16 + ro + 4 * v4);
+          so[0] = __floats2half2_rn(p.x, p.y);
+          so[1] = __floats2half2_rn(p.z, p.w);
         }
       }
     }
@@ -1458,9 +1491,11 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   // ---- b_enc[j] (a sharded optimizer updates the whole bias vector on every rank instead) ----
   if (lane == 0 && !a.b_enc_separately) {
     float m = a.m[SD + j], v = a.v[SD + j];
-    a.b_enc[j] = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+    const float nb = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+    a.b_enc[j] = nb;
     a.m[SD + j] = m;
     a.v[SD + j] = v;
+    if (a.bias_abs_max != nullptr) atomicMax(reinterpret_cast<int*>(a.bias_abs_max), __float_as_int(fabsf(nb)));
   }
   // ---- W_dec row (+ renorm) ----
   {
@@ -1505,9 +1540,11 @@ __global__ void adam_benc_kernel(AdamArgs a) {
   const AdamScalars sc = adam_scalars(a);
   const long long o = static_cast<long long>(a.S) * a.D + j;
   float m = a.m[o], v = a.v[o];
-  a.b_enc[j] = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+  const float nb = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
+  a.b_enc[j] = nb;
   a.m[o] = m;
   a.v[o] = v;
+  if (a.bias_abs_max != nullptr) atomicMax(reinterpret_cast<int*>(a.bias_abs_max), __float_as_int(fabsf(nb)));
 }
 
 __global__ void adam_bdec_kernel(AdamArgs a) {
@@ -1525,6 +1562,7 @@ __global__ void adam_bdec_kernel(AdamArgs a) {
 int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
   if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
+  if (a.bias_abs_max != nullptr && cudaMemsetAsync(a.bias_abs_max, 0, 4, s) != cudaSuccess) return 23;
   const int rows = a.row_end - a.row_begin;
   if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
   if (a.b_enc_separately) {

@@ -121,13 +121,17 @@ class Engine:
         return self._ws_tensor(self.lib.saev_b200_active_flags, torch.int32, self.S)
 
     def unsafe_rows(self) -> int:
+        """Rows the tensor-core screen could not certify since the last sync_weights() (each was re-done by the exact
+        fp32 path in the same forward, see `screen_stats()["repaired"]`).  Host sync."""
         return int(self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 1).item())
 
     def screen_stats(self) -> dict:
         """Cumulative diagnostics of the top-k screen since the last sync_weights(): rows that could not be
-        certified, candidates re-scored in fp32, candidate-list entries merged."""
-        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 5).tolist()
-        return {"unsafe_rows": t[0], "rescored": t[2] & 0xFFFFFFFF, "merged": t[4] & 0xFFFFFFFF}
+        certified, rows re-done by the exact path (equal once the forward has finished), candidates re-scored in
+        fp32, candidate-list entries merged."""
+        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 8).tolist()
+        return {"unsafe_rows": t[0], "repaired": t[7], "unrepaired": t[0] - t[7], "rescored": t[2] & 0xFFFFFFFF,
+                "merged": t[4] & 0xFFFFFFFF}
 
     # ---- parameters ------------------------------------------------------------------------
     @torch.no_grad()
@@ -162,7 +166,8 @@ class Engine:
     def sync_weights(self) -> None:
         with torch.cuda.device(self.device):
             self._ck(
-                self.lib.saev_b200_sync_weights(self.h, self.W_enc_t.data_ptr(), self.workspace.data_ptr(), self._stream())
+                self.lib.saev_b200_sync_weights(self.h, self.W_enc_t.data_ptr(), self.b_enc.data_ptr(),
+                                                self.workspace.data_ptr(), self._stream())
             )
 
     def normalize_w_dec(self) -> None:
@@ -255,8 +260,8 @@ class Engine:
         return self.sumsq
 
     def shadow_weights(self) -> torch.Tensor:
-        """The bf16 tensor-core operand copy of W_enc_t, [d_sae, d_model], inside the workspace."""
-        return self._ws_tensor(self.lib.saev_b200_shadow_weights, torch.bfloat16, self.S * self.D).view(self.S, self.D)
+        """The fp16 tensor-core operand copy of W_enc_t, [d_sae, d_model], inside the workspace."""
+        return self._ws_tensor(self.lib.saev_b200_shadow_weights, torch.float16, self.S * self.D).view(self.S, self.D)
 
     def wnorm_scalar(self) -> torch.Tensor:
         """Device scalar max_j ||W_enc_t[j]||^2 the top-k screen derives its admission margin from."""

@@ -39,7 +39,7 @@ class OracleEngine:
         self.losses, self.sumsq = torch.zeros(8), torch.zeros(1)
         self._flags = torch.zeros(S, dtype=torch.int32)
         self.toks = torch.zeros(S, dtype=torch.int64)
-        self._shadow = torch.zeros(S, D, dtype=torch.bfloat16)
+        self._shadow = torch.zeros(S, D, dtype=torch.float16)
         self._wnorm = torch.zeros(1)
         self.shard = None
         self.t = 0
@@ -62,7 +62,7 @@ class OracleEngine:
         return self._wnorm
 
     def sync_weights(self):
-        self._shadow.copy_(self.W_enc_t.bfloat16())
+        self._shadow.copy_(self.W_enc_t.half())
         self._wnorm[0] = self.W_enc_t.pow(2).sum(1).max()
 
     def set_optimizer_shard(self, j0, j1):
@@ -77,7 +77,7 @@ class OracleEngine:
         if phase & _lib.PHASE_A:
             self.calls.append("A")
             # the screen runs on the bf16 operand copy: it must be complete and current on every rank
-            assert torch.equal(self._shadow, self.W_enc_t.bfloat16()), "stale bf16 operand rows"
+            assert torch.equal(self._shadow, self.W_enc_t.half()), "stale fp16 operand rows"
             assert float(self._wnorm) == pytest.approx(float(self.W_enc_t.pow(2).sum(1).max()), rel=1e-6)
             st = self._st = self._state()
             h = orc.encode_pre(x, st.W_enc, st.b_enc)
@@ -150,7 +150,7 @@ class OracleEngine:
             p.sub_((lr / bc1) * (m / (v.sqrt() / bc2s + CFG.eps)))
         if renorm_w_dec:
             self.W_dec[j0:j1] = orc.normalize_w_dec(self.W_dec[j0:j1])
-        self._shadow[j0:j1] = self.W_enc_t[j0:j1].bfloat16()
+        self._shadow[j0:j1] = self.W_enc_t[j0:j1].half()
         self._wnorm[0] = self.W_enc_t[j0:j1].pow(2).sum(1).max()
 
 

@@ -89,6 +89,20 @@ size_t saev_b200_workspace_bytes(const saev_b200_handle* h);
 int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const float* b_enc, void* workspace,
                            void* stream);
 
+/* Datapoint initialisation of the dictionary on the device (src/saev/framework/train.py:141-185; saev runs it on the
+ * host, from batches it pulled through the loader).  acts[n_rows, d_model]: the sample rows (already shuffled as
+ * train.py:161 does); src_row[d_sae] (int64, device): for atom j the row of `acts` it is seeded from (train.py:169
+ * `idx`); noise[*, d_model]: the kaiming rows (train.py:165-166), atom j uses row noise_row[j] (int64, device; NULL: j).
+ *   enc_j = blend * (acts[src_row[j]] - mean(acts)) + (1 - blend) * noise[noise_row[j]]
+ *   tie_transpose (cfg.reinit_enc_dec_tranpose): W_dec[j] = enc_j;  normalize (cfg.normalize_w_dec): W_dec[j] /= ||.||
+ *   W_enc[:, j] = W_dec[j]                                              (train.py:181)
+ * mean_out[d_model] receives the column mean.  Ends with saev_b200_sync_weights. */
+int saev_b200_datapoint_init(saev_b200_handle* h, const float* acts, int64_t n_rows, const int64_t* src_row,
+                             const float* noise, const int64_t* noise_row, float blend, int32_t tie_transpose,
+                             int32_t normalize,
+                             float* mean_out, float* W_enc_t, const float* b_enc, float* W_dec, void* workspace,
+                             void* stream);
+
 /* W_dec[j,:] /= ||W_dec[j,:]||_2    (modeling.py:411-417) */
 int saev_b200_normalize_w_dec(saev_b200_handle* h, float* W_dec, void* stream);
 

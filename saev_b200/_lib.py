@@ -84,6 +84,7 @@ SIGNATURES = {
     "saev_b200_destroy": (C.c_int, [_p]),
     "saev_b200_workspace_bytes": (C.c_size_t, [_p]),
     "saev_b200_sync_weights": (C.c_int, [_p, _p, _p, _p, _p]),
+    "saev_b200_datapoint_init": (C.c_int, [_p, _p, _i64, _p, _p, _p, _f, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "saev_b200_normalize_w_dec": (C.c_int, [_p, _p, _p]),
     "saev_b200_forward": (
         C.c_int,

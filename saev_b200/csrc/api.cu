@@ -561,6 +561,30 @@ int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const floa
   return check_cuda(h, "sync_weights");
 }
 
+int saev_b200_datapoint_init(saev_b200_handle* h, const float* acts, int64_t n_rows, const int64_t* src_row,
+                             const float* noise, const int64_t* noise_row, float blend, int32_t tie_transpose, int32_t normalize,
+                             float* mean_out, float* W_enc_t, const float* b_enc, float* W_dec, void* workspace,
+                             void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h || !acts || !src_row || !noise || !mean_out || !W_enc_t || !W_dec || !workspace)
+    return fail(h, 32, "datapoint_init: null argument%s");
+  if (n_rows <= 0 || !(blend >= 0.f && blend <= 1.f)) return fail(h, 32, "datapoint_init: need n_rows > 0 and 0 <= blend <= 1%s");
+  const int D = h->cfg.d_model, S = h->cfg.d_sae;
+  // mean over the sample rows (train.py:163), in chunks the column-sum scratch was sized for
+  const int chunk = h->cfg.max_batch;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int rows = static_cast<int>(n_rows - r0 < chunk ? n_rows - r0 : chunk);
+    if (launch_colsum(acts + r0 * D, rows, D, static_cast<float>(1.0 / static_cast<double>(n_rows)), r0 > 0 ? 1 : 0,
+                      at<float>(workspace, h->ws.colsum_partial), mean_out, s))
+      return fail(h, 33, "datapoint_init: mean launch failed%s");
+  }
+  if (launch_datapoint_init(acts, reinterpret_cast<const long long*>(src_row), mean_out, noise,
+                            reinterpret_cast<const long long*>(noise_row), blend, tie_transpose,
+                            normalize, S, D, W_enc_t, W_dec, s))
+    return fail(h, 33, "datapoint_init: launch failed%s");
+  return saev_b200_sync_weights(h, W_enc_t, b_enc, workspace, stream);
+}
+
 int saev_b200_normalize_w_dec(saev_b200_handle* h, float* W_dec, void* stream) {
   if (launch_normalize_rows(W_dec, h->cfg.d_sae, h->cfg.d_model, static_cast<cudaStream_t>(stream)))
     return fail(h, 31, "normalize_w_dec: launch failed%s");

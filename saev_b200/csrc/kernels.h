@@ -155,6 +155,10 @@ int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStr
 // *out = max_i |v[i]|
 int launch_abs_max(const float* v, int n, float* out, cudaStream_t s);
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
+// datapoint initialisation (saev train.py:141-185); see the kernel
+int launch_datapoint_init(const float* acts, const long long* src_row, const float* mean, const float* noise,
+                          const long long* noise_row, float blend, int tie, int normalize, int S, int D, float* W_enc_t,
+                          float* W_dec, cudaStream_t s);
 int launch_log_metrics(const float* x, const float* r, int B, int D, const float* W, int S, const int* fired,
                        double* acc, const float* coh, double* out, cudaStream_t s);
 int launch_eval_accumulate(const float* x, const float* r, int B, int D, const float* losses, double* acc,

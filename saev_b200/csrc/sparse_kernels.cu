@@ -210,6 +210,74 @@ int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Datapoint initialisation of the dictionary (saev train.py:141-185), one warp per atom j:
+//   enc_j   = blend * (acts[src_row[j]] - mean) + (1 - blend) * noise[j]         (:168-171)
+//   W_dec[j] = enc_j (when the transpose is tied, :177-178), normalised (:179, cfg.normalize_w_dec)
+//   W_enc[:, j] = W_dec[j]                                                        (:181)
+// Both matrices are atom-major here, so the last two lines are one row written twice.
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) datapoint_init_kernel(const float* __restrict__ acts,
+                                                             const long long* __restrict__ src_row,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ noise,
+                                                             const long long* __restrict__ noise_row, float blend, int tie,
+                                                             int normalize, int S, int D, float* __restrict__ W_enc_t,
+                                                             float* __restrict__ W_dec) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= S) return;
+  const int lane = threadIdx.x & 31, D4 = D >> 2;
+  const float* arow = acts + src_row[j] * D;
+  const float* nrow = noise + (noise_row != nullptr ? noise_row[j] : static_cast<long long>(j)) * D;
+  float* drow = W_dec + static_cast<long long>(j) * D;
+  float4 w[VPL];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    w[i] = make_float4(0, 0, 0, 0);
+    if (v < D4) {
+      if (tie) {
+        const float4 a = ldg4(arow + 4 * v), m = ldg4(mean + 4 * v), n = ldg4(nrow + 4 * v);
+        // same operation order as the reference: blend * (a - m) + (1 - blend) * n
+        w[i].x = blend * (a.x - m.x) + (1.f - blend) * n.x;
+        w[i].y = blend * (a.y - m.y) + (1.f - blend) * n.y;
+        w[i].z = blend * (a.z - m.z) + (1.f - blend) * n.z;
+        w[i].w = blend * (a.w - m.w) + (1.f - blend) * n.w;
+      } else {
+        w[i] = *reinterpret_cast<const float4*>(drow + 4 * v);  // W_dec keeps its rows; only W_enc follows it
+      }
+      ss += dot4(w[i], w[i]);
+    }
+  }
+  if (normalize) {
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      w[i].x /= nrm; w[i].y /= nrm; w[i].z /= nrm; w[i].w /= nrm;
+    }
+  }
+  float* erow = W_enc_t + static_cast<long long>(j) * D;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) {
+      *reinterpret_cast<float4*>(drow + 4 * v) = w[i];
+      *reinterpret_cast<float4*>(erow + 4 * v) = w[i];
+    }
+  }
+}
+int launch_datapoint_init(const float* acts, const long long* src_row, const float* mean, const float* noise,
+                          const long long* noise_row, float blend, int tie, int normalize, int S, int D, float* W_enc_t,
+                          float* W_dec, cudaStream_t s) {
+  if (D % 4) return 21;
+  SB_DISPATCH_VPL(D, (datapoint_init_kernel<VPL><<<(S + 7) / 8, 256, 0, s>>>(acts, src_row, mean, noise, noise_row, blend, tie,
+                                                                             normalize, S, D, W_enc_t, W_dec)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Merge the per-split candidate buffers of a row, recompute the exact fp32 pre-activation of each
 // candidate (h = <x_b, W_enc_t[j]> + b_enc[j], saev modeling.py:344-347) and select the top-k of
 // those (TopKActivation.forward, modeling.py:169-179: no ReLU, exactly k kept).  One warp per row.

@@ -8,9 +8,11 @@ Same constructor, attributes and batch schema as the reference loader
 with every (example, content token) of the requested layer delivered exactly once per epoch in a shuffled order
 and a short last batch (`need = min(batch_size, remaining)`, shuffled.py:513).  The difference is where the work
 happens: the shuffle pool is a device-resident buffer filled from pinned staging chunks by native I/O threads
-(saev_b200/csrc/shard_loader.cu) and the batch tensors are CUDA tensors that alias the loader's ring of device
-batch buffers, so `batch["act"].to(device, non_blocking=True)` (train.py:333) is a no-op.  A batch stays valid
-until the iteration has advanced twice more (ring of 3 buffers by default).
+(saev_b200/csrc/shard_loader.cu) and the batch tensors are CUDA tensors, so `batch["act"].to(device,
+non_blocking=True)` (train.py:333) is a no-op.  By default every batch is an OWNED tensor (one device-to-device copy out
+of the loader's ring of batch buffers, ~20 us for 67 MB), valid for as long as the caller keeps it -- saev's
+`make_saes` holds four or more batches before concatenating them (train.py:147-160).  `alias_ring=True` hands out
+zero-copy views of the ring instead; such a batch is only valid until the iteration has advanced twice more.
 
 Multi-GPU: rank r of W reads the shards `order[r::W]` of the seeded shard permutation (disjoint files per rank)
 and every rank delivers the same number of rows per epoch (the minimum over ranks), so data-parallel steps stay
@@ -87,6 +89,30 @@ class Metadata:
         known = {f.name for f in dataclasses.fields(cls)}
         return cls(**{k: v for k, v in d.items() if k in known})
 
+    def _json_dict(self) -> dict:
+        d = dataclasses.asdict(self)
+        d["layers"] = list(self.layers)
+        d["dataset"] = str(self.dataset)
+        return d
+
+    @property
+    def hash(self) -> str:
+        """shards.py:126-135: first 8 hex digits of the SHA-256 of the sorted-key compact JSON of the metadata (what
+        orjson.dumps(..., OPT_SORT_KEYS) produces), i.e. the name of the shard directory."""
+        import hashlib
+
+        blob = json.dumps(self._json_dict(), sort_keys=True, separators=(",", ":"), ensure_ascii=False).encode("utf8")
+        return hashlib.sha256(blob).hexdigest()[:8]
+
+    def dump(self, shards_root) -> None:
+        """shards.py:112-124: write metadata.json into shards_root / hash."""
+        shards_root = pathlib.Path(shards_root)
+        assert shards_root.parts[-2:] == ("saev", "shards"), f"'{shards_root}' must end in saev/shards (disk.py:29-41)"
+        (shards_root / self.hash).mkdir(exist_ok=True, parents=True)
+        with open(shards_root / self.hash / "metadata.json", "w") as fd:
+            json.dump(self._json_dict(), fd, indent=2)
+            fd.write("\n")
+
     @property
     def tokens_per_example(self) -> int:
         return self.content_tokens_per_example + int(self.cls_token)
@@ -102,6 +128,85 @@ class Metadata:
     @property
     def shard_shape(self) -> tuple:
         return (self.examples_per_shard, len(self.layers), self.tokens_per_example, self.d_model)
+
+
+class ShardWriter:
+    """Writer side of the shard format the loader reads (mirror of saev's ShardWriter, shards.py:372-527): fp32
+    memmaps `acts%06d.bin` of shape [examples_per_shard, n_layers, tokens_per_example, d_model] plus `shards.json`
+    with the number of valid examples per file.  Same call protocol:
+
+        md.dump(shards_root)
+        with ShardWriter(shards_root, md) as w:
+            w.write_batch(acts[n, n_layers, tokens, d_model], start_idx)
+
+    `write_batch` accepts CPU or CUDA tensors (CUDA batches come down through one reused pinned buffer).  Like the
+    reference, a batch that exactly fills a shard rolls over to a new (empty, all-zero) one (`>=` at shards.py:434),
+    which readers skip through its `n_examples: 0` entry."""
+
+    def __init__(self, shards_root, md: Metadata):
+        shards_root = pathlib.Path(shards_root)
+        assert shards_root.parts[-2:] == ("saev", "shards"), f"'{shards_root}' must end in saev/shards"
+        self.md = md
+        self.shards_dir = shards_root / md.hash
+        self.shards_dir.mkdir(exist_ok=True, parents=True)
+        self._shards: list[dict] = []
+        self._pinned = None
+        self.shard = -1
+        self.acts = None
+        self.filled = 0
+        self.next_shard()
+
+    def _host(self, t) -> np.ndarray:
+        if isinstance(t, np.ndarray):
+            return t
+        if t.is_cuda:
+            if self._pinned is None or self._pinned.numel() < t.numel():
+                self._pinned = torch.empty(t.numel(), dtype=torch.float32).pin_memory()
+            dst = self._pinned[: t.numel()].view(t.shape)
+            dst.copy_(t.to(torch.float32), non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return dst.numpy()
+        return t.detach().to(torch.float32).numpy()
+
+    def write_batch(self, activations, start_idx: int, patch_labels=None) -> None:
+        if patch_labels is not None:
+            raise NotImplementedError("saev_b200.data.ShardWriter does not write labels.bin (segmentation labels)")
+        batch_size = len(activations)
+        end_idx = start_idx + batch_size
+        eps = self.md.examples_per_shard
+        offset = eps * self.shard
+        if end_idx >= offset + eps:  # shards.py:434
+            n_fit = offset + eps - start_idx
+            self.acts[start_idx - offset : start_idx - offset + n_fit] = self._host(activations[:n_fit])
+            self.filled = start_idx - offset + n_fit
+            self.next_shard()
+            if n_fit < batch_size:
+                self.write_batch(activations[n_fit:], start_idx + n_fit)
+        else:
+            assert 0 <= start_idx - offset and end_idx - offset <= eps, (start_idx, end_idx, offset, eps)
+            self.acts[start_idx - offset : end_idx - offset] = self._host(activations)
+            self.filled = end_idx - offset
+
+    def flush(self) -> None:
+        if self.acts is not None:
+            self.acts.flush()
+            self._shards.append({"name": os.path.basename(self.acts_path), "n_examples": int(self.filled)})
+            with open(self.shards_dir / "shards.json", "w") as fd:
+                json.dump(self._shards, fd, indent=2)
+        self.acts = None
+
+    def next_shard(self) -> None:
+        self.flush()
+        self.shard += 1
+        self.acts_path = self.shards_dir / f"acts{self.shard:06}.bin"
+        self.acts = np.memmap(self.acts_path, mode="w+", dtype=np.float32, shape=self.md.shard_shape)
+        self.filled = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.flush()
 
 
 def _load_metadata(shards_dir: pathlib.Path):
@@ -160,8 +265,10 @@ class ShuffledDataLoader:
     """Streaming shuffled loader over saev activation shards; see the module docstring."""
 
     def __init__(self, cfg, *, device: torch.device | str | None = None, rank: int | None = None,
-                 world_size: int | None = None, n_out_slots: int = 3, chunk_examples: int = 0):
+                 world_size: int | None = None, n_out_slots: int = 3, chunk_examples: int = 0,
+                 alias_ring: bool = False):
         self.cfg = cfg
+        self.alias_ring = alias_ring
         self._h = None
         self._lib = None
         self.reservoir = None
@@ -316,11 +423,16 @@ class ShuffledDataLoader:
                     raise RuntimeError(f"loader crashed:\n{lib.saev_b200_loader_last_error(h).decode()}")
                 if n.value == 0:
                     return
-                yield {
+                batch = {
                     "act": self._wrap(act.value, n.value, (n.value, D), torch.float32),
                     "example_idx": self._wrap(ex.value, n.value, (n.value,), torch.int32),
                     "token_idx": self._wrap(tok.value, n.value, (n.value,), torch.int32),
                 }
+                if not self.alias_ring:
+                    # owned copies, enqueued on the consumer stream right behind the loader's event wait (the ring
+                    # slot is not recycled before the stream has passed this point)
+                    batch = {k: v.clone() for k, v in batch.items()}
+                yield batch
         finally:
             self._iterating = False
             if self._h is h:  # shutdown() may already have destroyed the native loader

@@ -170,6 +170,24 @@ class Engine:
                                                 self.workspace.data_ptr(), self._stream())
             )
 
+    @torch.no_grad()
+    def datapoint_init(self, acts: torch.Tensor, src_row: torch.Tensor, noise: torch.Tensor,
+                       noise_row: torch.Tensor | None, blend: float, *, tie_transpose: bool = True) -> torch.Tensor:
+        """saev's datapoint initialisation (train.py:141-185) on the device; see saev_b200_datapoint_init.
+        Returns the column mean of `acts`."""
+        assert acts.is_cuda and acts.dtype == torch.float32 and acts.is_contiguous() and acts.shape[1] == self.D
+        assert src_row.is_cuda and src_row.dtype == torch.int64 and src_row.numel() == self.S
+        assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape[1] == self.D
+        if noise_row is not None:
+            assert noise_row.is_cuda and noise_row.dtype == torch.int64 and noise_row.numel() == self.S
+        mean = torch.empty(self.D, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_datapoint_init(
+                self.h, acts.data_ptr(), acts.shape[0], src_row.data_ptr(), noise.data_ptr(), _lib.ptr(noise_row),
+                float(blend), int(tie_transpose), int(self.cfg.normalize_w_dec), mean.data_ptr(), self.W_enc_t.data_ptr(),
+                self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.workspace.data_ptr(), self._stream()))
+        return mean
+
     def normalize_w_dec(self) -> None:
         if not self.cfg.normalize_w_dec:
             return

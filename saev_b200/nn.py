@@ -278,8 +278,16 @@ class SparseAutoencoder(torch.nn.Module):
         # Fold normalize_w_dec (train.py:334-335) into the tail of the Adam kernel.  Off by default: the reference
         # normalises at the START of the next step, so its checkpoints hold un-normalised rows.
         self.fuse_renorm = False
+        # loss.loss.backward() passes an upstream gradient of exactly 1 (so does (loss_a + loss_b).backward()); anything
+        # else (a scaled loss) is NOT honoured by the fused backward.  It is counted on the device and raised by the
+        # next Loss.metrics() / check_grad_out() -- the places that synchronise anyway.
+        self._check_grad_out = True
+        self._bad_grad_out: Tensor | None = None
         self._dp_group = None
         self._dp_world = 1
+        self._dp_synced = False      # replicas start from rank 0's parameters (first _bind after data_parallel())
+        self._fused_adam = None      # weakref to the FusedAdam that owns exactly these four parameters (optim.py)
+        self._seen_versions = None   # tensor version counters at the last bind: in-place writes by torch bump them
         ref = weakref.ref(self)
         for p in (self.W_dec, self.b_dec, self.W_enc, self.b_enc):
             p._b200_owner = ref
@@ -292,6 +300,7 @@ class SparseAutoencoder(torch.nn.Module):
             raise RuntimeError("data_parallel(): torch.distributed is not initialised")
         self._dp_group = group
         self._dp_world = dist.get_world_size(group)
+        self._dp_synced = False
         return self
 
     # ---- engine binding --------------------------------------------------------------------
@@ -340,7 +349,40 @@ class SparseAutoencoder(torch.nn.Module):
             self.b_dec.data = eng.b_dec
             eng.sync_weights()
             self._w_dec_normalized = False
+        elif self._seen_versions != self._param_versions():
+            # in-place writes through torch (load_state_dict's param.copy_, a stock optimizer such as Muon, W.mul_()):
+            # same storage, new values -- the screen's fp16 copy and norm bounds are stale
+            eng.sync_weights()
+            self._w_dec_normalized = False
+        if self._dp_world > 1 and not self._dp_synced:
+            # saev's init is unseeded and datapoint init reads rank-local shards: without this every replica would start
+            # from different weights and stay different (the summed gradient is the only thing the ranks share)
+            dist.broadcast(eng.params, src=dist.get_global_rank(self._dp_group, 0) if self._dp_group is not None else 0,
+                           group=self._dp_group)
+            dist.broadcast(eng.m, src=dist.get_global_rank(self._dp_group, 0) if self._dp_group is not None else 0,
+                           group=self._dp_group)
+            dist.broadcast(eng.v, src=dist.get_global_rank(self._dp_group, 0) if self._dp_group is not None else 0,
+                           group=self._dp_group)
+            eng.sync_weights()
+            self._w_dec_normalized = False
+            self._dp_synced = True
+        self._seen_versions = self._param_versions()
         return eng
+
+    def _param_versions(self) -> tuple:
+        return tuple(p._version for p in (self.W_enc, self.b_enc, self.W_dec, self.b_dec))
+
+    def parameter_checksum(self) -> Tensor:
+        """Device float64[4]: sums of the four parameters (data-parallel callers compare them across ranks)."""
+        return torch.stack([p.detach().double().sum() for p in (self.W_enc, self.b_enc, self.W_dec, self.b_dec)])
+
+    def check_grad_out(self) -> None:
+        """Raise if any backward since the last check received an upstream gradient other than 1 (host sync)."""
+        bad, self._bad_grad_out = self._bad_grad_out, None
+        if bad is not None and int(bad.item()) != 0:
+            raise NotImplementedError("saev_b200: the fused backward computes the gradients of loss.backward() only; "
+                                      f"{int(bad.item())} backward call(s) were given a scaled upstream gradient, which it "
+                                      "does not apply (scale the learning rate or the loss terms' coefficients instead)")
 
     def weights_changed(self) -> None:
         """Call after writing W_enc outside the optimizer (e.g. datapoint init, train.py:141-185) so the bf16
@@ -386,6 +428,11 @@ class SparseAutoencoder(torch.nn.Module):
             return
         if self._w_dec_normalized:
             return
+        if self.engine is None or self.W_dec.data_ptr() != self.engine.W_dec.data_ptr():
+            # no engine yet (first call of the loop, train.py:334): a plain row normalisation of the parameter; the
+            # engine is created by the forward that follows, at the real batch size
+            self.W_dec.data /= torch.norm(self.W_dec.data, dim=1, keepdim=True)
+            return
         self._bind(max(self._max_batch, 1)).normalize_w_dec()
 
     @torch.no_grad()
@@ -418,16 +465,24 @@ class MatryoshkaLoss:
     aux: Tensor
     n_dead: Tensor
     _total: Tensor = None
+    _sae: tp.Any = None
 
     @property
     def loss(self) -> Tensor:
         return self._total
 
     def metrics(self) -> dict[str, object]:
-        return {
+        out = {
             "loss": self.loss.item(), "mse": self.mse.item(), "l0": self.l0.item(), "l1": self.l1.item(),
             "sparsity": self.sparsity.item(), "aux": self.aux.item(), "n_dead": self.n_dead,
         }
+        if self._sae is not None:
+            self._sae.check_grad_out()
+            if self._sae.engine is not None and self._sae.engine.cfg.activation == "topk":
+                # rows the tensor-core screen could not certify and the exact fp32 path re-did (cumulative); not a
+                # reference key -- it shows up as loss/screen_repaired_rows in saev's log block (train.py:420)
+                out["screen_repaired_rows"] = self._sae.engine.screen_stats()["repaired"]
+        return out
 
 
 class _StepFunction(torch.autograd.Function):
@@ -454,6 +509,9 @@ class _StepFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         sae, eng = ctx.sae, ctx.sae.engine
+        if sae._check_grad_out:  # no host sync here: counted on the device, raised by the next Loss.metrics()
+            sae._bad_grad_out = (grad_out != 1).to(torch.int32) if sae._bad_grad_out is None else \
+                sae._bad_grad_out + (grad_out != 1).to(torch.int32)
         eng.backward(ctx.x, tokens_global=ctx.tokens_global)
         if sae._dp_world > 1:
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM, group=sae._dp_group)
@@ -465,7 +523,6 @@ class _StepFunction(torch.autograd.Function):
             elif p.grad.data_ptr() != g.data_ptr():
                 p.grad.add_(g)
         sae._grads_fused = True
-        # grad_out is 1 for `loss.backward()`; a scaled loss is not supported by the fused path
         return None, None, None, None, None, None, None
 
 
@@ -499,8 +556,54 @@ class MatryoshkaObjective(torch.nn.Module):
             total = eng.losses[6].clone()
         L = eng.losses.clone()
         loss = MatryoshkaLoss(mse=L[0], sparsity=L[2], l0=L[3], l1=L[4], aux=L[1], n_dead=L[5].to(torch.int64),
-                              _total=total)
+                              _total=total, _sae=sae)
         return loss, out
+
+
+@torch.no_grad()
+def datapoint_init(saes, dl, *, noise_device: str = "cuda") -> None:
+    """The datapoint initialisation of saev's `make_saes` (train.py:121-185) with the arithmetic on the device
+    (saev_b200_datapoint_init): pull max(d_sae, 65 536) rows from the loader, then per SAE
+        W_enc[:, j] = W_dec[j] = normalise(blend * (x_perm[idx[j]] - mean) + (1 - blend) * kaiming[idx[j]]).
+    The host draws (`randperm(n_samples)`, then one `randperm(d_sae)` per SAE) come from torch's global CPU generator in
+    the reference's order, so a seeded run picks the same rows; `kaiming` is drawn on `noise_device` (the reference
+    draws it wherever the loader's batches live: "cpu" with its own loader, "cuda" with this package's).
+    `saes`: saev_b200.nn.SparseAutoencoder modules already on the GPU."""
+    saes = list(saes)
+    if all(sae.cfg.reinit_blend == 0 for sae in saes):
+        return
+    assert saes, "Need at least one SAE to initialize."
+    d_sae = saes[0].cfg.d_sae
+    assert all(d_sae == sae.cfg.d_sae for sae in saes), "All SAEs must have same .d_sae"
+    n_samples = d_sae
+    if hasattr(dl, "n_samples"):
+        assert dl.n_samples >= n_samples, f"Need {n_samples} samples for datapoint init; dataloader has {dl.n_samples}."
+    n_samples = max(n_samples, 65_536)  # train.py:142-145
+    n_samples = min(n_samples, dl.n_samples)
+    dev = saes[0].W_dec.device
+    batches, n_seen = [], 0
+    for batch in dl:
+        act = batch["act"]
+        batches.append(act.to(dev))
+        n_seen += len(act)
+        if n_seen >= n_samples:
+            break
+    assert n_seen >= n_samples, f"Datapoint init requested {n_samples} samples but saw {n_seen}."
+    acts = torch.cat(batches, dim=0)[:n_samples].contiguous()
+    del batches
+    perm = torch.randperm(n_samples)  # train.py:161 `acts = acts[torch.randperm(n_samples)]`: folded into the row index
+    D = acts.shape[1]
+    noise = torch.empty(d_sae, D, device=noise_device)
+    torch.nn.init.kaiming_uniform_(noise)  # train.py:165-166
+    noise = noise.to(dev)
+    for sae in saes:
+        blend = sae.cfg.reinit_blend
+        assert 0.0 <= blend <= 1.0, f"reinit_blend must be in [0, 1], got {blend}."
+        idx = torch.randperm(d_sae)  # train.py:169
+        eng = sae._bind(max(sae._max_batch, 1))
+        eng.datapoint_init(acts, perm[idx].to(dev), noise, idx.to(dev), blend,
+                           tie_transpose=sae.cfg.reinit_enc_dec_tranpose)
+        sae._w_dec_normalized = bool(sae.cfg.normalize_w_dec)
 
 
 def get_objective(cfg) -> MatryoshkaObjective:
@@ -513,30 +616,36 @@ def get_objective(cfg) -> MatryoshkaObjective:
 # ----------------------------------------------------------------------------------------------
 # checkpoints (modeling.py:548-658, schema 5): one JSON header line + torch.save(state_dict)
 # ----------------------------------------------------------------------------------------------
-def _serialize_activation(act) -> dict:
-    d = {"key": act.key}
-    for f in dataclasses.fields(act):
-        if f.name == "key":
-            continue
-        v = getattr(act, f.name)
-        d[f.name] = _serialize_activation(v) if dataclasses.is_dataclass(v) else v
-    return d
+def _serialize_dataclass(obj) -> dict:
+    """modeling.py:466-472: {"cls": class name, "params": {field: value | nested payload}}."""
+    params = {}
+    for f in dataclasses.fields(obj):
+        v = getattr(obj, f.name)
+        params[f.name] = _serialize_dataclass(v) if dataclasses.is_dataclass(v) else v
+    return {"cls": type(obj).__name__, "params": params}
 
 
-_BY_KEY = {"no-sparsity": NoSparsity, "l1-sparsity": L1Sparsity, "no-aux": NoAux, "auxk": AuxK, "relu": Relu,
-           "top-k": TopK, "batch-top-k": BatchTopK}
+_BY_CLS = {c.__name__: c for c in (NoSparsity, L1Sparsity, NoAux, AuxK, Relu, TopK, BatchTopK)}
 
 
-def _deserialize(d: dict):
-    cls = _BY_KEY[d["key"]]
-    kw = {k: (_deserialize(v) if isinstance(v, dict) and "key" in v else v) for k, v in d.items() if k != "key"}
+def _deserialize_dataclass(payload: dict):
+    """modeling.py:486-505 (schema 5: no legacy nesting)."""
+    cls = _BY_CLS.get(payload["cls"])
+    if cls is None:
+        raise ValueError(f"Unknown activation class '{payload['cls']}' in payload.")
+    kw = {}
+    for k, v in payload["params"].items():
+        k = "key" if k == "kind" else k
+        kw[k] = _deserialize_dataclass(v) if isinstance(v, dict) and "cls" in v and "params" in v else v
     return cls(**kw)
 
 
 def dump(fpath, sae: SparseAutoencoder) -> None:
+    """modeling.py:548-574: one JSON header line {schema, cfg, commit, lib} + torch.save(state_dict).  The header is the
+    reference's schema 5, so `saev.nn.load` reads these files and `load` below reads saev's."""
     cfg = sae.cfg
     cfg_dict = {f.name: getattr(cfg, f.name) for f in dataclasses.fields(cfg)}
-    cfg_dict["activation"] = _serialize_activation(cfg.activation)
+    cfg_dict["activation"] = _serialize_dataclass(cfg.activation)
     header = {"schema": SCHEMA_VERSION, "cfg": cfg_dict, "commit": "unknown", "lib": f"saev_b200-{__version__}"}
     fpath = pathlib.Path(fpath)
     fpath.parent.mkdir(exist_ok=True, parents=True)
@@ -547,6 +656,7 @@ def dump(fpath, sae: SparseAutoencoder) -> None:
 
 
 def load(fpath, *, device="cpu") -> SparseAutoencoder:
+    """modeling.py:577-658 for schema-5 files (what saev.nn.dump and `dump` above write)."""
     with open(fpath, "rb") as fd:
         header = json.loads(fd.readline())
         buffer = io.BytesIO(fd.read())
@@ -554,7 +664,9 @@ def load(fpath, *, device="cpu") -> SparseAutoencoder:
         raise ValueError(f"saev_b200.nn.load reads schema {SCHEMA_VERSION} checkpoints; got {header.get('schema')!r} "
                          "(convert older files with saev.nn.load + saev.nn.dump)")
     cfg_dict = dict(header["cfg"])
-    cfg_dict["activation"] = _deserialize(cfg_dict["activation"])
+    cfg_dict["activation"] = _deserialize_dataclass(cfg_dict["activation"])
+    for legacy in ("n_reinit_samples", "seed"):  # modeling.py:449-453
+        cfg_dict.pop(legacy, None)
     known = {f.name for f in dataclasses.fields(SparseAutoencoderConfig)}
     cfg = SparseAutoencoderConfig(**{k: v for k, v in cfg_dict.items() if k in known})
     model = SparseAutoencoder(cfg)

@@ -15,6 +15,8 @@ is read once); every other parameter is passed to the stock torch implementation
 
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import Tensor
 
@@ -56,10 +58,18 @@ def clip_grad_norm_(parameters, max_norm, norm_type: float = 2.0, error_if_nonfi
                                       foreach=foreach)
     eng = sae.engine
     eng.grad_sumsq(local=sae._dp_world == 1)
-    sae._pending_clip = float(max_norm)
     total = eng.sumsq.sqrt().reshape(())
     if error_if_nonfinite and not bool(torch.isfinite(total)):
         raise RuntimeError("The total norm for gradients from `parameters` is non-finite, so it cannot be clipped.")
+    opt = sae._fused_adam() if sae._fused_adam is not None else None
+    if opt is None:
+        # the update will NOT go through saev_b200_adam_step (cfg.optim="muon", train.py:296-306, or any stock
+        # optimizer): scale the gradient bucket now, exactly as torch's clip_grad_norm_ does
+        coef = torch.clamp(float(max_norm) / (total + 1e-6), max=1.0)
+        eng.grads.mul_(coef)
+        sae._pending_clip = None
+    else:
+        sae._pending_clip = float(max_norm)
     return total
 
 
@@ -71,6 +81,13 @@ class FusedAdam(_TorchAdam):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **kw):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, **kw)
+        # a group holding exactly the four parameters of one SparseAutoencoder will be stepped by the fused kernel:
+        # tell the module, so that clip_grad_norm_ may defer the clip scale to it
+        for group in self.param_groups:
+            ps = group["params"]
+            sae = _owner(ps[0]) if len(ps) == 4 else None
+            if sae is not None and all(_owner(p) is sae for p in ps) and len({id(p) for p in ps}) == 4:
+                sae._fused_adam = weakref.ref(self)
 
     @torch.no_grad()
     def step(self, closure=None):

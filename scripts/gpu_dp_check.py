@@ -63,7 +63,7 @@ for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None
     if max(errs.values()) > 2e-5 or sh > 1e-6 or eng.unsafe_rows() != 0:
         ok = False
     if rank == 0:
-        print(f"sharded={sharded}: param rel-L2 vs single-GPU {errs}, bf16 operand {sh:.2e}, n_dead(last)={ref_losses[-1]['n_dead']}")
+        print(f"sharded={sharded}: param rel-L2 vs single-GPU {errs}, fp16 operand {sh:.2e}, n_dead(last)={ref_losses[-1]['n_dead']}")
 # ---- the drop-in surface under data parallelism: saev_b200.nn objective + optim shims, `sae.data_parallel()` ----
 from saev_b200 import nn as bnn, optim as boptim
 

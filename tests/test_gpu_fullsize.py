@@ -1,0 +1,146 @@
+"""Parity at the shapes BASELINE.json quotes (run with `-m gpu`).
+
+  * configs[1] at FULL size (d_model 768, d_sae 32 768, K 32, batch 4096, AuxK k_aux 512 live) and configs[2] dims
+    (d_model 1024, d_sae 65 536, K 32) at a batch the CPU oracle finishes in seconds: every loss term, n_dead, the
+    four un-clipped gradients, the fp64 gradient norm and the parameters after the steps against oracle/sae_oracle.py
+    (pinned to the live reference by tests/test_oracle_golden.py), tolerance 2e-5 relative (north-star bar: 1e-4).
+  * the selected top-k sets at the FULL configs[2] size (16 384 x 65 536) against an exact fp64 evaluation.
+  * the top-k screen under adversarial inputs: outlier coordinates of 30 and 100 rms, exact duplicates in the dictionary
+    (mass ties), all-zero rows; and the exact repair path forced on every row.
+  * data-parallel parity (N ranks x B/N rows == 1 rank x B rows) under torchrun when the box has >= 2 GPUs.
+"""
+import os
+import pathlib
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.test_gpu_golden import _midsize_run
+
+pytestmark = pytest.mark.gpu
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def test_c2_full_shape_matches_oracle(monkeypatch):
+    """BASELINE.json configs[1]: ViT-B/16 shape, full batch, MSE + AuxK(k_aux=512) with dead latents from step 2."""
+    _midsize_run("topk", 768, 32768, 32, 4096, "auto", monkeypatch, k_aux=512, n_steps=3, rank=48)
+
+
+def test_c3_dims_match_oracle(monkeypatch):
+    """BASELINE.json configs[2] dims (256 dictionary tiles, several candidate lists per row) at batch 2048."""
+    _midsize_run("topk", 1024, 65536, 32, 2048, "auto", monkeypatch, k_aux=512, n_steps=3, rank=64)
+
+
+def _exact_topk_check(eng, x, K, chunk=2048):
+    """(rows whose index set differs from the fp64 top-k, max |value - fp64 value|, max fp64 gap at a differing row)."""
+    B = x.shape[0]
+    bad, worst, worst_gap = 0, 0.0, 0.0
+    for r0 in range(0, B, chunk):
+        xs = x[r0:r0 + chunk]
+        h = xs.double() @ eng.W_enc_t.double().t() + eng.b_enc.double()
+        hv, hi = h.topk(K, dim=1)
+        oi = eng.topk_idx[r0:r0 + chunk].long()
+        ov = eng.topk_val[r0:r0 + chunk].double()
+        assert int((oi < 0).sum()) == 0
+        so, _ = oi.sort(dim=1)
+        sr, _ = hi.sort(dim=1)
+        rows_bad = (so != sr).any(dim=1)
+        bad += int(rows_bad.sum())
+        worst = max(worst, float((h.gather(1, oi) - ov).abs().max()))
+        if bool(rows_bad.any()):
+            # a differing row is only acceptable as an fp32-level tie: our k-th value vs the exact k-th value
+            ours_min = h.gather(1, oi).min(dim=1).values
+            worst_gap = max(worst_gap, float((hv[:, -1] - ours_min)[rows_bad].abs().max()))
+    return bad, worst, worst_gap
+
+
+def test_full_c3_topk_sets_match_fp64():
+    """16 384 x 65 536, K = 32: the screen + re-score selection against torch fp64, eval and training forward."""
+    from saev_b200.engine import Engine, EngineConfig
+
+    D, S, K, B = 1024, 65536, 32, 16384
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, max_batch=B, aux=False))
+    eng.init_params(seed=0)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    eng.b_enc.copy_(0.02 * torch.randn(S, device="cuda", generator=g))
+    eng.sync_weights()
+    for training in (False, True):
+        x = torch.randn(B, D, device="cuda", generator=g)
+        eng.forward(x, training=training)
+        bad, worst, gap = _exact_topk_check(eng, x, K)
+        scale = float(eng.topk_val[:B].abs().max())
+        assert worst <= 2e-6 * scale, worst          # fp32 re-score vs fp64
+        assert gap <= 4e-6 * scale, (bad, gap)       # index sets may differ only at fp32-level ties
+        assert bad <= 2, bad
+    st = eng.screen_stats()
+    assert st["unrepaired"] == 0, st
+    assert st["unsafe_rows"] == 0, st  # Gaussian inputs never overflow a candidate list
+
+
+@pytest.mark.parametrize("case", ["outlier30", "outlier100", "dup_atoms", "zero_rows", "tiny_rows", "forced"])
+def test_screen_is_exact_under_adversarial_inputs(case, monkeypatch):
+    """1024 x 16 384 dictionary, K = 32: the selection must equal the fp64 top-k whatever the inputs do to the screen.
+    outlier*: two coordinates scaled to 30 / 100 rms (massive activations of ViT register / CLS tokens) -- the margin
+    grows with ||x||_2 only, no list may overflow; dup_atoms: 300 exact copies of one atom (mass ties: lists overflow,
+    the exact path must take the rows); zero_rows: all-zero inputs (every column ties at b_enc); tiny_rows: rows of
+    magnitude 1e-30 (the power-of-two row scaling); forced: SAEV_B200_FORCE_REPAIR=1 sends every row down the exact
+    path."""
+    from saev_b200.engine import Engine, EngineConfig
+
+    if case == "forced":
+        monkeypatch.setenv("SAEV_B200_FORCE_REPAIR", "1")
+    D, S, K, B = 1024, 16384, 32, 1024
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, max_batch=B, aux=False))
+    eng.init_params(seed=3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    eng.b_enc.copy_(0.01 * torch.randn(S, device="cuda", generator=g))
+    x = torch.randn(B, D, device="cuda", generator=g)
+    if case.startswith("outlier"):
+        x[:, 17] *= float(case[7:])
+        x[:, 600] *= -float(case[7:])
+    elif case == "dup_atoms":
+        eng.W_enc_t[1000:1300] = eng.W_enc_t[1000]
+        eng.b_enc[1000:1300] = eng.b_enc[1000]
+        x = x + 3.0 * eng.W_enc_t[1000]  # the duplicated atom is among the strongest of every row
+    elif case == "zero_rows":
+        x[::4] = 0.0
+    elif case == "tiny_rows":
+        x[::3] *= 1e-30
+    eng.sync_weights()
+    eng.forward(x, training=True)
+    st = eng.screen_stats()
+    assert st["unrepaired"] == 0, st
+    if case in ("outlier30", "outlier100", "tiny_rows"):
+        assert st["unsafe_rows"] == 0, st
+    if case == "forced":
+        assert st["repaired"] == B, st
+    if case == "dup_atoms":
+        assert st["repaired"] > 0, st
+    # exactness: values at our indices are the fp32 pre-activations, and the multiset of selected VALUES equals the
+    # fp64 top-k values (index sets are ambiguous under exact ties by construction)
+    h = x.double() @ eng.W_enc_t.double().t() + eng.b_enc.double()
+    hv, _ = h.topk(K, dim=1)
+    oi = eng.topk_idx[:B].long()
+    assert int((oi < 0).sum()) == 0
+    assert int((oi.sort(dim=1).values.diff(dim=1) == 0).sum()) == 0, "a column was selected twice"
+    ov, _ = h.gather(1, oi).sort(dim=1, descending=True)
+    scale = h.abs().max(dim=1, keepdim=True).values.clamp(min=1e-300)
+    assert float(((ov - hv).abs() / scale).max()) <= 4e-6
+    assert float(((eng.topk_val[:B].double() - h.gather(1, oi)).abs() / scale).max()) <= 2e-6
+    # the per-atom counts the backward uses agree with the selection
+    eng.backward(x)
+    eng.grad_sumsq()
+    assert torch.isfinite(eng.sumsq).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs on one node")
+def test_data_parallel_matches_single_gpu():
+    """scripts/gpu_dp_check.py under torchrun: N ranks x (B/N) rows through every exchange mode of
+    DataParallelTrainer and through the nn / optim drop-in surface == one engine on the full batch."""
+    n = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "scripts" / "gpu_dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    assert out.returncode == 0 and "DP CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -132,7 +132,7 @@ def test_dense_features_with_two_pass_decode(monkeypatch):
     _midsize_run("topk", 256, 4096, 32, 1400, "auto", monkeypatch, dense_atoms=(5, 2049, 4095))
 
 
-def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=()):
+def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=64, n_steps=4, rank=24):
     """Four steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile).
 
     The library has two AuxK implementations (tensor-core split contractions / fp32 tiles) and picks one per step from
@@ -152,20 +152,20 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=()):
     for j in dense_atoms:
         b_enc[j] = 4.0
     l1 = 4e-4 if act == "relu" else 0.0
-    ocfg = orc.OracleConfig(d_model=D, d_sae=S, activation=act, top_k=max(K, 1), l1_coeff=l1, aux=True, k_aux=64,
+    ocfg = orc.OracleConfig(d_model=D, d_sae=S, activation=act, top_k=max(K, 1), l1_coeff=l1, aux=True, k_aux=k_aux,
                             dead_threshold_tokens=2 * B, lr=1e-3, n_lr_warmup=2, n_steps=10)
     st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
-    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation=act, aux=True, k_aux=64, l1_coeff=l1,
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation=act, aux=True, k_aux=k_aux, l1_coeff=l1,
                               dead_threshold_tokens=2 * B, max_batch=B))
     eng.load_params(W_enc, b_enc, W_dec, b_dec)
-    basis = torch.randn(24, D, generator=g)
+    basis = torch.randn(rank, D, generator=g)
     tol = TOL_DENSE if act == "relu" else TOL
     # ReLU case: the inputs carry a large common offset (x - 0.5), i.e. every contraction cancels heavily (the fp32
     # oracle itself is only good to 4e-6 here; the two-piece split, SAEV_B200_DENSE_TERMS=3, is at 1.7e-4)
     tol_g = TOL
     lr = 0.0
-    for step in range(4):  # dead latents appear at step 2; in "auto" step 3 is the first on the tensor-core path
-        x = torch.randn(B, 24, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)
+    for step in range(n_steps):  # dead latents appear at step 2; in "auto" step 3 is the first on the tensor-core path
+        x = torch.randn(B, rank, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)
         if act == "relu":
             x = x - 0.5  # push many pre-activations negative so that latents die
         xd = x.cuda()
@@ -197,7 +197,9 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=()):
     for name, p in (("W_enc", eng.W_enc_t.t()), ("b_enc", eng.b_enc), ("W_dec", eng.W_dec), ("b_dec", eng.b_dec)):
         assert rel_l2(p.cpu(), getattr(st, name)) < tol, name
     if act == "topk":
-        assert eng.unsafe_rows() == 0
+        st_ = eng.screen_stats()
+        assert st_["unrepaired"] == 0 and st_["unsafe_rows"] == 0, st_
+    return eng
 
 
 @pytest.mark.parametrize("nterms,tol", [(1, 6e-3), (3, 4e-5), (6, 8e-6)])

@@ -1,9 +1,11 @@
-"""Opt-in end-to-end drop-in test: the UNMODIFIED saev training entry point (`saev.framework.train.worker_fn`,
-train.py:204-240 -> train() :243-508 -> evaluate() :510-618) on a B200 with `saev_b200.install()` active.
+"""End-to-end drop-in tests: the UNMODIFIED saev training entry point (`saev.framework.train.worker_fn`,
+train.py:204-240 -> train() :243-508 -> evaluate() :510-618, and make_saes :109-189) on a B200 with
+`saev_b200.install()` active.
 
-The reference checkout does not exist on the GPU box, so this only runs when `SAEV_B200_REF_SRC` names a directory
-that contains the `saev` package (`scripts/stage_reference.sh` stages it under the git-ignored `baseline/_ref/`);
-otherwise it is skipped.  Import stubs for the three packages the image lacks come from `oracle/ref_stubs/`.
+The reference checkout does not exist on the GPU box; `__graft_entry__.build()` stages its (pure-Python) package,
+unmodified, under the git-ignored `oracle/_ref/` which travels with the snapshot (oracle/ref_harness.py;
+`SAEV_B200_REF_SRC` overrides the location).  Import stubs for the three packages the image lacks come from
+`oracle/ref_stubs/`.
 """
 
 import base64
@@ -16,15 +18,19 @@ import tempfile
 import pytest
 import torch
 
+from oracle import ref_harness
+
 pytestmark = pytest.mark.gpu
 
-REF = os.environ.get("SAEV_B200_REF_SRC", "")
+REF = ref_harness.reference_src()
+needs_ref = pytest.mark.skipif(REF is None, reason="reference package not staged (run __graft_entry__.build() where "
+                                                   "/root/reference exists)")
 
 
-@pytest.mark.skipif(not (REF and pathlib.Path(REF, "saev").is_dir()), reason="SAEV_B200_REF_SRC not staged")
+@needs_ref
 def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
     stubs = str(pathlib.Path(__file__).resolve().parent.parent / "oracle" / "ref_stubs")
-    sys.path[:0] = [stubs, str(pathlib.Path(REF).resolve())]
+    sys.path[:0] = [stubs, str(REF)]
     try:
         import saev.data
         import saev.data.datasets
@@ -91,5 +97,57 @@ def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
             ref_out = sae(x)
             nmse = float(((ref_out.x_hats[:, -1, :] - x) ** 2).sum() / ((x - x.mean(0)) ** 2).sum())
             assert nmse == pytest.approx(m.normalized_mse, rel=1e-3)
+    finally:
+        del sys.path[:2]
+
+
+@needs_ref
+def test_unmodified_make_saes_datapoint_init_over_many_batches(tmp_path):
+    """saev's DEFAULT configuration (reinit_blend = 0.8) runs make_saes' datapoint initialisation (train.py:141-185): it
+    appends >= 4 loader batches to a list and only then concatenates them.  With blend = 1 every decoder row must be
+    a DISTINCT, normalised, mean-centred data row -- rows repeat if batches alias recycled loader buffers."""
+    stubs = str(pathlib.Path(__file__).resolve().parent.parent / "oracle" / "ref_stubs")
+    sys.path[:0] = [stubs, str(REF)]
+    try:
+        import numpy as np
+        import saev.data
+        import saev.framework.train as train
+        import saev.nn
+        from saev.nn.modeling import TopK
+
+        import saev_b200
+        from saev_b200 import data as bdata
+
+        n_examples, T, D, S = 96, 16, 32, 1024
+        md = bdata.Metadata(family="fake-clip", ckpt="synthetic", layers=(0,), content_tokens_per_example=T,
+                            cls_token=False, d_model=D, n_examples=n_examples, max_tokens_per_shard=20 * T, data="",
+                            dataset="fake")
+        root = tmp_path / "saev" / "shards"
+        root.mkdir(parents=True)
+        md.dump(root)
+        acts = torch.randn(n_examples, 1, T, D, generator=torch.Generator().manual_seed(4)) + 0.5
+        with bdata.ShardWriter(root, md) as w:
+            w.write_batch(acts, 0)
+        saev_b200.install()
+        try:
+            dl = saev.data.ShuffledDataLoader(saev.data.ShuffledConfig(shards=root / md.hash, layer=0, batch_size=128,
+                                                                       buffer_size=2, n_threads=2))
+            assert type(dl).__module__.startswith("saev_b200")
+            cfgs = [(saev.nn.SparseAutoencoderConfig(d_model=D, d_sae=S, activation=TopK(top_k=8), reinit_blend=1.0),
+                     saev.nn.objectives.Matryoshka(n_prefixes=1))]
+            saes, objectives, pgs = train.make_saes(cfgs, dl)  # 1536 rows = 12 batches of 128, all held
+            dl.shutdown()
+        finally:
+            saev_b200.uninstall()
+        (sae,) = saes
+        rows = acts[:, 0].reshape(-1, D)
+        cand = rows - rows.mean(0, keepdim=True)
+        cand = (cand / cand.norm(dim=1, keepdim=True)).double()
+        W = sae.W_dec.detach().cpu().double()
+        cos = W @ cand.t()
+        best, who = cos.max(dim=1)
+        assert float(best.min()) > 1 - 1e-5, "a decoder row is not one of the (centred, normalised) data rows"
+        assert len(set(who.tolist())) == S, "datapoint init picked the same data row more than once"
+        assert torch.allclose(sae.W_enc.detach().cpu().t().double(), W)
     finally:
         del sys.path[:2]

@@ -419,3 +419,102 @@ def test_evaluate_loop_against_the_oracle_with_a_stand_in_engine():
     assert torch.allclose(m.mean_values[fired], ref["mean_values"][fired], rtol=1e-5)
     with pytest.raises(ValueError):
         ev.evaluate([cfg, types.SimpleNamespace(val_data="other", n_val=1)], [SAE()] * 2, [Objective()] * 2, loader_cls=Loader)
+
+
+# ---- shard writer side (saev shards.py:112-135, 372-527) ----------------------------------------
+def test_shard_writer_reproduces_the_reference_writers_directory(tmp_path):
+    """The golden shard directory was written by saev's own Metadata.dump + ShardWriter (oracle/gen_golden_host.py)
+    from tests/golden/shards_acts.npy with three write_batch calls; ours must produce the same directory name (the
+    metadata hash), the same shards.json and byte-identical acts%06d.bin files."""
+    md = data.Metadata.load(SHARDS)
+    assert md.hash == SHARDS.name
+    acts = torch.from_numpy(np.load(GOLDEN / "shards_acts.npy"))
+    root = tmp_path / "saev" / "shards"
+    root.mkdir(parents=True)
+    md.dump(root)
+    with data.ShardWriter(root, md) as w:
+        w.write_batch(acts[:3], 0)
+        w.write_batch(acts[3:9], 3)
+        w.write_batch(acts[9:], 9)
+    out = root / md.hash
+    assert json.loads((out / "metadata.json").read_text()) == json.loads((SHARDS / "metadata.json").read_text())
+    assert json.loads((out / "shards.json").read_text()) == json.loads((SHARDS / "shards.json").read_text())
+    bins = sorted(p.name for p in SHARDS.glob("acts*.bin"))
+    assert sorted(p.name for p in out.glob("acts*.bin")) == bins
+    for name in bins:
+        assert (out / name).read_bytes() == (SHARDS / name).read_bytes(), name
+
+
+def test_shard_writer_rolls_over_like_the_reference_when_a_batch_fills_a_shard_exactly(tmp_path):
+    """shards.py:434 uses `>=`: data that exactly fills the last shard leaves a trailing all-zero shard with
+    n_examples 0; readers skip it through shards.json."""
+    md = data.Metadata(family="fake-clip", ckpt="synthetic", layers=(0,), content_tokens_per_example=4, cls_token=False,
+                       d_model=8, n_examples=6, max_tokens_per_shard=3 * 4, data="", dataset="fake")
+    assert md.examples_per_shard == 3
+    root = tmp_path / "saev" / "shards"
+    root.mkdir(parents=True)
+    md.dump(root)
+    acts = torch.randn(6, 1, 4, 8)
+    with data.ShardWriter(root, md) as w:
+        w.write_batch(acts, 0)
+    info = json.loads((root / md.hash / "shards.json").read_text())
+    assert [e["n_examples"] for e in info] == [3, 3, 0]
+    got = np.fromfile(root / md.hash / "acts000001.bin", dtype=np.float32).reshape(md.shard_shape)
+    assert np.array_equal(got, acts[3:].numpy())
+
+
+# ---- checkpoints interoperate with the reference (modeling.py:448-658) ---------------------------------------------
+def _ref_modeling():
+    from oracle import ref_harness
+
+    try:
+        ref_harness.import_reference()
+    except ImportError:
+        pytest.skip("reference package not available (neither /root/reference nor oracle/_ref)")
+    import saev.nn.modeling as M
+
+    return M
+
+
+@pytest.mark.parametrize("act", ["topk", "relu", "batchtopk"])
+def test_checkpoint_header_is_the_references_schema_5(act, tmp_path):
+    from saev_b200 import nn as bnn
+
+    M = _ref_modeling()
+    mk = {"topk": lambda m: m.TopK(top_k=8, aux=m.AuxK(k_aux=64, alpha=0.125)),
+          "relu": lambda m: m.Relu(sparsity=m.L1Sparsity(coeff=3e-4), aux=m.NoAux()),
+          "batchtopk": lambda m: m.BatchTopK(top_k=4)}[act]
+    ours = bnn.SparseAutoencoder(bnn.SparseAutoencoderConfig(d_model=16, d_sae=64, activation=mk(bnn), reinit_blend=0.0))
+    theirs = M.SparseAutoencoder(M.SparseAutoencoderConfig(d_model=16, d_sae=64, activation=mk(M), reinit_blend=0.0))
+    # 1. same header payload for the activation as the reference's serializer produces
+    assert bnn._serialize_dataclass(ours.cfg.activation) == M._serialize_dataclass(theirs.cfg.activation)
+    if act == "batchtopk":
+        return  # (no CUDA path and no `activation.threshold` buffer here: only the header payload is mirrored)
+    # 2. ours -> reference loader
+    bnn.dump(tmp_path / "ours.pt", ours)
+    back = M.load(tmp_path / "ours.pt")
+    assert type(back.cfg.activation).__name__ == type(theirs.cfg.activation).__name__
+    assert back.cfg.activation == mk(M)
+    for k, v in ours.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v), k
+    # 3. reference -> our loader
+    M.dump(tmp_path / "theirs.pt", theirs)
+    mine = bnn.load(tmp_path / "theirs.pt")
+    assert mine.cfg.activation == mk(bnn)
+    assert mine.cfg.d_sae == 64 and mine.cfg.reinit_blend == 0.0
+    for k, v in theirs.state_dict().items():
+        assert torch.equal(mine.state_dict()[k], v), k
+
+
+def test_fused_adam_registers_only_full_sae_groups():
+    """clip_grad_norm_ may defer the clip scale to the optimizer only when a FusedAdam owns exactly the four parameters
+    of the SAE (train.py:292-306: cfg.optim == "muon" hands the matrices to torch.optim.Muon and only the biases to
+    Adam -- then the clip has to be applied to .grad at once)."""
+    from saev_b200 import nn as bnn
+
+    cfg = bnn.SparseAutoencoderConfig(d_model=8, d_sae=16, activation=bnn.TopK(top_k=2), reinit_blend=0.0)
+    a, b = bnn.SparseAutoencoder(cfg), bnn.SparseAutoencoder(cfg)
+    opt_a = optim.FusedAdam([{"params": a.parameters(), "lr": 0.0}])
+    assert a._fused_adam is not None and a._fused_adam() is opt_a
+    optim.FusedAdam([{"params": [b.b_enc, b.b_dec], "lr": 0.0}])  # the Muon split: biases only
+    assert b._fused_adam is None

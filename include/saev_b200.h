@@ -125,7 +125,9 @@ int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace);
 /* Screen diagnostics, cumulative since the last saev_b200_sync_weights (device pointer to uint32 counters):
  *   [0] rows the tensor-core screen could not certify (candidate list overflow, observed error above the bound);
  *       every one of them was re-done by the exact fp32 path inside the same forward      [2] candidates re-scored
- *   [4] candidate-list entries merged      [7] rows re-done by the exact path ( == [0] once the forward has run) */
+ *   [7] rows re-done by the exact path ( == [0] once the forward has run)      [9] candidate-list entries merged
+ *   [8] of [0]: rows whose OBSERVED screen error exceeded the deterministic bound (stays 0 unless the error model of
+ *       the tensor-core accumulation is violated; the expected cause of [0] is a candidate-list overflow) */
 uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace);
 
 /* Gradients of loss = mse + sparsity + aux for the batch of the last training forward
@@ -162,7 +164,8 @@ int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* 
  * W_enc_t / W_dec (and their Adam moments, fp16 operand rows and row-norm maximum), plus both bias vectors in full.
  * The caller reduce-scatters the two weight-gradient regions, all-reduces the bias gradients, takes the norm with
  * saev_b200_grad_sumsq_ranges over what it owns (+ an all-reduce of that scalar), and all-gathers the updated rows,
- * the fp16 operand (saev_b200_shadow_weights, [d_sae, d_model] fp16) and the row-norm maximum (MAX). */
+ * the fp16 operand (saev_b200_shadow_weights, [d_sae, d_model] fp16), the row norms (saev_b200_wnorm_rows) and the
+ * row-norm maximum (MAX). */
 int saev_b200_set_optimizer_shard(saev_b200_handle* h, int32_t row_begin, int32_t row_end);
 /* Leave `n_sms` SMs (rounded up to pairs) out of the top-k screen's persistent grid, so that NCCL kernels (the
  * all-gather of the fp32 rows a sharded optimizer step leaves behind) can run BESIDE the screen of the next step;
@@ -172,7 +175,12 @@ int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, in
                                 const int64_t* host_begins, const int64_t* host_ends, float* sumsq_out,
                                 void* workspace, void* stream);
 void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace); /* fp16 [d_sae, d_model] */
+/* float[3], the dictionary-wide inputs of the screen's error bound: max_j ||W_enc_t[j]||^2, max_j |b_enc[j]|,
+ * max_j ||w_j - fp16(w_j)|| / ||w_j||.  A sharded optimizer step computes them over its rows: MAX-all-reduce. */
 float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace);
+/* float[d_sae]: max(||w_j||, ||fp16(w_j)||) (rounded up), the per-column input of the screen's error bound; a sharded optimizer
+ * step refreshes rows [row_begin, row_end) only -- all-gather it with the fp16 operand. */
+float* saev_b200_wnorm_rows(const saev_b200_handle* h, void* workspace);
 
 /* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + fp16 operand refresh.
  *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)
@@ -239,6 +247,12 @@ int saev_b200_log_metrics(saev_b200_handle* h, const float* x, const float* resi
 int saev_b200_eval_accumulate(saev_b200_handle* h, const float* x, const float* resid, int32_t B,
                               const int32_t* topk_idx, const float* topk_val, const float* losses, double* acc,
                               float* n_fired, float* values, void* workspace, void* stream);
+
+/* Test hook: AuxK's selection of the last training forward (valid until the next forward).  mask[b * ld + i] != 0 iff
+ * the i-th entry of dead_list (ascending atom ids, *n_dead of them) is among row b's top-k_aux dead latents
+ * (modeling.py:93-97).  All four outputs are device pointers into the workspace. */
+int saev_b200_aux_selection(const saev_b200_handle* h, void* workspace, const uint8_t** mask, int64_t* ld,
+                            const int32_t** dead_list, const int32_t** n_dead);
 
 /* Test hook for the tensor-core contraction alone: out[M, N] = A[M, K] . Bt[N, K]^T + bias[N], computed
  * from bf16 copies of the operands (nterms = 1), the 3-term two-piece split (nterms = 3, ~2^-16 of sum |a b|) or the

@@ -168,11 +168,34 @@ def mean_squared_err(x_hat: Tensor, x: Tensor) -> Tensor:
     return (d * d * upper * upper).mean()
 
 
-def auxk(h: Tensor, r: Tensor, dead: Tensor, W_dec: Tensor, b_dec: Tensor, k_aux: int, alpha: float):
+def adopt_selection(h: Tensor, own_idx: Tensor, given_idx: Tensor, tie_tol: float = 4e-6, what: str = "top-k") -> Tensor:
+    """torch.topk breaks fp32-level ties between the k-th and (k+1)-th largest value of a row in an
+    implementation-defined way; at 10^8 (row, column) pairs per batch SOME row has such a tie, and the kernels (other
+    summation order) may keep the other column -- one swapped entry is 4e-3 of ||gW_enc|| at batch 4096.  This checks
+    that `given_idx` (the kernels' selection, int64 [B, k]) differs from torch's `own_idx` in at most a handful of rows
+    and ONLY by such ties (exchanged values agree to tie_tol * max|h_row|), then returns it for the oracle to use, so
+    that everything downstream of the selection can still be compared tightly."""
+    assert given_idx.shape == own_idx.shape, (what, given_idx.shape, own_idx.shape)
+    so, sr = given_idx.sort(dim=1).values, own_idx.sort(dim=1).values
+    rows = (so != sr).any(dim=1).nonzero().flatten()
+    assert rows.numel() <= max(2, h.shape[0] // 250), f"{what}: {rows.numel()} rows differ from torch.topk"
+    for r in rows.tolist():
+        a, b = set(so[r].tolist()), set(sr[r].tolist())
+        assert len(a) == so.shape[1], f"{what}: duplicate column in row {r}"
+        only_given, only_own = sorted(a - b), sorted(b - a)
+        finite = h[r][torch.isfinite(h[r])]
+        scale = float(finite.abs().max())
+        gap = (h[r, only_given].sort().values - h[r, only_own].sort().values).abs().max()
+        assert float(gap) <= tie_tol * scale, (what, r, only_given, only_own, float(gap), scale)
+    return given_idx
+
+
+def auxk(h: Tensor, r: Tensor, dead: Tensor, W_dec: Tensor, b_dec: Tensor, k_aux: int, alpha: float,
+         aux_idx: Tensor | None = None):
     """modeling.py:89-103.  e = (x - x_hat).detach() = -r; masked = h.masked_fill(~dead, -inf);
     k_use = min(k_aux, n_dead); top_i = masked.topk(k_use); f_aux = scatter(h at top_i);
     x_aux = decode(f_aux) (b_dec IS added); aux = alpha * mean((x_aux - e)^2).
-    Returns (aux scalar, f_aux[B,S] or None, r_aux[B,D] or None)."""
+    Returns (aux scalar, f_aux[B,S] or None, r_aux[B,D] or None).  `aux_idx`: see adopt_selection()."""
     n_dead = int(dead.sum())
     k_use = min(k_aux, n_dead)
     if k_use == 0:
@@ -180,6 +203,8 @@ def auxk(h: Tensor, r: Tensor, dead: Tensor, W_dec: Tensor, b_dec: Tensor, k_aux
     e = -r
     masked = h.masked_fill(~dead, float("-inf"))
     _, top_i = masked.topk(k_use, dim=-1)
+    if aux_idx is not None:
+        top_i = adopt_selection(masked, top_i, aux_idx, what="AuxK top-k_aux")
     f_aux = torch.zeros_like(h)
     f_aux.scatter_(-1, top_i, h.gather(-1, top_i))
     x_aux = decode(f_aux, W_dec, b_dec)
@@ -213,11 +238,20 @@ class ForwardOut:
         return self.mse + self.sparsity + self.aux
 
 
-def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True, prefixes=None) -> ForwardOut:
+def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True, prefixes=None,
+            topk_idx: Tensor | None = None, aux_idx=None) -> ForwardOut:
     """objectives.py:101-156.  `prefixes` = the sorted cut points sample_prefixes() drew for this step (last one =
-    d_sae); None / a single cut is the Matryoshka(n_prefixes=1) case."""
+    d_sae); None / a single cut is the Matryoshka(n_prefixes=1) case.
+    `topk_idx` (int64 [B, k]) / `aux_idx` (int64 [B, k_use], or a callable returning it, evaluated only when AuxK is
+    live): the kernels' selections; adopted after adopt_selection() has verified that they differ from torch.topk's
+    only at fp32-level ties."""
     h = encode_pre(x, st.W_enc, st.b_enc)
-    if cfg.activation == "topk":
+    if cfg.activation == "topk" and topk_idx is not None:
+        _, own = torch.topk(h, min(cfg.top_k, h.shape[1]), dim=-1)
+        topk_idx = adopt_selection(h, own, topk_idx, what="top-k")
+        mask = torch.zeros_like(h).scatter(-1, topk_idx, 1.0)
+        f = mask * h
+    elif cfg.activation == "topk":
         f, mask = topk_activation(h, cfg.top_k)
     elif cfg.activation == "relu":
         f, mask = relu_activation(h)
@@ -252,7 +286,9 @@ def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True
     if training and dead is not None:
         n_dead = int(dead.sum())
         if cfg.aux:
-            aux, fa, r_aux = auxk(h, r, dead, st.W_dec, st.b_dec, cfg.k_aux, cfg.aux_alpha)
+            if callable(aux_idx):
+                aux_idx = aux_idx(n_dead)
+            aux, fa, r_aux = auxk(h, r, dead, st.W_dec, st.b_dec, cfg.k_aux, cfg.aux_alpha, aux_idx=aux_idx)
     f_aux, mask_aux = fa if fa is not None else (None, None)
     return ForwardOut(h, f, mask, x_hat, r, mse, sparsity, l0, l1, aux, n_dead, f_aux, mask_aux, r_aux, x_hats, prefixes)
 
@@ -344,12 +380,13 @@ def warmup_cosine(step: int, n_warmup: int, peak: float, n_steps: int, init: flo
     return final
 
 
-def train_step(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None) -> dict:
+def train_step(cfg: OracleConfig, st: OracleState, x: Tensor, prefixes=None, topk_idx: Tensor | None = None,
+               aux_idx=None) -> dict:
     """One iteration of train.py:332-460 (log block excluded).  Mutates `st`; returns scalars and,
-    for parity tests, the clipped gradients."""
+    for parity tests, the clipped gradients.  `topk_idx`, `aux_idx`: see forward()."""
     if cfg.normalize_w_dec:
         st.W_dec = normalize_w_dec(st.W_dec)  # train.py:334-335
-    out = forward(cfg, st, x, training=True, prefixes=prefixes)  # train.py:341
+    out = forward(cfg, st, x, training=True, prefixes=prefixes, topk_idx=topk_idx, aux_idx=aux_idx)  # train.py:341
     grads = backward(cfg, st, x, out)  # train.py:348
     if cfg.remove_parallel_grads:
         grads["W_dec"] = remove_parallel_grads(grads["W_dec"], st.W_dec)  # train.py:352

@@ -102,6 +102,7 @@ SIGNATURES = {
     "saev_b200_grad_sumsq_ranges": (C.c_int, [_p, _p, _i32, C.POINTER(_i64), C.POINTER(_i64), _p, _p, _p]),
     "saev_b200_shadow_weights": (_p, [_p, _p]),
     "saev_b200_wnorm_scalar": (_p, [_p, _p]),
+    "saev_b200_wnorm_rows": (_p, [_p, _p]),
     "saev_b200_adam_step": (
         C.c_int,
         [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _p, _p],
@@ -116,6 +117,7 @@ SIGNATURES = {
     "saev_b200_log_scratch_bytes": (C.c_size_t, [_p]),
     "saev_b200_log_metrics": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, C.c_size_t, _p, _p]),
     "saev_b200_eval_accumulate": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "saev_b200_aux_selection": (C.c_int, [_p, _p, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_p), C.POINTER(_p)]),
     "saev_b200_gemm_nt": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "saev_b200_profile_enable": (C.c_int, [_p, _i32]),
     "saev_b200_profile_read": (C.c_int, [_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

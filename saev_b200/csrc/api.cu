@@ -21,7 +21,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_scale, unsafe_list, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_dx, row_scale, unsafe_list, wnorm_rows, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
@@ -146,7 +146,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.dhT_l2 = take(third ? S * LB * 2 : 0);
   }
   if (relu) {
-    w.cand = w.tau_keys = w.cand_cnt = w.row_norm = w.row_scale = w.unsafe_list = o;
+    w.cand = w.tau_keys = w.cand_cnt = w.row_norm = w.row_dx = w.row_scale = w.unsafe_list = w.wnorm_rows = o;
   } else {
     // candidate lists of the top-k screen: rows padded to 256, `nlists` lists per row; the list count depends on the
     // batch size (how many CTA-pair ranges touch one row block)
@@ -162,8 +162,10 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.tau_keys = take((B + 255) / 256 * 256 * 4);
     w.cand_cnt = take(row_lists * 4);
     w.row_norm = take((B + 255) / 256 * 256 * 4);
+    w.row_dx = take((B + 255) / 256 * 256 * 4);
     w.row_scale = take((B + 255) / 256 * 256 * 4);
     w.unsafe_list = take(B * 4);
+    w.wnorm_rows = take(S * 4);
   }
   w.dh = take(B * K * 4);
   w.row_sse = take(B * 4);
@@ -553,7 +555,8 @@ int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const floa
   if (h->cfg.act_kind == SAEV_B200_ACT_TOPK) {  // (the dense path re-splits its operands every forward)
     if (launch_to_half(W_enc_t, at<__half>(workspace, h->ws.shadow_hi), n, s))
       return fail(h, 30, "sync_weights: fp16 copy launch failed%s");
-    if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX, s))
+    if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX, s,
+                             at<float>(workspace, h->ws.wnorm_rows), at<float>(workspace, h->ws.scalars) + SC_RHO))
       return fail(h, 30, "sync_weights: row-norm launch failed%s");
     if (launch_abs_max(b_enc, h->cfg.d_sae, at<float>(workspace, h->ws.scalars) + SC_BIAS_ABS_MAX, s))
       return fail(h, 30, "sync_weights: bias-max launch failed%s");
@@ -622,7 +625,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     float* scal_f = at<float>(workspace, w.scalars);
     if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
-      if (launch_prep_x(x, B, D, x16, at<float>(workspace, w.row_norm), at<float>(workspace, w.row_scale), s))
+      if (launch_prep_x(x, B, D, x16, at<float>(workspace, w.row_norm), at<float>(workspace, w.row_dx),
+                        at<float>(workspace, w.row_scale), s))
         return fail(h, 41, "forward: prep_x launch failed%s");
     }
 
@@ -636,8 +640,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.bias = b_enc;
     g.top_k = K;
     g.row_norm = at<float>(workspace, w.row_norm);
+    g.row_dx = at<float>(workspace, w.row_dx);
     g.row_scale = at<float>(workspace, w.row_scale);
     g.scalars = scal_f;
+    g.col_norm = at<float>(workspace, w.wnorm_rows);
     g.cand_cnt = at<int>(workspace, w.cand_cnt);
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
@@ -663,8 +669,10 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     r.cand_stride = ENCODE2_CAPG;
     r.nsplit = g.nsplit;
     r.row_norm = g.row_norm;
+    r.row_dx = g.row_dx;
     r.row_scale = g.row_scale;
     r.scalars = scal_f;
+    r.col_norm = g.col_norm;
     r.unsafe_list = at<int>(workspace, w.unsafe_list);
     r.force_unsafe = h->force_repair ? 1 : 0;
     r.x = x;
@@ -999,9 +1007,13 @@ int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, in
 void* saev_b200_shadow_weights(const saev_b200_handle* h, void* workspace) {
   return at<char>(workspace, h->ws.shadow_hi);
 }
+float* saev_b200_wnorm_rows(const saev_b200_handle* h, void* workspace) {
+  return at<float>(workspace, h->ws.wnorm_rows);
+}
 float* saev_b200_wnorm_scalar(const saev_b200_handle* h, void* workspace) {
   return at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX;
 }
+
 
 int saev_b200_grad_sumsq_local(saev_b200_handle* h, const float* gb_dec, float* sumsq_out, void* workspace,
                                void* stream) {
@@ -1044,6 +1056,8 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.shadow16 = screen ? at<__half>(workspace, h->ws.shadow_hi) : nullptr;
   a.wnorm_sq_max = screen ? at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX : nullptr;
   a.bias_abs_max = screen ? at<float>(workspace, h->ws.scalars) + SC_BIAS_ABS_MAX : nullptr;
+  a.wnorm_rows = screen ? at<float>(workspace, h->ws.wnorm_rows) : nullptr;
+  a.rho = screen ? at<float>(workspace, h->ws.scalars) + SC_RHO : nullptr;
   a.D = static_cast<int>(D);
   a.S = static_cast<int>(S);
   a.lr = lr;
@@ -1227,6 +1241,17 @@ int saev_b200_eval_accumulate(saev_b200_handle* h, const float* x, const float* 
       return fail(h, 89, "eval_accumulate: launch failed%s");
   }
   return check_cuda(h, "eval_accumulate");
+}
+
+int saev_b200_aux_selection(const saev_b200_handle* h, void* workspace, const uint8_t** mask, int64_t* ld,
+                            const int32_t** dead_list, const int32_t** n_dead) {
+  if (!h || !workspace || !mask || !ld || !dead_list || !n_dead) return fail(h, 83, "aux_selection: null argument%s");
+  if (h->cfg.aux_kind != SAEV_B200_AUX_AUXK) return fail(h, 83, "aux_selection: the handle has no AuxK%s");
+  *mask = at<uint8_t>(workspace, h->ws.mask_aux);
+  *ld = h->aux_cap;
+  *dead_list = at<int32_t>(workspace, h->ws.dead_list);
+  *n_dead = at<int32_t>(workspace, h->ws.scalars) + SC_N_DEAD;
+  return 0;
 }
 
 int saev_b200_gemm_nt(saev_b200_handle* h, const float* A, const float* Bt, const float* bias, int32_t M,

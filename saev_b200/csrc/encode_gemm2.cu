@@ -6,12 +6,14 @@
 // operands: 11 significant bits at the bf16 rate; the power-of-two row scale keeps every row inside the fp16 range
 // without rounding) and every row of the batch leaves candidate lists that PROVABLY cover its exact top-k:
 //
-//   admission rule: a column is kept iff its screen value exceeds (k-th largest screen value of the row so far)
-//   - 2 E_b, where E_b is the deterministic bound on |h~ - h| of kernels.h (screen_bound: Cauchy-Schwarz on the fp16
-//   roundings, plus the accumulation terms).  With every error <= E_b each exact top-k column has
-//   h~ >= h_k - E_b >= (h~)_k - 2 E_b, i.e. is kept.  `rescore_topk_kernel` (sparse_kernels.cu) recomputes the
-//   candidates in fp32 from the fp32 master weights, picks the final top-k, and hands rows whose lists overflowed
-//   (or whose observed error contradicts the bound) to the exact repair path.
+//   admission rule: with E_bj = c_j P_b + Q_b the deterministic bound on |h~_bj - h_bj| of kernels.h
+//   (screen_bound: Cauchy-Schwarz on the fp16 roundings, plus the accumulation terms), every column has the interval
+//   [l_j, u_j] = [h~_j - E_bj, h~_j + E_bj] around its exact value.  L = the k-th largest LOWER bound seen so far in
+//   the row is a lower bound of the exact k-th largest value, so a column whose UPPER bound is below L can never be
+//   in the exact top-k; everything else is kept:  admit iff  h~_j + c_j P_b > L - Q_b.  The lists store
+//   (l_j, column).  `rescore_topk_kernel` (sparse_kernels.cu) recomputes the candidates in fp32 from the fp32 master
+//   weights, picks the final top-k, and hands rows whose lists overflowed (or whose observed error contradicts the
+//   bound) to the exact repair path.
 //
 // Organisation (profiles/r01_encode_gemm_full.md has the measurements that led here):
 //
@@ -58,8 +60,9 @@ constexpr int HALF = BN / 2;   // columns per epilogue warp per tile
 constexpr int CAPG = ENCODE2_CAPG;             // entries per candidate list
 constexpr int TRIGGER_MAX = CAPG - HALF;        // a list above this could not absorb a whole further tile
 
-constexpr size_t OFF_BIAS = static_cast<size_t>(STAGES) * STAGE_BYTES;            // [8 warps][2 acc stages][128] f32
-constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * ACC * HALF * 4;  // [2 halves][128 rows] f32
+constexpr size_t OFF_BIAS = static_cast<size_t>(STAGES) * STAGE_BYTES;            // [8 warps][2 acc stages][2][128] f32:
+                                                                                  // bias slice, then column-norm slice
+constexpr size_t OFF_TAU = OFF_BIAS + static_cast<size_t>(EPI_WARPS) * ACC * 2 * HALF * 4;  // [2 halves][128 rows] f32
 constexpr size_t OFF_HIST = OFF_TAU + 2 * BM * 4;                                    // [8 warps][256] i32
 constexpr size_t OFF_BARS = OFF_HIST + static_cast<size_t>(EPI_WARPS) * 256 * 4;
 constexpr size_t SMEM_TOTAL = OFF_BARS + (2 * STAGES + 2 * ACC) * 8 + 16 + 1024;
@@ -267,8 +270,10 @@ struct Params {
   int trigger;          // compact a list once it holds more than this many entries (<= TRIGGER_MAX)
   const float* bias;
   const float* row_norm;   // [M] ||x_b||_2
+  const float* row_dx;     // [M] ||2^e_b x16_b - x_b||_2
   const float* row_scale;  // [M] 2^e_b (the screen value is acc * 2^e_b + bias)
   const float* scalars;    // workspace scalar block: SC_WNORM_SQ_MAX, SC_BIAS_ABS_MAX
+  const float* col_norm;   // [N] ||w_j||_2 (rounded up)
   int D;                   // contraction length (for the error bound)
   int2* cand;
   int* cand_cnt;
@@ -384,7 +389,8 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row_local = q * 32 + lane;
     float* my_tau_s = tau_s + half * BM + row_local;
     const float* other_tau_s = tau_s + (half ^ 1) * BM + row_local;
-    const ScreenBound sbd = screen_bound(p.D, sqrtf(p.scalars[SC_WNORM_SQ_MAX]), p.scalars[SC_BIAS_ABS_MAX]);
+    const ScreenBound sbd = screen_bound(p.D, p.scalars[SC_RHO], p.scalars[SC_BIAS_ABS_MAX]);
+    const float wn_max = sqrtf(p.scalars[SC_WNORM_SQ_MAX]) * 1.00001f;
     int* hist_w = reinterpret_cast<int*>(smem + OFF_HIST) + w * 256;
     long long tc = 0;
     for (int uj = 0; uj < n_units; ++uj) {
@@ -399,7 +405,13 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool live = row < p.M;
       float tau = live ? -INFINITY : INFINITY;
       const float rs = live ? p.row_scale[row] : 1.f;
-      const float margin = live ? 2.f * (p.row_norm[row] * sbd.A + rs * sbd.Bc + sbd.C) : 0.f;
+      const float Pb = live ? screen_P(sbd, p.row_norm[row], p.row_dx[row]) : 0.f;  // E_bj = c_j Pb + Qb
+      const float Qb = screen_Q(sbd);
+      const float neg2P = -2.f * Pb;
+      // list maintenance works in l-space (stored lower bounds) with the widest band any column can have; the
+      // admission threshold `tau` lives in t-space (t_j = h~_j + ||w_j|| Pb):  tau = L - Qb = thr_l + shift
+      const float margin = 2.f * (wn_max * Pb + Qb);
+      const float shift = margin - Qb;
       int2* wp = my_buf;  // append cursor (a running pointer keeps the per-hit address arithmetic to one add)
       bool overflowed = false;
       *my_tau_s = -INFINITY;
@@ -410,16 +422,22 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int as = static_cast<int>(tc % ACC);
         const uint32_t aphase = static_cast<uint32_t>(tc / ACC) & 1u;
         const int n0 = n * BN + half * HALF;
-        float* bs = bias_s + (w * ACC + as) * HALF;
-        {  // warp-private bias slice; columns past the end get -inf so that they can never be admitted
+        float* bs = bias_s + (w * ACC + as) * 2 * HALF;
+        float* ws = bs + HALF;
+        {  // warp-private bias / column-norm slices; columns past the end get -inf so that they can never be admitted
           if (lane * 4 < HALF) {
-            float4 bv;
+            float4 bv, wv;
             const int c = n0 + lane * 4;
             bv.x = (c + 0 < p.N) ? __ldg(p.bias + c + 0) : -INFINITY;
             bv.y = (c + 1 < p.N) ? __ldg(p.bias + c + 1) : -INFINITY;
             bv.z = (c + 2 < p.N) ? __ldg(p.bias + c + 2) : -INFINITY;
             bv.w = (c + 3 < p.N) ? __ldg(p.bias + c + 3) : -INFINITY;
+            wv.x = (c + 0 < p.N) ? __ldg(p.col_norm + c + 0) : 0.f;
+            wv.y = (c + 1 < p.N) ? __ldg(p.col_norm + c + 1) : 0.f;
+            wv.z = (c + 2 < p.N) ? __ldg(p.col_norm + c + 2) : 0.f;
+            wv.w = (c + 3 < p.N) ? __ldg(p.col_norm + c + 3) : 0.f;
             *reinterpret_cast<float4*>(bs + lane * 4) = bv;
+            *reinterpret_cast<float4*>(ws + lane * 4) = wv;
           }
         }
         // thresholds other warps / other CTA pairs have already proven for this row (its other column ranges)
@@ -435,12 +453,13 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int col0 = n0 + c * CHUNK;
           float v[CHUNK];
 #pragma unroll
-          for (int i = 0; i < CHUNK; i += 4) {
+          for (int i = 0; i < CHUNK; i += 4) {  // v = t_j = h~_j + ||w_j|| Pb
             const float4 b4 = *reinterpret_cast<const float4*>(bs + c * CHUNK + i);
-            v[i] = fmaf(__uint_as_float(a[i]), rs, b4.x);
-            v[i + 1] = fmaf(__uint_as_float(a[i + 1]), rs, b4.y);
-            v[i + 2] = fmaf(__uint_as_float(a[i + 2]), rs, b4.z);
-            v[i + 3] = fmaf(__uint_as_float(a[i + 3]), rs, b4.w);
+            const float4 w4 = *reinterpret_cast<const float4*>(ws + c * CHUNK + i);
+            v[i] = fmaf(w4.x, Pb, fmaf(__uint_as_float(a[i]), rs, b4.x));
+            v[i + 1] = fmaf(w4.y, Pb, fmaf(__uint_as_float(a[i + 1]), rs, b4.y));
+            v[i + 2] = fmaf(w4.z, Pb, fmaf(__uint_as_float(a[i + 2]), rs, b4.z));
+            v[i + 3] = fmaf(w4.w, Pb, fmaf(__uint_as_float(a[i + 3]), rs, b4.w));
           }
           float gm[4];
 #pragma unroll
@@ -454,8 +473,9 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int i = 0; i < 4; ++i) {
                   const bool hit = v[4 * g + i] > tau;
                   if (__any_sync(FULL, hit)) {  // warp-uniform: usually a single lane of a single column
-                    if (hit) {
-                      *wp = make_int2(__float_as_int(v[4 * g + i]), col0 + 4 * g + i);
+                    if (hit) {  // store the lower bound l_j = t_j - 2 ||w_j|| Pb - Qb
+                      const float lj = fmaf(neg2P, ws[c * CHUNK + 4 * g + i], v[4 * g + i]) - Qb;
+                      *wp = make_int2(__float_as_int(lj), col0 + 4 * g + i);
                       ++wp;
                     }
                   }
@@ -490,13 +510,13 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           need &= need - 1;
           const int nn = __shfl_sync(FULL, cnt, l);
           const float mg = __shfl_sync(FULL, margin, l);
-          const float fl = __shfl_sync(FULL, tau, l);
+          const float fl = __shfl_sync(FULL, tau - shift, l);
           int n_out;
           bool ovf;
           const float thr = compact_list(warp_buf + l * lane_stride, nn, p.top_k, mg, fl, lane, hist_w, n_out, ovf);
           if (lane == l) {
             wp = my_buf + n_out;
-            tau = fmaxf(tau, thr);
+            tau = fmaxf(tau, thr + shift);
             overflowed |= ovf;
             *my_tau_s = tau;
             atomicMax(my_tau_g, fkey(tau));
@@ -509,7 +529,7 @@ encode_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int l = 0; l < 32; ++l) {
         const int nn = __shfl_sync(FULL, cnt_end, l);
         const float mg = __shfl_sync(FULL, margin, l);
-        const float fl = __shfl_sync(FULL, tau, l);
+        const float fl = __shfl_sync(FULL, tau - shift, l);
         const int grow = row - lane + l;
         if (grow >= p.M) continue;  // warp-uniform
         int n_out = nn;
@@ -618,7 +638,8 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
   using namespace g2;
   if (a.M <= 0 || a.N <= 0) return 0;
   if ((a.K % 8) != 0) return 10;
-  if (a.top_k <= 0 || a.top_k > encode2_max_top_k() || !a.cand || !a.cand_cnt || !a.row_norm || !a.row_scale || !a.scalars)
+  if (a.top_k <= 0 || a.top_k > encode2_max_top_k() || !a.cand || !a.cand_cnt || !a.row_norm || !a.row_dx || !a.row_scale || !a.scalars ||
+      !a.col_norm)
     return 12;
   CUtensorMap maps[2];
   if (make_tmap(&maps[0], a.A_hi, a.M, a.K, BM)) return 11;
@@ -652,8 +673,10 @@ int launch_encode_gemm2(const EncodeGemmArgs& a, const Encode2Plan& pl, cudaStre
   }
   p.bias = a.bias;
   p.row_norm = a.row_norm;
+  p.row_dx = a.row_dx;
   p.row_scale = a.row_scale;
   p.scalars = a.scalars;
+  p.col_norm = a.col_norm;
   p.D = a.K;
   p.cand = reinterpret_cast<int2*>(a.cand);
   p.cand_cnt = a.cand_cnt;

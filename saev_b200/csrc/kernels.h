@@ -19,41 +19,47 @@ enum ScalarSlot {
   SC_UNSAFE_TOTAL = 1,  // uint   rows the screen could not certify (cumulative since sync_weights); all were repaired
   SC_AUX_LOSS = 2,      // float
   SC_RESCORED = 3,      // uint   candidates re-scored in fp32 (cumulative)
+  // three floats a sharded optimizer MAX-all-reduces as one vector (saev_b200_wnorm_scalar):
   SC_WNORM_SQ_MAX = 4,  // float  max_j ||W_enc_t[j]||^2
-  SC_MERGED = 5,        // uint   candidate-list entries merged (cumulative)
-  SC_BIAS_ABS_MAX = 6,  // float  max_j |b_enc[j]|
+  SC_BIAS_ABS_MAX = 5,  // float  max_j |b_enc[j]|
+  SC_RHO = 6,           // float  max_j ||w_j - fp16(w_j)|| / max(||w_j||, ||fp16(w_j)||)
   SC_N_UNSAFE = 7,      // int    rows of the CURRENT forward handed to the exact repair path
   SC_REPAIRED = 8,      // uint   rows re-done by the exact path (cumulative)
+  SC_UNSAFE_ERR = 9,    // uint   of SC_UNSAFE_TOTAL: rows whose OBSERVED screen error exceeded the bound (must stay 0:
+                        //        it would mean the error model is wrong; list overflows are the expected cause)
+  SC_MERGED = 10,       // uint   candidate-list entries merged (cumulative)
   SC_SLOTS = 32
 };
 
 // ---- deterministic error bound of the fp16 top-k screen -----------------------------------------------------------
-// The screen computes  h~ = 2^e * sum_d fp16(x_d 2^-e) fp16(w_d) + b  on the tensor cores (fp32 accumulation), the
-// re-score kernel  he = fl32(sum_d x_d w_d) + b.  With u = 2^-11 (fp16 unit roundoff), s = 2^-25 (fp16 round-off in
-// the subnormal range), every |fp16(a) - a| <= u |a| + s, so by Cauchy-Schwarz
-//   |h~ - he| <= ||x||_2 ||w||_2 (2u + u^2 + g)  +  s' sqrt(D) (2^e ||w||_2 + ||x||_2)  +  2^-22 (||x|| ||w|| + |b|)
+// The screen computes  h~ = 2^e * sum_d x16_d w16_d + b  on the tensor cores (x16 = fp16(x 2^-e), w16 = fp16(w), fp32
+// accumulation), the re-score kernel  he = fl32(sum_d x_d w_d) + b.  In exact arithmetic
+//     h~ - h = 2^e <x16 - x 2^-e, w16> + <x, w16 - w>,
+// so by Cauchy-Schwarz on the ACTUAL rounding residuals (their norms are computed where the fp16 copies are made:
+// prep_x_kernel per batch row, the Adam / sync kernels per dictionary row)
+//     |h~ - he| <= ||dx_b|| ||w16_j|| + ||x_b|| ||dw_j|| + (g + r) ||x_b|| ||w_j|| + r |b_j|
 // where g bounds both accumulation errors (tensor core: one truncating fp32 update per 16 products, doubled for
-// safety; re-score: D/32 sequential FMAs per lane + 5 shuffle levels) and the last term the two final roundings.
-//   E_b = xnorm_b * A + 2^e_b * Bc + C
+// safety; re-score: D/32 sequential FMAs per lane + 5 shuffle levels) and r = 2^-21 the final roundings (bias add, the
+// epilogue's own FMAs).  Residual norms instead of the unit roundoff (2^-11 per operand) make the bound 2.3x tighter
+// for ordinary dense rows -- fp16 rounds to nearest, the residual of a dense vector is ~0.43 * 2^-11 of its norm --
+// and cover subnormals / exact zeros without special terms.  With c_j = max(||w_j||, ||w16_j||) (stored per column,
+// rounded up) and rho = max_j ||dw_j|| / c_j (one scalar):
+//     E_bj = c_j P_b + Q_b,      P_b = ||dx_b|| + ||x_b|| (rho + g + r),      Q_b = r max_j |b_j|.
+// The per-column factor matters once a few atoms carry much larger encoder rows than the rest: a bound through
+// max_j ||w_j|| would widen the admission band of every column.
 struct ScreenBound {
-  float A, Bc, C;
+  float c, q;  // P_b = 1.01 (dxn_b + xn_b c),  Q_b = 1.01 q   (the bound is evaluated in fp32 itself: 1 % head room)
 };
-__host__ __device__ inline ScreenBound screen_bound(int D, float wnorm_max, float bias_abs_max) {
-  const float u = 4.8828125e-4f;           // 2^-11
-  const float s = 2.9802322e-8f * 1.001f;  // 2^-25 (+ cross terms)
+__host__ __device__ inline ScreenBound screen_bound(int D, float rho, float bias_abs_max) {
   const float g = (2.f * (D / 16 + 16) + (D / 32 + 8)) * 1.1920929e-7f;  // * 2^-23
-  const float rnd = 2.3841858e-7f;         // 2^-22
-  const float sqd = sqrtf(static_cast<float>(D));
+  const float r = 4.7683716e-7f;                                           // 2^-21
   ScreenBound b;
-  b.A = wnorm_max * (2.f * u + u * u + g + rnd) + s * sqd;
-  b.Bc = s * sqd * wnorm_max;
-  b.C = rnd * bias_abs_max;
-  // everything above is evaluated in fp32 itself: 1 % head room
-  b.A *= 1.01f;
-  b.Bc *= 1.01f;
-  b.C *= 1.01f;
+  b.c = rho + g + r;
+  b.q = r * bias_abs_max;
   return b;
 }
+__host__ __device__ inline float screen_P(const ScreenBound& s, float xn, float dxn) { return 1.01f * (dxn + xn * s.c); }
+__host__ __device__ inline float screen_Q(const ScreenBound& s) { return 1.01f * s.q; }
 constexpr float FP16_MAX = 65504.f;  // encoder rows with a larger norm cannot be screened in fp16 (all rows repaired)
 
 // number of kernels this library has launched (all handles); read through saev_b200_launch_count()
@@ -112,8 +118,10 @@ struct EncodeGemmArgs {
   float* extra = nullptr;
   int top_k = 32;                       // screen (pair kernel): k of the final selection
   const float* row_norm = nullptr;      // screen: [M] ||x_b||_2
+  const float* row_dx = nullptr;        // screen: [M] ||2^e_b x16_b - x_b||_2, the row's fp16 rounding residual
   const float* row_scale = nullptr;     // screen: [M] 2^e_b, the power of two the fp16 operand row was divided by
   const float* scalars = nullptr;       // screen: the workspace scalar block (SC_WNORM_SQ_MAX, SC_BIAS_ABS_MAX)
+  const float* col_norm = nullptr;      // screen: [N] c_j = max(||w_j||, ||fp16(w_j)||) (rounded up)
   int nsplit = 1;                       // column splits of the dense epilogues
   int num_sms = 148;
   int* cand_cnt = nullptr;              // screen: [rows, nlists] entries kept (negative: overflowed)
@@ -146,12 +154,16 @@ int encode2_max_top_k();
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t s,
                       __nv_bfloat16* lo2 = nullptr, const int* gate = nullptr);
 // x[B,D] -> fp16 operand x16[b] = fp16(x[b] * 2^-e_b) (2^e_b: power of two just above ||x_b||_inf, exact scaling),
-// row_norm[b] = ||x_b||_2 (rounded up), row_scale[b] = 2^e_b        (operand of the top-k screen, encode_gemm2.cu)
-int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_scale, cudaStream_t s);
+// row_norm[b] = ||x_b||_2, row_dx[b] = ||2^e_b x16_b - x_b||_2 (both rounded up), row_scale[b] = 2^e_b
+// (operand and error-bound inputs of the top-k screen, encode_gemm2.cu)
+int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_dx, float* row_scale,
+                  cudaStream_t s);
 // fp32 -> fp16 (round to nearest): the screen's copy of W_enc_t
 int launch_to_half(const float* src, __half* dst, long long n, cudaStream_t s);
-// *out = max_j ||W[j,:]||^2
-int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s);
+// *out_max = max_j ||W[j,:]||^2; optionally the per-row inputs of the screen's error bound: col_norm[j] =
+// max(||W[j]||, ||fp16(W[j])||) (rounded up) and *rho = max_j ||W[j] - fp16(W[j])|| / col_norm[j]
+int launch_row_sumsq_max(const float* W, int rows, int cols, float* out_max, cudaStream_t s, float* col_norm = nullptr,
+                         float* rho = nullptr);
 // *out = max_i |v[i]|
 int launch_abs_max(const float* v, int n, float* out, cudaStream_t s);
 int launch_normalize_rows(float* W, int rows, int cols, cudaStream_t s);
@@ -173,7 +185,8 @@ int launch_coherence_finish(const float* W, int D, const float* row_best, const 
 
 struct RescoreArgs {
   void* cand; const int* cand_cnt; int cand_stride; int nsplit;  // (row, list) candidate buffers
-  const float* row_norm; const float* row_scale;
+  const float* row_norm; const float* row_dx; const float* row_scale;
+  const float* col_norm;  // [S] c_j = max(||w_j||, ||fp16(w_j)||) (rounded up)
   float* scalars;       // workspace scalar block (ScalarSlot): bounds in, counters out
   const float* x; const float* W_enc_t; const float* b_enc;
   int B, D, S, K;
@@ -262,6 +275,8 @@ struct AdamArgs {
   float* m; float* v;          // flat, same order/offsets as the gradient bucket
   __half* shadow16;            // fp16 copy of W_enc_t for the tensor-core screen (may be null)
   float* wnorm_sq_max;         // device scalar: max_j ||W_enc_t[j]||^2 after the update (zeroed by the launcher)
+  float* wnorm_rows;           // [S] c_j = max(||w_j||, ||fp16(w_j)||) after the update, rounded up (may be null)
+  float* rho;                  // device scalar: max_j ||w_j - fp16(w_j)|| / c_j (zeroed by the launcher)
   float* bias_abs_max;         // device scalar: max_j |b_enc[j]| after the update (zeroed by the launcher)
   int D, S;
   float lr, beta1, beta2, eps, bc1, bc2_sqrt;

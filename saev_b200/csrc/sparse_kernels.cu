@@ -14,6 +14,8 @@
 
 namespace sb {
 
+constexpr float NORM_UP = 1.00001f;  // stored norms scale upper bounds: round them up past the fp32 summation error
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, float4 v) {
@@ -79,7 +81,7 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, int B, int D,
                                                      __half* __restrict__ x16, float* __restrict__ row_norm,
-                                                     float* __restrict__ row_scale) {
+                                                     float* __restrict__ row_dx, float* __restrict__ row_scale) {
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31, D4 = D >> 2;
@@ -98,20 +100,30 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x
   if (mx > 0.f && mx <= 3.0e38f) frexpf(mx, &e);  // mx = m 2^e, m in [0.5, 1)
   e = max(-100, min(e, 126));
   const float down = ldexpf(1.f, -e);
+  float sd = 0.f;  // ||x16 - x 2^-e||^2, in the scaled units
   for (int v = lane; v < D4; v += 32) {
     const float4 q = ldg4(row + 4 * v);  // L1 hit
+    const float4 qs = make_float4(q.x * down, q.y * down, q.z * down, q.w * down);
+    const __half2 h01 = __floats2half2_rn(qs.x, qs.y), h23 = __floats2half2_rn(qs.z, qs.w);
     __half2* o = reinterpret_cast<__half2*>(orow + 4 * v);
-    o[0] = __floats2half2_rn(q.x * down, q.y * down);
-    o[1] = __floats2half2_rn(q.z * down, q.w * down);
+    o[0] = h01;
+    o[1] = h23;
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const float4 dq = make_float4(f01.x - qs.x, f01.y - qs.y, f23.x - qs.z, f23.y - qs.w);
+    sd += dot4(dq, dq);
   }
+  sd = warp_sum(sd);
   if (lane == 0) {
-    row_norm[b] = sqrtf(ss) * 1.00001f;  // (rounded up: it scales an upper bound)
-    row_scale[b] = ldexpf(1.f, e);
+    const float up = ldexpf(1.f, e);
+    row_norm[b] = sqrtf(ss) * NORM_UP;  // (rounded up: they scale an upper bound)
+    row_dx[b] = sqrtf(sd) * up * NORM_UP;
+    row_scale[b] = up;
   }
 }
-int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_scale, cudaStream_t s) {
+int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_dx, float* row_scale,
+                  cudaStream_t s) {
   if (D % 4) return 21;
-  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x16, row_norm, row_scale);
+  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x16, row_norm, row_dx, row_scale);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -149,30 +161,53 @@ int launch_abs_max(const float* v, int n, float* out, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
+// Per-row inputs of the screen's error bound from three sums of squares of a row and its fp16 rounding:
+//   c = max(||w||, ||fp16(w)||) rounded up,   ratio = ||w - fp16(w)|| / c   (0 for a zero row)
+__device__ __forceinline__ void screen_col_stats(float ssq, float ssq16, float ssd, float& c, float& ratio) {
+  c = sqrtf(fmaxf(ssq, ssq16)) * NORM_UP;
+  ratio = c > 0.f ? sqrtf(ssd) * NORM_UP / c : 0.f;
+}
+__device__ __forceinline__ void accum_fp16_stats(float4 p, float& ssq, float& ssq16, float& ssd) {
+  const float2 a = __half22float2(__floats2half2_rn(p.x, p.y)), b = __half22float2(__floats2half2_rn(p.z, p.w));
+  const float4 h = make_float4(a.x, a.y, b.x, b.y);
+  const float4 d = make_float4(h.x - p.x, h.y - p.y, h.z - p.z, h.w - p.w);
+  ssq += dot4(p, p);
+  ssq16 += dot4(h, h);
+  ssd += dot4(d, d);
+}
+
 // *out = max_j ||W[j,:]||^2   (non-negative floats order like their bit patterns: atomicMax on int)
 __global__ void __launch_bounds__(256) row_sumsq_max_kernel(const float* __restrict__ W, int rows, int D,
-                                                            float* __restrict__ out) {
+                                                            float* __restrict__ out, float* __restrict__ col_norm,
+                                                            float* __restrict__ rho) {
   const int lane = threadIdx.x & 31;
-  float best = 0.f;
+  float best = 0.f, best_ratio = 0.f;
   for (int j = blockIdx.x * 8 + (threadIdx.x >> 5); j < rows; j += gridDim.x * 8) {
     const float* row = W + static_cast<long long>(j) * D;
-    float ss = 0.f;
-    for (int v = lane; v < (D >> 2); v += 32) {
-      const float4 q = ldg4(row + 4 * v);
-      ss += dot4(q, q);
-    }
-    best = fmaxf(best, warp_sum(ss));
+    float ss = 0.f, ss16 = 0.f, sd = 0.f;
+    for (int v = lane; v < (D >> 2); v += 32) accum_fp16_stats(ldg4(row + 4 * v), ss, ss16, sd);
+    ss = warp_sum(ss);
+    ss16 = warp_sum(ss16);
+    sd = warp_sum(sd);
+    float c, ratio;
+    screen_col_stats(ss, ss16, sd, c, ratio);
+    if (col_norm != nullptr && lane == 0) col_norm[j] = c;
+    best = fmaxf(best, ss);
+    best_ratio = fmaxf(best_ratio, ratio);
   }
-  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
+  if (lane == 0) {
+    atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
+    if (rho != nullptr) atomicMax(reinterpret_cast<int*>(rho), __float_as_int(best_ratio));
+  }
 }
-int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s) {
+int launch_row_sumsq_max(const float* W, int rows, int cols, float* out, cudaStream_t s, float* col_norm, float* rho) {
   if (cols % 4) return 21;
   if (cudaMemsetAsync(out, 0, 4, s) != cudaSuccess) return 23;
-  row_sumsq_max_kernel<<<148 * 4, 256, 0, s>>>(W, rows, cols, out);
+  if (rho != nullptr && cudaMemsetAsync(rho, 0, 4, s) != cudaSuccess) return 23;
+  row_sumsq_max_kernel<<<148 * 4, 256, 0, s>>>(W, rows, cols, out, col_norm, rho);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
-
 // ------------------------------------------------------------------------------------------------
 // W[j,:] /= ||W[j,:]||_2      (saev modeling.py:411-417 normalize_w_dec)
 // ------------------------------------------------------------------------------------------------
@@ -354,23 +389,23 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
     n_total += abs(c);
   }
   const float wn = sqrtf(a.scalars[SC_WNORM_SQ_MAX]);
-  const ScreenBound sbd = screen_bound(a.D, wn, a.scalars[SC_BIAS_ABS_MAX]);
-  const float err_bound = a.row_norm[b] * sbd.A + a.row_scale[b] * sbd.Bc + sbd.C;  // E_b
-  const float margin = 2.f * err_bound;
+  const ScreenBound sbd = screen_bound(a.D, a.scalars[SC_RHO], a.scalars[SC_BIAS_ABS_MAX]);
+  const float Pb = screen_P(sbd, a.row_norm[b], a.row_dx[b]);  // E_bj = c_j Pb + Qb
+  const float Qb = screen_Q(sbd);
   // an encoder row outside the fp16 range makes the whole screen meaningless (inf / nan operands)
   overflow |= !(wn < FP16_MAX) || a.force_unsafe != 0;
 
-  // ---- merged admission threshold: (k-th largest screen value of the row, to 16 bits) - margin ----
-  // Every list was trimmed against ITS k-th largest; the row's k-th largest is at least as large.
-  unsigned int tkey = 0u;  // below every real key
+  // The lists hold LOWER bounds l_j = h~_j - E_bj of the exact pre-activations.  L = k-th largest lower bound of the
+  // row (to 16 bits, rounded down): a column can only be in the exact top-k if its UPPER bound l_j + 2 E_bj reaches L.
+  float Lk = -INFINITY;
   if (n_total > a.K) {
     unsigned int prefix = 0u;
     int need = a.K;
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 24, prefix, need, hist, lane);
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 16, prefix, need, hist, lane);
-    tkey = fkey(funkey(prefix << 16) - margin);
+    Lk = funkey(prefix << 16);
   }
-  // ---- collect the survivors ----
+  // ---- collect the survivors (sv = the column's error bound E_bj, used again below) ----
   int n = 0;
   for (int l = 0; l < a.nsplit; ++l) {
     const int c = abs(cnts[l]);
@@ -378,12 +413,17 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
     for (int e0 = 0; e0 < c; e0 += 32) {
       const int e = e0 + lane;
       int2 t = make_int2(0, -1);
-      if (e < c) t = __ldg(lb + e);
-      const bool take = (e < c) && fkey(__int_as_float(t.x)) >= tkey;
+      float E = 0.f;
+      bool take = false;
+      if (e < c) {
+        t = __ldg(lb + e);
+        E = fmaf(__ldg(a.col_norm + t.y), Pb, Qb);
+        take = fmaf(2.f, E, __int_as_float(t.x)) >= Lk;
+      }
       const unsigned bal = __ballot_sync(FULL, take);
       const int o = n + __popc(bal & ((1u << lane) - 1u));
       if (take && o < RESCORE_CAP) {
-        sv[o] = __int_as_float(t.x);
+        sv[o] = __int_as_float(t.x) + E;  // the screen value h~_j
         si[o] = t.y;
       }
       n += __popc(bal);
@@ -431,13 +471,12 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       }
     }
     __syncwarp();
-    // The candidate set covers the exact top-k when every screen error is <= E_b.  The bound is deterministic; the
+    // The candidate set covers the exact top-k when every screen error is <= E_bj.  The bound is deterministic; the
     // check below guards its assumptions (accumulation model of the tensor core) on the columns we can see.
-    float maxerr = 0.f;
-    for (int c = lane; c < n; c += 32) maxerr = fmaxf(maxerr, fabsf(sv[c] - se[c]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxerr = fmaxf(maxerr, __shfl_xor_sync(FULL, maxerr, o));
-    overflow = !(maxerr <= err_bound);  // (also catches NaN)
+    bool bad = false;
+    for (int c = lane; c < n; c += 32) bad |= !(fabsf(sv[c] - se[c]) <= fmaf(__ldg(a.col_norm + si[c]), Pb, Qb));  // (NaN -> bad)
+    overflow = __any_sync(FULL, bad);
+    if (overflow && lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(a.scalars) + SC_UNSAFE_ERR, 1u);
   }
   if (lane == 0) {
     unsigned int* cnt_u = reinterpret_cast<unsigned int*>(a.scalars);
@@ -1531,7 +1570,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   {
     float* mrow = a.m + ro;
     float* vrow = a.v + ro;
-    float ssq = 0.f;
+    float ssq = 0.f, ssq16 = 0.f, ssd = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v4 = lane + 32 * i;
@@ -1543,7 +1582,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
         *reinterpret_cast<float4*>(a.W_enc_t + ro + 4 * v4) = p;
         *reinterpret_cast<float4*>(mrow + 4 * v4) = m;
         *reinterpret_cast<float4*>(vrow + 4 * v4) = v;
-        ssq += dot4(p, p);
+        accum_fp16_stats(p, ssq, ssq16, ssd);
         if (a.shadow16 != nullptr) {
           __half2* so = reinterpret_cast<__half2*>(a.shadow16 + ro + 4 * v4);
           so[0] = __floats2half2_rn(p.x, p.y);
@@ -1553,7 +1592,15 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
     }
     if (a.wnorm_sq_max != nullptr) {
       ssq = warp_sum(ssq);
-      if (lane == 0) atomicMax(reinterpret_cast<int*>(a.wnorm_sq_max), __float_as_int(ssq));
+      ssq16 = warp_sum(ssq16);
+      ssd = warp_sum(ssd);
+      if (lane == 0) {
+        float c, ratio;
+        screen_col_stats(ssq, ssq16, ssd, c, ratio);
+        atomicMax(reinterpret_cast<int*>(a.wnorm_sq_max), __float_as_int(ssq));
+        if (a.wnorm_rows != nullptr) a.wnorm_rows[j] = c;
+        if (a.rho != nullptr) atomicMax(reinterpret_cast<int*>(a.rho), __float_as_int(ratio));
+      }
     }
   }
   // ---- b_enc[j] (a sharded optimizer updates the whole bias vector on every rank instead) ----
@@ -1631,6 +1678,7 @@ int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
   if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
   if (a.bias_abs_max != nullptr && cudaMemsetAsync(a.bias_abs_max, 0, 4, s) != cudaSuccess) return 23;
+  if (a.rho != nullptr && cudaMemsetAsync(a.rho, 0, 4, s) != cudaSuccess) return 23;
   const int rows = a.row_end - a.row_begin;
   if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
   if (a.b_enc_separately) {

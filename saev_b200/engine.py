@@ -129,9 +129,9 @@ class Engine:
         """Cumulative diagnostics of the top-k screen since the last sync_weights(): rows that could not be
         certified, rows re-done by the exact path (equal once the forward has finished), candidates re-scored in
         fp32, candidate-list entries merged."""
-        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 8).tolist()
-        return {"unsafe_rows": t[0], "repaired": t[7], "unrepaired": t[0] - t[7], "rescored": t[2] & 0xFFFFFFFF,
-                "merged": t[4] & 0xFFFFFFFF}
+        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 10).tolist()
+        return {"unsafe_rows": t[0], "repaired": t[7], "unrepaired": t[0] - t[7], "bound_violations": t[8],
+                "rescored": t[2] & 0xFFFFFFFF, "merged": t[9] & 0xFFFFFFFF}
 
     # ---- parameters ------------------------------------------------------------------------
     @torch.no_grad()
@@ -281,9 +281,14 @@ class Engine:
         """The fp16 tensor-core operand copy of W_enc_t, [d_sae, d_model], inside the workspace."""
         return self._ws_tensor(self.lib.saev_b200_shadow_weights, torch.float16, self.S * self.D).view(self.S, self.D)
 
+    def wnorm_rows(self) -> torch.Tensor:
+        """Device float32[d_sae]: ||W_enc_t[j]||_2, the per-column input of the screen's error bound."""
+        return self._ws_tensor(self.lib.saev_b200_wnorm_rows, torch.float32, self.S)
+
     def wnorm_scalar(self) -> torch.Tensor:
-        """Device scalar max_j ||W_enc_t[j]||^2 the top-k screen derives its admission margin from."""
-        return self._ws_tensor(self.lib.saev_b200_wnorm_scalar, torch.float32, 1)
+        """Device float32[3]: max_j ||W_enc_t[j]||^2, max_j |b_enc[j]|, max_j relative fp16 residual -- the
+        dictionary-wide inputs of the screen's error bound (MAX-all-reduced by a sharded optimizer)."""
+        return self._ws_tensor(self.lib.saev_b200_wnorm_scalar, torch.float32, 3)
 
     def adam_step(self, lr: float, *, max_norm: float = 1.0, grad_scale: float = 1.0, betas=(0.9, 0.999),
                   eps: float = 1e-8, renorm_w_dec: bool = False) -> None:
@@ -416,7 +421,26 @@ class Engine:
                 self.losses.data_ptr(), state["acc"].data_ptr(), state["n_fired"].data_ptr(), state["values"].data_ptr(),
                 self.workspace.data_ptr(), self._stream()))
 
-    # ---- test hook -------------------------------------------------------------------------
+    # ---- test hooks ------------------------------------------------------------------------
+    def aux_selection(self, B: int | None = None) -> torch.Tensor:
+        """int64 [B, k_use]: the atoms AuxK selected per row in the last training forward (ascending atom order), for
+        parity tests that have to tell fp32-level ties from errors.  Host sync (reads n_dead)."""
+        B = B or self._last_B
+        mask_p, ld, dl_p, nd_p = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.saev_b200_aux_selection(self.h, self.workspace.data_ptr(), C.byref(mask_p), C.byref(ld),
+                                                  C.byref(dl_p), C.byref(nd_p)))
+        base = self.workspace.data_ptr()
+
+        def view(p, nbytes, dtype):
+            return self.workspace[p - base : p - base + nbytes].view(dtype)
+
+        n_dead = int(view(nd_p.value, 4, torch.int32).item())
+        dead_list = view(dl_p.value, 4 * n_dead, torch.int32).long()
+        mask = view(mask_p.value, B * ld.value, torch.uint8).view(B, ld.value)[:, :n_dead] != 0
+        k_use = int(mask[0].sum().item()) if B > 0 else 0
+        assert bool((mask.sum(1) == k_use).all()), "AuxK selected a different number of latents in different rows"
+        return dead_list[mask.nonzero()[:, 1].view(B, k_use)]
+
     def gemm_nt(self, A: torch.Tensor, Bt: torch.Tensor, bias: torch.Tensor | None, nterms: int) -> torch.Tensor:
         M, K = A.shape
         N = Bt.shape[0]

@@ -16,7 +16,7 @@ Exchange per step (NCCL over NVLink):
         vectors are exposed.  Every rank then runs the same norm / clip / Adam pass.
       - `sharded=True` (d_sae divisible by the world size): the two weight-gradient regions are REDUCE-SCATTERED by
         dictionary rows, each rank runs the norm / clip / Adam / renorm kernel on its S/N rows only (Adam moments
-        exist only for those rows), and the updated rows, their bf16 operand copy and the row-norm maximum are
+        exist only for those rows), and the updated rows, their fp16 operand copy and the row-norm maximum are
         ALL-GATHERED.  Same bytes on the wire, the 28 B/param optimizer pass shrinks by N, but nothing overlaps.
 """
 
@@ -83,7 +83,7 @@ class DataParallelTrainer:
             eng.forward(x, training=True, tokens_global=tokens_global)
         else:
             if self._pending:
-                # the screen needs only the bf16 operand copy (gathered synchronously at the end of the last step);
+                # the screen needs only the fp16 operand copy (gathered synchronously at the end of the last step);
                 # the fp32 rows are still arriving on the gather group's stream
                 eng.forward(x, training=True, phase=_lib.PHASE_A_SCREEN, tokens_global=tokens_global)
                 self.finish()
@@ -125,6 +125,8 @@ class DataParallelTrainer:
             eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)  # rows [j0, j1) + both bias vectors
             shadow = eng.shadow_weights()
             dist.all_gather_into_tensor(shadow, shadow[j0:j1], group=g)
+            wn = eng.wnorm_rows()
+            dist.all_gather_into_tensor(wn, wn[j0:j1], group=g)
             dist.all_reduce(eng.wnorm_scalar(), op=dist.ReduceOp.MAX, group=g)
             if self.gather_group is not None:
                 gg = self.gather_group

@@ -41,6 +41,7 @@ class OracleEngine:
         self.toks = torch.zeros(S, dtype=torch.int64)
         self._shadow = torch.zeros(S, D, dtype=torch.float16)
         self._wnorm = torch.zeros(1)
+        self._wrows = torch.zeros(S)
         self.shard = None
         self.t = 0
         self.calls = []
@@ -61,9 +62,13 @@ class OracleEngine:
     def wnorm_scalar(self):
         return self._wnorm
 
+    def wnorm_rows(self):
+        return self._wrows
+
     def sync_weights(self):
         self._shadow.copy_(self.W_enc_t.half())
         self._wnorm[0] = self.W_enc_t.pow(2).sum(1).max()
+        self._wrows.copy_(self.W_enc_t.norm(dim=1))
 
     def set_optimizer_shard(self, j0, j1):
         self.shard = (j0, j1)
@@ -79,6 +84,7 @@ class OracleEngine:
             # the screen runs on the bf16 operand copy: it must be complete and current on every rank
             assert torch.equal(self._shadow, self.W_enc_t.half()), "stale fp16 operand rows"
             assert float(self._wnorm) == pytest.approx(float(self.W_enc_t.pow(2).sum(1).max()), rel=1e-6)
+            assert torch.allclose(self._wrows, self.W_enc_t.norm(dim=1), rtol=1e-6), "stale per-column norms"
             st = self._st = self._state()
             h = orc.encode_pre(x, st.W_enc, st.b_enc)
             f, mask = orc.topk_activation(h, K)
@@ -152,6 +158,7 @@ class OracleEngine:
             self.W_dec[j0:j1] = orc.normalize_w_dec(self.W_dec[j0:j1])
         self._shadow[j0:j1] = self.W_enc_t[j0:j1].half()
         self._wnorm[0] = self.W_enc_t[j0:j1].pow(2).sum(1).max()
+        self._wrows[j0:j1] = self.W_enc_t[j0:j1].norm(dim=1)
 
 
 def _data():

@@ -25,12 +25,22 @@ ROOT = pathlib.Path(__file__).resolve().parent.parent
 
 def test_c2_full_shape_matches_oracle(monkeypatch):
     """BASELINE.json configs[1]: ViT-B/16 shape, full batch, MSE + AuxK(k_aux=512) with dead latents from step 2."""
-    _midsize_run("topk", 768, 32768, 32, 4096, "auto", monkeypatch, k_aux=512, n_steps=3, rank=48)
+    # (the reference's fp32 clip_grad_norm_ over 5e7 elements is itself only good to ~3e-3 here; ours is compared with
+    #  the fp64 norm of the oracle's gradients to 2e-5 inside)
+    _midsize_run("topk", 768, 32768, 32, 4096, "auto", monkeypatch, k_aux=512, n_steps=3, rank=48, ref_norm_rel=1e-2, tie_tolerant=True)
+
+
+def test_c2_full_shape_gaussian_rows_match_oracle(monkeypatch):
+    """Same shape on full-rank Gaussian rows (the benchmark's inputs): nearly every atom fires, a handful die by step 2
+    and AuxK runs with k_use = n_dead < k_aux (no selection among the dead at all)."""
+    eng = _midsize_run("topk", 768, 32768, 32, 4096, "auto", monkeypatch, k_aux=512, n_steps=3, rank=0, ref_norm_rel=1e-2,
+                       tie_tolerant=True)
+    assert 0 < int(eng.losses[5]) < 512
 
 
 def test_c3_dims_match_oracle(monkeypatch):
     """BASELINE.json configs[2] dims (256 dictionary tiles, several candidate lists per row) at batch 2048."""
-    _midsize_run("topk", 1024, 65536, 32, 2048, "auto", monkeypatch, k_aux=512, n_steps=3, rank=64)
+    _midsize_run("topk", 1024, 65536, 32, 2048, "auto", monkeypatch, k_aux=512, n_steps=3, rank=64, ref_norm_rel=1e-2, tie_tolerant=True)
 
 
 def _exact_topk_check(eng, x, K, chunk=2048):
@@ -75,7 +85,7 @@ def test_full_c3_topk_sets_match_fp64():
         assert gap <= 4e-6 * scale, (bad, gap)       # index sets may differ only at fp32-level ties
         assert bad <= 2, bad
     st = eng.screen_stats()
-    assert st["unrepaired"] == 0, st
+    assert st["unrepaired"] == 0 and st["bound_violations"] == 0, st
     assert st["unsafe_rows"] == 0, st  # Gaussian inputs never overflow a candidate list
 
 
@@ -111,7 +121,7 @@ def test_screen_is_exact_under_adversarial_inputs(case, monkeypatch):
     eng.sync_weights()
     eng.forward(x, training=True)
     st = eng.screen_stats()
-    assert st["unrepaired"] == 0, st
+    assert st["unrepaired"] == 0 and st["bound_violations"] == 0, st
     if case in ("outlier30", "outlier100", "tiny_rows"):
         assert st["unsafe_rows"] == 0, st
     if case == "forced":

@@ -132,7 +132,8 @@ def test_dense_features_with_two_pass_decode(monkeypatch):
     _midsize_run("topk", 256, 4096, 32, 1400, "auto", monkeypatch, dense_atoms=(5, 2049, 4095))
 
 
-def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=64, n_steps=4, rank=24):
+def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=64, n_steps=4, rank=24,
+                 ref_norm_rel=1e-3, tie_tolerant=False):
     """Four steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile).
 
     The library has two AuxK implementations (tensor-core split contractions / fp32 tiles) and picks one per step from
@@ -158,14 +159,17 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
     eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation=act, aux=True, k_aux=k_aux, l1_coeff=l1,
                               dead_threshold_tokens=2 * B, max_batch=B))
     eng.load_params(W_enc, b_enc, W_dec, b_dec)
-    basis = torch.randn(rank, D, generator=g)
+    basis = torch.randn(max(rank, 1), D, generator=g)
     tol = TOL_DENSE if act == "relu" else TOL
     # ReLU case: the inputs carry a large common offset (x - 0.5), i.e. every contraction cancels heavily (the fp32
     # oracle itself is only good to 4e-6 here; the two-piece split, SAEV_B200_DENSE_TERMS=3, is at 1.7e-4)
     tol_g = TOL
     lr = 0.0
     for step in range(n_steps):  # dead latents appear at step 2; in "auto" step 3 is the first on the tensor-core path
-        x = torch.randn(B, rank, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)
+        if rank > 0:
+            x = torch.randn(B, rank, generator=g) @ basis / 4 + 0.1 * torch.randn(B, D, generator=g)
+        else:  # full-rank Gaussian rows: nearly every atom fires, only a handful die
+            x = torch.randn(B, D, generator=g)
         if act == "relu":
             x = x - 0.5  # push many pre-activations negative so that latents die
         xd = x.cuda()
@@ -173,7 +177,13 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
         eng.forward(xd, training=True)
         eng.backward(xd)
         eng.grad_sumsq()
-        ref = orc.train_step(ocfg, st, x)
+        forced, forced_aux = None, None
+        if act == "topk" and tie_tolerant:
+            # the oracle adopts the kernels' selections after checking that they differ from torch.topk's only at
+            # fp32-level ties (oracle.adopt_selection)
+            forced = eng.topk_idx[:B].cpu().long()
+            forced_aux = lambda n_dead: eng.aux_selection(B).cpu()  # noqa: E731
+        ref = orc.train_step(ocfg, st, x, topk_idx=forced, aux_idx=forced_aux)
         ld = eng.loss_dict()
         for key in ("mse", "aux", "sparsity", "l1", "loss"):
             assert ld[key] == pytest.approx(ref[key], rel=tol, abs=1e-7), (step, key)
@@ -188,10 +198,10 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
         ref_grads = {k: v / coef_ref for k, v in ref["grads"].items()}
         gn_ref64 = float(sum(v.double().pow(2).sum() for v in ref_grads.values()).sqrt())
         assert gn == pytest.approx(gn_ref64, rel=tol_g), step
-        assert gn == pytest.approx(ref["grad_norm"], rel=1e-3), step
+        assert gn == pytest.approx(ref["grad_norm"], rel=ref_norm_rel), step
         ours = dict(W_enc=eng.gW_enc_t.t(), b_enc=eng.gb_enc, W_dec=eng.gW_dec, b_dec=eng.gb_dec)
-        for k, gr in ours.items():
-            assert rel_l2(gr.cpu(), ref_grads[k]) < tol_g, (step, k)
+        errs = {k: rel_l2(gr.cpu(), ref_grads[k]) for k, gr in ours.items()}
+        assert max(errs.values()) < tol_g, (step, errs)
         eng.adam_step(lr, max_norm=ocfg.grad_clip)
         lr = st.lr
     for name, p in (("W_enc", eng.W_enc_t.t()), ("b_enc", eng.b_enc), ("W_dec", eng.W_dec), ("b_dec", eng.b_dec)):

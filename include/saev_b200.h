@@ -127,7 +127,9 @@ int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace);
  *       every one of them was re-done by the exact fp32 path inside the same forward      [2] candidates re-scored
  *   [7] rows re-done by the exact path ( == [0] once the forward has run)      [9] candidate-list entries merged
  *   [8] of [0]: rows whose OBSERVED screen error exceeded the deterministic bound (stays 0 unless the error model of
- *       the tensor-core accumulation is violated; the expected cause of [0] is a candidate-list overflow) */
+ *       the tensor-core accumulation is violated)
+ *   [11] of [0]: rows whose threshold guess (the screen's warm start, predicted from the previous forward) was too high;
+ *       a few per 10^4 rows by construction.  The other expected cause of [0] is a candidate-list overflow. */
 uint32_t* saev_b200_unsafe_rows(const saev_b200_handle* h, void* workspace);
 
 /* Gradients of loss = mse + sparsity + aux for the batch of the last training forward

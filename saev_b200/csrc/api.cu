@@ -21,7 +21,7 @@ constexpr size_t ALIGN = 256;
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 
 struct Workspace {
-  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_dx, row_scale, unsafe_list, wnorm_rows, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
+  size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_dx, row_scale, unsafe_list, wnorm_rows, guess_hist, guess_L, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
@@ -59,6 +59,9 @@ struct saev_b200_handle {
   bool dh_fused_fwd = false;     // the last training forward left dh to the backward
   bool aux_tc_always = false;    // SAEV_B200_AUX=tc: no selection (tests pin each path)
   bool force_repair = false;     // SAEV_B200_FORCE_REPAIR=1: every row is re-done by the exact top-k path (tests)
+  float guess_quantile = GUESS_QUANTILE;  // threshold guess of the screen (kernels.h); SAEV_B200_GUESS=0 turns it off,
+  float guess_safety = GUESS_SAFETY;      // SAEV_B200_GUESS_Q / SAEV_B200_GUESS_S override the two parameters
+  int guess_parity = 0;          // which half of the ratio histogram the current forward fills
   int dense_terms = 6;     // bf16 split of the dense (ReLU) contractions: 6 = three pieces per operand (fp32-class
                            // accuracy), 3 = two pieces (~2^-16 of sum |a b|, half the tensor work); SAEV_B200_DENSE_TERMS
   Workspace ws;
@@ -146,7 +149,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.dhT_l2 = take(third ? S * LB * 2 : 0);
   }
   if (relu) {
-    w.cand = w.tau_keys = w.cand_cnt = w.row_norm = w.row_dx = w.row_scale = w.unsafe_list = w.wnorm_rows = o;
+    w.cand = w.tau_keys = w.cand_cnt = w.row_norm = w.row_dx = w.row_scale = w.unsafe_list = w.wnorm_rows = w.guess_hist = w.guess_L = o;
   } else {
     // candidate lists of the top-k screen: rows padded to 256, `nlists` lists per row; the list count depends on the
     // batch size (how many CTA-pair ranges touch one row block)
@@ -166,6 +169,8 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.row_scale = take((B + 255) / 256 * 256 * 4);
     w.unsafe_list = take(B * 4);
     w.wnorm_rows = take(S * 4);
+    w.guess_hist = take(2 * GUESS_BINS * 4);
+    w.guess_L = take((B + 255) / 256 * 256 * 4);
   }
   w.dh = take(B * K * 4);
   w.row_sse = take(B * 4);
@@ -479,6 +484,12 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     h->aux_tc_always = v && v[0] == 't';
   }
   {
+    const char* v = getenv("SAEV_B200_GUESS");
+    if (v && v[0] == '0') h->guess_quantile = -1.f;
+    if (const char* q = getenv("SAEV_B200_GUESS_Q")) h->guess_quantile = static_cast<float>(atof(q));
+    if (const char* sfy = getenv("SAEV_B200_GUESS_S")) h->guess_safety = static_cast<float>(atof(sfy));
+  }
+  {
     const char* v = getenv("SAEV_B200_FORCE_REPAIR");  // test switch: every row takes the exact repair path
     h->force_repair = v && v[0] == '1';
   }
@@ -553,6 +564,8 @@ int saev_b200_sync_weights(saev_b200_handle* h, const float* W_enc_t, const floa
   const long long n = static_cast<long long>(h->cfg.d_sae) * h->cfg.d_model;
   cudaMemsetAsync(at<char>(workspace, h->ws.scalars), 0, SC_SLOTS * 4, s);
   if (h->cfg.act_kind == SAEV_B200_ACT_TOPK) {  // (the dense path re-splits its operands every forward)
+    // new weights: the threshold / norm ratios recorded so far say nothing about them (the next forward runs cold)
+    cudaMemsetAsync(at<char>(workspace, h->ws.guess_hist), 0, 2 * GUESS_BINS * 4, s);
     if (launch_to_half(W_enc_t, at<__half>(workspace, h->ws.shadow_hi), n, s))
       return fail(h, 30, "sync_weights: fp16 copy launch failed%s");
     if (launch_row_sumsq_max(W_enc_t, h->cfg.d_sae, h->cfg.d_model, at<float>(workspace, h->ws.scalars) + SC_WNORM_SQ_MAX, s,
@@ -623,10 +636,19 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   } else if (do_screen || do_rest) {
     __half* x16 = at<__half>(workspace, w.x_hi);
     float* scal_f = at<float>(workspace, w.scalars);
+    // `reserved_pairs` SM pairs are left idle (a data-parallel caller runs NCCL all-gathers beside this kernel)
+    const Encode2Plan pl = encode2_plan(B, S, h->max_pairs > h->reserved_pairs ? h->max_pairs - h->reserved_pairs : 1);
     if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_PREP, s);
+      // the threshold guess of this forward, from the ratios the previous one recorded (then that half of the
+      // histogram is clear and becomes the one this forward fills)
+      h->guess_parity ^= 1;
+      if (launch_screen_guess(at<int>(workspace, w.guess_hist) + (h->guess_parity ^ 1) * GUESS_BINS, h->guess_quantile,
+                              h->guess_safety, h->guess_quantile > 0.f ? 64 : 0x7fffffff, scal_f, s))
+        return fail(h, 41, "forward: threshold-guess launch failed%s");
       if (launch_prep_x(x, B, D, x16, at<float>(workspace, w.row_norm), at<float>(workspace, w.row_dx),
-                        at<float>(workspace, w.row_scale), s))
+                        at<float>(workspace, w.row_scale), scal_f, at<unsigned int>(workspace, w.tau_keys),
+                        at<float>(workspace, w.guess_L), pl.m_pairs * 256, s))
         return fail(h, 41, "forward: prep_x launch failed%s");
     }
 
@@ -648,8 +670,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     g.num_sms = h->num_sms;
     g.cand = at<char>(workspace, w.cand);
     g.tau_keys = at<unsigned int>(workspace, w.tau_keys);
-    // `reserved_pairs` SM pairs are left idle (a data-parallel caller runs NCCL all-gathers beside this kernel)
-    const Encode2Plan pl = encode2_plan(B, S, h->max_pairs > h->reserved_pairs ? h->max_pairs - h->reserved_pairs : 1);
+    g.tau_preset = 1;  // prep_x_kernel wrote every row's starting threshold
     g.nsplit = pl.nlists;  // what the re-score kernel merges per row
     if (do_screen) {
       StageTimer tm(h, SAEV_B200_STAGE_ENCODE_GEMM, s);
@@ -673,6 +694,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     r.row_scale = g.row_scale;
     r.scalars = scal_f;
     r.col_norm = g.col_norm;
+    r.guess_L = at<float>(workspace, w.guess_L);
+    r.guess_hist = at<int>(workspace, w.guess_hist) + h->guess_parity * GUESS_BINS;
     r.unsafe_list = at<int>(workspace, w.unsafe_list);
     r.force_unsafe = h->force_repair ? 1 : 0;
     r.x = x;

@@ -28,6 +28,8 @@ enum ScalarSlot {
   SC_UNSAFE_ERR = 9,    // uint   of SC_UNSAFE_TOTAL: rows whose OBSERVED screen error exceeded the bound (must stay 0:
                         //        it would mean the error model is wrong; list overflows are the expected cause)
   SC_MERGED = 10,       // uint   candidate-list entries merged (cumulative)
+  SC_RHO_GUESS = 11,    // float  threshold guess of the current forward, as (L + max|b|) / (||x|| max||w||); -inf: none
+  SC_GUESS_FAILED = 12, // uint   of SC_UNSAFE_TOTAL: rows whose threshold guess turned out too high (cumulative)
   SC_SLOTS = 32
 };
 
@@ -60,6 +62,19 @@ __host__ __device__ inline ScreenBound screen_bound(int D, float rho, float bias
 }
 __host__ __device__ inline float screen_P(const ScreenBound& s, float xn, float dxn) { return 1.01f * (dxn + xn * s.c); }
 __host__ __device__ inline float screen_Q(const ScreenBound& s) { return 1.01f * s.q; }
+// ---- threshold guess (warm start of the screen) --------------------------------------------------------------------
+// A cold sweep admits ~k (1 + ln(S / k)) columns per row before its threshold has converged; with the final threshold
+// known up front only the ~70 columns of the final band are admitted and the kernel runs at the tensor roofline
+// (measured at c3: 1.33 ms instead of 2.3 ms).  So every row starts from a GUESS of its k-th largest lower bound,
+//     L_guess_b = rho * ||x_b|| max_j||w_j|| - max_j|b_j|,
+// rho = a low quantile (GUESS_QUANTILE, shrunk by GUESS_SAFETY) of the same ratio over the rows of the PREVIOUS
+// forward (a 2048-bin device histogram filled by the re-score kernel).  The guess is verified, not trusted: the
+// re-score accepts a row only if it holds k candidates whose lower bounds reach L_guess_b (then L_guess_b really was a
+// lower bound of the exact k-th largest value and nothing was missed); any other row goes to the exact path.
+constexpr int GUESS_BINS = 2048;          // ratio in [-1, 1), bin width 2 / GUESS_BINS
+constexpr float GUESS_QUANTILE = 5e-4f;
+constexpr float GUESS_SAFETY = 0.03f;
+
 constexpr float FP16_MAX = 65504.f;  // encoder rows with a larger norm cannot be screened in fp16 (all rows repaired)
 
 // number of kernels this library has launched (all handles); read through saev_b200_launch_count()
@@ -127,6 +142,7 @@ struct EncodeGemmArgs {
   int* cand_cnt = nullptr;              // screen: [rows, nlists] entries kept (negative: overflowed)
   void* cand = nullptr;                 // screen: [rows padded to 256, nlists, ENCODE2_CAPG] x {value bits, column}
   unsigned int* tau_keys = nullptr;     // screen: [rows padded to 256] shared admission thresholds (scratch)
+  int tau_preset = 0;                   // screen: tau_keys already holds the rows' threshold guesses (do not clear)
   float* out = nullptr;                 // epilogue 1: [M, ldo]
   long long ldo = 0;
 };
@@ -156,8 +172,12 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 // x[B,D] -> fp16 operand x16[b] = fp16(x[b] * 2^-e_b) (2^e_b: power of two just above ||x_b||_inf, exact scaling),
 // row_norm[b] = ||x_b||_2, row_dx[b] = ||2^e_b x16_b - x_b||_2 (both rounded up), row_scale[b] = 2^e_b
 // (operand and error-bound inputs of the top-k screen, encode_gemm2.cu)
+// Also seeds the screen's per-row thresholds from the guess in scalars[SC_RHO_GUESS]: tau_keys[b] (rows up to
+// `rows_padded`, 0 = none) in the kernel's threshold space, guess_L[b] = L_guess_b (-inf = none).
 int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_dx, float* row_scale,
-                  cudaStream_t s);
+                  const float* scalars, unsigned int* tau_keys, float* guess_L, int rows_padded, cudaStream_t s);
+// scalars[SC_RHO_GUESS] from the histogram the previous forward filled (then clears it for re-use)
+int launch_screen_guess(int* hist, float quantile, float safety, int min_rows, float* scalars, cudaStream_t s);
 // fp32 -> fp16 (round to nearest): the screen's copy of W_enc_t
 int launch_to_half(const float* src, __half* dst, long long n, cudaStream_t s);
 // *out_max = max_j ||W[j,:]||^2; optionally the per-row inputs of the screen's error bound: col_norm[j] =
@@ -193,6 +213,8 @@ struct RescoreArgs {
   int* topk_idx; float* topk_val;
   int* feat_count;      // [S] += 1 per selected (b, j)   (may be null: eval)
   int* active;          // [S] = 1 where a non-zero activation was selected (may be null)
+  const float* guess_L; // [B] the threshold guess each row was screened with (-inf: none), verified here
+  int* guess_hist;      // [GUESS_BINS] histogram of this forward's threshold / norm ratios (input of the next guess)
   int* unsafe_list;     // [B] rows handed to the exact path (count in scalars[SC_N_UNSAFE], zeroed by the launcher)
   int force_unsafe;     // test switch: treat every row as uncertified
 };

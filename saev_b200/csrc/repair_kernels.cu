@@ -7,10 +7,11 @@
 // as the re-score, common.cuh row_dot) and the k largest are selected by a block-wide radix select with the
 // reference's tie rule (value descending, then column ascending).
 //
-//   repair_scan_kernel    grid (n_slices, R): block (s, r) takes unsafe rows r, r + R, ... and the s-th slice of the
-//                         dictionary; it walks the slice in tiles of TILE atoms (8 warps, one atom per warp at a time,
-//                         two in flight), keeps the best k so far in shared memory and leaves them, in column
-//                         order, in the row's own candidate-list storage (consumed by then): slot [s][0..k).
+//   repair_scan_kernel    grid (n_slices, G): block (s, g) takes groups of RP_ROWS unsafe rows (g, g + G, ...) and
+//                         the s-th slice of the dictionary; it walks the slice in tiles of RP_TILE atoms (8 warps, one
+//                         atom per warp at a time, two in flight, each multiplied with all rows of the group), keeps
+//                         the best k so far per row in shared memory and leaves them, in column order, in the row's
+//                         own candidate-list storage (consumed by then): slot [s][0..k).
 //   repair_select_kernel  grid R: merges the n_slices x k survivors of a row and writes topk_idx / topk_val
 //                         (rank order), the per-atom counts and the activity flags, exactly what the re-score
 //                         kernel writes for a certified row.
@@ -24,10 +25,11 @@ namespace {
 
 constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
-constexpr int RP_TILE = 2048;      // atoms per selection round of the scan
+constexpr int RP_TILE = 1024;      // atoms per selection round of the scan
+constexpr int RP_ROWS = 8;         // unsafe rows multiplied with one load of a dictionary row (4 when d_model > 1024)
 constexpr int RP_KMAX = 64;        // top_k <= 64 (saev_b200_create)
 constexpr int RP_MAX_SLICES = 64;
-constexpr int RP_ROW_SLOTS = 16;   // gridDim.y of the scan / gridDim.x of the select
+constexpr int RP_ROW_SLOTS = 8;    // gridDim.y of the scan (row groups in flight)
 
 __device__ __forceinline__ float4 ldg4r(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -129,30 +131,54 @@ __device__ int block_select_topk(const float* v, int n, int k, ColFn col_of, flo
   return taken_before;  // == k
 }
 
+// same FMA chain + shuffle tree as row_dot (common.cuh) with the x row read from shared memory: bit-identical values
 template <int VPL>
+__device__ __forceinline__ float row_dot_smem(const float4* __restrict__ xs4, const float4 (&w)[VPL], int lane, int D4) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    const float4 x = (v < D4) ? xs4[v] : make_float4(0, 0, 0, 0);
+    acc = fmaf(x.x, w[i].x, acc);
+    acc = fmaf(x.y, w[i].y, acc);
+    acc = fmaf(x.z, w[i].z, acc);
+    acc = fmaf(x.w, w[i].w, acc);
+  }
+  return warp_sum(acc);
+}
+
+// R unsafe rows per pass over the block's slice of the dictionary: every W_enc_t row is loaded once and multiplied
+// with all R batch rows (staged in shared memory), so repairing a handful of rows costs one sweep of the dictionary
+// (~270 MB at c3: ~50 us over 64 slices) instead of one sweep per row.
+template <int VPL, int R>
 __global__ void __launch_bounds__(RP_THREADS) repair_scan_kernel(RescoreArgs a, int n_slices, int slice_len) {
-  __shared__ float hv[RP_TILE + RP_KMAX];
-  __shared__ float best_v[RP_KMAX], tmp_v[RP_KMAX];
-  __shared__ int best_c[RP_KMAX], tmp_c[RP_KMAX];
+  extern __shared__ float4 rp_smem4[];
+  __shared__ float best_v[R][RP_KMAX], tmp_v[RP_KMAX];
+  __shared__ int best_c[R][RP_KMAX], tmp_c[RP_KMAX];
   __shared__ int hist[256], wtot[2 * RP_WARPS], bc[4];
   const int n_unsafe = min(reinterpret_cast<const int*>(a.scalars)[SC_N_UNSAFE], a.B);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D4 = a.D >> 2, K = a.K;
+  float4* xs4 = rp_smem4;                                                   // [R][D4]
+  float* hv = reinterpret_cast<float*>(rp_smem4 + static_cast<size_t>(R) * D4);  // [R][RP_TILE + RP_KMAX]
+  constexpr int HV = RP_TILE + RP_KMAX;
   const int j_begin = blockIdx.x * slice_len, j_end = min(a.S, j_begin + slice_len);
-  for (int u = blockIdx.y; u < n_unsafe; u += gridDim.y) {
-    const int b = a.unsafe_list[u];
-    float4 xr[VPL];
-    const float* xrow = a.x + static_cast<long long>(b) * a.D;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      xr[i] = (v < D4) ? ldg4r(xrow + 4 * v) : make_float4(0, 0, 0, 0);
+  for (int g0 = blockIdx.y * R; g0 < n_unsafe; g0 += gridDim.y * R) {
+    const int nr = min(R, n_unsafe - g0);
+    __syncthreads();
+    for (int i = tid; i < R * D4; i += RP_THREADS) {
+      const int r = i / D4, v = i - r * D4;
+      xs4[i] = r < nr ? ldg4r(a.x + static_cast<long long>(a.unsafe_list[g0 + r]) * a.D + 4 * v) : make_float4(0, 0, 0, 0);
     }
-    int n_best = 0;
+    int n_best = 0;  // (the same for every row of the group: min(K, atoms seen so far))
+    __syncthreads();
     for (int t0 = j_begin; t0 < j_end; t0 += RP_TILE) {
       const int nt = min(RP_TILE, j_end - t0);
       // the carried winners come from lower columns: they go in front, so that index order stays column order
-      for (int i = tid; i < n_best; i += RP_THREADS) hv[i] = best_v[i];
+      for (int i = tid; i < R * n_best; i += RP_THREADS) {
+        const int r = i / n_best, e = i - r * n_best;
+        hv[r * HV + e] = best_v[r][e];
+      }
       for (int a0 = warp; a0 < nt; a0 += 2 * RP_WARPS) {
         const int a1 = a0 + RP_WARPS;
         const int j0 = t0 + a0, j1 = t0 + min(a1, nt - 1);
@@ -165,30 +191,40 @@ __global__ void __launch_bounds__(RP_THREADS) repair_scan_kernel(RescoreArgs a, 
           w0[i] = (v < D4) ? ldg4r(r0 + 4 * v) : make_float4(0, 0, 0, 0);
           w1[i] = (v < D4) ? ldg4r(r1 + 4 * v) : make_float4(0, 0, 0, 0);
         }
-        const float h0 = row_dot<VPL>(xr, w0), h1 = row_dot<VPL>(xr, w1);
-        if (lane == 0) {
-          hv[n_best + a0] = h0 + __ldg(a.b_enc + j0);
-          if (a1 < nt) hv[n_best + a1] = h1 + __ldg(a.b_enc + j1);
+        const float b0 = __ldg(a.b_enc + j0), b1 = __ldg(a.b_enc + j1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float h0 = row_dot_smem<VPL>(xs4 + r * D4, w0, lane, D4);
+          const float h1 = row_dot_smem<VPL>(xs4 + r * D4, w1, lane, D4);
+          if (lane == 0) {
+            hv[r * HV + n_best + a0] = h0 + b0;
+            if (a1 < nt) hv[r * HV + n_best + a1] = h1 + b1;
+          }
         }
       }
       __syncthreads();
       const int nb = n_best;
-      const int got = block_select_topk(
-          hv, nb + nt, K, [&](int i) { return i < nb ? best_c[i] : t0 + (i - nb); }, tmp_v, tmp_c, hist, wtot, bc);
-      __syncthreads();
-      for (int i = tid; i < got; i += RP_THREADS) {
-        best_v[i] = tmp_v[i];
-        best_c[i] = tmp_c[i];
+      int got = 0;
+      for (int r = 0; r < nr; ++r) {
+        const int* bcr = best_c[r];
+        got = block_select_topk(hv + r * HV, nb + nt, K, [&](int i) { return i < nb ? bcr[i] : t0 + (i - nb); }, tmp_v,
+                                tmp_c, hist, wtot, bc);
+        __syncthreads();
+        for (int i = tid; i < got; i += RP_THREADS) {
+          best_v[r][i] = tmp_v[i];
+          best_c[r][i] = tmp_c[i];
+        }
+        __syncthreads();
       }
       n_best = got;
-      __syncthreads();
     }
-    // slot [slice][0 .. K) of the row's candidate storage; unused entries carry column -1
-    int2* out = reinterpret_cast<int2*>(a.cand) + static_cast<long long>(b) * a.nsplit * a.cand_stride +
-                static_cast<long long>(blockIdx.x) * K;
-    for (int i = tid; i < K; i += RP_THREADS)
-      out[i] = i < n_best ? make_int2(__float_as_int(best_v[i]), best_c[i]) : make_int2(0, -1);
-    __syncthreads();
+    // slot [slice][0 .. K) of each row's candidate storage; unused entries carry column -1
+    for (int i = tid; i < nr * K; i += RP_THREADS) {
+      const int r = i / K, e = i - r * K;
+      int2* out = reinterpret_cast<int2*>(a.cand) + static_cast<long long>(a.unsafe_list[g0 + r]) * a.nsplit * a.cand_stride +
+                  static_cast<long long>(blockIdx.x) * K;
+      out[e] = e < n_best ? make_int2(__float_as_int(best_v[r][e]), best_c[r][e]) : make_int2(0, -1);
+    }
   }
 }
 
@@ -262,8 +298,30 @@ int launch_repair_topk(const RescoreArgs& a, cudaStream_t s) {
   const int slice_len = (a.S + n_slices - 1) / n_slices;
   n_slices = (a.S + slice_len - 1) / slice_len;
   const dim3 grid(n_slices, RP_ROW_SLOTS);
-  SB_DISPATCH_VPL(a.D, (repair_scan_kernel<VPL><<<grid, RP_THREADS, 0, s>>>(a, n_slices, slice_len)));
-  repair_select_kernel<<<RP_ROW_SLOTS * 4, RP_THREADS, 0, s>>>(a, n_slices);
+  const int need = (a.D + 127) / 128;
+  ++g_launch_count;
+#define SB_REPAIR(V, R)                                                                                              \
+  {                                                                                                                  \
+    const size_t smem = static_cast<size_t>(R) * (a.D / 4) * 16 + static_cast<size_t>(R) * (RP_TILE + RP_KMAX) * 4;  \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      if (cudaFuncSetAttribute(repair_scan_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                               static_cast<int>(RP_ROWS * 2048 * 4 + RP_ROWS * (RP_TILE + RP_KMAX) * 4)) != cudaSuccess) \
+        return 3;                                                                                                    \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    repair_scan_kernel<V, R><<<grid, RP_THREADS, smem, s>>>(a, n_slices, slice_len);                                 \
+  }
+  if (need <= 1) SB_REPAIR(1, RP_ROWS)
+  else if (need <= 2) SB_REPAIR(2, RP_ROWS)
+  else if (need <= 4) SB_REPAIR(4, RP_ROWS)
+  else if (need <= 6) SB_REPAIR(6, RP_ROWS)
+  else if (need <= 8) SB_REPAIR(8, RP_ROWS)
+  else if (need <= 12) SB_REPAIR(12, RP_ROWS / 2)
+  else if (need <= 16) SB_REPAIR(16, RP_ROWS / 2)
+  else return 20;
+#undef SB_REPAIR
+  repair_select_kernel<<<64, RP_THREADS, 0, s>>>(a, n_slices);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -81,10 +81,16 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, lo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, int B, int D,
                                                      __half* __restrict__ x16, float* __restrict__ row_norm,
-                                                     float* __restrict__ row_dx, float* __restrict__ row_scale) {
+                                                     float* __restrict__ row_dx, float* __restrict__ row_scale,
+                                                     const float* __restrict__ scalars,
+                                                     unsigned int* __restrict__ tau_keys, float* __restrict__ guess_L,
+                                                     int rows_padded) {
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (b >= B) return;
   const int lane = threadIdx.x & 31, D4 = D >> 2;
+  if (b >= B) {
+    if (b < rows_padded && lane == 0) tau_keys[b] = 0u;  // rows past the batch: no threshold (they admit nothing anyway)
+    return;
+  }
   const float* row = x + static_cast<long long>(b) * D;
   __half* orow = x16 + static_cast<long long>(b) * D;
   float mx = 0.f, ss = 0.f;
@@ -115,15 +121,89 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x
   sd = warp_sum(sd);
   if (lane == 0) {
     const float up = ldexpf(1.f, e);
-    row_norm[b] = sqrtf(ss) * NORM_UP;  // (rounded up: they scale an upper bound)
-    row_dx[b] = sqrtf(sd) * up * NORM_UP;
+    const float xn = sqrtf(ss) * NORM_UP;  // (rounded up: they scale an upper bound)
+    const float dxn = sqrtf(sd) * up * NORM_UP;
+    row_norm[b] = xn;
+    row_dx[b] = dxn;
     row_scale[b] = up;
+    // threshold guess (kernels.h): L_guess = rho ||x|| max||w|| - max|b|; the kernel admits t_j > tau with tau = L - Q_b
+    const float rho = scalars[SC_RHO_GUESS];
+    float Lg = -INFINITY;
+    unsigned int key = 0u;
+    if (rho > -1.5f && rho < 1.5f) {
+      Lg = rho * (sqrtf(ss) * sqrtf(scalars[SC_WNORM_SQ_MAX])) - scalars[SC_BIAS_ABS_MAX];
+      const ScreenBound sbd = screen_bound(D, scalars[SC_RHO], scalars[SC_BIAS_ABS_MAX]);
+      key = fkey(Lg - screen_Q(sbd));
+    }
+    guess_L[b] = Lg;
+    tau_keys[b] = key;
   }
 }
 int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, float* row_dx, float* row_scale,
-                  cudaStream_t s) {
+                  const float* scalars, unsigned int* tau_keys, float* guess_L, int rows_padded, cudaStream_t s) {
   if (D % 4) return 21;
-  prep_x_kernel<<<(B + 7) / 8, 256, 0, s>>>(x, B, D, x16, row_norm, row_dx, row_scale);
+  prep_x_kernel<<<(rows_padded + 7) / 8, 256, 0, s>>>(x, B, D, x16, row_norm, row_dx, row_scale, scalars, tau_keys,
+                                                      guess_L, rows_padded);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// rho for the next screen = the `quantile` of the ratios the previous forward recorded, shrunk by `safety` (towards
+// "admit more"); -inf when fewer than `min_rows` rows were recorded.  Clears the histogram.
+__global__ void __launch_bounds__(1024) screen_guess_kernel(int* __restrict__ hist, float quantile, float safety,
+                                                            int min_rows, float* __restrict__ scalars) {
+  __shared__ int wsum[32];
+  __shared__ int s_total;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int c0 = hist[2 * t], c1 = hist[2 * t + 1];  // GUESS_BINS == 2048 == 2 * blockDim
+  hist[2 * t] = 0;
+  hist[2 * t + 1] = 0;
+  int incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, w, o);
+      if (lane >= o) w += v;
+    }
+    wsum[lane] = w;
+    if (lane == 31) s_total = w;
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int before = (warp > 0 ? wsum[warp - 1] : 0) + incl - (c0 + c1);  // rows in lower bins
+  if (t == 0 && total < min_rows) scalars[SC_RHO_GUESS] = -INFINITY;
+  if (total < min_rows) return;
+  __shared__ float s_q, s_med;
+  const int want = max(1, static_cast<int>(quantile * total));  // the `want`-th smallest ratio ...
+  const int half = max(1, total / 2);                            // ... and the median
+  // the bins holding them: before < rank <= before + c0 (+ c1)
+  auto bin_of = [&](int rank) {
+    if (before < rank && rank <= before + c0) return 2 * t;
+    if (before + c0 < rank && rank <= before + c0 + c1) return 2 * t + 1;
+    return -1;
+  };
+  const int bq = bin_of(want), bm = bin_of(half);
+  if (bq >= 0) s_q = -1.f + 2.f * bq / GUESS_BINS;  // lower edges
+  if (bm >= 0) s_med = -1.f + 2.f * bm / GUESS_BINS;
+  __syncthreads();
+  if (t == 0) {
+    // shrink towards "admit more": relative safety, one bin of resolution, and a share of the distribution's own
+    // width (rows of a heavy-tailed batch undercut the previous batch's quantile far more often than Gaussian rows)
+    const float q = s_q, width = fmaxf(0.f, s_med - s_q);
+    scalars[SC_RHO_GUESS] = q - fmaxf(safety * fabsf(q), 0.25f * width) - 2.f / GUESS_BINS;
+  }
+}
+int launch_screen_guess(int* hist, float quantile, float safety, int min_rows, float* scalars, cudaStream_t s) {
+  static_assert(GUESS_BINS == 2048, "screen_guess_kernel assumes two bins per thread");
+  screen_guess_kernel<<<1, 1024, 0, s>>>(hist, quantile, safety, min_rows, scalars);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -398,12 +478,35 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   // The lists hold LOWER bounds l_j = h~_j - E_bj of the exact pre-activations.  L = k-th largest lower bound of the
   // row (to 16 bits, rounded down): a column can only be in the exact top-k if its UPPER bound l_j + 2 E_bj reaches L.
   float Lk = -INFINITY;
+  const float Lg = a.guess_L != nullptr ? a.guess_L[b] : -INFINITY;
+  bool guess_failed = false;
   if (n_total > a.K) {
     unsigned int prefix = 0u;
     int need = a.K;
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 24, prefix, need, hist, lane);
     rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 16, prefix, need, hist, lane);
     Lk = funkey(prefix << 16);
+    if (Lg > Lk && Lg <= funkey((prefix << 16) | 0xffffu)) {  // too close to call at 16 bits: the exact k-th largest
+      rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 8, prefix, need, hist, lane);
+      rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 0, prefix, need, hist, lane);
+      Lk = funkey(prefix);
+    }
+  }
+  // The row was screened from a GUESSED threshold: everything whose upper bound reached L_guess was admitted.  If k of
+  // the admitted columns have lower bounds >= L_guess, the guess was a true lower bound of the exact k-th largest
+  // value and no top-k column can be missing; otherwise the row has to be redone without the guess.
+  if (Lg > -INFINITY && !(Lk >= Lg)) guess_failed = true;
+  if (a.guess_hist != nullptr && lane == 0 && !overflow) {
+    // this row's ratio for the next forward's guess (failed rows land in the lowest bin: they pull the quantile down)
+    const float den = a.row_norm[b] * wn;
+    float ratio = -1.f;
+    if (!guess_failed && n_total > a.K && den > 0.f) ratio = (Lk + a.scalars[SC_BIAS_ABS_MAX]) / den;
+    const int bin = min(GUESS_BINS - 1, max(0, static_cast<int>(floorf((ratio + 1.f) * (GUESS_BINS / 2)))));
+    if (n_total > a.K || guess_failed) atomicAdd(a.guess_hist + bin, 1);
+  }
+  if (guess_failed) {
+    overflow = true;
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(a.scalars) + SC_GUESS_FAILED, 1u);
   }
   // ---- collect the survivors (sv = the column's error bound E_bj, used again below) ----
   int n = 0;

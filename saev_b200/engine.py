@@ -127,11 +127,12 @@ class Engine:
 
     def screen_stats(self) -> dict:
         """Cumulative diagnostics of the top-k screen since the last sync_weights(): rows that could not be
-        certified, rows re-done by the exact path (equal once the forward has finished), candidates re-scored in
-        fp32, candidate-list entries merged."""
-        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 10).tolist()
+        certified, rows re-done by the exact path (equal once the forward has finished), of those the rows whose
+        threshold guess was too high (`guess_failed`, expected: a few per 10^4 rows) and the rows whose observed screen
+        error exceeded the bound (`bound_violations`, must be 0), candidates re-scored in fp32, list entries merged."""
+        t = self._ws_tensor(self.lib.saev_b200_unsafe_rows, torch.int32, 12).tolist()
         return {"unsafe_rows": t[0], "repaired": t[7], "unrepaired": t[0] - t[7], "bound_violations": t[8],
-                "rescored": t[2] & 0xFFFFFFFF, "merged": t[9] & 0xFFFFFFFF}
+                "guess_failed": t[11], "rescored": t[2] & 0xFFFFFFFF, "merged": t[9] & 0xFFFFFFFF}
 
     # ---- parameters ------------------------------------------------------------------------
     @torch.no_grad()

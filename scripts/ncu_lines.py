@@ -2,6 +2,7 @@
 usage: python scripts/ncu_lines.py <report.ncu-rep> <cubin from `cuobjdump -xelf all lib.so`> <kernel-name-substring> <source-file>"""
 import collections, csv, io, re, subprocess, sys
 rep, cubin, kname, srcfile = sys.argv[1:5]
+THR = float(sys.argv[5]) if len(sys.argv) > 5 else 0.01
 dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
 # walk the .text section of the kernel: remember the last "//## File ..., line N" (innermost non-inlined: take first of a run)
 line_of = {}; cur = None; inside = False
@@ -34,5 +35,5 @@ text = open(srcfile).read().splitlines()
 print(f"samples {ts}, executed {te}; lines with >=1% of either:")
 for ln in sorted(agg):
     sm, ex = agg[ln]
-    if sm >= ts * 0.01 or ex >= te * 0.01:
+    if sm >= ts * THR or ex >= te * THR:
         print(f"  L{ln:4d} smp {sm/ts*100:5.1f}%  exec {ex/te*100:5.1f}%  | {text[ln-1].strip()[:90] if 0 < ln <= len(text) else '?'}")

@@ -86,7 +86,51 @@ def test_full_c3_topk_sets_match_fp64():
         assert bad <= 2, bad
     st = eng.screen_stats()
     assert st["unrepaired"] == 0 and st["bound_violations"] == 0, st
-    assert st["unsafe_rows"] == 0, st  # Gaussian inputs never overflow a candidate list
+    assert st["unsafe_rows"] == st["guess_failed"] <= 16, st  # Gaussian inputs never overflow a candidate list
+
+
+def test_threshold_guess_is_verified_and_failures_are_repaired():
+    """The screen starts every row from a threshold predicted from the PREVIOUS forward (kernels.h, "threshold guess").
+    Train on structured (low-rank) rows, whose k-th largest pre-activation is large relative to their norm, then feed
+    batches for which that prediction is too optimistic (isotropic rows, rows with a large common offset): the guess
+    must fail verification there, the exact path must redo those rows, and the selection must equal the fp64 top-k on
+    every batch -- including batches for which the prediction holds."""
+    from saev_b200.engine import Engine, EngineConfig
+
+    D, S, K, B = 512, 16384, 32, 2048
+    eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, max_batch=B, aux=False))
+    eng.init_params(seed=1)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    basis = torch.randn(6, D, device="cuda", generator=g)
+
+    def structured():
+        return torch.randn(B, 6, device="cuda", generator=g) @ basis + 0.05 * torch.randn(B, D, device="cuda", generator=g)
+
+    for step in range(6):
+        eng.train_step(structured(), 1e-3)
+    st0 = eng.screen_stats()
+    assert st0["unrepaired"] == 0 and st0["bound_violations"] == 0, st0
+    batches = {
+        "same distribution": structured(),
+        "isotropic rows": torch.randn(B, D, device="cuda", generator=g),
+        "same distribution again": structured(),
+        "offset rows": structured() + 5.0,
+        "mixed norms": structured() * torch.logspace(-3, 2, B, device="cuda")[:, None],
+    }
+    failed = {}
+    for name, x in batches.items():
+        before = eng.screen_stats()
+        eng.forward(x, training=False)
+        bad, worst, gap = _exact_topk_check(eng, x, K, chunk=1024)
+        after = eng.screen_stats()
+        scale = float(eng.topk_val[:B].abs().max())
+        assert worst <= 2e-6 * scale and gap <= 4e-6 * scale and bad <= 2, (name, bad, worst, gap)
+        assert after["unrepaired"] == 0 and after["bound_violations"] == 0, (name, after)
+        failed[name] = after["guess_failed"] - before["guess_failed"]
+    # each forward is screened from the ratios of the one before it: going from one kind of rows to another and back
+    # must trip the verification on at least one side of the switch, and a repeat of the same kind must not
+    assert max(failed["isotropic rows"], failed["same distribution again"]) > B // 2, failed
+    assert failed["same distribution"] <= 8, failed
 
 
 @pytest.mark.parametrize("case", ["outlier30", "outlier100", "dup_atoms", "zero_rows", "tiny_rows", "forced"])
@@ -123,7 +167,7 @@ def test_screen_is_exact_under_adversarial_inputs(case, monkeypatch):
     st = eng.screen_stats()
     assert st["unrepaired"] == 0 and st["bound_violations"] == 0, st
     if case in ("outlier30", "outlier100", "tiny_rows"):
-        assert st["unsafe_rows"] == 0, st
+        assert st["unsafe_rows"] == 0, st  # (first forward after sync_weights: no threshold guess yet)
     if case == "forced":
         assert st["repaired"] == B, st
     if case == "dup_atoms":

@@ -85,7 +85,7 @@ def test_cuda_path_replays_reference_run(name):
     assert ld["aux"] == 0.0 and ld["n_dead"] == 0.0
     assert rel_l2(eng.x_hat(x).cpu(), z["eval_x_hat"]) < TOL
     if cfg.activation == "topk":
-        assert eng.unsafe_rows() == 0
+        _assert_screen_clean(eng)
 
 
 @pytest.mark.parametrize("name", ["c1_topk_auxk_live", "tiny_topk_auxk_clamp"])
@@ -111,6 +111,14 @@ def test_fused_renorm_equals_start_of_step_normalize():
     a.normalize_w_dec()
     assert rel_l2(b.W_dec.cpu(), a.W_dec.cpu()) < 1e-6
     assert rel_l2(b.W_enc_t.cpu(), a.W_enc_t.cpu()) < 1e-6
+
+
+def _assert_screen_clean(eng):
+    """Every row the tensor-core screen could not certify was redone by the exact path; the only expected cause is a
+    threshold guess that verification rejected (a row or so per step by construction) -- no candidate-list overflow,
+    no observed error above the deterministic bound."""
+    st = eng.screen_stats()
+    assert st["unrepaired"] == 0 and st["bound_violations"] == 0 and st["unsafe_rows"] == st["guess_failed"], st
 
 
 # ---- mid-size parity against the oracle on seeded inputs (sizes the CPU oracle finishes in seconds) ----
@@ -207,8 +215,7 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
     for name, p in (("W_enc", eng.W_enc_t.t()), ("b_enc", eng.b_enc), ("W_dec", eng.W_dec), ("b_dec", eng.b_dec)):
         assert rel_l2(p.cpu(), getattr(st, name)) < tol, name
     if act == "topk":
-        st_ = eng.screen_stats()
-        assert st_["unrepaired"] == 0 and st_["unsafe_rows"] == 0, st_
+        _assert_screen_clean(eng)
     return eng
 
 

@@ -187,11 +187,16 @@ float* saev_b200_wnorm_rows(const saev_b200_handle* h, void* workspace);
 /* clip_grad_norm_(max_norm) + Adam(fused) step + optional decoder row renorm + fp16 operand refresh.
  *   g_eff = grads * grad_scale;  coef = min(1, max_norm / (||g_eff|| + 1e-6))  (max_norm <= 0: no clip)
  *   `step` is the 1-based Adam step count AFTER this update (bias corrections use it).
- *   gnorm_out (optional, device) receives ||g_eff||, the value clip_grad_norm_ returns. */
+ *   gnorm_out (optional, device) receives ||g_eff||, the value clip_grad_norm_ returns.
+ *   `parts`: SAEV_B200_ADAM_ENCODER (W_enc_t, b_enc and what the screen keeps of them), SAEV_B200_ADAM_DECODER (W_dec with
+ *   the renorm, b_dec, gnorm_out) or both.  The next forward's screen reads only the encoder side, so a caller may
+ *   run the decoder half on a second stream beside it (same step, lr, sumsq; the HBM-bound update hides behind the
+ *   tensor-bound screen); the decoder-only launch uses small blocks that fit beside a resident screen CTA. */
+enum { SAEV_B200_ADAM_ENCODER = 1, SAEV_B200_ADAM_DECODER = 2, SAEV_B200_ADAM_ALL = 3 };
 int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float* W_dec, float* b_dec,
                         const float* grads_flat, float* m_flat, float* v_flat, float lr, float beta1,
                         float beta2, float eps, int64_t step, float max_norm, float grad_scale,
-                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, void* workspace,
+                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, int32_t parts, void* workspace,
                         void* stream);
 
 /* Lazy dense views for saev's logging block (train.py:365-442). */

@@ -18,6 +18,7 @@ ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
 PHASE_A, PHASE_B, PHASE_ALL = 1, 2, 3
 PHASE_A_SCREEN, PHASE_A_REST = 4, 8
+ADAM_ENCODER, ADAM_DECODER, ADAM_ALL = 1, 2, 3
 STAGES = ("prep", "encode_gemm", "rescore", "decode", "loss", "csc", "wgrad", "bias_aux", "sumsq", "adam")
 
 
@@ -105,7 +106,7 @@ SIGNATURES = {
     "saev_b200_wnorm_rows": (_p, [_p, _p]),
     "saev_b200_adam_step": (
         C.c_int,
-        [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _p, _p],
+        [_p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _f, _i64, _f, _f, _p, _i32, _p, _i32, _p, _p],
     ),
     "saev_b200_densify": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "saev_b200_dense_f": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),

@@ -1060,10 +1060,11 @@ int saev_b200_grad_sumsq(saev_b200_handle* h, const float* grads_flat, int64_t n
 int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float* W_dec, float* b_dec,
                         const float* grads_flat, float* m_flat, float* v_flat, float lr, float beta1,
                         float beta2, float eps, int64_t step, float max_norm, float grad_scale,
-                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, void* workspace,
+                        const float* sumsq, int32_t renorm_w_dec, float* gnorm_out, int32_t parts, void* workspace,
                         void* stream) {
   const long long S = h->cfg.d_sae, D = h->cfg.d_model;
   if (step < 1) return fail(h, 61, "adam_step: step must be >= 1%s");
+  if (parts < 1 || parts > 3) return fail(h, 61, "adam_step: parts must be 1 (encoder), 2 (decoder) or 3 (both)%s");
   AdamArgs a;
   a.W_enc_t = W_enc_t;
   a.b_enc = b_enc;
@@ -1113,6 +1114,8 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.row_begin = sharded ? h->shard_begin : 0;
   a.row_end = sharded ? h->shard_end : static_cast<int>(S);
   a.b_enc_separately = sharded ? 1 : 0;
+  a.parts = parts;
+  a.small_blocks = parts == 2 ? 1 : 0;  // a decoder-only update is meant to run beside the next step's screen kernel
   StageTimer tm(h, SAEV_B200_STAGE_ADAM, static_cast<cudaStream_t>(stream));
   if (launch_adam(a, static_cast<cudaStream_t>(stream))) return fail(h, 62, "adam_step: launch failed%s");
   return check_cuda(h, "adam_step");

@@ -68,12 +68,12 @@ __host__ __device__ inline float screen_Q(const ScreenBound& s) { return 1.01f *
 // (measured at c3: 1.33 ms instead of 2.3 ms).  So every row starts from a GUESS of its k-th largest lower bound,
 //     L_guess_b = rho * ||x_b|| max_j||w_j|| - max_j|b_j|,
 // rho = a low quantile (GUESS_QUANTILE, shrunk by GUESS_SAFETY) of the same ratio over the rows of the PREVIOUS
-// forward (a 2048-bin device histogram filled by the re-score kernel).  The guess is verified, not trusted: the
+// forward (an 8192-bin device histogram filled by the re-score kernel).  The guess is verified, not trusted: the
 // re-score accepts a row only if it holds k candidates whose lower bounds reach L_guess_b (then L_guess_b really was a
 // lower bound of the exact k-th largest value and nothing was missed); any other row goes to the exact path.
-constexpr int GUESS_BINS = 2048;          // ratio in [-1, 1), bin width 2 / GUESS_BINS
+constexpr int GUESS_BINS = 8192;          // ratio in [-1, 1), bin width 2 / GUESS_BINS
 constexpr float GUESS_QUANTILE = 5e-4f;
-constexpr float GUESS_SAFETY = 0.03f;
+constexpr float GUESS_SAFETY = 0.015f;
 
 constexpr float FP16_MAX = 65504.f;  // encoder rows with a larger norm cannot be screened in fp16 (all rows repaired)
 
@@ -307,6 +307,8 @@ struct AdamArgs {
   float* gnorm_out;            // optional: clipped-from norm (what clip_grad_norm_ returns)
   int row_begin, row_end;      // dictionary rows this call updates (sharded optimizer; default all)
   int b_enc_separately;        // 1: update the whole b_enc vector with a separate kernel (not only [row_begin, row_end))
+  int parts;                   // 1: W_enc_t rows + b_enc (+ the screen's fp16 copy and norms), 2: W_dec rows + b_dec, 3: both
+  int small_blocks;            // 64-thread blocks (fit beside a resident screen CTA: a parts == 2 launch on a side stream)
 };
 int launch_adam(const AdamArgs& a, cudaStream_t s);
 

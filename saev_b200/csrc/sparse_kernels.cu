@@ -152,13 +152,19 @@ int launch_prep_x(const float* x, int B, int D, __half* x16, float* row_norm, fl
 // "admit more"); -inf when fewer than `min_rows` rows were recorded.  Clears the histogram.
 __global__ void __launch_bounds__(1024) screen_guess_kernel(int* __restrict__ hist, float quantile, float safety,
                                                             int min_rows, float* __restrict__ scalars) {
+  constexpr int PER = GUESS_BINS / 1024;  // consecutive bins per thread
   __shared__ int wsum[32];
   __shared__ int s_total;
+  __shared__ float s_q, s_med;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int c0 = hist[2 * t], c1 = hist[2 * t + 1];  // GUESS_BINS == 2048 == 2 * blockDim
-  hist[2 * t] = 0;
-  hist[2 * t + 1] = 0;
-  int incl = c0 + c1;
+  int c[PER], mine = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    c[i] = hist[PER * t + i];
+    hist[PER * t + i] = 0;
+    mine += c[i];
+  }
+  int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int v = __shfl_up_sync(FULL, incl, o);
@@ -178,21 +184,17 @@ __global__ void __launch_bounds__(1024) screen_guess_kernel(int* __restrict__ hi
   }
   __syncthreads();
   const int total = s_total;
-  const int before = (warp > 0 ? wsum[warp - 1] : 0) + incl - (c0 + c1);  // rows in lower bins
   if (t == 0 && total < min_rows) scalars[SC_RHO_GUESS] = -INFINITY;
   if (total < min_rows) return;
-  __shared__ float s_q, s_med;
   const int want = max(1, static_cast<int>(quantile * total));  // the `want`-th smallest ratio ...
   const int half = max(1, total / 2);                            // ... and the median
-  // the bins holding them: before < rank <= before + c0 (+ c1)
-  auto bin_of = [&](int rank) {
-    if (before < rank && rank <= before + c0) return 2 * t;
-    if (before + c0 < rank && rank <= before + c0 + c1) return 2 * t + 1;
-    return -1;
-  };
-  const int bq = bin_of(want), bm = bin_of(half);
-  if (bq >= 0) s_q = -1.f + 2.f * bq / GUESS_BINS;  // lower edges
-  if (bm >= 0) s_med = -1.f + 2.f * bm / GUESS_BINS;
+  int before = (warp > 0 ? wsum[warp - 1] : 0) + incl - mine;    // rows in lower bins
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {  // the bins holding them: before < rank <= before + c[i]; lower edges
+    if (before < want && want <= before + c[i]) s_q = -1.f + 2.f * (PER * t + i) / GUESS_BINS;
+    if (before < half && half <= before + c[i]) s_med = -1.f + 2.f * (PER * t + i) / GUESS_BINS;
+    before += c[i];
+  }
   __syncthreads();
   if (t == 0) {
     // shrink towards "admit more": relative safety, one bin of resolution, and a share of the distribution's own
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(1024) screen_guess_kernel(int* __restrict__ hi
   }
 }
 int launch_screen_guess(int* hist, float quantile, float safety, int min_rows, float* scalars, cudaStream_t s) {
-  static_assert(GUESS_BINS == 2048, "screen_guess_kernel assumes two bins per thread");
+  static_assert(GUESS_BINS % 1024 == 0, "screen_guess_kernel gives every thread GUESS_BINS / 1024 bins");
   screen_guess_kernel<<<1, 1024, 0, s>>>(hist, quantile, safety, min_rows, scalars);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
@@ -1663,14 +1665,14 @@ __device__ __forceinline__ float4 adam_4(float4 p, float4 g, float4& m, float4& 
 template <int VPL>
 __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = a.row_begin + blockIdx.x * 8 + warp;
+  const int j = a.row_begin + blockIdx.x * (blockDim.x >> 5) + warp;
   if (j >= a.row_end) return;
   const AdamScalars sc = adam_scalars(a);
   const int D4 = a.D >> 2;
   const long long SD = static_cast<long long>(a.S) * a.D;
   const long long ro = static_cast<long long>(j) * a.D;
   // ---- W_enc_t row (+ fp16 screen copy, + max row norm for the screen's error bound) ----
-  {
+  if (a.parts & 1) {
     float* mrow = a.m + ro;
     float* vrow = a.v + ro;
     float ssq = 0.f, ssq16 = 0.f, ssd = 0.f;
@@ -1707,7 +1709,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
     }
   }
   // ---- b_enc[j] (a sharded optimizer updates the whole bias vector on every rank instead) ----
-  if (lane == 0 && !a.b_enc_separately) {
+  if (lane == 0 && !a.b_enc_separately && (a.parts & 1)) {
     float m = a.m[SD + j], v = a.v[SD + j];
     const float nb = adam_1(a.b_enc[j], a.gb_enc[j], m, v, sc);
     a.b_enc[j] = nb;
@@ -1716,7 +1718,7 @@ __global__ void __launch_bounds__(256) adam_rows_kernel(AdamArgs a) {
     if (a.bias_abs_max != nullptr) atomicMax(reinterpret_cast<int*>(a.bias_abs_max), __float_as_int(fabsf(nb)));
   }
   // ---- W_dec row (+ renorm) ----
-  {
+  if (a.parts & 2) {
     float* mrow = a.m + SD + a.S + ro;
     float* vrow = a.v + SD + a.S + ro;
     float4 p[VPL];
@@ -1779,17 +1781,22 @@ __global__ void adam_bdec_kernel(AdamArgs a) {
 
 int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
-  if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
-  if (a.bias_abs_max != nullptr && cudaMemsetAsync(a.bias_abs_max, 0, 4, s) != cudaSuccess) return 23;
-  if (a.rho != nullptr && cudaMemsetAsync(a.rho, 0, 4, s) != cudaSuccess) return 23;
+  if (a.parts & 1) {
+    if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
+    if (a.bias_abs_max != nullptr && cudaMemsetAsync(a.bias_abs_max, 0, 4, s) != cudaSuccess) return 23;
+    if (a.rho != nullptr && cudaMemsetAsync(a.rho, 0, 4, s) != cudaSuccess) return 23;
+  }
   const int rows = a.row_end - a.row_begin;
-  if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + 7) / 8, 256, 0, s>>>(a)));
-  if (a.b_enc_separately) {
+  const int wpb = a.small_blocks ? 2 : 8;
+  if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + wpb - 1) / wpb, 32 * wpb, 0, s>>>(a)));
+  if (a.b_enc_separately && (a.parts & 1)) {
     adam_benc_kernel<<<(a.S + 255) / 256, 256, 0, s>>>(a);
     ++g_launch_count;
   }
-  adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
-  ++g_launch_count;
+  if (a.parts & 2) {
+    adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
+    ++g_launch_count;
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

@@ -91,6 +91,11 @@ class Engine:
         self.gW_enc_t, self.gb_enc, self.gW_dec, self.gb_dec = self._views(self.grads)
         self.step_count = 0
         self._last_B = 0
+        # decoder half of an Adam step that has been deferred to run beside the next forward's screen (train_step)
+        self._dec_pending: dict | None = None
+        self._side_stream: torch.cuda.Stream | None = None
+        self._ev_grads = torch.cuda.Event()
+        self._ev_dec = torch.cuda.Event()
 
     def _views(self, flat):
         S, D = self.S, self.D
@@ -138,6 +143,7 @@ class Engine:
     @torch.no_grad()
     def load_params(self, W_enc, b_enc, W_dec, b_dec) -> None:
         """Copy saev-layout parameters in (W_enc is [d_model, d_sae] as in saev; stored transposed)."""
+        self._dec_pending = None
         self.W_enc_t.copy_(W_enc.to(self.device, torch.float32).t())
         self.b_enc.copy_(b_enc.to(self.device, torch.float32))
         self.W_dec.copy_(W_dec.to(self.device, torch.float32))
@@ -149,6 +155,7 @@ class Engine:
         """saev's initialisation (modeling.py:306-329): W_dec = kaiming_uniform_([S, D]) (bound sqrt(6/D)),
         row-normalised; W_enc = W_dec.T; biases zero.  saev leaves the global RNG unseeded; `seed` makes
         it reproducible."""
+        self._dec_pending = None
         gen = torch.Generator(device=self.device)
         if seed is not None:
             gen.manual_seed(seed)
@@ -190,6 +197,7 @@ class Engine:
         return mean
 
     def normalize_w_dec(self) -> None:
+        self.flush()
         if not self.cfg.normalize_w_dec:
             return
         with torch.cuda.device(self.device):
@@ -197,6 +205,10 @@ class Engine:
 
     # ---- step pieces -------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0):
+        self.flush()  # (a decoder update deferred by train_step(overlap_decoder_update=True) runs first)
+        return self._forward(x, training=training, phase=phase, tokens_global=tokens_global)
+
+    def _forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0):
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
         B = x.shape[0]
         self._last_B = B
@@ -292,28 +304,72 @@ class Engine:
         return self._ws_tensor(self.lib.saev_b200_wnorm_scalar, torch.float32, 3)
 
     def adam_step(self, lr: float, *, max_norm: float = 1.0, grad_scale: float = 1.0, betas=(0.9, 0.999),
-                  eps: float = 1e-8, renorm_w_dec: bool = False) -> None:
-        self.step_count += 1
+                  eps: float = 1e-8, renorm_w_dec: bool = False, parts: int = _lib.ADAM_ALL, step: int | None = None) -> None:
+        """`parts`: encoder half, decoder half or both (see saev_b200_adam_step); `step`: the 1-based step count of
+        this update (default: advance the engine's counter -- only the first half of a split update does that)."""
+        if step is None:
+            self.step_count += 1
+            step = self.step_count
         with torch.cuda.device(self.device):
             self._ck(
                 self.lib.saev_b200_adam_step(
                     self.h, self.W_enc_t.data_ptr(), self.b_enc.data_ptr(), self.W_dec.data_ptr(), self.b_dec.data_ptr(),
                     self.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), lr, betas[0], betas[1], eps,
-                    self.step_count, max_norm, grad_scale, self.sumsq.data_ptr(), int(renorm_w_dec),
-                    self.gnorm.data_ptr(), self.workspace.data_ptr(), self._stream(),
+                    step, max_norm, grad_scale, self.sumsq.data_ptr(), int(renorm_w_dec),
+                    self.gnorm.data_ptr(), parts, self.workspace.data_ptr(), self._stream(),
                 )
             )
 
     def train_step(self, x: torch.Tensor, lr: float, *, max_norm: float = 1.0, fused_renorm: bool = False,
-                   pre_normalized: bool = False) -> torch.Tensor:
-        """One iteration of train.py:332-460 on a single GPU (no logging block)."""
-        if not pre_normalized:
+                   pre_normalized: bool = False, overlap_decoder_update: bool = False) -> torch.Tensor:
+        """One iteration of train.py:332-460 on a single GPU (no logging block).
+
+        `overlap_decoder_update` (needs the fused renorm): the decoder half of the Adam step -- W_dec, its moments and
+        the row renorm, 28 B/param of pure HBM traffic -- is not run at the end of this step but on a side stream
+        BESIDE the tensor-bound screen of the NEXT call (which reads only the encoder side); the re-score / decode of
+        that call wait for it.  Same arithmetic, same results; call `flush()` before reading W_dec / b_dec from
+        outside (checkpoint, evaluation)."""
+        renorm = fused_renorm and self.cfg.normalize_w_dec
+        if not overlap_decoder_update or (self.cfg.normalize_w_dec and not renorm) or self.cfg.activation != "topk":
+            self.flush()
+            if not pre_normalized:
+                self.normalize_w_dec()
+            self.forward(x, training=True)
+            self.backward(x)
+            self.grad_sumsq(local=True)
+            self.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
+            return self.losses
+        if not pre_normalized and self._dec_pending is None:
             self.normalize_w_dec()
-        self.forward(x, training=True)
+        self._forward(x, training=True, phase=_lib.PHASE_A_SCREEN)
+        self._launch_pending_decoder_update()  # enqueued AFTER the screen kernel: its CTAs get the SMs first
+        self._forward(x, training=True, phase=_lib.PHASE_A_REST | _lib.PHASE_B)
         self.backward(x)
         self.grad_sumsq(local=True)
-        self.adam_step(lr, max_norm=max_norm, renorm_w_dec=fused_renorm and self.cfg.normalize_w_dec)
+        self.adam_step(lr, max_norm=max_norm, parts=_lib.ADAM_ENCODER)
+        self._ev_grads.record(torch.cuda.current_stream(self.device))
+        self._dec_pending = dict(lr=lr, max_norm=max_norm, renorm=renorm, step=self.step_count)
         return self.losses
+
+    def _launch_pending_decoder_update(self) -> None:
+        p, self._dec_pending = self._dec_pending, None
+        if p is None:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_event(self._ev_grads)
+        with torch.cuda.stream(side):
+            self.adam_step(p["lr"], max_norm=p["max_norm"], renorm_w_dec=p["renorm"], parts=_lib.ADAM_DECODER, step=p["step"])
+            self._ev_dec.record(side)
+        main.wait_event(self._ev_dec)
+
+    def flush(self) -> None:
+        """Run a deferred decoder update now (on the current stream)."""
+        p, self._dec_pending = self._dec_pending, None
+        if p is not None:
+            self.adam_step(p["lr"], max_norm=p["max_norm"], renorm_w_dec=p["renorm"], parts=_lib.ADAM_DECODER, step=p["step"])
 
     # ---- lazy dense views ------------------------------------------------------------------
     def dense_f_x(self, B: int | None = None) -> torch.Tensor:
@@ -355,6 +411,7 @@ class Engine:
         return out
 
     def loss_dict(self) -> dict:
+        self.flush()
         vals = self.losses.tolist()  # host sync, like Loss.metrics() in saev (objectives.py:80-89)
         return dict(zip(LOSS_KEYS, vals))
 
@@ -391,6 +448,7 @@ class Engine:
         """The per-SAE `metrics/*` of saev's log block (train.py:380-423) for the batch of the last forward, as a
         device float64[8] in LOG_KEYS order (+ the coherence screen maximum).  No host sync; nothing of size [B, S]
         or [S, S] is formed."""
+        self.flush()
         B = x.shape[0]
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
         n = int(self.lib.saev_b200_log_scratch_bytes(self.h))

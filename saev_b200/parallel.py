@@ -31,11 +31,20 @@ from .engine import LOSS_KEYS, Engine
 
 class DataParallelTrainer:
     def __init__(self, engine: Engine, group=None, sharded: bool | None = None, n_chunks: int = 4,
-                 gather_group=None, reserved_sms: int = 0):
+                 gather_group=None, reserved_sms: int = 0, overlap_decoder_update: bool = False):
         """`gather_group` (sharded mode): a second process group (ideally created with few NCCL CTAs, e.g.
         `ProcessGroupNCCL.Options().config.max_ctas = 4`) on which the all-gathers of the fp32 rows run in the
         background, beside the top-k screen of the NEXT step, which then leaves `reserved_sms` SMs idle for them."""
         self.eng = engine
+        import os
+
+        # single rank: run the decoder half of Adam beside the next step's screen (Engine.train_step).  Measured at c3
+        # (profiles/README.md): 4.33 instead of 4.37 ms/step -- the update has to fit into the ~6 K registers per SM
+        # the resident screen CTA leaves free (one 64-thread block), which stretches it over the whole screen, so it
+        # is off by default; SAEV_B200_OVERLAP_ADAM=1 turns it on.
+        self.overlap_decoder_update = overlap_decoder_update or os.environ.get("SAEV_B200_OVERLAP_ADAM", "0") == "1"
+        self._use_hp = os.environ.get("SAEV_B200_HP_STREAM", "1") != "0"
+        self._hp_stream = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -77,6 +86,24 @@ class DataParallelTrainer:
         Returns the device tensor of this rank's loss partials (see `global_losses`)."""
         eng, g = self.eng, self.group
         tokens_global = x.shape[0] * self.world  # equal per-rank batches (the loader guarantees it)
+        if self.world == 1 and self.overlap_decoder_update and hasattr(eng, "train_step"):
+            # single rank: the decoder half of Adam runs beside the next step's screen (Engine.train_step)
+            # The step runs on a HIGH-priority stream of its own: the deferred decoder update sits on a default-priority
+            # side stream, and the block scheduler must hand free SMs to the screen kernel's CTAs first.
+            cur = torch.cuda.current_stream(x.device)
+            if self._hp_stream is None and self._use_hp:
+                self._hp_stream = torch.cuda.Stream(device=x.device, priority=-1)
+            if self._hp_stream is not None:
+                self._hp_stream.wait_stream(cur)
+                with torch.cuda.stream(self._hp_stream):
+                    out = eng.train_step(x, lr, max_norm=max_norm, fused_renorm=fused_renorm,
+                                         pre_normalized=self._w_dec_normalized, overlap_decoder_update=True)
+                cur.wait_stream(self._hp_stream)
+            else:
+                out = eng.train_step(x, lr, max_norm=max_norm, fused_renorm=fused_renorm,
+                                     pre_normalized=self._w_dec_normalized, overlap_decoder_update=True)
+            self._w_dec_normalized = fused_renorm and eng.cfg.normalize_w_dec
+            return out
         if not self._w_dec_normalized:
             eng.normalize_w_dec()
         if self.world == 1:
@@ -144,6 +171,8 @@ class DataParallelTrainer:
         for wk in self._pending:
             wk.wait()
         self._pending = []
+        if hasattr(self.eng, "flush"):
+            self.eng.flush()
 
     def global_losses(self) -> dict:
         """Loss scalars of the global batch (host sync; call on log steps only)."""

@@ -276,3 +276,38 @@ def test_staged_backward_equals_one_shot_backward(fuse, monkeypatch):
             e.grad_sumsq()
             e.adam_step(1e-3, max_norm=1.0)
     assert int(a.losses[5]) > 0, "the case must exercise AuxK"
+
+
+def test_overlapped_decoder_update_is_the_same_step(monkeypatch):
+    """Engine.train_step(overlap_decoder_update=True) defers the decoder half of Adam to a side stream beside the next
+    forward's screen: same kernels on the same data, so parameters, moments and losses must be IDENTICAL to the
+    in-order step, including across a flush() in the middle and with AuxK live.  (One AuxK implementation is pinned:
+    the automatic choice between the two depends on when a lagged device-to-host read lands, i.e. on host timing.)"""
+    from saev_b200.engine import Engine, EngineConfig
+
+    monkeypatch.setenv("SAEV_B200_AUX", "sgemm")
+    D, S, K, B = 256, 4096, 16, 1024
+    g = torch.Generator().manual_seed(5)
+    basis = torch.randn(12, D, generator=g)
+    xs = [(torch.randn(B, 12, generator=g) @ basis / 3 + 0.1 * torch.randn(B, D, generator=g)).cuda() for _ in range(7)]
+    engs = []
+    for _ in range(2):
+        e = Engine(EngineConfig(d_model=D, d_sae=S, top_k=K, aux=True, k_aux=64, dead_threshold_tokens=2 * B, max_batch=B))
+        e.init_params(seed=3)
+        engs.append(e)
+    a, b = engs
+    losses = []
+    for i, x in enumerate(xs):
+        lr = 1e-3 * min(i, 3) / 3
+        a.train_step(x, lr, fused_renorm=True, pre_normalized=i > 0)
+        b.train_step(x, lr, fused_renorm=True, pre_normalized=i > 0, overlap_decoder_update=True)
+        if i == 3:
+            b.flush()  # e.g. a checkpoint in the middle of training
+            assert torch.equal(a.W_dec, b.W_dec)
+        losses.append((a.loss_dict(), b.loss_dict()))
+    for la, lb in losses:
+        assert la == lb
+    assert int(a.losses[5]) > 0, "the case must exercise AuxK"
+    b.flush()
+    for name in ("params", "m", "v", "toks_since_active"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name

@@ -295,11 +295,12 @@ def make_bench_shards(D, B, n_batches, rank):
     return root
 
 
-def workload_name(w, D, S, K, B, n_prefixes=1):
+def workload_name(w, D, S, K, B, n_prefixes=1, k_aux=512, dead_threshold=10_000_000):
     act = f"TopK k={K}" if K else "ReLU + L1Sparsity(4e-4)"
     mat = f"Matryoshka({n_prefixes} prefixes) " if n_prefixes > 1 else ""
-    return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective {mat}MSE+AuxK(k_aux=512, alpha=1/32, "
-            f"dead_threshold=10M tokens), remove_parallel_grads, clip 1.0, Adam, lr warmup; Gaussian activations")
+    thr = f"{dead_threshold // 1_000_000}M" if dead_threshold % 1_000_000 == 0 else f"{dead_threshold // 1000}k"
+    return (f"{w}: d_model={D} d_sae={S} {act} batch={B}/GPU, objective {mat}MSE+AuxK(k_aux={k_aux}, alpha=1/32, "
+            f"dead_threshold={thr} tokens), remove_parallel_grads, clip 1.0, Adam, lr warmup; Gaussian activations")
 
 
 def main():
@@ -317,13 +318,19 @@ def main():
     ap.add_argument("--preheat-s", type=float, default=2.0,
                     help="seconds of untimed steps before the timed region (clocks / power settle; beyond --warmup)")
     ap.add_argument("--no-aux", action="store_true")
-    ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap"],
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "chunked", "plain", "sharded", "sharded-overlap", "sharded-chunked"],
                     help="gradient exchange for N > 1 (see saev_b200/parallel.py)")
     ap.add_argument("--dense-features", type=int, default=0,
                     help="diagnostic (not the headline workload): give this many atoms a large encoder bias so that they "
                          "fire on every row, like the dense features of a real run")
     ap.add_argument("--n-prefixes", type=int, default=1,
                     help="Matryoshka prefixes (1 = the north-star objective; 10 = saev's default objective)")
+    ap.add_argument("--dead-threshold", type=int, default=10_000_000,
+                    help="Matryoshka.dead_threshold_tokens (the c5 AuxK sweep: 10M / 1M / 100k)")
+    ap.add_argument("--k-aux", type=int, default=512, help="AuxK.k_aux (the c5 AuxK sweep: 256 / 512 / 1024)")
+    ap.add_argument("--dead-atoms", type=int, default=0,
+                    help="diagnostic: give this many atoms a large negative encoder bias so that they never fire and die "
+                         "once dead_threshold_tokens have passed (AuxK then has work to do)")
     ap.add_argument("--gather-ctas", type=int, default=16)
     ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
@@ -361,25 +368,32 @@ def main():
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation="topk" if K else "relu",
-                              l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=512, aux_alpha=1 / 32,
-                              dead_threshold_tokens=10_000_000, max_batch=B, max_prefixes=max(1, args.n_prefixes)),
+                              l1_coeff=0.0 if K else 4e-4, aux=not args.no_aux, k_aux=args.k_aux, aux_alpha=1 / 32,
+                              dead_threshold_tokens=args.dead_threshold, max_batch=B,
+                              max_prefixes=max(1, args.n_prefixes)),
                  device=dev)
     eng.init_params(seed=0)
     if args.dense_features > 0:
         eng.b_enc[:: max(1, S // args.dense_features)][: args.dense_features] = 8.0
+    if args.dead_atoms > 0:
+        eng.b_enc[1 :: max(1, S // args.dead_atoms)][: args.dead_atoms] = -1e3
+    if args.dense_features > 0 or args.dead_atoms > 0:
+        eng.sync_weights()
+    if K == 0 and world > 1:
+        args.dp_mode = "plain"  # the dense (ReLU) path exchanges the whole gradient bucket with one all-reduce
     if args.dp_mode == "auto":
         # measured on B200 (profiles/README.md): at 2 ranks the chunked all-reduce hidden behind the weight-gradient
         # kernel wins (5.47 ms); from 4 ranks on the row-sharded optimizer whose fp32 all-gathers run beside the next
         # step's screen wins (N=4: 5.40 vs 5.91 ms plain; N=8: 5.28 vs 5.92 ms)
         args.dp_mode = "chunked" if world <= 2 else "sharded-overlap"
     gather_group = None
-    if world > 1 and args.dp_mode == "sharded-overlap":
+    if world > 1 and args.dp_mode in ("sharded-overlap", "sharded-chunked"):
         gopts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         gopts.config.max_ctas = args.gather_ctas
         gopts.config.min_ctas = 1
         gather_group = dist.new_group(backend="nccl", pg_options=gopts)
     tr = DataParallelTrainer(eng, sharded=args.dp_mode.startswith("sharded"),
-                             n_chunks=4 if args.dp_mode == "chunked" else 1, gather_group=gather_group,
+                             n_chunks=4 if args.dp_mode in ("chunked", "sharded-chunked") else 1, gather_group=gather_group,
                              reserved_sms=args.reserved_sms)
     tr.broadcast_params(0)
 
@@ -573,9 +587,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload_name(args.workload, D, S, K, B, args.n_prefixes),
+                "workload": workload_name(args.workload, D, S, K, B, args.n_prefixes, args.k_aux, args.dead_threshold),
                 "global_batch": world * B,
                 **({"dense_features": args.dense_features} if args.dense_features > 0 else {}),
+                **({"dead_atoms": args.dead_atoms} if args.dead_atoms > 0 else {}),
                 "parallelism": f"dp{world}" + (f" ({args.dp_mode} gradient exchange)" if world > 1 else ""),
                 "preheat_s": args.preheat_s,
                 "precision": ("fp16 tcgen05 screen of the encoder contraction (deterministic error bound) + exact fp32 "

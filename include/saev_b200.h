@@ -51,7 +51,10 @@ enum {
   SAEV_B200_PHASE_B = 2,
   SAEV_B200_PHASE_ALL = 3,
   SAEV_B200_PHASE_A_SCREEN = 4, /* first half of A: operand prep + tcgen05 screen (reads only the fp16 operand copy) */
-  SAEV_B200_PHASE_A_REST = 8    /* second half of A: exact re-score + decode (reads the fp32 W_enc_t / W_dec) */
+  SAEV_B200_PHASE_A_REST = 8,   /* second half of A: exact re-score + decode (reads the fp32 W_enc_t / W_dec) */
+  SAEV_B200_PHASE_A_RESCORE = 16, /* ... or in two calls: the re-score alone (the activity flags are final after it: a
+                                     data-parallel caller starts their all-reduce here, beside the decode) */
+  SAEV_B200_PHASE_A_DECODE = 32   /* ... and the decode */
 };
 
 typedef struct saev_b200_cfg {
@@ -191,8 +194,12 @@ float* saev_b200_wnorm_rows(const saev_b200_handle* h, void* workspace);
  *   `parts`: SAEV_B200_ADAM_ENCODER (W_enc_t, b_enc and what the screen keeps of them), SAEV_B200_ADAM_DECODER (W_dec with
  *   the renorm, b_dec, gnorm_out) or both.  The next forward's screen reads only the encoder side, so a caller may
  *   run the decoder half on a second stream beside it (same step, lr, sumsq; the HBM-bound update hides behind the
- *   tensor-bound screen); the decoder-only launch uses small blocks that fit beside a resident screen CTA. */
-enum { SAEV_B200_ADAM_ENCODER = 1, SAEV_B200_ADAM_DECODER = 2, SAEV_B200_ADAM_ALL = 3 };
+ *   tensor-bound screen); the decoder-only launch uses small blocks that fit beside a resident screen CTA.
+ *   A sharded optimizer that owns SEVERAL row ranges (saev_b200_set_optimizer_shard before each call) passes
+ *   SAEV_B200_ADAM_ALL for the first range and ALL | ROWS_ONLY | KEEP_MAXIMA for the others: the bias vectors are updated
+ *   once, and the dictionary-wide maxima the screen's error bound uses accumulate over the ranges. */
+enum { SAEV_B200_ADAM_ENCODER = 1, SAEV_B200_ADAM_DECODER = 2, SAEV_B200_ADAM_ALL = 3, SAEV_B200_ADAM_ROWS_ONLY = 4,
+       SAEV_B200_ADAM_KEEP_MAXIMA = 8 };
 int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float* W_dec, float* b_dec,
                         const float* grads_flat, float* m_flat, float* v_flat, float lr, float beta1,
                         float beta2, float eps, int64_t step, float max_norm, float grad_scale,

@@ -17,8 +17,8 @@ ABI_VERSION = 10
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
 PHASE_A, PHASE_B, PHASE_ALL = 1, 2, 3
-PHASE_A_SCREEN, PHASE_A_REST = 4, 8
-ADAM_ENCODER, ADAM_DECODER, ADAM_ALL = 1, 2, 3
+PHASE_A_SCREEN, PHASE_A_REST, PHASE_A_RESCORE, PHASE_A_DECODE = 4, 8, 16, 32
+ADAM_ENCODER, ADAM_DECODER, ADAM_ALL, ADAM_ROWS_ONLY, ADAM_KEEP_MAXIMA = 1, 2, 3, 4, 8
 STAGES = ("prep", "encode_gemm", "rescore", "decode", "loss", "csc", "wgrad", "bias_aux", "sumsq", "adam")
 
 

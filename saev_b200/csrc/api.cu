@@ -624,8 +624,11 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
   const bool tracked = training && toks_since_active != nullptr;
 
   const bool do_screen = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_SCREEN)) != 0;
-  const bool do_rest = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_REST)) != 0;
-  if ((phase & (SAEV_B200_PHASE_A_SCREEN | SAEV_B200_PHASE_A_REST)) && c.act_kind == SAEV_B200_ACT_RELU)
+  const bool do_rescore = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_REST | SAEV_B200_PHASE_A_RESCORE)) != 0;
+  const bool do_decode = (phase & (SAEV_B200_PHASE_A | SAEV_B200_PHASE_A_REST | SAEV_B200_PHASE_A_DECODE)) != 0;
+  const bool do_rest = do_rescore || do_decode;
+  if ((phase & (SAEV_B200_PHASE_A_SCREEN | SAEV_B200_PHASE_A_REST | SAEV_B200_PHASE_A_RESCORE | SAEV_B200_PHASE_A_DECODE)) &&
+      c.act_kind == SAEV_B200_ACT_RELU)
     return fail(h, 40, "forward: the split phase A (screen / rest) exists for the TopK path only%s");
   if ((phase & SAEV_B200_PHASE_A) && c.act_kind == SAEV_B200_ACT_RELU) {
     cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
@@ -681,7 +684,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
       }
     }
 
-    if (do_rest) {
+    if (do_rescore) {
     cudaMemsetAsync(at<int>(workspace, w.active), 0, static_cast<size_t>(S) * 4, s);
     if (training) cudaMemsetAsync(at<int>(workspace, w.feat_count), 0, static_cast<size_t>(S) * 4, s);
     RescoreArgs r;
@@ -714,7 +717,8 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
       if (launch_rescore_topk(r, s)) return fail(h, 43, "forward: rescore launch failed%s");
       if (launch_repair_topk(r, s)) return fail(h, 43, "forward: exact repair launch failed%s");
     }
-
+    }  // do_rescore
+    if (do_decode) {
     DecodeArgs d;
     d.x = x;
     d.topk_idx = topk_idx;
@@ -741,7 +745,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     }
     h->last_forward_training = training != 0;
     h->last_forward_tracked = false;
-    }  // do_rest
+    }  // do_decode
   }
 
   if (phase & SAEV_B200_PHASE_B) {
@@ -1015,7 +1019,7 @@ int saev_b200_grad_sumsq_ranges(saev_b200_handle* h, const float* grads_flat, in
                                 const int64_t* ends, float* sumsq_out, void* workspace, void* stream) {
   StageTimer tm(h, SAEV_B200_STAGE_SUMSQ, static_cast<cudaStream_t>(stream));
   long long b[SUMSQ_MAX_RANGES], e[SUMSQ_MAX_RANGES];
-  if (n_ranges < 1 || n_ranges > SUMSQ_MAX_RANGES) return fail(h, 65, "grad_sumsq_ranges: 1..4 ranges%s");
+  if (n_ranges < 1 || n_ranges > SUMSQ_MAX_RANGES) return fail(h, 65, "grad_sumsq_ranges: 1..18 ranges%s");
   for (int r = 0; r < n_ranges; ++r) {
     if (begins[r] % 4 != 0 || ends[r] < begins[r]) return fail(h, 65, "grad_sumsq_ranges: begins must be multiples of 4%s");
     b[r] = begins[r];
@@ -1064,7 +1068,7 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
                         void* stream) {
   const long long S = h->cfg.d_sae, D = h->cfg.d_model;
   if (step < 1) return fail(h, 61, "adam_step: step must be >= 1%s");
-  if (parts < 1 || parts > 3) return fail(h, 61, "adam_step: parts must be 1 (encoder), 2 (decoder) or 3 (both)%s");
+  if ((parts & 3) == 0 || parts > 15) return fail(h, 61, "adam_step: parts must select the encoder (1) and / or decoder (2) half%s");
   AdamArgs a;
   a.W_enc_t = W_enc_t;
   a.b_enc = b_enc;
@@ -1115,7 +1119,7 @@ int saev_b200_adam_step(saev_b200_handle* h, float* W_enc_t, float* b_enc, float
   a.row_end = sharded ? h->shard_end : static_cast<int>(S);
   a.b_enc_separately = sharded ? 1 : 0;
   a.parts = parts;
-  a.small_blocks = parts == 2 ? 1 : 0;  // a decoder-only update is meant to run beside the next step's screen kernel
+  a.small_blocks = (parts & 3) == 2 ? 1 : 0;  // a decoder-only update is meant to run beside the next step's screen kernel
   StageTimer tm(h, SAEV_B200_STAGE_ADAM, static_cast<cudaStream_t>(stream));
   if (launch_adam(a, static_cast<cudaStream_t>(stream))) return fail(h, 62, "adam_step: launch failed%s");
   return check_cuda(h, "adam_step");

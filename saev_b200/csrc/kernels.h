@@ -284,7 +284,7 @@ int launch_colsum(const float* src, int B, int D, float scale, int accumulate, f
 int colsum_partial_rows(int B);
 
 int launch_sumsq(const float* g, long long n, double* partial, float* out_sumsq, cudaStream_t s);
-constexpr int SUMSQ_MAX_RANGES = 4;
+constexpr int SUMSQ_MAX_RANGES = 18;
 // sum of squares over up to SUMSQ_MAX_RANGES sub-ranges [begin, end) (element offsets, begins multiples of 4) of g;
 // partial must hold SUMSQ_MAX_RANGES * 592 doubles
 int launch_sumsq_ranges(const float* g, int n_ranges, const long long* begins, const long long* ends, double* partial,
@@ -307,7 +307,10 @@ struct AdamArgs {
   float* gnorm_out;            // optional: clipped-from norm (what clip_grad_norm_ returns)
   int row_begin, row_end;      // dictionary rows this call updates (sharded optimizer; default all)
   int b_enc_separately;        // 1: update the whole b_enc vector with a separate kernel (not only [row_begin, row_end))
-  int parts;                   // 1: W_enc_t rows + b_enc (+ the screen's fp16 copy and norms), 2: W_dec rows + b_dec, 3: both
+  int parts;                   // 1: W_enc_t rows + b_enc (+ the screen's fp16 copy and norms), 2: W_dec rows + b_dec, 3: both;
+                               // + 4: rows only (no whole-vector bias kernels), + 8: keep (do not zero) the screen's
+                               // dictionary-wide maxima -- a sharded optimizer that owns several row ranges calls once
+                               // per range: first call 3, the others 3 + 4 + 8
   int small_blocks;            // 64-thread blocks (fit beside a resident screen CTA: a parts == 2 launch on a side stream)
 };
 int launch_adam(const AdamArgs& a, cudaStream_t s);

@@ -1781,7 +1781,7 @@ __global__ void adam_bdec_kernel(AdamArgs a) {
 
 int launch_adam(const AdamArgs& a, cudaStream_t s) {
   if (a.D % 4 || a.S % 4) return 21;
-  if (a.parts & 1) {
+  if ((a.parts & 1) && !(a.parts & 8)) {
     if (a.wnorm_sq_max != nullptr && cudaMemsetAsync(a.wnorm_sq_max, 0, 4, s) != cudaSuccess) return 23;
     if (a.bias_abs_max != nullptr && cudaMemsetAsync(a.bias_abs_max, 0, 4, s) != cudaSuccess) return 23;
     if (a.rho != nullptr && cudaMemsetAsync(a.rho, 0, 4, s) != cudaSuccess) return 23;
@@ -1789,11 +1789,11 @@ int launch_adam(const AdamArgs& a, cudaStream_t s) {
   const int rows = a.row_end - a.row_begin;
   const int wpb = a.small_blocks ? 2 : 8;
   if (rows > 0) SB_DISPATCH_VPL(a.D, (adam_rows_kernel<VPL><<<(rows + wpb - 1) / wpb, 32 * wpb, 0, s>>>(a)));
-  if (a.b_enc_separately && (a.parts & 1)) {
+  if (a.b_enc_separately && (a.parts & 1) && !(a.parts & 4)) {
     adam_benc_kernel<<<(a.S + 255) / 256, 256, 0, s>>>(a);
     ++g_launch_count;
   }
-  if (a.parts & 2) {
+  if ((a.parts & 2) && !(a.parts & 4)) {
     adam_bdec_kernel<<<(a.D + 255) / 256, 256, 0, s>>>(a);
     ++g_launch_count;
   }

@@ -44,6 +44,8 @@ class DataParallelTrainer:
         # is off by default; SAEV_B200_OVERLAP_ADAM=1 turns it on.
         self.overlap_decoder_update = overlap_decoder_update or os.environ.get("SAEV_B200_OVERLAP_ADAM", "0") == "1"
         self._use_hp = os.environ.get("SAEV_B200_HP_STREAM", "1") != "0"
+        self._split_decode = os.environ.get("SAEV_B200_DP_SPLIT_DECODE", "1") != "0" and hasattr(engine, "wnorm_rows")
+        self._small = None  # staging for the two bias gradients (one all-reduce instead of two)
         self._hp_stream = None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -62,13 +64,25 @@ class DataParallelTrainer:
             step_rows = -(-S // n_chunks)
             step_rows = (step_rows + 7) // 8 * 8
             self.chunks = [(r, min(S, r + step_rows)) for r in range(0, S, step_rows)]
+        self.shard_chunks = []  # sharded + chunked: [(chunk_begin, chunk_end, own_begin, own_end)]
         if self.sharded:
-            rows = S // self.world
-            self.j0, self.j1 = self.rank * rows, (self.rank + 1) * rows
-            engine.set_optimizer_shard(self.j0, self.j1)
+            C = n_chunks if (n_chunks > 1 and S % (n_chunks * self.world * 8) == 0 and hasattr(engine, "backward_stage")) else 1
             D = engine.D
             SD = S * D
-            self._ranges = [(self.j0 * D, self.j1 * D), (SD + S + self.j0 * D, SD + S + self.j1 * D)]
+            if C > 1:
+                per_chunk, per_rank = S // C, S // (C * self.world)
+                for c in range(C):
+                    c0 = c * per_chunk
+                    self.shard_chunks.append((c0, c0 + per_chunk, c0 + self.rank * per_rank, c0 + (self.rank + 1) * per_rank))
+                self._ranges = []
+                for _, _, o0, o1 in self.shard_chunks:
+                    self._ranges += [(o0 * D, o1 * D), (SD + S + o0 * D, SD + S + o1 * D)]
+                self.j0, self.j1 = self.shard_chunks[0][2], self.shard_chunks[0][3]
+            else:
+                rows = S // self.world
+                self.j0, self.j1 = self.rank * rows, (self.rank + 1) * rows
+                self._ranges = [(self.j0 * D, self.j1 * D), (SD + S + self.j0 * D, SD + S + self.j1 * D)]
+            engine.set_optimizer_shard(self.j0, self.j1)
             if self.rank == 0:  # the (all-reduced) bias gradients are counted once
                 self._ranges += [(SD, SD + S), (2 * SD + S, 2 * SD + S + D)]
             if gather_group is not None and reserved_sms > 0:
@@ -109,17 +123,37 @@ class DataParallelTrainer:
         if self.world == 1:
             eng.forward(x, training=True, tokens_global=tokens_global)
         else:
-            if self._pending:
-                # the screen needs only the fp16 operand copy (gathered synchronously at the end of the last step);
-                # the fp32 rows are still arriving on the gather group's stream
-                eng.forward(x, training=True, phase=_lib.PHASE_A_SCREEN, tokens_global=tokens_global)
-                self.finish()
-                eng.forward(x, training=True, phase=_lib.PHASE_A_REST, tokens_global=tokens_global)
-            else:
+            topk = getattr(eng.cfg, "activation", "topk") == "topk"
+            if not topk:  # the dense (ReLU) path has no split phase A
                 eng.forward(x, training=True, phase=_lib.PHASE_A, tokens_global=tokens_global)
-            dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g)
-            eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
+                dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g)
+                eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
+            else:
+                self._forward_topk(x, tokens_global)
         renorm = fused_renorm and eng.cfg.normalize_w_dec
+        return self._backward_and_update(x, lr, max_norm, renorm, tokens_global)
+
+    def _forward_topk(self, x, tokens_global):
+        """Objective forward on this rank's rows, with the activity flags of all ranks folded in between phases."""
+        eng, g = self.eng, self.group
+        # the screen needs only the fp16 operand copy (gathered synchronously at the end of the last step); the fp32
+        # rows may still be arriving on the gather group's stream
+        eng.forward(x, training=True, phase=_lib.PHASE_A_SCREEN, tokens_global=tokens_global)
+        if self._pending:
+            self.finish()
+        if self._split_decode:
+            # the activity flags are final after the re-score: their MAX all-reduce runs beside the decode
+            eng.forward(x, training=True, phase=_lib.PHASE_A_RESCORE, tokens_global=tokens_global)
+            wk = dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g, async_op=True)
+            eng.forward(x, training=True, phase=_lib.PHASE_A_DECODE, tokens_global=tokens_global)
+            wk.wait()
+        else:
+            eng.forward(x, training=True, phase=_lib.PHASE_A_REST, tokens_global=tokens_global)
+            dist.all_reduce(eng.active_flags(), op=dist.ReduceOp.MAX, group=g)
+        eng.forward(x, training=True, phase=_lib.PHASE_B, tokens_global=tokens_global)
+
+    def _backward_and_update(self, x, lr, max_norm, renorm, tokens_global):
+        eng, g = self.eng, self.group
         if self.chunks:
             eng.backward_stage(x, 0, tokens_global=tokens_global)
             works = []
@@ -135,6 +169,8 @@ class DataParallelTrainer:
             eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)
             self._w_dec_normalized = renorm
             return eng.losses
+        if self.shard_chunks:
+            return self._step_sharded_chunked(x, lr, max_norm, renorm, tokens_global)
         eng.backward(x, tokens_global=tokens_global)
         if not self.sharded:
             if self.world > 1:
@@ -145,8 +181,7 @@ class DataParallelTrainer:
             j0, j1 = self.j0, self.j1
             dist.reduce_scatter_tensor(eng.gW_enc_t[j0:j1], eng.gW_enc_t, op=dist.ReduceOp.SUM, group=g)
             dist.reduce_scatter_tensor(eng.gW_dec[j0:j1], eng.gW_dec, op=dist.ReduceOp.SUM, group=g)
-            dist.all_reduce(eng.gb_enc, op=dist.ReduceOp.SUM, group=g)
-            dist.all_reduce(eng.gb_dec, op=dist.ReduceOp.SUM, group=g)
+            self._all_reduce_bias_grads()
             eng.grad_sumsq_ranges(self._ranges)
             dist.all_reduce(eng.sumsq, op=dist.ReduceOp.SUM, group=g)
             eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm)  # rows [j0, j1) + both bias vectors
@@ -164,6 +199,59 @@ class DataParallelTrainer:
                 dist.all_gather_into_tensor(eng.W_dec, eng.W_dec[j0:j1], group=g)
         self._w_dec_normalized = renorm
         return eng.losses
+
+    def _step_sharded_chunked(self, x, lr, max_norm, renorm, tokens_global):
+        """Backward + exchange + optimizer of `step` for the sharded optimizer with interleaved chunk ownership."""
+        eng, g = self.eng, self.group
+        eng.backward_stage(x, 0, tokens_global=tokens_global)
+        works = []
+        for c0, c1, o0, o1 in self.shard_chunks:
+            eng.backward_stage(x, 1, c0, c1, tokens_global=tokens_global)
+            works.append(dist.reduce_scatter_tensor(eng.gW_enc_t[o0:o1], eng.gW_enc_t[c0:c1], op=dist.ReduceOp.SUM,
+                                                    group=g, async_op=True))
+            works.append(dist.reduce_scatter_tensor(eng.gW_dec[o0:o1], eng.gW_dec[c0:c1], op=dist.ReduceOp.SUM, group=g,
+                                                    async_op=True))
+        works.append(dist.all_reduce(eng.gb_enc, op=dist.ReduceOp.SUM, group=g, async_op=True))
+        works.append(dist.all_reduce(eng.gb_dec, op=dist.ReduceOp.SUM, group=g, async_op=True))
+        for wk in works:
+            wk.wait()
+        eng.grad_sumsq_ranges(self._ranges)
+        dist.all_reduce(eng.sumsq, op=dist.ReduceOp.SUM, group=g)
+        step = eng.step_count + 1
+        for i, (_, _, o0, o1) in enumerate(self.shard_chunks):
+            eng.set_optimizer_shard(o0, o1)
+            parts = _lib.ADAM_ALL if i == 0 else (_lib.ADAM_ALL | _lib.ADAM_ROWS_ONLY | _lib.ADAM_KEEP_MAXIMA)
+            eng.adam_step(lr, max_norm=max_norm, renorm_w_dec=renorm, parts=parts, step=None if i == 0 else step)
+        shadow, wn = eng.shadow_weights(), eng.wnorm_rows()
+        for c0, c1, o0, o1 in self.shard_chunks:
+            dist.all_gather_into_tensor(shadow[c0:c1], shadow[o0:o1], group=g)
+            dist.all_gather_into_tensor(wn[c0:c1], wn[o0:o1], group=g)
+        dist.all_reduce(eng.wnorm_scalar(), op=dist.ReduceOp.MAX, group=g)
+        gg = self.gather_group if self.gather_group is not None else g
+        pend = []
+        for c0, c1, o0, o1 in self.shard_chunks:
+            pend.append(dist.all_gather_into_tensor(eng.W_enc_t[c0:c1], eng.W_enc_t[o0:o1], group=gg, async_op=True))
+            pend.append(dist.all_gather_into_tensor(eng.W_dec[c0:c1], eng.W_dec[o0:o1], group=gg, async_op=True))
+        if self.gather_group is not None:
+            self._pending = pend
+        else:
+            for wk in pend:
+                wk.wait()
+        self._w_dec_normalized = renorm
+        return eng.losses
+
+    def _all_reduce_bias_grads(self) -> None:
+        """gb_enc and gb_dec in ONE all-reduce (they are not adjacent in the bucket; every small collective costs
+        ~30 us of latency at 8 ranks)."""
+        eng, g = self.eng, self.group
+        S, D = eng.gb_enc.numel(), eng.gb_dec.numel()
+        if self._small is None:
+            self._small = torch.empty(S + D, dtype=eng.gb_enc.dtype, device=eng.gb_enc.device)
+        self._small[:S].copy_(eng.gb_enc)
+        self._small[S:].copy_(eng.gb_dec)
+        dist.all_reduce(self._small, op=dist.ReduceOp.SUM, group=g)
+        eng.gb_enc.copy_(self._small[:S])
+        eng.gb_dec.copy_(self._small[S:])
 
     def finish(self) -> None:
         """Make the current stream wait for the background all-gathers of the last step (call before anything reads

@@ -39,12 +39,14 @@ per = B // world
 gopts = dist.ProcessGroupNCCL.Options()
 gopts.config.max_ctas = 4
 bg = dist.new_group(backend="nccl", pg_options=gopts)
-for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None), (True, 1, bg)):
+for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None), (True, 1, bg), (True, 4, None),
+                              (True, 4, bg)):
     eng = Engine(cfg, device=dev)
     eng.init_params(seed=7)
     tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks, gather_group=gg, reserved_sms=4 if gg else 0)
     tr.broadcast_params(0)
-    assert tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1)
+    assert tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1 and not sharded)
+    assert bool(tr.shard_chunks) == (n_chunks > 1 and sharded)
     sharded = f"{sharded}/chunks={n_chunks}/background-gather={gg is not None}"
     for i, (x, lr) in enumerate(zip(xs, lrs)):
         tr.step(x[rank * per:(rank + 1) * per].contiguous(), lr, fused_renorm=True)
@@ -60,7 +62,8 @@ for sharded, n_chunks, gg in ((False, 4, None), (False, 1, None), (True, 1, None
     errs = {n: rel(a, b) for n, a, b in (("W_enc_t", eng.W_enc_t, ref.W_enc_t), ("b_enc", eng.b_enc, ref.b_enc),
                                          ("W_dec", eng.W_dec, ref.W_dec), ("b_dec", eng.b_dec, ref.b_dec))}
     sh = rel(eng.shadow_weights().float(), ref.shadow_weights().float())
-    if max(errs.values()) > 2e-5 or sh > 1e-6 or eng.unsafe_rows() != 0:
+    st = eng.screen_stats()
+    if max(errs.values()) > 2e-5 or sh > 1e-6 or st["unrepaired"] != 0 or st["bound_violations"] != 0:
         ok = False
     if rank == 0:
         print(f"sharded={sharded}: param rel-L2 vs single-GPU {errs}, fp16 operand {sh:.2e}, n_dead(last)={ref_losses[-1]['n_dead']}")

@@ -79,7 +79,7 @@ class OracleEngine:
     def forward(self, x, *, training=True, phase=_lib.PHASE_ALL, tokens_global=0):
         Bl = x.shape[0]
         tg = tokens_global or Bl
-        if phase & _lib.PHASE_A:
+        if phase & (_lib.PHASE_A | _lib.PHASE_A_REST | _lib.PHASE_A_RESCORE):  # (the screen / decode halves: no-ops here)
             self.calls.append("A")
             # the screen runs on the bf16 operand copy: it must be complete and current on every rank
             assert torch.equal(self._shadow, self.W_enc_t.half()), "stale fp16 operand rows"
@@ -141,15 +141,27 @@ class OracleEngine:
         self.calls.append("sumsq")
         self.sumsq[0] = sum(self.grads[b:e].double().pow(2).sum() for b, e in ranges)
 
-    def adam_step(self, lr, *, max_norm=1.0, renorm_w_dec=False, **kw):
-        """torch Adam(fused) formulas (oracle.adam_step) on the rows of the shard + both bias vectors."""
-        self.calls.append("adam")
-        self.t += 1
+    @property
+    def step_count(self):
+        return self.t
+
+    def adam_step(self, lr, *, max_norm=1.0, renorm_w_dec=False, parts=_lib.ADAM_ALL, step=None, **kw):
+        """torch Adam(fused) formulas (oracle.adam_step) on the rows of the shard + both bias vectors (a sharded
+        optimizer with several row ranges calls once per range: the later calls carry ROWS_ONLY | KEEP_MAXIMA)."""
+        rows_only = bool(parts & _lib.ADAM_ROWS_ONLY)
+        if step is None:
+            assert not rows_only
+            self.calls.append("adam")
+            self.t += 1
+        else:
+            assert step == self.t and rows_only and (parts & _lib.ADAM_KEEP_MAXIMA)
         j0, j1 = self.shard or (0, S)
         coef = min(1.0, max_norm / (float(self.sumsq.sqrt()) + 1e-6))
         bc1, bc2s = 1.0 - CFG.beta1**self.t, (1.0 - CFG.beta2**self.t) ** 0.5
         ps, gs, ms, vs = self._views(self.params), self._views(self.grads), self._views(self.m), self._views(self.v)
         for i, rows in enumerate((slice(j0, j1), slice(None), slice(j0, j1), slice(None))):
+            if rows_only and i in (1, 3):
+                continue
             p, g, m, v = ps[i][rows], gs[i][rows] * coef, ms[i][rows], vs[i][rows]
             m.copy_(m + (g - m) * (1.0 - CFG.beta1))
             v.copy_(v * CFG.beta2 + (1.0 - CFG.beta2) * g * g)
@@ -157,7 +169,8 @@ class OracleEngine:
         if renorm_w_dec:
             self.W_dec[j0:j1] = orc.normalize_w_dec(self.W_dec[j0:j1])
         self._shadow[j0:j1] = self.W_enc_t[j0:j1].half()
-        self._wnorm[0] = self.W_enc_t[j0:j1].pow(2).sum(1).max()
+        mx = self.W_enc_t[j0:j1].pow(2).sum(1).max()
+        self._wnorm[0] = torch.maximum(self._wnorm[0], mx) if parts & _lib.ADAM_KEEP_MAXIMA else mx
         self._wrows[j0:j1] = self.W_enc_t[j0:j1].norm(dim=1)
 
 
@@ -176,7 +189,8 @@ def _worker(rank, world, port, out_dir, sharded, n_chunks):
         params, xs = _data()
         eng = OracleEngine(*params)
         tr = DataParallelTrainer(eng, sharded=sharded, n_chunks=n_chunks)
-        assert tr.world == world and tr.rank == rank and tr.sharded == sharded and bool(tr.chunks) == (n_chunks > 1)
+        assert tr.world == world and tr.rank == rank and tr.sharded == sharded
+        assert bool(tr.chunks) == (n_chunks > 1 and not sharded) and bool(tr.shard_chunks) == (n_chunks > 1 and sharded)
         tr.broadcast_params(0)
         per = B // world
         rec = []
@@ -186,12 +200,15 @@ def _worker(rank, world, port, out_dir, sharded, n_chunks):
             rec.append(tr.global_losses())
             lr = orc.warmup_cosine(step + 1, CFG.n_lr_warmup, CFG.lr, CFG.n_steps)
         # phase A -> flags all-reduce -> phase B -> backward (-> grads exchange) -> norm -> Adam, every step
-        bwd = ["bwd0"] + ["bwd1"] * len(tr.chunks) if tr.chunks else ["bwd"]
+        n_stage1 = len(tr.chunks) or len(tr.shard_chunks)
+        bwd = ["bwd0"] + ["bwd1"] * n_stage1 if n_stage1 else ["bwd"]
         assert eng.calls == (["A", "B"] + bwd + ["sumsq", "adam"]) * len(xs)
         if sharded:  # Adam moments exist for the rank's own rows only
-            j0, j1 = eng.shard
+            own = torch.zeros(S, dtype=torch.bool)
+            for o0, o1 in ([(c[2], c[3]) for c in tr.shard_chunks] or [eng.shard]):
+                own[o0:o1] = True
             mW = eng._views(eng.m)[0]
-            assert bool((mW[j0:j1] != 0).any()) and not bool((torch.cat([mW[:j0], mW[j1:]]) != 0).any())
+            assert bool((mW[own] != 0).any()) and not bool((mW[~own] != 0).any())
         torch.save(dict(rec=rec, W_enc=eng.W_enc_t.t().clone(), W_dec=eng.W_dec.clone(), b_enc=eng.b_enc.clone(),
                         b_dec=eng.b_dec.clone(), toks=eng.toks), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
@@ -205,8 +222,9 @@ def _free_port():
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("sharded,n_chunks", [(False, 1), (False, 3), (True, 1)],
-                         ids=["allreduce", "chunked-overlapped-allreduce", "sharded-optimizer"])
+@pytest.mark.parametrize("sharded,n_chunks", [(False, 1), (False, 3), (True, 1), (True, 2)],
+                         ids=["allreduce", "chunked-overlapped-allreduce", "sharded-optimizer",
+                              "sharded-optimizer-chunked-reduce-scatter"])
 def test_two_ranks_equal_one_rank_on_the_full_batch(tmp_path, sharded, n_chunks):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), sharded, n_chunks), nprocs=2, join=True)
     r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))

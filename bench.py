@@ -254,9 +254,28 @@ def final_check(eng, x, K):
         torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
-def make_bench_shards(D, B, n_batches, rank):
+def _fs_type(path):
+    """File-system magic of `path` (statfs f_type), e.g. 0x01021994 = tmpfs."""
+    import ctypes
+
+    class _Statfs(ctypes.Structure):
+        _fields_ = [("f_type", ctypes.c_long), ("pad", ctypes.c_long * 20)]
+
+    buf = _Statfs()
+    libc = ctypes.CDLL(None, use_errno=True)
+    if libc.statfs(str(path).encode(), ctypes.byref(buf)) != 0:
+        return None
+    return buf.f_type & 0xFFFFFFFF
+
+
+TMPFS_MAGIC = 0x01021994
+
+
+def make_bench_shards(D, B, n_batches, rank, storage="tmpfs"):
     """Synthetic Gaussian activation shards in saev's on-disk format (fp32 [examples, layers=1, tokens, d_model] +
-    metadata.json + shards.json, src/saev/data/shards.py:43-180, 575-636) on local scratch storage."""
+    metadata.json + shards.json, src/saev/data/shards.py:43-180, 575-636).  storage="tmpfs": under /dev/shm (page
+    cache); "disk": on the first candidate directory that is NOT tmpfs, written through and evicted from the page cache
+    (fsync + POSIX_FADV_DONTNEED) so that the loader really reads the device."""
     import shutil
     import tempfile
 
@@ -268,15 +287,20 @@ def make_bench_shards(D, B, n_batches, rank):
     per_shard = min(n_examples, max(1, (1 << 28) // (T * D * 4)))  # ~256 MB shards
     need = n_examples * T * D * 4
     base = None
-    for cand in ("/dev/shm", tempfile.gettempdir()):
+    cands = ("/dev/shm", tempfile.gettempdir()) if storage == "tmpfs" else (tempfile.gettempdir(), "/var/tmp", str(ROOT / "gpurun_out"))
+    for cand in cands:
         try:
+            if not os.path.isdir(cand):
+                continue
+            if storage == "disk" and _fs_type(cand) == TMPFS_MAGIC:
+                continue
             if shutil.disk_usage(cand).free > need * 1.2 + (1 << 30):
                 base = cand
                 break
         except OSError:
             continue
     if base is None:
-        raise RuntimeError("no scratch space for the benchmark shards")
+        raise RuntimeError(f"no scratch space for the benchmark shards ({storage})")
     root = pathlib.Path(tempfile.mkdtemp(prefix=f"saev_b200_bench_r{rank}_", dir=base)) / "saev" / "shards" / "bench0000"
     root.mkdir(parents=True)
     md = dict(family="fake-clip", ckpt="synthetic", layers=[0], content_tokens_per_example=T, cls_token=False, d_model=D,
@@ -290,9 +314,67 @@ def make_bench_shards(D, B, n_batches, rank):
         block = torch.randn(per_shard * T, D, generator=gen)  # fixed-size shard files, tail rows unused
         name = f"acts{s0 // per_shard:06d}.bin"
         block.numpy().tofile(root / name)
+        if storage == "disk":
+            fd = os.open(root / name, os.O_RDONLY)
+            try:
+                os.fsync(fd)
+                os.posix_fadvise(fd, 0, 0, os.POSIX_FADV_DONTNEED)
+            finally:
+                os.close(fd)
         info.append({"name": name, "n_examples": n})
     (root / "shards.json").write_text(json.dumps(info))
     return root
+
+
+def loader_leg(tr, eng, dev, world, rank, D, B, steps, n_threads, lr_fn, gstep, barrier, storage, zero_copy=None):
+    """`steps` training steps fed by saev_b200.data.ShuffledDataLoader from shard files (`storage`), every step's loss
+    vector read back to pinned host memory; returns (activations/s over all ranks, note, bytes/step, steps done)."""
+    import shutil
+
+    import torch
+    import torch.distributed as dist
+
+    from saev_b200 import data as bdata
+    from saev_b200.scheduling import BatchLimiter
+
+    loss_host = torch.empty(steps, 8, dtype=torch.float32).pin_memory()
+    n_batches = steps + 6
+    shards_root = make_bench_shards(D, B, n_batches, rank, storage)
+    try:
+        lcfg = bdata.ShuffledConfig(shards=shards_root, layer=0, batch_size=B, n_threads=n_threads, buffer_size=4,
+                                    seed=17 + rank, batch_timeout_s=60.0)
+        loader = bdata.ShuffledDataLoader(lcfg, device=dev, rank=0, world_size=1, zero_copy=zero_copy)  # own directory per rank
+        limiter = BatchLimiter(loader, steps * B + 2 * B)
+        it = iter(limiter)
+        zc = loader.zero_copy
+        for _ in range(2):  # pool fill + first batches are warm-up
+            tr.step(next(it)["act"], lr_fn(gstep))
+            gstep += 1
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            batch = next(it)
+            tr.step(batch["act"], lr_fn(gstep))
+            loss_host[i].copy_(eng.losses, non_blocking=True)
+            gstep += 1
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        it.close()
+        loader.shutdown()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value = world * B * steps / (float(t.item()) * 1e-3)
+        note = (f"ShuffledDataLoader over {n_batches} batches of fp32 shards under {shards_root.parents[3]} "
+                f"({'tmpfs' if _fs_type(shards_root) == TMPFS_MAGIC else 'disk, page cache dropped'}; {n_threads} I/O threads, "
+                + ("mmap + cudaHostRegister: DMA out of the page cache" if zc else "pread -> pinned staging")
+                + " -> HBM pool -> gather)")
+        return value, note, gstep, wall
+    finally:
+        shutil.rmtree(shards_root.parents[2], ignore_errors=True)
 
 
 def workload_name(w, D, S, K, B, n_prefixes=1, k_aux=512, dead_threshold=10_000_000):
@@ -335,6 +417,8 @@ def main():
     ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
     ap.add_argument("--loader-threads", type=int, default=0, help="I/O threads per rank (0 = cores / ranks - 1, 2..8)")
+    ap.add_argument("--no-disk-leg", action="store_true",
+                    help="skip the extra end-to-end leg that streams the shards from a non-tmpfs directory (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -397,8 +481,11 @@ def main():
                              reserved_sms=args.reserved_sms)
     tr.broadcast_params(0)
 
-    # synthetic activations: 4 rotating batches per rank, resident in HBM (value) and in pinned host memory (e2e)
-    NB = 4
+    # synthetic activations: NB rotating batches per rank, resident in HBM.  Many distinct batches on purpose: with only
+    # a few the SAE memorises them within the pre-heat (hundreds of steps), its pre-activations pile up just under each
+    # row's top-k threshold and the screen admits twice as many candidates as it does on fresh data (measured: 95 vs 45
+    # per row) -- a cost a real run, which never sees a batch twice, does not pay.
+    NB = 32
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = [torch.randn(B, D, generator=gen, device=dev) for _ in range(NB)]
     peak_lr, n_warm = 4e-4, 500
@@ -484,52 +571,27 @@ def main():
     e2e_path, e2e_note = "loader", ""
     e2e_value = None
     loss_host = torch.empty(args.steps, 8, dtype=torch.float32).pin_memory()
-    shards_root = None
+    e2e_disk = None
+    if args.loader_threads <= 0:  # do not oversubscribe the host: every rank also runs a feeder + the Python loop
+        args.loader_threads = max(2, min(8, (os.cpu_count() or 8) // world - 1))
     try:
         if args.e2e != "loader":
             raise RuntimeError("ring requested")
-        from saev_b200 import data as bdata
-        from saev_b200.scheduling import BatchLimiter
-
-        if args.loader_threads <= 0:  # do not oversubscribe the host: every rank also runs a feeder + the Python loop
-            args.loader_threads = max(2, min(8, (os.cpu_count() or 8) // world - 1))
-        n_batches = args.steps + 6
-        shards_root = make_bench_shards(D, B, n_batches, rank)
-        lcfg = bdata.ShuffledConfig(shards=shards_root, layer=0, batch_size=B, n_threads=args.loader_threads,
-                                    buffer_size=4, seed=17 + rank, batch_timeout_s=60.0)
-        loader = bdata.ShuffledDataLoader(lcfg, device=dev, rank=0, world_size=1)  # every rank owns its directory
-        limiter = BatchLimiter(loader, args.steps * B + 2 * B)
-        it = iter(limiter)
-        for _ in range(2):  # pool fill + first batches are warm-up
-            tr.step(next(it)["act"], lr_at(gstep))
-            gstep += 1
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            batch = next(it)
-            tr.step(batch["act"], lr_at(gstep))
-            loss_host[i].copy_(eng.losses, non_blocking=True)
-            gstep += 1
-        e1.record()
-        barrier()
-        it.close()
-        loader.shutdown()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
-        e2e_note = (f"ShuffledDataLoader over {n_batches} batches of fp32 shards under {shards_root.parents[3]} "
-                    f"({args.loader_threads} I/O threads, pinned staging -> HBM pool -> gather)")
+        e2e_value, e2e_note, gstep, _ = loader_leg(tr, eng, dev, world, rank, D, B, args.steps, args.loader_threads, lr_at,
+                                                   gstep, barrier, "tmpfs")
     except Exception as err:  # noqa: BLE001
         e2e_path, e2e_note = "pinned-ring", f"loader path unavailable ({type(err).__name__}: {str(err)[:80]})"
-    finally:
-        if shards_root is not None:
-            import shutil
-
-            shutil.rmtree(shards_root.parents[2], ignore_errors=True)
+    if e2e_value is not None and world == 1 and not args.no_disk_leg:
+        # the same leg from real storage (HBM-resident / page cache / disk reported separately)
+        try:
+            v, note, gstep, wall = loader_leg(tr, eng, dev, world, rank, D, B, args.steps, args.loader_threads, lr_at, gstep,
+                                              barrier, "disk", zero_copy=False)
+            e2e_disk = {"value": v, "unit": "activations/s", "read_GBps": v * D * 4 / 1e9, "note": note}
+        except Exception as err:  # noqa: BLE001
+            e2e_disk = {"error": f"{type(err).__name__}: {str(err)[:120]}"}
     if e2e_value is None:
-        x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
+        NH = min(NB, 4)  # pinned host copies for the fallback ring
+        x_host = [torch.empty(B, D, dtype=torch.float32).pin_memory() for _ in range(NH)]
         for h, d in zip(x_host, x_dev):
             h.copy_(d)
         stage_bufs = [torch.empty(B, D, device=dev) for _ in range(2)]
@@ -542,7 +604,7 @@ def main():
             slot = i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[slot])
-                stage_bufs[slot].copy_(x_host[i % NB], non_blocking=True)
+                stage_bufs[slot].copy_(x_host[i % NH], non_blocking=True)
                 copied[slot].record(copy_stream)
 
         for s in range(2):
@@ -599,12 +661,13 @@ def main():
                              ("dense path: all five contractions as 3-term bf16 split products on tcgen05 (~2^-17 "
                               "relative), fp32 accumulation; everything else fp32"),
                 "l2_policy": f"per-step working set (params+grads+Adam moments {eng.n_params * 16 / 1e9:.2f} GB, "
-                             f"{NB} rotating input batches) is far larger than the 126 MB L2; no explicit flush",
+                             f"{NB} rotating input batches of {B * D * 4 / 1e6:.0f} MB) is far larger than the 126 MB L2; "
+                             "no explicit flush",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "activations/s",
                     "h2d_bytes_per_step": B * D * 4 + (B * 8 if e2e_path == "loader" else 0), "d2h_bytes_per_step": 32,
-                    "path": e2e_path, "note": e2e_note},
+                    "path": e2e_path, "note": e2e_note, **({"from_disk": e2e_disk} if e2e_disk is not None else {})},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "encode_gemm2_kernel (tcgen05 cta_group::2 encoder contraction + "
                          "top-k screen)" if K else "encode_gemm_kernel<2> (tcgen05 encoder contraction, 3-term split, ReLU)",

@@ -310,7 +310,8 @@ int saev_b200_ring_host_sync(saev_b200_ring* r, int32_t slot); /* block host unt
 /* ---- shuffled activation loader with the shuffle pool in HBM (replaces saev's ShuffledDataLoader +
  *      ReservoirBuffer: src/saev/data/shuffled.py:133-363, 380-699; src/saev/data/buffers.py:91-231) ----
  * Shards are saev's `acts%06d.bin` files, fp32 [examples_per_shard, n_layers, tokens_per_example, d_model]
- * (src/saev/data/shards.py:168-180).  I/O threads pread whole examples into pinned staging chunks, a feeder
+ * (src/saev/data/shards.py:168-180).  I/O threads pread whole examples into pinned staging chunks (or, for shards on
+ * tmpfs, map + register the files so that the copies DMA out of the page cache: cfg.reserved), a feeder
  * thread appends them to a device-resident pool and prepares shuffled batches ahead of the consumer with a
  * gather kernel; saev_b200_loader_next returns DEVICE pointers, valid until the call after the next one.
  * Each (example, content token) row of the listed shards is delivered exactly once per epoch. */
@@ -332,7 +333,7 @@ typedef struct saev_b200_loader_cfg {
   int32_t n_out_slots;            /* device batch buffers handed out round-robin (>= 2; 0 = 3) */
   int32_t chunk_examples;         /* examples per I/O chunk, 0 = about 8 MB */
   float min_buffer_fill;          /* Config.min_buffer_fill                              shuffled.py:578-633 */
-  int32_t reserved;
+  int32_t reserved;               /* zero-copy mode: 0 = automatic (on when the shards live on tmpfs), 1 = off, 2 = on */
   int64_t n_rows_limit;           /* unused by the library (the epoch length is passed to start_epoch) */
   uint64_t seed;                  /* Config.seed */
   const uint8_t* labels;          /* optional labels.bin [n_examples, content_tokens] (host pointer) or NULL */
@@ -352,6 +353,9 @@ int saev_b200_loader_next(saev_b200_loader* l, void* consumer_stream, double tim
                           int32_t** example_idx, int32_t** token_idx, int32_t* n_rows);
 int saev_b200_loader_stats(saev_b200_loader* l, int64_t* pool_rows, int64_t* pool_capacity, int64_t* rows_delivered,
                            int64_t* bytes_read);
+/* 1 if the I/O threads mmap + cudaHostRegister the shard files and the H2D copies DMA straight out of the page cache
+ * (no pread -> pinned staging memcpy on the host), 0 if they pread into pinned staging chunks. */
+int saev_b200_loader_zero_copy(const saev_b200_loader* l);
 int saev_b200_loader_stop(saev_b200_loader* l);
 const char* saev_b200_loader_last_error(const saev_b200_loader* l);
 /* Host-only pieces, exported for tests: the chunk reader (returns rows kept, < 0 on error) and the draw /

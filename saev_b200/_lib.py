@@ -135,6 +135,7 @@ SIGNATURES = {
         C.c_int, [_p, _p, C.c_double, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i32)]),
     "saev_b200_loader_stats": (
         C.c_int, [_p, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "saev_b200_loader_zero_copy": (C.c_int, [_p]),
     "saev_b200_loader_stop": (C.c_int, [_p]),
     "saev_b200_loader_last_error": (C.c_char_p, [_p]),
     "saev_b200_loader_read_chunk": (_i64, [C.POINTER(LoaderCfg), _i32, _i32, _i32, _p, _p]),

@@ -9,6 +9,10 @@
 //   I/O threads  : pread() whole examples (content tokens of the requested layer are contiguous on disk:
 //                  shard layout [example, layer, token, d_model] fp32, shards.py:168-180) into PINNED staging
 //                  chunks, write the (example_idx, token_idx) pairs next to them, optionally drop rows by label.
+//                  ZERO-COPY mode (shards on tmpfs, or forced): the shard file is mmap()ed and registered with the
+//                  driver (cudaHostRegister), and the feeder's copies DMA straight out of the page cache -- no
+//                  pread -> staging memcpy on the host.  With 8 ranks on one host that memcpy was what bounded the
+//                  end-to-end rate (round 1: 11 M of 26 M activations/s).
 //   feeder thread: owns the loader's CUDA stream.  Appends ready chunks to the tail of the device pool with
 //                  cudaMemcpyAsync, and prepares batches ahead of the consumer: draws `need` distinct random pool
 //                  positions (host RNG), launches a gather kernel pool -> batch buffer, then a move kernel that
@@ -24,6 +28,9 @@
 #include <fcntl.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -219,9 +226,21 @@ __global__ void __launch_bounds__(256) loader_move_kernel(float* __restrict__ po
   }
 }
 
+// a shard file mapped and registered for DMA (zero-copy mode); unmapped once every chunk cut from it has been copied
+struct Mapping {
+  char* base = nullptr;
+  size_t len = 0;
+  int pending = 0;         // chunks handed to the feeder whose copies have not been enqueued yet (under L->mu)
+  bool closed = false;     // the I/O thread has cut its last chunk
+  cudaEvent_t last = nullptr;  // recorded after the newest copy out of this mapping
+};
+
 struct Chunk {
   int slot = -1;
   int64_t rows = 0;
+  Mapping* map = nullptr;  // zero-copy: the activations are `n_seg` segments of `seg_bytes` at map->base + off0, `stride` apart
+  size_t off0 = 0, seg_bytes = 0, stride = 0;
+  int n_seg = 0;
 };
 
 }  // namespace
@@ -260,6 +279,8 @@ struct saev_b200_loader {
   int64_t rows_appended = 0, rows_drawn = 0, rows_expected = 0, pool_fill = 0;
   int handed_out = -1;           // slot currently owned by the consumer
   std::string error;
+  int zero_copy = 0;             // 0: pread into pinned staging; 1: mmap + cudaHostRegister
+  std::vector<Mapping*> mappings;  // live zero-copy mappings (under mu)
   std::vector<std::thread> io_threads;
   std::thread feeder;
   std::atomic<long long> bytes_read{0};
@@ -279,6 +300,33 @@ void set_error(saev_b200_loader* L, const std::string& e) {
   if (L->error.empty()) L->error = e;
   L->stop = true;
   L->cv.notify_all();
+}
+
+// Unmap the zero-copy mappings whose chunks have all been copied (`wait`: block on the copies; else only the finished
+// ones).  Called by the I/O threads between shards and when the threads are joined.
+void reap_mappings(saev_b200_loader* L, bool wait) {
+  std::vector<Mapping*> done;
+  {
+    std::lock_guard<std::mutex> lk(L->mu);
+    for (size_t i = 0; i < L->mappings.size();) {
+      Mapping* m = L->mappings[i];
+      if (m->closed && m->pending == 0 && (wait || cudaEventQuery(m->last) == cudaSuccess)) {
+        done.push_back(m);
+        L->mappings[i] = L->mappings.back();
+        L->mappings.pop_back();
+      } else {
+        ++i;
+      }
+    }
+  }
+  cudaGetLastError();  // (cudaErrorNotReady from the queries is not an error)
+  for (Mapping* m : done) {
+    cudaEventSynchronize(m->last);
+    cudaHostUnregister(m->base);
+    munmap(m->base, m->len);
+    cudaEventDestroy(m->last);
+    delete m;
+  }
 }
 
 void io_main(saev_b200_loader* L) {
@@ -301,6 +349,33 @@ void io_main(saev_b200_loader* L) {
       break;
     }
     bool ok = true;
+    // zero-copy: map + register the whole shard file once; every chunk is then a (strided) window of it
+    Mapping* map = nullptr;
+    if (L->zero_copy && !g.filter) {
+      reap_mappings(L, false);
+      struct stat stt;
+      if (fstat(fd, &stt) == 0 && stt.st_size > 0) {
+        void* base = mmap(nullptr, static_cast<size_t>(stt.st_size), PROT_READ, MAP_SHARED | MAP_POPULATE, fd, 0);
+        if (base != MAP_FAILED) {
+          cudaError_t e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterReadOnly);
+          if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterDefault);
+          }
+          if (e == cudaSuccess) {
+            map = new Mapping();
+            map->base = static_cast<char*>(base);
+            map->len = static_cast<size_t>(stt.st_size);
+            cudaEventCreateWithFlags(&map->last, cudaEventDisableTiming);
+            std::lock_guard<std::mutex> lk(L->mu);
+            L->mappings.push_back(map);
+          } else {
+            cudaGetLastError();
+            munmap(base, static_cast<size_t>(stt.st_size));  // this file cannot be registered: pread path for it
+          }
+        }
+      }
+    }
     for (int ex = 0; ex < n_examples && ok; ex += L->chunk_examples) {
       const int n_ex = std::min(L->chunk_examples, n_examples - ex);
       int slot;
@@ -318,19 +393,54 @@ void io_main(saev_b200_loader* L) {
       cudaEventSynchronize(L->stage_done[slot]);
       float* act = reinterpret_cast<float*>(L->stage[slot]);
       int32_t* meta = reinterpret_cast<int32_t*>(L->stage[slot] + static_cast<size_t>(L->chunk_rows_max) * g.d_model * 4);
-      const int64_t rows = read_chunk(g, fd, shard, ex, n_ex, act, meta);
-      if (rows < 0) {
-        set_error(L, "short read / I/O error in " + path);
-        ok = false;
-        break;
+      Chunk ch;
+      ch.slot = slot;
+      if (map != nullptr) {
+        // only the (example, token) pairs go through the staging slot; the activations stay where they are
+        const size_t row_bytes = static_cast<size_t>(g.d_model) * 4, T = g.tokens_per_example, Lr = g.n_layers, C = g.content_tokens;
+        const bool contiguous = (Lr == 1 && g.cls_token == 0 && C == T);
+        ch.map = map;
+        ch.off0 = ((static_cast<size_t>(ex) * Lr + g.layer_index) * T + g.cls_token) * row_bytes;
+        ch.seg_bytes = contiguous ? static_cast<size_t>(n_ex) * C * row_bytes : C * row_bytes;
+        ch.stride = Lr * T * row_bytes;
+        ch.n_seg = contiguous ? 1 : n_ex;
+        const size_t last_end = ch.off0 + static_cast<size_t>(ch.n_seg - 1) * ch.stride + ch.seg_bytes;
+        if (last_end > map->len) {
+          set_error(L, "short file " + path);
+          ok = false;
+          break;
+        }
+        const int64_t ex0 = static_cast<int64_t>(shard) * g.examples_per_shard + ex;
+        int64_t r = 0;
+        for (int e = 0; e < n_ex; ++e)
+          for (size_t t = 0; t < C; ++t, ++r) {
+            meta[2 * r] = static_cast<int32_t>(ex0 + e);
+            meta[2 * r + 1] = static_cast<int32_t>(t);
+          }
+        ch.rows = r;
+      } else {
+        ch.rows = read_chunk(g, fd, shard, ex, n_ex, act, meta);
+        if (ch.rows < 0) {
+          set_error(L, "short read / I/O error in " + path);
+          ok = false;
+          break;
+        }
       }
       L->bytes_read += static_cast<long long>(n_ex) * g.content_tokens * g.d_model * 4;
       {
         std::lock_guard<std::mutex> lk(L->mu);
-        if (rows > 0) L->ready.push_back(Chunk{slot, rows});
-        else L->free_stage.push_back(slot);
+        if (ch.rows > 0) {
+          if (map != nullptr) ++map->pending;
+          L->ready.push_back(ch);
+        } else {
+          L->free_stage.push_back(slot);
+        }
         L->cv.notify_all();
       }
+    }
+    if (map != nullptr) {
+      std::lock_guard<std::mutex> lk(L->mu);
+      map->closed = true;
     }
     close(fd);
     if (!ok) break;
@@ -394,12 +504,23 @@ void feeder_main(saev_b200_loader* L) {
     if (have_chunk) {
       const float* act = reinterpret_cast<const float*>(L->stage[ch.slot]);
       const char* meta = L->stage[ch.slot] + static_cast<size_t>(L->chunk_rows_max) * D * 4;
-      cudaMemcpyAsync(L->pool_act + L->pool_fill * D, act, static_cast<size_t>(ch.rows) * D * 4, cudaMemcpyHostToDevice,
-                      L->stream);
+      if (ch.map != nullptr) {  // zero-copy: DMA out of the registered file mapping (strided when examples interleave layers)
+        if (ch.n_seg == 1)
+          cudaMemcpyAsync(L->pool_act + L->pool_fill * D, ch.map->base + ch.off0, ch.seg_bytes, cudaMemcpyHostToDevice,
+                          L->stream);
+        else
+          cudaMemcpy2DAsync(L->pool_act + L->pool_fill * D, ch.seg_bytes, ch.map->base + ch.off0, ch.stride, ch.seg_bytes,
+                            static_cast<size_t>(ch.n_seg), cudaMemcpyHostToDevice, L->stream);
+        cudaEventRecord(ch.map->last, L->stream);
+      } else {
+        cudaMemcpyAsync(L->pool_act + L->pool_fill * D, act, static_cast<size_t>(ch.rows) * D * 4, cudaMemcpyHostToDevice,
+                        L->stream);
+      }
       cudaMemcpyAsync(L->pool_meta + L->pool_fill, meta, static_cast<size_t>(ch.rows) * 8, cudaMemcpyHostToDevice,
                       L->stream);
       cudaEventRecord(L->stage_done[ch.slot], L->stream);
       std::lock_guard<std::mutex> lk(L->mu);
+      if (ch.map != nullptr) --ch.map->pending;
       L->pool_fill += ch.rows;
       L->rows_appended += ch.rows;
       L->free_stage.push_back(ch.slot);
@@ -452,6 +573,14 @@ void join_threads(saev_b200_loader* L) {
   L->io_threads.clear();
   if (L->feeder.joinable()) L->feeder.join();
   if (L->stream) cudaStreamSynchronize(L->stream);
+  {  // chunks that were cut but never copied (early stop) no longer pin their mapping
+    std::lock_guard<std::mutex> lk(L->mu);
+    for (Mapping* m : L->mappings) {
+      m->pending = 0;
+      m->closed = true;
+    }
+  }
+  reap_mappings(L, true);
 }
 
 }  // namespace
@@ -537,6 +666,18 @@ int saev_b200_loader_create(const saev_b200_loader_cfg* c, saev_b200_loader** ou
   L->seed = c->seed;
   L->min_fill = c->min_buffer_fill;
   L->rows_limit = c->n_rows_limit;
+  // zero-copy mode (cfg.reserved: 0 = automatic -- on when the shards live on tmpfs, i.e. already in RAM --, 1 = off,
+  // 2 = on for any file system; SAEV_B200_LOADER_ZERO_COPY=0|1 overrides).  Label filtering drops rows on the host
+  // and therefore always takes the staging path.
+  {
+    int mode = c->reserved;
+    if (const char* e = getenv("SAEV_B200_LOADER_ZERO_COPY")) mode = (e[0] == '0') ? 1 : 2;
+    if (mode == 0) {
+      struct statfs sfs;
+      mode = (statfs(c->shards_dir, &sfs) == 0 && static_cast<unsigned long>(sfs.f_type) == 0x01021994UL) ? 2 : 1;
+    }
+    L->zero_copy = (mode == 2) ? 1 : 0;
+  }
   // chunk: whole examples, about 8 MB of activations unless the caller fixed it
   const int64_t ex_bytes = static_cast<int64_t>(c->content_tokens) * c->d_model * 4;
   int ce = c->chunk_examples > 0 ? c->chunk_examples : static_cast<int>(std::max<int64_t>(1, (8LL << 20) / ex_bytes));
@@ -666,6 +807,8 @@ int saev_b200_loader_stats(saev_b200_loader* L, int64_t* pool_rows, int64_t* poo
   if (bytes_read) *bytes_read = L->bytes_read.load();
   return 0;
 }
+
+int saev_b200_loader_zero_copy(const saev_b200_loader* L) { return L ? L->zero_copy : 0; }
 
 int saev_b200_loader_stop(saev_b200_loader* L) {
   if (!L) return 0;

@@ -266,9 +266,13 @@ class ShuffledDataLoader:
 
     def __init__(self, cfg, *, device: torch.device | str | None = None, rank: int | None = None,
                  world_size: int | None = None, n_out_slots: int = 3, chunk_examples: int = 0,
-                 alias_ring: bool = False):
+                 alias_ring: bool = False, zero_copy: bool | None = None):
+        """`zero_copy`: None = automatic (shards on tmpfs are mmap()ed + registered with the driver and copied to the
+        GPU straight out of the page cache; anything else is pread into pinned staging chunks), True / False force
+        it.  Label filtering always takes the staging path."""
         self.cfg = cfg
         self.alias_ring = alias_ring
+        self._zero_copy = {None: 0, False: 1, True: 2}[zero_copy]
         self._h = None
         self._lib = None
         self.reservoir = None
@@ -354,6 +358,12 @@ class ShuffledDataLoader:
     def __len__(self) -> int:
         return math.ceil(self.n_samples / self.cfg.batch_size)
 
+    @property
+    def zero_copy(self) -> bool:
+        """Whether the native loader copies to the GPU straight out of the (registered) page cache."""
+        self._ensure_native()
+        return bool(self._lib.saev_b200_loader_zero_copy(self._h))
+
     # ---- native loader ------------------------------------------------------------------------
     def _ensure_native(self):
         if self._h is not None:
@@ -375,7 +385,7 @@ class ShuffledDataLoader:
             shard_order=order.ctypes.data_as(C.POINTER(C.c_int32)), shard_examples=n_ex.ctypes.data_as(C.POINTER(C.c_int32)),
             n_order=len(order), batch_size=self.cfg.batch_size, pool_batches=self.cfg.buffer_size,
             n_threads=self.cfg.n_threads, n_out_slots=self._n_out_slots, chunk_examples=self._chunk_examples,
-            min_buffer_fill=float(self.cfg.min_buffer_fill), reserved=0, n_rows_limit=-1, seed=int(self.cfg.seed),
+            min_buffer_fill=float(self.cfg.min_buffer_fill), reserved=self._zero_copy, n_rows_limit=-1, seed=int(self.cfg.seed),
             labels=self._labels.ctypes.data if self._labels is not None else None,
             ignore_lut=self._ignore_lut.ctypes.data if self._ignore_lut is not None else None,
         )

@@ -95,13 +95,17 @@ def run(sae, batches, *, content_tokens_per_example: int, n_samples: int, n_dist
             eng.eval_accumulate(xv, state)  # fp64 sum x^2, sum x, sum r^2; per-atom firings / activation sums
             if save:
                 idx, val = eng.topk_idx[:n_valid], eng.topk_val[:n_valid]
-                # distributions[example_idx[mask], :] = f_x[mask, :n_dists]  (:226 -- indexed by example, as written there)
-                rows = ex[mask].to(dev)
+                # distributions[example_idx[mask], :] = f_x[mask, :n_dists]  (:226).  As written there the row index is
+                # the EXAMPLE, so the tokens of one example overwrite each other; the sequential CPU assignment keeps
+                # the last one -- reproduced here by writing only the last valid token of every example
+                rows = ex[mask]
+                last = torch.ones(n_valid, dtype=torch.bool)
+                last[:-1] = rows[1:] != rows[:-1]
                 dense_head = torch.zeros(n_valid, n_dists, device=dev)
                 hit = (idx >= 0) & (idx < n_dists)
                 r, k = hit.nonzero(as_tuple=True)
                 dense_head[r, idx[r, k].long()] = val[r, k]
-                distributions[rows] = dense_head
+                distributions[rows[last].to(dev)] = dense_head[last.to(dev)]
                 indptr, indices, data = _sparse.topk_to_csr_parts(idx, val, S)
                 # re-insert the masked tokens as empty rows
                 counts = torch.zeros(bsz, dtype=torch.int64)

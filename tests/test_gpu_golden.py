@@ -280,9 +280,10 @@ def test_staged_backward_equals_one_shot_backward(fuse, monkeypatch):
 
 def test_overlapped_decoder_update_is_the_same_step(monkeypatch):
     """Engine.train_step(overlap_decoder_update=True) defers the decoder half of Adam to a side stream beside the next
-    forward's screen: same kernels on the same data, so parameters, moments and losses must be IDENTICAL to the
-    in-order step, including across a flush() in the middle and with AuxK live.  (One AuxK implementation is pinned:
-    the automatic choice between the two depends on when a lagged device-to-host read lands, i.e. on host timing.)"""
+    forward's screen: same kernels on the same data, so parameters, moments and losses must agree with the in-order
+    step to summation-order noise (atoms with long lists are accumulated with floating-point REDs), including across a
+    flush() in the middle and with AuxK live.  (One AuxK implementation is pinned: the automatic choice between the
+    two depends on when a lagged device-to-host read lands, i.e. on host timing.)"""
     from saev_b200.engine import Engine, EngineConfig
 
     monkeypatch.setenv("SAEV_B200_AUX", "sgemm")
@@ -303,11 +304,14 @@ def test_overlapped_decoder_update_is_the_same_step(monkeypatch):
         b.train_step(x, lr, fused_renorm=True, pre_normalized=i > 0, overlap_decoder_update=True)
         if i == 3:
             b.flush()  # e.g. a checkpoint in the middle of training
-            assert torch.equal(a.W_dec, b.W_dec)
-        losses.append((a.loss_dict(), b.loss_dict()))
+            assert rel_l2(b.W_dec.cpu(), a.W_dec.cpu()) < 1e-6
+        if i % 2 == 0:  # (loss_dict() flushes: keep steps whose decoder update really runs beside the next screen)
+            losses.append((a.loss_dict(), b.loss_dict()))
     for la, lb in losses:
-        assert la == lb
+        for k in la:
+            assert la[k] == pytest.approx(lb[k], rel=1e-6, abs=1e-9), k
     assert int(a.losses[5]) > 0, "the case must exercise AuxK"
     b.flush()
-    for name in ("params", "m", "v", "toks_since_active"):
-        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for name in ("params", "m", "v"):
+        assert rel_l2(getattr(b, name).cpu(), getattr(a, name).cpu()) < 1e-6, name
+    assert torch.equal(a.toks_since_active, b.toks_since_active)

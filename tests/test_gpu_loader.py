@@ -28,11 +28,13 @@ def _rows(batch):
 
 
 @pytest.mark.parametrize("case", CENSUS["cases"], ids=lambda c: f"layer{c['layer']}-bs{c['batch_size']}")
-@pytest.mark.parametrize("n_threads", [1, 3])
-def test_epoch_census_matches_reference_loader(case, n_threads):
+@pytest.mark.parametrize("n_threads,zero_copy", [(1, False), (3, False), (2, True)])
+def test_epoch_census_matches_reference_loader(case, n_threads, zero_copy):
+    """(zero_copy=True: the shard files are mmap()ed + registered and copied with strided DMA -- this directory has two
+    layers and a [CLS] token, so every example is its own segment; the label-filtered case falls back to staging.)"""
     cfg = data.ShuffledConfig(shards=SHARDS, layer=case["layer"], batch_size=case["batch_size"], n_threads=n_threads,
                               buffer_size=4, seed=3, ignore_labels=case["ignore_labels"], batch_timeout_s=10.0)
-    dl = data.ShuffledDataLoader(cfg, chunk_examples=1)
+    dl = data.ShuffledDataLoader(cfg, chunk_examples=2 if zero_copy else 1, zero_copy=zero_copy)
     for epoch in range(2):  # the loader is re-iterable (BatchLimiter restarts it, scheduling.py:104-106)
         rows, sizes = [], []
         for batch in dl:

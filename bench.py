@@ -417,6 +417,8 @@ def main():
     ap.add_argument("--reserved-sms", type=int, default=16)
     ap.add_argument("--e2e", default="loader", choices=["loader", "ring"], help="end-to-end input path")
     ap.add_argument("--loader-threads", type=int, default=0, help="I/O threads per rank (0 = cores / ranks - 1, 2..8)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not pin each rank to the CPUs local to its GPU (saev_b200/numa.py)")
     ap.add_argument("--no-disk-leg", action="store_true",
                     help="skip the extra end-to-end leg that streams the shards from a non-tmpfs directory (N = 1 only)")
     args = ap.parse_args()
@@ -444,6 +446,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; saev_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = {"cpus": 0, "how": "not requested"}
+    if world > 1 and not args.no_numa_bind:
+        from saev_b200.numa import bind_process_to_gpu
+
+        numa = bind_process_to_gpu(local_rank)  # before any pinned allocation / shard file is written
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL kernels on a high-priority stream: the chunked gradient all-reduce then really runs beside the
@@ -654,6 +661,7 @@ def main():
                 **({"dense_features": args.dense_features} if args.dense_features > 0 else {}),
                 **({"dead_atoms": args.dead_atoms} if args.dead_atoms > 0 else {}),
                 "parallelism": f"dp{world}" + (f" ({args.dp_mode} gradient exchange)" if world > 1 else ""),
+                **({"numa_bind": numa} if world > 1 else {}),
                 "preheat_s": args.preheat_s,
                 "precision": ("fp16 tcgen05 screen of the encoder contraction (deterministic error bound) + exact fp32 "
                               "re-score of the candidates; every value that reaches the loss / gradients / parameters "

@@ -41,6 +41,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -232,6 +233,7 @@ struct Mapping {
   size_t len = 0;
   int pending = 0;         // chunks handed to the feeder whose copies have not been enqueued yet (under L->mu)
   bool closed = false;     // the I/O thread has cut its last chunk
+  bool resident = false;   // kept mapped + registered for the loader's lifetime (within the pin budget)
   cudaEvent_t last = nullptr;  // recorded after the newest copy out of this mapping
 };
 
@@ -280,7 +282,13 @@ struct saev_b200_loader {
   int handed_out = -1;           // slot currently owned by the consumer
   std::string error;
   int zero_copy = 0;             // 0: pread into pinned staging; 1: mmap + cudaHostRegister
-  std::vector<Mapping*> mappings;  // live zero-copy mappings (under mu)
+  std::vector<Mapping*> mappings;  // live transient zero-copy mappings (under mu)
+  // Shard files that stay mapped + registered for the loader's lifetime, up to `pin_budget` bytes (default 16 GiB,
+  // SAEV_B200_LOADER_PIN_GB): registering pins every page, ~25 us per MB on this class of host, and an epoch over a
+  // tmpfs-resident data set would otherwise pay it again for every shard it revisits -- or, with several ranks on one
+  // host, queue behind the other ranks' registrations.  They are registered up front in saev_b200_loader_create.
+  std::unordered_map<int, Mapping*> resident;
+  size_t pin_budget = 0, pinned_bytes = 0;
   std::vector<std::thread> io_threads;
   std::thread feeder;
   std::atomic<long long> bytes_read{0};
@@ -300,6 +308,45 @@ void set_error(saev_b200_loader* L, const std::string& e) {
   if (L->error.empty()) L->error = e;
   L->stop = true;
   L->cv.notify_all();
+}
+
+// mmap + cudaHostRegister one shard file (read-only); nullptr if the file cannot be mapped or registered
+Mapping* map_shard(const saev_b200_loader* L, int shard) {
+  char name[64];
+  snprintf(name, sizeof(name), "/acts%06d.bin", shard);
+  const std::string path = L->geo.dir + name;
+  const int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) return nullptr;
+  Mapping* map = nullptr;
+  struct stat stt;
+  if (fstat(fd, &stt) == 0 && stt.st_size > 0) {
+    void* base = mmap(nullptr, static_cast<size_t>(stt.st_size), PROT_READ, MAP_SHARED | MAP_POPULATE, fd, 0);
+    if (base != MAP_FAILED) {
+      cudaError_t e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterReadOnly);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterDefault);
+      }
+      if (e == cudaSuccess) {
+        map = new Mapping();
+        map->base = static_cast<char*>(base);
+        map->len = static_cast<size_t>(stt.st_size);
+        cudaEventCreateWithFlags(&map->last, cudaEventDisableTiming);
+      } else {
+        cudaGetLastError();
+        munmap(base, static_cast<size_t>(stt.st_size));
+      }
+    }
+  }
+  close(fd);
+  return map;
+}
+
+void free_mapping(Mapping* m) {
+  cudaHostUnregister(m->base);
+  munmap(m->base, m->len);
+  cudaEventDestroy(m->last);
+  delete m;
 }
 
 // Unmap the zero-copy mappings whose chunks have all been copied (`wait`: block on the copies; else only the finished
@@ -322,10 +369,7 @@ void reap_mappings(saev_b200_loader* L, bool wait) {
   cudaGetLastError();  // (cudaErrorNotReady from the queries is not an error)
   for (Mapping* m : done) {
     cudaEventSynchronize(m->last);
-    cudaHostUnregister(m->base);
-    munmap(m->base, m->len);
-    cudaEventDestroy(m->last);
-    delete m;
+    free_mapping(m);
   }
 }
 
@@ -353,25 +397,21 @@ void io_main(saev_b200_loader* L) {
     Mapping* map = nullptr;
     if (L->zero_copy && !g.filter) {
       reap_mappings(L, false);
-      struct stat stt;
-      if (fstat(fd, &stt) == 0 && stt.st_size > 0) {
-        void* base = mmap(nullptr, static_cast<size_t>(stt.st_size), PROT_READ, MAP_SHARED | MAP_POPULATE, fd, 0);
-        if (base != MAP_FAILED) {
-          cudaError_t e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterReadOnly);
-          if (e != cudaSuccess) {
-            cudaGetLastError();
-            e = cudaHostRegister(base, static_cast<size_t>(stt.st_size), cudaHostRegisterDefault);
-          }
-          if (e == cudaSuccess) {
-            map = new Mapping();
-            map->base = static_cast<char*>(base);
-            map->len = static_cast<size_t>(stt.st_size);
-            cudaEventCreateWithFlags(&map->last, cudaEventDisableTiming);
-            std::lock_guard<std::mutex> lk(L->mu);
-            L->mappings.push_back(map);
+      {
+        std::lock_guard<std::mutex> lk(L->mu);
+        auto it = L->resident.find(shard);
+        if (it != L->resident.end()) map = it->second;
+      }
+      if (map == nullptr) {
+        map = map_shard(L, shard);  // (nullptr: this file cannot be registered -> pread path for it)
+        if (map != nullptr) {
+          std::lock_guard<std::mutex> lk(L->mu);
+          if (L->pinned_bytes + map->len <= L->pin_budget) {
+            map->resident = true;
+            L->pinned_bytes += map->len;
+            L->resident[shard] = map;
           } else {
-            cudaGetLastError();
-            munmap(base, static_cast<size_t>(stt.st_size));  // this file cannot be registered: pread path for it
+            L->mappings.push_back(map);
           }
         }
       }
@@ -430,7 +470,7 @@ void io_main(saev_b200_loader* L) {
       {
         std::lock_guard<std::mutex> lk(L->mu);
         if (ch.rows > 0) {
-          if (map != nullptr) ++map->pending;
+          if (map != nullptr && !map->resident) ++map->pending;
           L->ready.push_back(ch);
         } else {
           L->free_stage.push_back(slot);
@@ -438,7 +478,7 @@ void io_main(saev_b200_loader* L) {
         L->cv.notify_all();
       }
     }
-    if (map != nullptr) {
+    if (map != nullptr && !map->resident) {
       std::lock_guard<std::mutex> lk(L->mu);
       map->closed = true;
     }
@@ -520,7 +560,7 @@ void feeder_main(saev_b200_loader* L) {
                       L->stream);
       cudaEventRecord(L->stage_done[ch.slot], L->stream);
       std::lock_guard<std::mutex> lk(L->mu);
-      if (ch.map != nullptr) --ch.map->pending;
+      if (ch.map != nullptr && !ch.map->resident) --ch.map->pending;
       L->pool_fill += ch.rows;
       L->rows_appended += ch.rows;
       L->free_stage.push_back(ch.slot);
@@ -677,6 +717,9 @@ int saev_b200_loader_create(const saev_b200_loader_cfg* c, saev_b200_loader** ou
       mode = (statfs(c->shards_dir, &sfs) == 0 && static_cast<unsigned long>(sfs.f_type) == 0x01021994UL) ? 2 : 1;
     }
     L->zero_copy = (mode == 2) ? 1 : 0;
+    double gb = 16.0;
+    if (const char* e = getenv("SAEV_B200_LOADER_PIN_GB")) gb = atof(e);
+    L->pin_budget = gb > 0 ? static_cast<size_t>(gb * (1ull << 30)) : 0;
   }
   // chunk: whole examples, about 8 MB of activations unless the caller fixed it
   const int64_t ex_bytes = static_cast<int64_t>(c->content_tokens) * c->d_model * 4;
@@ -719,6 +762,36 @@ int saev_b200_loader_create(const saev_b200_loader_cfg* c, saev_b200_loader** ou
     cudaGetLastError();
     saev_b200_loader_destroy(L);
     return lfail(128, "loader_create: CUDA allocation failed (pool / pinned staging)");
+  }
+  if (L->zero_copy && !L->geo.filter && L->pin_budget > 0) {
+    // register this rank's shard files now, in visiting order, until the pin budget is spent (n_threads at a time)
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      cudaSetDevice(L->device);
+      for (;;) {
+        const size_t w = next.fetch_add(1);
+        if (w >= L->shard_order.size()) return;
+        {
+          std::lock_guard<std::mutex> lk(L->mu);
+          if (L->pinned_bytes >= L->pin_budget) return;
+        }
+        Mapping* m = map_shard(L, L->shard_order[w]);
+        if (m == nullptr) continue;
+        bool keep = false;
+        {
+          std::lock_guard<std::mutex> lk(L->mu);
+          if (L->pinned_bytes + m->len <= L->pin_budget && L->resident.find(L->shard_order[w]) == L->resident.end()) {
+            m->resident = keep = true;
+            L->pinned_bytes += m->len;
+            L->resident[L->shard_order[w]] = m;
+          }
+        }
+        if (!keep) free_mapping(m);
+      }
+    };
+    std::vector<std::thread> ts;
+    for (int i = 0; i < L->n_threads; ++i) ts.emplace_back(work);
+    for (auto& t : ts) t.join();
   }
   *out = L;
   return 0;
@@ -830,6 +903,8 @@ int saev_b200_loader_destroy(saev_b200_loader* L) {
   for (auto p : L->idx_dev) if (p) cudaFree(p);
   for (auto p : L->idx_host) if (p) cudaFreeHost(p);
   for (auto p : L->stage) if (p) cudaFreeHost(p);
+  for (auto& kv : L->resident) free_mapping(kv.second);
+  L->resident.clear();
   for (auto e : L->out_ready) if (e) cudaEventDestroy(e);
   for (auto e : L->out_released) if (e) cudaEventDestroy(e);
   for (auto e : L->stage_done) if (e) cudaEventDestroy(e);

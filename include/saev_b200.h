@@ -5,6 +5,7 @@
  *   src/saev/nn/modeling.py:343-349    SparseAutoencoder.encode          -> saev_b200_forward (phase A)
  *   src/saev/nn/modeling.py:169-179    TopKActivation.forward            -> saev_b200_forward (phase A)
  *   src/saev/nn/modeling.py:150-156    ReluActivation.forward (dense)    -> saev_b200_forward (phase A, act_kind RELU)
+ *   src/saev/nn/modeling.py:183-244    BatchTopKActivation.forward       -> saev_b200_batch_topk (between A_RESCORE and A_DECODE)
  *   src/saev/nn/modeling.py:351-409    SparseAutoencoder.decode          -> saev_b200_forward (phase A)
  *   src/saev/nn/objectives.py:101-156  MatryoshkaObjective.forward       -> saev_b200_forward (A + B)
  *   src/saev/nn/objectives.py:107-122  dead-latent tracker               -> saev_b200_forward (phase B)
@@ -42,7 +43,7 @@
 extern "C" {
 #endif
 
-#define SAEV_B200_ABI_VERSION 10
+#define SAEV_B200_ABI_VERSION 11
 
 enum { SAEV_B200_ACT_TOPK = 0, SAEV_B200_ACT_RELU = 1 };
 enum { SAEV_B200_AUX_NONE = 0, SAEV_B200_AUX_AUXK = 1 };
@@ -122,6 +123,23 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
                       const float* W_enc_t, const float* b_enc, const float* W_dec, const float* b_dec,
                       int64_t* toks_since_active, int32_t training, int32_t* topk_idx, float* topk_val,
                       float* resid, float* losses, void* workspace, void* stream);
+
+/* BatchTopKActivation.forward (modeling.py:214-244) on the sparse forward state.  The handle is created with act_kind
+ * TOPK and cfg.top_k = the per-row CAPACITY `cap` (<= 64; not BatchTopK.top_k).  Call it between
+ * saev_b200_forward(phase A_SCREEN | A_RESCORE) -- which leaves each row's `cap` largest exact pre-activations in
+ * topk_idx / topk_val -- and saev_b200_forward(phase A_DECODE | B):
+ *   training != 0 (:226-242): keeps the min(k_per_sample * B, all) largest entries of the WHOLE batch (`torch.topk` on the
+ *     flattened matrix; entries tied at the cut value are granted in (row, rank) order), and folds the smallest positive
+ *     survivor into the EMA buffer: *threshold = (1 - momentum) * *threshold + momentum * min_pos   (:237-242).
+ *   training == 0 (:220-224): JumpReLU, keeps value > max(*threshold, 0).
+ * Losing slots become empty (idx -1, value 0); the per-atom counts and activity flags the backward / tracker use are
+ * rebuilt from the survivors.  stats (device int32[4], optional): [0] entries kept, [1] rows that kept all `cap` slots
+ * while d_sae > cap -- the reference may have kept more of such a row, so [1] != 0 means the result is NOT certified
+ * equal to the reference's (raise cap, or treat as an error), [2] entries tied at the cut, [3] key of the cut value.
+ * The global selection does not shard: single rank only. */
+int saev_b200_batch_topk(saev_b200_handle* h, int32_t B, int32_t k_per_sample, int32_t training, float* threshold,
+                         float momentum, int32_t* topk_idx, float* topk_val, int32_t* stats, void* workspace,
+                         void* stream);
 
 /* int32[d_sae] activity flags written by phase A (device pointer inside the workspace). */
 int32_t* saev_b200_active_flags(const saev_b200_handle* h, void* workspace);

@@ -79,8 +79,8 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
     sae.train()
     objective.train()
 
-    rec = {k: [] for k in ("loss", "mse", "aux", "sparsity", "l0", "l1", "n_dead", "grad_norm", "lr")}
-    grads_rec, xhat_rec, grad_steps = {k: [] for k in init}, [], []
+    rec = {k: [] for k in ("loss", "mse", "aux", "sparsity", "l0", "l1", "n_dead", "grad_norm", "lr", "threshold")}
+    grads_rec, xhat_rec, grad_steps = {k: [] for k, _ in sae.named_parameters()}, [], []
     for step in range(n_steps):
         acts = xs[step]
         sae.normalize_w_dec()  # train.py:334-335
@@ -93,6 +93,8 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
             rec[key].append(float(getattr(loss, key)))
         rec["n_dead"].append(int(loss.n_dead))
         rec["grad_norm"].append(float(gn))
+        # BatchTopKActivation.threshold after this step's EMA update (modeling.py:237-242); 0 for the other activations
+        rec["threshold"].append(float(getattr(sae.activation, "threshold", torch.tensor(0.0))))
         if step % save_grads_every == 0 or step == n_steps - 1:
             grad_steps.append(step)
             for k, p in sae.named_parameters():
@@ -137,6 +139,8 @@ def run_case(name, *, D, S, B, n_steps, activation, dead_thr, lr, n_warmup, sche
                 remove_parallel=int(remove_parallel), n_prefixes=n_prefixes, seed=seed)
     if isinstance(activation, M.TopK):
         meta.update(act=0, top_k=activation.top_k)
+    elif isinstance(activation, M.BatchTopK):
+        meta.update(act=2, top_k=activation.top_k, momentum=activation.momentum)
     else:
         meta.update(act=1, top_k=0)
     sp = activation.sparsity
@@ -197,6 +201,19 @@ def main():
              activation=M.TopK(top_k=16, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
              dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=6, data="planted", save_grads_every=5, seed=19,
              n_prefixes=10)
+    # (8) BatchTopK (modeling.py:183-244): batch-wide top-(k B) selection in training, EMA threshold, JumpReLU in the
+    #     eval forward; planted data so that the per-row counts differ and latents die (AuxK live)
+    run_case("tiny_batchtopk_auxk", D=32, S=256, B=64, n_steps=10,
+             activation=M.BatchTopK(top_k=8, aux=M.AuxK(k_aux=16, alpha=1 / 32)),
+             dead_thr=3 * 64, lr=1e-2, n_warmup=4, sched_steps=10, data="planted", seed=23)
+    run_case("c1_batchtopk", D=128, S=512, B=256, n_steps=6,
+             activation=M.BatchTopK(top_k=16, momentum=0.4, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
+             dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=6, data="planted", save_grads_every=5, seed=29)
+    # BatchTopK under the reference's default objective family (Matryoshka prefixes)
+    run_case("c1_batchtopk_matryoshka", D=128, S=512, B=256, n_steps=6,
+             activation=M.BatchTopK(top_k=8, momentum=0.5, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
+             dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=6, data="planted", save_grads_every=5, seed=31,
+             n_prefixes=5)
 
 
 if __name__ == "__main__":

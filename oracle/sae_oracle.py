@@ -37,7 +37,8 @@ Tensor = torch.Tensor
 class OracleConfig:
     d_model: int
     d_sae: int
-    activation: str = "topk"  # "topk" | "relu"            modeling.py:111-126
+    activation: str = "topk"  # "topk" | "relu" | "batchtopk"   modeling.py:111-146
+    batch_momentum: float = 0.1  # BatchTopK.momentum          modeling.py:140
     top_k: int = 32  # modeling.py:123
     l1_coeff: float = 0.0  # L1Sparsity.coeff (0 => NoSparsity)  modeling.py:25-42
     aux: bool = True  # AuxK vs NoAux                  modeling.py:50-103
@@ -67,6 +68,7 @@ class OracleState:
     lr: float = 0.0  # param_group lr; 0.0 before the first step (train.py:118)
     sched_step: int = 0  # WarmupCosine._step
     toks_since_active: Tensor | None = None  # objectives.py:99,108-111 (lazily created)
+    threshold: float = 0.0  # BatchTopKActivation.threshold buffer (modeling.py:213): EMA of the smallest positive survivor
 
     @staticmethod
     def from_params(W_enc, b_enc, W_dec, b_dec) -> "OracleState":
@@ -111,6 +113,29 @@ def topk_activation(h: Tensor, top_k: int):
     _, idx = torch.topk(h, k, dim=-1, sorted=False)
     mask = torch.zeros_like(h).scatter(-1, idx, 1.0)
     return mask * h, mask
+
+
+def batch_topk_activation(h: Tensor, top_k: int, training: bool, threshold: float, momentum: float, flat_idx=None):
+    """modeling.py:214-244.  Training: the (top_k * B) largest entries of the flattened [B, S] matrix survive
+    (`torch.topk(x_flat, k, sorted=False)` -> scatter mask), and threshold <- (1 - m) threshold + m * min(positive
+    survivors).  Eval: JumpReLU, x if x > threshold else 0 (threshold <= 0: x if x > 0).  Returns (f, mask, threshold).
+    `flat_idx`: the kernels' selection as flat indices (adopted after a tie check, cf. adopt_selection)."""
+    if not training:
+        thr = max(float(threshold), 0.0)
+        mask = (h > thr).to(h.dtype)
+        return mask * h, mask, float(threshold)
+    B, S = h.shape
+    k = min(top_k * B, S * B)
+    flat = h.flatten()
+    _, idx = torch.topk(flat, k, sorted=False)
+    if flat_idx is not None:
+        idx = adopt_selection(flat[None, :], idx[None, :], flat_idx[None, :], what="batch top-k")[0]
+    mask = torch.zeros_like(flat).scatter(-1, idx, 1.0).reshape(h.shape)
+    f = mask * h
+    pos = f[f > 0]
+    if pos.numel() > 0:  # (the reference's `pos.min()` raises on an empty selection)
+        threshold = float(torch.tensor(float(threshold), dtype=torch.float32) * (1 - momentum) + momentum * pos.min())
+    return f, mask, threshold
 
 
 def relu_activation(h: Tensor):
@@ -255,6 +280,9 @@ def forward(cfg: OracleConfig, st: OracleState, x: Tensor, training: bool = True
         f, mask = topk_activation(h, cfg.top_k)
     elif cfg.activation == "relu":
         f, mask = relu_activation(h)
+    elif cfg.activation == "batchtopk":
+        f, mask, st.threshold = batch_topk_activation(h, cfg.top_k, training, st.threshold, cfg.batch_momentum,
+                                                      flat_idx=topk_idx)
     else:
         raise ValueError(cfg.activation)
 

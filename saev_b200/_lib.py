@@ -12,7 +12,7 @@ import pathlib
 
 LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libsaev_b200.so"
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 ACT_TOPK, ACT_RELU = 0, 1
 AUX_NONE, AUX_AUXK = 0, 1
@@ -91,6 +91,7 @@ SIGNATURES = {
         C.c_int,
         [_p, C.c_int, _p, _i32, _i64, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p],
     ),
+    "saev_b200_batch_topk": (C.c_int, [_p, _i32, _i32, _i32, _p, _f, _p, _p, _p, _p, _p]),
     "saev_b200_active_flags": (_p, [_p, _p]),
     "saev_b200_unsafe_rows": (_p, [_p, _p]),
     "saev_b200_backward": (C.c_int, [_p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -23,6 +23,7 @@ inline size_t align_up(size_t x) { return (x + ALIGN - 1) & ~(ALIGN - 1); }
 struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_dx, row_scale, unsafe_list, wnorm_rows, guess_hist, guess_L, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
+  size_t btk;  // BatchTopK selection scratch (batch_topk_scratch_bytes)
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
   size_t tc_we[3], tc_wd[3], tc_wdT[3], tc_x[3], tc_xT[3], tc_f[3], tc_fT[3], tc_r[3], tc_rT[3];
@@ -184,6 +185,7 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
   w.active = take(S * 4);
   w.dead_list = take(S * 4);
   w.scalars = take(SC_SLOTS * 4);  // see ScalarSlot (kernels.h)
+  w.btk = take(relu ? 0 : batch_topk_scratch_bytes(c.max_batch));
   w.sfx = take(c.max_prefixes > 1 ? B * static_cast<size_t>(c.max_prefixes) * D * 4 : 0);
   w.block_totals = take(((S + 1023) / 1024) * 4);
   w.heavy_list = take((B * K / WGRAD_HEAVY_ENTRIES + 2) * 4);  // [0] = count, then the atoms
@@ -433,7 +435,7 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     if (cfg->top_k <= 0 || cfg->top_k > cfg->d_sae)
       return fail(nullptr, 2, "saev_b200_create: need 0 < top_k <= d_sae%s");
     if (cfg->top_k > encode2_max_top_k())
-      return fail(nullptr, 3, "saev_b200_create: top_k > 64 is not supported by the screening kernel%s");
+      return fail(nullptr, 3, "saev_b200_create: top_k > 128 is not supported by the screening kernel%s");
   } else if (cfg->d_sae % 8 != 0) {
     return fail(nullptr, 2, "saev_b200_create: the dense (ReLU) path needs d_sae to be a multiple of 8%s");
   }
@@ -821,6 +823,25 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
     if (launch_finalize(f, s)) return fail(h, 47, "forward: finalize launch failed%s");
   }
   return check_cuda(h, "forward");
+}
+
+
+int saev_b200_batch_topk(saev_b200_handle* h, int32_t B, int32_t k_per_sample, int32_t training, float* threshold,
+                         float momentum, int32_t* topk_idx, float* topk_val, int32_t* stats, void* workspace,
+                         void* stream) {
+  bind_context(h);
+  const saev_b200_cfg& c = h->cfg;
+  const Workspace& w = h->ws;
+  if (c.act_kind != SAEV_B200_ACT_TOPK) return fail(h, 48, "batch_topk: the handle must be created with act_kind TOPK%s");
+  if (B <= 0 || B > c.max_batch) return fail(h, 40, "batch_topk: B out of range (0 < B <= cfg.max_batch)%s");
+  if (k_per_sample <= 0) return fail(h, 48, "batch_topk: k_per_sample must be positive%s");
+  if (!training && threshold == nullptr) return fail(h, 48, "batch_topk: eval mode needs the threshold buffer%s");
+  StageTimer tm(h, SAEV_B200_STAGE_RESCORE, static_cast<cudaStream_t>(stream));
+  if (launch_batch_topk(topk_idx, topk_val, B, c.top_k, c.d_sae, static_cast<long long>(k_per_sample) * B, training,
+                        threshold, momentum, at<int>(workspace, w.feat_count), at<int>(workspace, w.active),
+                        at<int>(workspace, w.btk), stats, static_cast<cudaStream_t>(stream)))
+    return fail(h, 48, "batch_topk: launch failed%s");
+  return check_cuda(h, "batch_topk");
 }
 
 }  // extern "C" (re-opened below)

@@ -589,7 +589,8 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 
 }  // namespace g2
 
-int encode2_max_top_k() { return 64; }
+// the lists keep the k largest plus the margin band within CAPG / 2 = 192 entries, and 2 k <= TRIGGER_MAX
+int encode2_max_top_k() { return 128; }
 
 // Number of CTA pairs that can be co-resident (one per TPC with both SMs free); 0 on failure.
 int encode2_max_pairs() {

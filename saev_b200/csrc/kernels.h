@@ -226,6 +226,16 @@ int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s);
 // the device (no host sync); uses the rows' own (already consumed) candidate lists as scratch.
 int launch_repair_topk(const RescoreArgs& a, cudaStream_t s);
 
+// BatchTopK (saev modeling.py:183-244) on the per-row top-`cap` lists the re-score left (batch_topk_kernels.cu): training
+// keeps the n_keep largest entries of the whole batch (ties at the cut in flat order) and folds the smallest positive
+// survivor into *threshold; eval keeps value > max(*threshold, 0).  Losers become empty slots (idx -1, value 0); the
+// per-atom counts (training) and activity flags are rebuilt from the survivors.  stats (device int[4]): kept entries,
+// rows whose capacity may have truncated the selection, entries tied at the cut, key of the cut value.
+size_t batch_topk_scratch_bytes(int max_batch);
+int launch_batch_topk(int* topk_idx, float* topk_val, int B, int cap, int S, long long n_keep, int training,
+                      float* threshold, float momentum, int* feat_count, int* active, int* scratch, int* stats,
+                      cudaStream_t s);
+
 struct DecodeArgs {
   const float* x; const int* topk_idx; const float* topk_val;
   const float* W_dec; const float* b_dec;

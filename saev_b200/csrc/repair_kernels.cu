@@ -27,8 +27,9 @@ constexpr int RP_THREADS = 256;
 constexpr int RP_WARPS = RP_THREADS / 32;
 constexpr int RP_TILE = 1024;      // atoms per selection round of the scan
 constexpr int RP_ROWS = 8;         // unsafe rows multiplied with one load of a dictionary row (4 when d_model > 1024)
-constexpr int RP_KMAX = 64;        // top_k <= 64 (saev_b200_create)
+constexpr int RP_KMAX = 128;       // top_k <= 128 (saev_b200_create)
 constexpr int RP_MAX_SLICES = 64;
+constexpr int RP_MERGE_CAP = 4096; // survivors repair_select_kernel merges per row: n_slices * top_k (64 slices up to top_k = 64)
 constexpr int RP_ROW_SLOTS = 8;    // gridDim.y of the scan (row groups in flight)
 
 __device__ __forceinline__ float4 ldg4r(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(RP_THREADS) repair_scan_kernel(RescoreArgs a, 
 }
 
 __global__ void __launch_bounds__(RP_THREADS) repair_select_kernel(RescoreArgs a, int n_slices) {
-  __shared__ float hv[RP_MAX_SLICES * RP_KMAX];
-  __shared__ int hc[RP_MAX_SLICES * RP_KMAX];
+  __shared__ float hv[RP_MERGE_CAP];
+  __shared__ int hc[RP_MERGE_CAP];
   __shared__ float win_v[RP_KMAX];
   __shared__ int win_c[RP_KMAX];
   __shared__ int hist[256], wtot[2 * RP_WARPS], bc[4];
@@ -292,6 +293,7 @@ int launch_repair_topk(const RescoreArgs& a, cudaStream_t s) {
   const long long cap = static_cast<long long>(a.nsplit) * a.cand_stride;
   int n_slices = static_cast<int>(cap / a.K);
   if (n_slices > RP_MAX_SLICES) n_slices = RP_MAX_SLICES;
+  if (n_slices > RP_MERGE_CAP / a.K) n_slices = RP_MERGE_CAP / a.K;
   const int by_len = (a.S + 255) / 256;  // no slice shorter than 256 atoms
   if (n_slices > by_len) n_slices = by_len;
   if (n_slices < 1) return 24;

@@ -400,7 +400,8 @@ int launch_datapoint_init(const float* acts, const long long* src_row, const flo
 // those (TopKActivation.forward, modeling.py:169-179: no ReLU, exactly k kept).  One warp per row.
 // ------------------------------------------------------------------------------------------------
 constexpr int RESCORE_WARPS = 8;
-constexpr int RESCORE_CAP = 192;  // most candidates of one row that survive the merged threshold
+constexpr int RESCORE_CAP = 192;      // most candidates of one row that survive the merged threshold (top_k <= 64)
+constexpr int RESCORE_CAP_WIDE = 384; // ... for 64 < top_k <= 128 (the row capacity of the BatchTopK path)
 
 // One radix pass of the warp-wide k-th-largest search over a row's candidate lists: histogram of the 8-bit digit
 // at `shift` of every screen key whose higher digits equal `prefix`, then the bin holding the `need`-th largest.
@@ -446,12 +447,12 @@ __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* 
 
 // WPB rows (warps) per block; the rows of a block hold their SM slot until the slowest one (longest candidate list)
 // is done, so small blocks keep more warps busy (same 24 resident warps per SM either way)
-template <int VPL, int WPB>
+template <int VPL, int WPB, int CAP = RESCORE_CAP>
 __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(RescoreArgs a) {
   __shared__ int hist_s[WPB][256];
-  __shared__ float sv_s[WPB][RESCORE_CAP];
-  __shared__ int si_s[WPB][RESCORE_CAP];
-  __shared__ float se_s[WPB][RESCORE_CAP];
+  __shared__ float sv_s[WPB][CAP];
+  __shared__ int si_s[WPB][CAP];
+  __shared__ float se_s[WPB][CAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * WPB + warp;
   if (b >= a.B) return;
@@ -527,16 +528,16 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       }
       const unsigned bal = __ballot_sync(FULL, take);
       const int o = n + __popc(bal & ((1u << lane) - 1u));
-      if (take && o < RESCORE_CAP) {
+      if (take && o < CAP) {
         sv[o] = __int_as_float(t.x) + E;  // the screen value h~_j
         si[o] = t.y;
       }
       n += __popc(bal);
     }
   }
-  if (n > RESCORE_CAP) {  // more near-ties than one warp re-scores: the exact path takes the row
+  if (n > CAP) {  // more near-ties than one warp re-scores: the exact path takes the row
     overflow = true;
-    n = RESCORE_CAP;
+    n = CAP;
   }
   if (n < min(a.K, a.S)) overflow = true;  // (cannot happen with a healthy screen: every list keeps >= k entries)
   __syncwarp();
@@ -624,14 +625,15 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
 }
 
 int launch_rescore_topk(const RescoreArgs& a, cudaStream_t s) {
-  if (a.D % 4) return 21;
+  if (a.D % 4 || a.K > 128) return 21;
   if (cudaMemsetAsync(reinterpret_cast<int*>(a.scalars) + SC_N_UNSAFE, 0, 4, s) != cudaSuccess) return 23;
   ++g_launch_count;
   const int need_ = (a.D + 127) / 128;
   static const int wpb = [] { const char* v = getenv("SAEV_B200_RESCORE_WPB"); return v ? atoi(v) : 1; }();
 #define SB_RESCORE(V)                                                                        \
   {                                                                                          \
-    if (wpb == 1) rescore_topk_kernel<V, 1><<<a.B, 32, 0, s>>>(a);                           \
+    if (a.K > 64) rescore_topk_kernel<V, 1, RESCORE_CAP_WIDE><<<a.B, 32, 0, s>>>(a);         \
+    else if (wpb == 1) rescore_topk_kernel<V, 1><<<a.B, 32, 0, s>>>(a);                      \
     else if (wpb == 2) rescore_topk_kernel<V, 2><<<(a.B + 1) / 2, 64, 0, s>>>(a);            \
     else rescore_topk_kernel<V, RESCORE_WARPS><<<(a.B + RESCORE_WARPS - 1) / RESCORE_WARPS, 32 * RESCORE_WARPS, 0, s>>>(a); \
   }

@@ -37,6 +37,11 @@ class EngineConfig:
     max_batch: int = 16384
     aux_cols_cap: int = 0
     max_prefixes: int = 1  # Matryoshka.n_prefixes the workspace is sized for
+    # BatchTopK (modeling.py:183-244): batch_k = BatchTopK.top_k (average actives per sample; 0 = plain TopK).  `top_k`
+    # is then the per-row CAPACITY of the sparse forward state (<= 64): the batch-wide selection is exact as long as no
+    # row owns more than `top_k` of the batch's winners (Engine.batch_topk_stats() counts the rows that might).
+    batch_k: int = 0
+    batch_momentum: float = 0.1
 
 
 LOSS_KEYS = ("mse", "aux", "sparsity", "l0", "l1", "n_dead", "loss")
@@ -87,6 +92,11 @@ class Engine:
             self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
             self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
             self.toks_since_active = torch.zeros(S, dtype=torch.int64, device=dev)
+            # BatchTopK: the EMA inference threshold (`activation.threshold` buffer of the reference, modeling.py:213)
+            # and the selection counters of the last forward
+            self.threshold = torch.zeros((), dtype=torch.float32, device=dev)
+            self.btk_stats = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.btk_truncated = torch.zeros((), dtype=torch.int64, device=dev)  # cumulative btk_stats[1]
         self.W_enc_t, self.b_enc, self.W_dec, self.b_dec = self._views(self.params)
         self.gW_enc_t, self.gb_enc, self.gW_dec, self.gb_dec = self._views(self.grads)
         self.step_count = 0
@@ -204,9 +214,38 @@ class Engine:
             self._ck(self.lib.saev_b200_normalize_w_dec(self.h, self.W_dec.data_ptr(), self._stream()))
 
     # ---- step pieces -------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0):
+    def forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0,
+                batch_select: bool | None = None):
+        """`batch_select` (BatchTopK only): True = batch-wide top-(k B) selection + threshold EMA (the activation's train
+        mode), False = JumpReLU with the stored threshold (its eval mode); default: follows `training`."""
         self.flush()  # (a decoder update deferred by train_step(overlap_decoder_update=True) runs first)
+        if self.cfg.batch_k > 0:
+            return self._forward_batch_topk(x, training=training, phase=phase, tokens_global=tokens_global,
+                                            batch_select=training if batch_select is None else batch_select)
         return self._forward(x, training=training, phase=phase, tokens_global=tokens_global)
+
+    def _forward_batch_topk(self, x: torch.Tensor, *, training: bool, phase: int, tokens_global: int, batch_select: bool):
+        """BatchTopK forward: screen + exact re-score leave each row's `top_k` (= capacity) largest pre-activations, then
+        saev_b200_batch_topk keeps the batch_k * B largest of the batch (training) or applies the JumpReLU threshold
+        (eval), then decode / losses run on the thinned lists."""
+        if phase != _lib.PHASE_ALL or (tokens_global not in (0, x.shape[0])):
+            raise NotImplementedError("BatchTopK selects over the whole batch: single rank, unsplit forward only "
+                                      "(the global top-k does not shard, SURVEY 8e)")
+        self._forward(x, training=training, phase=_lib.PHASE_A_SCREEN | _lib.PHASE_A_RESCORE)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.saev_b200_batch_topk(
+                self.h, x.shape[0], self.cfg.batch_k, int(batch_select), self.threshold.data_ptr(),
+                float(self.cfg.batch_momentum), self.topk_idx.data_ptr(), self.topk_val.data_ptr(),
+                self.btk_stats.data_ptr(), self.workspace.data_ptr(), self._stream()))
+        self.btk_truncated += self.btk_stats[1]
+        return self._forward(x, training=training, phase=_lib.PHASE_A_DECODE | _lib.PHASE_B)
+
+    def batch_topk_stats(self) -> dict:
+        """Counters of the last BatchTopK forward (host sync): entries kept, rows whose capacity may have truncated the
+        selection (must be 0 for the result to be certified equal to the reference's), entries tied at the cut value;
+        plus the cumulative truncated-row count."""
+        t = self.btk_stats.tolist()
+        return {"kept": t[0], "truncated_rows": t[1], "ties": t[2], "truncated_rows_total": int(self.btk_truncated.item())}
 
     def _forward(self, x: torch.Tensor, *, training: bool = True, phase: int = _lib.PHASE_ALL, tokens_global: int = 0):
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.D
@@ -330,7 +369,8 @@ class Engine:
         that call wait for it.  Same arithmetic, same results; call `flush()` before reading W_dec / b_dec from
         outside (checkpoint, evaluation)."""
         renorm = fused_renorm and self.cfg.normalize_w_dec
-        if not overlap_decoder_update or (self.cfg.normalize_w_dec and not renorm) or self.cfg.activation != "topk":
+        if not overlap_decoder_update or (self.cfg.normalize_w_dec and not renorm) or self.cfg.activation != "topk" \
+                or self.cfg.batch_k > 0:
             self.flush()
             if not pre_normalized:
                 self.normalize_w_dec()

@@ -22,8 +22,13 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     are unchanged, checkpoints interoperate with saev.nn.load / saev.nn.dump).
   * `Output.h_x`, `Output.f_x`, `Output.x_hats` are materialised lazily (the fused path never writes the
     [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
-  * BatchTopK, and Matryoshka n_prefixes > 1 combined with Relu, have no CUDA path in this build and raise
-    NotImplementedError at forward time (TopK + Matryoshka prefixes is supported).  Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05).
+  * Matryoshka n_prefixes > 1 combined with Relu has no CUDA path in this build and raises NotImplementedError at
+    forward time (TopK / BatchTopK + Matryoshka prefixes is supported).  Relu runs the dense path (five
+    error-compensated bf16 split contractions on tcgen05).  BatchTopK (modeling.py:183-244) runs on the sparse path:
+    per-row top-`capacity` lists (capacity = min(128, d_sae); 64 with Matryoshka prefixes), then a batch-wide
+    selection kernel; a row that would
+    need more than `capacity` slots is counted and `Loss.metrics()` raises (single rank only: the global selection
+    does not shard).
 """
 
 from __future__ import annotations
@@ -144,17 +149,21 @@ def sample_prefixes(d_sae: int, n_prefixes: int, min_prefix_length: int = 1, par
 def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
     act = sae_cfg.activation
     kind = _kind(act)
-    if kind == "BatchTopK":
-        raise NotImplementedError("BatchTopK has no CUDA path in saev_b200 (global top-k does not shard; SURVEY §8e)")
-    if kind not in ("TopK", "Relu"):
+    if kind not in ("TopK", "Relu", "BatchTopK"):
         raise TypeError(f"unknown activation config {act!r}")
     aux = getattr(act, "aux", None)
     sp = getattr(act, "sparsity", None)
+    top_k, batch_k = getattr(act, "top_k", 1), 0
+    if kind == "BatchTopK":
+        # the sparse forward state holds `capacity` slots per row; BatchTopK.top_k is the AVERAGE per sample
+        batch_k, top_k = top_k, batch_topk_capacity(top_k, sae_cfg.d_sae, int(getattr(obj_cfg, "n_prefixes", 1)))
     return EngineConfig(
         d_model=sae_cfg.d_model,
         d_sae=sae_cfg.d_sae,
-        top_k=getattr(act, "top_k", 1),
-        activation="topk" if kind == "TopK" else "relu",
+        top_k=top_k,
+        batch_k=batch_k,
+        batch_momentum=float(getattr(act, "momentum", 0.1)),
+        activation="relu" if kind == "Relu" else "topk",
         aux=_kind(aux) == "AuxK",
         k_aux=getattr(aux, "k_aux", 512),
         aux_alpha=getattr(aux, "alpha", 1 / 32),
@@ -163,8 +172,25 @@ def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
         remove_parallel_grads=sae_cfg.remove_parallel_grads,
         normalize_w_dec=sae_cfg.normalize_w_dec,
         max_batch=max_batch,
-        max_prefixes=max(1, min(int(getattr(obj_cfg, "n_prefixes", 1)), sae_cfg.d_sae)) if kind == "TopK" else 1,
+        max_prefixes=max(1, min(int(getattr(obj_cfg, "n_prefixes", 1)), sae_cfg.d_sae)) if kind != "Relu" else 1,
     )
+
+
+def batch_topk_capacity(top_k: int, d_sae: int, n_prefixes: int = 1) -> int:
+    """Slots per row of the sparse forward state under BatchTopK: the most the kernels hold -- 128 (screen / re-score /
+    repair), 64 when Matryoshka prefixes are decoded (decode_prefix_kernel ranks two slots per lane) -- or d_sae when
+    the dictionary is narrower.  SAEV_B200_BATCHTOPK_CAP lowers it (cheaper re-score when rows are known to be
+    balanced; the tests use it to provoke truncation)."""
+    import os
+
+    cap = min(128 if n_prefixes <= 1 else 64, d_sae)
+    env = os.environ.get("SAEV_B200_BATCHTOPK_CAP", "")
+    if env:
+        cap = max(1, min(cap, int(env)))
+    if top_k > cap and cap < d_sae:
+        raise NotImplementedError(f"BatchTopK(top_k={top_k}): the sparse forward state holds at most {cap} actives per "
+                                  "row, which cannot even hold the average")
+    return cap
 
 
 # ----------------------------------------------------------------------------------------------
@@ -238,11 +264,15 @@ class Output:
 
 
 class _Activation(torch.nn.Module):
-    """Placeholder for `sae.activation` (objectives.py:149 reads `.cfg.sparsity`)."""
+    """Placeholder for `sae.activation` (objectives.py:149 reads `.cfg.sparsity`).  BatchTopK carries the reference's
+    `threshold` buffer (modeling.py:213; state_dict key `activation.threshold`), aliased to the engine's device scalar
+    once the engine exists so that the selection kernel's EMA update lands in it."""
 
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
+        if _kind(cfg) == "BatchTopK":
+            self.register_buffer("threshold", torch.tensor(0.0))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -367,6 +397,10 @@ class SparseAutoencoder(torch.nn.Module):
             self._w_dec_normalized = False
             self._dp_synced = True
         self._seen_versions = self._param_versions()
+        if eng.cfg.batch_k > 0 and self.activation.threshold.data_ptr() != eng.threshold.data_ptr():
+            with torch.no_grad():
+                eng.threshold.copy_(self.activation.threshold)
+            self.activation.threshold = eng.threshold
         return eng
 
     def _param_versions(self) -> tuple:
@@ -384,6 +418,22 @@ class SparseAutoencoder(torch.nn.Module):
                                       f"{int(bad.item())} backward call(s) were given a scaled upstream gradient, which it "
                                       "does not apply (scale the learning rate or the loss terms' coefficients instead)")
 
+    def check_batch_topk(self) -> None:
+        """BatchTopK: raise if any forward since the last check had a row that filled all of its `capacity` slots -- the
+        reference may have kept more entries of such a row, so the step is not certified equal to it (host sync;
+        SAEV_B200_BATCHTOPK_ALLOW_TRUNCATION=1 downgrades the error to a counter)."""
+        import os
+
+        eng = self.engine
+        if eng is None or eng.cfg.batch_k <= 0:
+            return
+        n = int(eng.btk_truncated.item())
+        if n and os.environ.get("SAEV_B200_BATCHTOPK_ALLOW_TRUNCATION", "") != "1":
+            eng.btk_truncated.zero_()
+            raise RuntimeError(f"saev_b200 BatchTopK: {n} row(s) needed more than the {eng.cfg.top_k} slots per row the "
+                               "sparse forward state holds; the selection of those steps differs from the reference's "
+                               "(lower BatchTopK.top_k, or set SAEV_B200_BATCHTOPK_ALLOW_TRUNCATION=1 to accept)")
+
     def weights_changed(self) -> None:
         """Call after writing W_enc outside the optimizer (e.g. datapoint init, train.py:141-185) so the bf16
         operand copy is rebuilt.  `_bind` detects re-pointed storage by itself; in-place writes need this."""
@@ -395,7 +445,8 @@ class SparseAutoencoder(torch.nn.Module):
     def _eval_forward(self, x: Tensor):
         eng = self._bind(x.shape[0])
         eng.set_prefixes(None)  # SparseAutoencoder.forward decodes with the single full prefix (modeling.py:331-341)
-        eng.forward(x.contiguous(), training=False)
+        # BatchTopKActivation follows the module's own train/eval flag (modeling.py:219): batch selection in train mode
+        eng.forward(x.contiguous(), training=False, batch_select=self.training)
         self._ticket += 1
         return Output(self, x, self._ticket)
 
@@ -445,10 +496,12 @@ class SparseAutoencoder(torch.nn.Module):
         raise RuntimeError("remove_parallel_grads(): gradients were not produced by the fused backward")
 
     def _require_topk(self):
-        """TopK (sparse path) and Relu (dense path) have CUDA paths; BatchTopK does not."""
-        if _kind(self.cfg.activation) not in ("TopK", "Relu"):
-            raise NotImplementedError(f"activation {_kind(self.cfg.activation)} has no CUDA path in saev_b200 "
-                                      "(TopK and Relu only)")
+        """TopK / BatchTopK (sparse path) and Relu (dense path) have CUDA paths."""
+        if _kind(self.cfg.activation) not in ("TopK", "Relu", "BatchTopK"):
+            raise NotImplementedError(f"activation {_kind(self.cfg.activation)} has no CUDA path in saev_b200")
+        if _kind(self.cfg.activation) == "BatchTopK" and self._dp_world > 1:
+            raise NotImplementedError("BatchTopK selects over the whole batch and does not shard across ranks "
+                                      "(SURVEY 8e): run it on one GPU")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -482,6 +535,8 @@ class MatryoshkaLoss:
                 # rows the tensor-core screen could not certify and the exact fp32 path re-did (cumulative); not a
                 # reference key -- it shows up as loss/screen_repaired_rows in saev's log block (train.py:420)
                 out["screen_repaired_rows"] = self._sae.engine.screen_stats()["repaired"]
+            if self._sae.engine is not None and self._sae.engine.cfg.batch_k > 0:
+                self._sae.check_batch_topk()
         return out
 
 
@@ -536,9 +591,11 @@ class MatryoshkaObjective(torch.nn.Module):
 
     def forward(self, sae: SparseAutoencoder, x: Tensor):
         sae._require_topk()
-        if self.cfg.n_prefixes > 1 and _kind(sae.cfg.activation) != "TopK":
-            raise NotImplementedError("Matryoshka(n_prefixes > 1) has a CUDA path for the TopK activation only; "
-                                      "use n_prefixes=1 with Relu")
+        if self.cfg.n_prefixes > 1 and _kind(sae.cfg.activation) == "Relu":
+            raise NotImplementedError("Matryoshka(n_prefixes > 1) has a CUDA path for the TopK / BatchTopK activations "
+                                      "only; use n_prefixes=1 with Relu")
+        if _kind(sae.cfg.activation) == "BatchTopK" and sae.training != self.training:
+            raise NotImplementedError("BatchTopK: the SAE and the objective must be in the same train/eval mode")
         x = x.contiguous()
         eng = sae._bind(x.shape[0], self.cfg)
         # objectives.py:125: the cuts are drawn on the host from the global torch generator, every forward

@@ -8,14 +8,16 @@ from oracle import sae_oracle as orc
 
 GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 CASES = ["tiny_topk_auxk", "tiny_topk_auxk_clamp", "tiny_topk_noaux_noproj", "tiny_relu_l1_auxk", "c1_topk",
-         "c1_topk_auxk_live", "tiny_topk_matryoshka", "c1_topk_matryoshka"]
+         "c1_topk_auxk_live", "tiny_topk_matryoshka", "c1_topk_matryoshka", "tiny_batchtopk_auxk",
+         "c1_batchtopk", "c1_batchtopk_matryoshka"]
 
 
 def load_case(name):
     z = np.load(GOLDEN / f"{name}.npz")
     meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
     cfg = orc.OracleConfig(
-        d_model=meta["D"], d_sae=meta["S"], activation="topk" if meta["act"] == 0 else "relu", top_k=max(meta["top_k"], 1),
+        d_model=meta["D"], d_sae=meta["S"], activation=("topk", "relu", "batchtopk")[meta["act"]], top_k=max(meta["top_k"], 1),
+        batch_momentum=meta.get("momentum", 0.1),
         l1_coeff=meta["l1_coeff"], aux=bool(meta["aux"]), k_aux=max(meta["k_aux"], 1), aux_alpha=meta["alpha"],
         dead_threshold_tokens=meta["dead_thr"], normalize_w_dec=bool(meta["normalize"]),
         remove_parallel_grads=bool(meta["remove_parallel"]), lr=meta["lr"], n_lr_warmup=meta["n_warmup"],

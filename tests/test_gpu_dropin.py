@@ -18,13 +18,16 @@ def _make(z, meta, cfg):
     if cfg.activation == "relu":
         sp = nn.L1Sparsity(coeff=cfg.l1_coeff) if cfg.l1_coeff else nn.NoSparsity()
         act = nn.Relu(sparsity=sp, aux=aux)
+    elif cfg.activation == "batchtopk":
+        act = nn.BatchTopK(top_k=cfg.top_k, momentum=cfg.batch_momentum, aux=aux)
     else:
         act = nn.TopK(top_k=cfg.top_k, aux=aux)
     sae_cfg = nn.SparseAutoencoderConfig(
         d_model=cfg.d_model, d_sae=cfg.d_sae, activation=act, reinit_blend=0.0,
         remove_parallel_grads=cfg.remove_parallel_grads, normalize_w_dec=cfg.normalize_w_dec)
     sae = nn.SparseAutoencoder(sae_cfg)
-    sae.load_state_dict({k: t(z[f"init_{k}"]) for k in ("W_dec", "b_dec", "W_enc", "b_enc")})
+    keys = ("W_dec", "b_dec", "W_enc", "b_enc") + (("activation.threshold",) if cfg.activation == "batchtopk" else ())
+    sae.load_state_dict({k: t(z[f"init_{k}"]) for k in keys})
     objective = nn.get_objective(nn.Matryoshka(n_prefixes=max(1, meta.get("n_prefixes", 1)),
                                                dead_threshold_tokens=cfg.dead_threshold_tokens))
     return sae, objective
@@ -61,6 +64,8 @@ def test_loop_body_through_the_nn_api(name):
         assert int(m["n_dead"]) == int(z["rec_n_dead"][step])
         assert grad_norm.item() == pytest.approx(float(z["rec_grad_norm"][step]), rel=TOL)
         assert opt.param_groups[0]["lr"] == pytest.approx(float(z["rec_lr"][step]), rel=1e-12, abs=0)
+        if cfg.activation == "batchtopk":  # the EMA buffer of BatchTopKActivation (modeling.py:213,237-242)
+            assert float(sae.activation.threshold) == pytest.approx(float(z["rec_threshold"][step]), rel=1e-5), step
         if step in grad_steps:
             i = grad_steps.index(step)
             coef = min(1.0, cfg.grad_clip / (grad_norm.item() + 1e-6))
@@ -73,6 +78,8 @@ def test_loop_body_through_the_nn_api(name):
             assert fwd.f_x.shape == (meta["B"], cfg.d_sae)
             if cfg.activation == "topk":
                 assert int((fwd.f_x != 0).sum(1).max()) <= cfg.top_k
+            elif cfg.activation == "batchtopk":  # exactly k * B survivors over the whole batch (modeling.py:206)
+                assert int((fwd.f_x != 0).sum()) == cfg.top_k * meta["B"]
             else:
                 assert bool((fwd.f_x >= 0).all())
         opt.step()
@@ -80,7 +87,7 @@ def test_loop_body_through_the_nn_api(name):
         opt.zero_grad()
         assert sae.W_dec.grad is None
     sd = sae.state_dict()
-    assert list(sd) == ["W_dec", "b_dec", "W_enc", "b_enc"]
+    assert list(sd) == ["W_dec", "b_dec", "W_enc", "b_enc"] + (["activation.threshold"] if cfg.activation == "batchtopk" else [])
     for k in sd:
         assert rel_l2(sd[k].cpu(), z[f"final_{k}"]) < TOL, k
     assert torch.equal(objective.toks_since_active.cpu(), t(z["toks_since_active"]))
@@ -89,7 +96,36 @@ def test_loop_body_through_the_nn_api(name):
     objective.eval()
     loss, fwd = objective(sae, xs[-1].to("cuda"))
     assert loss.mse.item() == pytest.approx(float(z["eval_mse"]), rel=TOL)
+    assert loss.l0.item() == pytest.approx(float(z["eval_l0"]), rel=TOL)  # (BatchTopK: JumpReLU with the EMA threshold)
     assert loss.aux.item() == 0.0 and int(loss.n_dead) == 0
+    loss.metrics()  # BatchTopK: raises if a row ran out of slots
+
+
+def test_batchtopk_checkpoint_keeps_the_threshold(tmp_path):
+    """modeling.py:213: `threshold` is a registered buffer, so it travels in the state_dict / checkpoint."""
+    z, meta, cfg = load_case("tiny_batchtopk_auxk")
+    sae, objective = _make(z, meta, cfg)
+    sae, objective = sae.to("cuda").train(), objective.to("cuda").train()
+    objective(sae, t(z["xs"])[0].to("cuda"))
+    thr = float(sae.activation.threshold)
+    assert thr == pytest.approx(float(z["rec_threshold"][0]), rel=1e-5)
+    nn.dump(tmp_path / "sae.pt", sae)
+    back = nn.load(tmp_path / "sae.pt")
+    assert back.cfg == sae.cfg and float(back.activation.threshold) == thr
+
+
+def test_batchtopk_row_out_of_slots_is_reported(monkeypatch):
+    """With 16 slots per row (SAEV_B200_BATCHTOPK_CAP) the planted batches have rows that own more of the batch's
+    k * B winners than they can hold: the selection kernel counts them and Loss.metrics() raises instead of training
+    on a selection that differs from the reference's."""
+    monkeypatch.setenv("SAEV_B200_BATCHTOPK_CAP", "16")
+    z, meta, cfg = load_case("tiny_batchtopk_auxk")
+    sae, objective = _make(z, meta, cfg)
+    sae, objective = sae.to("cuda").train(), objective.to("cuda").train()
+    loss, _ = objective(sae, t(z["xs"])[0].to("cuda"))
+    assert sae.engine.cfg.top_k == 16 and sae.engine.batch_topk_stats()["truncated_rows"] > 0
+    with pytest.raises(RuntimeError, match="slots per row"):
+        loss.metrics()
 
 
 def test_checkpoint_round_trip(tmp_path):
@@ -105,12 +141,9 @@ def test_checkpoint_round_trip(tmp_path):
 
 
 def test_unsupported_configs_fail_loudly():
-    sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=256, activation=nn.BatchTopK(top_k=8),
-                                                          reinit_blend=0.0)).to("cuda")
-    with pytest.raises(NotImplementedError):
-        sae(torch.randn(4, 64, device="cuda"))
-    sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=256, activation=nn.TopK(top_k=8),
-                                                          reinit_blend=0.0)).to("cuda")
+    with pytest.raises(NotImplementedError, match="cannot even hold the average"):  # more than 128 actives per row
+        nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=512, activation=nn.BatchTopK(top_k=200),
+                                                        reinit_blend=0.0)).to("cuda")(torch.randn(4, 64, device="cuda"))
     sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=256, activation=nn.Relu(),
                                                           reinit_blend=0.0)).to("cuda")
     obj = nn.get_objective(nn.Matryoshka(n_prefixes=4))

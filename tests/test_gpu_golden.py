@@ -21,10 +21,15 @@ TOPK_CASES = [c for c in CASES if "relu" not in c]
 
 def _engine_for(meta, cfg, B):
     from saev_b200.engine import Engine, EngineConfig
+    from saev_b200.nn import batch_topk_capacity
 
+    act, top_k, batch_k = cfg.activation, cfg.top_k, 0
+    if act == "batchtopk":  # sparse path: `top_k` = slots per row, `batch_k` = BatchTopK.top_k
+        act, batch_k, top_k = "topk", cfg.top_k, batch_topk_capacity(cfg.top_k, cfg.d_sae, meta.get("n_prefixes", 1))
     return Engine(
         EngineConfig(
-            d_model=cfg.d_model, d_sae=cfg.d_sae, top_k=cfg.top_k, activation=cfg.activation, aux=cfg.aux,
+            d_model=cfg.d_model, d_sae=cfg.d_sae, top_k=top_k, activation=act, aux=cfg.aux, batch_k=batch_k,
+            batch_momentum=cfg.batch_momentum,
             k_aux=cfg.k_aux, aux_alpha=cfg.aux_alpha, l1_coeff=cfg.l1_coeff,
             dead_threshold_tokens=cfg.dead_threshold_tokens, remove_parallel_grads=cfg.remove_parallel_grads,
             normalize_w_dec=cfg.normalize_w_dec, max_batch=B, max_prefixes=max(1, meta.get("n_prefixes", 1)),
@@ -53,6 +58,10 @@ def test_cuda_path_replays_reference_run(name):
         for key in ("mse", "aux", "sparsity", "l0", "l1", "loss"):
             assert ld[key] == pytest.approx(float(z[f"rec_{key}"][step]), rel=TOL, abs=1e-7), (step, key)
         assert int(ld["n_dead"]) == int(z["rec_n_dead"][step]), step
+        if cfg.activation == "batchtopk":
+            st = eng.batch_topk_stats()
+            assert st["kept"] == cfg.top_k * B and st["truncated_rows"] == 0, (step, st)
+            assert float(eng.threshold) == pytest.approx(float(z["rec_threshold"][step]), rel=1e-5), step
         gn = float(eng.sumsq.sqrt())
         assert gn == pytest.approx(float(z["rec_grad_norm"][step]), rel=TOL), step
         if step in grad_steps:
@@ -84,8 +93,63 @@ def test_cuda_path_replays_reference_run(name):
     assert ld["l0"] == pytest.approx(float(z["eval_l0"]), rel=TOL)
     assert ld["aux"] == 0.0 and ld["n_dead"] == 0.0
     assert rel_l2(eng.x_hat(x).cpu(), z["eval_x_hat"]) < TOL
-    if cfg.activation == "topk":
+    if cfg.activation == "batchtopk":
+        assert eng.batch_topk_stats()["truncated_rows_total"] == 0
+    if cfg.activation != "relu":
         _assert_screen_clean(eng)
+
+
+def _identity_engine(S, k, B, dec_scale=1.0):
+    """D = S, W_enc = W_dec = I, zero biases: the pre-activations ARE the inputs, so the hand-computed cases of the
+    reference's activation tests can be fed through the fused forward."""
+    from saev_b200.engine import Engine, EngineConfig
+
+    eng = Engine(EngineConfig(d_model=S, d_sae=S, top_k=S, batch_k=k, activation="topk", aux=False, normalize_w_dec=False,
+                              remove_parallel_grads=False, max_batch=B))
+    eye = torch.eye(S)
+    eng.load_params(eye, torch.zeros(S), dec_scale * eye, torch.zeros(S))
+    return eng
+
+
+def test_batchtopk_known_answers():
+    """/root/reference/tests/test_nn_activations.py:171-233 through the CUDA path (columns padded with values below every
+    entry of the case): basic, uneven distribution across rows, ties (exactly k * B survive), k exceeding the element
+    count, and the gradient mask (:237-252: d f / d h = 1 on the survivors, 0 elsewhere -> gb_enc counts them)."""
+    S = 8
+    pad = lambda rows, fill: torch.tensor([r + [fill] * (S - len(r)) for r in rows]).cuda()  # noqa: E731
+    eng = _identity_engine(S, 2, 2)
+    eng.forward(pad([[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]], 0.0), training=True)
+    assert eng.dense_f_x(2)[:, :3].tolist() == [[5.0, 0.0, 3.0], [2.0, 4.0, 0.0]]
+    assert float(eng.threshold) == pytest.approx(0.1 * 2.0)
+    eng.forward(pad([[10.0, 20.0, 30.0], [1.0, 2.0, 3.0]], 0.0), training=True)
+    assert eng.dense_f_x(2)[:, :3].tolist() == [[10.0, 20.0, 30.0], [0.0, 0.0, 3.0]]
+    x = pad([[2.0, 2.0, 2.0], [2.0, 2.0, 2.0]], 0.0)
+    eng.forward(x, training=True)
+    f = eng.dense_f_x(2)
+    assert int((f != 0).sum()) == 4 and set(f[f != 0].tolist()) == {2.0}
+    st = eng.batch_topk_stats()
+    assert st["kept"] == 4 and st["ties"] == 6 and st["truncated_rows"] == 0
+    # gradient mask (:237-252): with W_dec = 2 I the residual on a survivor is its own value, so
+    # d loss / d h[b, j] = 2 / (B D) * 2 * h[b, j] on the survivors and 0 on every other entry
+    eng = _identity_engine(S, 2, 2, dec_scale=2.0)
+    x = pad([[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]], 0.0)
+    eng.forward(x, training=True)
+    eng.backward(x)
+    assert eng.gb_enc.tolist() == pytest.approx([0.25 * (5 + 2), 0.25 * 4, 0.25 * 3, 0, 0, 0, 0, 0])
+    # k exceeds the number of elements: everything survives (:184-193)
+    eng = _identity_engine(S, 8, 2)
+    x = pad([[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]], 0.5)
+    eng.forward(x, training=True)
+    assert torch.equal(eng.dense_f_x(2), x)
+    # eval: JumpReLU with the stored threshold (:220-224); threshold <= 0 -> ReLU
+    eng = _identity_engine(S, 2, 2)
+    h = pad([[0.5, -1.0, 2.0], [0.0625, 0.375, -0.25]], -3.0)
+    eng.threshold.fill_(0.25)
+    eng.forward(h, training=False)
+    assert eng.dense_f_x(2)[:, :3].tolist() == [[0.5, 0.0, 2.0], [0.0, 0.375, 0.0]]
+    eng.threshold.fill_(0.0)
+    eng.forward(h, training=False)
+    assert eng.dense_f_x(2)[:, :3].tolist() == [[0.5, 0.0, 2.0], [0.0625, 0.375, 0.0]]
 
 
 @pytest.mark.parametrize("name", ["c1_topk_auxk_live", "tiny_topk_auxk_clamp"])
@@ -123,7 +187,7 @@ def _assert_screen_clean(eng):
 
 # ---- mid-size parity against the oracle on seeded inputs (sizes the CPU oracle finishes in seconds) ----
 @pytest.mark.parametrize("act,D,S,K,B", [("topk", 256, 4096, 32, 1024), ("topk", 768, 8192, 32, 640), ("relu", 192, 2048, 0, 520),
-                                          ("topk", 128, 1000, 16, 300)])
+                                          ("topk", 128, 1000, 16, 300), ("topk", 256, 4096, 128, 520)])
 @pytest.mark.parametrize("aux_path", ["tc", "sgemm", "auto"])
 def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
     _midsize_run(act, D, S, K, B, aux_path, monkeypatch)

@@ -25,6 +25,8 @@ def test_oracle_replays_reference_run(name):
         for key in ("mse", "aux", "sparsity", "l0", "l1", "grad_norm", "loss"):
             assert out[key] == pytest.approx(float(z[f"rec_{key}"][step]), rel=TOL, abs=1e-7), (step, key)
         assert out["n_dead"] == int(z["rec_n_dead"][step]), step
+        if cfg.activation == "batchtopk":  # EMA of the smallest positive survivor (modeling.py:237-242)
+            assert st.threshold == pytest.approx(float(z["rec_threshold"][step]), rel=1e-6), step
         if step in grad_steps:
             i = grad_steps.index(step)
             for k in ("W_enc", "b_enc", "W_dec", "b_dec"):
@@ -110,6 +112,22 @@ def test_topk_known_answers():
     assert f.tolist() == [[0.0, -1.0, 0.0, -2.0]]
     f, _ = orc.topk_activation(torch.tensor([[1.0, 2.0]]), 5)  # k > d_sae clamps (modeling.py:175)
     assert f.tolist() == [[1.0, 2.0]]
+
+
+def test_batch_topk_known_answers():
+    """/root/reference/tests/test_nn_activations.py:171-233: basic, k exceeds the element count, single row, uneven
+    distribution across rows, ties (exactly k * B survive); :220-224 eval = JumpReLU with the stored threshold."""
+    bt = lambda h, k: orc.batch_topk_activation(torch.tensor(h), k, True, 0.0, 0.1)  # noqa: E731
+    assert bt([[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]], 2)[0].tolist() == [[5.0, 0.0, 3.0], [2.0, 4.0, 0.0]]
+    assert bt([[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]], 8)[0].tolist() == [[5.0, 1.0, 3.0], [2.0, 4.0, 1.0]]
+    assert bt([[1.0, 2.0, 3.0, 4.0]], 2)[0].tolist() == [[0.0, 0.0, 3.0, 4.0]]
+    assert bt([[10.0, 20.0, 30.0], [1.0, 2.0, 3.0]], 2)[0].tolist() == [[10.0, 20.0, 30.0], [0.0, 0.0, 3.0]]
+    f, mask, thr = bt([[2.0, 2.0, 2.0], [2.0, 2.0, 2.0]], 2)
+    assert int(mask.sum()) == 4 and set(f[f != 0].tolist()) == {2.0}
+    assert thr == pytest.approx(0.1 * 2.0)  # threshold <- 0.9 * 0 + 0.1 * min positive survivor
+    h = torch.tensor([[0.5, -1.0, 2.0], [0.0625, 0.375, -0.25]])
+    assert orc.batch_topk_activation(h, 2, False, 0.25, 0.1)[0].tolist() == [[0.5, 0.0, 2.0], [0.0, 0.375, 0.0]]
+    assert orc.batch_topk_activation(h, 2, False, 0.0, 0.1)[0].tolist() == [[0.5, 0.0, 2.0], [0.0625, 0.375, 0.0]]
 
 
 def test_mean_squared_err_known_answers():

@@ -83,7 +83,7 @@ def test_create_rejects_bad_configs(lib):
     assert rc(top_k=0)[0] == 2
     assert rc(top_k=1024)[0] == 2  # > d_sae
     assert rc(d_sae=510)[0] == 2
-    code, msg = rc(top_k=128, d_sae=4096)
+    code, msg = rc(top_k=200, d_sae=4096)  # > 128: the screen kernel's row capacity
     assert code == 3 and b"top_k" in msg
 
 

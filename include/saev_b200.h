@@ -230,7 +230,8 @@ int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float*
 /* Matryoshka prefix cuts for the following forward/backward calls (saev samples them per step on the host,
  * objectives.py:125,158-201): n strictly increasing column counts, the last one == d_sae.  n == 1 (or NULL) selects
  * the plain single-prefix objective.  x_hat_i = b_dec + sum of the active columns below cut i; the MSE is the mean
- * over batch x prefixes x d_model; AuxK and `resid` refer to the last (full) prefix. */
+ * over batch x prefixes x d_model; AuxK and `resid` refer to the last (full) prefix.  TopK: one sparse decode that emits
+ * every prefix (top_k <= 64).  ReLU: the decoder, dh and W_dec-gradient contractions run once per prefix block. */
 int saev_b200_set_prefixes(saev_b200_handle* h, const int32_t* host_prefixes, int32_t n);
 /* x_hats[B, n_prefixes, d_model] of the last forward (modeling.py:406); n_prefixes == 1 reduces to saev_b200_x_hat. */
 int saev_b200_x_hats(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hats_out,

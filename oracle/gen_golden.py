@@ -201,6 +201,10 @@ def main():
              activation=M.TopK(top_k=16, aux=M.AuxK(k_aux=64, alpha=1 / 32)),
              dead_thr=2 * 256, lr=2e-3, n_warmup=3, sched_steps=6, data="planted", save_grads_every=5, seed=19,
              n_prefixes=10)
+    # (7b) ReLU + L1 + AuxK under Matryoshka prefixes (the dense path with per-block contractions)
+    run_case("tiny_relu_matryoshka", D=32, S=256, B=64, n_steps=8,
+             activation=M.Relu(sparsity=M.L1Sparsity(coeff=4e-4), aux=M.AuxK(k_aux=16, alpha=1 / 32)),
+             dead_thr=3 * 64, lr=1e-2, n_warmup=4, sched_steps=8, data="planted", seed=37, b_enc_shift=-1.5, n_prefixes=4)
     # (8) BatchTopK (modeling.py:183-244): batch-wide top-(k B) selection in training, EMA threshold, JumpReLU in the
     #     eval forward; planted data so that the per-row counts differ and latents die (AuxK live)
     run_case("tiny_batchtopk_auxk", D=32, S=256, B=64, n_steps=10,

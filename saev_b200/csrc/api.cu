@@ -24,6 +24,7 @@ struct Workspace {
   size_t shadow_hi, x_hi, cand, tau_keys, cand_cnt, row_norm, row_dx, row_scale, unsafe_list, wnorm_rows, guess_hist, guess_L, dh, row_sse, row_l1, row_l0, row_sse_aux, feat_count, feat_off, cursor,
       entries, heavy_list, active, dead_list, scalars, block_totals, row_gsq, colsum_partial, sumsq_partial, h_aux, mask_aux, r_aux, aux_colpart, total;
   size_t btk;  // BatchTopK selection scratch (batch_topk_scratch_bytes)
+  size_t yblk; // dense path with Matryoshka prefixes: [P][B][D] fp32 partial decodes of the prefix blocks
   size_t sfx;  // Matryoshka: [B, max_prefixes, D] suffix sums of the per-prefix residuals
   // tensor-core AuxK path: bf16 piece buffers (3 pieces each, see AuxArgs)
   size_t tc_we[3], tc_wd[3], tc_wdT[3], tc_x[3], tc_xT[3], tc_f[3], tc_fT[3], tc_r[3], tc_rT[3];
@@ -127,10 +128,13 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.x_lo = take(B * D * 2);
     w.xT_hi = take((D + 16) * LB * 2);
     w.xT_lo = take((D + 16) * LB * 2);
-    w.g_hi = take(B * D * 2);
-    w.g_lo = take(B * D * 2);
-    w.gT_hi = take(D * LB * 2);
-    w.gT_lo = take(D * LB * 2);
+    // (with Matryoshka prefixes: one G = grad_scale * suffix-sum residual per prefix block, stacked)
+    const size_t PF = c.max_prefixes > 1 ? static_cast<size_t>(c.max_prefixes) : 1;
+    w.g_hi = take(PF * B * D * 2);
+    w.g_lo = take(PF * B * D * 2);
+    w.gT_hi = take(PF * D * LB * 2);
+    w.gT_lo = take(PF * D * LB * 2);
+    w.yblk = take(PF > 1 ? PF * B * D * 4 : 0);
     w.f_hi = take(B * S * 2);
     w.f_lo = take(B * S * 2);
     w.fT_hi = take(S * LB * 2);
@@ -143,8 +147,8 @@ Workspace plan_workspace(const saev_b200_cfg& c, int aux_cap, int max_pairs, int
     w.w_decT_l2 = take(third ? D * S * 2 : 0);
     w.x_l2 = take(third ? B * D * 2 : 0);
     w.xT_l2 = take(third ? (D + 16) * LB * 2 : 0);
-    w.g_l2 = take(third ? B * D * 2 : 0);
-    w.gT_l2 = take(third ? D * LB * 2 : 0);
+    w.g_l2 = take(third ? PF * B * D * 2 : 0);
+    w.gT_l2 = take(third ? PF * D * LB * 2 : 0);
     w.f_l2 = take(third ? B * S * 2 : 0);
     w.fT_l2 = take(third ? S * LB * 2 : 0);
     w.dhT_l2 = take(third ? S * LB * 2 : 0);
@@ -342,23 +346,57 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
   }
   {
     StageTimer tm(h, SAEV_B200_STAGE_DECODE, s);
-    // x_hat = f W_dec + b_dec, then r = x_hat - x, SSE partials and G = 2 r / (B D)
-    EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, bf(w.w_decT_hi), bf(w.w_decT_lo),
-                                  b3(w.w_decT_l2), S, B, D, S, 1);
-    g.bias = b_dec;
-    g.out = resid;
-    g.ldo = D;
-    if (int rc = launch_encode_gemm(g, s)) {
-      char buf[64];
-      snprintf(buf, sizeof(buf), "%d", rc);
-      return fail(h, 44, "forward(relu): decoder contraction launch failed (code %s)", buf);
+    const int P = h->pf.n;
+    h->pf_fwd = h->pf;
+    const float gs = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * P * D));
+    const long long LB = w.ldb, BD = static_cast<long long>(B) * D;
+    if (P <= 1) {
+      // x_hat = f W_dec + b_dec, then r = x_hat - x, SSE partials and G = 2 r / (B D)
+      EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, bf(w.w_decT_hi), bf(w.w_decT_lo),
+                                    b3(w.w_decT_l2), S, B, D, S, 1);
+      g.bias = b_dec;
+      g.out = resid;
+      g.ldo = D;
+      if (int rc = launch_encode_gemm(g, s)) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%d", rc);
+        return fail(h, 44, "forward(relu): decoder contraction launch failed (code %s)", buf);
+      }
+      if (launch_dense_resid(resid, x, B, D, gs, at<float>(workspace, w.row_sse), training ? bf(w.g_hi) : nullptr,
+                             training ? bf(w.g_lo) : nullptr, s, training ? b3(w.g_l2) : nullptr))
+        return fail(h, 44, "forward(relu): residual launch failed%s");
+      if (training && launch_transpose_split(resid, B, D, gs, bf(w.gT_hi), bf(w.gT_lo), w.ldb, 0, D, s, b3(w.gT_l2)))
+        return fail(h, 44, "forward(relu): G^T launch failed%s");
+    } else {
+      // Matryoshka (modeling.py:364-406): one decoder contraction per prefix block, over the dictionary columns
+      // [cut_{c-1}, cut_c) only (a window on the same K-major operands: the tensor maps end at cut_c, the TMA
+      // coordinates start at cut_{c-1}), each into its own partial reconstruction y_c; b_dec rides on block 0
+      float* y = at<float>(workspace, w.yblk);
+      for (int cb = 0; cb < P; ++cb) {
+        EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, bf(w.w_decT_hi), bf(w.w_decT_lo),
+                                      b3(w.w_decT_l2), S, B, D, h->pf.cut[cb], 1);
+        g.k_begin = cb > 0 ? h->pf.cut[cb - 1] : 0;
+        g.bias = cb == 0 ? b_dec : nullptr;
+        g.out = y + cb * BD;
+        g.ldo = D;
+        if (int rc = launch_encode_gemm(g, s)) {
+          char buf[64];
+          snprintf(buf, sizeof(buf), "%d", rc);
+          return fail(h, 44, "forward(relu): prefix-block decoder contraction launch failed (code %s)", buf);
+        }
+      }
+      float* sfx = at<float>(workspace, w.sfx);
+      if (launch_dense_prefix_resid(y, x, B, D, P, gs, resid, sfx, at<float>(workspace, w.row_sse),
+                                    training ? bf(w.g_hi) : nullptr, training ? bf(w.g_lo) : nullptr,
+                                    training ? b3(w.g_l2) : nullptr, s))
+        return fail(h, 44, "forward(relu): prefix residual launch failed%s");
+      if (training)
+        for (int cb = 0; cb < P; ++cb)  // G_c^T [D, ldb], the operand of the per-block W_dec gradient
+          if (launch_transpose_split(sfx + static_cast<long long>(cb) * D, B, D, gs, bf(w.gT_hi) + cb * D * LB,
+                                     bf(w.gT_lo) + cb * D * LB, w.ldb, 0, D, s, third ? bf(w.gT_l2) + cb * D * LB : nullptr,
+                                     nullptr, static_cast<long long>(P) * D))
+            return fail(h, 44, "forward(relu): G^T launch failed%s");
     }
-    const float gs = static_cast<float>(2.0 / (static_cast<double>(tokens_global) * D));
-    if (launch_dense_resid(resid, x, B, D, gs, at<float>(workspace, w.row_sse), training ? bf(w.g_hi) : nullptr,
-                           training ? bf(w.g_lo) : nullptr, s, training ? b3(w.g_l2) : nullptr))
-      return fail(h, 44, "forward(relu): residual launch failed%s");
-    if (training && launch_transpose_split(resid, B, D, gs, bf(w.gT_hi), bf(w.gT_lo), w.ldb, 0, D, s, b3(w.gT_l2)))
-      return fail(h, 44, "forward(relu): G^T launch failed%s");
   }
   return 0;
 }
@@ -373,31 +411,42 @@ int backward_relu(saev_b200_handle* h, const float* x, int B, long long tokens_g
   const bool third = h->dense_terms == 6;
   auto b3 = [&](size_t off) { return third ? at<__nv_bfloat16>(workspace, off) : nullptr; };
   StageTimer tm(h, SAEV_B200_STAGE_WGRAD, s);
-  // dh = (f > 0) * (G W_dec^T + l1 / B), stored transposed as the operand of the W_enc gradient
-  EncodeGemmArgs g3 = dense_gemm(h, bf(w.g_hi), bf(w.g_lo), b3(w.g_l2), D, bf(w.w_dec_hi), bf(w.w_dec_lo), b3(w.w_dec_l2),
-                                 D, B, S, D, 3);
-  g3.f_hi = bf(w.f_hi);
-  g3.ldf = S;
-  g3.t_hi = bf(w.dhT_hi);
-  g3.t_lo = bf(w.dhT_lo);
-  g3.t_lo2 = b3(w.dhT_l2);
-  g3.ldt = w.ldb;
-  g3.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
-  if (int rc = launch_encode_gemm(g3, s)) {
-    char buf[32];
-    snprintf(buf, sizeof(buf), "%d", rc);
-    return fail(h, 52, "backward(relu): dh contraction launch failed (code %s)", buf);
+  // dh = (f > 0) * (G W_dec^T + l1 / B), stored transposed as the operand of the W_enc gradient.  With Matryoshka
+  // prefixes the columns of block c see G_c = the suffix sum of the per-prefix residual gradients: one contraction per
+  // block over the dictionary columns [cut_{c-1}, cut_c)
+  const int P = h->pf_fwd.n;
+  const long long LB = w.ldb, BD = static_cast<long long>(B) * D;
+  for (int cb = 0; cb < P; ++cb) {
+    EncodeGemmArgs g3 = dense_gemm(h, bf(w.g_hi) + cb * BD, bf(w.g_lo) + cb * BD, third ? bf(w.g_l2) + cb * BD : nullptr, D,
+                                   bf(w.w_dec_hi), bf(w.w_dec_lo), b3(w.w_dec_l2), D, B, P > 1 ? h->pf_fwd.cut[cb] : S, D, 3);
+    g3.n_begin = cb > 0 ? h->pf_fwd.cut[cb - 1] : 0;
+    g3.f_hi = bf(w.f_hi);
+    g3.ldf = S;
+    g3.t_hi = bf(w.dhT_hi);
+    g3.t_lo = bf(w.dhT_lo);
+    g3.t_lo2 = b3(w.dhT_l2);
+    g3.ldt = w.ldb;
+    g3.l1_over_b = c.l1_coeff != 0.f ? static_cast<float>(c.l1_coeff / static_cast<double>(tokens_global)) : 0.f;
+    if (int rc = launch_encode_gemm(g3, s)) {
+      char buf[32];
+      snprintf(buf, sizeof(buf), "%d", rc);
+      return fail(h, 52, "backward(relu): dh contraction launch failed (code %s)", buf);
+    }
   }
   // x^T with an extra row of ones: column D of the next product is sum_b dh = gb_enc
   if (launch_transpose_split(x, B, D, 1.f, bf(w.xT_hi), bf(w.xT_lo), w.ldb, 1, D + 16, s, b3(w.xT_l2)))
     return fail(h, 52, "backward(relu): x^T launch failed%s");
-  // gW_dec = f^T G
-  EncodeGemmArgs g4 = dense_gemm(h, bf(w.fT_hi), bf(w.fT_lo), b3(w.fT_l2), w.ldb, bf(w.gT_hi), bf(w.gT_lo), b3(w.gT_l2),
-                                 w.ldb, S, D, B, 4);
-  g4.out = gW_dec;
-  g4.ldo = D;
-  g4.n_main = D;
-  if (launch_encode_gemm(g4, s)) return fail(h, 52, "backward(relu): gW_dec contraction launch failed%s");
+  // gW_dec = f^T G  (per prefix block: the rows [cut_{c-1}, cut_c) of f^T against G_c^T)
+  for (int cb = 0; cb < P; ++cb) {
+    EncodeGemmArgs g4 = dense_gemm(h, bf(w.fT_hi), bf(w.fT_lo), b3(w.fT_l2), w.ldb, bf(w.gT_hi) + cb * D * LB,
+                                   bf(w.gT_lo) + cb * D * LB, third ? bf(w.gT_l2) + cb * D * LB : nullptr, w.ldb,
+                                   P > 1 ? h->pf_fwd.cut[cb] : S, D, B, 4);
+    g4.m_begin = cb > 0 ? h->pf_fwd.cut[cb - 1] : 0;
+    g4.out = gW_dec;
+    g4.ldo = D;
+    g4.n_main = D;
+    if (launch_encode_gemm(g4, s)) return fail(h, 52, "backward(relu): gW_dec contraction launch failed%s");
+  }
   if (c.remove_parallel_grads && launch_project_rows(gW_dec, W_dec, S, D, s))
     return fail(h, 52, "backward(relu): projection launch failed%s");
   // gW_enc_t = dh^T x ; gb_enc = dh^T 1
@@ -456,9 +505,9 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     delete h;
     return fail(nullptr, 2, "saev_b200_create: max_prefixes must be <= 32%s");
   }
-  if (h->cfg.max_prefixes > 1 && (cfg->act_kind != SAEV_B200_ACT_TOPK || cfg->top_k > 64)) {
+  if (h->cfg.max_prefixes > 1 && cfg->act_kind == SAEV_B200_ACT_TOPK && cfg->top_k > 64) {
     delete h;
-    return fail(nullptr, 3, "saev_b200_create: Matryoshka prefixes need the TopK path with top_k <= 64%s");
+    return fail(nullptr, 3, "saev_b200_create: Matryoshka prefixes on the TopK path need top_k <= 64%s");
   }
   h->max_prefixes = h->cfg.max_prefixes;
   h->pf.n = 1;
@@ -917,7 +966,7 @@ int bwd_bias_aux(const BwdCtx& c) {
   const saev_b200_cfg& cf = h->cfg;
   const Workspace& w = h->ws;
   const int D = cf.d_model;
-  const int P = cf.act_kind == SAEV_B200_ACT_TOPK ? h->pf_fwd.n : 1;
+  const int P = h->pf_fwd.n;
   const float grad_scale = static_cast<float>(2.0 / (static_cast<double>(c.tokens_global) * P * D));
   StageTimer tm_tail(h, SAEV_B200_STAGE_BIAS_AUX, c.s);
   // gb_dec = sum_b sum_i G_i: with prefixes that is the column sum of the block-0 suffix sums
@@ -1188,7 +1237,7 @@ int saev_b200_set_prefixes(saev_b200_handle* h, const int32_t* host_prefixes, in
 int saev_b200_x_hats(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hats_out,
                      void* workspace, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int P = h->cfg.act_kind == SAEV_B200_ACT_TOPK ? h->pf_fwd.n : 1;
+  const int P = h->pf_fwd.n;
   if (P <= 1) return saev_b200_x_hat(h, resid, x, B, x_hats_out, stream);
   if (!workspace) return fail(h, 71, "x_hats: workspace needed%s");
   if (launch_x_hats_prefix(at<float>(workspace, h->ws.sfx), x, B, h->cfg.d_model, P, x_hats_out, s))

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ dst_lo, long long ldr,
                                                               int ones_row, int C_pad,
                                                               __nv_bfloat16* __restrict__ dst_lo2,
-                                                              const int* __restrict__ gate) {
+                                                              const int* __restrict__ gate, long long src_ld) {
   __shared__ float tile[32][33];
   if (gate != nullptr && *gate == 0) return;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
   if (c0 < C) {
     for (int i = ty; i < 32; i += 8) {
       const int r = r0 + i, c = c0 + tx;
-      tile[i][tx] = (r < R && c < C) ? __ldg(src + static_cast<long long>(r) * C + c) * scale : 0.f;
+      tile[i][tx] = (r < R && c < C) ? __ldg(src + static_cast<long long>(r) * src_ld + c) * scale : 0.f;
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -61,10 +61,11 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
 
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
                            long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2,
-                           const int* gate) {
+                           const int* gate, long long src_ld) {
   if (R <= 0 || C <= 0) return 0;
   dim3 grid((R + 31) / 32, (C + 31) / 32 + (ones_row ? 1 : 0));
-  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad, dst_lo2, gate);
+  transpose_split_kernel<<<grid, 256, 0, s>>>(src, R, C, scale, dst_hi, dst_lo, ldr, ones_row, C_pad, dst_lo2, gate,
+                                              src_ld > 0 ? src_ld : C);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
@@ -100,6 +101,61 @@ __global__ void __launch_bounds__(256) dense_resid_kernel(float* __restrict__ xh
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
                        __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2) {
   dense_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(xhat, x, B, D, grad_scale, row_sse, g_hi, g_lo, g_lo2);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
+// Matryoshka prefixes on the dense path (saev modeling.py:364-406, objectives.py:124-138).  y[c][b][:] is the partial
+// decode of prefix block c (block 0 includes b_dec), so x_hat_i = sum_{c <= i} y_c and r_i = x_hat_i - x.  One warp per
+// row writes resid = r_{P-1} (AuxK / logging use the full prefix), row_sse[b] = sum_i ||r_i||^2, the suffix sums
+// sfx[b][c][:] = sum_{i >= c} r_i (what the columns of block c see in the backward pass; same layout as the sparse
+// path's, so gb_dec and x_hats come from the same kernels) and, when training, G_c = grad_scale * sfx_c as bf16 pieces
+// g[c][b][:] (operand of the per-block dh contraction).
+__global__ void __launch_bounds__(256) dense_prefix_resid_kernel(const float* __restrict__ y, const float* __restrict__ x, int B,
+                                                                 int D, int P, float grad_scale, float* __restrict__ resid,
+                                                                 float* __restrict__ sfx, float* __restrict__ row_sse,
+                                                                 __nv_bfloat16* __restrict__ g_hi,
+                                                                 __nv_bfloat16* __restrict__ g_lo,
+                                                                 __nv_bfloat16* __restrict__ g_lo2) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const long long BD = static_cast<long long>(B) * D, o = static_cast<long long>(b) * D;
+  float sse = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float xv = __ldg(x + o + d);
+    float r[MAX_PREFIXES];
+    float run = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < P; ++c) {
+      run += __ldg(y + c * BD + o + d);
+      r[c] = run - xv;
+      sse = fmaf(r[c], r[c], sse);
+    }
+    resid[o + d] = r[P - 1];
+    float suf = 0.f;
+#pragma unroll 1
+    for (int c = P - 1; c >= 0; --c) {
+      suf += r[c];
+      sfx[(static_cast<long long>(b) * P + c) * D + d] = suf;
+      if (g_hi != nullptr) {
+        __nv_bfloat16 h, l;
+        split1(suf * grad_scale, h, l);
+        g_hi[c * BD + o + d] = h;
+        g_lo[c * BD + o + d] = l;
+        if (g_lo2 != nullptr) g_lo2[c * BD + o + d] = split_third(suf * grad_scale, h, l);
+      }
+    }
+  }
+  sse = warp_sum(sse);
+  if (lane == 0) row_sse[b] = sse;
+}
+
+int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, int P, float grad_scale, float* resid,
+                              float* sfx, float* row_sse, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo, __nv_bfloat16* g_lo2,
+                              cudaStream_t s) {
+  if (P < 1 || P > MAX_PREFIXES) return 24;
+  dense_prefix_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(y, x, B, D, P, grad_scale, resid, sfx, row_sse, g_hi, g_lo, g_lo2);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

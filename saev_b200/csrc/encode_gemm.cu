@@ -50,6 +50,10 @@ struct EpiExtra {
   const int* row_map;      // EPI 4: output row index of accumulator row r (scatter into the full gradient)
   float alpha;             // EPI 1 / 4: scale of the accumulator
   int ksplit;              // EPI 1 / 4: CTAs sharing the K chunks of one output tile (>= 1)
+  // sub-range of the problem (Matryoshka prefix blocks of the dense path): rows [m_begin, M), columns [n_begin, N) and
+  // contraction elements [k_begin, K) of the operands the tensor maps describe; TMA coordinates and every epilogue
+  // address stay ABSOLUTE, so a block of dictionary columns is just a window on the full operands
+  int m_begin, n_begin, k_begin;
 };
 
 struct EncodeSmemLayout {
@@ -118,8 +122,8 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (ex.m_limit_dev != nullptr) M = min(M, *ex.m_limit_dev);
   if (ex.k_limit_dev != nullptr) kblocks_per_term = min(kblocks_per_term, (*ex.k_limit_dev + BK - 1) / BK);
   // nothing to do (no dead latents / rows past the dynamic row count): leave before any barrier or TMEM is touched
-  if (n_cols <= 0 || kblocks_per_term <= 0 || (blockIdx.x % m_blocks) * BM >= M) return;
-  const int n_tiles_total = (n_cols + BN - 1) / BN;
+  if (n_cols <= ex.n_begin || kblocks_per_term <= 0 || ex.m_begin + (blockIdx.x % m_blocks) * BM >= M) return;
+  const int n_tiles_total = (n_cols - ex.n_begin + BN - 1) / BN;
   int tile_begin = split * tiles_per_split;
   const int tile_end = min(n_tiles_total, tile_begin + tiles_per_split);
   if (EPI == 5) tile_begin = max(tile_begin, (m_blk * BM + 1) / BN);  // first tile holding a column > row
@@ -170,18 +174,18 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       uint32_t phase = 0;
       for (int vt = 0; vt < num_vtiles; ++vt) {
         const int t = vt / n_chunks, kc = chunk_begin + vt - t * n_chunks;
-        const int n0 = (tile_begin + t) * BN;
+        const int n0 = ex.n_begin + (tile_begin + t) * BN;
         const int clen = min(kchunk, kblocks_per_term - kc * kchunk);
         for (int kb = 0; kb < nterms * clen; ++kb) {
           const int term = kb / clen;
-          const int k0 = (kc * kchunk + kb - term * clen) * BK;
+          const int k0 = ex.k_begin + (kc * kchunk + kb - term * clen) * BK;
           // (A piece, B piece) per term: 0:(hi,hi) 1:(hi,lo) 2:(lo,hi) 3:(hi,lo2) 4:(lo2,hi) 5:(lo,lo)
           const CUtensorMap* ma = (term == 2 || term == 5) ? &tmA_lo : (term == 4 ? &tmA_lo2 : &tmA_hi);
           const CUtensorMap* mb = (term == 1 || term == 5) ? &tmB_lo : (term == 3 ? &tmB_lo2 : &tmB_hi);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tma_load_2d(sa, ma, full_bar(stage), k0, m_blk * BM);
+          tma_load_2d(sa, ma, full_bar(stage), k0, ex.m_begin + m_blk * BM);
           tma_load_2d(sa + A_BYTES, mb, full_bar(stage), k0, n0);
           if (++stage == STAGES) {
             stage = 0;
@@ -228,7 +232,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // ===================== epilogue =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     const int row_local = q * 32 + lane;    // accumulator row == TMEM lane
-    const int row = m_blk * BM + row_local;
+    const int row = ex.m_begin + m_blk * BM + row_local;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     float acc_l1 = 0.f, acc_l0 = 0.f;  // EPI 2
     float best = -1.f;                 // EPI 5
@@ -240,7 +244,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const bool accum = (vt - t * n_chunks) > 0 || ex.ksplit > 1;
       const int as = vt & 1;
       const uint32_t aphase = (vt >> 1) & 1u;
-      const int n0 = (tile_begin + t) * BN;
+      const int n0 = ex.n_begin + (tile_begin + t) * BN;
       float* bs = bias_s + as * BN;
       // Stage the bias slice of this tile (double buffered by accumulator stage; see barrier note below).
       for (int c = et; c < BN; c += 128) {
@@ -273,7 +277,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (EPI == 1) {
           if (row < M) {
             float* o = out + static_cast<long long>(row) * ldo + col0;
-            if (col0 + CHUNK <= n_cols && (ldo & 3) == 0) {
+            if (col0 + CHUNK <= n_cols && ((ldo | col0) & 3) == 0) {
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 4) {
                 if (accum) red_add_f32x4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -306,7 +310,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           if (rv) {
             __nv_bfloat16* fh = ex.f_hi + static_cast<long long>(row) * ex.ldf + col0;
             __nv_bfloat16* fl = ex.f_lo + static_cast<long long>(row) * ex.ldf + col0;
-            if (col0 + CHUNK <= n_cols && (ex.ldf & 7) == 0) {
+            if (col0 + CHUNK <= n_cols && ((ex.ldf | col0) & 7) == 0) {
               *reinterpret_cast<uint4*>(fh) = *reinterpret_cast<const uint4*>(&hi[0]);
               *reinterpret_cast<uint4*>(fh + 8) = *reinterpret_cast<const uint4*>(&hi[8]);
               *reinterpret_cast<uint4*>(fl) = *reinterpret_cast<const uint4*>(&lo[0]);
@@ -339,7 +343,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           if (row < M) {
             __align__(16) __nv_bfloat16 fh[CHUNK];
             const __nv_bfloat16* fp = ex.f_hi + static_cast<long long>(row) * ex.ldf + col0;
-            if (col0 + CHUNK <= n_cols && (ex.ldf & 7) == 0) {
+            if (col0 + CHUNK <= n_cols && ((ex.ldf | col0) & 7) == 0) {
               *reinterpret_cast<uint4*>(&fh[0]) = __ldg(reinterpret_cast<const uint4*>(fp));
               *reinterpret_cast<uint4*>(&fh[8]) = __ldg(reinterpret_cast<const uint4*>(fp + 8));
             } else {
@@ -373,7 +377,7 @@ encode_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           if (row < M) {
             const long long orow = ex.row_map != nullptr ? ex.row_map[row] : row;
             float* o = out + orow * ldo + col0;
-            if (col0 + CHUNK <= ex.n_main && (ldo & 3) == 0) {
+            if (col0 + CHUNK <= ex.n_main && ((ldo | col0) & 3) == 0) {
 #pragma unroll
               for (int i = 0; i < CHUNK; i += 4) {
                 if (accum) red_add_f32x4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -480,8 +484,9 @@ static int launch_variant(const EncodeGemmArgs& a, const CUtensorMap* maps, int 
       return 3;
     attr_set = true;
   }
-  const int kblocks_per_term = (a.K + BK - 1) / BK;
+  const int kblocks_per_term = (a.K - a.k_begin + BK - 1) / BK;
   EpiExtra ex;
+  ex.m_begin = a.m_begin; ex.n_begin = a.n_begin; ex.k_begin = a.k_begin;
   ex.f_hi = a.f_hi; ex.f_lo = a.f_lo; ex.t_hi = a.t_hi; ex.t_lo = a.t_lo; ex.ldf = a.ldf; ex.ldt = a.ldt;
   ex.f_lo2 = a.f_lo2; ex.t_lo2 = a.t_lo2;
   ex.row_l1 = a.row_l1; ex.row_l0 = a.row_l0; ex.active = a.active; ex.l1_over_b = a.l1_over_b;
@@ -511,7 +516,9 @@ int encode_gemm_nsplit(int M, int N, int num_sms) {
 }
 
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
-  if (a.M <= 0 || a.N <= 0) return 0;
+  if (a.M <= a.m_begin || a.N <= a.n_begin || a.K <= a.k_begin) return 0;
+  if (a.m_begin < 0 || a.n_begin < 0 || a.k_begin < 0) return 12;
+  if ((a.m_begin || a.n_begin || a.k_begin) && (a.m_limit_dev || a.n_limit_dev || a.k_limit_dev || a.epilogue == 5)) return 12;
   if (a.lda <= 0 && a.ldb <= 0 && (a.K % 8) != 0) return 10;  // TMA needs 16-byte aligned row pitch
   CUtensorMap maps[6];
   const long long lda = a.lda > 0 ? a.lda : a.K, ldb = a.ldb > 0 ? a.ldb : a.K;
@@ -533,11 +540,11 @@ int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
-  const int m_blocks = (a.M + BM - 1) / BM;
-  const int n_tiles = (a.N + BN - 1) / BN;
+  const int m_blocks = (a.M - a.m_begin + BM - 1) / BM;
+  const int n_tiles = (a.N - a.n_begin + BN - 1) / BN;
   if (a.epilogue >= 1) {
     // dense epilogues: any column split works; use enough CTAs to fill the GPU
-    int nsplit = a.nsplit > 0 ? a.nsplit : encode_gemm_nsplit(a.M, a.N, a.num_sms);
+    int nsplit = a.nsplit > 0 ? a.nsplit : encode_gemm_nsplit(a.M - a.m_begin, a.N - a.n_begin, a.num_sms);
     const int tps = (n_tiles + nsplit - 1) / nsplit;
     nsplit = (n_tiles + tps - 1) / tps;
     switch (a.epilogue) {

@@ -104,6 +104,8 @@ struct EncodeGemmArgs {
   const __nv_bfloat16* A_lo2 = nullptr; // third pieces, nterms == 6 only
   const __nv_bfloat16* B_lo2 = nullptr;
   int nterms = 1;                       // 1: A_hi.B_hi    3: + A_hi.B_lo + A_lo.B_hi    6: + A_hi.B_lo2 + A_lo2.B_hi + A_lo.B_lo
+  int m_begin = 0, n_begin = 0, k_begin = 0;  // dense epilogues: work on rows [m_begin, M), columns [n_begin, N),
+                                        // contraction [k_begin, K) of the operands (absolute indices everywhere)
   int M = 0, N = 0, K = 0;
   long long lda = 0, ldb = 0;           // row pitch of A / B in elements (0 = K); must be multiples of 8
   int k_chunk_blocks = 0;               // epilogues 1 / 4: accumulate K in chunks of this many 64-wide k-blocks per term
@@ -343,9 +345,14 @@ int launch_add_rows(const float* a, const float* b, long long n, float* out, cud
 // ---- dense_kernels.cu (ReLU / dense path) ----------------------------------------------------------------
 int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo,
                            long long ldr, int ones_row, int C_pad, cudaStream_t s, __nv_bfloat16* dst_lo2 = nullptr,
-                           const int* gate = nullptr);
+                           const int* gate = nullptr, long long src_ld = 0 /* row pitch of src, 0 = C */);
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
                        __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2 = nullptr);
+// Matryoshka prefixes on the dense path: y[P][B][D] block partial decodes -> resid (last prefix), sfx[B][P][D] suffix
+// sums of the per-prefix residuals, row_sse, and (training) g[P][B][D] = grad_scale * sfx_c as bf16 pieces
+int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, int P, float grad_scale, float* resid,
+                              float* sfx, float* row_sse, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo, __nv_bfloat16* g_lo2,
+                              cudaStream_t s);
 int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t s);
 int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s,
                      const __nv_bfloat16* lo2 = nullptr);

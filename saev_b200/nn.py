@@ -22,9 +22,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     are unchanged, checkpoints interoperate with saev.nn.load / saev.nn.dump).
   * `Output.h_x`, `Output.f_x`, `Output.x_hats` are materialised lazily (the fused path never writes the
     [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
-  * Matryoshka n_prefixes > 1 combined with Relu has no CUDA path in this build and raises NotImplementedError at
-    forward time (TopK / BatchTopK + Matryoshka prefixes is supported).  Relu runs the dense path (five
-    error-compensated bf16 split contractions on tcgen05).  BatchTopK (modeling.py:183-244) runs on the sparse path:
+  * Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05); with Matryoshka prefixes the
+    decoder, dh and W_dec-gradient contractions run once per prefix block on a window of the same operands.  BatchTopK (modeling.py:183-244) runs on the sparse path:
     per-row top-`capacity` lists (capacity = min(128, d_sae); 64 with Matryoshka prefixes), then a batch-wide
     selection kernel; a row that would
     need more than `capacity` slots is counted and `Loss.metrics()` raises (single rank only: the global selection
@@ -172,7 +171,7 @@ def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
         remove_parallel_grads=sae_cfg.remove_parallel_grads,
         normalize_w_dec=sae_cfg.normalize_w_dec,
         max_batch=max_batch,
-        max_prefixes=max(1, min(int(getattr(obj_cfg, "n_prefixes", 1)), sae_cfg.d_sae)) if kind != "Relu" else 1,
+        max_prefixes=max(1, min(int(getattr(obj_cfg, "n_prefixes", 1)), sae_cfg.d_sae)),
     )
 
 
@@ -582,7 +581,7 @@ class _StepFunction(torch.autograd.Function):
 
 
 class MatryoshkaObjective(torch.nn.Module):
-    """objectives.py:92-156 for n_prefixes == 1."""
+    """objectives.py:92-156."""
 
     def __init__(self, cfg):
         super().__init__()
@@ -591,9 +590,6 @@ class MatryoshkaObjective(torch.nn.Module):
 
     def forward(self, sae: SparseAutoencoder, x: Tensor):
         sae._require_topk()
-        if self.cfg.n_prefixes > 1 and _kind(sae.cfg.activation) == "Relu":
-            raise NotImplementedError("Matryoshka(n_prefixes > 1) has a CUDA path for the TopK / BatchTopK activations "
-                                      "only; use n_prefixes=1 with Relu")
         if _kind(sae.cfg.activation) == "BatchTopK" and sae.training != self.training:
             raise NotImplementedError("BatchTopK: the SAE and the objective must be in the same train/eval mode")
         x = x.contiguous()

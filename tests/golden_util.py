@@ -8,7 +8,7 @@ from oracle import sae_oracle as orc
 
 GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 CASES = ["tiny_topk_auxk", "tiny_topk_auxk_clamp", "tiny_topk_noaux_noproj", "tiny_relu_l1_auxk", "c1_topk",
-         "c1_topk_auxk_live", "tiny_topk_matryoshka", "c1_topk_matryoshka", "tiny_batchtopk_auxk",
+         "c1_topk_auxk_live", "tiny_topk_matryoshka", "c1_topk_matryoshka", "tiny_relu_matryoshka", "tiny_batchtopk_auxk",
          "c1_batchtopk", "c1_batchtopk_matryoshka"]
 
 

@@ -144,8 +144,3 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(NotImplementedError, match="cannot even hold the average"):  # more than 128 actives per row
         nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=512, activation=nn.BatchTopK(top_k=200),
                                                         reinit_blend=0.0)).to("cuda")(torch.randn(4, 64, device="cuda"))
-    sae = nn.SparseAutoencoder(nn.SparseAutoencoderConfig(d_model=64, d_sae=256, activation=nn.Relu(),
-                                                          reinit_blend=0.0)).to("cuda")
-    obj = nn.get_objective(nn.Matryoshka(n_prefixes=4))
-    with pytest.raises(NotImplementedError, match="n_prefixes"):
-        obj(sae, torch.randn(4, 64, device="cuda"))

@@ -193,6 +193,15 @@ def test_midsize_steps_match_oracle(act, D, S, K, B, aux_path, monkeypatch):
     _midsize_run(act, D, S, K, B, aux_path, monkeypatch)
 
 
+@pytest.mark.parametrize("act,D,S,K,B", [("relu", 192, 2048, 0, 520), ("topk", 256, 4096, 32, 640)])
+def test_midsize_matryoshka_steps_match_oracle(act, D, S, K, B, monkeypatch):
+    """Matryoshka prefixes with cuts that are not multiples of any tile size (objectives.py:124-138): the dense path
+    runs the decoder / dh / W_dec-gradient contractions per prefix block on windows [cut_{c-1}, cut_c) of the operands
+    (a 1-column block, a block inside one k-block, blocks straddling tiles); the sparse path emits every prefix from
+    one decode."""
+    _midsize_run(act, D, S, K, B, "auto", monkeypatch, prefixes=[1, 37, 100, 777, S - 3, S])
+
+
 def test_dense_features_take_the_block_per_atom_path(monkeypatch):
     """Three atoms with a large encoder bias fire on every row of a 1400-row batch: their lists (> 512 entries) are
     handled by wgrad_heavy_kernel (one block per atom) instead of one warp; same oracle, same tolerances."""
@@ -205,7 +214,7 @@ def test_dense_features_with_two_pass_decode(monkeypatch):
 
 
 def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=64, n_steps=4, rank=24,
-                 ref_norm_rel=1e-3, tie_tolerant=False):
+                 ref_norm_rel=1e-3, tie_tolerant=False, prefixes=None):
     """Four steps (AuxK live from step 2, L1 on for ReLU, ragged batch sizes, d_sae not a multiple of the tile).
 
     The library has two AuxK implementations (tensor-core split contractions / fp32 tiles) and picks one per step from
@@ -229,8 +238,9 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
                             dead_threshold_tokens=2 * B, lr=1e-3, n_lr_warmup=2, n_steps=10)
     st = orc.OracleState.from_params(W_enc, b_enc, W_dec, b_dec)
     eng = Engine(EngineConfig(d_model=D, d_sae=S, top_k=max(K, 1), activation=act, aux=True, k_aux=k_aux, l1_coeff=l1,
-                              dead_threshold_tokens=2 * B, max_batch=B))
+                              dead_threshold_tokens=2 * B, max_batch=B, max_prefixes=len(prefixes) if prefixes else 1))
     eng.load_params(W_enc, b_enc, W_dec, b_dec)
+    eng.set_prefixes(prefixes)
     basis = torch.randn(max(rank, 1), D, generator=g)
     tol = TOL_DENSE if act == "relu" else TOL
     # ReLU case: the inputs carry a large common offset (x - 0.5), i.e. every contraction cancels heavily (the fp32
@@ -255,8 +265,10 @@ def _midsize_run(act, D, S, K, B, aux_path, monkeypatch, dense_atoms=(), k_aux=6
             # fp32-level ties (oracle.adopt_selection)
             forced = eng.topk_idx[:B].cpu().long()
             forced_aux = lambda n_dead: eng.aux_selection(B).cpu()  # noqa: E731
-        ref = orc.train_step(ocfg, st, x, topk_idx=forced, aux_idx=forced_aux)
+        ref = orc.train_step(ocfg, st, x, topk_idx=forced, aux_idx=forced_aux, prefixes=prefixes)
         ld = eng.loss_dict()
+        if prefixes:
+            assert rel_l2(eng.x_hats(xd).cpu(), ref["out"].x_hats) < 10 * tol, step
         for key in ("mse", "aux", "sparsity", "l1", "loss"):
             assert ld[key] == pytest.approx(ref[key], rel=tol, abs=1e-7), (step, key)
         assert abs(ld["l0"] - ref["l0"]) <= (1e-3 if act == "relu" else 0) * max(ref["l0"], 1) + 1e-6, step

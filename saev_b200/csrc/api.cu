@@ -369,14 +369,19 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
         return fail(h, 44, "forward(relu): G^T launch failed%s");
     } else {
       // Matryoshka (modeling.py:364-406): one decoder contraction per prefix block, over the dictionary columns
-      // [cut_{c-1}, cut_c) only (a window on the same K-major operands: the tensor maps end at cut_c, the TMA
-      // coordinates start at cut_{c-1}), each into its own partial reconstruction y_c; b_dec rides on block 0
+      // [cut_{c-1}, cut_c) only -- a window on the same K-major operands: the tensor maps end at cut_c and the TMA
+      // coordinates start at the block's first 8-aligned column (16-byte aligned spans along the contraction); the <= 7
+      // columns in front of it and b_dec are added in fp32 by the residual kernel
       float* y = at<float>(workspace, w.yblk);
+      unsigned int tensor_mask = 0u;
       for (int cb = 0; cb < P; ++cb) {
+        const int k0 = cb > 0 ? h->pf.cut[cb - 1] : 0, k1 = h->pf.cut[cb];
+        const int ka = (k0 + 7) & ~7;
+        if (ka >= k1) continue;
+        tensor_mask |= 1u << cb;
         EncodeGemmArgs g = dense_gemm(h, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, bf(w.w_decT_hi), bf(w.w_decT_lo),
-                                      b3(w.w_decT_l2), S, B, D, h->pf.cut[cb], 1);
-        g.k_begin = cb > 0 ? h->pf.cut[cb - 1] : 0;
-        g.bias = cb == 0 ? b_dec : nullptr;
+                                      b3(w.w_decT_l2), S, B, D, k1, 1);
+        g.k_begin = ka;
         g.out = y + cb * BD;
         g.ldo = D;
         if (int rc = launch_encode_gemm(g, s)) {
@@ -386,9 +391,9 @@ int forward_relu_phase_a(saev_b200_handle* h, const float* x, int B, long long t
         }
       }
       float* sfx = at<float>(workspace, w.sfx);
-      if (launch_dense_prefix_resid(y, x, B, D, P, gs, resid, sfx, at<float>(workspace, w.row_sse),
-                                    training ? bf(w.g_hi) : nullptr, training ? bf(w.g_lo) : nullptr,
-                                    training ? b3(w.g_l2) : nullptr, s))
+      if (launch_dense_prefix_resid(y, x, B, D, h->pf, tensor_mask, bf(w.f_hi), bf(w.f_lo), b3(w.f_l2), S, W_dec, b_dec, gs,
+                                    resid, sfx, at<float>(workspace, w.row_sse), training ? bf(w.g_hi) : nullptr,
+                                    training ? bf(w.g_lo) : nullptr, training ? b3(w.g_l2) : nullptr, s))
         return fail(h, 44, "forward(relu): prefix residual launch failed%s");
       if (training)
         for (int cb = 0; cb < P; ++cb)  // G_c^T [D, ldb], the operand of the per-block W_dec gradient

@@ -105,30 +105,48 @@ int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_sca
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
-// Matryoshka prefixes on the dense path (saev modeling.py:364-406, objectives.py:124-138).  y[c][b][:] is the partial
-// decode of prefix block c (block 0 includes b_dec), so x_hat_i = sum_{c <= i} y_c and r_i = x_hat_i - x.  One warp per
-// row writes resid = r_{P-1} (AuxK / logging use the full prefix), row_sse[b] = sum_i ||r_i||^2, the suffix sums
-// sfx[b][c][:] = sum_{i >= c} r_i (what the columns of block c see in the backward pass; same layout as the sparse
-// path's, so gb_dec and x_hats come from the same kernels) and, when training, G_c = grad_scale * sfx_c as bf16 pieces
-// g[c][b][:] (operand of the per-block dh contraction).
+// Matryoshka prefixes on the dense path (saev modeling.py:364-406, objectives.py:124-138).  The decoder contraction of
+// prefix block c = dictionary columns [cut_{c-1}, cut_c) runs on the tensor cores from the first column that is a
+// multiple of 8 (TMA reads 16-byte aligned spans along the contraction dimension) into y[c][b][:]; the <= 7 columns in
+// front of it are added here in fp32 from the bf16 pieces of f and the fp32 dictionary rows, as is b_dec.  So
+// x_hat_i = b_dec + sum_{c <= i} (head_c + y_c) and r_i = x_hat_i - x.  One warp per row writes resid = r_{P-1} (AuxK /
+// logging use the full prefix), row_sse[b] = sum_i ||r_i||^2, the suffix sums sfx[b][c][:] = sum_{i >= c} r_i (what the
+// columns of block c see in the backward pass; same layout as the sparse path's, so gb_dec and x_hats come from the
+// same kernels) and, when training, G_c = grad_scale * sfx_c as bf16 pieces g[c][b][:] (operand of the per-block dh
+// contraction).  `tensor_mask` bit c: y_c was written (the block reaches past its aligned start).
 __global__ void __launch_bounds__(256) dense_prefix_resid_kernel(const float* __restrict__ y, const float* __restrict__ x, int B,
-                                                                 int D, int P, float grad_scale, float* __restrict__ resid,
-                                                                 float* __restrict__ sfx, float* __restrict__ row_sse,
+                                                                 int D, PrefixCuts pf, unsigned int tensor_mask,
+                                                                 const __nv_bfloat16* __restrict__ f_hi,
+                                                                 const __nv_bfloat16* __restrict__ f_lo,
+                                                                 const __nv_bfloat16* __restrict__ f_lo2, long long ldf,
+                                                                 const float* __restrict__ W_dec,
+                                                                 const float* __restrict__ b_dec, float grad_scale,
+                                                                 float* __restrict__ resid, float* __restrict__ sfx,
+                                                                 float* __restrict__ row_sse,
                                                                  __nv_bfloat16* __restrict__ g_hi,
                                                                  __nv_bfloat16* __restrict__ g_lo,
                                                                  __nv_bfloat16* __restrict__ g_lo2) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
+  const int P = pf.n;
   const long long BD = static_cast<long long>(B) * D, o = static_cast<long long>(b) * D;
   float sse = 0.f;
   for (int d = lane; d < D; d += 32) {
     const float xv = __ldg(x + o + d);
     float r[MAX_PREFIXES];
-    float run = 0.f;
+    float run = __ldg(b_dec + d);
 #pragma unroll 1
     for (int c = 0; c < P; ++c) {
-      run += __ldg(y + c * BD + o + d);
+      const int k0 = c ? pf.cut[c - 1] : 0, k1 = pf.cut[c];
+      const int ka = min(k1, (k0 + 7) & ~7);
+      for (int k = k0; k < ka; ++k) {
+        const long long fi = static_cast<long long>(b) * ldf + k;
+        float fv = __bfloat162float(f_hi[fi]) + __bfloat162float(f_lo[fi]);
+        if (f_lo2 != nullptr) fv += __bfloat162float(f_lo2[fi]);
+        if (fv != 0.f) run = fmaf(fv, __ldg(W_dec + static_cast<long long>(k) * D + d), run);
+      }
+      if ((tensor_mask >> c) & 1u) run += __ldg(y + c * BD + o + d);
       r[c] = run - xv;
       sse = fmaf(r[c], r[c], sse);
     }
@@ -151,11 +169,14 @@ __global__ void __launch_bounds__(256) dense_prefix_resid_kernel(const float* __
   if (lane == 0) row_sse[b] = sse;
 }
 
-int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, int P, float grad_scale, float* resid,
+int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, const PrefixCuts& pf, unsigned int tensor_mask,
+                              const __nv_bfloat16* f_hi, const __nv_bfloat16* f_lo, const __nv_bfloat16* f_lo2,
+                              long long ldf, const float* W_dec, const float* b_dec, float grad_scale, float* resid,
                               float* sfx, float* row_sse, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo, __nv_bfloat16* g_lo2,
                               cudaStream_t s) {
-  if (P < 1 || P > MAX_PREFIXES) return 24;
-  dense_prefix_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(y, x, B, D, P, grad_scale, resid, sfx, row_sse, g_hi, g_lo, g_lo2);
+  if (pf.n < 1 || pf.n > MAX_PREFIXES) return 24;
+  dense_prefix_resid_kernel<<<(B + 7) / 8, 256, 0, s>>>(y, x, B, D, pf, tensor_mask, f_hi, f_lo, f_lo2, ldf, W_dec, b_dec,
+                                                        grad_scale, resid, sfx, row_sse, g_hi, g_lo, g_lo2);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }

@@ -256,6 +256,14 @@ struct PrefixCuts {
   int n;
   int cut[MAX_PREFIXES];
 };
+// Matryoshka prefixes on the dense path: y[P][B][D] tensor-core partial decodes of the prefix blocks (from each block's
+// first 8-aligned column; bit c of tensor_mask: written) + the unaligned head columns and b_dec in fp32 -> resid (last
+// prefix), sfx[B][P][D] suffix sums of the per-prefix residuals, row_sse, (training) g[P][B][D] = grad_scale * sfx_c
+int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, const PrefixCuts& pf, unsigned int tensor_mask,
+                              const __nv_bfloat16* f_hi, const __nv_bfloat16* f_lo, const __nv_bfloat16* f_lo2,
+                              long long ldf, const float* W_dec, const float* b_dec, float grad_scale, float* resid,
+                              float* sfx, float* row_sse, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo, __nv_bfloat16* g_lo2,
+                              cudaStream_t s);
 // Decode with prefixes: x_hat_i = b_dec + sum over the active columns below cut[i]; r_i = x_hat_i - x.
 // Writes resid = r_{n-1}, sfx[b, c, :] = sum_{i >= c} r_i (what column block c sees in the backward pass),
 // row_sse[b] = sum_i ||r_i||^2, and dh (scaled by a.grad_scale = 2 / (B_global * n * D)).
@@ -348,11 +356,7 @@ int launch_transpose_split(const float* src, int R, int C, float scale, __nv_bfl
                            const int* gate = nullptr, long long src_ld = 0 /* row pitch of src, 0 = C */);
 int launch_dense_resid(float* xhat, const float* x, int B, int D, float grad_scale, float* row_sse, __nv_bfloat16* g_hi,
                        __nv_bfloat16* g_lo, cudaStream_t s, __nv_bfloat16* g_lo2 = nullptr);
-// Matryoshka prefixes on the dense path: y[P][B][D] block partial decodes -> resid (last prefix), sfx[B][P][D] suffix
-// sums of the per-prefix residuals, row_sse, and (training) g[P][B][D] = grad_scale * sfx_c as bf16 pieces
-int launch_dense_prefix_resid(const float* y, const float* x, int B, int D, int P, float grad_scale, float* resid,
-                              float* sfx, float* row_sse, __nv_bfloat16* g_hi, __nv_bfloat16* g_lo, __nv_bfloat16* g_lo2,
-                              cudaStream_t s);
+
 int launch_project_rows(float* g, const float* w, int rows, int D, cudaStream_t s);
 int launch_join_bf16(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out, cudaStream_t s,
                      const __nv_bfloat16* lo2 = nullptr);

@@ -28,7 +28,10 @@ needs_ref = pytest.mark.skipif(REF is None, reason="reference package not staged
 
 
 @needs_ref
-def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
+@pytest.mark.parametrize("variant", ["topk", "batchtopk-matryoshka", "relu-matryoshka"])
+def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels(variant):
+    """`variant`: TopK with a single prefix (the headline path); BatchTopK and Relu under the reference's DEFAULT
+    objective, Matryoshka(n_prefixes=10) (objectives.py:22)."""
     stubs = str(pathlib.Path(__file__).resolve().parent.parent / "oracle" / "ref_stubs")
     sys.path[:0] = [stubs, str(REF)]
     try:
@@ -37,11 +40,14 @@ def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
         import saev.data.shards as shards
         import saev.framework.train as train
         import saev.nn
-        from saev.nn.modeling import TopK
+        from saev.nn.modeling import BatchTopK, Relu, TopK
 
         import saev_b200
         from saev_b200 import _lib
 
+        activation = {"topk": TopK(top_k=8), "batchtopk-matryoshka": BatchTopK(top_k=8, momentum=0.3),
+                      "relu-matryoshka": Relu()}[variant]
+        objective = saev.nn.objectives.Matryoshka(n_prefixes=1 if variant == "topk" else 10)
         with tempfile.TemporaryDirectory() as tmp:
             tmp = pathlib.Path(tmp)
             root = tmp / "saev" / "shards"
@@ -63,10 +69,10 @@ def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
             (tmp / "saev" / "runs").mkdir(parents=True)
             cfg = train.Config(
                 n_train=4 * n_examples * T, n_val=n_examples * T, device="cuda", track=False, log_every=4, lr=2e-3,
-                n_lr_warmup=4, runs_root=tmp / "saev" / "runs", objective=saev.nn.objectives.Matryoshka(n_prefixes=1),
+                n_lr_warmup=4, runs_root=tmp / "saev" / "runs", objective=objective,
                 train_data=saev.data.ShuffledConfig(shards=d, layer=0, batch_size=512),
                 val_data=saev.data.ShuffledConfig(shards=d, layer=0, batch_size=512),
-                sae=saev.nn.SparseAutoencoderConfig(d_model=D, d_sae=8 * D, activation=TopK(top_k=8), reinit_blend=0.0),
+                sae=saev.nn.SparseAutoencoderConfig(d_model=D, d_sae=8 * D, activation=activation, reinit_blend=0.0),
             )
             evals = []
             saev_b200.install()
@@ -90,11 +96,15 @@ def test_unmodified_worker_fn_trains_and_evaluates_through_the_kernels():
             assert type(sae).__module__.startswith("saev.") and sae.W_dec.shape == (8 * D, D)
             (m,) = evals
             assert isinstance(m, train.EvalMetrics)
-            assert 0.0 < m.normalized_mse < 0.9, m.normalized_mse  # it learned something on the planted data
-            assert m.l0 == pytest.approx(8.0)
+            assert 0.0 < m.normalized_mse < (0.9 if variant == "topk" else 1.0), m.normalized_mse  # it learned something
+            if variant == "topk":
+                assert m.l0 == pytest.approx(8.0)
             # the reference's own forward on the trained weights agrees with what our evaluate() measured
+            # (eval mode: BatchTopK is then the JumpReLU with the threshold buffer our kernels trained, modeling.py:220-224)
             x = acts[:, 0].reshape(-1, D)
-            ref_out = sae(x)
+            sae.eval()
+            with torch.no_grad():
+                ref_out = sae(x)
             nmse = float(((ref_out.x_hats[:, -1, :] - x) ** 2).sum() / ((x - x.mean(0)) ** 2).sum())
             assert nmse == pytest.approx(m.normalized_mse, rel=1e-3)
     finally:

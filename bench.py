@@ -666,8 +666,13 @@ def main():
                 "precision": ("fp16 tcgen05 screen of the encoder contraction (deterministic error bound) + exact fp32 "
                               "re-score of the candidates; every value that reaches the loss / gradients / parameters "
                               "is fp32") if K else
-                             ("dense path: all five contractions as 3-term bf16 split products on tcgen05 (~2^-17 "
-                              "relative), fp32 accumulation; everything else fp32"),
+                             ("dense path: all five contractions as " +
+                              ("3-term (two-piece, ~2^-17 relative)" if os.environ.get("SAEV_B200_DENSE_TERMS", "6")[:1] == "3"
+                               else "6-term (three-piece, fp32-class)") +
+                              " bf16 split products on tcgen05" +
+                              (" (single-CTA kernel)" if os.environ.get("SAEV_B200_DENSE_PAIR", "1")[:1] == "0"
+                               else " (CTA-pair kernel, pieces staged once per k-block)") +
+                              ", fp32 accumulation; everything else fp32"),
                 "l2_policy": f"per-step working set (params+grads+Adam moments {eng.n_params * 16 / 1e9:.2f} GB, "
                              f"{NB} rotating input batches of {B * D * 4 / 1e6:.0f} MB) is far larger than the 126 MB L2; "
                              "no explicit flush",

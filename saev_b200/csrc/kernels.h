@@ -149,6 +149,10 @@ struct EncodeGemmArgs {
   long long ldo = 0;
 };
 int launch_encode_gemm(const EncodeGemmArgs& a, cudaStream_t stream);
+// CTA-pair version of the dense split-product contraction (dense_gemm2.cu): epilogues 1-4, 3 or 6 terms, static sizes;
+// launch_encode_gemm forwards to it when dense_gemm2_eligible(a) (SAEV_B200_DENSE_PAIR=0 keeps the single-CTA kernel).
+bool dense_gemm2_eligible(const EncodeGemmArgs& a);
+int launch_dense_gemm2(const EncodeGemmArgs& a, cudaStream_t stream);
 
 // ---- encode_gemm2.cu: CTA-pair (cta_group::2) top-k screen ------------------------------------------------
 struct Encode2Plan {

@@ -298,6 +298,8 @@ struct WgradArgs {
   int row_begin, row_end;              // atoms handled by this launch
   const long long* skip_toks;          // optional: leave atoms with no entries and toks >= threshold untouched
   long long skip_threshold;
+  int split = 0;                       // two-pass form: decoder side (+ dh into dh_scratch) over all atoms, then encoder side
+  float* dh_scratch = nullptr;         // [B, K]
 };
 int launch_wgrad(const WgradArgs& a, cudaStream_t s);
 

@@ -1482,10 +1482,201 @@ static int launch_wgrad_light(const WgradArgs& a, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-pass form of the weight gradients (the default; SAEV_B200_WGRAD_SPLIT=0 selects the one-pass kernel above, which
+// gathers a residual row
+// AND an x row per active entry: a 134 MB gather set at c3 that the L2 serves only half of (ncu: 2.15 GB of the 4.3 GB
+// of gathers come from DRAM).  Here the decoder side runs first over ALL atoms -- gW_dec, gb_enc, and dh_bk =
+// grad_scale <r_b, w_j> written to the [B, K] scratch, gathering residual rows only (67 MB) -- then the encoder side
+// gathers x rows only.  Each pass works on a gather set that fits the L2.  Heavy atoms (lists > WGRAD_HEAVY_ENTRIES) stay
+// with wgrad_heavy_kernel, which both passes prepare exactly as wgrad_kernel does.
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(32, 16) wgrad_dec_kernel(WgradArgs a, float* __restrict__ dh_out) {
+  __shared__ float4 w[VPL * 32];  // this atom's dictionary row (lane-strided: no bank conflicts)
+  const int lane = threadIdx.x;
+  const int j = a.row_begin + blockIdx.x;
+  if (j >= a.row_end) return;
+  const int D4 = a.D >> 2;
+  const int beg = a.feat_off[j], end = a.feat_off[j + 1];
+  if (a.skip_toks != nullptr && beg == end && a.skip_toks[j] >= a.skip_threshold) return;
+  float* gdrow = a.gW_dec + static_cast<long long>(j) * a.D;
+  if ((a.heavy_list != nullptr && end - beg > WGRAD_HEAVY_ENTRIES) || beg == end) {
+    // heavy: wgrad_heavy_kernel adds its slices into zeroed rows; empty: the dense .grad rows saev's loop expects
+    for (int v = lane; v < D4; v += 32) __stcs(reinterpret_cast<float4*>(gdrow + 4 * v), make_float4(0, 0, 0, 0));
+    if (lane == 0) {
+      a.gb_enc[j] = 0.f;
+      if (beg != end) a.heavy_ticket[j] = 0;
+      else if (a.row_gsq) a.row_gsq[j] = 0.f;
+    }
+    return;
+  }
+  float4 gd[VPL];
+  const float* wrow = a.W_dec + static_cast<long long>(j) * a.D;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    gd[i] = make_float4(0, 0, 0, 0);
+    w[v] = (v < D4) ? __ldcs(reinterpret_cast<const float4*>(wrow + 4 * v)) : make_float4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  const float* rbase = a.resid;
+  long long rstride = a.D;
+  if (a.sfx != nullptr) {
+    int c = 0;
+    while (c < a.pf.n - 1 && j >= a.pf.cut[c]) ++c;
+    rbase = a.sfx + static_cast<long long>(c) * a.D;
+    rstride = static_cast<long long>(a.pf.n) * a.D;
+  }
+  float sdh = 0.f;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    int mp = 0;
+    float mf = 0.f, mine = 0.f;
+    if (e < end) {
+      mp = a.entries[e];
+      mf = a.topk_val[mp];
+    }
+    const int cnt = min(32, end - e0);
+    for (int t = 0; t < cnt; t += 2) {  // two residual rows in flight
+      const int p0 = __shfl_sync(FULL, mp, t), p1 = __shfl_sync(FULL, mp, min(t + 1, cnt - 1));
+      const float f0 = __shfl_sync(FULL, mf, t), f1 = (t + 1 < cnt) ? __shfl_sync(FULL, mf, t + 1) : 0.f;
+      const float* r0 = rbase + static_cast<long long>(p0 / a.K) * rstride;
+      const float* r1 = rbase + static_cast<long long>(p1 / a.K) * rstride;
+      float4 v0[VPL], v1[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        v0[i] = (v < D4) ? ldg4(r0 + 4 * v) : make_float4(0, 0, 0, 0);
+        v1[i] = (v < D4) ? ldg4(r1 + 4 * v) : make_float4(0, 0, 0, 0);
+      }
+      float pd0 = 0.f, pd1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        fma4(gd[i], f0, v0[i]);
+        fma4(gd[i], f1, v1[i]);  // (f1 == 0 for the padding round)
+        const float4 wv = w[lane + 32 * i];
+        pd0 += dot4(v0[i], wv);
+        pd1 += dot4(v1[i], wv);
+      }
+      pd0 = warp_sum(pd0);
+      pd1 = warp_sum(pd1);
+      float d0 = a.grad_scale * pd0, d1 = a.grad_scale * pd1;
+      if (a.l1_over_b != 0.f) {
+        d0 += a.l1_over_b * ((f0 > 0.f) ? 1.f : ((f0 < 0.f) ? -1.f : 0.f));
+        d1 += a.l1_over_b * ((f1 > 0.f) ? 1.f : ((f1 < 0.f) ? -1.f : 0.f));
+      }
+      if (lane == t) mine = d0;
+      if (lane == t + 1 && t + 1 < cnt) mine = d1;
+    }
+    if (e < end) {
+      dh_out[mp] = mine;
+      sdh += mine;
+    }
+  }
+  sdh = warp_sum(sdh);
+  float dot = 0.f, nsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    gd[i].x *= a.grad_scale; gd[i].y *= a.grad_scale; gd[i].z *= a.grad_scale; gd[i].w *= a.grad_scale;
+    dot += dot4(gd[i], w[lane + 32 * i]);
+    nsq += dot4(w[lane + 32 * i], w[lane + 32 * i]);
+  }
+  if (a.remove_parallel) {
+    dot = warp_sum(dot);
+    nsq = warp_sum(nsq);
+    const float sc = (nsq > 0.f) ? dot / nsq : 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) fma4(gd[i], -sc, w[lane + 32 * i]);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) __stcs(reinterpret_cast<float4*>(gdrow + 4 * v), gd[i]);
+    ss += dot4(gd[i], gd[i]);
+  }
+  if (a.row_gsq != nullptr) {
+    ss = warp_sum(ss);
+    if (lane == 0) a.row_gsq[j] = ss + sdh * sdh;
+  }
+  if (lane == 0) a.gb_enc[j] = sdh;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(32, 20) wgrad_enc_kernel(WgradArgs a, const float* __restrict__ dh_in) {
+  const int lane = threadIdx.x;
+  const int j = a.row_begin + blockIdx.x;
+  if (j >= a.row_end) return;
+  const int D4 = a.D >> 2;
+  const int beg = a.feat_off[j], end = a.feat_off[j + 1];
+  if (a.skip_toks != nullptr && beg == end && a.skip_toks[j] >= a.skip_threshold) return;
+  float* gerow = a.gW_enc_t + static_cast<long long>(j) * a.D;
+  if ((a.heavy_list != nullptr && end - beg > WGRAD_HEAVY_ENTRIES) || beg == end) {
+    for (int v = lane; v < D4; v += 32) __stcs(reinterpret_cast<float4*>(gerow + 4 * v), make_float4(0, 0, 0, 0));
+    return;
+  }
+  float4 ge[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) ge[i] = make_float4(0, 0, 0, 0);
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    int mb = 0;
+    float md = 0.f;
+    if (e < end) {
+      const int p = a.entries[e];
+      mb = p / a.K;
+      md = dh_in[p];
+    }
+    const int cnt = min(32, end - e0);
+    for (int t = 0; t < cnt; t += 2) {  // two x rows in flight
+      const int b0 = __shfl_sync(FULL, mb, t), b1 = __shfl_sync(FULL, mb, min(t + 1, cnt - 1));
+      const float d0 = __shfl_sync(FULL, md, t), d1 = (t + 1 < cnt) ? __shfl_sync(FULL, md, t + 1) : 0.f;
+      const float* x0 = a.x + static_cast<long long>(b0) * a.D;
+      const float* x1 = a.x + static_cast<long long>(b1) * a.D;
+      float4 v0[VPL], v1[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        v0[i] = (v < D4) ? ldg4(x0 + 4 * v) : make_float4(0, 0, 0, 0);
+        v1[i] = (v < D4) ? ldg4(x1 + 4 * v) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        fma4(ge[i], d0, v0[i]);
+        fma4(ge[i], d1, v1[i]);
+      }
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < D4) __stcs(reinterpret_cast<float4*>(gerow + 4 * v), ge[i]);
+    ss += dot4(ge[i], ge[i]);
+  }
+  if (a.row_gsq != nullptr) {
+    ss = warp_sum(ss);
+    if (lane == 0) a.row_gsq[j] += ss;  // (wgrad_dec_kernel wrote this atom's decoder share)
+  }
+}
+
+static int launch_wgrad_split(const WgradArgs& a, cudaStream_t s) {
+  if (a.D % 4 || a.dh_scratch == nullptr) return 21;
+  const int rows = a.row_end - a.row_begin;
+  if (rows <= 0) return 0;
+  SB_DISPATCH_VPL(a.D, (wgrad_dec_kernel<VPL><<<rows, 32, 0, s>>>(a, a.dh_scratch)));
+  SB_DISPATCH_VPL(a.D, (wgrad_enc_kernel<VPL><<<rows, 32, 0, s>>>(a, a.dh_scratch)));
+  return cudaGetLastError() == cudaSuccess ? 0 : 22;
+}
+
 // ------------------------------------------------------------------------------------------------
 
 int launch_wgrad(const WgradArgs& a, cudaStream_t s) {
-  if (int rc = launch_wgrad_light(a, s)) return rc;
+  // the two-pass form applies where dh is computed in the weight-gradient kernel (a.dh == nullptr)
+  if (int rc = (a.split && a.dh == nullptr && a.dh_scratch != nullptr) ? launch_wgrad_split(a, s) : launch_wgrad_light(a, s))
+    return rc;
   if (a.heavy_list == nullptr || a.row_end <= a.row_begin) return 0;
   const int grid = 148 * 2;  // every block walks the (device-side) heavy list and takes its slices; exits at once if empty
   if (a.dh == nullptr) { SB_DISPATCH_VPL(a.D, (wgrad_heavy_kernel<VPL, true><<<grid, 256, 0, s>>>(a))); }

@@ -510,9 +510,9 @@ int saev_b200_create(const saev_b200_cfg* cfg, saev_b200_handle** out) {
     delete h;
     return fail(nullptr, 2, "saev_b200_create: max_prefixes must be <= 32%s");
   }
-  if (h->cfg.max_prefixes > 1 && cfg->act_kind == SAEV_B200_ACT_TOPK && cfg->top_k > 64) {
+  if (h->cfg.max_prefixes > 1 && cfg->act_kind == SAEV_B200_ACT_TOPK && cfg->top_k > 128) {
     delete h;
-    return fail(nullptr, 3, "saev_b200_create: Matryoshka prefixes on the TopK path need top_k <= 64%s");
+    return fail(nullptr, 3, "saev_b200_create: Matryoshka prefixes on the TopK path need top_k <= 128%s");
   }
   h->max_prefixes = h->cfg.max_prefixes;
   h->pf.n = 1;

@@ -771,22 +771,23 @@ int launch_decode(const DecodeArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Matryoshka decode (saev modeling.py:364-406, objectives.py:124-138): the active columns of a row are walked in
 // ascending column order; whenever the walk crosses a prefix cut the running reconstruction is that prefix's x_hat.
-// One warp per row; K <= 64 (two top-k slots per lane).
+// One warp per row; K <= 128 (two or four top-k slots per lane).
 // ------------------------------------------------------------------------------------------------
-template <int VPL>
+// NS = top-k slots per lane: 2 (K <= 64) or 4 (K <= 128, the row capacity of the BatchTopK path)
+template <int VPL, int NS>
 __global__ void __launch_bounds__(256, 2) decode_prefix_kernel(DecodeArgs a, PrefixCuts pf, float* __restrict__ sfx) {
-  __shared__ int order_s[8][64];
+  __shared__ int order_s[8][32 * NS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
   if (b >= a.B) return;
   const int D4 = a.D >> 2, K = a.K, P = pf.n;
   const long long kb = static_cast<long long>(b) * K;
-  // this lane's (up to) two slots
-  int mj[2];
-  float mf[2];
+  // this lane's (up to) NS slots
+  int mj[NS];
+  float mf[NS];
   float l1 = 0.f, l0 = 0.f;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < NS; ++u) {
     const int kk = lane + 32 * u;
     mj[u] = (kk < K) ? a.topk_idx[kb + kk] : -1;
     mf[u] = (kk < K) ? a.topk_val[kb + kk] : 0.f;
@@ -798,18 +799,27 @@ __global__ void __launch_bounds__(256, 2) decode_prefix_kernel(DecodeArgs a, Pre
   // rank of every slot by column (empty slots last, ties among them by slot)
   int* order = order_s[warp];
   {
-    int rank[2] = {0, 0};
-    const unsigned int key0 = mj[0] < 0 ? 0x7fffffffu : static_cast<unsigned int>(mj[0]);
-    const unsigned int key1 = mj[1] < 0 ? 0x7fffffffu : static_cast<unsigned int>(mj[1]);
-    for (int t = 0; t < K; ++t) {
-      const int src = t & 31;
-      const unsigned int k0 = __shfl_sync(FULL, key0, src), k1 = __shfl_sync(FULL, key1, src);
-      const unsigned int kt = (t < 32) ? k0 : k1;
-      rank[0] += (kt < key0) || (kt == key0 && t < lane);
-      rank[1] += (kt < key1) || (kt == key1 && t < lane + 32);
+    int rank[NS];
+    unsigned int key[NS];
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      rank[u] = 0;
+      key[u] = mj[u] < 0 ? 0x7fffffffu : static_cast<unsigned int>(mj[u]);
     }
-    if (lane < K) order[rank[0]] = lane;
-    if (lane + 32 < K) order[rank[1]] = lane + 32;
+    for (int t = 0; t < K; ++t) {
+      const int src = t & 31, su = t >> 5;
+      unsigned int kt = 0u;
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const unsigned int ku = __shfl_sync(FULL, key[u], src);
+        if (u == su) kt = ku;
+      }
+#pragma unroll
+      for (int u = 0; u < NS; ++u) rank[u] += (kt < key[u]) || (kt == key[u] && t < lane + 32 * u);
+    }
+#pragma unroll
+    for (int u = 0; u < NS; ++u)
+      if (lane + 32 * u < K) order[rank[u]] = lane + 32 * u;
   }
   __syncwarp();
 
@@ -842,10 +852,19 @@ __global__ void __launch_bounds__(256, 2) decode_prefix_kernel(DecodeArgs a, Pre
   // slot -> (column, value) of the t-th active in ascending column order (empty slots sort last)
   auto entry = [&](int t, int& j, float& f) {
     const int k = order[min(t, K - 1)];
-    const int j0 = __shfl_sync(FULL, mj[0], k & 31), j1 = __shfl_sync(FULL, mj[1], k & 31);
-    const float f0 = __shfl_sync(FULL, mf[0], k & 31), f1 = __shfl_sync(FULL, mf[1], k & 31);
-    j = (t < K) ? ((k < 32) ? j0 : j1) : -1;
-    f = (k < 32) ? f0 : f1;
+    int jj = -1;
+    float ff = 0.f;
+#pragma unroll
+    for (int u = 0; u < NS; ++u) {
+      const int ju = __shfl_sync(FULL, mj[u], k & 31);
+      const float fu = __shfl_sync(FULL, mf[u], k & 31);
+      if ((k >> 5) == u) {
+        jj = ju;
+        ff = fu;
+      }
+    }
+    j = (t < K) ? jj : -1;
+    f = ff;
   };
   // two dictionary rows per round, all 2 x VPL loads issued before the first FMA (gather latency, see decode_kernel)
   for (int t = 0; t < K; t += 2) {
@@ -967,8 +986,9 @@ __global__ void __launch_bounds__(256, 2) decode_prefix_kernel(DecodeArgs a, Pre
 
 int launch_decode_prefix(const DecodeArgs& a, const PrefixCuts& pf, float* sfx, cudaStream_t s) {
   if (a.D % 4) return 21;
-  if (a.K > 64 || pf.n < 1 || pf.n > MAX_PREFIXES) return 24;
-  SB_DISPATCH_VPL(a.D, (decode_prefix_kernel<VPL><<<(a.B + 7) / 8, 256, 0, s>>>(a, pf, sfx)));
+  if (a.K > 128 || pf.n < 1 || pf.n > MAX_PREFIXES) return 24;
+  if (a.K <= 64) { SB_DISPATCH_VPL(a.D, (decode_prefix_kernel<VPL, 2><<<(a.B + 7) / 8, 256, 0, s>>>(a, pf, sfx))); }
+  else { SB_DISPATCH_VPL(a.D, (decode_prefix_kernel<VPL, 4><<<(a.B + 7) / 8, 256, 0, s>>>(a, pf, sfx))); }
   return cudaGetLastError() == cudaSuccess ? 0 : 22;
 }
 

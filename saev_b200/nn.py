@@ -24,8 +24,7 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     [B, d_sae] matrices); saev's logging block (train.py:365-442) reads them on log steps only.
   * Relu runs the dense path (five error-compensated bf16 split contractions on tcgen05); with Matryoshka prefixes the
     decoder, dh and W_dec-gradient contractions run once per prefix block on a window of the same operands.  BatchTopK (modeling.py:183-244) runs on the sparse path:
-    per-row top-`capacity` lists (capacity = min(128, d_sae); 64 with Matryoshka prefixes), then a batch-wide
-    selection kernel; a row that would
+    per-row top-`capacity` lists (capacity = min(128, d_sae)), then a batch-wide selection kernel; a row that would
     need more than `capacity` slots is counted and `Loss.metrics()` raises (single rank only: the global selection
     does not shard).
 """
@@ -176,13 +175,12 @@ def engine_config(sae_cfg, obj_cfg, max_batch: int) -> EngineConfig:
 
 
 def batch_topk_capacity(top_k: int, d_sae: int, n_prefixes: int = 1) -> int:
-    """Slots per row of the sparse forward state under BatchTopK: the most the kernels hold -- 128 (screen / re-score /
-    repair), 64 when Matryoshka prefixes are decoded (decode_prefix_kernel ranks two slots per lane) -- or d_sae when
-    the dictionary is narrower.  SAEV_B200_BATCHTOPK_CAP lowers it (cheaper re-score when rows are known to be
+    """Slots per row of the sparse forward state under BatchTopK: the most the kernels hold (128: screen, re-score,
+    repair, prefix decode), or d_sae when the dictionary is narrower.  SAEV_B200_BATCHTOPK_CAP lowers it (cheaper re-score when rows are known to be
     balanced; the tests use it to provoke truncation)."""
     import os
 
-    cap = min(128 if n_prefixes <= 1 else 64, d_sae)
+    cap = min(128, d_sae)
     env = os.environ.get("SAEV_B200_BATCHTOPK_CAP", "")
     if env:
         cap = max(1, min(cap, int(env)))

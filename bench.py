@@ -473,10 +473,9 @@ def main():
     if K == 0 and world > 1:
         args.dp_mode = "plain"  # the dense (ReLU) path exchanges the whole gradient bucket with one all-reduce
     if args.dp_mode == "auto":
-        # measured on B200 (profiles/README.md): at 2 ranks the chunked all-reduce hidden behind the weight-gradient
-        # kernel wins (5.47 ms); from 4 ranks on the row-sharded optimizer whose fp32 all-gathers run beside the next
-        # step's screen wins (N=4: 5.40 vs 5.91 ms plain; N=8: 5.28 vs 5.92 ms)
-        args.dp_mode = "chunked" if world <= 2 else "sharded-overlap"
+        # measured on B200 (profiles/README.md, round 2): the row-sharded optimizer whose fp32 all-gathers run beside the
+        # next step's screen wins at every rank count (N=2: 5.04 vs 5.26 ms chunked all-reduce; N=8: 4.7-4.9 vs 5.2-5.9 ms)
+        args.dp_mode = "sharded-overlap"
     gather_group = None
     if world > 1 and args.dp_mode in ("sharded-overlap", "sharded-chunked"):
         gopts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)

@@ -125,7 +125,7 @@ int saev_b200_forward(saev_b200_handle* h, int phase, const float* x, int32_t B,
                       float* resid, float* losses, void* workspace, void* stream);
 
 /* BatchTopKActivation.forward (modeling.py:214-244) on the sparse forward state.  The handle is created with act_kind
- * TOPK and cfg.top_k = the per-row CAPACITY `cap` (<= 64; not BatchTopK.top_k).  Call it between
+ * TOPK and cfg.top_k = the per-row CAPACITY `cap` (<= 128; not BatchTopK.top_k).  Call it between
  * saev_b200_forward(phase A_SCREEN | A_RESCORE) -- which leaves each row's `cap` largest exact pre-activations in
  * topk_idx / topk_val -- and saev_b200_forward(phase A_DECODE | B):
  *   training != 0 (:226-242): keeps the min(k_per_sample * B, all) largest entries of the WHOLE batch (`torch.topk` on the
@@ -231,7 +231,7 @@ int saev_b200_densify(saev_b200_handle* h, const int32_t* topk_idx, const float*
  * objectives.py:125,158-201): n strictly increasing column counts, the last one == d_sae.  n == 1 (or NULL) selects
  * the plain single-prefix objective.  x_hat_i = b_dec + sum of the active columns below cut i; the MSE is the mean
  * over batch x prefixes x d_model; AuxK and `resid` refer to the last (full) prefix.  TopK: one sparse decode that emits
- * every prefix (top_k <= 64).  ReLU: the decoder, dh and W_dec-gradient contractions run once per prefix block. */
+ * every prefix (top_k <= 128).  ReLU: the decoder, dh and W_dec-gradient contractions run once per prefix block. */
 int saev_b200_set_prefixes(saev_b200_handle* h, const int32_t* host_prefixes, int32_t n);
 /* x_hats[B, n_prefixes, d_model] of the last forward (modeling.py:406); n_prefixes == 1 reduces to saev_b200_x_hat. */
 int saev_b200_x_hats(saev_b200_handle* h, const float* resid, const float* x, int32_t B, float* x_hats_out,

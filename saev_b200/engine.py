@@ -38,7 +38,7 @@ class EngineConfig:
     aux_cols_cap: int = 0
     max_prefixes: int = 1  # Matryoshka.n_prefixes the workspace is sized for
     # BatchTopK (modeling.py:183-244): batch_k = BatchTopK.top_k (average actives per sample; 0 = plain TopK).  `top_k`
-    # is then the per-row CAPACITY of the sparse forward state (<= 64): the batch-wide selection is exact as long as no
+    # is then the per-row CAPACITY of the sparse forward state (<= 128): the batch-wide selection is exact as long as no
     # row owns more than `top_k` of the batch's winners (Engine.batch_topk_stats() counts the rows that might).
     batch_k: int = 0
     batch_momentum: float = 0.1

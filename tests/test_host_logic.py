@@ -488,8 +488,9 @@ def test_checkpoint_header_is_the_references_schema_5(act, tmp_path):
     theirs = M.SparseAutoencoder(M.SparseAutoencoderConfig(d_model=16, d_sae=64, activation=mk(M), reinit_blend=0.0))
     # 1. same header payload for the activation as the reference's serializer produces
     assert bnn._serialize_dataclass(ours.cfg.activation) == M._serialize_dataclass(theirs.cfg.activation)
-    if act == "batchtopk":
-        return  # (no CUDA path and no `activation.threshold` buffer here: only the header payload is mirrored)
+    if act == "batchtopk":  # the EMA threshold is a registered buffer on both sides (modeling.py:213)
+        assert list(ours.state_dict()) == list(theirs.state_dict())
+        assert "activation.threshold" in ours.state_dict()
     # 2. ours -> reference loader
     bnn.dump(tmp_path / "ours.pt", ours)
     back = M.load(tmp_path / "ours.pt")
@@ -518,3 +519,30 @@ def test_fused_adam_registers_only_full_sae_groups():
     assert a._fused_adam is not None and a._fused_adam() is opt_a
     optim.FusedAdam([{"params": [b.b_enc, b.b_dec], "lr": 0.0}])  # the Muon split: biases only
     assert b._fused_adam is None
+
+
+def test_batchtopk_maps_to_a_row_capacity_on_the_sparse_path(monkeypatch):
+    """BatchTopK(top_k = k) runs as TopK lists of `capacity` slots per row + a batch-wide selection of k * B entries
+    (engine_config): capacity = min(128, d_sae), SAEV_B200_BATCHTOPK_CAP lowers it, and an average that does not fit
+    raises up front."""
+    from saev_b200 import nn as bnn
+
+    monkeypatch.delenv("SAEV_B200_BATCHTOPK_CAP", raising=False)
+    cfg = bnn.SparseAutoencoderConfig(d_model=64, d_sae=4096, activation=bnn.BatchTopK(top_k=32, momentum=0.2))
+    ec = bnn.engine_config(cfg, bnn.Matryoshka(n_prefixes=10), 512)
+    assert (ec.activation, ec.top_k, ec.batch_k, ec.batch_momentum, ec.max_prefixes) == ("topk", 128, 32, 0.2, 10)
+    assert bnn.batch_topk_capacity(8, 96) == 96  # a dictionary narrower than the capacity: every column is a slot
+    monkeypatch.setenv("SAEV_B200_BATCHTOPK_CAP", "16")
+    assert bnn.batch_topk_capacity(8, 4096) == 16
+    with pytest.raises(NotImplementedError, match="cannot even hold the average"):
+        bnn.batch_topk_capacity(32, 4096)
+    monkeypatch.delenv("SAEV_B200_BATCHTOPK_CAP")
+    with pytest.raises(NotImplementedError):
+        bnn.batch_topk_capacity(200, 4096)
+    # plain TopK and Relu are untouched by the BatchTopK fields
+    ec = bnn.engine_config(bnn.SparseAutoencoderConfig(d_model=64, d_sae=4096, activation=bnn.TopK(top_k=32)),
+                           bnn.Matryoshka(n_prefixes=1), 512)
+    assert (ec.top_k, ec.batch_k) == (32, 0)
+    ec = bnn.engine_config(bnn.SparseAutoencoderConfig(d_model=64, d_sae=4096, activation=bnn.Relu()),
+                           bnn.Matryoshka(n_prefixes=4), 512)
+    assert (ec.activation, ec.batch_k, ec.max_prefixes) == ("relu", 0, 4)

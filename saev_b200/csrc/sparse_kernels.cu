@@ -445,6 +445,45 @@ __device__ __forceinline__ void rescore_radix_pass(const int2* cbuf, const int* 
   __syncwarp();
 }
 
+// Same pass over a row's candidates staged in shared memory (value bits in .x): the common case, see the kernel.
+__device__ __forceinline__ void rescore_radix_pass_staged(const int2* st, int n, int shift, unsigned int& prefix, int& need,
+                                                          int* hist, int lane) {
+  int4* h4 = reinterpret_cast<int4*>(hist);
+  h4[2 * lane] = make_int4(0, 0, 0, 0);
+  h4[2 * lane + 1] = make_int4(0, 0, 0, 0);
+  __syncwarp();
+  for (int e = lane; e < n; e += 32) {
+    const unsigned int key = fkey(__int_as_float(st[e].x));
+    if (shift == 24 || (key >> (shift + 8)) == prefix) atomicAdd(hist + ((key >> shift) & 255u), 1);
+  }
+  __syncwarp();
+  const int4 a = h4[2 * lane], b = h4[2 * lane + 1];
+  const int c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const int mine = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  int suf = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_down_sync(FULL, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  const unsigned int bal = __ballot_sync(FULL, suf >= need);
+  const int L = 31 - __clz(bal);
+  int cum = suf - mine, j = 7;
+#pragma unroll
+  for (int jj = 7; jj > 0; --jj) {
+    if (j == jj && cum + c[jj] < need) {
+      cum += c[jj];
+      j = jj - 1;
+    }
+  }
+  const int bin = __shfl_sync(FULL, 8 * lane + j, L);
+  need = __shfl_sync(FULL, need - cum, L);
+  prefix = (prefix << 8) | static_cast<unsigned int>(bin);
+  __syncwarp();
+}
+
+constexpr int RESCORE_STAGE = 256;  // candidates of one row staged in shared memory (8 per lane, loaded in one go)
+
 // WPB rows (warps) per block; the rows of a block hold their SM slot until the slowest one (longest candidate list)
 // is done, so small blocks keep more warps busy (same 24 resident warps per SM either way)
 template <int VPL, int WPB, int CAP = RESCORE_CAP>
@@ -453,6 +492,7 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   __shared__ float sv_s[WPB][CAP];
   __shared__ int si_s[WPB][CAP];
   __shared__ float se_s[WPB][CAP];
+  __shared__ int2 stage_s[WPB][RESCORE_STAGE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * WPB + warp;
   if (b >= a.B) return;
@@ -471,6 +511,43 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
     overflow |= c < 0;
     n_total += abs(c);
   }
+  // The common case (a row leaves ~100 list entries): pull all of them into shared memory with ONE round of loads
+  // (8 independent loads per lane) -- the radix passes and the collection below then never wait on global memory.
+  // Entries keep their (list, position) order, so the survivors come out exactly as in the list-walking path.
+  int2* stage = stage_s[warp];
+  const bool staged = n_total <= RESCORE_STAGE && a.nsplit <= 32;
+  if (staged) {
+    const int my_cnt = (lane < a.nsplit) ? abs(cnts[lane]) : 0;
+    int my_off = my_cnt;  // inclusive scan over the lists -> exclusive offset of list `lane`
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, my_off, o);
+      if (lane >= o) my_off += t;
+    }
+    my_off -= my_cnt;
+    int2 t[RESCORE_STAGE / 32];
+#pragma unroll
+    for (int i = 0; i < RESCORE_STAGE / 32; ++i) {
+      const int g = lane + 32 * i;
+      t[i] = make_int2(0, -1);
+      // list holding global entry g: the last list whose offset is <= g (lists are few: a ballot per step)
+      int l = 0, off_l = 0;
+      for (int q = 0; q < a.nsplit; ++q) {
+        const int oq = __shfl_sync(FULL, my_off, q), cq = __shfl_sync(FULL, my_cnt, q);
+        if (g >= oq && g < oq + cq) {
+          l = q;
+          off_l = oq;
+        }
+      }
+      if (g < n_total) t[i] = __ldg(cbuf + static_cast<long long>(l) * a.cand_stride + (g - off_l));
+    }
+#pragma unroll
+    for (int i = 0; i < RESCORE_STAGE / 32; ++i) {
+      const int g = lane + 32 * i;
+      if (g < n_total) stage[g] = t[i];
+    }
+    __syncwarp();
+  }
   const float wn = sqrtf(a.scalars[SC_WNORM_SQ_MAX]);
   const ScreenBound sbd = screen_bound(a.D, a.scalars[SC_RHO], a.scalars[SC_BIAS_ABS_MAX]);
   const float Pb = screen_P(sbd, a.row_norm[b], a.row_dx[b]);  // E_bj = c_j Pb + Qb
@@ -486,12 +563,16 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   if (n_total > a.K) {
     unsigned int prefix = 0u;
     int need = a.K;
-    rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 24, prefix, need, hist, lane);
-    rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 16, prefix, need, hist, lane);
+    auto pass = [&](int shift) {
+      if (staged) rescore_radix_pass_staged(stage, n_total, shift, prefix, need, hist, lane);
+      else rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, shift, prefix, need, hist, lane);
+    };
+    pass(24);
+    pass(16);
     Lk = funkey(prefix << 16);
     if (Lg > Lk && Lg <= funkey((prefix << 16) | 0xffffu)) {  // too close to call at 16 bits: the exact k-th largest
-      rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 8, prefix, need, hist, lane);
-      rescore_radix_pass(cbuf, cnts, a.nsplit, a.cand_stride, 0, prefix, need, hist, lane);
+      pass(8);
+      pass(0);
       Lk = funkey(prefix);
     }
   }
@@ -513,16 +594,14 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   }
   // ---- collect the survivors (sv = the column's error bound E_bj, used again below) ----
   int n = 0;
-  for (int l = 0; l < a.nsplit; ++l) {
-    const int c = abs(cnts[l]);
-    const int2* lb = cbuf + static_cast<long long>(l) * a.cand_stride;
-    for (int e0 = 0; e0 < c; e0 += 32) {
+  if (staged) {
+    for (int e0 = 0; e0 < n_total; e0 += 32) {
       const int e = e0 + lane;
       int2 t = make_int2(0, -1);
       float E = 0.f;
       bool take = false;
-      if (e < c) {
-        t = __ldg(lb + e);
+      if (e < n_total) {
+        t = stage[e];
         E = fmaf(__ldg(a.col_norm + t.y), Pb, Qb);
         take = fmaf(2.f, E, __int_as_float(t.x)) >= Lk;
       }
@@ -533,6 +612,29 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
         si[o] = t.y;
       }
       n += __popc(bal);
+    }
+  } else {
+    for (int l = 0; l < a.nsplit; ++l) {
+      const int c = abs(cnts[l]);
+      const int2* lb = cbuf + static_cast<long long>(l) * a.cand_stride;
+      for (int e0 = 0; e0 < c; e0 += 32) {
+        const int e = e0 + lane;
+        int2 t = make_int2(0, -1);
+        float E = 0.f;
+        bool take = false;
+        if (e < c) {
+          t = __ldg(lb + e);
+          E = fmaf(__ldg(a.col_norm + t.y), Pb, Qb);
+          take = fmaf(2.f, E, __int_as_float(t.x)) >= Lk;
+        }
+        const unsigned bal = __ballot_sync(FULL, take);
+        const int o = n + __popc(bal & ((1u << lane) - 1u));
+        if (take && o < CAP) {
+          sv[o] = __int_as_float(t.x) + E;  // the screen value h~_j
+          si[o] = t.y;
+        }
+        n += __popc(bal);
+      }
     }
   }
   if (n > CAP) {  // more near-ties than one warp re-scores: the exact path takes the row
@@ -556,10 +658,12 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
   if (!overflow) {
     for (int c0 = 0; c0 < n; c0 += RB) {
       int jj[RB];
+      float bj[RB];
       float4 w[RB][VPL];
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
         jj[u] = si[min(c0 + u, n - 1)];
+        bj[u] = __ldg(a.b_enc + jj[u]);  // issued with the row loads (a dependent load after the dot costs a round trip)
         const float* r = a.W_enc_t + static_cast<long long>(jj[u]) * a.D;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
@@ -573,7 +677,7 @@ __global__ void __launch_bounds__(32 * WPB, 24 / WPB) rescore_topk_kernel(Rescor
       if (lane == 0) {
 #pragma unroll
         for (int u = 0; u < RB; ++u)
-          if (c0 + u < n) se[c0 + u] = acc[u] + __ldg(a.b_enc + jj[u]);
+          if (c0 + u < n) se[c0 + u] = acc[u] + bj[u];
       }
     }
     __syncwarp();

@@ -1,9 +1,13 @@
-// Dense contractions on tcgen05 tensor cores:  out = A . B^T (+ bias), bf16 operand pieces, fp32 accumulate in TMEM.
+// Dense contractions on tcgen05 tensor cores, single-CTA version:  out = A . B^T (+ bias), bf16 operand pieces, fp32
+// accumulate in TMEM.
 //
-// One kernel, five fused epilogues (template parameter EPI, see below) for the dense (ReLU) path of the SAE step
-// (saev src/saev/nn/modeling.py:150-156, 343-409 and their autograd), the AuxK contractions over the dead latents
-// (modeling.py:75-103), the dictionary-coherence screen of the log block (train.py:411-417) and the test hook
-// saev_b200_gemm_nt.  The TopK screen of the encoder contraction is the CTA-pair kernel in encode_gemm2.cu.
+// One kernel, five fused epilogues (template parameter EPI, see dense_epilogue.cuh).  launch_encode_gemm is the entry
+// for every dense contraction of the library; it forwards epilogues 1-4 with static problem sizes -- the dense (ReLU)
+// path of the SAE step (saev src/saev/nn/modeling.py:150-156, 343-409 and their autograd) and the saev_b200_gemm_nt test
+// hook -- to the CTA-pair kernel of dense_gemm2.cu (SAEV_B200_DENSE_PAIR=0 keeps them here) and runs the rest itself: the
+// AuxK contractions over the dead latents, whose sizes live on the device (modeling.py:75-103), K splits, and the
+// dictionary-coherence screen of the log block (train.py:411-417).  The TopK screen of the encoder contraction is the
+// CTA-pair kernel in encode_gemm2.cu.
 //
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (TMEM lane quadrant = warp_idx % 4).  Pipelines: STAGES-deep smem ring (TMA <-> MMA),
@@ -12,7 +16,7 @@
 // Operands are K-major bf16 with 128-byte swizzle.  `nterms == 3` runs the error-compensated split product
 // (x_hi.W_hi + x_hi.W_lo + x_lo.W_hi, ~2^-17 relative) by walking three (A,B) tensor-map pairs along K; `nterms == 6`
 // adds a third piece per operand (hi + lo + lo2 = 24 bits: fp32-class accuracy, terms hi.hi, hi.lo, lo.hi, hi.lo2,
-// lo2.hi, lo.lo).
+// lo2.hi, lo.lo).  Optional (m, n, k) windows (Matryoshka prefix blocks): see EpiExtra.
 #include <stdio.h>
 
 #include "common.cuh"
